@@ -1,0 +1,224 @@
+/* rrl.h -- C ABI of librrl.so: the B200 (sm_100a) hot path of Recovery RL.
+ *
+ * The reference (abalakrishna123/recovery-rl) has NO native/FFI interface: its seam is the
+ * Python class API consumed by recovery_rl/experiment.py.  Each entry point below therefore
+ * cites the reference Python symbol (file:line) whose arithmetic it replaces; the Python
+ * binding a maintainer would add is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 on error; rrl_last_error() gives the message
+ *     (thread-local).  Launch-only: functions ENQUEUE work on `stream` (a cudaStream_t passed
+ *     as void*) and never synchronise, so every call is CUDA-graph capturable, except the
+ *     explicitly named *_host helpers which touch host memory.
+ *   - all arrays are caller-owned DEVICE pointers (e.g. torch tensors' data_ptr()); nothing
+ *     is allocated here.  No global state; the device is whatever is current (cudaSetDevice).
+ *   - layouts: env state fp64 SoA [2][n] (plane 0 = x, plane 1 = y); actions fp32 [n][2];
+ *     replay = ring of 32-byte records {s.x,s.y,a.x,a.y,r,s2.x,s2.y,mask} fp32 (one DRAM
+ *     sector per transition) + one flag byte per slot for the constraint buffer.
+ *   - data-dependent control flow (len(memory) > batch_size, the Q_risk online gate, the
+ *     effective batch size) lives in device counters so that a captured graph replays exactly.
+ */
+#ifndef RRL_H_
+#define RRL_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RRL_VERSION 1
+
+const char* rrl_last_error(void);
+int rrl_version(void);
+
+/* ------------------------------------------------------------------ environments ------- */
+enum { RRL_ENV_NAV1 = 0, RRL_ENV_NAV2 = 1, RRL_ENV_MAZE = 2 };
+
+/* device counter block (int64), shared by env/replay/agent kernels */
+enum {
+    RRL_C_TOTAL_NUMSTEPS = 0,  /* experiment.py:429  total_numsteps                       */
+    RRL_C_EPISODES       = 1,  /* finished episodes                                        */
+    RRL_C_NUM_VIOLS      = 2,  /* experiment.py:455-456                                    */
+    RRL_C_NUM_SUCCESSES  = 3,  /* experiment.py:461                                        */
+    RRL_C_VIOL_RECOVERY  = 4,  /* experiment.py:457-458                                    */
+    RRL_C_VIOL_NO_RECOV  = 5,  /* experiment.py:459-460                                    */
+    RRL_C_OFFLINE_VIOLS  = 6,  /* experiment.py:279  num_constraint_violations (host-set) */
+    RRL_C_VEC_STEP       = 7,  /* vector-step index (Philox counter)                       */
+    RRL_C_SAC_UPDATES    = 8,  /* experiment.py:416  updates                               */
+    RRL_C_QRISK_UPDATES  = 9,  /* qrisk.py:163       self.updates                          */
+    RRL_C_TASK_POS       = 10, /* replay_memory.py:25 position  (task buffer)              */
+    RRL_C_TASK_LEN       = 11, /* len(memory)                                              */
+    RRL_C_CONS_POS       = 12, /* replay_memory.py:52 position  (constraint buffer)        */
+    RRL_C_CONS_LEN       = 13,
+    RRL_C_SAC_ROWS       = 14, /* effective batch rows of the current SAC update (0 = skip)*/
+    RRL_C_QRISK_ROWS     = 15, /* effective batch rows of the current Q_risk update        */
+    RRL_C_ADAM_T0        = 16, /* Adam step counts: critic, policy, qrisk, recovery        */
+    RRL_C_EXT_VIOLS      = 20, /* violations seen on OTHER ranks (multi-GPU gate), host/NCCL-set */
+    RRL_C_RETURN_SUM_BITS= 21, /* double bit pattern: sum of finished-episode returns      */
+    RRL_C_ERROR          = 22, /* sticky device-side error code (1: sample larger than population) */
+    RRL_NUM_COUNTERS     = 32
+};
+
+typedef struct {
+    int32_t kind;              /* RRL_ENV_*                                                */
+    int32_t horizon;           /* _max_episode_steps: navigation1.py:34,65  maze.py:16,121 */
+    int64_t n_envs;
+    double  reward_penalty;    /* experiment.py:431-432 constraint_reward_penalty          */
+    uint64_t seed;             /* Philox key (production RNG mode)                         */
+    int32_t stream_id;         /* rank: second half of the Philox key                      */
+    int32_t maze_substeps;     /* maze.py:147 (500)                                        */
+} rrl_env_config_t;
+
+/* env.reset (navigation1.py:91-97, navigation2.py:90-96, maze.py:184-213 mode 'h').
+ * mask: NULL = reset all, else reset env i iff mask[i] != 0.
+ * draws: NULL = Philox, else host-supplied fp64 [2][n]: N(0,1) for navigation, U[0,1) for maze. */
+int rrl_env_reset(const rrl_env_config_t* cfg, const uint8_t* mask, const double* draws,
+                  double* state, int32_t* ep_steps, double* ep_return, const int64_t* counters,
+                  void* stream);
+
+/* One vector step of N env copies (navigation1.py:71-110, navigation2.py:70-110,
+ * maze.py:139-168, obstacle.py:13-15,44-45) fused with what experiment.py:420-461 does with
+ * the result: reward penalty, mask = !done BEFORE the horizon check, push of
+ * (s, a_task, r, s', mask) into the task ring and (s, a_real, constraint, s', mask) into the
+ * constraint ring (replay_memory.py:21-25,47-52), episode statistics, auto-reset.
+ *   action_task/action_real : fp32 [n][2] proposed / executed action (experiment.py:438-445)
+ *   recovery                : u8 [n] recovery_used flag (may be NULL)
+ *   noise      : NULL = Philox; else fp64 [2][n] N(0,1) dynamics noise (navigation only)
+ *   reset_draws: NULL = Philox; else fp64 [2][n] draws used by envs that finish this step
+ *   task_ring / cons_ring / cons_flags : may be NULL (no push)
+ *   out_*      : per-env results of THIS step (pre-reset), any may be NULL
+ */
+int rrl_env_step(const rrl_env_config_t* cfg, const float* action_task, const float* action_real,
+                 const uint8_t* recovery, const double* noise, const double* reset_draws,
+                 double* state, int32_t* ep_steps, double* ep_return,
+                 float* task_ring, int64_t task_capacity,
+                 float* cons_ring, uint8_t* cons_flags, int64_t cons_capacity,
+                 int64_t* counters,
+                 double* out_next_state, double* out_reward, uint8_t* out_done,
+                 uint8_t* out_constraint, uint8_t* out_success, void* stream);
+
+/* After rrl_env_step: position/len of both rings += n, total_numsteps += n, vec_step += 1
+ * (replay_memory.py:22-25; experiment.py:429).  push_task / push_cons select the rings. */
+int rrl_counters_advance(int64_t* counters, int64_t n, int64_t task_capacity, int64_t cons_capacity,
+                         int push_task, int push_cons, void* stream);
+
+/* ------------------------------------------------------------------ replay ------------- */
+/* CPython `random.seed(int)` (init_by_array) -> 624-word MT19937 state + index (word 624).
+ * Host helper: fills a HOST buffer of 625 uint32 (replay_memory.py:16,41). */
+int rrl_mt19937_seed_host(const uint32_t* key_limbs, int n_limbs, uint32_t* state625_host);
+
+/* ReplayMemory.push / ConstraintReplayMemory.push for n caller-supplied transitions (offline
+ * demos: experiment.py:277-282).  rec: fp32 [n][8]; flags written when cons_flags != NULL. */
+int rrl_replay_push(float* ring, uint8_t* cons_flags, int64_t capacity, const float* rec, int64_t n,
+                    int64_t* counters, int is_constraint_buffer, void* stream);
+
+/* Per-chunk positive/negative counts of the constraint flags (np.argwhere over pos_idx,
+ * replay_memory.py:58-66).  chunk_counts: int32 [2][n_chunks]. */
+int rrl_replay_flag_count(const uint8_t* cons_flags, int64_t capacity, int32_t chunk,
+                          int32_t* chunk_counts, void* stream);
+
+typedef struct {
+    int64_t capacity;
+    int32_t batch_size;        /* requested B                                             */
+    int32_t is_constraint;     /* 0: ReplayMemory.sample, 1: ConstraintReplayMemory.sample */
+    double  pos_fraction;      /* < 0: None (qrisk.py:77)                                  */
+    int32_t gate_mode;         /* 0: always sample min(B, len) rows (pre-training, qrisk.py:100-104);
+                                  1: SAC gate   len > B                 (experiment.py:397);
+                                  2: Q_risk gate len > B && (viols)/B > pos_fraction (experiment.py:407-410) */
+    int32_t chunk;             /* flag chunk size used by rrl_replay_flag_count            */
+    double  gate_pos_fraction; /* exp_cfg.pos_fraction as given on the command line        */
+} rrl_sample_config_t;
+
+/* random.sample-compatible index draw + gather (replay_memory.py:27-30, 54-72; CPython
+ * random.py sample/_randbelow).  Single-CTA kernel; writes the effective row count into
+ * counters[rows_counter] (0 = gate closed: the MT stream is NOT advanced).
+ *   mt_state : uint32 [625] device (shared by both buffers: one global `random` stream)
+ *   out_idx  : int64 [B] slot indices;  out_* : fp32 batch arrays [B][2],[B][2],[B],[B][2],[B] */
+int rrl_replay_sample(const rrl_sample_config_t* cfg, const float* ring, const uint8_t* cons_flags,
+                      const int32_t* chunk_counts, uint32_t* mt_state, int64_t* counters,
+                      int rows_counter, int64_t* out_idx, float* out_s, float* out_a, float* out_r,
+                      float* out_s2, float* out_m, void* stream);
+
+/* ------------------------------------------------------------------ agent -------------- */
+enum { RRL_NET_CRITIC = 0, RRL_NET_CRITIC_TARGET = 1, RRL_NET_POLICY = 2, RRL_NET_QRISK = 3,
+       RRL_NET_QRISK_TARGET = 4, RRL_NET_RECOVERY = 5, RRL_NUM_NETS = 6 };
+
+typedef struct {
+    int32_t hidden;            /* 256 (arg_utils.py:89-92); kernels are specialised for 256 */
+    int32_t max_batch;         /* rows of update scratch                                   */
+    float gamma, alpha, tau;               /* arg_utils.py:55-68                            */
+    float gamma_safe, tau_safe, eps_safe;  /* arg_utils.py:113-127                          */
+    float lr, beta1, beta2, adam_eps;      /* torch.optim.Adam defaults, sac.py:84          */
+    float action_scale[2], action_bias[2]; /* model.py:312-315                              */
+    int32_t target_update_interval;        /* arg_utils.py:39-43                            */
+    int32_t mf_recovery;                   /* qrisk.py:150                                  */
+    float grad_scale;                      /* 1/world_size applied inside Adam              */
+    int32_t use_tensor_cores;              /* act kernel: 0 = fp32 FFMA, 1 = tcgen05 bf16x3 */
+} rrl_agent_config_t;
+
+/* Arena layout (fp32 elements).  Tensors of every net follow torch's parameters() order of the
+ * reference module (model.py:49-76,172-199,295-343,489-530), each padded to 4 floats. */
+int64_t rrl_agent_arena_floats(const rrl_agent_config_t* cfg);
+int rrl_agent_num_tensors(int net);
+int rrl_agent_tensor_info(const rrl_agent_config_t* cfg, int net, int tensor, int64_t* offset,
+                          int64_t* rows, int64_t* cols);
+/* flat gradient block [critic | policy | qrisk | recovery] for the NCCL all-reduce */
+int rrl_agent_grad_range(const rrl_agent_config_t* cfg, int net, int64_t* offset, int64_t* count);
+/* named scratch regions inside the arena (batch arrays, per-row outputs, losses) */
+int rrl_agent_scratch_info(const rrl_agent_config_t* cfg, const char* name, int64_t* offset,
+                           int64_t* count);
+
+/* Composite action selection for N envs (experiment.py:546-577; sac.py:133-168;
+ * qrisk.py:184-213; model.py:317-338, 512-525):
+ *   a_task = tanh(mu + sigma*eps_task)*scale + bias   (or mean action when eval != 0;
+ *            or U(low,high) while total_numsteps < start_steps, experiment.py:559-560)
+ *   recovery = max(Q1,Q2)_risk(s, a_task) > eps_safe   (only if use_recovery)
+ *   a_real = recovery ? mu_rec + sigma_rec*eps_rec : a_task
+ * state fp64 [2][n]; eps_* fp32 [n][2] or NULL (Philox); rand_u fp32 [n][2] U[0,1) or NULL. */
+int rrl_agent_act(const rrl_agent_config_t* cfg, float* arena, int64_t n, const double* state,
+                  const float* eps_task, const float* eps_rec, const float* rand_u,
+                  int use_recovery, int eval, int64_t start_steps, uint64_t seed, int32_t stream_id,
+                  const int64_t* counters, float* action_task, float* action_real,
+                  uint8_t* recovery, float* qrisk_out, void* stream);
+
+/* SAC.update_parameters (sac.py:170-277, ordering "Variant B" of SURVEY.md §8c) split so that
+ * the host can all-reduce the gradient block between the two halves:
+ *   rrl_sac_backward : forward passes, losses, grads of critic and policy into the grad block
+ *   rrl_sac_apply    : Adam on critic+policy (torch.optim.Adam), Polyak on critic_target
+ * batch arrays live in the arena scratch ("sac_s","sac_a","sac_r","sac_s2","sac_m");
+ * eps_next/eps_cur fp32 [B][2] or NULL (Philox).  losses: fp32 [8] device:
+ *   {qf1_loss, qf2_loss, policy_loss, alpha_loss(0), alpha}. */
+int rrl_sac_backward(const rrl_agent_config_t* cfg, float* arena, const float* eps_next,
+                     const float* eps_cur, uint64_t seed, int32_t stream_id, int64_t* counters,
+                     float* losses, void* stream);
+int rrl_sac_apply(const rrl_agent_config_t* cfg, float* arena, int64_t* counters, void* stream);
+
+/* QRiskWrapper.update_parameters (qrisk.py:86-182): critic half, then the MF recovery policy
+ * on the POST-step critic (qrisk.py:150-158), then Polyak (qrisk.py:160-163).
+ * losses: fp32 [8]: {q1_loss, q2_loss, recovery_policy_loss}. */
+int rrl_qrisk_backward(const rrl_agent_config_t* cfg, float* arena, const float* eps_next,
+                       uint64_t seed, int32_t stream_id, int64_t* counters, float* losses,
+                       void* stream);
+int rrl_qrisk_apply(const rrl_agent_config_t* cfg, float* arena, int64_t* counters, void* stream);
+int rrl_recovery_backward(const rrl_agent_config_t* cfg, float* arena, const float* eps_rec,
+                          uint64_t seed, int32_t stream_id, int64_t* counters, float* losses,
+                          void* stream);
+int rrl_recovery_apply(const rrl_agent_config_t* cfg, float* arena, int64_t* counters, void* stream);
+
+/* Twin forward used by QRiskWrapper.get_value / __call__ and the critic (qrisk.py:184-196,
+ * 303-307; model.py:65-76,188-199): q1,q2 fp32 [n]; s,a fp32 [n][2]. */
+int rrl_twin_q_forward(const rrl_agent_config_t* cfg, const float* arena, int net, int64_t n,
+                       const float* s, const float* a, float* q1, float* q2, void* stream);
+/* GaussianPolicy.sample / StochasticPolicy.sample on fp32 states (model.py:325-338,522-525). */
+int rrl_policy_sample(const rrl_agent_config_t* cfg, const float* arena, int net, int64_t n,
+                      const float* s, const float* eps, float* action, float* log_prob,
+                      float* mean_action, void* stream);
+
+/* utils.soft_update / hard_update (utils.py:46-54) on whole nets. */
+int rrl_hard_update(const rrl_agent_config_t* cfg, float* arena, int dst_net, int src_net, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RRL_H_ */

@@ -1,0 +1,343 @@
+// env.cu -- vectorised point environments (Navigation1 / Navigation2 / Maze) fused with the
+// replay push, episode statistics and auto-reset.  One thread per env copy; fp64 SoA state.
+//
+// Compiled with -fmad=false AND written with explicit __dadd_rn/__dmul_rn/__fma_rn so that the
+// arithmetic is bit-identical to the numpy expressions of the reference:
+//   navigation  s' = (s + (double)clip(a)) + (0.05 * n)     env/navigation1.py:99-104
+//               cost = -sqrt(fma(s.y, s.y, s.x*s.x))        env/navigation1.py:106-110 (OpenBLAS ddot)
+//   maze        restated physics, see oracle/envs.py (MuJoCo is a closed third-party binary)
+#include "common.cuh"
+
+namespace {
+
+struct EnvParams {
+    rrl_env_config_t cfg;
+    // maze constants (host-computed in double, identical expressions in oracle/envs.py)
+    double c_a, c_b, h, gear;
+    double wx0[4], wx1[4], wy0[4], wy1[4];  // 1A, 1B, 2A, 2B rectangles
+};
+
+// ---- obstacle.py:13-15, 44-45 : closed-interval rectangles ---------------------------------
+__device__ __forceinline__ bool in_rect(double x, double y, double x0, double x1, double y0, double y1) {
+    return (x0 <= x) && (x <= x1) && (y0 <= y) && (y <= y1);
+}
+__device__ __forceinline__ bool nav_obstacle(int kind, double x, double y) {
+    if (kind == RRL_ENV_NAV1) {  // navigation1.py:41-42
+        return in_rect(x, y, -100.0, 150.0, 5.0, 10.0) || in_rect(x, y, -100.0, -80.0, -10.0, 10.0) ||
+               in_rect(x, y, -100.0, 150.0, -10.0, -5.0);
+    }
+    return in_rect(x, y, -30.0, -20.0, -7.5, 7.5);  // navigation2.py:41
+}
+
+// ---- maze geometry: simple_maze.xml:16-25 + maze.py:201-206 ----------------------------------
+// disc radius r against the 4 outer planes (closed) and 4 axis-aligned rectangles (strict).
+#define MAZE_R 0.025
+__device__ __forceinline__ bool maze_rect_touch(double x, double y, double x0, double x1, double y0, double y1) {
+    double dx = fmax(fmax(__dsub_rn(x0, x), 0.0), __dsub_rn(x, x1));
+    double dy = fmax(fmax(__dsub_rn(y0, y), 0.0), __dsub_rn(y, y1));
+    double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+    return d2 < (MAZE_R * MAZE_R);
+}
+__device__ __forceinline__ bool maze_touch(const EnvParams& P, double x, double y) {
+    bool planes = (__dsub_rn(x, MAZE_R) <= -0.3) || (__dadd_rn(x, MAZE_R) >= 0.3) ||
+                  (__dsub_rn(y, MAZE_R) <= -0.3) || (__dadd_rn(y, MAZE_R) >= 0.3);
+    bool walls = false;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) walls = walls || maze_rect_touch(x, y, P.wx0[w], P.wx1[w], P.wy0[w], P.wy1[w]);
+    return planes || walls;
+}
+// conservative: can a disc starting at (x,y) and moving at most `reach` per axis touch anything?
+__device__ __forceinline__ bool maze_may_touch(double x, double y, double reach) {
+    const double R = MAZE_R + reach;
+    if (x - R <= -0.3 || x + R >= 0.3 || y - R <= -0.3 || y + R >= 0.3) return true;
+    bool near1 = (x >= -0.105 - R) && (x <= -0.095 + R);
+    bool near2 = (x >= 0.095 - R) && (x <= 0.105 + R);
+    return near1 || near2;
+}
+
+__device__ __forceinline__ void reset_state(const EnvParams& P, int64_t i, const double* draws, int64_t n,
+                                            uint64_t vec_step, uint32_t draw_id, double* x, double* y) {
+    double d0, d1;
+    if (draws) {
+        d0 = draws[i];
+        d1 = draws[n + i];
+    } else {
+        Philox4 p = rrl_philox(P.cfg.seed, (uint32_t)P.cfg.stream_id, (uint64_t)i, vec_step, draw_id);
+        if (P.cfg.kind == RRL_ENV_MAZE) {
+            d0 = rrl_u53(p.x, p.y);
+            d1 = rrl_u53(p.z, p.w);
+        } else {
+            rrl_normal2_f64(p, &d0, &d1);
+        }
+    }
+    if (P.cfg.kind == RRL_ENV_MAZE) {
+        // maze.py:195-197 mode 'h': np.random.uniform(lo, hi) = lo + (hi - lo) * u
+        *x = __dadd_rn(-0.22, __dmul_rn((-0.13) - (-0.22), d0));
+        *y = __dadd_rn(-0.22, __dmul_rn(0.22 - (-0.22), d1));
+    } else {
+        // navigation1.py:92  START_STATE + np.random.randn(2)
+        *x = __dadd_rn(-50.0, d0);
+        *y = __dadd_rn(0.0, d1);
+    }
+}
+
+__global__ void __launch_bounds__(256) env_reset_kernel(EnvParams P, const uint8_t* __restrict__ mask,
+                                                        const double* __restrict__ draws, double* __restrict__ state,
+                                                        int32_t* __restrict__ ep_steps, double* __restrict__ ep_return,
+                                                        const int64_t* __restrict__ counters) {
+    const int64_t n = P.cfg.n_envs;
+    const uint64_t vstep = counters ? (uint64_t)counters[RRL_C_VEC_STEP] : 0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        if (mask && !mask[i]) continue;
+        double x, y;
+        reset_state(P, i, draws, n, vstep, RRL_DRAW_INIT_RESET, &x, &y);
+        state[i] = x;
+        state[n + i] = y;
+        if (ep_steps) ep_steps[i] = 0;
+        if (ep_return) ep_return[i] = 0.0;
+    }
+}
+
+__device__ __forceinline__ void warp_count_add(bool pred, int64_t* addr) {
+    unsigned m = __ballot_sync(__activemask(), pred);
+    if (pred && (threadIdx.x & 31) == (__ffs(m) - 1)) atomicAdd((unsigned long long*)addr, (unsigned long long)__popc(m));
+}
+
+__global__ void __launch_bounds__(256)
+env_step_kernel(EnvParams P, const float* __restrict__ a_task, const float* __restrict__ a_real,
+                const uint8_t* __restrict__ recovery, const double* __restrict__ noise,
+                const double* __restrict__ reset_draws, double* __restrict__ state, int32_t* __restrict__ ep_steps,
+                double* __restrict__ ep_return, float* __restrict__ task_ring, int64_t task_cap,
+                float* __restrict__ cons_ring, uint8_t* __restrict__ cons_flags, int64_t cons_cap,
+                int64_t* __restrict__ counters, double* __restrict__ o_next, double* __restrict__ o_reward,
+                uint8_t* __restrict__ o_done, uint8_t* __restrict__ o_cons, uint8_t* __restrict__ o_succ) {
+    const int64_t n = P.cfg.n_envs;
+    const int kind = P.cfg.kind;
+    const uint64_t vstep = (uint64_t)counters[RRL_C_VEC_STEP];
+    const int64_t task_pos = counters[RRL_C_TASK_POS];
+    const int64_t cons_pos = counters[RRL_C_CONS_POS];
+    for (int64_t i0 = blockIdx.x * (int64_t)blockDim.x; i0 < n; i0 += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = i0 + threadIdx.x;
+        const bool live = i < n;
+        bool ep_end = false, viol = false, succ_end = false, rec_used = false;
+        double ep_ret_final = 0.0;
+        if (live) {
+            const double sx = state[i], sy = state[n + i];
+            const float2 at = reinterpret_cast<const float2*>(a_task)[i];
+            const float2 ar = reinterpret_cast<const float2*>(a_real)[i];
+            double nx, ny, reward;
+            bool constraint, done, success;
+            if (kind != RRL_ENV_MAZE) {
+                // E1: process_action  np.clip(a, -1, 1) stays fp32
+                const float cx = fminf(fmaxf(ar.x, -1.0f), 1.0f), cy = fminf(fmaxf(ar.y, -1.0f), 1.0f);
+                if (nav_obstacle(kind, sx, sy)) {  // E2: stuck inside an obstacle
+                    nx = sx;
+                    ny = sy;
+                } else {
+                    double e0, e1;
+                    if (noise) {
+                        e0 = noise[i];
+                        e1 = noise[n + i];
+                    } else {
+                        Philox4 p = rrl_philox(P.cfg.seed, (uint32_t)P.cfg.stream_id, (uint64_t)i, vstep, RRL_DRAW_ENV_NOISE);
+                        rrl_normal2_f64(p, &e0, &e1);
+                    }
+                    nx = __dadd_rn(__dadd_rn(sx, (double)cx), __dmul_rn(0.05, e0));
+                    ny = __dadd_rn(__dadd_rn(sy, (double)cy), __dmul_rn(0.05, e1));
+                }
+                // E3: -||GOAL - s|| on the PRE-step state; ddot accumulates with one FMA
+                const double cost = -sqrt(__fma_rn(sy, sy, __dmul_rn(sx, sx)));
+                constraint = nav_obstacle(kind, nx, ny);
+                success = cost > -4.0;
+                done = success || constraint;
+                reward = cost;
+            } else {
+                // E8: maze.  clip in fp32 to float32(0.1), then ctrl is fp64
+                const float cx = fminf(fmaxf(ar.x, -0.1f), 0.1f), cy = fminf(fmaxf(ar.y, -0.1f), 0.1f);
+                const double fbx = __dmul_rn(P.c_b, __dmul_rn(P.gear, (double)cx));
+                const double fby = __dmul_rn(P.c_b, __dmul_rn(P.gear, (double)cy));
+                double x = sx, y = sy, vx = 0.0, vy = 0.0;
+                bool contact = false;
+                const int nsub = P.cfg.maze_substeps;
+                if (!maze_may_touch(x, y, 0.03)) {
+                    // free flight: contact tests cannot fire (|displacement| <= 0.0247 per axis per step)
+                    for (int k = 0; k < nsub; ++k) {
+                        vx = __dadd_rn(__dmul_rn(P.c_a, vx), fbx);
+                        vy = __dadd_rn(__dmul_rn(P.c_a, vy), fby);
+                        x = __dadd_rn(x, __dmul_rn(P.h, vx));
+                        y = __dadd_rn(y, __dmul_rn(P.h, vy));
+                    }
+                } else {
+                    for (int k = 0; k < nsub; ++k) {
+                        if (maze_touch(P, x, y)) {  // collision phase precedes integration; contact freezes the disc
+                            contact = true;
+                            break;
+                        }
+                        vx = __dadd_rn(__dmul_rn(P.c_a, vx), fbx);
+                        vy = __dadd_rn(__dmul_rn(P.c_a, vy), fby);
+                        x = __dadd_rn(x, __dmul_rn(P.h, vx));
+                        y = __dadd_rn(y, __dmul_rn(P.h, vy));
+                    }
+                }
+                nx = x;
+                ny = y;
+                constraint = contact;
+                // E10: sqrt(mean((goal - qpos)^2)), goal = (0.25, 0), unfused
+                const double d0 = __dsub_rn(0.25, nx), d1 = __dsub_rn(0.0, ny);
+                const double dist = sqrt(__dmul_rn(__dadd_rn(__dmul_rn(d0, d0), __dmul_rn(d1, d1)), 0.5));
+                reward = -dist;
+                done = (ep_steps[i] + 1 >= P.cfg.horizon) || constraint || (dist < 0.03);
+                success = reward > -0.03;
+            }
+            const int steps = ep_steps[i] + 1;
+            // experiment.py:431-435: penalty, mask BEFORE the horizon truncation
+            const double r_pen = constraint ? __dsub_rn(reward, P.cfg.reward_penalty) : reward;
+            const float mask = done ? 0.0f : 1.0f;
+            const bool done_h = done || (steps == P.cfg.horizon);
+            const double ret = __dadd_rn(ep_return[i], reward);
+
+            if (o_next) {
+                o_next[i] = nx;
+                o_next[n + i] = ny;
+            }
+            if (o_reward) o_reward[i] = reward;
+            if (o_done) o_done[i] = done_h;
+            if (o_cons) o_cons[i] = constraint;
+            if (o_succ) o_succ[i] = success;
+
+            const float fsx = (float)sx, fsy = (float)sy, fnx = (float)nx, fny = (float)ny;
+            if (task_ring) {
+                float4* rec = reinterpret_cast<float4*>(task_ring + ((task_pos + i) % task_cap) * 8);
+                rec[0] = make_float4(fsx, fsy, at.x, at.y);
+                rec[1] = make_float4((float)r_pen, fnx, fny, mask);
+            }
+            if (cons_ring) {
+                const int64_t slot = (cons_pos + i) % cons_cap;
+                float4* rec = reinterpret_cast<float4*>(cons_ring + slot * 8);
+                rec[0] = make_float4(fsx, fsy, ar.x, ar.y);
+                rec[1] = make_float4(constraint ? 1.0f : 0.0f, fnx, fny, mask);
+                cons_flags[slot] = constraint ? 1 : 2;  // bit0: pos_idx != 0, bit1: (1 - pos_idx) != 0
+            }
+            if (done_h) {
+                ep_end = true;
+                viol = constraint;
+                succ_end = success;
+                rec_used = recovery ? (recovery[i] != 0) : false;
+                ep_ret_final = ret;
+                double rx, ry;
+                reset_state(P, i, reset_draws, n, vstep, RRL_DRAW_ENV_RESET, &rx, &ry);
+                state[i] = rx;
+                state[n + i] = ry;
+                ep_steps[i] = 0;
+                ep_return[i] = 0.0;
+            } else {
+                state[i] = nx;
+                state[n + i] = ny;
+                ep_steps[i] = steps;
+                ep_return[i] = ret;
+            }
+        }
+        // experiment.py:455-461 episode statistics from the LAST step's info
+        warp_count_add(ep_end, counters + RRL_C_EPISODES);
+        warp_count_add(ep_end && viol, counters + RRL_C_NUM_VIOLS);
+        warp_count_add(ep_end && succ_end, counters + RRL_C_NUM_SUCCESSES);
+        warp_count_add(ep_end && viol && rec_used, counters + RRL_C_VIOL_RECOVERY);
+        warp_count_add(ep_end && viol && !rec_used, counters + RRL_C_VIOL_NO_RECOV);
+        if (ep_end) atomicAdd(reinterpret_cast<double*>(counters + RRL_C_RETURN_SUM_BITS), ep_ret_final);
+    }
+}
+
+__global__ void counters_advance_kernel(int64_t* counters, int64_t n, int64_t task_cap, int64_t cons_cap,
+                                        int push_task, int push_cons) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        counters[RRL_C_TOTAL_NUMSTEPS] += n;
+        counters[RRL_C_VEC_STEP] += 1;
+        if (push_task) {
+            counters[RRL_C_TASK_POS] = (counters[RRL_C_TASK_POS] + n) % task_cap;
+            int64_t l = counters[RRL_C_TASK_LEN] + n;
+            counters[RRL_C_TASK_LEN] = l < task_cap ? l : task_cap;
+        }
+        if (push_cons) {
+            counters[RRL_C_CONS_POS] = (counters[RRL_C_CONS_POS] + n) % cons_cap;
+            int64_t l = counters[RRL_C_CONS_LEN] + n;
+            counters[RRL_C_CONS_LEN] = l < cons_cap ? l : cons_cap;
+        }
+    }
+}
+
+EnvParams make_params(const rrl_env_config_t* cfg) {
+    EnvParams P;
+    P.cfg = *cfg;
+    // simple_maze.xml: cylinder r = 0.025, half-height 0.025 (:28), default density 1000,
+    // slide joints damping 0.01 (:29-30), motor gear 0.05 (:8), timestep 0.002 (MuJoCo default)
+    const double mass = 1000.0 * 3.141592653589793 * 0.025 * 0.025 * 0.05;
+    const double h = 0.002, d = 0.01;
+    P.h = h;
+    P.gear = 0.05;
+    P.c_a = mass / (mass + h * d);
+    P.c_b = h / (mass + h * d);
+    // wall boxes: half-sizes (.02,.2,.005) with the thin axis along world x at x = -/+0.1
+    // (simple_maze.xml:22-25); y centres after reset(): maze.py:199-206
+    const double w1 = -0.08, w2 = 0.08;
+    const double cy[4] = {0.5 + w1, -0.25 + w1, 0.4 + w2, -0.25 + w2};
+    const double cx[4] = {-0.1, -0.1, 0.1, 0.1};
+    for (int w = 0; w < 4; ++w) {
+        P.wx0[w] = cx[w] - 0.005;
+        P.wx1[w] = cx[w] + 0.005;
+        P.wy0[w] = cy[w] - 0.2;
+        P.wy1[w] = cy[w] + 0.2;
+    }
+    return P;
+}
+
+int grid_for(int64_t n) {
+    int64_t blocks = (n + 255) / 256;
+    int64_t cap = (int64_t)rrl_num_sms() * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+}  // namespace
+
+extern "C" int rrl_env_reset(const rrl_env_config_t* cfg, const uint8_t* mask, const double* draws, double* state,
+                             int32_t* ep_steps, double* ep_return, const int64_t* counters, void* stream) {
+    RRL_CHECK_ARG(cfg && state, "null argument");
+    RRL_CHECK_ARG(cfg->kind >= RRL_ENV_NAV1 && cfg->kind <= RRL_ENV_MAZE, "unknown env kind");
+    RRL_CHECK_ARG(cfg->n_envs > 0, "n_envs must be positive");
+    EnvParams P = make_params(cfg);
+    env_reset_kernel<<<grid_for(cfg->n_envs), 256, 0, (cudaStream_t)stream>>>(P, mask, draws, state, ep_steps,
+                                                                              ep_return, counters);
+    RRL_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int rrl_env_step(const rrl_env_config_t* cfg, const float* action_task, const float* action_real,
+                            const uint8_t* recovery, const double* noise, const double* reset_draws, double* state,
+                            int32_t* ep_steps, double* ep_return, float* task_ring, int64_t task_capacity,
+                            float* cons_ring, uint8_t* cons_flags, int64_t cons_capacity, int64_t* counters,
+                            double* out_next_state, double* out_reward, uint8_t* out_done, uint8_t* out_constraint,
+                            uint8_t* out_success, void* stream) {
+    RRL_CHECK_ARG(cfg && action_task && action_real && state && ep_steps && ep_return && counters, "null argument");
+    RRL_CHECK_ARG(cfg->kind >= RRL_ENV_NAV1 && cfg->kind <= RRL_ENV_MAZE, "unknown env kind");
+    RRL_CHECK_ARG(cfg->n_envs > 0, "n_envs must be positive");
+    RRL_CHECK_ARG(!task_ring || task_capacity >= cfg->n_envs, "task ring smaller than one vector step");
+    RRL_CHECK_ARG(!cons_ring || (cons_flags && cons_capacity >= cfg->n_envs), "constraint ring too small / flags missing");
+    EnvParams P = make_params(cfg);
+    env_step_kernel<<<grid_for(cfg->n_envs), 256, 0, (cudaStream_t)stream>>>(
+        P, action_task, action_real, recovery, noise, reset_draws, state, ep_steps, ep_return, task_ring,
+        task_capacity > 0 ? task_capacity : 1, cons_ring, cons_flags, cons_capacity > 0 ? cons_capacity : 1, counters,
+        out_next_state, out_reward, out_done, out_constraint, out_success);
+    RRL_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int rrl_counters_advance(int64_t* counters, int64_t n, int64_t task_capacity, int64_t cons_capacity,
+                                    int push_task, int push_cons, void* stream) {
+    RRL_CHECK_ARG(counters, "null counters");
+    counters_advance_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(counters, n, task_capacity > 0 ? task_capacity : 1,
+                                                               cons_capacity > 0 ? cons_capacity : 1, push_task,
+                                                               push_cons);
+    RRL_CHECK_LAUNCH();
+    return 0;
+}

