@@ -169,6 +169,11 @@ int rrl_agent_grad_range(const rrl_agent_config_t* cfg, int net, int64_t* offset
 int rrl_agent_scratch_info(const rrl_agent_config_t* cfg, const char* name, int64_t* offset,
                            int64_t* count);
 
+/* Rebuild the derived weight images (k-major copies of the ten 256x256 hidden matrices that the GEMM
+ * kernels stream) after the host wrote parameters into the arena (e.g. the xavier init of
+ * model.py:23-26 or a checkpoint load).  The update kernels keep them fresh themselves. */
+int rrl_agent_refresh(const rrl_agent_config_t* cfg, float* arena, void* stream);
+
 /* Composite action selection for N envs (experiment.py:546-577; sac.py:133-168;
  * qrisk.py:184-213; model.py:317-338, 512-525):
  *   a_task = tanh(mu + sigma*eps_task)*scale + bias   (or mean action when eval != 0;

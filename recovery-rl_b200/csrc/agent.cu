@@ -1,0 +1,1642 @@
+// agent.cu -- SAC + safety-critic (Q_risk) + recovery-policy networks of Recovery RL on one flat arena.
+//
+// Replaces the torch modules / autograd / Adam calls of recovery_rl/model.py:49-76,172-199,295-343,
+// 489-530, recovery_rl/sac.py:133-277, recovery_rl/qrisk.py:86-213, recovery_rl/utils.py:46-54 and the
+// composite action selection of recovery_rl/experiment.py:546-577.
+//
+// All four MLPs are 2x256-hidden: the first layer (K = 2 or 4) and the heads (N = 1..4) are SIMT
+// prologue/epilogue of the one 256x256 contraction, which is a shared-memory tiled fp32 GEMM here
+// (agent_tc.cu holds the tcgen05 version of the same contraction for the large-N acting kernel).
+#include "agent_layout.cuh"
+
+using namespace rrl;
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int KC = 16;  // k-chunk of the streamed operand
+
+enum Head { HEAD_Q = 0, HEAD_QRISK = 1, HEAD_GAUSS = 2, HEAD_STOCH = 3 };
+
+#define LOG_SIG_MAX 2.0f
+#define LOG_SIG_MIN (-20.0f)
+#define MIN_LOG_STD (-13.815510557964274f) /* np.log(1e-6), model.py:499 */
+#define HALF_LOG_2PI 0.9189385332046727f   /* math.log(math.sqrt(2*math.pi)) */
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// ---------------------------------------------------------------------------------------------
+// weights of one single-head MLP (pointers into the arena)
+// ---------------------------------------------------------------------------------------------
+struct HeadW {
+    const float *W1, *b1, *W2, *W2T, *b2, *W3a, *b3a, *W3b, *b3b, *log_std;
+    int n_in, na, nb;  // inputs (2|4); rows of W3a / W3b
+};
+struct HeadG {  // gradient pointers (same shapes); NULL = not needed
+    float *W1, *b1, *W2, *b2, *W3a, *b3a, *W3b, *b3b, *log_std;
+};
+
+HeadW head_w(const Layout& L, const float* arena, int net, int head) {
+    HeadW w;
+    memset(&w, 0, sizeof(w));
+    const int64_t* t = L.t_off[net];
+    if (net == RRL_NET_POLICY) {
+        w.W1 = arena + t[0]; w.b1 = arena + t[1]; w.W2 = arena + t[2]; w.b2 = arena + t[3];
+        w.W3a = arena + t[4]; w.b3a = arena + t[5]; w.W3b = arena + t[6]; w.b3b = arena + t[7];
+        w.n_in = 2; w.na = 2; w.nb = 2;
+    } else if (net == RRL_NET_RECOVERY) {
+        w.log_std = arena + t[0];
+        w.W1 = arena + t[1]; w.b1 = arena + t[2]; w.W2 = arena + t[3]; w.b2 = arena + t[4];
+        w.W3a = arena + t[5]; w.b3a = arena + t[6];
+        w.n_in = 2; w.na = 2; w.nb = 0;
+    } else {
+        const int b = ((net == RRL_NET_QRISK || net == RRL_NET_QRISK_TARGET) ? 2 : 0) + 6 * head;
+        w.W1 = arena + t[b]; w.b1 = arena + t[b + 1]; w.W2 = arena + t[b + 2]; w.b2 = arena + t[b + 3];
+        w.W3a = arena + t[b + 4]; w.b3a = arena + t[b + 5];
+        w.n_in = 4; w.na = 1; w.nb = 0;
+    }
+    w.W2T = arena + L.img_off[image_index(net, head)];
+    return w;
+}
+HeadG head_g(const Layout& L, float* arena, int net, int head) {
+    HeadW w = head_w(L, arena, net, head);
+    const int64_t d = L.grad_off;  // trainable params start at offset 0 of the arena
+    HeadG g;
+    g.W1 = const_cast<float*>(w.W1) + d; g.b1 = const_cast<float*>(w.b1) + d;
+    g.W2 = const_cast<float*>(w.W2) + d; g.b2 = const_cast<float*>(w.b2) + d;
+    g.W3a = const_cast<float*>(w.W3a) + d; g.b3a = const_cast<float*>(w.b3a) + d;
+    g.W3b = w.W3b ? const_cast<float*>(w.W3b) + d : nullptr;
+    g.b3b = w.b3b ? const_cast<float*>(w.b3b) + d : nullptr;
+    g.log_std = w.log_std ? const_cast<float*>(w.log_std) + d : nullptr;
+    return g;
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward tile: BM rows through one head.  Result: S.raw[m][0..n_out) = W3 h2 + b3.
+// ---------------------------------------------------------------------------------------------
+template <int BM>
+struct FwdSmem {
+    float As[H][BM];      // h1 tile, k-major (operand A)
+    float Bs[2][KC][H];   // streamed W2T chunks (operand B)
+    float W1s[H][4];
+    float b1s[H], b2s[H];
+    float w3s[4][H];
+    float b3s[4];
+    float xin[4][BM];     // s0, s1, a0, a1
+    float raw[BM][4];
+    float aux[BM][4];     // kernel-specific per-row stash
+    int flag;
+};
+
+template <int BM>
+__device__ __forceinline__ void load_b_chunk(FwdSmem<BM>& S, const float* __restrict__ W2T, int c, int buf) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int idx = threadIdx.x + kThreads * j;  // 1024 float4 per chunk
+        const int row = idx >> 6, c4 = idx & 63;
+        cp_async16(&S.Bs[buf][row][c4 * 4], W2T + (size_t)(c * KC + row) * H + c4 * 4);
+    }
+    cp_async_commit();
+}
+
+template <int BM>
+__device__ void mlp_tile_forward(FwdSmem<BM>& S, const HeadW& w, float* __restrict__ h1_out, float* __restrict__ h2_out,
+                                 int64_t row0, int64_t rows) {
+    constexpr int RPW = BM / 8;  // rows per warp
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    load_b_chunk(S, w.W2T, 0, 0);
+    {  // stage the small tensors (t == hidden unit)
+        const int n_in = w.n_in;
+        float4 w1 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (n_in == 4) {
+            w1 = *reinterpret_cast<const float4*>(w.W1 + t * 4);
+        } else {
+            const float2 v = *reinterpret_cast<const float2*>(w.W1 + t * 2);
+            w1.x = v.x; w1.y = v.y;
+        }
+        *reinterpret_cast<float4*>(S.W1s[t]) = w1;
+        S.b1s[t] = w.b1[t];
+        S.b2s[t] = w.b2[t];
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+            float v = 0.f;
+            if (o < w.na) v = w.W3a[o * H + t];
+            else if (o < w.na + w.nb) v = w.W3b[(o - w.na) * H + t];
+            S.w3s[o][t] = v;
+        }
+        if (t < 4) {
+            float v = 0.f;
+            if (t < w.na) v = w.b3a[t];
+            else if (t < w.na + w.nb) v = w.b3b[t - w.na];
+            S.b3s[t] = v;
+        }
+    }
+    __syncthreads();  // small tensors + xin (written by the caller) visible
+    {  // layer 1: h1 = relu(W1 x + b1)   (model.py:68,191,318,513)
+        const int m = t % BM, kb = t / BM;
+        constexpr int KSTEP = kThreads / BM;
+        const float x0 = S.xin[0][m], x1 = S.xin[1][m], x2 = S.xin[2][m], x3 = S.xin[3][m];
+        const bool store = h1_out != nullptr && (row0 + m) < rows;
+        const bool four = w.n_in == 4;
+#pragma unroll 4
+        for (int k = kb; k < H; k += KSTEP) {
+            const float4 wv = *reinterpret_cast<const float4*>(S.W1s[k]);
+            float h = fmaf(wv.x, x0, S.b1s[k]);
+            h = fmaf(wv.y, x1, h);
+            if (four) {
+                h = fmaf(wv.z, x2, h);
+                h = fmaf(wv.w, x3, h);
+            }
+            h = fmaxf(h, 0.f);
+            S.As[k][m] = h;
+            if (store) h1_out[(row0 + m) * H + k] = h;
+        }
+    }
+    float acc[RPW][8];
+#pragma unroll
+    for (int r = 0; r < RPW; ++r)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[r][j] = 0.f;
+
+    for (int c = 0; c < H / KC; ++c) {
+        if (c + 1 < H / KC) {
+            load_b_chunk(S, w.W2T, c + 1, (c + 1) & 1);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+        const int buf = c & 1;
+#pragma unroll
+        for (int kk = 0; kk < KC; ++kk) {
+            float a[RPW];
+#pragma unroll
+            for (int r4 = 0; r4 < RPW / 4; ++r4) {
+                const float4 av = *reinterpret_cast<const float4*>(&S.As[c * KC + kk][warp * RPW + r4 * 4]);
+                a[r4 * 4 + 0] = av.x; a[r4 * 4 + 1] = av.y; a[r4 * 4 + 2] = av.z; a[r4 * 4 + 3] = av.w;
+            }
+            const float4 b0 = *reinterpret_cast<const float4*>(&S.Bs[buf][kk][lane * 4]);
+            const float4 b1 = *reinterpret_cast<const float4*>(&S.Bs[buf][kk][128 + lane * 4]);
+#pragma unroll
+            for (int r = 0; r < RPW; ++r) {
+                acc[r][0] = fmaf(a[r], b0.x, acc[r][0]);
+                acc[r][1] = fmaf(a[r], b0.y, acc[r][1]);
+                acc[r][2] = fmaf(a[r], b0.z, acc[r][2]);
+                acc[r][3] = fmaf(a[r], b0.w, acc[r][3]);
+                acc[r][4] = fmaf(a[r], b1.x, acc[r][4]);
+                acc[r][5] = fmaf(a[r], b1.y, acc[r][5]);
+                acc[r][6] = fmaf(a[r], b1.z, acc[r][6]);
+                acc[r][7] = fmaf(a[r], b1.w, acc[r][7]);
+            }
+        }
+        __syncthreads();
+    }
+    // epilogue: h2 = relu(acc + b2); heads
+    const int n_out = w.na + w.nb;
+    const float4 bb0 = *reinterpret_cast<const float4*>(&S.b2s[lane * 4]);
+    const float4 bb1 = *reinterpret_cast<const float4*>(&S.b2s[128 + lane * 4]);
+    float myraw[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int r = 0; r < RPW; ++r) {
+        float h[8];
+        h[0] = fmaxf(acc[r][0] + bb0.x, 0.f); h[1] = fmaxf(acc[r][1] + bb0.y, 0.f);
+        h[2] = fmaxf(acc[r][2] + bb0.z, 0.f); h[3] = fmaxf(acc[r][3] + bb0.w, 0.f);
+        h[4] = fmaxf(acc[r][4] + bb1.x, 0.f); h[5] = fmaxf(acc[r][5] + bb1.y, 0.f);
+        h[6] = fmaxf(acc[r][6] + bb1.z, 0.f); h[7] = fmaxf(acc[r][7] + bb1.w, 0.f);
+        const int64_t row = row0 + warp * RPW + r;
+        if (h2_out != nullptr && row < rows) {
+            *reinterpret_cast<float4*>(h2_out + row * H + lane * 4) = make_float4(h[0], h[1], h[2], h[3]);
+            *reinterpret_cast<float4*>(h2_out + row * H + 128 + lane * 4) = make_float4(h[4], h[5], h[6], h[7]);
+        }
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+            if (o < n_out) {
+                const float4 w0 = *reinterpret_cast<const float4*>(&S.w3s[o][lane * 4]);
+                const float4 w1 = *reinterpret_cast<const float4*>(&S.w3s[o][128 + lane * 4]);
+                float p = h[0] * w0.x;
+                p = fmaf(h[1], w0.y, p); p = fmaf(h[2], w0.z, p); p = fmaf(h[3], w0.w, p);
+                p = fmaf(h[4], w1.x, p); p = fmaf(h[5], w1.y, p); p = fmaf(h[6], w1.z, p); p = fmaf(h[7], w1.w, p);
+#pragma unroll
+                for (int s = 16; s > 0; s >>= 1) p += __shfl_xor_sync(0xffffffffu, p, s);
+                if (lane == r) myraw[o] = p + S.b3s[o];
+            }
+        }
+    }
+    if (lane < RPW) *reinterpret_cast<float4*>(S.raw[warp * RPW + lane]) = make_float4(myraw[0], myraw[1], myraw[2], myraw[3]);
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------
+// head post-processing
+// ---------------------------------------------------------------------------------------------
+struct ActionSpace {
+    float scale[2], bias[2];
+};
+
+// GaussianPolicy.sample (model.py:325-338)
+__device__ __forceinline__ void gauss_sample(const float raw[4], const float eps[2], const ActionSpace& sp, float a[2],
+                                             float* logp, float mean_a[2]) {
+    float lp = 0.f;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const float mean = raw[i];
+        const float ls = fminf(fmaxf(raw[2 + i], LOG_SIG_MIN), LOG_SIG_MAX);
+        const float sd = expf(ls);
+        const float x = fmaf(sd, eps[i], mean);  // rsample: loc + eps * scale
+        const float y = tanhf(x);
+        a[i] = fmaf(y, sp.scale[i], sp.bias[i]);
+        const float d = x - mean;
+        float l = -(d * d) / (2.0f * (sd * sd)) - logf(sd) - HALF_LOG_2PI;  // Normal.log_prob
+        l -= logf(sp.scale[i] * (1.0f - y * y) + 1e-6f);
+        lp += l;
+        mean_a[i] = fmaf(tanhf(mean), sp.scale[i], sp.bias[i]);
+    }
+    *logp = lp;
+}
+
+// StochasticPolicy.sample (model.py:512-525)
+__device__ __forceinline__ void stoch_sample(const float raw[2], const float* log_std, const float eps[2],
+                                             const ActionSpace& sp, float a[2], float mean_a[2], float* logp) {
+    float lp = 0.f;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const float mean = fmaf(tanhf(raw[i]), sp.scale[i], sp.bias[i]);
+        const float ls = fmaxf(log_std[i], MIN_LOG_STD);
+        const float sd = expf(ls);
+        a[i] = fmaf(sd, eps[i], mean);
+        mean_a[i] = mean;
+        const float d = a[i] - mean;
+        lp += -(d * d) / (2.0f * (sd * sd)) - logf(sd) - HALF_LOG_2PI;
+    }
+    *logp = lp;
+}
+
+__device__ __forceinline__ void philox_eps(uint64_t seed, uint32_t stream_id, uint64_t row, uint64_t step, uint32_t draw,
+                                           float e[2]) {
+    const Philox4 p = rrl_philox(seed, stream_id, row, step, draw);
+    rrl_normal2_f32(p.x, p.y, &e[0], &e[1]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// grouped forward kernel (training batches and the stand-alone forward entry points)
+// ---------------------------------------------------------------------------------------------
+struct FwdPass {
+    HeadW w;
+    int head;
+    const float* xs;  // [rows][2]
+    const float* xa;  // [rows][2] (n_in == 4)
+    float *h1, *h2;
+    const float* eps;  // [rows][2] or NULL (Philox)
+    uint32_t draw_id;
+    float *out_q, *out_a, *out_logp, *out_mean, *out_raw, *out_eps;
+};
+struct FwdArgs {
+    FwdPass p[6];
+    int n_pass;
+    const int64_t* rows_ptr;
+    int64_t rows_const;
+    ActionSpace sp;
+    uint64_t seed;
+    uint32_t stream_id;
+    const int64_t* counters;
+    int step_counter;  // which counter supplies the Philox step
+};
+
+template <int BM>
+__global__ void __launch_bounds__(kThreads, (BM == 64) ? 2 : 3) mlp_forward_kernel(const __grid_constant__ FwdArgs A) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    FwdSmem<BM>& S = *reinterpret_cast<FwdSmem<BM>*>(smem_raw);
+    const int64_t rows = A.rows_ptr ? *A.rows_ptr : A.rows_const;
+    const int64_t row0 = (int64_t)blockIdx.x * BM;
+    if (row0 >= rows) return;
+    const FwdPass& P = A.p[blockIdx.y];
+    const int t = threadIdx.x;
+    if (t < BM) {
+        const int64_t row = row0 + t;
+        float2 s = make_float2(0.f, 0.f), a = make_float2(0.f, 0.f);
+        if (row < rows) {
+            s = reinterpret_cast<const float2*>(P.xs)[row];
+            if (P.xa) a = reinterpret_cast<const float2*>(P.xa)[row];
+        }
+        S.xin[0][t] = s.x; S.xin[1][t] = s.y; S.xin[2][t] = a.x; S.xin[3][t] = a.y;
+    }
+    mlp_tile_forward<BM>(S, P.w, P.h1, P.h2, row0, rows);
+    if (t < BM) {
+        const int64_t row = row0 + t;
+        if (row < rows) {
+            const float4 rv = *reinterpret_cast<const float4*>(S.raw[t]);
+            const float raw[4] = {rv.x, rv.y, rv.z, rv.w};
+            if (P.out_raw) *reinterpret_cast<float4*>(P.out_raw + row * 4) = rv;
+            if (P.head == HEAD_Q) {
+                P.out_q[row] = raw[0];
+            } else if (P.head == HEAD_QRISK) {
+                P.out_q[row] = sigmoidf_(raw[0]);
+            } else {
+                float e[2];
+                if (P.eps) {
+                    const float2 ev = reinterpret_cast<const float2*>(P.eps)[row];
+                    e[0] = ev.x; e[1] = ev.y;
+                } else {
+                    philox_eps(A.seed, A.stream_id, (uint64_t)row, (uint64_t)A.counters[A.step_counter], P.draw_id, e);
+                }
+                float a[2], mean_a[2], lp;
+                if (P.head == HEAD_GAUSS) gauss_sample(raw, e, A.sp, a, &lp, mean_a);
+                else stoch_sample(raw, P.w.log_std, e, A.sp, a, mean_a, &lp);
+                if (P.out_a) reinterpret_cast<float2*>(P.out_a)[row] = make_float2(a[0], a[1]);
+                if (P.out_logp) P.out_logp[row] = lp;
+                if (P.out_mean) reinterpret_cast<float2*>(P.out_mean)[row] = make_float2(mean_a[0], mean_a[1]);
+                if (P.out_eps) reinterpret_cast<float2*>(P.out_eps)[row] = make_float2(e[0], e[1]);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// fused acting kernel (experiment.py:546-577): policy -> Q_risk threshold -> recovery policy -> select
+// ---------------------------------------------------------------------------------------------
+struct ActArgs {
+    HeadW pol, qr1, qr2, rec;
+    int64_t n;
+    const double* state;  // [2][n]
+    const float *eps_task, *eps_rec, *rand_u;
+    int use_recovery, eval;
+    int64_t start_steps;
+    uint64_t seed;
+    uint32_t stream_id;
+    const int64_t* counters;
+    float eps_safe;
+    ActionSpace sp;
+    float *action_task, *action_real, *qrisk_out;
+    uint8_t* recovery;
+};
+
+__global__ void __launch_bounds__(kThreads, 2) act_kernel(const __grid_constant__ ActArgs A) {
+    constexpr int BM = 64;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    FwdSmem<BM>& S = *reinterpret_cast<FwdSmem<BM>*>(smem_raw);
+    const int t = threadIdx.x;
+    const uint64_t vstep = A.counters ? (uint64_t)A.counters[RRL_C_VEC_STEP] : 0;
+    const bool random_phase = A.counters && !A.eval && (A.start_steps > A.counters[RRL_C_TOTAL_NUMSTEPS]);
+    for (int64_t row0 = (int64_t)blockIdx.x * BM; row0 < A.n; row0 += (int64_t)gridDim.x * BM) {
+        const int64_t row = row0 + t;
+        const bool live = t < BM && row < A.n;
+        if (t < BM) {
+            float sx = 0.f, sy = 0.f;
+            if (live) {  // torch.FloatTensor(state): fp64 -> fp32 (sac.py:137)
+                sx = (float)A.state[row];
+                sy = (float)A.state[A.n + row];
+            }
+            S.xin[0][t] = sx; S.xin[1][t] = sy; S.xin[2][t] = 0.f; S.xin[3][t] = 0.f;
+        }
+        float at[2] = {0.f, 0.f};
+        if (!random_phase) {
+            mlp_tile_forward<BM>(S, A.pol, nullptr, nullptr, row0, A.n);
+            if (live) {
+                const float4 rv = *reinterpret_cast<const float4*>(S.raw[t]);
+                const float raw[4] = {rv.x, rv.y, rv.z, rv.w};
+                float e[2], mean_a[2], lp;
+                if (A.eps_task) {
+                    const float2 ev = reinterpret_cast<const float2*>(A.eps_task)[row];
+                    e[0] = ev.x; e[1] = ev.y;
+                } else {
+                    philox_eps(A.seed, A.stream_id, (uint64_t)row, vstep, RRL_DRAW_ACT_TASK, e);
+                }
+                gauss_sample(raw, e, A.sp, at, &lp, mean_a);
+                if (A.eval) { at[0] = mean_a[0]; at[1] = mean_a[1]; }  // sac.py:166-167
+            }
+        } else if (live) {  // env.action_space.sample(): U(low, high)  (experiment.py:559-560)
+            float u[2];
+            if (A.rand_u) {
+                const float2 uv = reinterpret_cast<const float2*>(A.rand_u)[row];
+                u[0] = uv.x; u[1] = uv.y;
+            } else {
+                const Philox4 p = rrl_philox(A.seed, A.stream_id, (uint64_t)row, vstep, RRL_DRAW_ACT_RAND);
+                u[0] = rrl_u24(p.x); u[1] = rrl_u24(p.y);
+            }
+            at[0] = fmaf(2.0f * u[0] - 1.0f, A.sp.scale[0], A.sp.bias[0]);
+            at[1] = fmaf(2.0f * u[1] - 1.0f, A.sp.scale[1], A.sp.bias[1]);
+        }
+        bool rec = false;
+        float qmax = 0.f;
+        float ar[2] = {at[0], at[1]};
+        if (A.use_recovery) {
+            __syncthreads();
+            if (t < BM) { S.xin[2][t] = at[0]; S.xin[3][t] = at[1]; }
+            mlp_tile_forward<BM>(S, A.qr1, nullptr, nullptr, row0, A.n);
+            const float q1 = (t < BM) ? sigmoidf_(S.raw[t][0]) : 0.f;
+            __syncthreads();
+            mlp_tile_forward<BM>(S, A.qr2, nullptr, nullptr, row0, A.n);
+            if (live) {
+                const float q2 = sigmoidf_(S.raw[t][0]);
+                qmax = fmaxf(q1, q2);               // qrisk.py:196
+                rec = qmax > A.eps_safe;            // experiment.py:555
+            }
+            if (t == 0) S.flag = 0;
+            __syncthreads();
+            if (rec) S.flag = 1;
+            __syncthreads();
+            if (S.flag) {  // at least one env of this tile recovers (block-uniform branch)
+                mlp_tile_forward<BM>(S, A.rec, nullptr, nullptr, row0, A.n);
+                if (rec) {
+                    const float raw[2] = {S.raw[t][0], S.raw[t][1]};
+                    float e[2], mean_a[2], lp;
+                    if (A.eps_rec) {
+                        const float2 ev = reinterpret_cast<const float2*>(A.eps_rec)[row];
+                        e[0] = ev.x; e[1] = ev.y;
+                    } else {
+                        philox_eps(A.seed, A.stream_id, (uint64_t)row, vstep, RRL_DRAW_ACT_REC, e);
+                    }
+                    stoch_sample(raw, A.rec.log_std, e, A.sp, ar, mean_a, &lp);  // qrisk.py:207-213
+                }
+            }
+        }
+        if (live) {
+            reinterpret_cast<float2*>(A.action_task)[row] = make_float2(at[0], at[1]);
+            reinterpret_cast<float2*>(A.action_real)[row] = make_float2(ar[0], ar[1]);
+            if (A.recovery) A.recovery[row] = rec ? 1 : 0;
+            if (A.qrisk_out) A.qrisk_out[row] = qmax;
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward building blocks (training batches: rows <= max_batch)
+// ---------------------------------------------------------------------------------------------
+// (1) head backward: dh2 = (dout W3) * relu'(h2)  [+ transposed copy], dW3, db3, db2
+struct HeadBwdPass {
+    const float* dout;  // [rows][stride]
+    int stride, n_out, na;
+    const float *W3a, *W3b, *h2;
+    float *dh2, *dh2t;            // [rows][H], [H][R]
+    float *gW3a, *gW3b, *gb3a, *gb3b, *gb2;  // NULL when no weight grads are needed
+};
+struct HeadBwdArgs {
+    HeadBwdPass p[4];
+    const int64_t* rows_ptr;
+    int64_t R;
+};
+
+__global__ void __launch_bounds__(kThreads) head_backward_kernel(const __grid_constant__ HeadBwdArgs A) {
+    const int64_t rows = *A.rows_ptr;
+    if (rows <= 0) return;
+    const HeadBwdPass& P = A.p[blockIdx.y];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int j = blockIdx.x * 32 + tx;
+    __shared__ float red[5][8][32];
+    float w3[4];
+#pragma unroll
+    for (int o = 0; o < 4; ++o) w3[o] = o < P.na ? P.W3a[o * H + j] : (o < P.n_out ? P.W3b[(o - P.na) * H + j] : 0.f);
+    float gb2 = 0.f, gw[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int64_t r = ty; r < rows; r += 8) {
+        float d[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int o = 0; o < 4; ++o)
+            if (o < P.n_out) d[o] = P.dout[r * P.stride + o];
+        const float h = P.h2[r * H + j];
+        float g = d[0] * w3[0];
+        g = fmaf(d[1], w3[1], g); g = fmaf(d[2], w3[2], g); g = fmaf(d[3], w3[3], g);
+        g = h > 0.f ? g : 0.f;
+        P.dh2[r * H + j] = g;
+        P.dh2t[(int64_t)j * A.R + r] = g;
+        gb2 += g;
+#pragma unroll
+        for (int o = 0; o < 4; ++o) gw[o] = fmaf(d[o], h, gw[o]);
+    }
+    if (P.gb2 == nullptr) return;
+    red[0][ty][tx] = gb2;
+#pragma unroll
+    for (int o = 0; o < 4; ++o) red[1 + o][ty][tx] = gw[o];
+    __syncthreads();
+    if (ty == 0) {
+        float s[5];
+#pragma unroll
+        for (int q = 0; q < 5; ++q) {
+            float v = 0.f;
+#pragma unroll
+            for (int y = 0; y < 8; ++y) v += red[q][y][tx];
+            s[q] = v;
+        }
+        P.gb2[j] = s[0];
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+            if (o < P.na) P.gW3a[o * H + j] = s[1 + o];
+            else if (o < P.n_out) P.gW3b[(o - P.na) * H + j] = s[1 + o];
+        }
+    }
+    if (blockIdx.x == 0 && ty == 1) {  // db3[o] = sum_r dout[r][o]
+        for (int o = 0; o < P.n_out; ++o) {
+            float v = 0.f;
+            for (int64_t r = tx; r < rows; r += 32) v += P.dout[r * P.stride + o];
+#pragma unroll
+            for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+            if (tx == 0) {
+                if (o < P.na) P.gb3a[o] = v;
+                else P.gb3b[o - P.na] = v;
+            }
+        }
+    }
+}
+
+// (2) streamed GEMM: C[m][n] = sum_k A[k][m] * B[k][n], n = 0..255, m tile of 32, both operands k-major.
+//     DATA  : A = dh2t [H][R] (k = hidden, m = row), B = W2 [H][H], C = dh1 [row][H] masked by h1 > 0
+//     WEIGHT: A = dh2 [rows][H] (k = row, m = out unit), B = h1 [rows][H], C = gW2 [H][H]
+struct GemmPass {
+    const float *A, *B;
+    int lda;
+    int k_is_rows;      // K = rows (WEIGHT) else K = H
+    const float* mask;  // DATA: h1
+    float* C;
+};
+struct GemmArgs {
+    GemmPass p[8];
+    const int64_t* rows_ptr;
+};
+
+__global__ void __launch_bounds__(kThreads) gemm_stream_kernel(const __grid_constant__ GemmArgs G) {
+    constexpr int BM = 32;
+    const int64_t rows = *G.rows_ptr;
+    if (rows <= 0) return;
+    const GemmPass& P = G.p[blockIdx.y];
+    const int m0 = blockIdx.x * BM;
+    const int M = P.k_is_rows ? H : (int)rows;
+    if (m0 >= M) return;
+    const int K = P.k_is_rows ? (int)rows : H;
+    __shared__ __align__(16) float As[2][KC][BM];
+    __shared__ __align__(16) float Bs[2][KC][H];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    auto load = [&](int c, int buf) {
+        const int k0 = c * KC;
+        if (t < 128) {
+            const int kk = t >> 3, m4 = t & 7;
+            if (k0 + kk < K) cp_async16(&As[buf][kk][m4 * 4], P.A + (size_t)(k0 + kk) * P.lda + m0 + m4 * 4);
+            else *reinterpret_cast<float4*>(&As[buf][kk][m4 * 4]) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int idx = t + kThreads * j;
+            const int kk = idx >> 6, c4 = idx & 63;
+            if (k0 + kk < K) cp_async16(&Bs[buf][kk][c4 * 4], P.B + (size_t)(k0 + kk) * H + c4 * 4);
+            else *reinterpret_cast<float4*>(&Bs[buf][kk][c4 * 4]) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        cp_async_commit();
+    };
+    float acc[4][8];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[r][j] = 0.f;
+    const int nchunks = (K + KC - 1) / KC;
+    load(0, 0);
+    for (int c = 0; c < nchunks; ++c) {
+        if (c + 1 < nchunks) {
+            load(c + 1, (c + 1) & 1);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+        const int buf = c & 1;
+#pragma unroll
+        for (int kk = 0; kk < KC; ++kk) {
+            const float4 av = *reinterpret_cast<const float4*>(&As[buf][kk][warp * 4]);
+            const float a[4] = {av.x, av.y, av.z, av.w};
+            const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][kk][lane * 4]);
+            const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][kk][128 + lane * 4]);
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                acc[r][0] = fmaf(a[r], b0.x, acc[r][0]); acc[r][1] = fmaf(a[r], b0.y, acc[r][1]);
+                acc[r][2] = fmaf(a[r], b0.z, acc[r][2]); acc[r][3] = fmaf(a[r], b0.w, acc[r][3]);
+                acc[r][4] = fmaf(a[r], b1.x, acc[r][4]); acc[r][5] = fmaf(a[r], b1.y, acc[r][5]);
+                acc[r][6] = fmaf(a[r], b1.z, acc[r][6]); acc[r][7] = fmaf(a[r], b1.w, acc[r][7]);
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int m = m0 + warp * 4 + r;
+        if (m >= M) continue;
+        float4 o0 = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+        float4 o1 = make_float4(acc[r][4], acc[r][5], acc[r][6], acc[r][7]);
+        if (P.mask) {
+            const float4 k0 = *reinterpret_cast<const float4*>(P.mask + (size_t)m * H + lane * 4);
+            const float4 k1 = *reinterpret_cast<const float4*>(P.mask + (size_t)m * H + 128 + lane * 4);
+            o0.x = k0.x > 0.f ? o0.x : 0.f; o0.y = k0.y > 0.f ? o0.y : 0.f;
+            o0.z = k0.z > 0.f ? o0.z : 0.f; o0.w = k0.w > 0.f ? o0.w : 0.f;
+            o1.x = k1.x > 0.f ? o1.x : 0.f; o1.y = k1.y > 0.f ? o1.y : 0.f;
+            o1.z = k1.z > 0.f ? o1.z : 0.f; o1.w = k1.w > 0.f ? o1.w : 0.f;
+        }
+        *reinterpret_cast<float4*>(P.C + (size_t)m * H + lane * 4) = o0;
+        *reinterpret_cast<float4*>(P.C + (size_t)m * H + 128 + lane * 4) = o1;
+    }
+}
+
+// (3) layer-1 backward: gW1, gb1 (blockIdx.x == 0) and d(action input) (blockIdx.x == 1)
+struct L1BwdPass {
+    const float *dh1, *xs, *xa, *W1;
+    int n_in;
+    float *gW1, *gb1;  // NULL: skip
+    float* dxa;        // [rows][2] gradient w.r.t. the action input; NULL: skip
+};
+struct L1BwdArgs {
+    L1BwdPass p[4];
+    const int64_t* rows_ptr;
+};
+
+__global__ void __launch_bounds__(kThreads) layer1_backward_kernel(const __grid_constant__ L1BwdArgs A) {
+    const int64_t rows = *A.rows_ptr;
+    if (rows <= 0) return;
+    const L1BwdPass& P = A.p[blockIdx.y];
+    const int t = threadIdx.x;
+    if (blockIdx.x == 0) {
+        if (!P.gW1) return;
+        float g[4] = {0.f, 0.f, 0.f, 0.f}, gb = 0.f;
+        for (int64_t r = 0; r < rows; ++r) {
+            const float d = P.dh1[r * H + t];
+            const float2 s = reinterpret_cast<const float2*>(P.xs)[r];
+            g[0] = fmaf(d, s.x, g[0]);
+            g[1] = fmaf(d, s.y, g[1]);
+            if (P.n_in == 4) {
+                const float2 a = reinterpret_cast<const float2*>(P.xa)[r];
+                g[2] = fmaf(d, a.x, g[2]);
+                g[3] = fmaf(d, a.y, g[3]);
+            }
+            gb += d;
+        }
+        for (int i = 0; i < P.n_in; ++i) P.gW1[t * P.n_in + i] = g[i];
+        P.gb1[t] = gb;
+    } else {
+        if (!P.dxa) return;
+        const int lane = t & 31, warp = t >> 5;
+        float w2[8], w3[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            w2[q] = P.W1[(lane + 32 * q) * 4 + 2];
+            w3[q] = P.W1[(lane + 32 * q) * 4 + 3];
+        }
+        for (int64_t r = warp; r < rows; r += 8) {
+            float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const float d = P.dh1[r * H + lane + 32 * q];
+                a0 = fmaf(d, w2[q], a0);
+                a1 = fmaf(d, w3[q], a1);
+            }
+#pragma unroll
+            for (int s = 16; s > 0; s >>= 1) {
+                a0 += __shfl_xor_sync(0xffffffffu, a0, s);
+                a1 += __shfl_xor_sync(0xffffffffu, a1, s);
+            }
+            if (lane == 0) reinterpret_cast<float2*>(P.dxa)[r] = make_float2(a0, a1);
+        }
+    }
+}
+
+// deterministic block sum of one float per thread (256 threads); result valid on thread 0
+__device__ float block_sum(float v, float* red /*[8]*/) {
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float r = 0.f;
+    if (threadIdx.x == 0)
+        for (int w = 0; w < 8; ++w) r += red[w];
+    return r;
+}
+
+// (4) SAC losses (sac.py:192-231): TD target, critic MSE, policy loss, and the output gradients
+struct SacLossArgs {
+    const float *r, *m, *next_logp, *qt1, *qt2, *qf1, *qf2, *logp, *qp1, *qp2;
+    float *target, *dqf1, *dqf2, *dqp1, *dqp2, *minq, *losses;
+    float gamma, alpha;
+    const int64_t* rows_ptr;
+};
+__global__ void __launch_bounds__(kThreads) sac_loss_kernel(const __grid_constant__ SacLossArgs A) {
+    const int64_t rows = *A.rows_ptr;
+    if (rows <= 0) return;
+    __shared__ float red[8];
+    const float inv = 1.0f / (float)rows;
+    float l1 = 0.f, l2 = 0.f, lp = 0.f;
+    for (int64_t i = threadIdx.x; i < rows; i += kThreads) {
+        const float minq_next = fminf(A.qt1[i], A.qt2[i]) - A.alpha * A.next_logp[i];
+        const float y = A.r[i] + A.m[i] * A.gamma * minq_next;
+        A.target[i] = y;
+        const float e1 = A.qf1[i] - y, e2 = A.qf2[i] - y;
+        l1 = fmaf(e1, e1, l1);
+        l2 = fmaf(e2, e2, l2);
+        A.dqf1[i] = 2.0f * e1 * inv;
+        A.dqf2[i] = 2.0f * e2 * inv;
+        const float p1 = A.qp1[i], p2 = A.qp2[i];
+        const float mq = fminf(p1, p2);
+        A.minq[i] = mq;
+        lp += A.alpha * A.logp[i] - mq;
+        // d(-min)/dq: torch.min(a, b) routes the gradient to the smaller input (ties split evenly)
+        A.dqp1[i] = p1 < p2 ? -inv : (p1 == p2 ? -0.5f * inv : 0.f);
+        A.dqp2[i] = p2 < p1 ? -inv : (p1 == p2 ? -0.5f * inv : 0.f);
+    }
+    const float s1 = block_sum(l1, red);
+    const float s2 = block_sum(l2, red);
+    const float s3 = block_sum(lp, red);
+    if (threadIdx.x == 0) {
+        A.losses[0] = s1 * inv;
+        A.losses[1] = s2 * inv;
+        A.losses[2] = s3 * inv;
+        A.losses[3] = 0.f;      // alpha_loss (automatic_entropy_tuning False)
+        A.losses[4] = A.alpha;
+    }
+}
+
+// (5) GaussianPolicy.sample backward: d raw(mean, log_std) from dL/da (through the critic) and alpha*logp
+struct GaussBwdArgs {
+    const float *raw, *eps, *dxa1, *dxa2;
+    float* draw;
+    float alpha;
+    ActionSpace sp;
+    const int64_t* rows_ptr;
+};
+__global__ void __launch_bounds__(kThreads) gauss_backward_kernel(const __grid_constant__ GaussBwdArgs A) {
+    const int64_t rows = *A.rows_ptr;
+    const int64_t i = blockIdx.x * (int64_t)kThreads + threadIdx.x;
+    if (i >= rows) return;
+    const float inv = 1.0f / (float)rows;
+    const float4 rv = reinterpret_cast<const float4*>(A.raw)[i];
+    const float raw[4] = {rv.x, rv.y, rv.z, rv.w};
+    const float2 e = reinterpret_cast<const float2*>(A.eps)[i];
+    const float2 d1 = reinterpret_cast<const float2*>(A.dxa1)[i], d2 = reinterpret_cast<const float2*>(A.dxa2)[i];
+    const float da[2] = {d1.x + d2.x, d1.y + d2.y};
+    const float ev[2] = {e.x, e.y};
+    float out[4];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const float lsr = raw[2 + k];
+        const float ls = fminf(fmaxf(lsr, LOG_SIG_MIN), LOG_SIG_MAX);
+        const float sd = expf(ls);
+        const float x = fmaf(sd, ev[k], raw[k]);
+        const float y = tanhf(x);
+        const float om = 1.0f - y * y;
+        const float den = A.sp.scale[k] * om + 1e-6f;
+        // dL/dy = dL/da * scale + (alpha/B) * d(-log(scale*(1-y^2)+1e-6))/dy
+        const float dy = da[k] * A.sp.scale[k] + A.alpha * inv * (2.0f * A.sp.scale[k] * y) / den;
+        const float dx = dy * om;
+        out[k] = dx;                                               // d mean
+        const float dls = dx * sd * ev[k] - A.alpha * inv;         // through x and through -log(std)
+        out[2 + k] = (lsr >= LOG_SIG_MIN && lsr <= LOG_SIG_MAX) ? dls : 0.f;  // clamp backward
+    }
+    reinterpret_cast<float4*>(A.draw)[i] = make_float4(out[0], out[1], out[2], out[3]);
+}
+
+// (6) Q_risk losses (qrisk.py:118-148): target = c + m*gamma_safe*max(q1', q2'); MSE through the sigmoid
+struct QrLossArgs {
+    const float *c, *m, *qt1, *qt2, *q1, *q2;
+    float *target, *dq1, *dq2, *losses;
+    float gamma_safe;
+    const int64_t* rows_ptr;
+};
+__global__ void __launch_bounds__(kThreads) qrisk_loss_kernel(const __grid_constant__ QrLossArgs A) {
+    const int64_t rows = *A.rows_ptr;
+    if (rows <= 0) return;
+    __shared__ float red[8];
+    const float inv = 1.0f / (float)rows;
+    float l1 = 0.f, l2 = 0.f;
+    for (int64_t i = threadIdx.x; i < rows; i += kThreads) {
+        const float y = A.c[i] + A.m[i] * A.gamma_safe * fmaxf(A.qt1[i], A.qt2[i]);
+        A.target[i] = y;
+        const float q1 = A.q1[i], q2 = A.q2[i];
+        const float e1 = q1 - y, e2 = q2 - y;
+        l1 = fmaf(e1, e1, l1);
+        l2 = fmaf(e2, e2, l2);
+        A.dq1[i] = 2.0f * e1 * inv * q1 * (1.0f - q1);  // d/d(raw) through sigmoid
+        A.dq2[i] = 2.0f * e2 * inv * q2 * (1.0f - q2);
+    }
+    const float s1 = block_sum(l1, red);
+    const float s2 = block_sum(l2, red);
+    if (threadIdx.x == 0) {
+        A.losses[0] = s1 * inv;
+        A.losses[1] = s2 * inv;
+    }
+}
+
+// (7) recovery-policy loss (qrisk.py:150-155): mean max(Q1, Q2)(s, pi_rec(s))
+struct RecLossArgs {
+    const float *q1, *q2;
+    float *dq1, *dq2, *losses;
+    const int64_t* rows_ptr;
+};
+__global__ void __launch_bounds__(kThreads) recovery_loss_kernel(const __grid_constant__ RecLossArgs A) {
+    const int64_t rows = *A.rows_ptr;
+    if (rows <= 0) return;
+    __shared__ float red[8];
+    const float inv = 1.0f / (float)rows;
+    float l = 0.f;
+    for (int64_t i = threadIdx.x; i < rows; i += kThreads) {
+        const float q1 = A.q1[i], q2 = A.q2[i];
+        l += fmaxf(q1, q2);
+        const float g1 = q1 > q2 ? inv : (q1 == q2 ? 0.5f * inv : 0.f);
+        const float g2 = q2 > q1 ? inv : (q1 == q2 ? 0.5f * inv : 0.f);
+        A.dq1[i] = g1 * q1 * (1.0f - q1);
+        A.dq2[i] = g2 * q2 * (1.0f - q2);
+    }
+    const float s = block_sum(l, red);
+    if (threadIdx.x == 0) A.losses[2] = s * inv;
+}
+
+// (8) StochasticPolicy.sample backward (single CTA): d raw mean, d log_std
+struct StochBwdArgs {
+    const float *raw, *eps, *dxa1, *dxa2, *log_std;
+    float *draw, *g_log_std;
+    ActionSpace sp;
+    const int64_t* rows_ptr;
+};
+__global__ void __launch_bounds__(kThreads) stoch_backward_kernel(const __grid_constant__ StochBwdArgs A) {
+    const int64_t rows = *A.rows_ptr;
+    if (rows <= 0) return;
+    __shared__ float red[8];
+    float gl[2] = {0.f, 0.f};
+    float sd[2], pass[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const float ls = A.log_std[k];
+        sd[k] = expf(fmaxf(ls, MIN_LOG_STD));
+        pass[k] = ls >= MIN_LOG_STD ? 1.f : 0.f;
+    }
+    for (int64_t i = threadIdx.x; i < rows; i += kThreads) {
+        const float4 rv = reinterpret_cast<const float4*>(A.raw)[i];
+        const float2 e = reinterpret_cast<const float2*>(A.eps)[i];
+        const float2 d1 = reinterpret_cast<const float2*>(A.dxa1)[i], d2 = reinterpret_cast<const float2*>(A.dxa2)[i];
+        const float da0 = d1.x + d2.x, da1 = d1.y + d2.y;
+        const float t0 = tanhf(rv.x), t1 = tanhf(rv.y);
+        reinterpret_cast<float4*>(A.draw)[i] =
+            make_float4(da0 * A.sp.scale[0] * (1.0f - t0 * t0), da1 * A.sp.scale[1] * (1.0f - t1 * t1), 0.f, 0.f);
+        gl[0] = fmaf(da0 * sd[0], e.x, gl[0]);
+        gl[1] = fmaf(da1 * sd[1], e.y, gl[1]);
+    }
+    const float s0 = block_sum(gl[0], red);
+    const float s1 = block_sum(gl[1], red);
+    if (threadIdx.x == 0) {
+        A.g_log_std[0] = s0 * pass[0];
+        A.g_log_std[1] = s1 * pass[1];
+    }
+}
+
+// (9) Adam (torch.optim.Adam defaults: sac.py:84,114; qrisk.py:58,75) over a flat range + W2T image refresh
+struct ImgRef {
+    int64_t off;  // offset of a 256x256 tensor inside the arena
+    int64_t img;  // offset of its transposed image
+};
+struct AdamArgs {
+    float* arena;
+    int64_t off, count, grad_off, m_off, v_off;
+    float lr, b1, b2, eps, grad_scale;
+    const int64_t* counters;
+    int t_counter, rows_counter;
+    ImgRef img[4];
+    int n_img;
+};
+__global__ void __launch_bounds__(kThreads) adam_kernel(const __grid_constant__ AdamArgs A) {
+    if (A.counters[A.rows_counter] <= 0) return;
+    const double tstep = (double)(A.counters[A.t_counter] + 1);
+    const float bc1 = (float)(1.0 - pow((double)A.b1, tstep));
+    const float bc2s = (float)sqrt(1.0 - pow((double)A.b2, tstep));
+    const float step_size = A.lr / bc1;
+    for (int64_t i = blockIdx.x * (int64_t)kThreads + threadIdx.x; i < A.count; i += (int64_t)gridDim.x * kThreads) {
+        const int64_t o = A.off + i;
+        const float g = A.arena[A.grad_off + o] * A.grad_scale;
+        float m = A.arena[A.m_off + o], v = A.arena[A.v_off + o];
+        m = m + (g - m) * (1.0f - A.b1);               // exp_avg.lerp_(grad, 1 - beta1)
+        v = v * A.b2 + (1.0f - A.b2) * g * g;           // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+        const float denom = sqrtf(v) / bc2s + A.eps;
+        const float p = A.arena[o] - step_size * (m / denom);
+        A.arena[A.m_off + o] = m;
+        A.arena[A.v_off + o] = v;
+        A.arena[o] = p;
+        for (int q = 0; q < A.n_img; ++q) {
+            const int64_t d = o - A.img[q].off;
+            if (d >= 0 && d < (int64_t)H * H) A.arena[A.img[q].img + (d & (H - 1)) * H + (d >> 8)] = p;
+        }
+    }
+}
+
+// (10) soft_update (utils.py:46-49): target = target*(1-tau) + source*tau over a whole net (+ image refresh)
+struct PolyakArgs {
+    float* arena;
+    int64_t dst_off, src_off, count;
+    float tau;
+    const int64_t* counters;
+    int rows_counter, upd_counter, interval;  // rows_counter < 0: unconditional
+    ImgRef img[2];                            // of the destination net
+    int n_img;
+};
+__global__ void __launch_bounds__(kThreads) polyak_kernel(const __grid_constant__ PolyakArgs A) {
+    if (A.rows_counter >= 0) {
+        if (A.counters[A.rows_counter] <= 0) return;
+        if (A.interval > 1 && (A.counters[A.upd_counter] % A.interval) != 0) return;
+    }
+    const float omt = (float)(1.0 - (double)A.tau);
+    for (int64_t i = blockIdx.x * (int64_t)kThreads + threadIdx.x; i < A.count; i += (int64_t)gridDim.x * kThreads) {
+        const float s = A.arena[A.src_off + i];
+        const float p = A.tau >= 1.0f ? s : (A.arena[A.dst_off + i] * omt + s * A.tau);
+        A.arena[A.dst_off + i] = p;
+        for (int q = 0; q < A.n_img; ++q) {
+            const int64_t d = A.dst_off + i - A.img[q].off;
+            if (d >= 0 && d < (int64_t)H * H) A.arena[A.img[q].img + (d & (H - 1)) * H + (d >> 8)] = p;
+        }
+    }
+}
+
+// (11) rebuild every W2T image from the parameters (after the host wrote parameters)
+struct RefreshArgs {
+    float* arena;
+    ImgRef img[kNumImages];
+};
+__global__ void __launch_bounds__(kThreads) refresh_images_kernel(const __grid_constant__ RefreshArgs A) {
+    __shared__ float tile[32][33];
+    const ImgRef R = A.img[blockIdx.z];
+    const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int r = ty; r < 32; r += 8) tile[r][tx] = A.arena[R.off + (int64_t)(by + r) * H + bx + tx];
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) A.arena[R.img + (int64_t)(bx + r) * H + by + tx] = tile[tx][r];
+}
+
+// (12) bookkeeping after an apply: Adam step counts, update counters (single thread)
+__global__ void bump_kernel(int64_t* counters, int rows_counter, int t0, int t1, int upd_counter) {
+    if (threadIdx.x == 0 && blockIdx.x == 0 && counters[rows_counter] > 0) {
+        if (t0 >= 0) counters[t0] += 1;
+        if (t1 >= 0) counters[t1] += 1;
+        if (upd_counter >= 0) counters[upd_counter] += 1;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host helpers
+// ---------------------------------------------------------------------------------------------
+int check_cfg(const rrl_agent_config_t* cfg) {
+    if (!cfg) { rrl_set_error("null config"); return -2; }
+    if (cfg->hidden != H) { rrl_set_error("kernels are specialised for hidden_size 256 (got %d)", cfg->hidden); return -2; }
+    if (cfg->max_batch < 32 || cfg->max_batch % 32 != 0 || cfg->max_batch > 8192) {
+        rrl_set_error("max_batch must be a multiple of 32 in [32, 8192] (got %d)", cfg->max_batch);
+        return -2;
+    }
+    return 0;
+}
+#define CHECK_CFG(cfg)                      \
+    do {                                    \
+        int rc_ = check_cfg(cfg);           \
+        if (rc_) return rc_;                \
+    } while (0)
+
+ActionSpace action_space(const rrl_agent_config_t* cfg) {
+    ActionSpace sp;
+    sp.scale[0] = cfg->action_scale[0]; sp.scale[1] = cfg->action_scale[1];
+    sp.bias[0] = cfg->action_bias[0]; sp.bias[1] = cfg->action_bias[1];
+    return sp;
+}
+
+template <int BM>
+int launch_forward(const FwdArgs& A, int64_t max_rows, cudaStream_t st) {
+    static bool configured = false;
+    const size_t smem = sizeof(FwdSmem<BM>);
+    if (!configured) {
+        RRL_CUDA(cudaFuncSetAttribute(mlp_forward_kernel<BM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    dim3 grid((unsigned)((max_rows + BM - 1) / BM), (unsigned)A.n_pass);
+    mlp_forward_kernel<BM><<<grid, kThreads, smem, st>>>(A);
+    RRL_CHECK_LAUNCH();
+    return 0;
+}
+
+int imgs_of_net(const Layout& L, int net, ImgRef* out) {
+    const int heads = (net == RRL_NET_POLICY || net == RRL_NET_RECOVERY) ? 1 : 2;
+    for (int h = 0; h < heads; ++h) out[h] = ImgRef{L.t_off[net][w2_tensor(net, h)], L.img_off[image_index(net, h)]};
+    return heads;
+}
+
+int launch_adam(const rrl_agent_config_t* cfg, const Layout& L, float* arena, int64_t* counters, int net_a, int net_b,
+                int t_counter, int rows_counter, cudaStream_t st) {
+    // nets a (and b, contiguous after a in storage order) share one launch
+    AdamArgs A;
+    memset(&A, 0, sizeof(A));
+    A.arena = arena;
+    A.off = L.net_off[net_a];
+    A.count = L.net_size[net_a] + (net_b >= 0 ? L.net_size[net_b] : 0);
+    A.grad_off = L.grad_off; A.m_off = L.m_off; A.v_off = L.v_off;
+    A.lr = cfg->lr; A.b1 = cfg->beta1; A.b2 = cfg->beta2; A.eps = cfg->adam_eps;
+    A.grad_scale = cfg->grad_scale;
+    A.counters = counters;
+    A.t_counter = t_counter;
+    A.rows_counter = rows_counter;
+    A.n_img = imgs_of_net(L, net_a, A.img);
+    if (net_b >= 0) A.n_img += imgs_of_net(L, net_b, A.img + A.n_img);
+    const int blocks = (int)((A.count + kThreads * 4 - 1) / (kThreads * 4));
+    adam_kernel<<<blocks, kThreads, 0, st>>>(A);
+    RRL_CHECK_LAUNCH();
+    return 0;
+}
+
+int launch_polyak(const Layout& L, float* arena, const int64_t* counters, int dst, int src, float tau, int rows_counter,
+                  int upd_counter, int interval, cudaStream_t st) {
+    PolyakArgs A;
+    memset(&A, 0, sizeof(A));
+    A.arena = arena;
+    A.dst_off = L.net_off[dst]; A.src_off = L.net_off[src]; A.count = L.net_size[dst];
+    A.tau = tau;
+    A.counters = counters;
+    A.rows_counter = rows_counter; A.upd_counter = upd_counter; A.interval = interval;
+    A.n_img = imgs_of_net(L, dst, A.img);
+    const int blocks = (int)((A.count + kThreads * 4 - 1) / (kThreads * 4));
+    polyak_kernel<<<blocks, kThreads, 0, st>>>(A);
+    RRL_CHECK_LAUNCH();
+    return 0;
+}
+
+FwdPass q_pass(const Layout& L, float* arena, int net, int head, const float* xs, const float* xa, int slot, float* out_q) {
+    FwdPass p;
+    memset(&p, 0, sizeof(p));
+    p.w = head_w(L, arena, net, head);
+    p.head = (net == RRL_NET_QRISK || net == RRL_NET_QRISK_TARGET) ? HEAD_QRISK : HEAD_Q;
+    p.xs = xs; p.xa = xa;
+    if (slot >= 0) { p.h1 = arena + L.h1[slot]; p.h2 = arena + L.h2[slot]; }
+    p.out_q = out_q;
+    return p;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------
+extern "C" int64_t rrl_agent_arena_floats(const rrl_agent_config_t* cfg) {
+    if (check_cfg(cfg)) return -1;
+    return make_layout(cfg).total;
+}
+
+extern "C" int rrl_agent_num_tensors(int net) {
+    TDesc d[kMaxTensors];
+    if (net < 0 || net >= RRL_NUM_NETS) return -1;
+    return net_tensors(net, d);
+}
+
+extern "C" int rrl_agent_tensor_info(const rrl_agent_config_t* cfg, int net, int tensor, int64_t* offset, int64_t* rows,
+                                     int64_t* cols) {
+    CHECK_CFG(cfg);
+    RRL_CHECK_ARG(net >= 0 && net < RRL_NUM_NETS, "bad net id");
+    const Layout L = make_layout(cfg);
+    RRL_CHECK_ARG(tensor >= 0 && tensor < L.n_tensors[net], "bad tensor index");
+    if (offset) *offset = L.t_off[net][tensor];
+    if (rows) *rows = L.t_desc[net][tensor].rows;
+    if (cols) *cols = L.t_desc[net][tensor].cols;
+    return 0;
+}
+
+extern "C" int rrl_agent_grad_range(const rrl_agent_config_t* cfg, int net, int64_t* offset, int64_t* count) {
+    CHECK_CFG(cfg);
+    const Layout L = make_layout(cfg);
+    if (net < 0) {  // whole block
+        if (offset) *offset = L.grad_off;
+        if (count) *count = L.train_floats;
+        return 0;
+    }
+    RRL_CHECK_ARG(net == RRL_NET_CRITIC || net == RRL_NET_POLICY || net == RRL_NET_QRISK || net == RRL_NET_RECOVERY,
+                  "net has no gradients");
+    if (offset) *offset = L.grad_off + L.net_off[net];
+    if (count) *count = L.net_size[net];
+    return 0;
+}
+
+extern "C" int rrl_agent_scratch_info(const rrl_agent_config_t* cfg, const char* name, int64_t* offset, int64_t* count) {
+    CHECK_CFG(cfg);
+    RRL_CHECK_ARG(name, "null name");
+    const Layout L = make_layout(cfg);
+    for (int i = 0; i < L.n_names; ++i)
+        if (strcmp(L.names[i].name, name) == 0) {
+            if (offset) *offset = L.names[i].off;
+            if (count) *count = L.names[i].count;
+            return 0;
+        }
+    if (strcmp(name, "adam_m") == 0 || strcmp(name, "adam_v") == 0) {
+        if (offset) *offset = name[5] == 'm' ? L.m_off : L.v_off;
+        if (count) *count = L.train_floats;
+        return 0;
+    }
+    rrl_set_error("rrl_agent_scratch_info: unknown region '%s'", name);
+    return -2;
+}
+
+extern "C" int rrl_agent_refresh(const rrl_agent_config_t* cfg, float* arena, void* stream) {
+    CHECK_CFG(cfg);
+    RRL_CHECK_ARG(arena, "null arena");
+    const Layout L = make_layout(cfg);
+    RefreshArgs A;
+    A.arena = arena;
+    int n = 0;
+    static const int nets[6] = {RRL_NET_CRITIC, RRL_NET_CRITIC_TARGET, RRL_NET_POLICY, RRL_NET_QRISK, RRL_NET_QRISK_TARGET,
+                                RRL_NET_RECOVERY};
+    for (int i = 0; i < 6; ++i) n += imgs_of_net(L, nets[i], A.img + n);
+    refresh_images_kernel<<<dim3(H / 32, H / 32, kNumImages), kThreads, 0, (cudaStream_t)stream>>>(A);
+    RRL_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int rrl_hard_update(const rrl_agent_config_t* cfg, float* arena, int dst_net, int src_net, void* stream) {
+    CHECK_CFG(cfg);
+    RRL_CHECK_ARG(arena, "null arena");
+    RRL_CHECK_ARG((dst_net == RRL_NET_CRITIC_TARGET && src_net == RRL_NET_CRITIC) ||
+                      (dst_net == RRL_NET_QRISK_TARGET && src_net == RRL_NET_QRISK),
+                  "hard_update: dst must be the target of src");
+    const Layout L = make_layout(cfg);
+    return launch_polyak(L, arena, nullptr, dst_net, src_net, 1.0f, -1, -1, 1, (cudaStream_t)stream);
+}
+
+extern "C" int rrl_agent_act(const rrl_agent_config_t* cfg, float* arena, int64_t n, const double* state,
+                             const float* eps_task, const float* eps_rec, const float* rand_u, int use_recovery,
+                             int eval, int64_t start_steps, uint64_t seed, int32_t stream_id, const int64_t* counters,
+                             float* action_task, float* action_real, uint8_t* recovery, float* qrisk_out,
+                             void* stream) {
+    CHECK_CFG(cfg);
+    RRL_CHECK_ARG(arena && state && action_task && action_real, "null argument");
+    RRL_CHECK_ARG(n > 0, "n must be positive");
+    const Layout L = make_layout(cfg);
+    ActArgs A;
+    memset(&A, 0, sizeof(A));
+    A.pol = head_w(L, arena, RRL_NET_POLICY, 0);
+    A.qr1 = head_w(L, arena, RRL_NET_QRISK, 0);
+    A.qr2 = head_w(L, arena, RRL_NET_QRISK, 1);
+    A.rec = head_w(L, arena, RRL_NET_RECOVERY, 0);
+    A.n = n; A.state = state;
+    A.eps_task = eps_task; A.eps_rec = eps_rec; A.rand_u = rand_u;
+    A.use_recovery = use_recovery; A.eval = eval; A.start_steps = start_steps;
+    A.seed = seed; A.stream_id = (uint32_t)stream_id; A.counters = counters;
+    A.eps_safe = cfg->eps_safe;
+    A.sp = action_space(cfg);
+    A.action_task = action_task; A.action_real = action_real; A.qrisk_out = qrisk_out; A.recovery = recovery;
+    static bool configured = false;
+    const size_t smem = sizeof(FwdSmem<64>);
+    if (!configured) {
+        RRL_CUDA(cudaFuncSetAttribute(act_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    int64_t tiles = (n + 63) / 64;
+    const int64_t cap = (int64_t)rrl_num_sms() * 2;
+    const int grid = (int)(tiles < cap ? tiles : cap);
+    act_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(A);
+    RRL_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int rrl_twin_q_forward(const rrl_agent_config_t* cfg, const float* arena, int net, int64_t n, const float* s,
+                                  const float* a, float* q1, float* q2, void* stream) {
+    CHECK_CFG(cfg);
+    RRL_CHECK_ARG(arena && s && a && q1 && q2 && n > 0, "bad argument");
+    RRL_CHECK_ARG(net == RRL_NET_CRITIC || net == RRL_NET_CRITIC_TARGET || net == RRL_NET_QRISK || net == RRL_NET_QRISK_TARGET,
+                  "net is not a twin critic");
+    const Layout L = make_layout(cfg);
+    FwdArgs A;
+    memset(&A, 0, sizeof(A));
+    A.p[0] = q_pass(L, const_cast<float*>(arena), net, 0, s, a, -1, q1);
+    A.p[1] = q_pass(L, const_cast<float*>(arena), net, 1, s, a, -1, q2);
+    A.n_pass = 2;
+    A.rows_const = n;
+    A.sp = action_space(cfg);
+    return launch_forward<64>(A, n, (cudaStream_t)stream);
+}
+
+extern "C" int rrl_policy_sample(const rrl_agent_config_t* cfg, const float* arena, int net, int64_t n, const float* s,
+                                 const float* eps, float* action, float* log_prob, float* mean_action, void* stream) {
+    CHECK_CFG(cfg);
+    RRL_CHECK_ARG(arena && s && eps && action && n > 0, "bad argument");
+    RRL_CHECK_ARG(net == RRL_NET_POLICY || net == RRL_NET_RECOVERY, "net is not a policy");
+    const Layout L = make_layout(cfg);
+    FwdArgs A;
+    memset(&A, 0, sizeof(A));
+    FwdPass& p = A.p[0];
+    p.w = head_w(L, arena, net, 0);
+    p.head = net == RRL_NET_POLICY ? HEAD_GAUSS : HEAD_STOCH;
+    p.xs = s; p.eps = eps;
+    p.out_a = action; p.out_logp = log_prob; p.out_mean = mean_action;
+    A.n_pass = 1;
+    A.rows_const = n;
+    A.sp = action_space(cfg);
+    return launch_forward<64>(A, n, (cudaStream_t)stream);
+}
+
+// ---- SAC.update_parameters (sac.py:170-277), "Variant B" ordering ------------------------------
+extern "C" int rrl_sac_backward(const rrl_agent_config_t* cfg, float* arena, const float* eps_next, const float* eps_cur,
+                                uint64_t seed, int32_t stream_id, int64_t* counters, float* losses, void* stream) {
+    CHECK_CFG(cfg);
+    RRL_CHECK_ARG(arena && counters, "null argument");
+    const Layout L = make_layout(cfg);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t R = L.R;
+    const int64_t* rows_ptr = counters + RRL_C_SAC_ROWS;
+    float* s = arena + L.batch_off[0][0]; float* a = arena + L.batch_off[0][1]; float* r = arena + L.batch_off[0][2];
+    float* s2 = arena + L.batch_off[0][3]; float* m = arena + L.batch_off[0][4];
+    auto RA = [&](int id) { return arena + L.rows_f[id]; };
+    auto R2 = [&](int id) { return arena + L.rows2_f[id]; };
+    auto R4 = [&](int id) { return arena + L.rows4_f[id]; };
+    if (!losses) losses = arena + L.losses;
+    const ActionSpace sp = action_space(cfg);
+
+    {  // policy on s' (no grad, sac.py:192-194) and on s (sac.py:216)
+        FwdArgs A;
+        memset(&A, 0, sizeof(A));
+        A.n_pass = 2; A.rows_ptr = rows_ptr; A.sp = sp; A.seed = seed; A.stream_id = (uint32_t)stream_id;
+        A.counters = counters; A.step_counter = RRL_C_SAC_UPDATES;
+        FwdPass& p0 = A.p[0];
+        p0.w = head_w(L, arena, RRL_NET_POLICY, 0); p0.head = HEAD_GAUSS; p0.xs = s2; p0.eps = eps_next;
+        p0.draw_id = RRL_DRAW_SAC_NEXT; p0.out_a = R2(R2_NEXT_A); p0.out_logp = RA(RA_NEXT_LOGP);
+        FwdPass& p1 = A.p[1];
+        p1.w = p0.w; p1.head = HEAD_GAUSS; p1.xs = s; p1.eps = eps_cur; p1.draw_id = RRL_DRAW_SAC_CUR;
+        p1.h1 = arena + L.h1[4]; p1.h2 = arena + L.h2[4];
+        p1.out_a = R2(R2_PI); p1.out_logp = RA(RA_LOGP); p1.out_raw = R4(R4_RAW_POL); p1.out_eps = R2(R2_EPS_CUR);
+        int rc = launch_forward<32>(A, R, st);
+        if (rc) return rc;
+    }
+    {  // critic_target(s', a'), critic(s, a), critic(s, pi)   (sac.py:195-196, 206-207, 218)
+        FwdArgs A;
+        memset(&A, 0, sizeof(A));
+        A.n_pass = 6; A.rows_ptr = rows_ptr; A.sp = sp;
+        A.p[0] = q_pass(L, arena, RRL_NET_CRITIC_TARGET, 0, s2, R2(R2_NEXT_A), -1, RA(RA_QT1));
+        A.p[1] = q_pass(L, arena, RRL_NET_CRITIC_TARGET, 1, s2, R2(R2_NEXT_A), -1, RA(RA_QT2));
+        A.p[2] = q_pass(L, arena, RRL_NET_CRITIC, 0, s, a, 0, RA(RA_QF1));
+        A.p[3] = q_pass(L, arena, RRL_NET_CRITIC, 1, s, a, 1, RA(RA_QF2));
+        A.p[4] = q_pass(L, arena, RRL_NET_CRITIC, 0, s, R2(R2_PI), 2, RA(RA_QP1));
+        A.p[5] = q_pass(L, arena, RRL_NET_CRITIC, 1, s, R2(R2_PI), 3, RA(RA_QP2));
+        int rc = launch_forward<32>(A, R, st);
+        if (rc) return rc;
+    }
+    {
+        SacLossArgs A;
+        A.r = r; A.m = m; A.next_logp = RA(RA_NEXT_LOGP); A.qt1 = RA(RA_QT1); A.qt2 = RA(RA_QT2);
+        A.qf1 = RA(RA_QF1); A.qf2 = RA(RA_QF2); A.logp = RA(RA_LOGP); A.qp1 = RA(RA_QP1); A.qp2 = RA(RA_QP2);
+        A.target = RA(RA_TARGET); A.dqf1 = RA(RA_DQF1); A.dqf2 = RA(RA_DQF2); A.dqp1 = RA(RA_DQP1); A.dqp2 = RA(RA_DQP2);
+        A.minq = RA(RA_MINQ); A.losses = losses; A.gamma = cfg->gamma; A.alpha = cfg->alpha; A.rows_ptr = rows_ptr;
+        sac_loss_kernel<<<1, kThreads, 0, st>>>(A);
+        RRL_CHECK_LAUNCH();
+    }
+    const HeadW c1 = head_w(L, arena, RRL_NET_CRITIC, 0), c2 = head_w(L, arena, RRL_NET_CRITIC, 1);
+    const HeadG g1 = head_g(L, arena, RRL_NET_CRITIC, 0), g2 = head_g(L, arena, RRL_NET_CRITIC, 1);
+    {  // head backward of the four critic passes
+        HeadBwdArgs A;
+        memset(&A, 0, sizeof(A));
+        A.rows_ptr = rows_ptr; A.R = R;
+        const float* dout[4] = {RA(RA_DQF1), RA(RA_DQF2), RA(RA_DQP1), RA(RA_DQP2)};
+        for (int q = 0; q < 4; ++q) {
+            HeadBwdPass& p = A.p[q];
+            const HeadW& w = (q & 1) ? c2 : c1;
+            const HeadG& g = (q & 1) ? g2 : g1;
+            p.dout = dout[q]; p.stride = 1; p.n_out = 1; p.na = 1;
+            p.W3a = w.W3a; p.h2 = arena + L.h2[q]; p.dh2 = arena + L.dh2[q]; p.dh2t = arena + L.dh2t[q];
+            if (q < 2) { p.gW3a = g.W3a; p.gb3a = g.b3a; p.gb2 = g.b2; }
+        }
+        head_backward_kernel<<<dim3(H / 32, 4), kThreads, 0, st>>>(A);
+        RRL_CHECK_LAUNCH();
+    }
+    {  // dh1 for all four passes + gW2 for the (s, a) passes
+        GemmArgs G;
+        memset(&G, 0, sizeof(G));
+        G.rows_ptr = rows_ptr;
+        for (int q = 0; q < 4; ++q) {
+            GemmPass& p = G.p[q];
+            p.A = arena + L.dh2t[q]; p.lda = (int)R; p.B = ((q & 1) ? c2 : c1).W2; p.k_is_rows = 0;
+            p.mask = arena + L.h1[q]; p.C = arena + L.dh1[q];
+        }
+        for (int q = 0; q < 2; ++q) {
+            GemmPass& p = G.p[4 + q];
+            p.A = arena + L.dh2[q]; p.lda = H; p.B = arena + L.h1[q]; p.k_is_rows = 1; p.C = (q ? g2 : g1).W2;
+        }
+        const int mt = (int)((R > H ? R : H) / 32);
+        gemm_stream_kernel<<<dim3(mt, 6), kThreads, 0, st>>>(G);
+        RRL_CHECK_LAUNCH();
+    }
+    {  // layer-1 backward: weight grads for (s, a); d/d(pi) for (s, pi)
+        L1BwdArgs A;
+        memset(&A, 0, sizeof(A));
+        A.rows_ptr = rows_ptr;
+        for (int q = 0; q < 4; ++q) {
+            L1BwdPass& p = A.p[q];
+            const HeadW& w = (q & 1) ? c2 : c1;
+            const HeadG& g = (q & 1) ? g2 : g1;
+            p.dh1 = arena + L.dh1[q]; p.xs = s; p.xa = q < 2 ? a : R2(R2_PI); p.W1 = w.W1; p.n_in = 4;
+            if (q < 2) { p.gW1 = g.W1; p.gb1 = g.b1; }
+            else p.dxa = q == 2 ? R2(R2_DPI) : arena + L.rows2_f[R2_REC_DPI];  // second head: borrowed scratch
+        }
+        layer1_backward_kernel<<<dim3(2, 4), kThreads, 0, st>>>(A);
+        RRL_CHECK_LAUNCH();
+    }
+    const HeadW pw = head_w(L, arena, RRL_NET_POLICY, 0);
+    const HeadG pg = head_g(L, arena, RRL_NET_POLICY, 0);
+    {
+        GaussBwdArgs A;
+        A.raw = R4(R4_RAW_POL); A.eps = R2(R2_EPS_CUR); A.dxa1 = R2(R2_DPI); A.dxa2 = arena + L.rows2_f[R2_REC_DPI];
+        A.draw = R4(R4_DRAW_POL); A.alpha = cfg->alpha; A.sp = sp; A.rows_ptr = rows_ptr;
+        gauss_backward_kernel<<<(unsigned)((R + kThreads - 1) / kThreads), kThreads, 0, st>>>(A);
+        RRL_CHECK_LAUNCH();
+    }
+    {
+        HeadBwdArgs A;
+        memset(&A, 0, sizeof(A));
+        A.rows_ptr = rows_ptr; A.R = R;
+        HeadBwdPass& p = A.p[0];
+        p.dout = R4(R4_DRAW_POL); p.stride = 4; p.n_out = 4; p.na = 2;
+        p.W3a = pw.W3a; p.W3b = pw.W3b; p.h2 = arena + L.h2[4]; p.dh2 = arena + L.dh2[4]; p.dh2t = arena + L.dh2t[4];
+        p.gW3a = pg.W3a; p.gW3b = pg.W3b; p.gb3a = pg.b3a; p.gb3b = pg.b3b; p.gb2 = pg.b2;
+        head_backward_kernel<<<dim3(H / 32, 1), kThreads, 0, st>>>(A);
+        RRL_CHECK_LAUNCH();
+    }
+    {
+        GemmArgs G;
+        memset(&G, 0, sizeof(G));
+        G.rows_ptr = rows_ptr;
+        G.p[0].A = arena + L.dh2t[4]; G.p[0].lda = (int)R; G.p[0].B = pw.W2; G.p[0].mask = arena + L.h1[4];
+        G.p[0].C = arena + L.dh1[4];
+        G.p[1].A = arena + L.dh2[4]; G.p[1].lda = H; G.p[1].B = arena + L.h1[4]; G.p[1].k_is_rows = 1; G.p[1].C = pg.W2;
+        const int mt = (int)((R > H ? R : H) / 32);
+        gemm_stream_kernel<<<dim3(mt, 2), kThreads, 0, st>>>(G);
+        RRL_CHECK_LAUNCH();
+    }
+    {
+        L1BwdArgs A;
+        memset(&A, 0, sizeof(A));
+        A.rows_ptr = rows_ptr;
+        L1BwdPass& p = A.p[0];
+        p.dh1 = arena + L.dh1[4]; p.xs = s; p.W1 = pw.W1; p.n_in = 2; p.gW1 = pg.W1; p.gb1 = pg.b1;
+        layer1_backward_kernel<<<dim3(1, 1), kThreads, 0, st>>>(A);
+        RRL_CHECK_LAUNCH();
+    }
+    return 0;
+}
+
+extern "C" int rrl_sac_apply(const rrl_agent_config_t* cfg, float* arena, int64_t* counters, void* stream) {
+    CHECK_CFG(cfg);
+    RRL_CHECK_ARG(arena && counters, "null argument");
+    const Layout L = make_layout(cfg);
+    cudaStream_t st = (cudaStream_t)stream;
+    // critic_optim.step(); policy_optim.step()  (sac.py:233-239).  Both Adams have the same step count.
+    int rc = launch_adam(cfg, L, arena, counters, RRL_NET_CRITIC, RRL_NET_POLICY, RRL_C_ADAM_T0 + 0, RRL_C_SAC_ROWS, st);
+    if (rc) return rc;
+    // soft_update(critic_target, critic, tau) if updates % target_update_interval == 0  (sac.py:273-274)
+    rc = launch_polyak(L, arena, counters, RRL_NET_CRITIC_TARGET, RRL_NET_CRITIC, cfg->tau, RRL_C_SAC_ROWS,
+                       RRL_C_SAC_UPDATES, cfg->target_update_interval, st);
+    if (rc) return rc;
+    bump_kernel<<<1, 32, 0, st>>>(counters, RRL_C_SAC_ROWS, RRL_C_ADAM_T0 + 0, RRL_C_ADAM_T0 + 1, RRL_C_SAC_UPDATES);
+    RRL_CHECK_LAUNCH();
+    return 0;
+}
+
+// ---- QRiskWrapper.update_parameters (qrisk.py:86-182) --------------------------------------------
+extern "C" int rrl_qrisk_backward(const rrl_agent_config_t* cfg, float* arena, const float* eps_next, uint64_t seed,
+                                  int32_t stream_id, int64_t* counters, float* losses, void* stream) {
+    CHECK_CFG(cfg);
+    RRL_CHECK_ARG(arena && counters, "null argument");
+    const Layout L = make_layout(cfg);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t R = L.R;
+    const int64_t* rows_ptr = counters + RRL_C_QRISK_ROWS;
+    float* s = arena + L.batch_off[1][0]; float* a = arena + L.batch_off[1][1]; float* c = arena + L.batch_off[1][2];
+    float* s2 = arena + L.batch_off[1][3]; float* m = arena + L.batch_off[1][4];
+    auto RA = [&](int id) { return arena + L.rows_f[id]; };
+    auto R2 = [&](int id) { return arena + L.rows2_f[id]; };
+    if (!losses) losses = arena + L.losses + 8;
+    const ActionSpace sp = action_space(cfg);
+    {  // a' ~ TASK policy(s')  (qrisk.py:118-120; policy = agent.policy, experiment.py:413)
+        FwdArgs A;
+        memset(&A, 0, sizeof(A));
+        A.n_pass = 1; A.rows_ptr = rows_ptr; A.sp = sp; A.seed = seed; A.stream_id = (uint32_t)stream_id;
+        A.counters = counters; A.step_counter = RRL_C_QRISK_UPDATES;
+        FwdPass& p0 = A.p[0];
+        p0.w = head_w(L, arena, RRL_NET_POLICY, 0); p0.head = HEAD_GAUSS; p0.xs = s2; p0.eps = eps_next;
+        p0.draw_id = RRL_DRAW_QR_NEXT; p0.out_a = R2(R2_QR_NEXT_A); p0.out_logp = RA(RA_QR_NEXT_LOGP);
+        int rc = launch_forward<32>(A, R, st);
+        if (rc) return rc;
+    }
+    {
+        FwdArgs A;
+        memset(&A, 0, sizeof(A));
+        A.n_pass = 4; A.rows_ptr = rows_ptr; A.sp = sp;
+        A.p[0] = q_pass(L, arena, RRL_NET_QRISK_TARGET, 0, s2, R2(R2_QR_NEXT_A), -1, RA(RA_QR_QT1));
+        A.p[1] = q_pass(L, arena, RRL_NET_QRISK_TARGET, 1, s2, R2(R2_QR_NEXT_A), -1, RA(RA_QR_QT2));
+        A.p[2] = q_pass(L, arena, RRL_NET_QRISK, 0, s, a, 0, RA(RA_QR_Q1));
+        A.p[3] = q_pass(L, arena, RRL_NET_QRISK, 1, s, a, 1, RA(RA_QR_Q2));
+        int rc = launch_forward<32>(A, R, st);
+        if (rc) return rc;
+    }
+    {
+        QrLossArgs A;
+        A.c = c; A.m = m; A.qt1 = RA(RA_QR_QT1); A.qt2 = RA(RA_QR_QT2); A.q1 = RA(RA_QR_Q1); A.q2 = RA(RA_QR_Q2);
+        A.target = RA(RA_QR_TARGET); A.dq1 = RA(RA_QR_DQ1); A.dq2 = RA(RA_QR_DQ2); A.losses = losses;
+        A.gamma_safe = cfg->gamma_safe; A.rows_ptr = rows_ptr;
+        qrisk_loss_kernel<<<1, kThreads, 0, st>>>(A);
+        RRL_CHECK_LAUNCH();
+    }
+    const HeadW c1 = head_w(L, arena, RRL_NET_QRISK, 0), c2 = head_w(L, arena, RRL_NET_QRISK, 1);
+    const HeadG g1 = head_g(L, arena, RRL_NET_QRISK, 0), g2 = head_g(L, arena, RRL_NET_QRISK, 1);
+    {
+        HeadBwdArgs A;
+        memset(&A, 0, sizeof(A));
+        A.rows_ptr = rows_ptr; A.R = R;
+        for (int q = 0; q < 2; ++q) {
+            HeadBwdPass& p = A.p[q];
+            const HeadW& w = q ? c2 : c1;
+            const HeadG& g = q ? g2 : g1;
+            p.dout = q ? RA(RA_QR_DQ2) : RA(RA_QR_DQ1); p.stride = 1; p.n_out = 1; p.na = 1;
+            p.W3a = w.W3a; p.h2 = arena + L.h2[q]; p.dh2 = arena + L.dh2[q]; p.dh2t = arena + L.dh2t[q];
+            p.gW3a = g.W3a; p.gb3a = g.b3a; p.gb2 = g.b2;
+        }
+        head_backward_kernel<<<dim3(H / 32, 2), kThreads, 0, st>>>(A);
+        RRL_CHECK_LAUNCH();
+    }
+    {
+        GemmArgs G;
+        memset(&G, 0, sizeof(G));
+        G.rows_ptr = rows_ptr;
+        for (int q = 0; q < 2; ++q) {
+            GemmPass& p = G.p[q];
+            p.A = arena + L.dh2t[q]; p.lda = (int)R; p.B = (q ? c2 : c1).W2; p.mask = arena + L.h1[q]; p.C = arena + L.dh1[q];
+            GemmPass& w = G.p[2 + q];
+            w.A = arena + L.dh2[q]; w.lda = H; w.B = arena + L.h1[q]; w.k_is_rows = 1; w.C = (q ? g2 : g1).W2;
+        }
+        const int mt = (int)((R > H ? R : H) / 32);
+        gemm_stream_kernel<<<dim3(mt, 4), kThreads, 0, st>>>(G);
+        RRL_CHECK_LAUNCH();
+    }
+    {
+        L1BwdArgs A;
+        memset(&A, 0, sizeof(A));
+        A.rows_ptr = rows_ptr;
+        for (int q = 0; q < 2; ++q) {
+            L1BwdPass& p = A.p[q];
+            p.dh1 = arena + L.dh1[q]; p.xs = s; p.xa = a; p.W1 = (q ? c2 : c1).W1; p.n_in = 4;
+            p.gW1 = (q ? g2 : g1).W1; p.gb1 = (q ? g2 : g1).b1;
+        }
+        layer1_backward_kernel<<<dim3(1, 2), kThreads, 0, st>>>(A);
+        RRL_CHECK_LAUNCH();
+    }
+    return 0;
+}
+
+extern "C" int rrl_qrisk_apply(const rrl_agent_config_t* cfg, float* arena, int64_t* counters, void* stream) {
+    CHECK_CFG(cfg);
+    RRL_CHECK_ARG(arena && counters, "null argument");
+    const Layout L = make_layout(cfg);
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = launch_adam(cfg, L, arena, counters, RRL_NET_QRISK, -1, RRL_C_ADAM_T0 + 2, RRL_C_QRISK_ROWS, st);
+    if (rc) return rc;
+    bump_kernel<<<1, 32, 0, st>>>(counters, RRL_C_QRISK_ROWS, RRL_C_ADAM_T0 + 2, -1, -1);
+    RRL_CHECK_LAUNCH();
+    return 0;
+}
+
+// recovery policy on the POST-step safety critic (qrisk.py:150-158), then Polyak (qrisk.py:160-163)
+extern "C" int rrl_recovery_backward(const rrl_agent_config_t* cfg, float* arena, const float* eps_rec, uint64_t seed,
+                                     int32_t stream_id, int64_t* counters, float* losses, void* stream) {
+    CHECK_CFG(cfg);
+    RRL_CHECK_ARG(arena && counters, "null argument");
+    const Layout L = make_layout(cfg);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t R = L.R;
+    const int64_t* rows_ptr = counters + RRL_C_QRISK_ROWS;
+    float* s = arena + L.batch_off[1][0];
+    auto RA = [&](int id) { return arena + L.rows_f[id]; };
+    auto R2 = [&](int id) { return arena + L.rows2_f[id]; };
+    auto R4 = [&](int id) { return arena + L.rows4_f[id]; };
+    if (!losses) losses = arena + L.losses + 8;
+    const ActionSpace sp = action_space(cfg);
+    if (!cfg->mf_recovery) return 0;
+    {
+        FwdArgs A;
+        memset(&A, 0, sizeof(A));
+        A.n_pass = 1; A.rows_ptr = rows_ptr; A.sp = sp; A.seed = seed; A.stream_id = (uint32_t)stream_id;
+        A.counters = counters; A.step_counter = RRL_C_QRISK_UPDATES;
+        FwdPass& p0 = A.p[0];
+        p0.w = head_w(L, arena, RRL_NET_RECOVERY, 0); p0.head = HEAD_STOCH; p0.xs = s; p0.eps = eps_rec;
+        p0.draw_id = RRL_DRAW_QR_REC; p0.h1 = arena + L.h1[4]; p0.h2 = arena + L.h2[4];
+        p0.out_a = R2(R2_REC_PI); p0.out_logp = RA(RA_REC_LOGP); p0.out_raw = R4(R4_RAW_REC); p0.out_eps = R2(R2_REC_EPS);
+        int rc = launch_forward<32>(A, R, st);
+        if (rc) return rc;
+    }
+    {
+        FwdArgs A;
+        memset(&A, 0, sizeof(A));
+        A.n_pass = 2; A.rows_ptr = rows_ptr; A.sp = sp;
+        A.p[0] = q_pass(L, arena, RRL_NET_QRISK, 0, s, R2(R2_REC_PI), 2, RA(RA_REC_Q1));
+        A.p[1] = q_pass(L, arena, RRL_NET_QRISK, 1, s, R2(R2_REC_PI), 3, RA(RA_REC_Q2));
+        int rc = launch_forward<32>(A, R, st);
+        if (rc) return rc;
+    }
+    {
+        RecLossArgs A;
+        A.q1 = RA(RA_REC_Q1); A.q2 = RA(RA_REC_Q2); A.dq1 = RA(RA_REC_DQ1); A.dq2 = RA(RA_REC_DQ2); A.losses = losses;
+        A.rows_ptr = rows_ptr;
+        recovery_loss_kernel<<<1, kThreads, 0, st>>>(A);
+        RRL_CHECK_LAUNCH();
+    }
+    const HeadW c1 = head_w(L, arena, RRL_NET_QRISK, 0), c2 = head_w(L, arena, RRL_NET_QRISK, 1);
+    {
+        HeadBwdArgs A;
+        memset(&A, 0, sizeof(A));
+        A.rows_ptr = rows_ptr; A.R = R;
+        for (int q = 0; q < 2; ++q) {
+            HeadBwdPass& p = A.p[q];
+            p.dout = q ? RA(RA_REC_DQ2) : RA(RA_REC_DQ1); p.stride = 1; p.n_out = 1; p.na = 1;
+            p.W3a = (q ? c2 : c1).W3a; p.h2 = arena + L.h2[2 + q]; p.dh2 = arena + L.dh2[2 + q]; p.dh2t = arena + L.dh2t[2 + q];
+        }
+        head_backward_kernel<<<dim3(H / 32, 2), kThreads, 0, st>>>(A);
+        RRL_CHECK_LAUNCH();
+    }
+    {
+        GemmArgs G;
+        memset(&G, 0, sizeof(G));
+        G.rows_ptr = rows_ptr;
+        for (int q = 0; q < 2; ++q) {
+            GemmPass& p = G.p[q];
+            p.A = arena + L.dh2t[2 + q]; p.lda = (int)R; p.B = (q ? c2 : c1).W2; p.mask = arena + L.h1[2 + q];
+            p.C = arena + L.dh1[2 + q];
+        }
+        gemm_stream_kernel<<<dim3((int)(R / 32), 2), kThreads, 0, st>>>(G);
+        RRL_CHECK_LAUNCH();
+    }
+    {
+        L1BwdArgs A;
+        memset(&A, 0, sizeof(A));
+        A.rows_ptr = rows_ptr;
+        for (int q = 0; q < 2; ++q) {
+            L1BwdPass& p = A.p[q];
+            p.dh1 = arena + L.dh1[2 + q]; p.xs = s; p.xa = R2(R2_REC_PI); p.W1 = (q ? c2 : c1).W1; p.n_in = 4;
+            p.dxa = q ? R2(R2_DPI) : R2(R2_REC_DPI);
+        }
+        layer1_backward_kernel<<<dim3(2, 2), kThreads, 0, st>>>(A);
+        RRL_CHECK_LAUNCH();
+    }
+    const HeadW pw = head_w(L, arena, RRL_NET_RECOVERY, 0);
+    const HeadG pg = head_g(L, arena, RRL_NET_RECOVERY, 0);
+    {
+        StochBwdArgs A;
+        A.raw = R4(R4_RAW_REC); A.eps = R2(R2_REC_EPS); A.dxa1 = R2(R2_REC_DPI); A.dxa2 = R2(R2_DPI);
+        A.log_std = pw.log_std; A.draw = R4(R4_DRAW_REC); A.g_log_std = pg.log_std; A.sp = sp; A.rows_ptr = rows_ptr;
+        stoch_backward_kernel<<<1, kThreads, 0, st>>>(A);
+        RRL_CHECK_LAUNCH();
+    }
+    {
+        HeadBwdArgs A;
+        memset(&A, 0, sizeof(A));
+        A.rows_ptr = rows_ptr; A.R = R;
+        HeadBwdPass& p = A.p[0];
+        p.dout = R4(R4_DRAW_REC); p.stride = 4; p.n_out = 2; p.na = 2;
+        p.W3a = pw.W3a; p.h2 = arena + L.h2[4]; p.dh2 = arena + L.dh2[4]; p.dh2t = arena + L.dh2t[4];
+        p.gW3a = pg.W3a; p.gb3a = pg.b3a; p.gb2 = pg.b2;
+        head_backward_kernel<<<dim3(H / 32, 1), kThreads, 0, st>>>(A);
+        RRL_CHECK_LAUNCH();
+    }
+    {
+        GemmArgs G;
+        memset(&G, 0, sizeof(G));
+        G.rows_ptr = rows_ptr;
+        G.p[0].A = arena + L.dh2t[4]; G.p[0].lda = (int)R; G.p[0].B = pw.W2; G.p[0].mask = arena + L.h1[4];
+        G.p[0].C = arena + L.dh1[4];
+        G.p[1].A = arena + L.dh2[4]; G.p[1].lda = H; G.p[1].B = arena + L.h1[4]; G.p[1].k_is_rows = 1; G.p[1].C = pg.W2;
+        const int mt = (int)((R > H ? R : H) / 32);
+        gemm_stream_kernel<<<dim3(mt, 2), kThreads, 0, st>>>(G);
+        RRL_CHECK_LAUNCH();
+    }
+    {
+        L1BwdArgs A;
+        memset(&A, 0, sizeof(A));
+        A.rows_ptr = rows_ptr;
+        L1BwdPass& p = A.p[0];
+        p.dh1 = arena + L.dh1[4]; p.xs = s; p.W1 = pw.W1; p.n_in = 2; p.gW1 = pg.W1; p.gb1 = pg.b1;
+        layer1_backward_kernel<<<dim3(1, 1), kThreads, 0, st>>>(A);
+        RRL_CHECK_LAUNCH();
+    }
+    return 0;
+}
+
+extern "C" int rrl_recovery_apply(const rrl_agent_config_t* cfg, float* arena, int64_t* counters, void* stream) {
+    CHECK_CFG(cfg);
+    RRL_CHECK_ARG(arena && counters, "null argument");
+    const Layout L = make_layout(cfg);
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = 0;
+    if (cfg->mf_recovery) {
+        rc = launch_adam(cfg, L, arena, counters, RRL_NET_RECOVERY, -1, RRL_C_ADAM_T0 + 3, RRL_C_QRISK_ROWS, st);
+        if (rc) return rc;
+    }
+    // soft_update(safety_critic_target, safety_critic, tau_safe) if self.updates % interval == 0; self.updates += 1
+    rc = launch_polyak(L, arena, counters, RRL_NET_QRISK_TARGET, RRL_NET_QRISK, cfg->tau_safe, RRL_C_QRISK_ROWS,
+                       RRL_C_QRISK_UPDATES, cfg->target_update_interval, st);
+    if (rc) return rc;
+    bump_kernel<<<1, 32, 0, st>>>(counters, RRL_C_QRISK_ROWS, cfg->mf_recovery ? RRL_C_ADAM_T0 + 3 : -1, -1,
+                                  RRL_C_QRISK_UPDATES);
+    RRL_CHECK_LAUNCH();
+    return 0;
+}
