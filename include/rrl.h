@@ -68,7 +68,11 @@ typedef struct {
     uint64_t seed;             /* Philox key (production RNG mode)                         */
     int32_t stream_id;         /* rank: second half of the Philox key                      */
     int32_t maze_substeps;     /* maze.py:147 (500)                                        */
+    int32_t flags;             /* RRL_ENV_NO_AUTO_RESET: the caller resets explicitly (gym-style
+                                  env.reset(), offline-data generators that keep stepping after done) */
+    int32_t reserved;
 } rrl_env_config_t;
+enum { RRL_ENV_NO_AUTO_RESET = 1 };
 
 /* env.reset (navigation1.py:91-97, navigation2.py:90-96, maze.py:184-213 mode 'h').
  * mask: NULL = reset all, else reset env i iff mask[i] != 0.
@@ -88,6 +92,8 @@ int rrl_env_reset(const rrl_env_config_t* cfg, const uint8_t* mask, const double
  *   reset_draws: NULL = Philox; else fp64 [2][n] draws used by envs that finish this step
  *   task_ring / cons_ring / cons_flags : may be NULL (no push)
  *   out_*      : per-env results of THIS step (pre-reset), any may be NULL
+ *   action_real_f64 : NULL, or fp64 [n][2] executed action used for the DYNAMICS instead of action_real
+ *                (the offline-data generators step with float64 actions: navigation1.py:150-152)
  */
 int rrl_env_step(const rrl_env_config_t* cfg, const float* action_task, const float* action_real,
                  const uint8_t* recovery, const double* noise, const double* reset_draws,
@@ -96,7 +102,7 @@ int rrl_env_step(const rrl_env_config_t* cfg, const float* action_task, const fl
                  float* cons_ring, uint8_t* cons_flags, int64_t cons_capacity,
                  int64_t* counters,
                  double* out_next_state, double* out_reward, uint8_t* out_done,
-                 uint8_t* out_constraint, uint8_t* out_success, void* stream);
+                 uint8_t* out_constraint, uint8_t* out_success, const double* action_real_f64, void* stream);
 
 /* After rrl_env_step: position/len of both rings += n, total_numsteps += n, vec_step += 1
  * (replay_memory.py:22-25; experiment.py:429).  push_task / push_cons select the rings. */
@@ -125,7 +131,7 @@ typedef struct {
     double  pos_fraction;      /* < 0: None (qrisk.py:77)                                  */
     int32_t gate_mode;         /* 0: always sample min(B, len) rows (pre-training, qrisk.py:100-104);
                                   1: SAC gate   len > B                 (experiment.py:397);
-                                  2: Q_risk gate len > B && (viols)/B > pos_fraction (experiment.py:407-410) */
+                                  2: Q_risk gate: SAC gate && len > B && (viols)/B > pos_fraction (experiment.py:397,407-410) */
     int32_t chunk;             /* flag chunk size used by rrl_replay_flag_count            */
     double  gate_pos_fraction; /* exp_cfg.pos_fraction as given on the command line        */
 } rrl_sample_config_t;

@@ -246,3 +246,45 @@ def maze_offline_data(num_transitions, action_rng=None):
             tr.append((state, action, int(cons[0]), ns[0], not bool(done[0])))
             state = ns[0]
     return tr
+
+
+_WALLS = None
+
+
+def maze_step_scalar(state, action, ep_steps, substeps=MAZE_SUBSTEPS):
+    """maze_step for ONE env in plain Python floats (same IEEE-754 double operations, same order) -- the
+    N = 1 CPU baseline loop uses it; tests check it against the vectorised maze_step."""
+    global _WALLS
+    if _WALLS is None:
+        _WALLS = maze_walls()
+    a = np.clip(np.asarray(action), -0.1, 0.1)
+    fbx = MAZE_CB * (MAZE_GEAR * float(a[0]))
+    fby = MAZE_CB * (MAZE_GEAR * float(a[1]))
+    x, y = float(state[0]), float(state[1])
+    vx = vy = 0.0
+    contact = False
+    r2 = MAZE_R * MAZE_R
+    for _ in range(substeps):
+        if (x - MAZE_R <= -0.3) or (x + MAZE_R >= 0.3) or (y - MAZE_R <= -0.3) or (y + MAZE_R >= 0.3):
+            contact = True
+            break
+        hit = False
+        for x0, x1, y0, y1 in _WALLS:
+            dx = max(max(x0 - x, 0.0), x - x1)
+            dy = max(max(y0 - y, 0.0), y - y1)
+            if dx * dx + dy * dy < r2:
+                hit = True
+                break
+        if hit:
+            contact = True
+            break
+        vx = MAZE_CA * vx + fbx
+        vy = MAZE_CA * vy + fby
+        x = x + MAZE_H * vx
+        y = y + MAZE_H * vy
+    d0 = MAZE_GOAL[0] - x
+    d1 = MAZE_GOAL[1] - y
+    dist = float(np.sqrt((d0 * d0 + d1 * d1) * 0.5))
+    reward = -dist
+    done = (ep_steps + 1 >= MAZE_HORIZON) or contact or (dist < MAZE_GOAL_THRESH)
+    return np.array([x, y]), reward, bool(done), bool(contact), bool(reward > -0.03)

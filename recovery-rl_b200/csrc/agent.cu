@@ -640,7 +640,7 @@ __global__ void __launch_bounds__(kThreads) gemm_stream_kernel(const __grid_cons
     }
 }
 
-// (3) layer-1 backward: gW1, gb1 (blockIdx.x == 0) and d(action input) (blockIdx.x == 1)
+// (3) layer-1 backward: gW1, gb1 (first H/32 blocks of x) and d(action input) (remaining blocks of x)
 struct L1BwdPass {
     const float *dh1, *xs, *xa, *W1;
     int n_in;
@@ -652,16 +652,21 @@ struct L1BwdArgs {
     const int64_t* rows_ptr;
 };
 
+constexpr int kL1ColBlocks = H / 32;  // blockIdx.x <  kL1ColBlocks : weight grads of 32 hidden units
+constexpr int kL1RowBlocks = 8;       // blockIdx.x >= kL1ColBlocks : d(action) for a slice of the rows
+
 __global__ void __launch_bounds__(kThreads) layer1_backward_kernel(const __grid_constant__ L1BwdArgs A) {
     const int64_t rows = *A.rows_ptr;
     if (rows <= 0) return;
     const L1BwdPass& P = A.p[blockIdx.y];
-    const int t = threadIdx.x;
-    if (blockIdx.x == 0) {
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    if (blockIdx.x < kL1ColBlocks) {
         if (!P.gW1) return;
+        __shared__ float red[5][8][32];
+        const int j = blockIdx.x * 32 + lane;
         float g[4] = {0.f, 0.f, 0.f, 0.f}, gb = 0.f;
-        for (int64_t r = 0; r < rows; ++r) {
-            const float d = P.dh1[r * H + t];
+        for (int64_t r = warp; r < rows; r += 8) {
+            const float d = P.dh1[r * H + j];
             const float2 s = reinterpret_cast<const float2*>(P.xs)[r];
             g[0] = fmaf(d, s.x, g[0]);
             g[1] = fmaf(d, s.y, g[1]);
@@ -672,18 +677,31 @@ __global__ void __launch_bounds__(kThreads) layer1_backward_kernel(const __grid_
             }
             gb += d;
         }
-        for (int i = 0; i < P.n_in; ++i) P.gW1[t * P.n_in + i] = g[i];
-        P.gb1[t] = gb;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) red[i][warp][lane] = g[i];
+        red[4][warp][lane] = gb;
+        __syncthreads();
+        if (warp == 0) {
+            float sum[5];
+#pragma unroll
+            for (int q = 0; q < 5; ++q) {
+                float v = 0.f;
+#pragma unroll
+                for (int y = 0; y < 8; ++y) v += red[q][y][lane];
+                sum[q] = v;
+            }
+            for (int i = 0; i < P.n_in; ++i) P.gW1[j * P.n_in + i] = sum[i];
+            P.gb1[j] = sum[4];
+        }
     } else {
         if (!P.dxa) return;
-        const int lane = t & 31, warp = t >> 5;
         float w2[8], w3[8];
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
             w2[q] = P.W1[(lane + 32 * q) * 4 + 2];
             w3[q] = P.W1[(lane + 32 * q) * 4 + 3];
         }
-        for (int64_t r = warp; r < rows; r += 8) {
+        for (int64_t r = (int64_t)(blockIdx.x - kL1ColBlocks) * 8 + warp; r < rows; r += 8 * kL1RowBlocks) {
             float a0 = 0.f, a1 = 0.f;
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
@@ -1331,7 +1349,7 @@ extern "C" int rrl_sac_backward(const rrl_agent_config_t* cfg, float* arena, con
             if (q < 2) { p.gW1 = g.W1; p.gb1 = g.b1; }
             else p.dxa = q == 2 ? R2(R2_DPI) : arena + L.rows2_f[R2_REC_DPI];  // second head: borrowed scratch
         }
-        layer1_backward_kernel<<<dim3(2, 4), kThreads, 0, st>>>(A);
+        layer1_backward_kernel<<<dim3(kL1ColBlocks + kL1RowBlocks, 4), kThreads, 0, st>>>(A);
         RRL_CHECK_LAUNCH();
     }
     const HeadW pw = head_w(L, arena, RRL_NET_POLICY, 0);
@@ -1371,7 +1389,7 @@ extern "C" int rrl_sac_backward(const rrl_agent_config_t* cfg, float* arena, con
         A.rows_ptr = rows_ptr;
         L1BwdPass& p = A.p[0];
         p.dh1 = arena + L.dh1[4]; p.xs = s; p.W1 = pw.W1; p.n_in = 2; p.gW1 = pg.W1; p.gb1 = pg.b1;
-        layer1_backward_kernel<<<dim3(1, 1), kThreads, 0, st>>>(A);
+        layer1_backward_kernel<<<dim3(kL1ColBlocks, 1), kThreads, 0, st>>>(A);
         RRL_CHECK_LAUNCH();
     }
     return 0;
@@ -1479,7 +1497,7 @@ extern "C" int rrl_qrisk_backward(const rrl_agent_config_t* cfg, float* arena, c
             p.dh1 = arena + L.dh1[q]; p.xs = s; p.xa = a; p.W1 = (q ? c2 : c1).W1; p.n_in = 4;
             p.gW1 = (q ? g2 : g1).W1; p.gb1 = (q ? g2 : g1).b1;
         }
-        layer1_backward_kernel<<<dim3(1, 2), kThreads, 0, st>>>(A);
+        layer1_backward_kernel<<<dim3(kL1ColBlocks, 2), kThreads, 0, st>>>(A);
         RRL_CHECK_LAUNCH();
     }
     return 0;
@@ -1575,7 +1593,7 @@ extern "C" int rrl_recovery_backward(const rrl_agent_config_t* cfg, float* arena
             p.dh1 = arena + L.dh1[2 + q]; p.xs = s; p.xa = R2(R2_REC_PI); p.W1 = (q ? c2 : c1).W1; p.n_in = 4;
             p.dxa = q ? R2(R2_DPI) : R2(R2_REC_DPI);
         }
-        layer1_backward_kernel<<<dim3(2, 2), kThreads, 0, st>>>(A);
+        layer1_backward_kernel<<<dim3(kL1ColBlocks + kL1RowBlocks, 2), kThreads, 0, st>>>(A);
         RRL_CHECK_LAUNCH();
     }
     const HeadW pw = head_w(L, arena, RRL_NET_RECOVERY, 0);
@@ -1615,7 +1633,7 @@ extern "C" int rrl_recovery_backward(const rrl_agent_config_t* cfg, float* arena
         A.rows_ptr = rows_ptr;
         L1BwdPass& p = A.p[0];
         p.dh1 = arena + L.dh1[4]; p.xs = s; p.W1 = pw.W1; p.n_in = 2; p.gW1 = pg.W1; p.gb1 = pg.b1;
-        layer1_backward_kernel<<<dim3(1, 1), kThreads, 0, st>>>(A);
+        layer1_backward_kernel<<<dim3(kL1ColBlocks, 1), kThreads, 0, st>>>(A);
         RRL_CHECK_LAUNCH();
     }
     return 0;

@@ -7,6 +7,7 @@
 //               cost = -sqrt(fma(s.y, s.y, s.x*s.x))        env/navigation1.py:106-110 (OpenBLAS ddot)
 //   maze        restated physics, see oracle/envs.py (MuJoCo is a closed third-party binary)
 #include "common.cuh"
+#include <math.h>
 
 namespace {
 
@@ -14,6 +15,8 @@ struct EnvParams {
     rrl_env_config_t cfg;
     // maze constants (host-computed in double, identical expressions in oracle/envs.py)
     double c_a, c_b, h, gear;
+    int hi_plane, hi_band_lo, hi_band_hi;  // high words of 0.27, 0.069, 0.131 (conservative pre-filter)
+    double plane_lo, plane_hi;  // x <= plane_lo  <=>  fl(x - R) <= -0.3 ;  x >= plane_hi  <=>  fl(x + R) >= 0.3
     double wx0[4], wx1[4], wy0[4], wy1[4];  // 1A, 1B, 2A, 2B rectangles
 };
 
@@ -31,20 +34,27 @@ __device__ __forceinline__ bool nav_obstacle(int kind, double x, double y) {
 
 // ---- maze geometry: simple_maze.xml:16-25 + maze.py:201-206 ----------------------------------
 // disc radius r against the 4 outer planes (closed) and 4 axis-aligned rectangles (strict).
+// The oracle's tests are   x - R <= -0.3 | x + R >= 0.3 | ...   and   dx*dx + dy*dy < R*R  with
+// dx = max(max(x0 - x, 0), x - x1).  Both are evaluated here in exactly equivalent, cheaper forms:
+//   * fl(x - R) <= -0.3 is a down-set in x (rounding is monotonic), i.e. x <= plane_lo with plane_lo the
+//     largest double that satisfies it (found on the host with the same IEEE arithmetic); same for the
+//     other three planes -> four compares, no arithmetic;
+//   * dx >= R  =>  fl(dx*dx) >= fl(R*R)  =>  fl(dx*dx + dy*dy) >= fl(R*R): no touch, so dy is only needed
+//     inside the wall's x band; walls 1A/1B and 2A/2B share their x range.
 #define MAZE_R 0.025
-__device__ __forceinline__ bool maze_rect_touch(double x, double y, double x0, double x1, double y0, double y1) {
-    double dx = fmax(fmax(__dsub_rn(x0, x), 0.0), __dsub_rn(x, x1));
+__device__ __forceinline__ bool maze_rect_touch_y(double dx, double y, double y0, double y1) {
     double dy = fmax(fmax(__dsub_rn(y0, y), 0.0), __dsub_rn(y, y1));
     double d2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
     return d2 < (MAZE_R * MAZE_R);
 }
 __device__ __forceinline__ bool maze_touch(const EnvParams& P, double x, double y) {
-    bool planes = (__dsub_rn(x, MAZE_R) <= -0.3) || (__dadd_rn(x, MAZE_R) >= 0.3) ||
-                  (__dsub_rn(y, MAZE_R) <= -0.3) || (__dadd_rn(y, MAZE_R) >= 0.3);
-    bool walls = false;
-#pragma unroll
-    for (int w = 0; w < 4; ++w) walls = walls || maze_rect_touch(x, y, P.wx0[w], P.wx1[w], P.wy0[w], P.wy1[w]);
-    return planes || walls;
+    if ((x <= P.plane_lo) || (x >= P.plane_hi) || (y <= P.plane_lo) || (y >= P.plane_hi)) return true;
+    const double dx1 = fmax(fmax(__dsub_rn(P.wx0[0], x), 0.0), __dsub_rn(x, P.wx1[0]));
+    const double dx2 = fmax(fmax(__dsub_rn(P.wx0[2], x), 0.0), __dsub_rn(x, P.wx1[2]));
+    bool hit = false;
+    if (dx1 < MAZE_R) hit = maze_rect_touch_y(dx1, y, P.wy0[0], P.wy1[0]) || maze_rect_touch_y(dx1, y, P.wy0[1], P.wy1[1]);
+    if (dx2 < MAZE_R) hit = hit || maze_rect_touch_y(dx2, y, P.wy0[2], P.wy1[2]) || maze_rect_touch_y(dx2, y, P.wy0[3], P.wy1[3]);
+    return hit;
 }
 // conservative: can a disc starting at (x,y) and moving at most `reach` per axis touch anything?
 __device__ __forceinline__ bool maze_may_touch(double x, double y, double reach) {
@@ -110,7 +120,8 @@ env_step_kernel(EnvParams P, const float* __restrict__ a_task, const float* __re
                 double* __restrict__ ep_return, float* __restrict__ task_ring, int64_t task_cap,
                 float* __restrict__ cons_ring, uint8_t* __restrict__ cons_flags, int64_t cons_cap,
                 int64_t* __restrict__ counters, double* __restrict__ o_next, double* __restrict__ o_reward,
-                uint8_t* __restrict__ o_done, uint8_t* __restrict__ o_cons, uint8_t* __restrict__ o_succ) {
+                uint8_t* __restrict__ o_done, uint8_t* __restrict__ o_cons, uint8_t* __restrict__ o_succ,
+                const double* __restrict__ a_f64) {
     const int64_t n = P.cfg.n_envs;
     const int kind = P.cfg.kind;
     const uint64_t vstep = (uint64_t)counters[RRL_C_VEC_STEP];
@@ -130,6 +141,9 @@ env_step_kernel(EnvParams P, const float* __restrict__ a_task, const float* __re
             if (kind != RRL_ENV_MAZE) {
                 // E1: process_action  np.clip(a, -1, 1) stays fp32
                 const float cx = fminf(fmaxf(ar.x, -1.0f), 1.0f), cy = fminf(fmaxf(ar.y, -1.0f), 1.0f);
+                // fp64 actions (offline-data generators: np.clip(np.random.randn(2), -1, 1)) stay fp64
+                const double dax = a_f64 ? fmin(fmax(a_f64[2 * i], -1.0), 1.0) : (double)cx;
+                const double day = a_f64 ? fmin(fmax(a_f64[2 * i + 1], -1.0), 1.0) : (double)cy;
                 if (nav_obstacle(kind, sx, sy)) {  // E2: stuck inside an obstacle
                     nx = sx;
                     ny = sy;
@@ -142,8 +156,8 @@ env_step_kernel(EnvParams P, const float* __restrict__ a_task, const float* __re
                         Philox4 p = rrl_philox(P.cfg.seed, (uint32_t)P.cfg.stream_id, (uint64_t)i, vstep, RRL_DRAW_ENV_NOISE);
                         rrl_normal2_f64(p, &e0, &e1);
                     }
-                    nx = __dadd_rn(__dadd_rn(sx, (double)cx), __dmul_rn(0.05, e0));
-                    ny = __dadd_rn(__dadd_rn(sy, (double)cy), __dmul_rn(0.05, e1));
+                    nx = __dadd_rn(__dadd_rn(sx, dax), __dmul_rn(0.05, e0));
+                    ny = __dadd_rn(__dadd_rn(sy, day), __dmul_rn(0.05, e1));
                 }
                 // E3: -||GOAL - s|| on the PRE-step state; ddot accumulates with one FMA
                 const double cost = -sqrt(__fma_rn(sy, sy, __dmul_rn(sx, sx)));
@@ -154,8 +168,10 @@ env_step_kernel(EnvParams P, const float* __restrict__ a_task, const float* __re
             } else {
                 // E8: maze.  clip in fp32 to float32(0.1), then ctrl is fp64
                 const float cx = fminf(fmaxf(ar.x, -0.1f), 0.1f), cy = fminf(fmaxf(ar.y, -0.1f), 0.1f);
-                const double fbx = __dmul_rn(P.c_b, __dmul_rn(P.gear, (double)cx));
-                const double fby = __dmul_rn(P.c_b, __dmul_rn(P.gear, (double)cy));
+                const double dax = a_f64 ? fmin(fmax(a_f64[2 * i], -0.1), 0.1) : (double)cx;
+                const double day = a_f64 ? fmin(fmax(a_f64[2 * i + 1], -0.1), 0.1) : (double)cy;
+                const double fbx = __dmul_rn(P.c_b, __dmul_rn(P.gear, dax));
+                const double fby = __dmul_rn(P.c_b, __dmul_rn(P.gear, day));
                 double x = sx, y = sy, vx = 0.0, vy = 0.0;
                 bool contact = false;
                 const int nsub = P.cfg.maze_substeps;
@@ -169,7 +185,12 @@ env_step_kernel(EnvParams P, const float* __restrict__ a_task, const float* __re
                     }
                 } else {
                     for (int k = 0; k < nsub; ++k) {
-                        if (maze_touch(P, x, y)) {  // collision phase precedes integration; contact freezes the disc
+                        // collision phase precedes integration; contact freezes the disc.  Integer pre-filter on
+                        // the high words of |x|, |y| (monotone in the value): the exact fp64 test runs only when
+                        // the disc centre is within 0.03 of a plane or inside the 0.06-wide band around a wall.
+                        const int hx = __double2hiint(x) & 0x7fffffff, hy = __double2hiint(y) & 0x7fffffff;
+                        const bool near = (max(hx, hy) >= P.hi_plane) || (hx >= P.hi_band_lo && hx <= P.hi_band_hi);
+                        if (near && maze_touch(P, x, y)) {
                             contact = true;
                             break;
                         }
@@ -218,7 +239,7 @@ env_step_kernel(EnvParams P, const float* __restrict__ a_task, const float* __re
                 rec[1] = make_float4(constraint ? 1.0f : 0.0f, fnx, fny, mask);
                 cons_flags[slot] = constraint ? 1 : 2;  // bit0: pos_idx != 0, bit1: (1 - pos_idx) != 0
             }
-            if (done_h) {
+            if (done_h && !(P.cfg.flags & RRL_ENV_NO_AUTO_RESET)) {
                 ep_end = true;
                 viol = constraint;
                 succ_end = success;
@@ -287,11 +308,28 @@ EnvParams make_params(const rrl_env_config_t* cfg) {
         P.wy0[w] = cy[w] - 0.2;
         P.wy1[w] = cy[w] + 0.2;
     }
+    // exact thresholds of the plane tests (see maze_touch): walk to the boundary of the monotone predicate
+    {
+        double c = -0.3 + MAZE_R;
+        while (c - MAZE_R <= -0.3) c = nextafter(c, 1.0);
+        while (!(c - MAZE_R <= -0.3)) c = nextafter(c, -1.0);
+        P.plane_lo = c;  // largest x with fl(x - R) <= -0.3
+        c = 0.3 - MAZE_R;
+        while (c + MAZE_R >= 0.3) c = nextafter(c, -1.0);
+        while (!(c + MAZE_R >= 0.3)) c = nextafter(c, 1.0);
+        P.plane_hi = c;  // smallest x with fl(x + R) >= 0.3
+    }
+    {
+        auto hi = [](double v) { uint64_t b; memcpy(&b, &v, 8); return (int)(b >> 32); };
+        P.hi_plane = hi(0.27);      // |x| < 0.27 (by high word)  =>  |x| + R < 0.3: no plane contact
+        P.hi_band_lo = hi(0.069);   // outside [0.069, 0.131]  =>  distance to the wall slab [0.095,0.105] > R
+        P.hi_band_hi = hi(0.131) + 1;
+    }
     return P;
 }
 
-int grid_for(int64_t n) {
-    int64_t blocks = (n + 255) / 256;
+int grid_for(int64_t n, int threads = 256) {
+    int64_t blocks = (n + threads - 1) / threads;
     int64_t cap = (int64_t)rrl_num_sms() * 8;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
@@ -317,17 +355,19 @@ extern "C" int rrl_env_step(const rrl_env_config_t* cfg, const float* action_tas
                             int32_t* ep_steps, double* ep_return, float* task_ring, int64_t task_capacity,
                             float* cons_ring, uint8_t* cons_flags, int64_t cons_capacity, int64_t* counters,
                             double* out_next_state, double* out_reward, uint8_t* out_done, uint8_t* out_constraint,
-                            uint8_t* out_success, void* stream) {
+                            uint8_t* out_success, const double* action_real_f64, void* stream) {
     RRL_CHECK_ARG(cfg && action_task && action_real && state && ep_steps && ep_return && counters, "null argument");
     RRL_CHECK_ARG(cfg->kind >= RRL_ENV_NAV1 && cfg->kind <= RRL_ENV_MAZE, "unknown env kind");
     RRL_CHECK_ARG(cfg->n_envs > 0, "n_envs must be positive");
     RRL_CHECK_ARG(!task_ring || task_capacity >= cfg->n_envs, "task ring smaller than one vector step");
     RRL_CHECK_ARG(!cons_ring || (cons_flags && cons_capacity >= cfg->n_envs), "constraint ring too small / flags missing");
     EnvParams P = make_params(cfg);
-    env_step_kernel<<<grid_for(cfg->n_envs), 256, 0, (cudaStream_t)stream>>>(
+    // maze: 500 dependent substeps per env and divergent contact paths -> small CTAs balance the 148 SMs better
+    const int threads = cfg->kind == RRL_ENV_MAZE ? 64 : 256;
+    env_step_kernel<<<grid_for(cfg->n_envs, threads), threads, 0, (cudaStream_t)stream>>>(
         P, action_task, action_real, recovery, noise, reset_draws, state, ep_steps, ep_return, task_ring,
         task_capacity > 0 ? task_capacity : 1, cons_ring, cons_flags, cons_capacity > 0 ? cons_capacity : 1, counters,
-        out_next_state, out_reward, out_done, out_constraint, out_success);
+        out_next_state, out_reward, out_done, out_constraint, out_success, action_real_f64);
     RRL_CHECK_LAUNCH();
     return 0;
 }

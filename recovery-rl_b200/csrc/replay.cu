@@ -287,7 +287,8 @@ replay_sample_kernel(rrl_sample_config_t cfg, const float* __restrict__ ring, co
     if (cfg.gate_mode == 1) open = len > B;
     if (cfg.gate_mode == 2) {
         const int64_t viols = counters[RRL_C_NUM_VIOLS] + counters[RRL_C_OFFLINE_VIOLS] + counters[RRL_C_EXT_VIOLS];
-        open = (len > B) && ((double)viols / (double)B > cfg.gate_pos_fraction);
+        // nested inside `if len(self.memory) > batch_size` (experiment.py:397): needs the task ring gate too
+        open = (counters[RRL_C_TASK_LEN] > B) && (len > B) && ((double)viols / (double)B > cfg.gate_pos_fraction);
     }
     int rows = 0;
     if (open) {

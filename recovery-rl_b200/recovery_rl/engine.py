@@ -1,0 +1,324 @@
+"""VecEngine -- the vectorised Recovery RL training step on one GPU (one process per GPU).
+
+One `step()` is what recovery_rl/experiment.py:396-452 does for one env step, for N env copies at once:
+
+    [len(memory) > batch_size]   SAC.update_parameters            (sac.py:170-277)
+    [Q_risk online gate]         QRiskWrapper.update_parameters   (qrisk.py:86-182)
+    get_action                   policy -> Q_risk threshold -> recovery policy   (experiment.py:546-577)
+    env.step + both memory.push  (env/*.py, replay_memory.py:21-25,47-52) + episode statistics
+
+Everything lives in HBM; every call below only ENQUEUES kernels of librrl.so on the current stream, all
+data-dependent control flow (gates, effective batch rows, ring positions) is read from the device counter
+block, so the whole step is captured once into a CUDA graph and replayed.  With world_size > 1 each rank
+owns N/world env copies and its own replay shards; gradients are summed with one NCCL all-reduce per
+optimizer step over the flat gradient block (1/world applied inside Adam).
+"""
+import numpy as np
+import torch
+
+from . import native
+from .arena import AgentArena
+
+HORIZON = {"navigation1": 100, "navigation2": 100, "maze": 100}
+ACTION_SCALE = {"navigation1": 1.0, "navigation2": 1.0, "maze": float(np.float32(0.1))}
+FLAG_CHUNK = 512
+
+
+class VecEngine(object):
+    def __init__(self, env_name, num_envs, batch_size=256, replay_size=1000000, safe_replay_size=1000000,
+                 gamma=0.99, alpha=0.2, tau=0.005, lr=3e-4, gamma_safe=0.5, tau_safe=0.0002, eps_safe=0.1,
+                 target_update_interval=1, use_recovery=True, mf_recovery=True, pos_fraction=-1.0,
+                 disable_online_updates=False, constraint_reward_penalty=0.0, start_steps=100, seed=0,
+                 device="cuda:0", rank=0, world_size=1, process_group=None, host_inputs=False, log_outputs=False,
+                 use_tensor_cores=0, maze_substeps=500):
+        native.require_cuda()
+        self.device = torch.device(device)
+        torch.cuda.set_device(self.device)
+        self.env_name = env_name
+        self.kind = native.ENV_KIND[env_name]
+        self.n = int(num_envs)
+        self.B = int(batch_size)
+        self.rank, self.world = int(rank), int(world_size)
+        self.pg = process_group
+        self.seed = int(seed)
+        self.use_recovery = bool(use_recovery)
+        self.mf_recovery = bool(mf_recovery)
+        self.online_qrisk = self.use_recovery and not disable_online_updates
+        self.gate_pos_fraction = float(pos_fraction)                          # experiment.py:410
+        self.pos_fraction = pos_fraction if pos_fraction >= 0 else None        # qrisk.py:77
+        self.start_steps = int(start_steps)
+        self.host_inputs = bool(host_inputs)
+        self.log_outputs = bool(log_outputs) or self.host_inputs
+        sc = ACTION_SCALE[env_name]
+        self.agent = AgentArena(self.device, max_batch=self.B, gamma=gamma, alpha=alpha, tau=tau, lr=lr,
+                                gamma_safe=gamma_safe, tau_safe=tau_safe, eps_safe=eps_safe,
+                                target_update_interval=target_update_interval, mf_recovery=mf_recovery,
+                                action_scale=(sc, sc), grad_scale=1.0 / self.world,
+                                use_tensor_cores=use_tensor_cores)
+        self.cfg = self.agent.cfg
+        self.arena = self.agent.arena
+        self.counters = self.agent.counters
+        self.env_cfg = native.env_config(self.kind, self.n, horizon=HORIZON[env_name],
+                                         reward_penalty=constraint_reward_penalty, seed=self.seed, stream_id=self.rank,
+                                         maze_substeps=maze_substeps)
+        dev = self.device
+        n = self.n
+        self.task_cap = max(int(replay_size), n)
+        self.cons_cap = (max(int(safe_replay_size), n) + 15) // 16 * 16
+        self.state = torch.zeros(2, n, dtype=torch.float64, device=dev)
+        self.ep_steps = torch.zeros(n, dtype=torch.int32, device=dev)
+        self.ep_return = torch.zeros(n, dtype=torch.float64, device=dev)
+        self.action_task = torch.zeros(n, 2, device=dev)
+        self.action_real = torch.zeros(n, 2, device=dev)
+        self.recovery = torch.zeros(n, dtype=torch.uint8, device=dev)
+        self.qrisk = torch.zeros(n, device=dev)
+        self.task_ring = torch.zeros(self.task_cap, 8, device=dev)
+        self.cons_ring = torch.zeros(self.cons_cap, 8, device=dev)
+        self.cons_flags = torch.zeros(self.cons_cap, dtype=torch.uint8, device=dev)
+        self.n_chunks = (self.cons_cap + FLAG_CHUNK - 1) // FLAG_CHUNK
+        self.chunk_counts = torch.zeros(2, self.n_chunks, dtype=torch.int32, device=dev)
+        # ONE CPython-compatible MT19937 stream shared by both buffers (replay_memory.py:16,41); every rank
+        # gets its own stream (seed + rank) so that shards draw different batches
+        self.mt_state = native.mt19937_seed(self.seed + self.rank).to(dev)
+        self.losses = torch.zeros(16, device=dev)
+        self.sac_sample_cfg = native.sample_config(self.task_cap, self.B, False, None, gate_mode=1)
+        self.qr_sample_cfg = native.sample_config(self.cons_cap, self.B, True, self.pos_fraction, gate_mode=2,
+                                                  chunk=FLAG_CHUNK, gate_pos_fraction=self.gate_pos_fraction)
+        # per-step outputs (logging schema of experiment.py:421 / run_stats.pkl), only when asked for
+        if self.log_outputs:
+            self.out_next = torch.zeros(2, n, dtype=torch.float64, device=dev)
+            self.out_reward = torch.zeros(n, dtype=torch.float64, device=dev)
+            self.out_done = torch.zeros(n, dtype=torch.uint8, device=dev)
+            self.out_cons = torch.zeros(n, dtype=torch.uint8, device=dev)
+            self.out_succ = torch.zeros(n, dtype=torch.uint8, device=dev)
+        else:
+            self.out_next = self.out_reward = self.out_done = self.out_cons = self.out_succ = None
+        # host-supplied randomness (parity / end-to-end mode): device staging + pinned host buffers
+        if self.host_inputs:
+            B = self.B
+            self.in_dev = dict(
+                reset_draws=torch.zeros(2, n, dtype=torch.float64, device=dev),
+                env_noise=torch.zeros(2, n, dtype=torch.float64, device=dev) if self.kind != native.ENV_MAZE else None,
+                eps_task=torch.zeros(n, 2, device=dev), eps_rec=torch.zeros(n, 2, device=dev),
+                rand_u=torch.zeros(n, 2, device=dev),
+                sac_eps_next=torch.zeros(B, 2, device=dev), sac_eps_cur=torch.zeros(B, 2, device=dev),
+                qr_eps_next=torch.zeros(B, 2, device=dev), qr_eps_rec=torch.zeros(B, 2, device=dev))
+            self.in_host = {k: torch.zeros(v.shape, dtype=v.dtype).pin_memory() for k, v in self.in_dev.items()
+                            if v is not None}
+            self.out_host = dict(
+                losses=torch.zeros(16).pin_memory(), counters=torch.zeros(native.NUM_COUNTERS, dtype=torch.int64).pin_memory(),
+                next_state=torch.zeros(2, n, dtype=torch.float64).pin_memory(), reward=torch.zeros(n, dtype=torch.float64).pin_memory(),
+                done=torch.zeros(n, dtype=torch.uint8).pin_memory(), constraint=torch.zeros(n, dtype=torch.uint8).pin_memory(),
+                success=torch.zeros(n, dtype=torch.uint8).pin_memory(), recovery=torch.zeros(n, dtype=torch.uint8).pin_memory(),
+                action=torch.zeros(n, 2).pin_memory())
+        else:
+            self.in_dev = {}
+        self.graph = None
+        self.launches_per_step = 0
+        self._grad_views = None
+
+    # ------------------------------------------------------------------------------------------
+    def _in(self, name):
+        return self.in_dev.get(name) if self.host_inputs else None
+
+    def h2d_bytes_per_step(self):
+        return sum(v.numel() * v.element_size() for v in self.in_host.values()) if self.host_inputs else 0
+
+    def d2h_bytes_per_step(self):
+        return sum(v.numel() * v.element_size() for v in self.out_host.values()) if self.host_inputs else 0
+
+    def init_agent(self, modules=None):
+        """xavier init in the reference's construction order (draws from the torch global RNG), identical on
+        every rank when the torch seed is."""
+        if modules is None:
+            from .model import build_reference_modules
+            sc = ACTION_SCALE[self.env_name]
+            modules = build_reference_modules(hidden=256, action_scale=(sc, sc))
+        self.agent.load_modules(modules)
+
+    def reset(self, draws=None):
+        """env.reset() for every env copy (experiment.py:383)."""
+        native.env_reset(self.env_cfg, self.state, self.ep_steps, self.ep_return, self.counters, draws=draws)
+
+    def push_offline(self, transitions):
+        """pretrain_critic_recovery: recovery_memory.push(*transition) for the demos (experiment.py:277-282)."""
+        rec = np.zeros((len(transitions), 8), np.float32)
+        for i, t in enumerate(transitions):
+            rec[i, 0:2] = t[0]; rec[i, 2:4] = t[1]; rec[i, 4] = float(t[2]); rec[i, 5:7] = t[3]; rec[i, 7] = float(t[4])
+        self.push_offline_records(rec)
+
+    def push_offline_records(self, rec):
+        rec = np.ascontiguousarray(rec, np.float32)
+        n = len(rec)
+        if n == 0:
+            return
+        native.replay_push(self.cons_ring, self.cons_cap, torch.from_numpy(rec).to(self.device), n, self.counters,
+                           cons_flags=self.cons_flags)
+        self.counters[native.C_OFFLINE_VIOLS] += int((rec[:, 4] != 0).sum())
+
+    # ---- one Q_risk (+ recovery policy) update -----------------------------------------------------
+    def _all_reduce(self, net_names):
+        if self.world == 1:
+            return
+        import torch.distributed as dist
+        if self._grad_views is None:
+            self._grad_views = {}
+            for name in ("critic", "policy", "qrisk", "recovery"):
+                off, cnt = native.agent_grad_range(self.cfg, native.NET_NAMES.index(name))
+                self._grad_views[name] = (off, cnt)
+        lo = min(self._grad_views[nm][0] for nm in net_names)
+        hi = max(self._grad_views[nm][0] + self._grad_views[nm][1] for nm in net_names)
+        dist.all_reduce(self.arena[lo:hi], op=dist.ReduceOp.SUM, group=self.pg)
+
+    def _sync_gate_counts(self):
+        """multi-GPU: the Q_risk online gate (experiment.py:407-410) must open on every rank at once, so it
+        sees the global violation count: EXT_VIOLS = sum over the other ranks of (num_viols + offline)."""
+        if self.world == 1:
+            return
+        import torch.distributed as dist
+        local = (self.counters[native.C_NUM_VIOLS] + self.counters[native.C_OFFLINE_VIOLS]).reshape(1).clone()
+        total = local.clone()
+        dist.all_reduce(total, op=dist.ReduceOp.SUM, group=self.pg)
+        self.counters[native.C_EXT_VIOLS:native.C_EXT_VIOLS + 1] = total - local
+
+    def qrisk_update(self, sample_cfg=None, count=True):
+        cfg, ar, cn = self.cfg, self.arena, self.counters
+        sc = sample_cfg or self.qr_sample_cfg
+        k = 0
+        if sc.pos_fraction >= 0:
+            native.replay_flag_count(self.cons_flags, self.cons_cap, FLAG_CHUNK, self.chunk_counts); k += 1
+        a = self.agent
+        native.replay_sample(sc, self.cons_ring, self.mt_state, cn, native.C_QRISK_ROWS, a.scratch("qr_s"),
+                             a.scratch("qr_a"), a.scratch("qr_c"), a.scratch("qr_s2"), a.scratch("qr_m"),
+                             cons_flags=self.cons_flags, chunk_counts=self.chunk_counts); k += 1
+        native.qrisk_backward(cfg, ar, cn, self.losses[8:], self._in("qr_eps_next"), seed=self.seed, stream_id=self.rank); k += 6
+        self._all_reduce(["qrisk"])
+        native.qrisk_apply(cfg, ar, cn); k += 2
+        native.recovery_backward(cfg, ar, cn, self.losses[8:], self._in("qr_eps_rec"), seed=self.seed, stream_id=self.rank)
+        self._all_reduce(["recovery"])
+        native.recovery_apply(cfg, ar, cn)
+        k += (10 if self.mf_recovery else 0) + (3 if self.mf_recovery else 2)
+        return k
+
+    def sac_update(self):
+        cfg, ar, cn, a = self.cfg, self.arena, self.counters, self.agent
+        native.replay_sample(self.sac_sample_cfg, self.task_ring, self.mt_state, cn, native.C_SAC_ROWS,
+                             a.scratch("sac_s"), a.scratch("sac_a"), a.scratch("sac_r"), a.scratch("sac_s2"),
+                             a.scratch("sac_m"))
+        native.sac_backward(cfg, ar, cn, self.losses, self._in("sac_eps_next"), self._in("sac_eps_cur"), seed=self.seed,
+                            stream_id=self.rank)
+        self._all_reduce(["critic", "policy"])
+        native.sac_apply(cfg, ar, cn)
+        return 1 + 10 + 3
+
+    def pretrain_qrisk(self, steps, n_demos=None):
+        """experiment.py:289-296: critic_safe_pretraining_steps x QRiskWrapper.update_parameters with
+        batch_size = min(batch_size, len(constraint_demo_data)); no gate."""
+        b = self.B if n_demos is None else min(self.B, int(n_demos))
+        sc = native.sample_config(self.cons_cap, b, True, self.pos_fraction, gate_mode=0, chunk=FLAG_CHUNK)
+        for _ in range(int(steps)):
+            self.qrisk_update(sc)
+
+    # ---- the vector step -------------------------------------------------------------------------
+    def _enqueue_step(self):
+        k = 0
+        k += self.sac_update()                                                     # experiment.py:397-406
+        if self.online_qrisk:
+            self._sync_gate_counts()
+            k += self.qrisk_update()                                               # experiment.py:407-415
+        native.agent_act(self.cfg, self.arena, self.n, self.state, self.counters, self.action_task, self.action_real,
+                         self.recovery, self.qrisk, self._in("eps_task"), self._in("eps_rec"), self._in("rand_u"),
+                         use_recovery=self.use_recovery, start_steps=self.start_steps, seed=self.seed,
+                         stream_id=self.rank)                                      # experiment.py:419
+        native.env_step(self.env_cfg, self.action_task, self.action_real, self.state, self.ep_steps, self.ep_return,
+                        self.counters, recovery=self.recovery, noise=self._in("env_noise"),
+                        reset_draws=self._in("reset_draws"), task_ring=self.task_ring, task_capacity=self.task_cap,
+                        cons_ring=self.cons_ring if self.use_recovery else None,
+                        cons_flags=self.cons_flags if self.use_recovery else None,
+                        cons_capacity=self.cons_cap if self.use_recovery else 0, out_next_state=self.out_next,
+                        out_reward=self.out_reward, out_done=self.out_done, out_constraint=self.out_cons,
+                        out_success=self.out_succ)                                 # experiment.py:420-461
+        native.counters_advance(self.counters, self.n, self.task_cap, self.cons_cap, True, self.use_recovery)
+        self.launches_per_step = k + 3
+        return self.launches_per_step
+
+    def step(self):
+        """one vector step, eagerly enqueued."""
+        return self._enqueue_step()
+
+    def capture(self):
+        """warm up (lazy cudaFuncSetAttribute calls must happen outside capture) and record the step."""
+        saved = self.snapshot()
+        self._enqueue_step()
+        torch.cuda.synchronize()
+        self.restore(saved)
+        try:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._enqueue_step()
+            self.graph = g
+        except Exception as ex:     # e.g. a collective that cannot be captured: keep the eager path
+            self.graph = None
+            self.capture_error = repr(ex)
+            torch.cuda.synchronize()
+        self.restore(saved)
+        return self.graph
+
+    def replay(self):
+        if self.graph is None:
+            self._enqueue_step()
+        else:
+            self.graph.replay()
+
+    # ---- host-buffer step (end-to-end face) --------------------------------------------------------
+    def step_host(self, inputs):
+        """inputs: dict of host arrays for this step's random draws (see self.in_host).  Uploads them from
+        pinned memory, runs the step, downloads losses / counters / per-env outputs into pinned buffers."""
+        assert self.host_inputs
+        for k, h in self.in_host.items():
+            src = h
+            if inputs is not None and k in inputs:
+                x = inputs[k]
+                if torch.is_tensor(x) and x.is_pinned() and x.shape == h.shape and x.dtype == h.dtype:
+                    src = x                                   # caller's own pinned buffer: no staging copy
+                else:
+                    h.copy_(torch.as_tensor(x).reshape(h.shape))
+            self.in_dev[k].copy_(src, non_blocking=True)
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._enqueue_step()
+        o = self.out_host
+        o["losses"].copy_(self.losses, non_blocking=True)
+        o["counters"].copy_(self.counters, non_blocking=True)
+        o["next_state"].copy_(self.out_next, non_blocking=True)
+        o["reward"].copy_(self.out_reward, non_blocking=True)
+        o["done"].copy_(self.out_done, non_blocking=True)
+        o["constraint"].copy_(self.out_cons, non_blocking=True)
+        o["success"].copy_(self.out_succ, non_blocking=True)
+        o["recovery"].copy_(self.recovery, non_blocking=True)
+        o["action"].copy_(self.action_real, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return o
+
+    # ---- state snapshots (capture warm-up, tests) -----------------------------------------------------
+    def snapshot(self):
+        return dict(arena=self.arena.clone(), counters=self.counters.clone(), state=self.state.clone(),
+                    ep_steps=self.ep_steps.clone(), ep_return=self.ep_return.clone(), mt=self.mt_state.clone(),
+                    flags=self.cons_flags.clone())
+
+    def restore(self, s):
+        self.arena.copy_(s["arena"]); self.counters.copy_(s["counters"]); self.state.copy_(s["state"])
+        self.ep_steps.copy_(s["ep_steps"]); self.ep_return.copy_(s["ep_return"]); self.mt_state.copy_(s["mt"])
+        self.cons_flags.copy_(s["flags"])
+
+    def read_counters(self):
+        c = self.counters.cpu().numpy()
+        names = dict(total_numsteps=native.C_TOTAL_NUMSTEPS, episodes=native.C_EPISODES, num_viols=native.C_NUM_VIOLS,
+                     num_successes=native.C_NUM_SUCCESSES, viol_and_recovery=native.C_VIOL_RECOVERY,
+                     viol_and_no_recovery=native.C_VIOL_NO_RECOV, offline_viols=native.C_OFFLINE_VIOLS,
+                     vec_steps=native.C_VEC_STEP, sac_updates=native.C_SAC_UPDATES, qrisk_updates=native.C_QRISK_UPDATES,
+                     task_len=native.C_TASK_LEN, cons_len=native.C_CONS_LEN, error=native.C_ERROR)
+        out = {k: int(c[v]) for k, v in names.items()}
+        out["return_sum"] = float(c[native.C_RETURN_SUM_BITS:native.C_RETURN_SUM_BITS + 1].view(np.float64)[0])
+        return out

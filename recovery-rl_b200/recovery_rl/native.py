@@ -30,7 +30,7 @@ NET_NAMES = ["critic", "critic_target", "policy", "qrisk", "qrisk_target", "reco
 class EnvConfig(C.Structure):
     _fields_ = [("kind", C.c_int32), ("horizon", C.c_int32), ("n_envs", C.c_int64),
                 ("reward_penalty", C.c_double), ("seed", C.c_uint64), ("stream_id", C.c_int32),
-                ("maze_substeps", C.c_int32)]
+                ("maze_substeps", C.c_int32), ("flags", C.c_int32), ("reserved", C.c_int32)]
 
 
 class SampleConfig(C.Structure):
@@ -107,9 +107,13 @@ def version():
 # ------------------------------------------------------------------------------------------------
 # environments
 # ------------------------------------------------------------------------------------------------
-def env_config(kind, n_envs, horizon=100, reward_penalty=0.0, seed=0, stream_id=0, maze_substeps=500):
+ENV_NO_AUTO_RESET = 1
+
+
+def env_config(kind, n_envs, horizon=100, reward_penalty=0.0, seed=0, stream_id=0, maze_substeps=500,
+               auto_reset=True):
     return EnvConfig(kind, horizon, n_envs, float(reward_penalty), seed & 0xFFFFFFFFFFFFFFFF, stream_id,
-                     maze_substeps)
+                     maze_substeps, 0 if auto_reset else ENV_NO_AUTO_RESET, 0)
 
 
 def env_reset(cfg, state, ep_steps=None, ep_return=None, counters=None, mask=None, draws=None, stream=None):
@@ -120,13 +124,14 @@ def env_reset(cfg, state, ep_steps=None, ep_return=None, counters=None, mask=Non
 def env_step(cfg, action_task, action_real, state, ep_steps, ep_return, counters, recovery=None, noise=None,
              reset_draws=None, task_ring=None, task_capacity=0, cons_ring=None, cons_flags=None, cons_capacity=0,
              out_next_state=None, out_reward=None, out_done=None, out_constraint=None, out_success=None,
-             stream=None):
+             action_f64=None, stream=None):
     _check(lib().rrl_env_step(C.byref(cfg), p(action_task, "f32"), p(action_real, "f32"), p(recovery, "u8"),
                               p(noise, "f64"), p(reset_draws, "f64"), p(state, "f64"), p(ep_steps, "i32"),
                               p(ep_return, "f64"), p(task_ring, "f32"), C.c_int64(task_capacity),
                               p(cons_ring, "f32"), p(cons_flags, "u8"), C.c_int64(cons_capacity), p(counters, "i64"),
                               p(out_next_state, "f64"), p(out_reward, "f64"), p(out_done, "u8"),
-                              p(out_constraint, "u8"), p(out_success, "u8"), _stream(stream)), "rrl_env_step")
+                              p(out_constraint, "u8"), p(out_success, "u8"), p(action_f64, "f64"), _stream(stream)),
+           "rrl_env_step")
 
 
 def counters_advance(counters, n, task_capacity, cons_capacity, push_task=True, push_cons=True, stream=None):

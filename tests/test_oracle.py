@@ -102,3 +102,48 @@ def test_replay_streams_match_reference(golden_dir, name):
             ci.append(cm.buf[sl, 0].astype(np.int64))
     assert np.array_equal(np.concatenate(ti), z[name + "_task_ids"])
     assert np.array_equal(np.concatenate(ci), z[name + "_cons_ids"])
+
+
+def test_maze_scalar_matches_vectorised():
+    rs = np.random.RandomState(2)
+    s = rs.uniform(-0.28, 0.28, (300, 2))
+    s[:100, 0] = -0.1 + rs.uniform(-0.05, 0.05, 100)
+    a = rs.uniform(-0.12, 0.12, (300, 2)).astype(np.float32)
+    steps = rs.randint(0, 100, 300)
+    ns, r, d, c, su = envs.maze_step(s, a, steps)
+    for i in range(300):
+        o = envs.maze_step_scalar(s[i], a[i], int(steps[i]))
+        assert np.array_equal(o[0], ns[i]) and o[1] == r[i] and o[2] == d[i] and o[3] == c[i] and o[4] == su[i]
+
+
+def test_oracle_loop_reproduces_reference_trajectory(golden_dir):
+    """oracle/loop.py fed the recorded noise == the reference's Experiment (12 episodes, seed 7): states,
+    flags, replay indices bit-exact; final weights to fp32 round-off."""
+    from oracle.loop import OracleExperiment, NoiseSource
+    z = np.load(os.path.join(golden_dir, "traj_nav1_seed7.npz"))
+    sizes = z["eps_sizes"]
+    offs = np.concatenate([[0], np.cumsum(sizes)])
+    eps = [z["eps"][offs[i]:offs[i + 1]] for i in range(len(sizes))]
+    noise = NoiseSource(7, eps=eps, env_noise=list(z["env_noise"]), rand_actions=list(z["rand_actions"]))
+    exp = OracleExperiment("navigation1", seed=7, batch_size=16, gamma_safe=0.8, eps_safe=0.3, noise=noise)
+    tr = [(z["offline_state"][i], z["offline_action"][i], z["offline_constraint"][i], z["offline_next_state"][i],
+           z["offline_mask"][i]) for i in range(len(z["offline_state"]))]
+    exp.pretrain(tr, 30, num_unsafe_transitions=2000)
+    assert len(exp.idx_log) == int(z["n_pre_idx"])
+    infos = []
+    for _ in range(int(z["ep_len"].sum())):
+        infos.append(exp.step())
+    assert np.array_equal(np.array([i["state"] for i in infos]), z["state"])
+    assert np.array_equal(np.array([i["next_state"] for i in infos]), z["next_state"])
+    assert np.array_equal(np.array([i["action"] for i in infos], np.float32), z["action"])
+    assert np.array_equal(np.array([i["constraint"] for i in infos]), z["constraint"])
+    assert np.array_equal(np.array([i["recovery"] for i in infos]), z["recovery"].astype(bool))
+    ends = np.cumsum(z["ep_len"]) - 1
+    assert [i for i, x in enumerate(infos) if x["episode_end"]] == list(ends)
+    assert np.array_equal(np.concatenate(exp.idx_log), z["idx"])
+    assert exp.num_viols == int(z["num_viols"]) and exp.num_successes == int(z["num_successes"])
+    assert exp.total_numsteps == int(z["total_numsteps"]) and exp.updates == int(z["updates"])
+    stride = int(z["stride"])
+    for net in ("critic", "critic_target", "policy", "qrisk", "qrisk_target", "recovery"):
+        for i, p in enumerate(exp.agent.params(net)):
+            assert np.allclose(p.ravel()[::stride], z["final_%s_%d" % (net, i)], rtol=0, atol=0)

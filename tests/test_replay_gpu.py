@@ -89,7 +89,8 @@ def test_gates_and_stream_not_advanced_when_closed(native, cuda):
     assert rows == 256 and not torch.equal(mt0, g.mt)
     st = oreplay.MT19937(9)
     assert np.array_equal(idx, st.sample_indices(257, 256))
-    # Q_risk gate: (num_viols + offline_viols)/B > pos_fraction (experiment.py:407-410)
+    # Q_risk gate: (num_viols + offline_viols)/B > pos_fraction (experiment.py:407-410), nested in the SAC gate
+    g.cnt[native.C_TASK_LEN] = 257
     mt1 = g.mt.clone()
     rows, _, _ = g.sample(256, True, None, gate_mode=2, gate_pf=0.3)
     assert rows == 0 and torch.equal(mt1, g.mt)
