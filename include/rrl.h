@@ -160,7 +160,7 @@ typedef struct {
     int32_t target_update_interval;        /* arg_utils.py:39-43                            */
     int32_t mf_recovery;                   /* qrisk.py:150                                  */
     float grad_scale;                      /* 1/world_size applied inside Adam              */
-    int32_t use_tensor_cores;              /* act kernel: 0 = fp32 FFMA, 1 = tcgen05 bf16x3 */
+    int32_t use_tensor_cores;              /* act kernel: 0 = fp32 FFMA, 1 = tcgen05 fp16 hi/lo split (3 MMAs) */
 } rrl_agent_config_t;
 
 /* Arena layout (fp32 elements).  Tensors of every net follow torch's parameters() order of the
@@ -179,6 +179,10 @@ int rrl_agent_scratch_info(const rrl_agent_config_t* cfg, const char* name, int6
  * kernels stream) after the host wrote parameters into the arena (e.g. the xavier init of
  * model.py:23-26 or a checkpoint load).  The update kernels keep them fresh themselves. */
 int rrl_agent_refresh(const rrl_agent_config_t* cfg, float* arena, void* stream);
+
+/* Rebuild only the fp16 hi/lo operand images the tensor-core acting kernel streams (policy, Q_risk twin,
+ * recovery policy); call after an optimizer step when cfg->use_tensor_cores is set. */
+int rrl_agent_tc_refresh(const rrl_agent_config_t* cfg, float* arena, void* stream);
 
 /* Composite action selection for N envs (experiment.py:546-577; sac.py:133-168;
  * qrisk.py:184-213; model.py:317-338, 512-525):

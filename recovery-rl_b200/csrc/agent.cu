@@ -7,7 +7,7 @@
 // All four MLPs are 2x256-hidden: the first layer (K = 2 or 4) and the heads (N = 1..4) are SIMT
 // prologue/epilogue of the one 256x256 contraction, which is a shared-memory tiled fp32 GEMM here
 // (agent_tc.cu holds the tcgen05 version of the same contraction for the large-N acting kernel).
-#include "agent_layout.cuh"
+#include "agent_common.cuh"
 
 using namespace rrl;
 
@@ -16,13 +16,6 @@ namespace {
 constexpr int kThreads = 256;
 constexpr int KC = 16;  // k-chunk of the streamed operand
 
-enum Head { HEAD_Q = 0, HEAD_QRISK = 1, HEAD_GAUSS = 2, HEAD_STOCH = 3 };
-
-#define LOG_SIG_MAX 2.0f
-#define LOG_SIG_MIN (-20.0f)
-#define MIN_LOG_STD (-13.815510557964274f) /* np.log(1e-6), model.py:499 */
-#define HALF_LOG_2PI 0.9189385332046727f   /* math.log(math.sqrt(2*math.pi)) */
-
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
     unsigned s = (unsigned)__cvta_generic_to_shared(smem);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
@@ -30,54 +23,6 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
-
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
-
-// ---------------------------------------------------------------------------------------------
-// weights of one single-head MLP (pointers into the arena)
-// ---------------------------------------------------------------------------------------------
-struct HeadW {
-    const float *W1, *b1, *W2, *W2T, *b2, *W3a, *b3a, *W3b, *b3b, *log_std;
-    int n_in, na, nb;  // inputs (2|4); rows of W3a / W3b
-};
-struct HeadG {  // gradient pointers (same shapes); NULL = not needed
-    float *W1, *b1, *W2, *b2, *W3a, *b3a, *W3b, *b3b, *log_std;
-};
-
-HeadW head_w(const Layout& L, const float* arena, int net, int head) {
-    HeadW w;
-    memset(&w, 0, sizeof(w));
-    const int64_t* t = L.t_off[net];
-    if (net == RRL_NET_POLICY) {
-        w.W1 = arena + t[0]; w.b1 = arena + t[1]; w.W2 = arena + t[2]; w.b2 = arena + t[3];
-        w.W3a = arena + t[4]; w.b3a = arena + t[5]; w.W3b = arena + t[6]; w.b3b = arena + t[7];
-        w.n_in = 2; w.na = 2; w.nb = 2;
-    } else if (net == RRL_NET_RECOVERY) {
-        w.log_std = arena + t[0];
-        w.W1 = arena + t[1]; w.b1 = arena + t[2]; w.W2 = arena + t[3]; w.b2 = arena + t[4];
-        w.W3a = arena + t[5]; w.b3a = arena + t[6];
-        w.n_in = 2; w.na = 2; w.nb = 0;
-    } else {
-        const int b = ((net == RRL_NET_QRISK || net == RRL_NET_QRISK_TARGET) ? 2 : 0) + 6 * head;
-        w.W1 = arena + t[b]; w.b1 = arena + t[b + 1]; w.W2 = arena + t[b + 2]; w.b2 = arena + t[b + 3];
-        w.W3a = arena + t[b + 4]; w.b3a = arena + t[b + 5];
-        w.n_in = 4; w.na = 1; w.nb = 0;
-    }
-    w.W2T = arena + L.img_off[image_index(net, head)];
-    return w;
-}
-HeadG head_g(const Layout& L, float* arena, int net, int head) {
-    HeadW w = head_w(L, arena, net, head);
-    const int64_t d = L.grad_off;  // trainable params start at offset 0 of the arena
-    HeadG g;
-    g.W1 = const_cast<float*>(w.W1) + d; g.b1 = const_cast<float*>(w.b1) + d;
-    g.W2 = const_cast<float*>(w.W2) + d; g.b2 = const_cast<float*>(w.b2) + d;
-    g.W3a = const_cast<float*>(w.W3a) + d; g.b3a = const_cast<float*>(w.b3a) + d;
-    g.W3b = w.W3b ? const_cast<float*>(w.W3b) + d : nullptr;
-    g.b3b = w.b3b ? const_cast<float*>(w.b3b) + d : nullptr;
-    g.log_std = w.log_std ? const_cast<float*>(w.log_std) + d : nullptr;
-    return g;
-}
 
 // ---------------------------------------------------------------------------------------------
 // forward tile: BM rows through one head.  Result: S.raw[m][0..n_out) = W3 h2 + b3.
@@ -235,57 +180,6 @@ __device__ void mlp_tile_forward(FwdSmem<BM>& S, const HeadW& w, float* __restri
 }
 
 // ---------------------------------------------------------------------------------------------
-// head post-processing
-// ---------------------------------------------------------------------------------------------
-struct ActionSpace {
-    float scale[2], bias[2];
-};
-
-// GaussianPolicy.sample (model.py:325-338)
-__device__ __forceinline__ void gauss_sample(const float raw[4], const float eps[2], const ActionSpace& sp, float a[2],
-                                             float* logp, float mean_a[2]) {
-    float lp = 0.f;
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        const float mean = raw[i];
-        const float ls = fminf(fmaxf(raw[2 + i], LOG_SIG_MIN), LOG_SIG_MAX);
-        const float sd = expf(ls);
-        const float x = fmaf(sd, eps[i], mean);  // rsample: loc + eps * scale
-        const float y = tanhf(x);
-        a[i] = fmaf(y, sp.scale[i], sp.bias[i]);
-        const float d = x - mean;
-        float l = -(d * d) / (2.0f * (sd * sd)) - logf(sd) - HALF_LOG_2PI;  // Normal.log_prob
-        l -= logf(sp.scale[i] * (1.0f - y * y) + 1e-6f);
-        lp += l;
-        mean_a[i] = fmaf(tanhf(mean), sp.scale[i], sp.bias[i]);
-    }
-    *logp = lp;
-}
-
-// StochasticPolicy.sample (model.py:512-525)
-__device__ __forceinline__ void stoch_sample(const float raw[2], const float* log_std, const float eps[2],
-                                             const ActionSpace& sp, float a[2], float mean_a[2], float* logp) {
-    float lp = 0.f;
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        const float mean = fmaf(tanhf(raw[i]), sp.scale[i], sp.bias[i]);
-        const float ls = fmaxf(log_std[i], MIN_LOG_STD);
-        const float sd = expf(ls);
-        a[i] = fmaf(sd, eps[i], mean);
-        mean_a[i] = mean;
-        const float d = a[i] - mean;
-        lp += -(d * d) / (2.0f * (sd * sd)) - logf(sd) - HALF_LOG_2PI;
-    }
-    *logp = lp;
-}
-
-__device__ __forceinline__ void philox_eps(uint64_t seed, uint32_t stream_id, uint64_t row, uint64_t step, uint32_t draw,
-                                           float e[2]) {
-    const Philox4 p = rrl_philox(seed, stream_id, row, step, draw);
-    rrl_normal2_f32(p.x, p.y, &e[0], &e[1]);
-}
-
-// ---------------------------------------------------------------------------------------------
 // grouped forward kernel (training batches and the stand-alone forward entry points)
 // ---------------------------------------------------------------------------------------------
 struct FwdPass {
@@ -362,22 +256,6 @@ __global__ void __launch_bounds__(kThreads, (BM == 64) ? 2 : 3) mlp_forward_kern
 // ---------------------------------------------------------------------------------------------
 // fused acting kernel (experiment.py:546-577): policy -> Q_risk threshold -> recovery policy -> select
 // ---------------------------------------------------------------------------------------------
-struct ActArgs {
-    HeadW pol, qr1, qr2, rec;
-    int64_t n;
-    const double* state;  // [2][n]
-    const float *eps_task, *eps_rec, *rand_u;
-    int use_recovery, eval;
-    int64_t start_steps;
-    uint64_t seed;
-    uint32_t stream_id;
-    const int64_t* counters;
-    float eps_safe;
-    ActionSpace sp;
-    float *action_task, *action_real, *qrisk_out;
-    uint8_t* recovery;
-};
-
 __global__ void __launch_bounds__(kThreads, 2) act_kernel(const __grid_constant__ ActArgs A) {
     constexpr int BM = 64;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1163,7 +1041,14 @@ extern "C" int rrl_agent_refresh(const rrl_agent_config_t* cfg, float* arena, vo
     for (int i = 0; i < 6; ++i) n += imgs_of_net(L, nets[i], A.img + n);
     refresh_images_kernel<<<dim3(H / 32, H / 32, kNumImages), kThreads, 0, (cudaStream_t)stream>>>(A);
     RRL_CHECK_LAUNCH();
-    return 0;
+    return tc_images_launch(arena, L, (cudaStream_t)stream);
+}
+
+extern "C" int rrl_agent_tc_refresh(const rrl_agent_config_t* cfg, float* arena, void* stream) {
+    CHECK_CFG(cfg);
+    RRL_CHECK_ARG(arena, "null arena");
+    const Layout L = make_layout(cfg);
+    return tc_images_launch(arena, L, (cudaStream_t)stream);
 }
 
 extern "C" int rrl_hard_update(const rrl_agent_config_t* cfg, float* arena, int dst_net, int src_net, void* stream) {
@@ -1198,6 +1083,7 @@ extern "C" int rrl_agent_act(const rrl_agent_config_t* cfg, float* arena, int64_
     A.eps_safe = cfg->eps_safe;
     A.sp = action_space(cfg);
     A.action_task = action_task; A.action_real = action_real; A.qrisk_out = qrisk_out; A.recovery = recovery;
+    if (cfg->use_tensor_cores) return act_tc_launch(A, arena, L, (cudaStream_t)stream);
     static bool configured = false;
     const size_t smem = sizeof(FwdSmem<64>);
     if (!configured) {

@@ -1,0 +1,136 @@
+// agent_common.cuh -- pieces shared by the SIMT (agent.cu) and tcgen05 (agent_tc.cu) agent kernels:
+// weight views into the arena, the head post-processing of the four network families, acting arguments.
+#pragma once
+#include "agent_layout.cuh"
+
+namespace rrl {
+
+enum Head { HEAD_Q = 0, HEAD_QRISK = 1, HEAD_GAUSS = 2, HEAD_STOCH = 3 };
+
+#define LOG_SIG_MAX 2.0f
+#define LOG_SIG_MIN (-20.0f)
+#define MIN_LOG_STD (-13.815510557964274f) /* np.log(1e-6), model.py:499 */
+#define HALF_LOG_2PI 0.9189385332046727f   /* math.log(math.sqrt(2*math.pi)) */
+
+static __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+
+// ---------------------------------------------------------------------------------------------
+// weights of one single-head MLP (pointers into the arena)
+// ---------------------------------------------------------------------------------------------
+struct HeadW {
+    const float *W1, *b1, *W2, *W2T, *b2, *W3a, *b3a, *W3b, *b3b, *log_std;
+    int n_in, na, nb;  // inputs (2|4); rows of W3a / W3b
+};
+struct HeadG {  // gradient pointers (same shapes); NULL = not needed
+    float *W1, *b1, *W2, *b2, *W3a, *b3a, *W3b, *b3b, *log_std;
+};
+
+inline HeadW head_w(const Layout& L, const float* arena, int net, int head) {
+    HeadW w;
+    memset(&w, 0, sizeof(w));
+    const int64_t* t = L.t_off[net];
+    if (net == RRL_NET_POLICY) {
+        w.W1 = arena + t[0]; w.b1 = arena + t[1]; w.W2 = arena + t[2]; w.b2 = arena + t[3];
+        w.W3a = arena + t[4]; w.b3a = arena + t[5]; w.W3b = arena + t[6]; w.b3b = arena + t[7];
+        w.n_in = 2; w.na = 2; w.nb = 2;
+    } else if (net == RRL_NET_RECOVERY) {
+        w.log_std = arena + t[0];
+        w.W1 = arena + t[1]; w.b1 = arena + t[2]; w.W2 = arena + t[3]; w.b2 = arena + t[4];
+        w.W3a = arena + t[5]; w.b3a = arena + t[6];
+        w.n_in = 2; w.na = 2; w.nb = 0;
+    } else {
+        const int b = ((net == RRL_NET_QRISK || net == RRL_NET_QRISK_TARGET) ? 2 : 0) + 6 * head;
+        w.W1 = arena + t[b]; w.b1 = arena + t[b + 1]; w.W2 = arena + t[b + 2]; w.b2 = arena + t[b + 3];
+        w.W3a = arena + t[b + 4]; w.b3a = arena + t[b + 5];
+        w.n_in = 4; w.na = 1; w.nb = 0;
+    }
+    w.W2T = arena + L.img_off[image_index(net, head)];
+    return w;
+}
+inline HeadG head_g(const Layout& L, float* arena, int net, int head) {
+    HeadW w = head_w(L, arena, net, head);
+    const int64_t d = L.grad_off;  // trainable params start at offset 0 of the arena
+    HeadG g;
+    g.W1 = const_cast<float*>(w.W1) + d; g.b1 = const_cast<float*>(w.b1) + d;
+    g.W2 = const_cast<float*>(w.W2) + d; g.b2 = const_cast<float*>(w.b2) + d;
+    g.W3a = const_cast<float*>(w.W3a) + d; g.b3a = const_cast<float*>(w.b3a) + d;
+    g.W3b = w.W3b ? const_cast<float*>(w.W3b) + d : nullptr;
+    g.b3b = w.b3b ? const_cast<float*>(w.b3b) + d : nullptr;
+    g.log_std = w.log_std ? const_cast<float*>(w.log_std) + d : nullptr;
+    return g;
+}
+
+// ---------------------------------------------------------------------------------------------
+// head post-processing
+// ---------------------------------------------------------------------------------------------
+struct ActionSpace {
+    float scale[2], bias[2];
+};
+
+// GaussianPolicy.sample (model.py:325-338)
+static __device__ __forceinline__ void gauss_sample(const float raw[4], const float eps[2], const ActionSpace& sp, float a[2],
+                                             float* logp, float mean_a[2]) {
+    float lp = 0.f;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const float mean = raw[i];
+        const float ls = fminf(fmaxf(raw[2 + i], LOG_SIG_MIN), LOG_SIG_MAX);
+        const float sd = expf(ls);
+        const float x = fmaf(sd, eps[i], mean);  // rsample: loc + eps * scale
+        const float y = tanhf(x);
+        a[i] = fmaf(y, sp.scale[i], sp.bias[i]);
+        const float d = x - mean;
+        float l = -(d * d) / (2.0f * (sd * sd)) - logf(sd) - HALF_LOG_2PI;  // Normal.log_prob
+        l -= logf(sp.scale[i] * (1.0f - y * y) + 1e-6f);
+        lp += l;
+        mean_a[i] = fmaf(tanhf(mean), sp.scale[i], sp.bias[i]);
+    }
+    *logp = lp;
+}
+
+// StochasticPolicy.sample (model.py:512-525)
+static __device__ __forceinline__ void stoch_sample(const float raw[2], const float* log_std, const float eps[2],
+                                             const ActionSpace& sp, float a[2], float mean_a[2], float* logp) {
+    float lp = 0.f;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const float mean = fmaf(tanhf(raw[i]), sp.scale[i], sp.bias[i]);
+        const float ls = fmaxf(log_std[i], MIN_LOG_STD);
+        const float sd = expf(ls);
+        a[i] = fmaf(sd, eps[i], mean);
+        mean_a[i] = mean;
+        const float d = a[i] - mean;
+        lp += -(d * d) / (2.0f * (sd * sd)) - logf(sd) - HALF_LOG_2PI;
+    }
+    *logp = lp;
+}
+
+static __device__ __forceinline__ void philox_eps(uint64_t seed, uint32_t stream_id, uint64_t row, uint64_t step, uint32_t draw,
+                                           float e[2]) {
+    const Philox4 p = rrl_philox(seed, stream_id, row, step, draw);
+    rrl_normal2_f32(p.x, p.y, &e[0], &e[1]);
+}
+
+struct ActArgs {
+    HeadW pol, qr1, qr2, rec;
+    int64_t n;
+    const double* state;  // [2][n]
+    const float *eps_task, *eps_rec, *rand_u;
+    int use_recovery, eval;
+    int64_t start_steps;
+    uint64_t seed;
+    uint32_t stream_id;
+    const int64_t* counters;
+    float eps_safe;
+    ActionSpace sp;
+    float *action_task, *action_real, *qrisk_out;
+    uint8_t* recovery;
+};
+
+
+// agent_tc.cu
+int act_tc_launch(const ActArgs& A, const float* arena, const Layout& L, cudaStream_t st);
+int tc_images_launch(float* arena, const Layout& L, cudaStream_t st);
+
+}  // namespace rrl

@@ -4,6 +4,7 @@
 //   [ grads : critic | policy | qrisk | recovery ]      <- ONE contiguous block = the NCCL all-reduce payload
 //   [ adam m: same 4 nets ] [ adam v: same 4 nets ]
 //   [ W2T images: the ten 256x256 hidden matrices transposed to k-major (operand B of the forward GEMM) ]
+//   [ tcgen05 images: fp16 hi/lo split of the four acting matrices in UMMA canonical K-major layout ]
 //   [ scratch: sampled batches, activations, per-row outputs, losses ]
 //
 // Within a net the tensors follow torch's parameters() order of the reference module
@@ -17,6 +18,7 @@ namespace rrl {
 constexpr int H = 256;  // hidden width (arg_utils.py:89-92); all kernels are specialised for it
 constexpr int kMaxTensors = 14;
 constexpr int kNumImages = 10;
+constexpr int kTcHeads = 4;    // policy, qrisk head 1, qrisk head 2, recovery (the nets the acting kernel runs)
 constexpr int kPassSlots = 5;  // activation slots shared by the SAC and Q_risk updates
 
 struct TDesc {
@@ -78,6 +80,7 @@ struct Layout {
     int64_t train_floats;  // size of the grad / m / v blocks
     int64_t grad_off, m_off, v_off;
     int64_t img_off[kNumImages];
+    int64_t tc_img_off[kTcHeads];          // fp16 hi/lo operand images for tcgen05 (agent_tc.cu), 65536 floats each
     int64_t R;  // max_batch
     // scratch
     int64_t batch_off[2][5];               // [sac|qr][s,a,r,s2,m]
@@ -155,6 +158,10 @@ inline Layout make_layout(const rrl_agent_config_t* cfg) {
     for (int i = 0; i < kNumImages; ++i) {
         L.img_off[i] = off;
         off += (int64_t)H * H;
+    }
+    for (int i = 0; i < kTcHeads; ++i) {
+        L.tc_img_off[i] = off;
+        off += (int64_t)H * H;  // 2 images (hi, lo) x 65536 halves = 65536 floats
     }
     const int64_t R = L.R;
     static const char* bn[2][5] = {{"sac_s", "sac_a", "sac_r", "sac_s2", "sac_m"}, {"qr_s", "qr_a", "qr_c", "qr_s2", "qr_m"}};

@@ -1,0 +1,489 @@
+// agent_tc.cu -- the acting kernel (experiment.py:546-577) with the 256x256 contractions on the 5th-gen
+// tensor cores: tcgen05.mma (kind::f16, M128 N256 K16) issued by one thread, operands staged in shared
+// memory, accumulators in TMEM, epilogue through tcgen05.ld.
+//
+// Precision: the reference computes these layers in fp32 and the parity bar is 1e-4, so a single fp16/bf16
+// MMA is not enough.  Both operands are split into two fp16 terms (x*S = hi + lo, S a power of two that
+// keeps lo out of the subnormal range) and three MMAs are accumulated in fp32:
+//     D += Ahi*Bhi ;  D += Ahi*Blo ;  D += Alo*Bhi          (the dropped Alo*Blo term is ~2^-22 relative)
+// which reproduces the fp32 product to ~1e-6 relative -- measured against the SIMT path in the tests.
+//
+// Per CTA (one per SM, persistent over 128-row tiles), 6 warps:
+//   warps 0-3  one thread per env row: layer 1 (K = 2|4, SIMT) -> fp16 hi/lo A tiles written straight into
+//              the UMMA canonical K-major layout; later the epilogue of the same row (TMEM lane == row):
+//              +b2, ReLU, the 1..4 output heads, tanh-Gaussian / sigmoid / recovery maths, action select
+//   warp 4     TMEM allocation + the single MMA-issuing thread
+//   warp 5     one thread streams the pre-split weight images (32 KB per k-chunk) with cp.async.bulk
+// Pipelines: a 3-stage smem ring (full/empty mbarriers; tcgen05.commit frees a stage) and two 256-column
+// TMEM accumulators (acc_full / acc_empty) so the epilogue of one network overlaps the MMAs of the next.
+// Pass order per tile: policy, recovery, Q_risk head 1, Q_risk head 2 (the two state-only networks first so
+// the tensor pipe has work while the policy epilogue produces the action the Q_risk passes need).
+#include "agent_common.cuh"
+#include <cuda_fp16.h>
+
+using namespace rrl;
+
+namespace {
+
+constexpr int TM = 128;                  // rows per tile == TMEM lanes
+constexpr int KCH = 32;                  // k per stage
+constexpr int NSTAGE = 3;
+constexpr int NCHUNK = H / KCH;          // 8
+constexpr int A_IMG = TM * KCH * 2;      // 8 KB   (one fp16 image of the A chunk)
+constexpr int B_IMG = H * KCH * 2;       // 16 KB
+constexpr int STAGE_BYTES = 2 * A_IMG + 2 * B_IMG;  // 48 KB: [A hi][A lo][B hi][B lo]
+constexpr int kTcThreads = 192;
+constexpr float SA = 16.0f, SB = 64.0f;  // power-of-two operand scales
+constexpr float INV_SCALE = 1.0f / (SA * SB);
+// canonical K-major, no swizzle: core matrix = 8 rows x 16 B (128 B contiguous)
+//   A chunk [128 x 32]: core (kc, g) at (kc * 16 + g) * 128  -> LBO (next core along K) = 2048, SBO (next 8 rows) = 128
+//   B chunk [256 x 32]: core (kc, g) at (kc * 32 + g) * 128  -> LBO = 4096, SBO = 128
+constexpr uint32_t LBO_A = 16 * 128, LBO_B = 32 * 128, SBO = 128;
+// instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (bits 4-5 = 1), a/b format F16 (0),
+// K-major A and B, N >> 3 at bit 17, M >> 4 at bit 24
+constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(H >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+
+enum { PASS_POL = 0, PASS_REC = 1, PASS_QR1 = 2, PASS_QR2 = 3 };
+
+struct TcSmall {
+    float W1[4][H][4];
+    float b1[4][H];
+    float b2[4][H];
+    float w3[4][4][H];
+    float b3[4][4];
+    float log_std[2];
+};
+
+struct TcSmem {
+    unsigned char stage[NSTAGE][STAGE_BYTES];
+    TcSmall sm;
+    unsigned long long full[NSTAGE], empty[NSTAGE], acc_full[2], acc_empty[2];
+    uint32_t tmem_base;
+};
+
+// ---- PTX wrappers -----------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() { asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(IDESC), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start >> 4 | LBO >> 4 << 16 | SBO >> 4 << 32 |
+// version 1 << 46 | layout SWIZZLE_NONE (0) << 61
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) |
+           ((uint64_t)1 << 46);
+}
+
+__device__ __forceinline__ void split_f16(float v, __half* hi, __half* lo) {
+    v = fminf(v, 60000.0f);
+    const __half h = __float2half_rn(v);
+    *hi = h;
+    *lo = __float2half_rn(v - __half2float(h));
+}
+
+// ---- weight images -----------------------------------------------------------------------------------
+// element (n, k) of W2[n][k] * SB -> fp16 hi / lo at halves index
+//   (((c * 2 + hl) * 4 + kc) * 32 + g) * 64 + r * 8 + e,   c = k / 32, kc = (k % 32) / 8, e = k % 8, g = n / 8, r = n % 8
+struct TcImgArgs {
+    const float* W2[kTcHeads];
+    __half* img[kTcHeads];
+};
+__global__ void __launch_bounds__(256) tc_images_kernel(const __grid_constant__ TcImgArgs A) {
+    const int head = blockIdx.y;
+    const float* __restrict__ W = A.W2[head];
+    __half* __restrict__ img = A.img[head];
+    // one thread per (n, 8 consecutive k): coalesced 32 B reads, 16 B writes
+    const int idx = blockIdx.x * 256 + threadIdx.x;  // 0 .. 256*32
+    const int n = idx >> 5, k8 = idx & 31;
+    const float4 v0 = *reinterpret_cast<const float4*>(W + n * H + k8 * 8);
+    const float4 v1 = *reinterpret_cast<const float4*>(W + n * H + k8 * 8 + 4);
+    const float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+    __align__(16) __half hi[8], lo[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const float s = fmaxf(fminf(v[e] * SB, 60000.0f), -60000.0f);
+        const __half h = __float2half_rn(s);
+        hi[e] = h;
+        lo[e] = __float2half_rn(s - __half2float(h));
+    }
+    const int c = k8 >> 2, kc = k8 & 3, g = n >> 3, r = n & 7;
+    const size_t base_hi = ((((size_t)c * 2 + 0) * 4 + kc) * 32 + g) * 64 + r * 8;
+    const size_t base_lo = ((((size_t)c * 2 + 1) * 4 + kc) * 32 + g) * 64 + r * 8;
+    *reinterpret_cast<uint4*>(img + base_hi) = *reinterpret_cast<const uint4*>(hi);
+    *reinterpret_cast<uint4*>(img + base_lo) = *reinterpret_cast<const uint4*>(lo);
+}
+
+// ---- the acting kernel -----------------------------------------------------------------------------
+struct TcActArgs {
+    ActArgs a;
+    const __half* img[4];  // by pass: POL, REC, QR1, QR2
+    int n_pass;            // 1 (no recovery) or 4
+};
+
+__device__ __forceinline__ const HeadW& pass_head(const ActArgs& a, int p) {
+    return p == PASS_POL ? a.pol : (p == PASS_REC ? a.rec : (p == PASS_QR1 ? a.qr1 : a.qr2));
+}
+
+// producer: layer 1 of `pass` for this thread's row, k-chunk c -> stage (fp16 hi/lo, canonical layout)
+__device__ __forceinline__ void produce_chunk(TcSmem& S, int pass, int c, int stage, int t, float x0, float x1, float x2,
+                                              float x3, bool four) {
+    unsigned char* a_hi = S.stage[stage];
+    unsigned char* a_lo = a_hi + A_IMG;
+#pragma unroll
+    for (int kc = 0; kc < KCH / 8; ++kc) {
+        __align__(16) __half hi[8], lo[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int k = c * KCH + kc * 8 + e;
+            const float4 wv = *reinterpret_cast<const float4*>(S.sm.W1[pass][k]);
+            float h = fmaf(wv.x, x0, S.sm.b1[pass][k]);
+            h = fmaf(wv.y, x1, h);
+            if (four) {
+                h = fmaf(wv.z, x2, h);
+                h = fmaf(wv.w, x3, h);
+            }
+            h = fmaxf(h, 0.f) * SA;
+            split_f16(h, &hi[e], &lo[e]);
+        }
+        *reinterpret_cast<uint4*>(a_hi + kc * LBO_A + t * 16) = *reinterpret_cast<const uint4*>(hi);
+        *reinterpret_cast<uint4*>(a_lo + kc * LBO_A + t * 16) = *reinterpret_cast<const uint4*>(lo);
+    }
+}
+
+// epilogue: this thread's row of accumulator `d` -> raw head outputs (W3 relu(acc + b2) + b3)
+__device__ __forceinline__ void epilogue_row(TcSmem& S, int pass, int n_out, uint32_t taddr, float raw[4]) {
+    float out[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+    for (int cc = 0; cc < H / 32; ++cc) {
+        float v[32];
+        tmem_ld32(taddr + cc * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const int k = cc * 32 + j;
+            const float h = fmaxf(fmaf(v[j], INV_SCALE, S.sm.b2[pass][k]), 0.f);
+            out[0] = fmaf(h, S.sm.w3[pass][0][k], out[0]);
+            if (n_out > 1) out[1] = fmaf(h, S.sm.w3[pass][1][k], out[1]);
+            if (n_out > 2) {
+                out[2] = fmaf(h, S.sm.w3[pass][2][k], out[2]);
+                out[3] = fmaf(h, S.sm.w3[pass][3][k], out[3]);
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 0; o < 4; ++o) raw[o] = out[o] + S.sm.b3[pass][o];
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1) act_tc_kernel(const __grid_constant__ TcActArgs T) {
+    extern __shared__ unsigned char smem_raw[];
+    TcSmem& S = *reinterpret_cast<TcSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+    const ActArgs& A = T.a;
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const int n_pass = T.n_pass;
+    const int64_t n_tiles = (A.n + TM - 1) / TM;
+
+    // ---- one-time setup: small tensors, barriers, TMEM ----
+    for (int p = 0; p < n_pass; ++p) {
+        const HeadW& w = pass_head(A, p);
+        for (int k = t; k < H; k += kTcThreads) {
+            float4 w1 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (w.n_in == 4) {
+                w1 = *reinterpret_cast<const float4*>(w.W1 + k * 4);
+            } else {
+                const float2 v = *reinterpret_cast<const float2*>(w.W1 + k * 2);
+                w1.x = v.x; w1.y = v.y;
+            }
+            *reinterpret_cast<float4*>(S.sm.W1[p][k]) = w1;
+            S.sm.b1[p][k] = w.b1[k];
+            S.sm.b2[p][k] = w.b2[k];
+            for (int o = 0; o < 4; ++o) {
+                float v = 0.f;
+                if (o < w.na) v = w.W3a[o * H + k];
+                else if (o < w.na + w.nb) v = w.W3b[(o - w.na) * H + k];
+                S.sm.w3[p][o][k] = v;
+            }
+        }
+        if (t < 4) {
+            float v = 0.f;
+            if (t < w.na) v = w.b3a[t];
+            else if (t < w.na + w.nb) v = w.b3b[t - w.na];
+            S.sm.b3[p][t] = v;
+        }
+    }
+    if (t < 2 && n_pass > 1) S.sm.log_std[t] = A.rec.log_std[t];
+    if (t == 0) {
+        for (int s = 0; s < NSTAGE; ++s) {
+            mbar_init(smem_u32(&S.full[s]), TM + 1);  // 128 producer arrivals + the loader's expect_tx arrival
+            mbar_init(smem_u32(&S.empty[s]), 1);      // tcgen05.commit
+        }
+        for (int d = 0; d < 2; ++d) {
+            mbar_init(smem_u32(&S.acc_full[d]), 1);   // tcgen05.commit
+            mbar_init(smem_u32(&S.acc_empty[d]), TM); // 128 epilogue arrivals
+        }
+        fence_barrier_init();
+    }
+    if (warp == 4) {
+        tmem_alloc(smem_u32(&S.tmem_base), 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = S.tmem_base;
+
+    const uint64_t vstep = A.counters ? (uint64_t)A.counters[RRL_C_VEC_STEP] : 0;
+    const bool random_phase = A.counters && !A.eval && (A.start_steps > A.counters[RRL_C_TOTAL_NUMSTEPS]);
+
+    if (warp < 4) {
+        // ================= producer + epilogue: thread t owns row t of every tile =================
+        uint32_t it = 0;            // running (pass, chunk) index: stage = it % NSTAGE
+        uint32_t acc_use[2] = {0, 0};
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int64_t row = tile * TM + t;
+            const bool live = row < A.n;
+            float sx = 0.f, sy = 0.f;
+            if (live) {  // torch.FloatTensor(state): fp64 -> fp32 (sac.py:137)
+                sx = (float)A.state[row];
+                sy = (float)A.state[A.n + row];
+            }
+            float at[2] = {0.f, 0.f}, ar[2] = {0.f, 0.f}, arec[2] = {0.f, 0.f};
+            float q1 = 0.f, qmax = 0.f;
+            bool rec = false;
+            auto produce_pass = [&](int pass, float x2, float x3) {
+                const bool four = pass >= PASS_QR1;
+                for (int c = 0; c < NCHUNK; ++c, ++it) {
+                    const int stage = it % NSTAGE;
+                    mbar_wait(smem_u32(&S.empty[stage]), ((it / NSTAGE) & 1) ^ 1);
+                    produce_chunk(S, pass, c, stage, t, sx, sy, x2, x3, four);
+                    fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+                    mbar_arrive(smem_u32(&S.full[stage]));
+                }
+            };
+            auto epilogue_pass = [&](int pass, int d, int n_out, float raw[4]) {
+                mbar_wait(smem_u32(&S.acc_full[d]), acc_use[d] & 1);
+                tc_fence_after();
+                epilogue_row(S, pass, n_out, lane_addr + d * H, raw);
+                tc_fence_before();
+                mbar_arrive(smem_u32(&S.acc_empty[d]));
+                ++acc_use[d];
+            };
+            float raw[4];
+            produce_pass(PASS_POL, 0.f, 0.f);
+            if (n_pass > 1) produce_pass(PASS_REC, 0.f, 0.f);
+            // ---- policy head (model.py:325-338) ----
+            epilogue_pass(PASS_POL, 0, 4, raw);
+            if (!random_phase) {
+                float e[2], mean_a[2], lp;
+                if (A.eps_task) {
+                    const float2 ev = live ? reinterpret_cast<const float2*>(A.eps_task)[row] : make_float2(0.f, 0.f);
+                    e[0] = ev.x; e[1] = ev.y;
+                } else {
+                    philox_eps(A.seed, A.stream_id, (uint64_t)row, vstep, RRL_DRAW_ACT_TASK, e);
+                }
+                gauss_sample(raw, e, A.sp, at, &lp, mean_a);
+                if (A.eval) { at[0] = mean_a[0]; at[1] = mean_a[1]; }
+            } else {  // env.action_space.sample() (experiment.py:559-560)
+                float u[2] = {0.f, 0.f};
+                if (A.rand_u) {
+                    if (live) {
+                        const float2 uv = reinterpret_cast<const float2*>(A.rand_u)[row];
+                        u[0] = uv.x; u[1] = uv.y;
+                    }
+                } else {
+                    const Philox4 p = rrl_philox(A.seed, A.stream_id, (uint64_t)row, vstep, RRL_DRAW_ACT_RAND);
+                    u[0] = rrl_u24(p.x); u[1] = rrl_u24(p.y);
+                }
+                at[0] = fmaf(2.0f * u[0] - 1.0f, A.sp.scale[0], A.sp.bias[0]);
+                at[1] = fmaf(2.0f * u[1] - 1.0f, A.sp.scale[1], A.sp.bias[1]);
+            }
+            ar[0] = at[0]; ar[1] = at[1];
+            if (n_pass > 1) {
+                produce_pass(PASS_QR1, at[0], at[1]);
+                // ---- recovery policy head (model.py:512-525) ----
+                epilogue_pass(PASS_REC, 1, 2, raw);
+                {
+                    float e[2], mean_a[2], lp;
+                    if (A.eps_rec) {
+                        const float2 ev = live ? reinterpret_cast<const float2*>(A.eps_rec)[row] : make_float2(0.f, 0.f);
+                        e[0] = ev.x; e[1] = ev.y;
+                    } else {
+                        philox_eps(A.seed, A.stream_id, (uint64_t)row, vstep, RRL_DRAW_ACT_REC, e);
+                    }
+                    stoch_sample(raw, S.sm.log_std, e, A.sp, arec, mean_a, &lp);
+                }
+                produce_pass(PASS_QR2, at[0], at[1]);
+                epilogue_pass(PASS_QR1, 0, 1, raw);
+                q1 = sigmoidf_(raw[0]);
+                epilogue_pass(PASS_QR2, 1, 1, raw);
+                qmax = fmaxf(q1, sigmoidf_(raw[0]));   // qrisk.py:196
+                rec = qmax > A.eps_safe;               // experiment.py:555
+                if (rec) { ar[0] = arec[0]; ar[1] = arec[1]; }
+            }
+            if (live) {
+                reinterpret_cast<float2*>(A.action_task)[row] = make_float2(at[0], at[1]);
+                reinterpret_cast<float2*>(A.action_real)[row] = make_float2(ar[0], ar[1]);
+                if (A.recovery) A.recovery[row] = rec ? 1 : 0;
+                if (A.qrisk_out) A.qrisk_out[row] = qmax;
+            }
+        }
+    } else if (warp == 4) {
+        // ================= MMA issuer (one thread) =================
+        if (lane == 0) {
+            uint32_t it = 0;
+            uint32_t acc_use[2] = {0, 0};
+            for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                for (int p = 0; p < n_pass; ++p) {
+                    const int d = p & 1;  // POL -> 0, REC -> 1, QR1 -> 0, QR2 -> 1
+                    mbar_wait(smem_u32(&S.acc_empty[d]), (acc_use[d] & 1) ^ 1);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + d * H;
+                    for (int c = 0; c < NCHUNK; ++c, ++it) {
+                        const int stage = it % NSTAGE;
+                        mbar_wait(smem_u32(&S.full[stage]), (it / NSTAGE) & 1);
+                        tc_fence_after();
+                        const uint32_t a_hi = smem_u32(S.stage[stage]);
+                        const uint32_t a_lo = a_hi + A_IMG, b_hi = a_hi + 2 * A_IMG, b_lo = b_hi + B_IMG;
+#pragma unroll
+                        for (int j = 0; j < KCH / 16; ++j) {
+                            const uint64_t dah = make_desc(a_hi + j * 2 * LBO_A, LBO_A, SBO);
+                            const uint64_t dal = make_desc(a_lo + j * 2 * LBO_A, LBO_A, SBO);
+                            const uint64_t dbh = make_desc(b_hi + j * 2 * LBO_B, LBO_B, SBO);
+                            const uint64_t dbl = make_desc(b_lo + j * 2 * LBO_B, LBO_B, SBO);
+                            umma_f16(d_tmem, dah, dbh, (c | j) ? 1u : 0u);
+                            umma_f16(d_tmem, dah, dbl, 1u);
+                            umma_f16(d_tmem, dal, dbh, 1u);
+                        }
+                        umma_commit(smem_u32(&S.empty[stage]));  // stage free once these MMAs have read it
+                    }
+                    umma_commit(smem_u32(&S.acc_full[d]));       // accumulator complete
+                    ++acc_use[d];
+                }
+            }
+        }
+    } else {
+        // ================= weight-image loader (one thread) =================
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                for (int p = 0; p < n_pass; ++p) {
+                    const unsigned char* img = reinterpret_cast<const unsigned char*>(T.img[p]);
+                    for (int c = 0; c < NCHUNK; ++c, ++it) {
+                        const int stage = it % NSTAGE;
+                        mbar_wait(smem_u32(&S.empty[stage]), ((it / NSTAGE) & 1) ^ 1);
+                        const uint32_t bar = smem_u32(&S.full[stage]);
+                        const uint32_t dst = smem_u32(S.stage[stage]) + 2 * A_IMG;
+                        mbar_arrive_expect_tx(bar, 2 * B_IMG);
+                        bulk_g2s(dst, img + (size_t)c * 2 * B_IMG, B_IMG, bar);
+                        bulk_g2s(dst + B_IMG, img + (size_t)c * 2 * B_IMG + B_IMG, B_IMG, bar);
+                    }
+                }
+            }
+        }
+    }
+    // ---- teardown ----
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace
+
+namespace rrl {
+
+int tc_images_launch(float* arena, const Layout& L, cudaStream_t st) {
+    TcImgArgs A;
+    static const int nets[kTcHeads] = {RRL_NET_POLICY, RRL_NET_QRISK, RRL_NET_QRISK, RRL_NET_RECOVERY};
+    static const int heads[kTcHeads] = {0, 0, 1, 0};
+    for (int i = 0; i < kTcHeads; ++i) {
+        A.W2[i] = arena + L.t_off[nets[i]][w2_tensor(nets[i], heads[i])];
+        A.img[i] = reinterpret_cast<__half*>(arena + L.tc_img_off[i]);
+    }
+    tc_images_kernel<<<dim3(H * 32 / 256, kTcHeads), 256, 0, st>>>(A);
+    RRL_CHECK_LAUNCH();
+    return 0;
+}
+
+int act_tc_launch(const ActArgs& A, const float* arena, const Layout& L, cudaStream_t st) {
+    TcActArgs T;
+    T.a = A;
+    // image slots: 0 policy, 1 qrisk h1, 2 qrisk h2, 3 recovery ; pass order: POL, REC, QR1, QR2
+    T.img[PASS_POL] = reinterpret_cast<const __half*>(arena + L.tc_img_off[0]);
+    T.img[PASS_REC] = reinterpret_cast<const __half*>(arena + L.tc_img_off[3]);
+    T.img[PASS_QR1] = reinterpret_cast<const __half*>(arena + L.tc_img_off[1]);
+    T.img[PASS_QR2] = reinterpret_cast<const __half*>(arena + L.tc_img_off[2]);
+    T.n_pass = A.use_recovery ? 4 : 1;
+    static bool configured = false;
+    const size_t smem = sizeof(TcSmem) + 128;
+    if (!configured) {
+        RRL_CUDA(cudaFuncSetAttribute(act_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    const int64_t tiles = (A.n + TM - 1) / TM;
+    const int64_t sms = rrl_num_sms();
+    const int grid = (int)(tiles < sms ? tiles : sms);
+    act_tc_kernel<<<grid, kTcThreads, smem, st>>>(T);
+    RRL_CHECK_LAUNCH();
+    return 0;
+}
+
+}  // namespace rrl

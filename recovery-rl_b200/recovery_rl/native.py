@@ -235,6 +235,10 @@ def agent_refresh(cfg, arena, stream=None):
     _check(lib().rrl_agent_refresh(C.byref(cfg), p(arena, "f32"), _stream(stream)), "rrl_agent_refresh")
 
 
+def agent_tc_refresh(cfg, arena, stream=None):
+    _check(lib().rrl_agent_tc_refresh(C.byref(cfg), p(arena, "f32"), _stream(stream)), "rrl_agent_tc_refresh")
+
+
 def agent_act(cfg, arena, n, state, counters, action_task, action_real, recovery=None, qrisk_out=None,
               eps_task=None, eps_rec=None, rand_u=None, use_recovery=True, eval=False, start_steps=0, seed=0,
               stream_id=0, stream=None):

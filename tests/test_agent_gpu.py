@@ -140,7 +140,14 @@ def test_updates_and_acting_vs_reference(native, cuda, golden_dir, tag):
     assert list(c[native.C_ADAM_T0:native.C_ADAM_T0 + 4]) == [n_upd] * 4
     _sync_from_oracle(native, ar, ora)           # final weights == the reference's (bit-exact oracle)
 
-    # ---- acting on the updated weights (experiment.py:546-577) ----
+    for tc in (0, 1):
+        _check_acting(native, cuda, ar, z, tc)
+
+
+def _check_acting(native, cuda, ar, z, tc):
+    """composite action selection (experiment.py:546-577) on the reference's final weights; tc = 1 runs the
+    256x256 contractions on the tensor cores (tcgen05, fp16 hi/lo split) and must meet the same bar."""
+    ar.cfg.use_tensor_cores = tc
     N = len(z["act_s"])
     ar.cfg.eps_safe = float(z["act_thresh"])
     st = torch.from_numpy(np.ascontiguousarray(z["act_s"].T)).to(cuda)
@@ -223,3 +230,37 @@ def test_partial_batch_and_closed_gate(native, cuda, golden_dir):
     for net in ("qrisk", "qrisk_target", "recovery"):
         for w, o in zip(ar.params(net), ora.params(net)):
             close(w, o, rtol=2e-4, atol=2e-6)
+
+
+def test_act_tensor_cores_match_simt_many_tiles(native, cuda, golden_dir):
+    """tcgen05 acting kernel vs the fp32 SIMT kernel on 40,001 rows (several tiles per CTA, ragged last tile):
+    actions / Q_risk within 1e-4, recovery flags equal away from the threshold."""
+    z = np.load(os.path.join(golden_dir, "agent_maze_b64.npz"))
+    ora = _oracle_agent(z)
+    ar = _arena(native, cuda, z, 64)
+    ar.load_modules(ora.nets())
+    rs = np.random.RandomState(0)
+    N = 40001
+    st = torch.from_numpy(rs.uniform(-0.28, 0.28, (2, N))).to(cuda)
+    e_task, e_rec = _dev(rs.randn(N, 2), cuda), _dev(rs.randn(N, 2), cuda)
+    outs = []
+    for tc in (0, 1):
+        ar.cfg.use_tensor_cores = tc
+        q = torch.zeros(N, device=cuda)
+        native.agent_act(ar.cfg, ar.arena, N, st, None, torch.zeros(N, 2, device=cuda), torch.zeros(N, 2, device=cuda),
+                         torch.zeros(N, dtype=torch.uint8, device=cuda), q, e_task, e_rec)
+        med = float(q.median())
+        ar.cfg.eps_safe = med                      # both branches of experiment.py:555 occur
+        a_task = torch.zeros(N, 2, device=cuda); a_real = torch.zeros(N, 2, device=cuda)
+        rec = torch.zeros(N, dtype=torch.uint8, device=cuda)
+        native.agent_act(ar.cfg, ar.arena, N, st, None, a_task, a_real, rec, q, e_task, e_rec)
+        torch.cuda.synchronize()
+        outs.append((a_task.cpu().numpy(), a_real.cpu().numpy(), rec.cpu().numpy().astype(bool), q.cpu().numpy(), med))
+    (t0, r0, f0, q0, m0), (t1, r1, f1, q1, m1) = outs
+    close(t1, t0, atol=2e-6)
+    close(q1, q0, atol=2e-6)
+    sure = np.abs(q0 - m0) > 1e-5
+    assert abs(m0 - m1) < 1e-6
+    assert np.array_equal(f0[sure], f1[sure]) and 1000 < f0.sum() < N - 1000
+    same = f0 == f1
+    close(r1[same], r0[same], atol=2e-6)
