@@ -1,0 +1,326 @@
+"""Experiment wrapper (reference recovery_rl/experiment.py:42-577): seeding, env / agent construction, offline
+data, Q_risk pre-training, train / test rollouts, composite action selection, pickle logging -- same class
+and method names, same log files (`args.pkl`, `run_stats.pkl` with "train_stats" / "test_stats").
+
+Two execution modes behind the same surface:
+  * --num_envs 1 (default): the reference's loop, statement for statement, on the drop-in classes
+    (env.step, SAC, QRiskWrapper, ReplayMemory) whose arithmetic runs in the CUDA kernels;
+  * --num_envs N > 1: the vectorised engine (recovery_rl/engine.py) -- N env copies per GPU, the whole
+    step replayed as one CUDA graph, per-step host traffic only for the env copies that are logged.
+Model-based (PETS / visual MPC) recovery, image observations and task demos are outside this build.
+"""
+import datetime
+import itertools
+import os
+import os.path as osp
+import pickle
+
+import numpy as np
+import torch
+
+from recovery_rl.sac import SAC
+from recovery_rl.replay_memory import ReplayMemory, ConstraintReplayMemory
+from recovery_rl.utils import linear_schedule
+from env.make_utils import register_env, make_env
+
+
+def torchify(x):
+    return torch.FloatTensor(x).to('cuda')
+
+
+class Experiment:
+    def __init__(self, exp_cfg):
+        self.exp_cfg = exp_cfg
+        self.logdir = os.path.join(
+            self.exp_cfg.logdir, '{}_SAC_{}_{}_{}'.format(datetime.datetime.now().strftime("%Y-%m-%d_%H-%M-%S"),
+                                                          self.exp_cfg.env_name, self.exp_cfg.policy,
+                                                          self.exp_cfg.logdir_suffix))
+        if not os.path.exists(self.logdir):
+            os.makedirs(self.logdir)
+        print("LOGDIR: ", self.logdir)
+        pickle.dump(self.exp_cfg, open(os.path.join(self.logdir, "args.pkl"), "wb"))
+        self.num_envs = int(getattr(self.exp_cfg, "num_envs", 1))
+        if self.exp_cfg.use_recovery and not (self.exp_cfg.MF_recovery or self.exp_cfg.Q_sampling_recovery):
+            raise NotImplementedError("model-based (PETS/CEM) recovery is outside this build: pass --MF_recovery")
+        if self.exp_cfg.task_demos:
+            raise NotImplementedError("--task_demos is outside this build (DESIGN.md, 'next')")
+
+        self.experiment_setup()
+
+        self.total_numsteps = 0
+        self.updates = 0
+        self.num_constraint_violations = 0
+        self.num_unsafe_transitions = 0
+        self.num_viols = 0
+        self.num_successes = 0
+        self.viol_and_recovery = 0
+        self.viol_and_no_recovery = 0
+        self.task_demos = self.exp_cfg.task_demos
+        if self.num_envs == 1:
+            self.memory = ReplayMemory(self.exp_cfg.replay_size, self.exp_cfg.seed)
+            self.recovery_memory = ConstraintReplayMemory(self.exp_cfg.safe_replay_size, self.exp_cfg.seed)
+        self.all_ep_data = []
+        self.constraint_demo_data, self.task_demo_data, self.obs_seqs, self.ac_seqs, self.constraint_seqs = \
+            self.get_offline_data()
+        if self.exp_cfg.nu_schedule:
+            self.nu_schedule = linear_schedule(self.exp_cfg.nu_start, self.exp_cfg.nu_end, self.exp_cfg.num_eps)
+        else:
+            self.nu_schedule = linear_schedule(self.exp_cfg.nu, self.exp_cfg.nu, 0)
+
+    # ------------------------------------------------------------------------------------------------
+    def experiment_setup(self):
+        torch.manual_seed(self.exp_cfg.seed)
+        np.random.seed(self.exp_cfg.seed)
+        register_env(self.exp_cfg.env_name)
+        env = make_env(self.exp_cfg.env_name)
+        self.env = env
+        self.recovery_policy = None
+        self.env.seed(self.exp_cfg.seed)
+        self.env.action_space.seed(self.exp_cfg.seed)
+        if self.num_envs == 1:
+            self.agent = self.agent_setup(env)
+            self.engine = None
+        else:
+            self.agent = None
+            self.engine = self.engine_setup()
+
+    def agent_setup(self, env):
+        return SAC(env.observation_space, env.action_space, self.exp_cfg, self.logdir,
+                   tmp_env=make_env(self.exp_cfg.env_name))
+
+    def engine_setup(self):
+        from recovery_rl.engine import VecEngine
+        c = self.exp_cfg
+        rank = int(os.environ.get("RANK", "0"))
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        pg = None
+        if world > 1:
+            import torch.distributed as dist
+            local = int(os.environ.get("LOCAL_RANK", "0"))
+            torch.cuda.set_device(local)
+            if not dist.is_initialized():
+                dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            pg = dist.group.WORLD
+        dev = torch.device("cuda", torch.cuda.current_device())
+        eng = VecEngine(c.env_name, self.num_envs, batch_size=c.batch_size, replay_size=c.replay_size,
+                        safe_replay_size=c.safe_replay_size, gamma=c.gamma, alpha=c.alpha, tau=c.tau, lr=c.lr,
+                        gamma_safe=c.gamma_safe, tau_safe=c.tau_safe, eps_safe=c.eps_safe,
+                        target_update_interval=c.target_update_interval, use_recovery=c.use_recovery,
+                        mf_recovery=c.MF_recovery, pos_fraction=c.pos_fraction,
+                        disable_online_updates=c.disable_online_updates,
+                        constraint_reward_penalty=c.constraint_reward_penalty, start_steps=c.start_steps, seed=c.seed,
+                        device=dev, rank=rank, world_size=world, process_group=pg,
+                        log_outputs=getattr(c, "log_envs", 1) > 0, use_tensor_cores=getattr(c, "tensor_cores", 1))
+        eng.init_agent()          # same torch seed on every rank -> identical replicas
+        return eng
+
+    def get_offline_data(self):
+        """experiment.py:177-246.  Navigation: env.transition_function(n).  Maze: the reference loads a pickle of
+        MuJoCo demos (demos/maze/constraint_demos.pkl); it is used when present, else the demos are regenerated
+        with the restated physics (env/maze.py get_offline_data)."""
+        task_demo_data = None
+        if 'maze' in self.exp_cfg.env_name:
+            path = osp.join("demos", self.exp_cfg.env_name, "constraint_demos.pkl")
+            if osp.exists(path):
+                constraint_demo_data = pickle.load(open(path, "rb"))
+            else:
+                constraint_demo_data = self.env.transition_function(self.exp_cfg.num_unsafe_transitions)
+        else:
+            constraint_demo_data = self.env.transition_function(self.exp_cfg.num_unsafe_transitions)
+        return constraint_demo_data, task_demo_data, [], [], []
+
+    def pretrain_critic_recovery(self):
+        """experiment.py:261-296."""
+        demos = self.constraint_demo_data[:self.exp_cfg.num_unsafe_transitions]
+        self.num_unsafe_transitions = len(demos)
+        self.num_constraint_violations += int(sum(int(t[2]) for t in demos))
+        print("Number of Constraint Transitions: ", self.num_unsafe_transitions)
+        print("Number of Constraint Violations: ", self.num_constraint_violations)
+        bs = min(self.exp_cfg.batch_size, len(self.constraint_demo_data))
+        if self.engine is not None:
+            self.engine.push_offline(demos)
+            self.engine.pretrain_qrisk(self.exp_cfg.critic_safe_pretraining_steps, n_demos=len(self.constraint_demo_data))
+            return
+        for transition in demos:
+            self.recovery_memory.push(*transition)
+        for i in range(self.exp_cfg.critic_safe_pretraining_steps):
+            if i % 100 == 0:
+                print("CRITIC SAFE UPDATE STEP: ", i)
+            self.agent.safety_critic.update_parameters(memory=self.recovery_memory, policy=self.agent.policy,
+                                                       batch_size=bs)
+
+    # ------------------------------------------------------------------------------------------------
+    def run(self):
+        if not self.exp_cfg.disable_offline_updates and (self.exp_cfg.use_recovery or self.exp_cfg.DGD_constraints
+                                                          or self.exp_cfg.RCPO):
+            self.pretrain_critic_recovery()
+        if self.engine is not None:
+            return self.run_vectorised()
+        train_rollouts = []
+        test_rollouts = []
+        for i_episode in itertools.count(1):
+            train_rollouts.append(self.get_train_rollout(i_episode))
+            if i_episode % 10 == 0 and self.exp_cfg.eval:
+                test_rollouts.append(self.get_test_rollout(i_episode))
+            if self.total_numsteps > self.exp_cfg.num_steps or i_episode > self.exp_cfg.num_eps:
+                break
+            self.dump_logs(train_rollouts, test_rollouts)
+
+    def get_train_rollout(self, i_episode):
+        """experiment.py:379-491, statement for statement."""
+        episode_reward = 0
+        episode_steps = 0
+        done = False
+        state = self.env.reset()
+        train_rollout_info = []
+        if i_episode % 10 == 0:
+            print("SEED: ", self.exp_cfg.seed)
+            print("LOGDIR: ", self.logdir)
+        while not done:
+            if len(self.memory) > self.exp_cfg.batch_size:
+                for i in range(self.exp_cfg.updates_per_step):
+                    self.agent.update_parameters(self.memory, min(self.exp_cfg.batch_size, len(self.memory)),
+                                                 self.updates, safety_critic=self.agent.safety_critic,
+                                                 nu=self.nu_schedule(i_episode))
+                    if not self.exp_cfg.disable_online_updates and len(self.recovery_memory) > self.exp_cfg.batch_size \
+                            and (self.num_viols + self.num_constraint_violations) / self.exp_cfg.batch_size > \
+                            self.exp_cfg.pos_fraction:
+                        self.agent.safety_critic.update_parameters(memory=self.recovery_memory, policy=self.agent.policy,
+                                                                   batch_size=self.exp_cfg.batch_size, plot=0)
+                    self.updates += 1
+            action, real_action, recovery_used = self.get_action(state)
+            next_state, reward, done, info = self.env.step(real_action)
+            info['recovery'] = recovery_used
+            train_rollout_info.append(info)
+            episode_steps += 1
+            episode_reward += reward
+            self.total_numsteps += 1
+            if info['constraint']:
+                reward -= self.exp_cfg.constraint_reward_penalty
+            mask = float(not done)
+            done = done or episode_steps == self.env._max_episode_steps
+            if not self.exp_cfg.disable_action_relabeling:
+                self.memory.push(state, action, reward, next_state, mask)
+            else:
+                self.memory.push(state, real_action, reward, next_state, mask)
+            if self.exp_cfg.use_recovery or self.exp_cfg.DGD_constraints or self.exp_cfg.RCPO:
+                self.recovery_memory.push(state, real_action, info['constraint'], next_state, mask)
+                if recovery_used and self.exp_cfg.add_both_transitions:
+                    self.memory.push(state, real_action, reward, next_state, mask)
+            state = next_state
+        if info['constraint']:
+            self.num_viols += 1
+            if info['recovery']:
+                self.viol_and_recovery += 1
+            else:
+                self.viol_and_no_recovery += 1
+        self.num_successes += int(info['success'])
+        print("Episode: {}, total numsteps: {}, episode steps: {}, reward: {}".format(
+            i_episode, self.total_numsteps, episode_steps, round(episode_reward, 2)))
+        print("Num Violations So Far: %d" % self.num_viols)
+        print("Violations with Recovery: %d" % self.viol_and_recovery)
+        print("Violations with No Recovery: %d" % self.viol_and_no_recovery)
+        print("Num Successes So Far: %d" % self.num_successes)
+        return train_rollout_info
+
+    def get_test_rollout(self, i_episode):
+        """experiment.py:493-538 without the MuJoCo gif rendering."""
+        test_rollout_info = []
+        state = self.env.reset()
+        episode_reward = 0
+        episode_steps = 0
+        done = False
+        while not done:
+            action, real_action, recovery_used = self.get_action(state, train=False)
+            next_state, reward, done, info = self.env.step(real_action)
+            info['recovery'] = recovery_used
+            done = done or episode_steps == self.env._max_episode_steps
+            test_rollout_info.append(info)
+            episode_reward += reward
+            episode_steps += 1
+            state = next_state
+        print("----------------------------------------")
+        print("Avg. Reward: {}".format(round(episode_reward, 2)))
+        print("----------------------------------------")
+        return test_rollout_info
+
+    def dump_logs(self, train_rollouts, test_rollouts):
+        data = {"test_stats": test_rollouts, "train_stats": train_rollouts}
+        with open(osp.join(self.logdir, "run_stats.pkl"), "wb") as f:
+            pickle.dump(data, f)
+
+    def get_action(self, state, train=True):
+        """experiment.py:546-577."""
+        def recovery_thresh(state, action):
+            if not self.exp_cfg.use_recovery:
+                return False
+            critic_val = self.agent.safety_critic.get_value(torchify(state).unsqueeze(0), torchify(action).unsqueeze(0))
+            if critic_val > self.exp_cfg.eps_safe:
+                return True
+            return False
+
+        if self.exp_cfg.start_steps > self.total_numsteps and train:
+            action = self.env.action_space.sample()
+        elif train:
+            action = self.agent.select_action(state)
+        else:
+            action = self.agent.select_action(state, eval=True)
+        if recovery_thresh(state, action):
+            recovery = True
+            real_action = self.agent.safety_critic.select_action(state)
+        else:
+            recovery = False
+            real_action = np.copy(action)
+        return action, real_action, recovery
+
+    # ------------------------------------------------------------------------------------------------
+    def run_vectorised(self, report_every=50):
+        """N env copies per GPU.  Termination as in run(): total_numsteps > num_steps or episodes > num_eps.
+        `train_stats` keeps the reference's schema (a list of episodes, each a list of per-step info dicts) for
+        the first --log_envs env copies; the global counters go to `vec_stats`."""
+        eng = self.engine
+        c = self.exp_cfg
+        eng.reset()
+        eng.capture()
+        k = min(max(int(getattr(c, "log_envs", 1)), 0), eng.n)
+        train_rollouts, open_eps, vec_stats = [], [[] for _ in range(k)], []
+        step = 0
+        while True:
+            if k:
+                prev = eng.state[:, :k].t().cpu().numpy().copy()
+            eng.replay()
+            step += 1
+            if k:
+                ns = eng.out_next[:, :k].t().cpu().numpy()
+                rew = eng.out_reward[:k].cpu().numpy()
+                done = eng.out_done[:k].cpu().numpy()
+                cons = eng.out_cons[:k].cpu().numpy()
+                succ = eng.out_succ[:k].cpu().numpy()
+                act = eng.action_real[:k].cpu().numpy()
+                rec = eng.recovery[:k].cpu().numpy()
+                for i in range(k):
+                    open_eps[i].append({"constraint": int(cons[i]), "reward": float(rew[i]), "state": prev[i],
+                                        "next_state": ns[i], "action": act[i], "success": bool(succ[i]),
+                                        "recovery": bool(rec[i])})
+                    if done[i]:
+                        train_rollouts.append(open_eps[i])
+                        open_eps[i] = []
+            if step % report_every == 0:
+                cn = eng.read_counters()
+                if cn["error"]:
+                    raise RuntimeError("device-side sampler error %d (sample larger than population)" % cn["error"])
+                self.total_numsteps = cn["total_numsteps"]
+                self.num_viols, self.num_successes = cn["num_viols"], cn["num_successes"]
+                self.viol_and_recovery, self.viol_and_no_recovery = cn["viol_and_recovery"], cn["viol_and_no_recovery"]
+                self.updates = cn["sac_updates"]
+                if True:
+                    vec_stats.append(cn)
+                    if eng.rank == 0:
+                        print("Vector step: {}, total numsteps: {}, episodes: {}, violations: {}, successes: {}".format(
+                            step, cn["total_numsteps"], cn["episodes"], cn["num_viols"], cn["num_successes"]))
+                    data = {"test_stats": [], "train_stats": train_rollouts, "vec_stats": vec_stats}
+                    with open(osp.join(self.logdir, "run_stats.pkl"), "wb") as f:
+                        pickle.dump(data, f)
+                if cn["total_numsteps"] * eng.world > c.num_steps or cn["episodes"] * eng.world > c.num_eps:
+                    break
+        return vec_stats

@@ -1,0 +1,123 @@
+"""GPU: the drop-in surface (rrl_main / arg_utils / Experiment / SAC / QRiskWrapper / ReplayMemory / env classes)
+against the reference: offline-data generators bit-exact, replay API, and the reference's own 12-episode
+Navigation1 run (seed 7) reproduced through `Experiment` with live RNGs."""
+import os
+import random
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", ["nav1", "nav2"])
+def test_offline_data_generators_bit_exact(native, cuda, golden_dir, name):
+    import importlib
+    mod = importlib.import_module("env.navigation%s" % name[-1])
+    z = np.load(os.path.join(golden_dir, "offline_%s.npz" % name))
+    np.random.seed(int(z["seed"]))
+    tr = mod.get_offline_data(int(z["num"]))
+    assert len(tr) == len(z["state"])
+    assert np.array_equal(np.array([t[0] for t in tr]), z["state"])
+    assert np.array_equal(np.array([t[1] for t in tr]), z["action"])
+    assert np.array_equal(np.array([float(t[2]) for t in tr]), z["constraint"])
+    assert np.array_equal(np.array([t[3] for t in tr]), z["next_state"])
+
+
+def test_env_classes_follow_gym_contract(native, cuda):
+    from env.make_utils import make_env
+    from oracle import envs as oenvs
+    for name in ("navigation1", "navigation2", "maze"):
+        env = make_env(name)
+        np.random.seed(3)
+        s = env.reset()
+        assert s.shape == (2,) and env._max_episode_steps == 100 and env.action_space.shape == (2,)
+        env.action_space.seed(3)
+        for _ in range(5):
+            a = env.action_space.sample()
+            st = np.random.get_state()
+            s2, r, done, info = env.step(a)
+            assert set(info) >= {"constraint", "reward", "state", "next_state", "action", "success"}
+            if name == "maze":
+                ns, rr, d, c, su = oenvs.maze_step_scalar(s, a, env.steps - 1)
+            else:
+                np.random.set_state(st)
+                ns, rr, d, c, su = oenvs.nav_step(oenvs.KIND_BY_NAME[name], s[None], a[None], np.random.randn(1, 2))
+                ns, rr, d, c, su = ns[0], rr[0], d[0], c[0], su[0]
+            assert np.array_equal(s2, ns) and r == rr and bool(done) == bool(d) and info["constraint"] == int(c)
+            s = s2
+
+
+def test_replay_memory_api_matches_cpython(native, cuda):
+    from recovery_rl.replay_memory import ReplayMemory, ConstraintReplayMemory
+    mem = ReplayMemory(1000, 5)
+    cmem = ConstraintReplayMemory(1000, 5)
+    random.seed(5)
+    rs = np.random.RandomState(0)
+    for i in range(300):
+        s = np.array([float(i), 0.5])
+        mem.push(s, np.zeros(2, np.float32), -1.0, s + 1, 1.0)
+        cmem.push(s, np.zeros(2, np.float32), float(rs.rand() < 0.3), s + 1, 0.0)
+    assert len(mem) == 300 and len(cmem) == 300
+    st, a, r, s2, m = mem.sample(64)
+    assert np.array_equal(st[:, 0].astype(int), random.sample(range(300), 64))
+    assert st.shape == (64, 2) and r.shape == (64,) and np.all(s2 == st + 1)
+    st, a, c, s2, m = cmem.sample(64, pos_fraction=0.25)
+    pos = np.flatnonzero(cmem.pos_idx)
+    neg = np.flatnonzero(1 - cmem.pos_idx[:300])
+    ref = [pos[j] for j in random.sample(range(len(pos)), 16)] + [neg[j] for j in random.sample(range(len(neg)), 48)]
+    assert np.array_equal(st[:, 0].astype(int), ref)
+    assert c[:16].all() and not c[16:].any()
+    with pytest.raises(ValueError):
+        mem.sample(301)
+
+
+def test_experiment_reproduces_reference_run(native, cuda, golden_dir, tmp_path):
+    """scripts/navigation1.sh-style command through the drop-in Experiment with LIVE RNGs (numpy, torch, Box,
+    CPython-compatible sampler) == the reference's own run at seed 7: same episode lengths, constraint and
+    recovery flags; states to fp32 round-off of the recovery actions."""
+    import arg_utils
+    from recovery_rl.experiment import Experiment
+    z = np.load(os.path.join(golden_dir, "traj_nav1_seed7.npz"))
+    argv = [str(x) for x in z["argv"]]
+    argv[argv.index("--logdir") + 1] = str(tmp_path)
+    args = arg_utils.get_args(argv + ["--tensor_cores", "0"])
+    assert args.num_envs == 1
+    exp = Experiment(args)
+    off = exp.constraint_demo_data
+    assert np.array_equal(np.array([t[0] for t in off]), z["offline_state"])
+    assert np.array_equal(np.array([t[3] for t in off]), z["offline_next_state"])
+    exp.pretrain_critic_recovery()
+    infos, ep_len = [], []
+    for ep in range(1, 13):
+        info = exp.get_train_rollout(ep)
+        infos += info
+        ep_len.append(len(info))
+    assert ep_len == list(z["ep_len"])
+    assert np.array_equal(np.array([i["constraint"] for i in infos]), z["constraint"])
+    assert np.array_equal(np.array([bool(i["recovery"]) for i in infos]), z["recovery"].astype(bool))
+    assert np.allclose(np.array([i["state"] for i in infos]), z["state"], rtol=0, atol=1e-4)
+    assert np.allclose(np.array([i["action"] for i in infos]), z["action"], rtol=0, atol=1e-4)
+    assert exp.num_viols == int(z["num_viols"]) and exp.total_numsteps == int(z["total_numsteps"])
+    assert exp.updates == int(z["updates"])
+    stride = int(z["stride"])
+    for net in ("critic", "policy", "qrisk", "recovery"):
+        for i, p in enumerate(exp.agent.arena.params(net)):
+            ref = z["final_%s_%d" % (net, i)]
+            assert np.allclose(p.ravel()[::stride], ref, rtol=0, atol=2e-3), (net, i, np.abs(p.ravel()[::stride] - ref).max())
+
+
+def test_vectorised_experiment_runs(native, cuda, tmp_path):
+    import arg_utils
+    from recovery_rl.experiment import Experiment
+    args = arg_utils.get_args(["--env-name", "maze", "--use_recovery", "--MF_recovery", "--gamma_safe", "0.5",
+                               "--eps_safe", "0.15", "--pos_fraction", "0.3", "--num_unsafe_transitions", "2000",
+                               "--critic_safe_pretraining_steps", "20", "--batch_size", "64", "--num_envs", "1024",
+                               "--num_steps", "60000", "--seed", "3", "--logdir", str(tmp_path), "--replay_size", "100000",
+                               "--safe_replay_size", "100000"])
+    exp = Experiment(args)
+    stats = exp.run()
+    assert stats[-1]["total_numsteps"] > 60000 and stats[-1]["error"] == 0
+    assert stats[-1]["sac_updates"] > 40 and stats[-1]["qrisk_updates"] > 40
+    assert os.path.exists(os.path.join(exp.logdir, "run_stats.pkl")) and os.path.exists(os.path.join(exp.logdir, "args.pkl"))
