@@ -1,0 +1,45 @@
+"""Collective plumbing of the sharded engine (one process per GPU, torch.distributed; NCCL on the GPUs, gloo in
+the CPU tests).  The path shards by env copies: every rank owns its envs, its replay shards and its sampler
+stream; the only exchange is the gradient sum before each optimizer step (+ one scalar for the Q_risk gate).
+"""
+import torch
+
+from . import native
+
+GRAD_NETS = ("critic", "policy", "qrisk", "recovery")
+
+
+def grad_ranges(cfg):
+    """{net: (offset, count)} of the four trainable nets inside the flat arena (contiguous, in this order)."""
+    return {name: native.agent_grad_range(cfg, native.NET_NAMES.index(name)) for name in GRAD_NETS}
+
+
+def span(ranges, names):
+    lo = min(ranges[n][0] for n in names)
+    hi = max(ranges[n][0] + ranges[n][1] for n in names)
+    return lo, hi
+
+
+def all_reduce_grads(arena, ranges, names, group=None):
+    """SUM the gradient block of `names` (adjacent nets -> one collective); Adam applies 1/world (grad_scale)."""
+    import torch.distributed as dist
+    lo, hi = span(ranges, names)
+    dist.all_reduce(arena[lo:hi], op=dist.ReduceOp.SUM, group=group)
+
+
+def sync_gate_counts(counters, group=None):
+    """The Q_risk online gate (experiment.py:407-410) must open on every rank in the same step, so each rank adds
+    the violations seen elsewhere: EXT_VIOLS = sum over other ranks of (num_viols + offline_viols)."""
+    import torch.distributed as dist
+    local = (counters[native.C_NUM_VIOLS] + counters[native.C_OFFLINE_VIOLS]).reshape(1).clone()
+    total = local.clone()
+    dist.all_reduce(total, op=dist.ReduceOp.SUM, group=group)
+    counters[native.C_EXT_VIOLS:native.C_EXT_VIOLS + 1] = total - local
+    return int(0)
+
+
+def shard(n_total, rank, world):
+    """[lo, hi) of the env copies rank owns when a global env count is split (remainder to the first ranks)."""
+    base, rem = divmod(int(n_total), int(world))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)

@@ -16,7 +16,7 @@ optimizer step over the flat gradient block (1/world applied inside Adam).
 import numpy as np
 import torch
 
-from . import native
+from . import dist_utils, native
 from .arena import AgentArena
 
 HORIZON = {"navigation1": 100, "navigation2": 100, "maze": 100}
@@ -160,26 +160,13 @@ class VecEngine(object):
     def _all_reduce(self, net_names):
         if self.world == 1:
             return
-        import torch.distributed as dist
         if self._grad_views is None:
-            self._grad_views = {}
-            for name in ("critic", "policy", "qrisk", "recovery"):
-                off, cnt = native.agent_grad_range(self.cfg, native.NET_NAMES.index(name))
-                self._grad_views[name] = (off, cnt)
-        lo = min(self._grad_views[nm][0] for nm in net_names)
-        hi = max(self._grad_views[nm][0] + self._grad_views[nm][1] for nm in net_names)
-        dist.all_reduce(self.arena[lo:hi], op=dist.ReduceOp.SUM, group=self.pg)
+            self._grad_views = dist_utils.grad_ranges(self.cfg)
+        dist_utils.all_reduce_grads(self.arena, self._grad_views, net_names, self.pg)
 
     def _sync_gate_counts(self):
-        """multi-GPU: the Q_risk online gate (experiment.py:407-410) must open on every rank at once, so it
-        sees the global violation count: EXT_VIOLS = sum over the other ranks of (num_viols + offline)."""
-        if self.world == 1:
-            return
-        import torch.distributed as dist
-        local = (self.counters[native.C_NUM_VIOLS] + self.counters[native.C_OFFLINE_VIOLS]).reshape(1).clone()
-        total = local.clone()
-        dist.all_reduce(total, op=dist.ReduceOp.SUM, group=self.pg)
-        self.counters[native.C_EXT_VIOLS:native.C_EXT_VIOLS + 1] = total - local
+        if self.world > 1:
+            dist_utils.sync_gate_counts(self.counters, self.pg)
 
     def qrisk_update(self, sample_cfg=None, count=True):
         cfg, ar, cn = self.cfg, self.arena, self.counters

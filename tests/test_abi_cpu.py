@@ -1,0 +1,76 @@
+"""CPU: librrl.so builds (nvcc cross-compiles sm_100a without a GPU), loads, and exports every entry point that
+include/rrl.h declares; host-only entry points (arena layout, CPython-compatible seeding) behave; compute
+entry points refuse to run without a device instead of falling back."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_every_declared_symbol_is_exported(native):
+    hdr = open(os.path.join(ROOT, "include", "rrl.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = sorted(set(re.findall(r"\b(rrl_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(names) >= 25
+    lib = ctypes.CDLL(native.LIB_PATH)
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+    assert native.version() == 1
+
+
+def test_arena_layout_matches_reference_parameter_shapes(native):
+    cfg = native.agent_config(max_batch=256)
+    shapes = {
+        "critic": [(256, 4), (256,), (256, 256), (256,), (1, 256), (1,)] * 2,
+        "policy": [(256, 2), (256,), (256, 256), (256,), (2, 256), (2,), (2, 256), (2,)],
+        "qrisk": [(4,), (4,)] + [(256, 4), (256,), (256, 256), (256,), (1, 256), (1,)] * 2,
+        "recovery": [(2,), (256, 2), (256,), (256, 256), (256,), (2, 256), (2,)],
+    }
+    shapes["critic_target"] = shapes["critic"]
+    shapes["qrisk_target"] = shapes["qrisk"]
+    seen = []
+    for net, want in shapes.items():
+        idx = native.NET_NAMES.index(net)
+        assert native.agent_num_tensors(idx) == len(want)
+        for i, shp in enumerate(want):
+            off, rows, cols = native.agent_tensor_info(cfg, idx, i)
+            assert ((rows, cols) if cols else (rows,)) == shp
+            assert off % 4 == 0
+            seen.append((off, int(np.prod(shp))))
+    seen.sort()
+    for (o0, n0), (o1, _) in zip(seen, seen[1:]):
+        assert o0 + n0 <= o1                                   # no overlap
+    assert native.agent_arena_floats(cfg) > seen[-1][0]
+    with pytest.raises(native.RRLError):
+        native.agent_tensor_info(cfg, 0, 99)
+    bad = native.agent_config(hidden=128)
+    assert native.agent_arena_floats(bad) < 0                  # kernels are specialised for hidden 256
+
+
+def test_seed_matches_cpython(native):
+    import random
+    from oracle.replay import MT19937
+    for seed in (0, 1, 123456, 2 ** 40 + 5, -3):
+        st = native.mt19937_seed(seed).numpy().view(np.uint32)
+        assert np.array_equal(st, MT19937(seed).state625())
+        random.seed(seed)
+        ref = random.getstate()[1]
+        assert list(st[:624]) == list(ref[:624])
+
+
+def test_no_cpu_fallback(native):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(native.RRLError):
+        native.require_cuda()
+    from recovery_rl.engine import VecEngine
+    with pytest.raises(native.RRLError):
+        VecEngine("maze", 128)
+    cpu = torch.zeros(8)
+    with pytest.raises(native.RRLError):
+        native.p(cpu, "f32")
