@@ -50,7 +50,7 @@ def parse():
     ap.add_argument("--pretrain", type=int, default=1000, help="Q_risk pre-training updates (untimed)")
     ap.add_argument("--demos", type=int, default=10000)
     ap.add_argument("--seed", type=int, default=1)
-    ap.add_argument("--tc", type=int, default=int(os.environ.get("RRL_TENSOR_CORES", "0")))
+    ap.add_argument("--tc", type=int, default=int(os.environ.get("RRL_TENSOR_CORES", "1")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-steps", type=int, default=400)
     return ap.parse_args()
@@ -351,16 +351,23 @@ def run_ours(args, rank, world, local_rank):
                            "l2": "flushed between timed steps (256 MiB write, outside the per-step event pairs)",
                            "timing": "sum of per-step CUDA-event intervals on the launching stream, max over ranks",
                            "rng": "Philox4x32-10 on device (value); host draws uploaded (e2e)",
-                           "cuda_graph": True, "tensor_cores": bool(args.tc),
+                           "cuda_graph": eng.graph is not None, "tensor_cores": bool(args.tc),
                            "grad_allreduce": "nccl, flat grad block, 3 per step" if world > 1 else "none (1 GPU)"},
                 "roofline": roofline, "roofline_env": roofline_env, "cpu_baseline": cpu_baseline, "e2e": e2e,
                 "gpu_launches": eng.launches_per_step * K, "launches_per_step": eng.launches_per_step, "clocks": clocks,
                 "counters": {k: c[k] for k in ("total_numsteps", "episodes", "num_viols", "num_successes", "sac_updates",
                                                "qrisk_updates")}}
         print(json.dumps(line))
+        sys.stdout.flush()
     if world > 1:
+        # the captured graphs hold NCCL kernels: drop them before the communicator, then leave without the
+        # (sometimes blocking) communicator teardown
+        eng.graph = None
+        torch.cuda.synchronize()
         dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        os._exit(0)
 
 
 def main():

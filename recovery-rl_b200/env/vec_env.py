@@ -9,9 +9,9 @@ from recovery_rl import native
 
 
 class PointEnvBatch(object):
-    def __init__(self, env_name, n=1, device="cuda:0", horizon=100, seed=0):
+    def __init__(self, env_name, n=1, device=None, horizon=100, seed=0):
         native.require_cuda()
-        self.device = torch.device(device)
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.kind = native.ENV_KIND[env_name]
         self.n = n
         self.cfg = native.env_config(self.kind, n, horizon=horizon, seed=seed, auto_reset=False)

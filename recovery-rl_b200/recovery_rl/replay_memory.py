@@ -27,9 +27,9 @@ def _seed_shared(seed, device):
 class ReplayMemory(object):
     is_constraint = False
 
-    def __init__(self, capacity, seed, device="cuda:0"):
+    def __init__(self, capacity, seed, device=None):
         native.require_cuda()
-        self.device = torch.device(device)
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         _seed_shared(seed, self.device)                         # random.seed(seed)
         self.capacity = int(capacity)
         self.cap_pad = (self.capacity + 15) // 16 * 16
