@@ -349,12 +349,12 @@ __global__ void __launch_bounds__(kThreads, 2) act_kernel(const __grid_constant_
 // ---------------------------------------------------------------------------------------------
 // backward building blocks (training batches: rows <= max_batch)
 // ---------------------------------------------------------------------------------------------
-// (1) head backward: dh2 = (dout W3) * relu'(h2)  [+ transposed copy], dW3, db3, db2
+// (1) head backward: dh2 = (dout W3) * relu'(h2), dW3, db3, db2
 struct HeadBwdPass {
     const float* dout;  // [rows][stride]
     int stride, n_out, na;
     const float *W3a, *W3b, *h2;
-    float *dh2, *dh2t;            // [rows][H], [H][R]
+    float* dh2;                   // [rows][H]
     float *gW3a, *gW3b, *gb3a, *gb3b, *gb2;  // NULL when no weight grads are needed
 };
 struct HeadBwdArgs {
@@ -384,7 +384,6 @@ __global__ void __launch_bounds__(kThreads) head_backward_kernel(const __grid_co
         g = fmaf(d[1], w3[1], g); g = fmaf(d[2], w3[2], g); g = fmaf(d[3], w3[3], g);
         g = h > 0.f ? g : 0.f;
         P.dh2[r * H + j] = g;
-        P.dh2t[(int64_t)j * A.R + r] = g;
         gb2 += g;
 #pragma unroll
         for (int o = 0; o < 4; ++o) gw[o] = fmaf(d[o], h, gw[o]);
@@ -425,7 +424,7 @@ __global__ void __launch_bounds__(kThreads) head_backward_kernel(const __grid_co
 }
 
 // (2) streamed GEMM: C[m][n] = sum_k A[k][m] * B[k][n], n = 0..255, m tile of 32, both operands k-major.
-//     DATA  : A = dh2t [H][R] (k = hidden, m = row), B = W2 [H][H], C = dh1 [row][H] masked by h1 > 0
+//     DATA  : A = dh2 [rows][H] read TRANSPOSED (k = hidden, m = row), B = W2 [H][H], C = dh1 [row][H] masked by h1 > 0
 //     WEIGHT: A = dh2 [rows][H] (k = row, m = out unit), B = h1 [rows][H], C = gW2 [H][H]
 struct GemmPass {
     const float *A, *B;
@@ -454,9 +453,17 @@ __global__ void __launch_bounds__(kThreads) gemm_stream_kernel(const __grid_cons
     auto load = [&](int c, int buf) {
         const int k0 = c * KC;
         if (t < 128) {
-            const int kk = t >> 3, m4 = t & 7;
-            if (k0 + kk < K) cp_async16(&As[buf][kk][m4 * 4], P.A + (size_t)(k0 + kk) * P.lda + m0 + m4 * 4);
-            else *reinterpret_cast<float4*>(&As[buf][kk][m4 * 4]) = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (P.k_is_rows) {  // WEIGHT: A is k-major already
+                const int kk = t >> 3, m4 = t & 7;
+                if (k0 + kk < K) cp_async16(&As[buf][kk][m4 * 4], P.A + (size_t)(k0 + kk) * P.lda + m0 + m4 * 4);
+                else *reinterpret_cast<float4*>(&As[buf][kk][m4 * 4]) = make_float4(0.f, 0.f, 0.f, 0.f);
+            } else {            // DATA: A(k, m) = dh2[m][k] -> transposing load (4 consecutive k of one row)
+                const int m = t >> 2, kq = t & 3;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (m0 + m < M) v = *reinterpret_cast<const float4*>(P.A + (size_t)(m0 + m) * H + k0 + kq * 4);
+                As[buf][kq * 4 + 0][m] = v.x; As[buf][kq * 4 + 1][m] = v.y;
+                As[buf][kq * 4 + 2][m] = v.z; As[buf][kq * 4 + 3][m] = v.w;
+            }
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -800,9 +807,14 @@ struct AdamArgs {
 };
 __global__ void __launch_bounds__(kThreads) adam_kernel(const __grid_constant__ AdamArgs A) {
     if (A.counters[A.rows_counter] <= 0) return;
-    const double tstep = (double)(A.counters[A.t_counter] + 1);
-    const float bc1 = (float)(1.0 - pow((double)A.b1, tstep));
-    const float bc2s = (float)sqrt(1.0 - pow((double)A.b2, tstep));
+    __shared__ float s_bc[2];
+    if (threadIdx.x == 0) {  // bias corrections in double, once per block
+        const double tstep = (double)(A.counters[A.t_counter] + 1);
+        s_bc[0] = (float)(1.0 - pow((double)A.b1, tstep));
+        s_bc[1] = (float)sqrt(1.0 - pow((double)A.b2, tstep));
+    }
+    __syncthreads();
+    const float bc1 = s_bc[0], bc2s = s_bc[1];
     const float step_size = A.lr / bc1;
     for (int64_t i = blockIdx.x * (int64_t)kThreads + threadIdx.x; i < A.count; i += (int64_t)gridDim.x * kThreads) {
         const int64_t o = A.off + i;
@@ -1200,7 +1212,7 @@ extern "C" int rrl_sac_backward(const rrl_agent_config_t* cfg, float* arena, con
             const HeadW& w = (q & 1) ? c2 : c1;
             const HeadG& g = (q & 1) ? g2 : g1;
             p.dout = dout[q]; p.stride = 1; p.n_out = 1; p.na = 1;
-            p.W3a = w.W3a; p.h2 = arena + L.h2[q]; p.dh2 = arena + L.dh2[q]; p.dh2t = arena + L.dh2t[q];
+            p.W3a = w.W3a; p.h2 = arena + L.h2[q]; p.dh2 = arena + L.dh2[q];
             if (q < 2) { p.gW3a = g.W3a; p.gb3a = g.b3a; p.gb2 = g.b2; }
         }
         head_backward_kernel<<<dim3(H / 32, 4), kThreads, 0, st>>>(A);
@@ -1212,7 +1224,7 @@ extern "C" int rrl_sac_backward(const rrl_agent_config_t* cfg, float* arena, con
         G.rows_ptr = rows_ptr;
         for (int q = 0; q < 4; ++q) {
             GemmPass& p = G.p[q];
-            p.A = arena + L.dh2t[q]; p.lda = (int)R; p.B = ((q & 1) ? c2 : c1).W2; p.k_is_rows = 0;
+            p.A = arena + L.dh2[q]; p.lda = H; p.B = ((q & 1) ? c2 : c1).W2; p.k_is_rows = 0;
             p.mask = arena + L.h1[q]; p.C = arena + L.dh1[q];
         }
         for (int q = 0; q < 2; ++q) {
@@ -1253,7 +1265,7 @@ extern "C" int rrl_sac_backward(const rrl_agent_config_t* cfg, float* arena, con
         A.rows_ptr = rows_ptr; A.R = R;
         HeadBwdPass& p = A.p[0];
         p.dout = R4(R4_DRAW_POL); p.stride = 4; p.n_out = 4; p.na = 2;
-        p.W3a = pw.W3a; p.W3b = pw.W3b; p.h2 = arena + L.h2[4]; p.dh2 = arena + L.dh2[4]; p.dh2t = arena + L.dh2t[4];
+        p.W3a = pw.W3a; p.W3b = pw.W3b; p.h2 = arena + L.h2[4]; p.dh2 = arena + L.dh2[4];
         p.gW3a = pg.W3a; p.gW3b = pg.W3b; p.gb3a = pg.b3a; p.gb3b = pg.b3b; p.gb2 = pg.b2;
         head_backward_kernel<<<dim3(H / 32, 1), kThreads, 0, st>>>(A);
         RRL_CHECK_LAUNCH();
@@ -1262,7 +1274,7 @@ extern "C" int rrl_sac_backward(const rrl_agent_config_t* cfg, float* arena, con
         GemmArgs G;
         memset(&G, 0, sizeof(G));
         G.rows_ptr = rows_ptr;
-        G.p[0].A = arena + L.dh2t[4]; G.p[0].lda = (int)R; G.p[0].B = pw.W2; G.p[0].mask = arena + L.h1[4];
+        G.p[0].A = arena + L.dh2[4]; G.p[0].lda = H; G.p[0].B = pw.W2; G.p[0].mask = arena + L.h1[4];
         G.p[0].C = arena + L.dh1[4];
         G.p[1].A = arena + L.dh2[4]; G.p[1].lda = H; G.p[1].B = arena + L.h1[4]; G.p[1].k_is_rows = 1; G.p[1].C = pg.W2;
         const int mt = (int)((R > H ? R : H) / 32);
@@ -1354,7 +1366,7 @@ extern "C" int rrl_qrisk_backward(const rrl_agent_config_t* cfg, float* arena, c
             const HeadW& w = q ? c2 : c1;
             const HeadG& g = q ? g2 : g1;
             p.dout = q ? RA(RA_QR_DQ2) : RA(RA_QR_DQ1); p.stride = 1; p.n_out = 1; p.na = 1;
-            p.W3a = w.W3a; p.h2 = arena + L.h2[q]; p.dh2 = arena + L.dh2[q]; p.dh2t = arena + L.dh2t[q];
+            p.W3a = w.W3a; p.h2 = arena + L.h2[q]; p.dh2 = arena + L.dh2[q];
             p.gW3a = g.W3a; p.gb3a = g.b3a; p.gb2 = g.b2;
         }
         head_backward_kernel<<<dim3(H / 32, 2), kThreads, 0, st>>>(A);
@@ -1366,7 +1378,7 @@ extern "C" int rrl_qrisk_backward(const rrl_agent_config_t* cfg, float* arena, c
         G.rows_ptr = rows_ptr;
         for (int q = 0; q < 2; ++q) {
             GemmPass& p = G.p[q];
-            p.A = arena + L.dh2t[q]; p.lda = (int)R; p.B = (q ? c2 : c1).W2; p.mask = arena + L.h1[q]; p.C = arena + L.dh1[q];
+            p.A = arena + L.dh2[q]; p.lda = H; p.B = (q ? c2 : c1).W2; p.mask = arena + L.h1[q]; p.C = arena + L.dh1[q];
             GemmPass& w = G.p[2 + q];
             w.A = arena + L.dh2[q]; w.lda = H; w.B = arena + L.h1[q]; w.k_is_rows = 1; w.C = (q ? g2 : g1).W2;
         }
@@ -1453,7 +1465,7 @@ extern "C" int rrl_recovery_backward(const rrl_agent_config_t* cfg, float* arena
         for (int q = 0; q < 2; ++q) {
             HeadBwdPass& p = A.p[q];
             p.dout = q ? RA(RA_REC_DQ2) : RA(RA_REC_DQ1); p.stride = 1; p.n_out = 1; p.na = 1;
-            p.W3a = (q ? c2 : c1).W3a; p.h2 = arena + L.h2[2 + q]; p.dh2 = arena + L.dh2[2 + q]; p.dh2t = arena + L.dh2t[2 + q];
+            p.W3a = (q ? c2 : c1).W3a; p.h2 = arena + L.h2[2 + q]; p.dh2 = arena + L.dh2[2 + q];
         }
         head_backward_kernel<<<dim3(H / 32, 2), kThreads, 0, st>>>(A);
         RRL_CHECK_LAUNCH();
@@ -1464,7 +1476,7 @@ extern "C" int rrl_recovery_backward(const rrl_agent_config_t* cfg, float* arena
         G.rows_ptr = rows_ptr;
         for (int q = 0; q < 2; ++q) {
             GemmPass& p = G.p[q];
-            p.A = arena + L.dh2t[2 + q]; p.lda = (int)R; p.B = (q ? c2 : c1).W2; p.mask = arena + L.h1[2 + q];
+            p.A = arena + L.dh2[2 + q]; p.lda = H; p.B = (q ? c2 : c1).W2; p.mask = arena + L.h1[2 + q];
             p.C = arena + L.dh1[2 + q];
         }
         gemm_stream_kernel<<<dim3((int)(R / 32), 2), kThreads, 0, st>>>(G);
@@ -1497,7 +1509,7 @@ extern "C" int rrl_recovery_backward(const rrl_agent_config_t* cfg, float* arena
         A.rows_ptr = rows_ptr; A.R = R;
         HeadBwdPass& p = A.p[0];
         p.dout = R4(R4_DRAW_REC); p.stride = 4; p.n_out = 2; p.na = 2;
-        p.W3a = pw.W3a; p.h2 = arena + L.h2[4]; p.dh2 = arena + L.dh2[4]; p.dh2t = arena + L.dh2t[4];
+        p.W3a = pw.W3a; p.h2 = arena + L.h2[4]; p.dh2 = arena + L.dh2[4];
         p.gW3a = pg.W3a; p.gb3a = pg.b3a; p.gb2 = pg.b2;
         head_backward_kernel<<<dim3(H / 32, 1), kThreads, 0, st>>>(A);
         RRL_CHECK_LAUNCH();
@@ -1506,7 +1518,7 @@ extern "C" int rrl_recovery_backward(const rrl_agent_config_t* cfg, float* arena
         GemmArgs G;
         memset(&G, 0, sizeof(G));
         G.rows_ptr = rows_ptr;
-        G.p[0].A = arena + L.dh2t[4]; G.p[0].lda = (int)R; G.p[0].B = pw.W2; G.p[0].mask = arena + L.h1[4];
+        G.p[0].A = arena + L.dh2[4]; G.p[0].lda = H; G.p[0].B = pw.W2; G.p[0].mask = arena + L.h1[4];
         G.p[0].C = arena + L.dh1[4];
         G.p[1].A = arena + L.dh2[4]; G.p[1].lda = H; G.p[1].B = arena + L.h1[4]; G.p[1].k_is_rows = 1; G.p[1].C = pg.W2;
         const int mt = (int)((R > H ? R : H) / 32);

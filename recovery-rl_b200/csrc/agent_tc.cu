@@ -8,12 +8,14 @@
 //     D += Ahi*Bhi ;  D += Ahi*Blo ;  D += Alo*Bhi          (the dropped Alo*Blo term is ~2^-22 relative)
 // which reproduces the fp32 product to ~1e-6 relative -- measured against the SIMT path in the tests.
 //
-// Per CTA (one per SM, persistent over 128-row tiles), 6 warps:
-//   warps 0-3  one thread per env row: layer 1 (K = 2|4, SIMT) -> fp16 hi/lo A tiles written straight into
-//              the UMMA canonical K-major layout; later the epilogue of the same row (TMEM lane == row):
-//              +b2, ReLU, the 1..4 output heads, tanh-Gaussian / sigmoid / recovery maths, action select
-//   warp 4     TMEM allocation + the single MMA-issuing thread
-//   warp 5     one thread streams the pre-split weight images (32 KB per k-chunk) with cp.async.bulk
+// Per CTA (one per SM, persistent over 128-row tiles), 18 warps:
+//   warps 0-15 four threads per env row (TMEM lane quadrant = warp % 4, quarter q = warp / 4): layer 1
+//              (K = 2|4, SIMT) -> fp16 hi/lo A tiles written straight into the UMMA canonical K-major layout
+//              (thread q writes core column q of each 32-wide k-chunk); later the epilogue of the same row:
+//              columns [64q, 64q+64) through tcgen05.ld, +b2, ReLU, partial head sums exchanged through smem,
+//              then the tanh-Gaussian / sigmoid / recovery maths and the action select
+//   warp 16    TMEM allocation + the single MMA-issuing thread
+//   warp 17    one thread streams the pre-split weight images (32 KB per k-chunk) with cp.async.bulk
 // Pipelines: a 3-stage smem ring (full/empty mbarriers; tcgen05.commit frees a stage) and two 256-column
 // TMEM accumulators (acc_full / acc_empty) so the epilogue of one network overlaps the MMAs of the next.
 // Pass order per tile: policy, recovery, Q_risk head 1, Q_risk head 2 (the two state-only networks first so
@@ -32,7 +34,8 @@ constexpr int NCHUNK = H / KCH;          // 8
 constexpr int A_IMG = TM * KCH * 2;      // 8 KB   (one fp16 image of the A chunk)
 constexpr int B_IMG = H * KCH * 2;       // 16 KB
 constexpr int STAGE_BYTES = 2 * A_IMG + 2 * B_IMG;  // 48 KB: [A hi][A lo][B hi][B lo]
-constexpr int kTcThreads = 192;
+constexpr int kProd = 512;                // producer/epilogue threads: 4 per row (16 warps)
+constexpr int kTcThreads = kProd + 64;    // + MMA warp + loader warp
 constexpr float SA = 16.0f, SB = 64.0f;  // power-of-two operand scales
 constexpr float INV_SCALE = 1.0f / (SA * SB);
 // canonical K-major, no swizzle: core matrix = 8 rows x 16 B (128 B contiguous)
@@ -57,6 +60,7 @@ struct TcSmall {
 struct TcSmem {
     unsigned char stage[NSTAGE][STAGE_BYTES];
     TcSmall sm;
+    float4 part[2][4][TM];   // per-row partial head sums of the 4 column quarters (double-buffered)
     unsigned long long full[NSTAGE], empty[NSTAGE], acc_full[2], acc_empty[2];
     uint32_t tmem_base;
 };
@@ -183,54 +187,65 @@ __device__ __forceinline__ const HeadW& pass_head(const ActArgs& a, int p) {
     return p == PASS_POL ? a.pol : (p == PASS_REC ? a.rec : (p == PASS_QR1 ? a.qr1 : a.qr2));
 }
 
-// producer: layer 1 of `pass` for this thread's row, k-chunk c -> stage (fp16 hi/lo, canonical layout)
-__device__ __forceinline__ void produce_chunk(TcSmem& S, int pass, int c, int stage, int t, float x0, float x1, float x2,
-                                              float x3, bool four) {
+// producer: layer 1 of `pass`, row r, the 8 hidden units of core column q of k-chunk c -> stage (fp16 hi/lo,
+// canonical layout).  W1/b1 are staged pre-multiplied by SA (a power of two: exact).
+__device__ __forceinline__ void produce_chunk(TcSmem& S, int pass, int c, int stage, int r, int q, float x0, float x1,
+                                              float x2, float x3, bool four) {
     unsigned char* a_hi = S.stage[stage];
     unsigned char* a_lo = a_hi + A_IMG;
+    __align__(16) __half hi[8], lo[8];
 #pragma unroll
-    for (int kc = 0; kc < KCH / 8; ++kc) {
-        __align__(16) __half hi[8], lo[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            const int k = c * KCH + kc * 8 + e;
-            const float4 wv = *reinterpret_cast<const float4*>(S.sm.W1[pass][k]);
-            float h = fmaf(wv.x, x0, S.sm.b1[pass][k]);
-            h = fmaf(wv.y, x1, h);
-            if (four) {
-                h = fmaf(wv.z, x2, h);
-                h = fmaf(wv.w, x3, h);
-            }
-            h = fmaxf(h, 0.f) * SA;
-            split_f16(h, &hi[e], &lo[e]);
+    for (int e = 0; e < 8; ++e) {
+        const int k = c * KCH + q * 8 + e;
+        const float4 wv = *reinterpret_cast<const float4*>(S.sm.W1[pass][k]);
+        float h = fmaf(wv.x, x0, S.sm.b1[pass][k]);
+        h = fmaf(wv.y, x1, h);
+        if (four) {
+            h = fmaf(wv.z, x2, h);
+            h = fmaf(wv.w, x3, h);
         }
-        *reinterpret_cast<uint4*>(a_hi + kc * LBO_A + t * 16) = *reinterpret_cast<const uint4*>(hi);
-        *reinterpret_cast<uint4*>(a_lo + kc * LBO_A + t * 16) = *reinterpret_cast<const uint4*>(lo);
+        split_f16(fmaxf(h, 0.f), &hi[e], &lo[e]);
     }
+    *reinterpret_cast<uint4*>(a_hi + q * LBO_A + r * 16) = *reinterpret_cast<const uint4*>(hi);
+    *reinterpret_cast<uint4*>(a_lo + q * LBO_A + r * 16) = *reinterpret_cast<const uint4*>(lo);
 }
 
-// epilogue: this thread's row of accumulator `d` -> raw head outputs (W3 relu(acc + b2) + b3)
-__device__ __forceinline__ void epilogue_row(TcSmem& S, int pass, int n_out, uint32_t taddr, float raw[4]) {
+// epilogue: columns [64 q, 64 q + 64) of this thread's row of accumulator `d` -> partial head sums
+__device__ __forceinline__ float4 epilogue_quarter(TcSmem& S, int pass, int n_out, uint32_t taddr, int q) {
     float out[4] = {0.f, 0.f, 0.f, 0.f};
+    const float4* b2v = reinterpret_cast<const float4*>(S.sm.b2[pass]);
+    const float4* w0v = reinterpret_cast<const float4*>(S.sm.w3[pass][0]);
+    const float4* w1v = reinterpret_cast<const float4*>(S.sm.w3[pass][1]);
+    const float4* w2v = reinterpret_cast<const float4*>(S.sm.w3[pass][2]);
+    const float4* w3v = reinterpret_cast<const float4*>(S.sm.w3[pass][3]);
 #pragma unroll 1
-    for (int cc = 0; cc < H / 32; ++cc) {
+    for (int cc = 0; cc < 2; ++cc) {
         float v[32];
-        tmem_ld32(taddr + cc * 32, v);
+        const int col0 = q * 64 + cc * 32;
+        tmem_ld32(taddr + col0, v);
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            const int k = cc * 32 + j;
-            const float h = fmaxf(fmaf(v[j], INV_SCALE, S.sm.b2[pass][k]), 0.f);
-            out[0] = fmaf(h, S.sm.w3[pass][0][k], out[0]);
-            if (n_out > 1) out[1] = fmaf(h, S.sm.w3[pass][1][k], out[1]);
+        for (int j4 = 0; j4 < 8; ++j4) {
+            const int i4 = (col0 >> 2) + j4;
+            const float4 b = b2v[i4];
+            const float h0 = fmaxf(fmaf(v[4 * j4 + 0], INV_SCALE, b.x), 0.f);
+            const float h1 = fmaxf(fmaf(v[4 * j4 + 1], INV_SCALE, b.y), 0.f);
+            const float h2 = fmaxf(fmaf(v[4 * j4 + 2], INV_SCALE, b.z), 0.f);
+            const float h3 = fmaxf(fmaf(v[4 * j4 + 3], INV_SCALE, b.w), 0.f);
+            const float4 wa = w0v[i4];
+            out[0] = fmaf(h3, wa.w, fmaf(h2, wa.z, fmaf(h1, wa.y, fmaf(h0, wa.x, out[0]))));
+            if (n_out > 1) {
+                const float4 wb = w1v[i4];
+                out[1] = fmaf(h3, wb.w, fmaf(h2, wb.z, fmaf(h1, wb.y, fmaf(h0, wb.x, out[1]))));
+            }
             if (n_out > 2) {
-                out[2] = fmaf(h, S.sm.w3[pass][2][k], out[2]);
-                out[3] = fmaf(h, S.sm.w3[pass][3][k], out[3]);
+                const float4 wc = w2v[i4], wd = w3v[i4];
+                out[2] = fmaf(h3, wc.w, fmaf(h2, wc.z, fmaf(h1, wc.y, fmaf(h0, wc.x, out[2]))));
+                out[3] = fmaf(h3, wd.w, fmaf(h2, wd.z, fmaf(h1, wd.y, fmaf(h0, wd.x, out[3]))));
             }
         }
     }
-#pragma unroll
-    for (int o = 0; o < 4; ++o) raw[o] = out[o] + S.sm.b3[pass][o];
+    return make_float4(out[0], out[1], out[2], out[3]);
 }
 
 __global__ void __launch_bounds__(kTcThreads, 1) act_tc_kernel(const __grid_constant__ TcActArgs T) {
@@ -252,8 +267,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) act_tc_kernel(const __grid_cons
                 const float2 v = *reinterpret_cast<const float2*>(w.W1 + k * 2);
                 w1.x = v.x; w1.y = v.y;
             }
+            w1.x *= SA; w1.y *= SA; w1.z *= SA; w1.w *= SA;   // exact (power of two): h1 * SA comes out of layer 1
             *reinterpret_cast<float4*>(S.sm.W1[p][k]) = w1;
-            S.sm.b1[p][k] = w.b1[k];
+            S.sm.b1[p][k] = w.b1[k] * SA;
             S.sm.b2[p][k] = w.b2[k];
             for (int o = 0; o < 4; ++o) {
                 float v = 0.f;
@@ -272,16 +288,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) act_tc_kernel(const __grid_cons
     if (t < 2 && n_pass > 1) S.sm.log_std[t] = A.rec.log_std[t];
     if (t == 0) {
         for (int s = 0; s < NSTAGE; ++s) {
-            mbar_init(smem_u32(&S.full[s]), TM + 1);  // 128 producer arrivals + the loader's expect_tx arrival
+            mbar_init(smem_u32(&S.full[s]), kProd + 1);  // producer arrivals + the loader's expect_tx arrival
             mbar_init(smem_u32(&S.empty[s]), 1);      // tcgen05.commit
         }
         for (int d = 0; d < 2; ++d) {
             mbar_init(smem_u32(&S.acc_full[d]), 1);   // tcgen05.commit
-            mbar_init(smem_u32(&S.acc_empty[d]), TM); // 128 epilogue arrivals
+            mbar_init(smem_u32(&S.acc_empty[d]), kProd); // epilogue arrivals
         }
         fence_barrier_init();
     }
-    if (warp == 4) {
+    if (warp == kProd / 32) {
         tmem_alloc(smem_u32(&S.tmem_base), 512);
         tmem_relinquish();
     }
@@ -293,13 +309,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) act_tc_kernel(const __grid_cons
     const uint64_t vstep = A.counters ? (uint64_t)A.counters[RRL_C_VEC_STEP] : 0;
     const bool random_phase = A.counters && !A.eval && (A.start_steps > A.counters[RRL_C_TOTAL_NUMSTEPS]);
 
-    if (warp < 4) {
-        // ================= producer + epilogue: thread t owns row t of every tile =================
+    if (warp < kProd / 32) {
+        // ========== producer + epilogue: 4 threads (q = 0..3) per row r; TMEM lane quadrant = warp % 4 ==========
         uint32_t it = 0;            // running (pass, chunk) index: stage = it % NSTAGE
         uint32_t acc_use[2] = {0, 0};
-        const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+        uint32_t n_epi = 0;         // epilogues done (selects the partial-sum buffer)
+        const int q = warp >> 2, r = (warp & 3) * 32 + lane;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            const int64_t row = tile * TM + t;
+            const int64_t row = tile * TM + r;
             const bool live = row < A.n;
             float sx = 0.f, sy = 0.f;
             if (live) {  // torch.FloatTensor(state): fp64 -> fp32 (sac.py:137)
@@ -314,7 +332,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) act_tc_kernel(const __grid_cons
                 for (int c = 0; c < NCHUNK; ++c, ++it) {
                     const int stage = it % NSTAGE;
                     mbar_wait(smem_u32(&S.empty[stage]), ((it / NSTAGE) & 1) ^ 1);
-                    produce_chunk(S, pass, c, stage, t, sx, sy, x2, x3, four);
+                    produce_chunk(S, pass, c, stage, r, q, sx, sy, x2, x3, four);
                     fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
                     mbar_arrive(smem_u32(&S.full[stage]));
                 }
@@ -322,10 +340,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) act_tc_kernel(const __grid_cons
             auto epilogue_pass = [&](int pass, int d, int n_out, float raw[4]) {
                 mbar_wait(smem_u32(&S.acc_full[d]), acc_use[d] & 1);
                 tc_fence_after();
-                epilogue_row(S, pass, n_out, lane_addr + d * H, raw);
+                const float4 mine = epilogue_quarter(S, pass, n_out, lane_addr + d * H, q);
                 tc_fence_before();
                 mbar_arrive(smem_u32(&S.acc_empty[d]));
                 ++acc_use[d];
+                // exchange the four column quarters of the row; every thread of the row then holds the full sums
+                const int pb = n_epi & 1;
+                ++n_epi;
+                S.part[pb][q][r] = mine;
+                asm volatile("bar.sync 1, %0;" ::"n"(kProd) : "memory");
+                const float4 p0 = S.part[pb][0][r], p1 = S.part[pb][1][r], p2 = S.part[pb][2][r], p3 = S.part[pb][3][r];
+                raw[0] = ((p0.x + p1.x) + (p2.x + p3.x)) + S.sm.b3[pass][0];
+                raw[1] = ((p0.y + p1.y) + (p2.y + p3.y)) + S.sm.b3[pass][1];
+                raw[2] = ((p0.z + p1.z) + (p2.z + p3.z)) + S.sm.b3[pass][2];
+                raw[3] = ((p0.w + p1.w) + (p2.w + p3.w)) + S.sm.b3[pass][3];
             };
             float raw[4];
             produce_pass(PASS_POL, 0.f, 0.f);
@@ -379,14 +407,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) act_tc_kernel(const __grid_cons
                 rec = qmax > A.eps_safe;               // experiment.py:555
                 if (rec) { ar[0] = arec[0]; ar[1] = arec[1]; }
             }
-            if (live) {
+            if (live && q == 0) {
                 reinterpret_cast<float2*>(A.action_task)[row] = make_float2(at[0], at[1]);
                 reinterpret_cast<float2*>(A.action_real)[row] = make_float2(ar[0], ar[1]);
                 if (A.recovery) A.recovery[row] = rec ? 1 : 0;
                 if (A.qrisk_out) A.qrisk_out[row] = qmax;
             }
         }
-    } else if (warp == 4) {
+    } else if (warp == kProd / 32) {
         // ================= MMA issuer (one thread) =================
         if (lane == 0) {
             uint32_t it = 0;
@@ -443,7 +471,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) act_tc_kernel(const __grid_cons
     // ---- teardown ----
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) tmem_dealloc(tmem_base, 512);
+    if (warp == kProd / 32) tmem_dealloc(tmem_base, 512);
 }
 
 }  // namespace

@@ -15,7 +15,6 @@ struct EnvParams {
     rrl_env_config_t cfg;
     // maze constants (host-computed in double, identical expressions in oracle/envs.py)
     double c_a, c_b, h, gear;
-    int hi_plane, hi_band_lo, hi_band_hi;  // high words of 0.27, 0.069, 0.131 (conservative pre-filter)
     double plane_lo, plane_hi;  // x <= plane_lo  <=>  fl(x - R) <= -0.3 ;  x >= plane_hi  <=>  fl(x + R) >= 0.3
     double wx0[4], wx1[4], wy0[4], wy1[4];  // 1A, 1B, 2A, 2B rectangles
 };
@@ -40,7 +39,8 @@ __device__ __forceinline__ bool nav_obstacle(int kind, double x, double y) {
 //     largest double that satisfies it (found on the host with the same IEEE arithmetic); same for the
 //     other three planes -> four compares, no arithmetic;
 //   * dx >= R  =>  fl(dx*dx) >= fl(R*R)  =>  fl(dx*dx + dy*dy) >= fl(R*R): no touch, so dy is only needed
-//     inside the wall's x band; walls 1A/1B and 2A/2B share their x range.
+//     inside the wall's x band; walls 1A/1B and 2A/2B share their x range;
+//   * tests that provably fail are skipped altogether (clearance argument in env_step_kernel).
 #define MAZE_R 0.025
 __device__ __forceinline__ bool maze_rect_touch_y(double dx, double y, double y0, double y1) {
     double dy = fmax(fmax(__dsub_rn(y0, y), 0.0), __dsub_rn(y, y1));
@@ -56,13 +56,78 @@ __device__ __forceinline__ bool maze_touch(const EnvParams& P, double x, double 
     if (dx2 < MAZE_R) hit = hit || maze_rect_touch_y(dx2, y, P.wy0[2], P.wy1[2]) || maze_rect_touch_y(dx2, y, P.wy0[3], P.wy1[3]);
     return hit;
 }
-// conservative: can a disc starting at (x,y) and moving at most `reach` per axis touch anything?
-__device__ __forceinline__ bool maze_may_touch(double x, double y, double reach) {
-    const double R = MAZE_R + reach;
-    if (x - R <= -0.3 || x + R >= 0.3 || y - R <= -0.3 || y + R >= 0.3) return true;
-    bool near1 = (x >= -0.105 - R) && (x <= -0.095 + R);
-    bool near2 = (x >= 0.095 - R) && (x <= 0.105 + R);
-    return near1 || near2;
+// 500 substeps for one warp of envs.  Per-substep semantics (oracle/envs.py): contact test on the
+// pre-integration position, then one semi-implicit Euler substep; contact freezes the disc.  Tests whose outcome
+// is provably "no contact" are skipped: a coordinate moves at most dmax per substep (|v| <= nsub * |fb| since
+// c_a < 1), the max-norm clearance to every solid is 1-Lipschitz in each coordinate, and a disc with clearance
+// > R + 1e-9 cannot satisfy any of the exact tests -- so after measuring the clearance once, the largest j with
+// j*h*(vmax + j*fbmax) <= clearance - R substeps run test-free.  The trip counts are made WARP-UNIFORM (min over the
+// lanes) so the 32 envs of a warp advance in lockstep instead of serialising their different schedules.
+__device__ __forceinline__ void maze_substeps_warp(const EnvParams& P, bool idle, double fbx, double fby, double& x,
+                                                   double& y, bool& contact) {
+    const int nsub = P.cfg.maze_substeps;
+    const double fbmax = fmax(fabs(fbx), fabs(fby)) * (1.0 + 1e-9) + 1e-300;
+    double vx = 0.0, vy = 0.0;
+    bool frozen = idle;  // idle lanes (beyond n) and lanes in contact do not move
+    int k = 0;
+    while (k < nsub) {
+        // number of substeps this lane can take before ANY exact contact test could fire:
+        // after j more substeps each coordinate has moved at most j*h*(vmax + j*fbmax)  (|v| grows by <= |fb| per substep)
+        int safe_lane = nsub - k;
+        if (!frozen) {
+            // max-norm clearance of the disc CENTRE to the solids (a lower bound of the Euclidean distance): the
+            // outer planes at +-0.3 and the two wall slabs x in -0.1 +- 0.005 (walls 1A/1B leave the y gap
+            // (-0.13, 0.22)) and x in 0.1 +- 0.005 (2A/2B leave (0.03, 0.28))
+            const double dxl = fmax(fabs(x + 0.1) - 0.005, 0.0), dxr = fmax(fabs(x - 0.1) - 0.005, 0.0);
+            const double dyl = fmax(fmin(y - P.wy1[1], P.wy0[0] - y), 0.0);
+            const double dyr = fmax(fmin(y - P.wy1[3], P.wy0[2] - y), 0.0);
+            const double cl = fmin(fmin(0.3 - fabs(x), 0.3 - fabs(y)), fmin(fmax(dxl, dyl), fmax(dxr, dyr)));
+            const double room = cl - MAZE_R - 1e-9;
+            safe_lane = 0;
+            if (room > 0.0) {
+                // largest j with j * (vmax + j * fbmax) <= room / h, estimated in fp32 (fast sqrt/div), then
+                // VERIFIED in fp64 -- the estimate only has to be a guess, the check makes the skip exact
+                const double vmax = fmax(fabs(vx), fabs(vy)) * (1.0 + 1e-9);
+                const double q = room / P.h;
+                const float vf = (float)vmax, ff = (float)fbmax, qf = (float)q;
+                float jf = floorf(0.999f * (sqrtf(vf * vf + 4.0f * ff * qf) - vf) / (2.0f * ff)) - 1.0f;
+                jf = fminf(fmaxf(jf, 0.0f), (float)(nsub - k));
+                const double j = (double)jf;
+                safe_lane = (j * (vmax + j * fbmax) <= q) ? (int)jf : 0;
+            }
+        }
+        const int safe = __reduce_min_sync(0xffffffffu, safe_lane);
+        if (safe >= 1) {
+            for (int j = 0; j < safe; ++j) {
+                if (!frozen) {
+                    vx = __dadd_rn(__dmul_rn(P.c_a, vx), fbx);
+                    vy = __dadd_rn(__dmul_rn(P.c_a, vy), fby);
+                    x = __dadd_rn(x, __dmul_rn(P.h, vx));
+                    y = __dadd_rn(y, __dmul_rn(P.h, vy));
+                }
+            }
+            k += safe;
+        } else {
+            // some lane is too close to a solid: up to 8 substeps with the exact test, only for the lanes that need it
+            const int burst = min(8, nsub - k);
+            const bool needs_test = safe_lane < burst;
+            for (int j = 0; j < burst; ++j) {
+                if (!frozen) {
+                    if (needs_test && maze_touch(P, x, y)) {
+                        frozen = true;
+                        contact = true;
+                    } else {
+                        vx = __dadd_rn(__dmul_rn(P.c_a, vx), fbx);
+                        vy = __dadd_rn(__dmul_rn(P.c_a, vy), fby);
+                        x = __dadd_rn(x, __dmul_rn(P.h, vx));
+                        y = __dadd_rn(y, __dmul_rn(P.h, vy));
+                    }
+                }
+            }
+            k += burst;
+            if (__all_sync(0xffffffffu, frozen)) break;
+        }
+    }
 }
 
 __device__ __forceinline__ void reset_state(const EnvParams& P, int64_t i, const double* draws, int64_t n,
@@ -132,6 +197,23 @@ env_step_kernel(EnvParams P, const float* __restrict__ a_task, const float* __re
         const bool live = i < n;
         bool ep_end = false, viol = false, succ_end = false, rec_used = false;
         double ep_ret_final = 0.0;
+        double mz_x = 0.0, mz_y = 0.0;
+        bool mz_contact = false;
+        if (kind == RRL_ENV_MAZE) {  // all 32 lanes take part (warp-uniform substep loop)
+            double fbx = 0.0, fby = 0.0;
+            if (live) {
+                mz_x = state[i];
+                mz_y = state[n + i];
+                // E8: maze.  clip in fp32 to float32(0.1), then ctrl is fp64
+                const float2 ar = reinterpret_cast<const float2*>(a_real)[i];
+                const float cx = fminf(fmaxf(ar.x, -0.1f), 0.1f), cy = fminf(fmaxf(ar.y, -0.1f), 0.1f);
+                const double dax = a_f64 ? fmin(fmax(a_f64[2 * i], -0.1), 0.1) : (double)cx;
+                const double day = a_f64 ? fmin(fmax(a_f64[2 * i + 1], -0.1), 0.1) : (double)cy;
+                fbx = __dmul_rn(P.c_b, __dmul_rn(P.gear, dax));
+                fby = __dmul_rn(P.c_b, __dmul_rn(P.gear, day));
+            }
+            maze_substeps_warp(P, !live, fbx, fby, mz_x, mz_y, mz_contact);
+        }
         if (live) {
             const double sx = state[i], sy = state[n + i];
             const float2 at = reinterpret_cast<const float2*>(a_task)[i];
@@ -167,39 +249,8 @@ env_step_kernel(EnvParams P, const float* __restrict__ a_task, const float* __re
                 reward = cost;
             } else {
                 // E8: maze.  clip in fp32 to float32(0.1), then ctrl is fp64
-                const float cx = fminf(fmaxf(ar.x, -0.1f), 0.1f), cy = fminf(fmaxf(ar.y, -0.1f), 0.1f);
-                const double dax = a_f64 ? fmin(fmax(a_f64[2 * i], -0.1), 0.1) : (double)cx;
-                const double day = a_f64 ? fmin(fmax(a_f64[2 * i + 1], -0.1), 0.1) : (double)cy;
-                const double fbx = __dmul_rn(P.c_b, __dmul_rn(P.gear, dax));
-                const double fby = __dmul_rn(P.c_b, __dmul_rn(P.gear, day));
-                double x = sx, y = sy, vx = 0.0, vy = 0.0;
-                bool contact = false;
-                const int nsub = P.cfg.maze_substeps;
-                if (!maze_may_touch(x, y, 0.03)) {
-                    // free flight: contact tests cannot fire (|displacement| <= 0.0247 per axis per step)
-                    for (int k = 0; k < nsub; ++k) {
-                        vx = __dadd_rn(__dmul_rn(P.c_a, vx), fbx);
-                        vy = __dadd_rn(__dmul_rn(P.c_a, vy), fby);
-                        x = __dadd_rn(x, __dmul_rn(P.h, vx));
-                        y = __dadd_rn(y, __dmul_rn(P.h, vy));
-                    }
-                } else {
-                    for (int k = 0; k < nsub; ++k) {
-                        // collision phase precedes integration; contact freezes the disc.  Integer pre-filter on
-                        // the high words of |x|, |y| (monotone in the value): the exact fp64 test runs only when
-                        // the disc centre is within 0.03 of a plane or inside the 0.06-wide band around a wall.
-                        const int hx = __double2hiint(x) & 0x7fffffff, hy = __double2hiint(y) & 0x7fffffff;
-                        const bool near = (max(hx, hy) >= P.hi_plane) || (hx >= P.hi_band_lo && hx <= P.hi_band_hi);
-                        if (near && maze_touch(P, x, y)) {
-                            contact = true;
-                            break;
-                        }
-                        vx = __dadd_rn(__dmul_rn(P.c_a, vx), fbx);
-                        vy = __dadd_rn(__dmul_rn(P.c_a, vy), fby);
-                        x = __dadd_rn(x, __dmul_rn(P.h, vx));
-                        y = __dadd_rn(y, __dmul_rn(P.h, vy));
-                    }
-                }
+                const double x = mz_x, y = mz_y;
+                const bool contact = mz_contact;
                 nx = x;
                 ny = y;
                 constraint = contact;
@@ -318,12 +369,6 @@ EnvParams make_params(const rrl_env_config_t* cfg) {
         while (c + MAZE_R >= 0.3) c = nextafter(c, -1.0);
         while (!(c + MAZE_R >= 0.3)) c = nextafter(c, 1.0);
         P.plane_hi = c;  // smallest x with fl(x + R) >= 0.3
-    }
-    {
-        auto hi = [](double v) { uint64_t b; memcpy(&b, &v, 8); return (int)(b >> 32); };
-        P.hi_plane = hi(0.27);      // |x| < 0.27 (by high word)  =>  |x| + R < 0.3: no plane contact
-        P.hi_band_lo = hi(0.069);   // outside [0.069, 0.131]  =>  distance to the wall slab [0.095,0.105] > R
-        P.hi_band_hi = hi(0.131) + 1;
     }
     return P;
 }

@@ -114,6 +114,9 @@ class VecEngine(object):
         else:
             self.in_dev = {}
         self.graph = None
+        self._side = torch.cuda.Stream(device=dev)
+        self._ev_fork = torch.cuda.Event()
+        self._ev_join = torch.cuda.Event()
         self.launches_per_step = 0
         self._grad_views = None
 
@@ -168,35 +171,47 @@ class VecEngine(object):
         if self.world > 1:
             dist_utils.sync_gate_counts(self.counters, self.pg)
 
-    def qrisk_update(self, sample_cfg=None, count=True):
-        cfg, ar, cn = self.cfg, self.arena, self.counters
+    def _qr_sample(self, sample_cfg=None):
         sc = sample_cfg or self.qr_sample_cfg
         k = 0
         if sc.pos_fraction >= 0:
             native.replay_flag_count(self.cons_flags, self.cons_cap, FLAG_CHUNK, self.chunk_counts); k += 1
         a = self.agent
-        native.replay_sample(sc, self.cons_ring, self.mt_state, cn, native.C_QRISK_ROWS, a.scratch("qr_s"),
+        native.replay_sample(sc, self.cons_ring, self.mt_state, self.counters, native.C_QRISK_ROWS, a.scratch("qr_s"),
                              a.scratch("qr_a"), a.scratch("qr_c"), a.scratch("qr_s2"), a.scratch("qr_m"),
-                             cons_flags=self.cons_flags, chunk_counts=self.chunk_counts); k += 1
-        native.qrisk_backward(cfg, ar, cn, self.losses[8:], self._in("qr_eps_next"), seed=self.seed, stream_id=self.rank); k += 6
+                             cons_flags=self.cons_flags, chunk_counts=self.chunk_counts)
+        return k + 1
+
+    def _qr_compute(self):
+        cfg, ar, cn = self.cfg, self.arena, self.counters
+        native.qrisk_backward(cfg, ar, cn, self.losses[8:], self._in("qr_eps_next"), seed=self.seed, stream_id=self.rank)
         self._all_reduce(["qrisk"])
-        native.qrisk_apply(cfg, ar, cn); k += 2
+        native.qrisk_apply(cfg, ar, cn)
         native.recovery_backward(cfg, ar, cn, self.losses[8:], self._in("qr_eps_rec"), seed=self.seed, stream_id=self.rank)
         self._all_reduce(["recovery"])
         native.recovery_apply(cfg, ar, cn)
-        k += (10 if self.mf_recovery else 0) + (3 if self.mf_recovery else 2)
-        return k
+        return 6 + 2 + (10 if self.mf_recovery else 0) + (3 if self.mf_recovery else 2)
 
-    def sac_update(self):
-        cfg, ar, cn, a = self.cfg, self.arena, self.counters, self.agent
-        native.replay_sample(self.sac_sample_cfg, self.task_ring, self.mt_state, cn, native.C_SAC_ROWS,
+    def qrisk_update(self, sample_cfg=None):
+        return self._qr_sample(sample_cfg) + self._qr_compute()
+
+    def _sac_sample(self):
+        a = self.agent
+        native.replay_sample(self.sac_sample_cfg, self.task_ring, self.mt_state, self.counters, native.C_SAC_ROWS,
                              a.scratch("sac_s"), a.scratch("sac_a"), a.scratch("sac_r"), a.scratch("sac_s2"),
                              a.scratch("sac_m"))
+        return 1
+
+    def _sac_compute(self):
+        cfg, ar, cn = self.cfg, self.arena, self.counters
         native.sac_backward(cfg, ar, cn, self.losses, self._in("sac_eps_next"), self._in("sac_eps_cur"), seed=self.seed,
                             stream_id=self.rank)
         self._all_reduce(["critic", "policy"])
         native.sac_apply(cfg, ar, cn)
-        return 1 + 10 + 3
+        return 10 + 3
+
+    def sac_update(self):
+        return self._sac_sample() + self._sac_compute()
 
     def pretrain_qrisk(self, steps, n_demos=None):
         """experiment.py:289-296: critic_safe_pretraining_steps x QRiskWrapper.update_parameters with
@@ -209,10 +224,22 @@ class VecEngine(object):
     # ---- the vector step -------------------------------------------------------------------------
     def _enqueue_step(self):
         k = 0
-        k += self.sac_update()                                                     # experiment.py:397-406
+        main = torch.cuda.current_stream()
+        k += self._sac_sample()          # draws first from the shared sampler stream (replay_memory.py:28)
         if self.online_qrisk:
+            # the Q_risk batch (flag scan + stratified sample + gather) does not depend on the SAC update: it runs
+            # on a side stream, forked after the SAC sample (stream order of the ONE shared generator) and joined
+            # before the Q_risk kernels.  Captured as a fork/join in the CUDA graph.
             self._sync_gate_counts()
-            k += self.qrisk_update()                                               # experiment.py:407-415
+            self._ev_fork.record(main)
+            self._side.wait_event(self._ev_fork)
+            with torch.cuda.stream(self._side):
+                k += self._qr_sample()
+                self._ev_join.record(self._side)
+        k += self._sac_compute()                                                   # experiment.py:397-406
+        if self.online_qrisk:
+            main.wait_event(self._ev_join)
+            k += self._qr_compute()                                                # experiment.py:407-415
         if self.cfg.use_tensor_cores:
             native.agent_tc_refresh(self.cfg, self.arena); k += 1   # fp16 hi/lo images of the freshly updated weights
         native.agent_act(self.cfg, self.arena, self.n, self.state, self.counters, self.action_task, self.action_real,
