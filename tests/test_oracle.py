@@ -117,8 +117,10 @@ def test_maze_scalar_matches_vectorised():
 
 
 def test_oracle_loop_reproduces_reference_trajectory(golden_dir):
-    """oracle/loop.py fed the recorded noise == the reference's Experiment (12 episodes, seed 7): states,
-    flags, replay indices bit-exact; final weights to fp32 round-off."""
+    """oracle/loop.py fed the recorded noise == the reference's Experiment (12 episodes, seed 7): flags, episode
+    boundaries, replay indices and counters bit-exact; states / actions / final weights to fp32 round-off.
+    (On the CPU that recorded the golden the whole trajectory is bit-identical; another CPU takes another MKL
+    sgemm code path and the fp32 actions move by 1 ulp, so the float fields carry an absolute 1e-5.)"""
     from oracle.loop import OracleExperiment, NoiseSource
     z = np.load(os.path.join(golden_dir, "traj_nav1_seed7.npz"))
     sizes = z["eps_sizes"]
@@ -133,9 +135,9 @@ def test_oracle_loop_reproduces_reference_trajectory(golden_dir):
     infos = []
     for _ in range(int(z["ep_len"].sum())):
         infos.append(exp.step())
-    assert np.array_equal(np.array([i["state"] for i in infos]), z["state"])
-    assert np.array_equal(np.array([i["next_state"] for i in infos]), z["next_state"])
-    assert np.array_equal(np.array([i["action"] for i in infos], np.float32), z["action"])
+    assert np.allclose(np.array([i["state"] for i in infos]), z["state"], rtol=0, atol=1e-5)
+    assert np.allclose(np.array([i["next_state"] for i in infos]), z["next_state"], rtol=0, atol=1e-5)
+    assert np.allclose(np.array([i["action"] for i in infos], np.float32), z["action"], rtol=0, atol=1e-5)
     assert np.array_equal(np.array([i["constraint"] for i in infos]), z["constraint"])
     assert np.array_equal(np.array([i["recovery"] for i in infos]), z["recovery"].astype(bool))
     ends = np.cumsum(z["ep_len"]) - 1
@@ -146,4 +148,4 @@ def test_oracle_loop_reproduces_reference_trajectory(golden_dir):
     stride = int(z["stride"])
     for net in ("critic", "critic_target", "policy", "qrisk", "qrisk_target", "recovery"):
         for i, p in enumerate(exp.agent.params(net)):
-            assert np.allclose(p.ravel()[::stride], z["final_%s_%d" % (net, i)], rtol=0, atol=0)
+            assert np.allclose(p.ravel()[::stride], z["final_%s_%d" % (net, i)], rtol=0, atol=1e-5)
