@@ -3,7 +3,10 @@
 Restates, with the reference's own numeric library (torch CPU fp32, torch.optim.Adam):
   recovery_rl/model.py:49-76   QNetwork            :172-199 QNetworkConstraint (incl. the dead BatchNorm1d)
   recovery_rl/model.py:295-343 GaussianPolicy      :489-530 StochasticPolicy      :23-26 weights_init_
-  recovery_rl/sac.py:133-168   SAC.select_action   :170-277 SAC.update_parameters (default + --use_recovery branch)
+  recovery_rl/sac.py:133-168   SAC.select_action (incl. the SQRL filter :139-161)
+  recovery_rl/sac.py:170-277   SAC.update_parameters: default / --use_recovery, and the comparison branches
+                               LR/RSPO (--DGD_constraints, --update_nu :221-228,256-262), RCPO (:202-205,265-271),
+                               automatic entropy tuning (:241-253), --policy Deterministic (model.py:447-485)
   recovery_rl/qrisk.py:86-182  QRiskWrapper.update_parameters   :184-213 get_value / select_action
   recovery_rl/utils.py:46-54   soft_update / hard_update
   recovery_rl/experiment.py:546-577 composite action selection
@@ -13,7 +16,7 @@ optimizer before policy_loss.backward(), which is only legal on its pinned torch
 expressions are evaluated as written, then critic grads, policy grads (w.r.t. policy parameters only),
 critic step, policy step.  The golden vectors were generated from the reference under the same patch.
 
-PINNED against tests/golden/agent_nav1_b256.npz, agent_maze_b64.npz and traj_nav1_seed7.npz (outputs of
+PINNED against tests/golden/agent_nav1_b256.npz, agent_maze_b64.npz, agent_algos_b64.npz and traj_nav1_seed7.npz (outputs of
 the reference's own classes, oracle/ref_harness/make_golden.py).  Noise (eps) is always an explicit input.
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline/reference legs may import this.
@@ -115,6 +118,30 @@ class StochasticPolicy(nn.Module):
         return action, _normal_log_prob(action, mean, std).sum(-1), mean
 
 
+class DeterministicPolicy(nn.Module):
+    """model.py:447-485.  `noise` is ONE [num_actions] vector per sample() call, N(0, 0.1) clamped to +-0.25 and
+    broadcast over the batch; it is an explicit input here (already scaled and clamped)."""
+
+    def __init__(self, num_inputs, num_actions, hidden_dim, action_scale, action_bias):
+        super().__init__()
+        self.linear1 = nn.Linear(num_inputs, hidden_dim)
+        self.linear2 = nn.Linear(hidden_dim, hidden_dim)
+        self.mean = nn.Linear(hidden_dim, num_actions)
+        self.apply(weights_init_)
+        self.action_scale = torch.as_tensor(action_scale, dtype=torch.float32)
+        self.action_bias = torch.as_tensor(action_bias, dtype=torch.float32)
+
+    def sample(self, state, noise):
+        x = F.relu(self.linear2(F.relu(self.linear1(state))))
+        mean = torch.tanh(self.mean(x)) * self.action_scale + self.action_bias
+        return mean + torch.as_tensor(noise, dtype=torch.float32), torch.tensor(0.), mean
+
+
+def deterministic_noise():
+    """the draw of DeterministicPolicy.sample (model.py:478-479) from the torch global generator."""
+    return torch.Tensor(2).normal_(0., std=0.1).clamp(-0.25, 0.25)
+
+
 def soft_update(target, source, tau):
     for tp, p in zip(target.parameters(), source.parameters()):
         tp.data.copy_(tp.data * (1.0 - tau) + p.data * tau)
@@ -130,8 +157,25 @@ class Agent(object):
     (which fixes the xavier draws from the torch global RNG)."""
 
     def __init__(self, action_scale=(1.0, 1.0), action_bias=(0.0, 0.0), hidden=256, gamma=0.99, alpha=0.2, tau=0.005,
-                 gamma_safe=0.5, tau_safe=0.0002, eps_safe=0.1, lr=3e-4, target_update_interval=1, mf_recovery=True):
+                 gamma_safe=0.5, tau_safe=0.0002, eps_safe=0.1, lr=3e-4, target_update_interval=1, mf_recovery=True,
+                 dgd=False, update_nu=False, rcpo=False, auto_alpha=False, deterministic=False, nu=0.01,
+                 lambda_rcpo=0.01):
         self.gamma, self.alpha, self.tau = gamma, alpha, tau
+        self.dgd, self.update_nu, self.rcpo = bool(dgd), bool(update_nu), bool(rcpo)
+        self.deterministic = bool(deterministic)
+        self.auto_alpha = bool(auto_alpha) and not self.deterministic
+        # sac.py:56-72: float64 scalars (np.log of a python float), Adam lr 0.1*lr
+        self.nu, self.lambda_rcpo = nu, lambda_rcpo
+        self.log_nu = torch.tensor(np.log(nu), requires_grad=True)
+        self.nu_optim = Adam([self.log_nu], lr=0.1 * lr)
+        self.log_lambda = torch.tensor(np.log(lambda_rcpo), requires_grad=True)
+        self.lambda_optim = Adam([self.log_lambda], lr=0.1 * lr)
+        if self.auto_alpha:                                   # sac.py:95-101
+            self.target_entropy = -2.0
+            self.log_alpha = torch.zeros(1, requires_grad=True)
+            self.alpha_optim = Adam([self.log_alpha], lr=lr)
+        if self.deterministic:                                # sac.py:116-117
+            self.alpha = 0
         self.gamma_safe, self.tau_safe, self.eps_safe = gamma_safe, tau_safe, eps_safe
         self.target_update_interval = target_update_interval
         self.mf_recovery = mf_recovery
@@ -139,7 +183,8 @@ class Agent(object):
         self.critic_target = QNetwork(2, 2, hidden)
         self.critic_optim = Adam(self.critic.parameters(), lr=lr)
         hard_update(self.critic_target, self.critic)
-        self.policy = GaussianPolicy(2, 2, hidden, action_scale, action_bias)
+        pol_cls = DeterministicPolicy if self.deterministic else GaussianPolicy
+        self.policy = pol_cls(2, 2, hidden, action_scale, action_bias)
         self.policy_optim = Adam(self.policy.parameters(), lr=lr)
         self.qrisk = QNetwork(2, 2, hidden, constraint=True)
         self.qrisk_target = QNetwork(2, 2, hidden, constraint=True)
@@ -167,7 +212,11 @@ class Agent(object):
         return [p.detach().numpy().copy() for p in self.nets()[name].parameters()]
 
     # ---- sac.py:170-277 (Variant B) -------------------------------------------------------------
-    def sac_update(self, batch, eps_next, eps_cur, updates):
+    def sac_update(self, batch, eps_next, eps_cur, updates, nu=None):
+        """eps_next / eps_cur: [B, 2] standard normals (Gaussian policy) or the two [2] noise vectors of
+        DeterministicPolicy.sample.  nu: the argument experiment.py:406 passes (nu_schedule(i_episode))."""
+        if nu is None:
+            nu = self.nu
         s, a, r, s2, m = [torch.as_tensor(np.asarray(x), dtype=torch.float32) for x in batch]
         r, m = r.reshape(-1, 1), m.reshape(-1, 1)
         eps_next = torch.as_tensor(eps_next, dtype=torch.float32)
@@ -176,12 +225,20 @@ class Agent(object):
             na, nlp, _ = self.policy.sample(s2, eps_next)
             q1n, q2n = self.critic_target(s2, na)
             y = r + m * self.gamma * (torch.min(q1n, q2n) - self.alpha * nlp)
+            if self.rcpo:                                      # sac.py:202-205
+                qsafe = torch.max(*self.qrisk(s, a))
+                y -= self.lambda_rcpo * qsafe
         qf1, qf2 = self.critic(s, a)
         qf1_loss, qf2_loss = F.mse_loss(qf1, y), F.mse_loss(qf2, y)
         pi, log_pi, _ = self.policy.sample(s, eps_cur)
         qf1_pi, qf2_pi = self.critic(s, pi)
         min_qf_pi = torch.min(qf1_pi, qf2_pi)
-        policy_loss = ((self.alpha * log_pi) - min_qf_pi).mean()
+        sqf1_pi, sqf2_pi = self.qrisk(s, pi)                   # sac.py:221-222
+        max_sqf_pi = torch.max(sqf1_pi, sqf2_pi)
+        if self.dgd:                                           # sac.py:224-228
+            policy_loss = ((self.alpha * log_pi) + nu * (max_sqf_pi - self.eps_safe) - 1. * min_qf_pi).mean()
+        else:
+            policy_loss = ((self.alpha * log_pi) - min_qf_pi).mean()
         self.critic_optim.zero_grad()
         (qf1_loss + qf2_loss).backward(retain_graph=True)
         pol_params = list(self.policy.parameters())
@@ -191,14 +248,50 @@ class Agent(object):
         for p, g in zip(pol_params, pol_grads):
             p.grad = g
         self.policy_optim.step()
+        alpha_loss, alpha_log = 0.0, float(self.alpha)
+        if self.auto_alpha:                                    # sac.py:241-250
+            a_loss = -(self.log_alpha * (log_pi + self.target_entropy).detach()).mean()
+            self.alpha_optim.zero_grad()
+            a_loss.backward()
+            self.alpha_optim.step()
+            self.alpha = self.log_alpha.exp().detach()
+            alpha_loss, alpha_log = a_loss.item(), self.alpha.item()
+        if self.update_nu:                                     # sac.py:256-262
+            nu_loss = (self.log_nu * (self.eps_safe - max_sqf_pi).detach()).mean()
+            self.nu_optim.zero_grad()
+            nu_loss.backward()
+            self.nu_optim.step()
+            self.nu = self.log_nu.exp().detach()
+        if self.rcpo:                                          # sac.py:265-271
+            l_loss = (self.log_lambda * (self.eps_safe - qsafe).detach()).mean()
+            self.lambda_optim.zero_grad()
+            l_loss.backward()
+            self.lambda_optim.step()
+            self.lambda_rcpo = self.log_lambda.exp().detach()
         if updates % self.target_update_interval == 0:
             soft_update(self.critic_target, self.critic, self.tau)
         self.dbg = dict(qf1=qf1.detach().numpy(), qf2=qf2.detach().numpy(), target=y.numpy(), pi=pi.detach().numpy(),
                         log_pi=log_pi.detach().numpy(), min_qf_pi=min_qf_pi.detach().numpy(), next_action=na.numpy(),
-                        next_log_pi=nlp.numpy(),
+                        next_log_pi=nlp.numpy(), max_sqf_pi=max_sqf_pi.detach().numpy(),
                         critic_grads=[p.grad.detach().numpy().copy() for p in self.critic.parameters()],
                         policy_grads=[g.detach().numpy().copy() for g in pol_grads])
-        return qf1_loss.item(), qf2_loss.item(), policy_loss.item(), 0.0, self.alpha
+        return qf1_loss.item(), qf2_loss.item(), policy_loss.item(), alpha_loss, alpha_log
+
+    # ---- sac.py:139-161: SQRL action filter ------------------------------------------------------
+    def select_action_sqrl(self, state, eps, eps_safe=None, safe_samples=100):
+        """eps: [safe_samples, 2].  The Categorical draw comes from the torch global generator, as in the reference."""
+        eps_safe = self.eps_safe if eps_safe is None else eps_safe
+        with torch.no_grad():
+            sb = torch.as_tensor(np.asarray(state), dtype=torch.float32).unsqueeze(0).repeat(safe_samples, 1)
+            pi, log_pi, _ = self.policy.sample(sb, torch.as_tensor(eps, dtype=torch.float32))
+            qmax = torch.max(*self.qrisk(sb, pi))
+            idxs = (qmax <= eps_safe).nonzero()[:, 0]
+            probs = torch.exp(log_pi[idxs]).flatten()
+            if probs.numel() == 0:
+                return pi[torch.argmin(qmax)].numpy()
+            # NB sac.py:157-159 indexes `pi` with the index INTO THE FILTERED SET (not thresh_idxs[sampled_idx]):
+            # reproduced as written
+            return pi[torch.distributions.Categorical(probs).sample()].numpy()
 
     # ---- qrisk.py:86-182 ---------------------------------------------------------------------------
     def qrisk_update(self, batch, eps_next, eps_rec):

@@ -424,6 +424,138 @@ def golden_trajectory():
     _save("traj_nav1_seed7.npz", **out)
 
 
+# ---------------------------------------------------------------------------------------
+# G. comparison-algorithm branches of SAC (sac.py:139-161, 202-205, 221-228, 241-271; model.py:447-485):
+#    LR (--DGD_constraints --update_nu), RSPO (--DGD_constraints, scheduled nu), RCPO, automatic entropy
+#    tuning, --policy Deterministic, and the SQRL action filter (--use_constraint_sampling)
+# ---------------------------------------------------------------------------------------
+ALGO_CASES = [
+    # tag        env            scale  extra argv
+    ("lr",      "navigation1", 1.0, ["--DGD_constraints", "--nu", "5000", "--update_nu", "--gamma_safe", "0.8", "--eps_safe", "0.3"]),
+    ("rspo",    "navigation1", 1.0, ["--DGD_constraints", "--nu_schedule", "--nu_start", "10000", "--gamma_safe", "0.8", "--eps_safe", "0.3"]),
+    ("rcpo",    "maze",        0.1, ["--RCPO", "--lambda", "50", "--gamma_safe", "0.5", "--eps_safe", "0.15", "--pos_fraction", "0.3"]),
+    ("autoalpha", "maze",      0.1, ["--automatic_entropy_tuning", "1"]),
+    ("det",     "navigation1", 1.0, ["--policy", "Deterministic"]),
+    ("sqrl",    "maze",        0.1, ["--DGD_constraints", "--use_constraint_sampling", "--nu", "100", "--update_nu", "--gamma_safe", "0.5", "--eps_safe", "0.15", "--pos_fraction", "0.3"]),
+]
+
+
+def golden_algos(B=64, n_qr=12, n_updates=3, seed=23):
+    harness.setup()
+    from gym.spaces import Box
+    from recovery_rl.sac import SAC
+    from recovery_rl.utils import linear_schedule
+    STR = 13
+    out = {"tags": np.array([c[0] for c in ALGO_CASES]), "B": np.int64(B), "n_qr": np.int64(n_qr),
+           "n_updates": np.int64(n_updates), "seed": np.int64(seed), "stride": np.int64(STR)}
+    for tag, env_name, scale, extra in ALGO_CASES:
+        args = harness.get_args(extra + ["--env-name", env_name, "--seed", str(seed), "--batch_size", str(B)])
+        torch.manual_seed(seed)
+        np.random.seed(seed)
+        obs_space = Box(-np.ones(2) * float("inf"), np.ones(2) * float("inf"))
+        act_space = Box(-np.ones(2) * scale, np.ones(2) * scale)
+        agent = SAC(obs_space, act_space, args, "/tmp/none", tmp_env=_DummyEnv())
+        qr = agent.safety_critic
+        P = tag + "_"
+        out[P + "env"] = np.array(env_name)
+        out[P + "scale"] = np.float64(scale)
+        for k in ("gamma", "gamma_safe", "alpha", "tau", "tau_safe", "lr", "eps_safe", "nu", "lambda_RCPO"):
+            out[P + k] = np.float64(getattr(args, k))
+        out[P + "flags"] = np.array([int(args.DGD_constraints), int(args.update_nu), int(args.RCPO),
+                                     int(bool(args.automatic_entropy_tuning) and args.policy == "Gaussian"),
+                                     int(args.policy != "Gaussian"), int(args.use_constraint_sampling)], np.int64)
+        out[P + "mf_recovery"] = np.int64(int(args.MF_recovery))
+        if args.nu_schedule:
+            sched = linear_schedule(args.nu_start, args.nu_end, args.num_eps)
+        else:
+            sched = linear_schedule(args.nu, args.nu, 0)
+        rng = np.random.RandomState(4321 + seed)
+        if env_name == "maze":
+            def states(n):
+                return rng.uniform(-0.27, 0.27, (n, 2))
+            step_scale = 0.02
+        else:
+            def states(n):
+                return np.stack([rng.uniform(-75, 10, n), rng.uniform(-9, 9, n)], 1)
+            step_scale = 1.0
+        mem = _FixedMemory()
+        # a few Q_risk updates first so that the safety critic is not at its (flat) initialisation
+        for u in range(n_qr):
+            s = states(B)
+            a = rng.uniform(-scale, scale, (B, 2)).astype(np.float32)
+            s2 = s + step_scale * a.astype(np.float64) / scale + 0.05 * step_scale * rng.randn(B, 2)
+            c = (s[:, 1] * (1.0 if env_name != "maze" else 30.0) + rng.randn(B) > 2.0).astype(np.float64)
+            m = 1.0 - c
+            e_next = rng.randn(B, 2).astype(np.float32)
+            mem.batch = (s, a, c, s2, m)
+            if args.policy == "Gaussian":
+                harness.eps_queue.append(e_next)
+            else:
+                torch.manual_seed(500 + u)
+            if args.MF_recovery:
+                harness.eps_queue.append(rng.randn(B, 2).astype(np.float32))
+            qr.update_parameters(memory=mem, policy=agent.policy, batch_size=B)
+            assert not harness.eps_queue
+            q = "%sqr%d_" % (P, u)
+            out.update({q + "s": s, q + "a": a, q + "c": c, q + "s2": s2, q + "m": m, q + "eps_next": e_next})
+        for u in range(n_updates):
+            s = states(B)
+            a = rng.uniform(-scale, scale, (B, 2)).astype(np.float32)
+            s2 = s + step_scale * a.astype(np.float64) / scale + 0.05 * step_scale * rng.randn(B, 2)
+            r = -np.linalg.norm(s, axis=1)
+            m = (rng.rand(B) > 0.1).astype(np.float64)
+            e_next = rng.randn(B, 2).astype(np.float32)
+            e_cur = rng.randn(B, 2).astype(np.float32)
+            mem.batch = (s, a, r, s2, m)
+            nu_arg = float(sched(1 + 40 * u))           # experiment.py:406 nu=self.nu_schedule(i_episode)
+            if args.policy == "Gaussian":
+                harness.eps_queue.extend([e_next, e_cur])
+            else:
+                torch.manual_seed(1000 + u)              # DeterministicPolicy.sample draws self.noise.normal_ (model.py:478)
+            losses = agent.update_parameters(mem, B, u, safety_critic=qr, nu=nu_arg)
+            assert not harness.eps_queue
+            q = "%ssac%d_" % (P, u)
+            out.update({q + "s": s, q + "a": a, q + "r": r, q + "s2": s2, q + "m": m, q + "eps_next": e_next,
+                        q + "eps_cur": e_cur, q + "nu_arg": np.float64(nu_arg), q + "losses": np.array(losses, np.float64)})
+            for k, v in agent._dbg.items():
+                if isinstance(v, list):
+                    if u == 0:
+                        for i, g in enumerate(v):
+                            out["%s%s_%d" % (q, k, i)] = _sub(g, STR)
+                else:
+                    out[q + k] = np.asarray(v)
+            out[q + "log_nu"] = np.float64(agent.log_nu.item())
+            out[q + "log_lambda"] = np.float64(agent.log_lambda_RCPO.item())
+            out[q + "lambda"] = np.float64(float(agent.lambda_RCPO))
+            out[q + "alpha_after"] = np.float64(float(agent.alpha))
+            if agent.automatic_entropy_tuning:
+                out[q + "log_alpha"] = np.float64(agent.log_alpha.item())
+            for nm, mod in (("critic", agent.critic), ("critic_target", agent.critic_target), ("policy", agent.policy)):
+                for i, pp in enumerate(_params(mod)):
+                    if u in (0, n_updates - 1):
+                        out["%safter_%s_%d" % (q, nm, i)] = _sub(pp, STR)
+        if args.use_constraint_sampling:
+            # SQRL action filter (sac.py:139-161): 100 policy samples, keep Q_risk <= eps_safe, Categorical over exp(log_pi)
+            n_sel = 24
+            st = states(n_sel)
+            eps = rng.randn(n_sel, 100, 2).astype(np.float32)
+            acts = np.zeros((n_sel, 2), np.float32)
+            thr = np.zeros(n_sel)
+            with torch.no_grad():
+                probe = qr.get_value(torch.FloatTensor(st), torch.zeros(n_sel, 2)).numpy()[:, 0]
+            for i in range(n_sel):
+                # thresholds around the actual Q_risk range so that all/some/none of the samples pass
+                thr[i] = float(probe[i]) + (0.02 * (i % 3 - 1) if i % 4 else -1.0)
+                agent.eps_safe = thr[i]
+                harness.eps_queue.append(eps[i])
+                torch.manual_seed(7000 + i)
+                acts[i] = agent.select_action(st[i])
+                assert not harness.eps_queue
+            agent.eps_safe = args.eps_safe
+            out.update({P + "sel_s": st, P + "sel_eps": eps, P + "sel_thresh": thr, P + "sel_action": acts})
+    _save("agent_algos_b%d.npz" % B, **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     harness.setup()
@@ -436,6 +568,7 @@ def main():
                  ["--use_recovery", "--MF_recovery", "--gamma_safe", "0.5", "--eps_safe", "0.15",
                   "--pos_fraction", "0.3"], 64, dump_init=False)
     golden_trajectory()
+    golden_algos()
 
 
 if __name__ == "__main__":

@@ -149,3 +149,72 @@ def test_oracle_loop_reproduces_reference_trajectory(golden_dir):
     for net in ("critic", "critic_target", "policy", "qrisk", "qrisk_target", "recovery"):
         for i, p in enumerate(exp.agent.params(net)):
             assert np.allclose(p.ravel()[::stride], z["final_%s_%d" % (net, i)], rtol=0, atol=1e-5)
+
+
+# ---- comparison-algorithm branches (LR / RSPO / RCPO / auto-alpha / Deterministic / SQRL) ---------------------
+ALGO_TAGS = ["lr", "rspo", "rcpo", "autoalpha", "det", "sqrl"]
+
+
+def algo_oracle_agent(z, tag):
+    """oracle Agent configured like the reference SAC of golden case `tag` (same torch RNG order -> same init)."""
+    import torch
+    from oracle.agent import Agent
+    P = tag + "_"
+    f = z[P + "flags"]
+    seed = int(z["seed"])
+    torch.manual_seed(seed)
+    np.random.seed(seed)
+    sc = np.float32(float(z[P + "scale"]))
+    return Agent(action_scale=(sc, sc), gamma=float(z[P + "gamma"]), alpha=float(z[P + "alpha"]), tau=float(z[P + "tau"]),
+                 gamma_safe=float(z[P + "gamma_safe"]), tau_safe=float(z[P + "tau_safe"]), eps_safe=float(z[P + "eps_safe"]),
+                 lr=float(z[P + "lr"]), mf_recovery=bool(int(z[P + "mf_recovery"])), dgd=bool(f[0]), update_nu=bool(f[1]),
+                 rcpo=bool(f[2]), auto_alpha=bool(f[3]), deterministic=bool(f[4]), nu=float(z[P + "nu"]),
+                 lambda_rcpo=float(z[P + "lambda_RCPO"]))
+
+
+def algo_noise(z, tag, key, seed_base, u):
+    """the policy noise of update u: recorded eps for the Gaussian policy, re-drawn from the torch generator for
+    the Deterministic policy (the golden script seeds torch with seed_base + u right before the update)."""
+    import torch
+    from oracle.agent import deterministic_noise
+    if int(z[tag + "_flags"][4]):
+        torch.manual_seed(seed_base + u)
+        n1 = deterministic_noise()
+        n2 = deterministic_noise()
+        return n1.numpy(), n2.numpy()
+    return z["%s_%s%d_eps_next" % (tag, key, u)], (z["%s_%s%d_eps_cur" % (tag, key, u)] if key == "sac" else None)
+
+
+@pytest.mark.parametrize("tag", ALGO_TAGS)
+def test_oracle_comparison_branches_match_reference(golden_dir, tag):
+    """oracle/agent.py == the reference's SAC.update_parameters on its LR / RSPO / RCPO / auto-alpha / Deterministic
+    branches: losses, multipliers and (strided) weights after each update; SQRL action filter."""
+    import torch
+    z = np.load(os.path.join(golden_dir, "agent_algos_b64.npz"))
+    ag = algo_oracle_agent(z, tag)
+    P = tag + "_"
+    stride = int(z["stride"])
+    for u in range(int(z["n_qr"])):
+        q = "%sqr%d_" % (P, u)
+        e_next, _ = algo_noise(z, tag, "qr", 500, u)
+        ag.qrisk_update([z[q + k] for k in ("s", "a", "c", "s2", "m")], e_next, None)
+    n_upd = int(z["n_updates"])
+    for u in range(n_upd):
+        q = "%ssac%d_" % (P, u)
+        e_next, e_cur = algo_noise(z, tag, "sac", 1000, u)
+        L = ag.sac_update([z[q + k] for k in ("s", "a", "r", "s2", "m")], e_next, e_cur, u, nu=float(z[q + "nu_arg"]))
+        assert np.allclose(L, z[q + "losses"], rtol=1e-5, atol=1e-7), (L, z[q + "losses"])
+        for k in ("qf1", "qf2", "target", "pi", "min_qf_pi"):
+            assert np.allclose(ag.dbg[k], z[q + k], rtol=1e-5, atol=1e-6), k
+        assert np.isclose(ag.log_nu.item(), float(z[q + "log_nu"]), rtol=1e-9, atol=1e-12)
+        assert np.isclose(ag.log_lambda.item(), float(z[q + "log_lambda"]), rtol=1e-9, atol=1e-12)
+        assert np.isclose(float(ag.alpha), float(z[q + "alpha_after"]), rtol=1e-6)
+        if u in (0, n_upd - 1):
+            for net in ("critic", "critic_target", "policy"):
+                for i, p in enumerate(ag.params(net)):
+                    assert np.allclose(p.ravel()[::stride], z["%safter_%s_%d" % (q, net, i)], rtol=1e-5, atol=1e-6), (net, i)
+    if tag == "sqrl":
+        for i in range(len(z["sqrl_sel_s"])):
+            torch.manual_seed(7000 + i)
+            a = ag.select_action_sqrl(z["sqrl_sel_s"][i], z["sqrl_sel_eps"][i], eps_safe=float(z["sqrl_sel_thresh"][i]))
+            assert np.allclose(a, z["sqrl_sel_action"][i], rtol=1e-5, atol=1e-7), i
