@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define RRL_VERSION 1
+#define RRL_VERSION 2
 
 const char* rrl_last_error(void);
 int rrl_version(void);
@@ -57,6 +57,9 @@ enum {
     RRL_C_EXT_VIOLS      = 20, /* violations seen on OTHER ranks (multi-GPU gate), host/NCCL-set */
     RRL_C_RETURN_SUM_BITS= 21, /* double bit pattern: sum of finished-episode returns      */
     RRL_C_ERROR          = 22, /* sticky device-side error code (1: sample larger than population) */
+    RRL_C_ADAM_T_ALPHA   = 23, /* Adam step counts of the scalar multipliers: log_alpha (sac.py:245-247),  */
+    RRL_C_ADAM_T_NU      = 24, /*   log_nu (sac.py:259-261),                                                */
+    RRL_C_ADAM_T_LAMBDA  = 25, /*   log_lambda_RCPO (sac.py:268-270)                                        */
     RRL_NUM_COUNTERS     = 32
 };
 
@@ -161,7 +164,36 @@ typedef struct {
     int32_t mf_recovery;                   /* qrisk.py:150                                  */
     float grad_scale;                      /* 1/world_size applied inside Adam              */
     int32_t use_tensor_cores;              /* act kernel: 0 = fp32 FFMA, 1 = tcgen05 fp16 hi/lo split (3 MMAs) */
+    /* comparison-algorithm branches of SAC.update_parameters (sac.py:52-72, 95-101, 116-117) */
+    int32_t algo_flags;                    /* RRL_ALGO_* bits                               */
+    float target_entropy;                  /* -dim(A) (sac.py:97-98)                         */
+    double nu, lambda_rcpo;                /* initial multipliers (arg_utils.py:230-255)     */
+    double lr64;                           /* args.lr as the python float (0 -> (double)lr): the scalar
+                                              multipliers are float64 tensors with Adam lr 0.1*lr (sac.py:64,72) */
 } rrl_agent_config_t;
+enum {
+    RRL_ALGO_DGD = 1,            /* --DGD_constraints: policy loss += nu*(max Q_risk(s,pi) - eps_safe)  sac.py:224-228 */
+    RRL_ALGO_UPDATE_NU = 2,      /* --update_nu: Adam on log_nu                                    sac.py:256-262 */
+    RRL_ALGO_RCPO = 4,           /* --RCPO: target -= lambda*max Q_risk(s,a); Adam on log_lambda   sac.py:202-205,265-271 */
+    RRL_ALGO_AUTO_ALPHA = 8,     /* --automatic_entropy_tuning: Adam on log_alpha                  sac.py:241-250 */
+    RRL_ALGO_DETERMINISTIC = 16  /* --policy Deterministic (model.py:447-485): alpha = 0, action = mean + noise */
+};
+/* scalar block inside the arena (scratch name "scalars", 32 floats, 8-byte aligned).  fp32 slots: */
+enum {
+    RRL_S_ALPHA = 0,       /* alpha used by the NEXT update (args.alpha, or exp(log_alpha) after a tuning step) */
+    RRL_S_NU_ARG = 1,      /* the `nu` argument of update_parameters (experiment.py:406: nu_schedule(i_episode)); host-set */
+    RRL_S_LOG_ALPHA = 2, RRL_S_G_LOG_ALPHA = 3, RRL_S_M_ALPHA = 4, RRL_S_V_ALPHA = 5,
+    RRL_S_ALPHA_LOSS = 6,
+    RRL_S_F64_BASE = 8     /* float64 slots follow (index in doubles from here): */
+};
+enum {
+    RRL_D_G_LOG_NU = 0, RRL_D_G_LOG_LAMBDA = 1,   /* adjacent: the multi-GPU gradient sum of the two */
+    RRL_D_LOG_NU = 2, RRL_D_M_NU = 3, RRL_D_V_NU = 4,
+    RRL_D_LOG_LAMBDA = 5, RRL_D_M_LAMBDA = 6, RRL_D_V_LAMBDA = 7,
+    RRL_D_LAMBDA = 8,      /* lambda_RCPO used by the next update (args value, then exp(log_lambda)) */
+    RRL_D_NU_LEARNED = 9,  /* exp(log_nu) (sac.py:262; the reference never feeds it back: nu is always passed) */
+    RRL_D_ZERO = 10        /* constant 0: log_std of the Deterministic policy's unit-variance noise term */
+};
 
 /* Arena layout (fp32 elements).  Tensors of every net follow torch's parameters() order of the
  * reference module (model.py:49-76,172-199,295-343,489-530), each padded to 4 floats. */
@@ -174,6 +206,10 @@ int rrl_agent_grad_range(const rrl_agent_config_t* cfg, int net, int64_t* offset
 /* named scratch regions inside the arena (batch arrays, per-row outputs, losses) */
 int rrl_agent_scratch_info(const rrl_agent_config_t* cfg, const char* name, int64_t* offset,
                            int64_t* count);
+
+/* Write the initial values of the scalar block (alpha, nu, lambda, their logs; Adam moments zero) from cfg.
+ * Call once after allocating the arena (sac.py:48,56-72,99-101). */
+int rrl_agent_init_scalars(const rrl_agent_config_t* cfg, float* arena, void* stream);
 
 /* Rebuild the derived weight images (k-major copies of the ten 256x256 hidden matrices that the GEMM
  * kernels stream) after the host wrote parameters into the arena (e.g. the xavier init of
@@ -203,7 +239,11 @@ int rrl_agent_act(const rrl_agent_config_t* cfg, float* arena, int64_t n, const 
  *   rrl_sac_apply    : Adam on critic+policy (torch.optim.Adam), Polyak on critic_target
  * batch arrays live in the arena scratch ("sac_s","sac_a","sac_r","sac_s2","sac_m");
  * eps_next/eps_cur fp32 [B][2] or NULL (Philox).  losses: fp32 [8] device:
- *   {qf1_loss, qf2_loss, policy_loss, alpha_loss(0), alpha}. */
+ *   {qf1_loss, qf2_loss, policy_loss, alpha_loss, alpha (before this update's tuning step)}.
+ * cfg->algo_flags selects the comparison branches: they read alpha / nu / lambda from the scalar block, add the
+ * Q_risk(s,a) (RCPO) and Q_risk(s,pi) (DGD, update_nu) passes, and rrl_sac_apply also steps the scalar Adams.
+ * With RRL_ALGO_DETERMINISTIC eps_next / eps_cur hold the (already scaled and clamped) noise vector of
+ * DeterministicPolicy.sample repeated on every row, and must not be NULL. */
 int rrl_sac_backward(const rrl_agent_config_t* cfg, float* arena, const float* eps_next,
                      const float* eps_cur, uint64_t seed, int32_t stream_id, int64_t* counters,
                      float* losses, void* stream);

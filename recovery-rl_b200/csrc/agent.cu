@@ -193,7 +193,7 @@ struct FwdPass {
     float *out_q, *out_a, *out_logp, *out_mean, *out_raw, *out_eps;
 };
 struct FwdArgs {
-    FwdPass p[6];
+    FwdPass p[10];
     int n_pass;
     const int64_t* rows_ptr;
     int64_t rows_const;
@@ -244,6 +244,7 @@ __global__ void __launch_bounds__(kThreads, (BM == 64) ? 2 : 3) mlp_forward_kern
                 float a[2], mean_a[2], lp;
                 if (P.head == HEAD_GAUSS) gauss_sample(raw, e, A.sp, a, &lp, mean_a);
                 else stoch_sample(raw, P.w.log_std, e, A.sp, a, mean_a, &lp);
+                if (P.head == HEAD_DET) lp = 0.f;  // DeterministicPolicy.sample returns torch.tensor(0.) (model.py:481)
                 if (P.out_a) reinterpret_cast<float2*>(P.out_a)[row] = make_float2(a[0], a[1]);
                 if (P.out_logp) P.out_logp[row] = lp;
                 if (P.out_mean) reinterpret_cast<float2*>(P.out_mean)[row] = make_float2(mean_a[0], mean_a[1]);
@@ -358,7 +359,7 @@ struct HeadBwdPass {
     float *gW3a, *gW3b, *gb3a, *gb3b, *gb2;  // NULL when no weight grads are needed
 };
 struct HeadBwdArgs {
-    HeadBwdPass p[4];
+    HeadBwdPass p[6];
     const int64_t* rows_ptr;
     int64_t R;
 };
@@ -533,7 +534,7 @@ struct L1BwdPass {
     float* dxa;        // [rows][2] gradient w.r.t. the action input; NULL: skip
 };
 struct L1BwdArgs {
-    L1BwdPass p[4];
+    L1BwdPass p[6];
     const int64_t* rows_ptr;
 };
 
@@ -617,22 +618,51 @@ __device__ float block_sum(float v, float* red /*[8]*/) {
     return r;
 }
 
-// (4) SAC losses (sac.py:192-231): TD target, critic MSE, policy loss, and the output gradients
+// (4) SAC losses (sac.py:192-231): TD target, critic MSE, policy loss, and the output gradients; plus the
+//     comparison branches: RCPO target penalty (:202-205), DGD policy penalty (:224-228) and the gradients of the
+//     three scalar multipliers log_alpha (:241-243), log_nu (:257-258), log_lambda (:266-267)
 struct SacLossArgs {
     const float *r, *m, *next_logp, *qt1, *qt2, *qf1, *qf2, *logp, *qp1, *qp2;
-    float *target, *dqf1, *dqf2, *dqp1, *dqp2, *minq, *losses;
-    float gamma, alpha;
+    const float *sq1, *sq2;  // Q_risk(s, pi)  (DGD / update_nu) or NULL
+    const float *qs1, *qs2;  // Q_risk(s, a)   (RCPO) or NULL
+    float *target, *dqf1, *dqf2, *dqp1, *dqp2, *minq, *dsq1, *dsq2, *losses;
+    float* scal;             // scalar block (RRL_S_* / RRL_D_*)
+    float gamma, eps_safe, target_entropy;
+    int flags;
     const int64_t* rows_ptr;
 };
+__device__ double block_sum_d(double v, double* red /*[8]*/) {
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double r = 0.0;
+    if (threadIdx.x == 0)
+        for (int w = 0; w < 8; ++w) r += red[w];
+    return r;
+}
 __global__ void __launch_bounds__(kThreads) sac_loss_kernel(const __grid_constant__ SacLossArgs A) {
     const int64_t rows = *A.rows_ptr;
     if (rows <= 0) return;
     __shared__ float red[8];
+    __shared__ double redd[8];
     const float inv = 1.0f / (float)rows;
-    float l1 = 0.f, l2 = 0.f, lp = 0.f;
+    const float alpha = A.scal[RRL_S_ALPHA];
+    const float nu = A.scal[RRL_S_NU_ARG];
+    double* sd = reinterpret_cast<double*>(A.scal + RRL_S_F64_BASE);
+    const float lambda = (float)sd[RRL_D_LAMBDA];  // 0-dim float64 tensor times a float32 tensor: computed in float32
+    const bool dgd = (A.flags & RRL_ALGO_DGD) != 0, rcpo = (A.flags & RRL_ALGO_RCPO) != 0;
+    float l1 = 0.f, l2 = 0.f, lp = 0.f, la = 0.f;
+    double gnu = 0.0, glam = 0.0;
     for (int64_t i = threadIdx.x; i < rows; i += kThreads) {
-        const float minq_next = fminf(A.qt1[i], A.qt2[i]) - A.alpha * A.next_logp[i];
-        const float y = A.r[i] + A.m[i] * A.gamma * minq_next;
+        const float minq_next = fminf(A.qt1[i], A.qt2[i]) - alpha * A.next_logp[i];
+        float y = A.r[i] + A.m[i] * A.gamma * minq_next;
+        if (rcpo) {
+            const float qsafe = fmaxf(A.qs1[i], A.qs2[i]);
+            y -= lambda * qsafe;
+            glam += (double)(A.eps_safe - qsafe);
+        }
         A.target[i] = y;
         const float e1 = A.qf1[i] - y, e2 = A.qf2[i] - y;
         l1 = fmaf(e1, e1, l1);
@@ -642,7 +672,23 @@ __global__ void __launch_bounds__(kThreads) sac_loss_kernel(const __grid_constan
         const float p1 = A.qp1[i], p2 = A.qp2[i];
         const float mq = fminf(p1, p2);
         A.minq[i] = mq;
-        lp += A.alpha * A.logp[i] - mq;
+        const float lg = A.logp[i];
+        float row = alpha * lg;
+        if (A.sq1) {
+            const float s1 = A.sq1[i], s2 = A.sq2[i];
+            const float ms = fmaxf(s1, s2);
+            gnu += (double)(A.eps_safe - ms);
+            if (dgd) {
+                row += nu * (ms - A.eps_safe);
+                // d(nu*max)/d(raw): torch.max routes to the larger input (ties split evenly), through the sigmoid
+                const float g1 = s1 > s2 ? nu * inv : (s1 == s2 ? 0.5f * nu * inv : 0.f);
+                const float g2 = s2 > s1 ? nu * inv : (s1 == s2 ? 0.5f * nu * inv : 0.f);
+                A.dsq1[i] = g1 * s1 * (1.0f - s1);
+                A.dsq2[i] = g2 * s2 * (1.0f - s2);
+            }
+        }
+        lp += row - mq;
+        la += lg + A.target_entropy;
         // d(-min)/dq: torch.min(a, b) routes the gradient to the smaller input (ties split evenly)
         A.dqp1[i] = p1 < p2 ? -inv : (p1 == p2 ? -0.5f * inv : 0.f);
         A.dqp2[i] = p2 < p1 ? -inv : (p1 == p2 ? -0.5f * inv : 0.f);
@@ -650,20 +696,32 @@ __global__ void __launch_bounds__(kThreads) sac_loss_kernel(const __grid_constan
     const float s1 = block_sum(l1, red);
     const float s2 = block_sum(l2, red);
     const float s3 = block_sum(lp, red);
+    const float s4 = block_sum(la, red);
+    const double d1 = block_sum_d(gnu, redd);
+    const double d2 = block_sum_d(glam, redd);
     if (threadIdx.x == 0) {
         A.losses[0] = s1 * inv;
         A.losses[1] = s2 * inv;
         A.losses[2] = s3 * inv;
-        A.losses[3] = 0.f;      // alpha_loss (automatic_entropy_tuning False)
-        A.losses[4] = A.alpha;
+        A.losses[4] = alpha;
+        float alpha_loss = 0.f;
+        if (A.flags & RRL_ALGO_AUTO_ALPHA) {  // alpha_loss = -(log_alpha * (log_pi + target_entropy)).mean()
+            const float mean_t = s4 * inv;
+            alpha_loss = -(A.scal[RRL_S_LOG_ALPHA] * mean_t);
+            A.scal[RRL_S_G_LOG_ALPHA] = -mean_t;
+        }
+        A.losses[3] = alpha_loss;
+        A.scal[RRL_S_ALPHA_LOSS] = alpha_loss;
+        if (A.flags & RRL_ALGO_UPDATE_NU) sd[RRL_D_G_LOG_NU] = d1 / (double)rows;
+        if (rcpo) sd[RRL_D_G_LOG_LAMBDA] = d2 / (double)rows;
     }
 }
 
 // (5) GaussianPolicy.sample backward: d raw(mean, log_std) from dL/da (through the critic) and alpha*logp
 struct GaussBwdArgs {
-    const float *raw, *eps, *dxa1, *dxa2;
+    const float *raw, *eps, *dxa1, *dxa2, *dxa3, *dxa4;  // dxa3/4: through Q_risk(s, pi) (DGD) or NULL
     float* draw;
-    float alpha;
+    const float* scal;
     ActionSpace sp;
     const int64_t* rows_ptr;
 };
@@ -676,7 +734,13 @@ __global__ void __launch_bounds__(kThreads) gauss_backward_kernel(const __grid_c
     const float raw[4] = {rv.x, rv.y, rv.z, rv.w};
     const float2 e = reinterpret_cast<const float2*>(A.eps)[i];
     const float2 d1 = reinterpret_cast<const float2*>(A.dxa1)[i], d2 = reinterpret_cast<const float2*>(A.dxa2)[i];
-    const float da[2] = {d1.x + d2.x, d1.y + d2.y};
+    float da[2] = {d1.x + d2.x, d1.y + d2.y};
+    if (A.dxa3) {
+        const float2 d3 = reinterpret_cast<const float2*>(A.dxa3)[i], d4 = reinterpret_cast<const float2*>(A.dxa4)[i];
+        da[0] += d3.x + d4.x;
+        da[1] += d3.y + d4.y;
+    }
+    const float alpha = A.scal[RRL_S_ALPHA];
     const float ev[2] = {e.x, e.y};
     float out[4];
 #pragma unroll
@@ -689,10 +753,10 @@ __global__ void __launch_bounds__(kThreads) gauss_backward_kernel(const __grid_c
         const float om = 1.0f - y * y;
         const float den = A.sp.scale[k] * om + 1e-6f;
         // dL/dy = dL/da * scale + (alpha/B) * d(-log(scale*(1-y^2)+1e-6))/dy
-        const float dy = da[k] * A.sp.scale[k] + A.alpha * inv * (2.0f * A.sp.scale[k] * y) / den;
+        const float dy = da[k] * A.sp.scale[k] + alpha * inv * (2.0f * A.sp.scale[k] * y) / den;
         const float dx = dy * om;
         out[k] = dx;                                               // d mean
-        const float dls = dx * sd * ev[k] - A.alpha * inv;         // through x and through -log(std)
+        const float dls = dx * sd * ev[k] - alpha * inv;           // through x and through -log(std)
         out[2 + k] = (lsr >= LOG_SIG_MIN && lsr <= LOG_SIG_MAX) ? dls : 0.f;  // clamp backward
     }
     reinterpret_cast<float4*>(A.draw)[i] = make_float4(out[0], out[1], out[2], out[3]);
@@ -755,7 +819,7 @@ __global__ void __launch_bounds__(kThreads) recovery_loss_kernel(const __grid_co
 
 // (8) StochasticPolicy.sample backward (single CTA): d raw mean, d log_std
 struct StochBwdArgs {
-    const float *raw, *eps, *dxa1, *dxa2, *log_std;
+    const float *raw, *eps, *dxa1, *dxa2, *dxa3, *dxa4, *log_std;  // dxa3/4 optional; g_log_std NULL: Deterministic policy
     float *draw, *g_log_std;
     ActionSpace sp;
     const int64_t* rows_ptr;
@@ -776,7 +840,12 @@ __global__ void __launch_bounds__(kThreads) stoch_backward_kernel(const __grid_c
         const float4 rv = reinterpret_cast<const float4*>(A.raw)[i];
         const float2 e = reinterpret_cast<const float2*>(A.eps)[i];
         const float2 d1 = reinterpret_cast<const float2*>(A.dxa1)[i], d2 = reinterpret_cast<const float2*>(A.dxa2)[i];
-        const float da0 = d1.x + d2.x, da1 = d1.y + d2.y;
+        float da0 = d1.x + d2.x, da1 = d1.y + d2.y;
+        if (A.dxa3) {
+            const float2 d3 = reinterpret_cast<const float2*>(A.dxa3)[i], d4 = reinterpret_cast<const float2*>(A.dxa4)[i];
+            da0 += d3.x + d4.x;
+            da1 += d3.y + d4.y;
+        }
         const float t0 = tanhf(rv.x), t1 = tanhf(rv.y);
         reinterpret_cast<float4*>(A.draw)[i] =
             make_float4(da0 * A.sp.scale[0] * (1.0f - t0 * t0), da1 * A.sp.scale[1] * (1.0f - t1 * t1), 0.f, 0.f);
@@ -785,7 +854,7 @@ __global__ void __launch_bounds__(kThreads) stoch_backward_kernel(const __grid_c
     }
     const float s0 = block_sum(gl[0], red);
     const float s1 = block_sum(gl[1], red);
-    if (threadIdx.x == 0) {
+    if (threadIdx.x == 0 && A.g_log_std) {
         A.g_log_std[0] = s0 * pass[0];
         A.g_log_std[1] = s1 * pass[1];
     }
@@ -800,6 +869,7 @@ struct AdamArgs {
     float* arena;
     int64_t off, count, grad_off, m_off, v_off;
     float lr, b1, b2, eps, grad_scale;
+    double lr64;
     const int64_t* counters;
     int t_counter, rows_counter;
     ImgRef img[4];
@@ -808,14 +878,13 @@ struct AdamArgs {
 __global__ void __launch_bounds__(kThreads) adam_kernel(const __grid_constant__ AdamArgs A) {
     if (A.counters[A.rows_counter] <= 0) return;
     __shared__ float s_bc[2];
-    if (threadIdx.x == 0) {  // bias corrections in double, once per block
+    if (threadIdx.x == 0) {  // bias corrections and step size in double (python floats in torch), once per block
         const double tstep = (double)(A.counters[A.t_counter] + 1);
-        s_bc[0] = (float)(1.0 - pow((double)A.b1, tstep));
+        s_bc[0] = (float)(A.lr64 / (1.0 - pow((double)A.b1, tstep)));
         s_bc[1] = (float)sqrt(1.0 - pow((double)A.b2, tstep));
     }
     __syncthreads();
-    const float bc1 = s_bc[0], bc2s = s_bc[1];
-    const float step_size = A.lr / bc1;
+    const float step_size = s_bc[0], bc2s = s_bc[1];
     for (int64_t i = blockIdx.x * (int64_t)kThreads + threadIdx.x; i < A.count; i += (int64_t)gridDim.x * kThreads) {
         const int64_t o = A.off + i;
         const float g = A.arena[A.grad_off + o] * A.grad_scale;
@@ -832,6 +901,60 @@ __global__ void __launch_bounds__(kThreads) adam_kernel(const __grid_constant__ 
             if (d >= 0 && d < (int64_t)H * H) A.arena[A.img[q].img + (d & (H - 1)) * H + (d >> 8)] = p;
         }
     }
+}
+
+// (9b) Adam on the scalar multipliers (sac.py:241-271): log_alpha is a float32 tensor with lr; log_nu and
+//      log_lambda_RCPO are float64 tensors (np.log of a python float) with lr 0.1*lr.  One thread.
+struct ScalarAdamArgs {
+    float* scal;
+    int64_t* counters;
+    double lr, b1, b2, eps, grad_scale;
+    int flags, rows_counter;
+};
+template <typename T>
+__device__ void adam_scalar(T& p, T g, T& m, T& v, double lr, double b1, double b2, double eps, double tstep) {
+    m = m + (g - m) * (T)(1.0 - b1);
+    v = v * (T)b2 + (T)(1.0 - b2) * g * g;
+    const double bc1 = 1.0 - pow(b1, tstep), bc2s = sqrt(1.0 - pow(b2, tstep));
+    const T denom = (T)sqrt((double)v) / (T)bc2s + (T)eps;
+    p = p - (T)(lr / bc1) * (m / denom);
+}
+__global__ void scalar_adam_kernel(const ScalarAdamArgs A) {
+    if (threadIdx.x != 0 || blockIdx.x != 0 || A.counters[A.rows_counter] <= 0) return;
+    double* sd = reinterpret_cast<double*>(A.scal + RRL_S_F64_BASE);
+    if (A.flags & RRL_ALGO_AUTO_ALPHA) {
+        const double t = (double)(A.counters[RRL_C_ADAM_T_ALPHA] + 1);
+        adam_scalar<float>(A.scal[RRL_S_LOG_ALPHA], A.scal[RRL_S_G_LOG_ALPHA] * (float)A.grad_scale, A.scal[RRL_S_M_ALPHA],
+                           A.scal[RRL_S_V_ALPHA], A.lr, A.b1, A.b2, A.eps, t);
+        A.scal[RRL_S_ALPHA] = expf(A.scal[RRL_S_LOG_ALPHA]);  // self.alpha = self.log_alpha.exp()
+        A.counters[RRL_C_ADAM_T_ALPHA] += 1;
+    }
+    if (A.flags & RRL_ALGO_UPDATE_NU) {
+        const double t = (double)(A.counters[RRL_C_ADAM_T_NU] + 1);
+        adam_scalar<double>(sd[RRL_D_LOG_NU], sd[RRL_D_G_LOG_NU] * A.grad_scale, sd[RRL_D_M_NU], sd[RRL_D_V_NU], 0.1 * A.lr,
+                            A.b1, A.b2, A.eps, t);
+        sd[RRL_D_NU_LEARNED] = exp(sd[RRL_D_LOG_NU]);
+        A.counters[RRL_C_ADAM_T_NU] += 1;
+    }
+    if (A.flags & RRL_ALGO_RCPO) {
+        const double t = (double)(A.counters[RRL_C_ADAM_T_LAMBDA] + 1);
+        adam_scalar<double>(sd[RRL_D_LOG_LAMBDA], sd[RRL_D_G_LOG_LAMBDA] * A.grad_scale, sd[RRL_D_M_LAMBDA], sd[RRL_D_V_LAMBDA],
+                            0.1 * A.lr, A.b1, A.b2, A.eps, t);
+        sd[RRL_D_LAMBDA] = exp(sd[RRL_D_LOG_LAMBDA]);
+        A.counters[RRL_C_ADAM_T_LAMBDA] += 1;
+    }
+}
+__global__ void init_scalars_kernel(float* scal, float alpha, double nu, double lambda) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    for (int i = 0; i < 32; ++i) scal[i] = 0.f;
+    double* sd = reinterpret_cast<double*>(scal + RRL_S_F64_BASE);
+    scal[RRL_S_ALPHA] = alpha;
+    scal[RRL_S_NU_ARG] = (float)nu;
+    scal[RRL_S_LOG_ALPHA] = 0.f;  // torch.zeros(1) (sac.py:99-101)
+    sd[RRL_D_LOG_NU] = log(nu);
+    sd[RRL_D_LOG_LAMBDA] = log(lambda);
+    sd[RRL_D_LAMBDA] = lambda;
+    sd[RRL_D_NU_LEARNED] = nu;
 }
 
 // (10) soft_update (utils.py:46-49): target = target*(1-tau) + source*tau over a whole net (+ image refresh)
@@ -940,6 +1063,7 @@ int launch_adam(const rrl_agent_config_t* cfg, const Layout& L, float* arena, in
     A.count = L.net_size[net_a] + (net_b >= 0 ? L.net_size[net_b] : 0);
     A.grad_off = L.grad_off; A.m_off = L.m_off; A.v_off = L.v_off;
     A.lr = cfg->lr; A.b1 = cfg->beta1; A.b2 = cfg->beta2; A.eps = cfg->adam_eps;
+    A.lr64 = cfg->lr64 > 0.0 ? cfg->lr64 : (double)cfg->lr;
     A.grad_scale = cfg->grad_scale;
     A.counters = counters;
     A.t_counter = t_counter;
@@ -1041,6 +1165,17 @@ extern "C" int rrl_agent_scratch_info(const rrl_agent_config_t* cfg, const char*
     return -2;
 }
 
+extern "C" int rrl_agent_init_scalars(const rrl_agent_config_t* cfg, float* arena, void* stream) {
+    CHECK_CFG(cfg);
+    RRL_CHECK_ARG(arena, "null arena");
+    RRL_CHECK_ARG(cfg->nu > 0.0 && cfg->lambda_rcpo > 0.0, "nu and lambda_rcpo must be positive (their logs are the parameters)");
+    const Layout L = make_layout(cfg);
+    const float alpha = (cfg->algo_flags & RRL_ALGO_DETERMINISTIC) ? 0.f : cfg->alpha;  // sac.py:116
+    init_scalars_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(arena + L.scalars, alpha, cfg->nu, cfg->lambda_rcpo);
+    RRL_CHECK_LAUNCH();
+    return 0;
+}
+
 extern "C" int rrl_agent_refresh(const rrl_agent_config_t* cfg, float* arena, void* stream) {
     CHECK_CFG(cfg);
     RRL_CHECK_ARG(arena, "null arena");
@@ -1137,7 +1272,8 @@ extern "C" int rrl_policy_sample(const rrl_agent_config_t* cfg, const float* are
     memset(&A, 0, sizeof(A));
     FwdPass& p = A.p[0];
     p.w = head_w(L, arena, net, 0);
-    p.head = net == RRL_NET_POLICY ? HEAD_GAUSS : HEAD_STOCH;
+    p.head = HEAD_STOCH;
+    if (net == RRL_NET_POLICY) p.w = task_policy_w(L, arena, cfg, &p.head);
     p.xs = s; p.eps = eps;
     p.out_a = action; p.out_logp = log_prob; p.out_mean = mean_action;
     A.n_pass = 1;
@@ -1161,7 +1297,17 @@ extern "C" int rrl_sac_backward(const rrl_agent_config_t* cfg, float* arena, con
     auto R2 = [&](int id) { return arena + L.rows2_f[id]; };
     auto R4 = [&](int id) { return arena + L.rows4_f[id]; };
     if (!losses) losses = arena + L.losses;
+    float* scal = arena + L.scalars;
     const ActionSpace sp = action_space(cfg);
+    const int flags = cfg->algo_flags;
+    const bool det = (flags & RRL_ALGO_DETERMINISTIC) != 0;
+    const bool rcpo = (flags & RRL_ALGO_RCPO) != 0;
+    const bool dgd = (flags & RRL_ALGO_DGD) != 0;
+    const bool sq_pi = dgd || (flags & RRL_ALGO_UPDATE_NU);  // sac.py:221-222 is dead code otherwise
+    RRL_CHECK_ARG(!det || (eps_next && eps_cur), "the Deterministic policy needs its noise as an input");
+    int pol_head = HEAD_GAUSS;
+    const HeadW pw = task_policy_w(L, arena, cfg, &pol_head);
+    const HeadG pg = head_g(L, arena, RRL_NET_POLICY, 0);
 
     {  // policy on s' (no grad, sac.py:192-194) and on s (sac.py:216)
         FwdArgs A;
@@ -1169,94 +1315,123 @@ extern "C" int rrl_sac_backward(const rrl_agent_config_t* cfg, float* arena, con
         A.n_pass = 2; A.rows_ptr = rows_ptr; A.sp = sp; A.seed = seed; A.stream_id = (uint32_t)stream_id;
         A.counters = counters; A.step_counter = RRL_C_SAC_UPDATES;
         FwdPass& p0 = A.p[0];
-        p0.w = head_w(L, arena, RRL_NET_POLICY, 0); p0.head = HEAD_GAUSS; p0.xs = s2; p0.eps = eps_next;
+        p0.w = pw; p0.head = pol_head; p0.xs = s2; p0.eps = eps_next;
         p0.draw_id = RRL_DRAW_SAC_NEXT; p0.out_a = R2(R2_NEXT_A); p0.out_logp = RA(RA_NEXT_LOGP);
         FwdPass& p1 = A.p[1];
-        p1.w = p0.w; p1.head = HEAD_GAUSS; p1.xs = s; p1.eps = eps_cur; p1.draw_id = RRL_DRAW_SAC_CUR;
+        p1.w = pw; p1.head = pol_head; p1.xs = s; p1.eps = eps_cur; p1.draw_id = RRL_DRAW_SAC_CUR;
         p1.h1 = arena + L.h1[4]; p1.h2 = arena + L.h2[4];
         p1.out_a = R2(R2_PI); p1.out_logp = RA(RA_LOGP); p1.out_raw = R4(R4_RAW_POL); p1.out_eps = R2(R2_EPS_CUR);
         int rc = launch_forward<32>(A, R, st);
         if (rc) return rc;
     }
     {  // critic_target(s', a'), critic(s, a), critic(s, pi)   (sac.py:195-196, 206-207, 218)
+       // [+ Q_risk(s, pi) (sac.py:221) for DGD / update_nu, + Q_risk(s, a) (sac.py:203-204) for RCPO]
         FwdArgs A;
         memset(&A, 0, sizeof(A));
-        A.n_pass = 6; A.rows_ptr = rows_ptr; A.sp = sp;
-        A.p[0] = q_pass(L, arena, RRL_NET_CRITIC_TARGET, 0, s2, R2(R2_NEXT_A), -1, RA(RA_QT1));
-        A.p[1] = q_pass(L, arena, RRL_NET_CRITIC_TARGET, 1, s2, R2(R2_NEXT_A), -1, RA(RA_QT2));
-        A.p[2] = q_pass(L, arena, RRL_NET_CRITIC, 0, s, a, 0, RA(RA_QF1));
-        A.p[3] = q_pass(L, arena, RRL_NET_CRITIC, 1, s, a, 1, RA(RA_QF2));
-        A.p[4] = q_pass(L, arena, RRL_NET_CRITIC, 0, s, R2(R2_PI), 2, RA(RA_QP1));
-        A.p[5] = q_pass(L, arena, RRL_NET_CRITIC, 1, s, R2(R2_PI), 3, RA(RA_QP2));
+        A.rows_ptr = rows_ptr; A.sp = sp;
+        int n = 0;
+        A.p[n++] = q_pass(L, arena, RRL_NET_CRITIC_TARGET, 0, s2, R2(R2_NEXT_A), -1, RA(RA_QT1));
+        A.p[n++] = q_pass(L, arena, RRL_NET_CRITIC_TARGET, 1, s2, R2(R2_NEXT_A), -1, RA(RA_QT2));
+        A.p[n++] = q_pass(L, arena, RRL_NET_CRITIC, 0, s, a, 0, RA(RA_QF1));
+        A.p[n++] = q_pass(L, arena, RRL_NET_CRITIC, 1, s, a, 1, RA(RA_QF2));
+        A.p[n++] = q_pass(L, arena, RRL_NET_CRITIC, 0, s, R2(R2_PI), 2, RA(RA_QP1));
+        A.p[n++] = q_pass(L, arena, RRL_NET_CRITIC, 1, s, R2(R2_PI), 3, RA(RA_QP2));
+        if (sq_pi) {
+            A.p[n++] = q_pass(L, arena, RRL_NET_QRISK, 0, s, R2(R2_PI), dgd ? 5 : -1, RA(RA_SQ1));
+            A.p[n++] = q_pass(L, arena, RRL_NET_QRISK, 1, s, R2(R2_PI), dgd ? 6 : -1, RA(RA_SQ2));
+        }
+        if (rcpo) {
+            A.p[n++] = q_pass(L, arena, RRL_NET_QRISK, 0, s, a, -1, RA(RA_QS1));
+            A.p[n++] = q_pass(L, arena, RRL_NET_QRISK, 1, s, a, -1, RA(RA_QS2));
+        }
+        A.n_pass = n;
         int rc = launch_forward<32>(A, R, st);
         if (rc) return rc;
     }
     {
         SacLossArgs A;
+        memset(&A, 0, sizeof(A));
         A.r = r; A.m = m; A.next_logp = RA(RA_NEXT_LOGP); A.qt1 = RA(RA_QT1); A.qt2 = RA(RA_QT2);
         A.qf1 = RA(RA_QF1); A.qf2 = RA(RA_QF2); A.logp = RA(RA_LOGP); A.qp1 = RA(RA_QP1); A.qp2 = RA(RA_QP2);
+        if (sq_pi) { A.sq1 = RA(RA_SQ1); A.sq2 = RA(RA_SQ2); A.dsq1 = RA(RA_DSQ1); A.dsq2 = RA(RA_DSQ2); }
+        if (rcpo) { A.qs1 = RA(RA_QS1); A.qs2 = RA(RA_QS2); }
         A.target = RA(RA_TARGET); A.dqf1 = RA(RA_DQF1); A.dqf2 = RA(RA_DQF2); A.dqp1 = RA(RA_DQP1); A.dqp2 = RA(RA_DQP2);
-        A.minq = RA(RA_MINQ); A.losses = losses; A.gamma = cfg->gamma; A.alpha = cfg->alpha; A.rows_ptr = rows_ptr;
+        A.minq = RA(RA_MINQ); A.losses = losses; A.scal = scal; A.gamma = cfg->gamma; A.eps_safe = cfg->eps_safe;
+        A.target_entropy = cfg->target_entropy; A.flags = flags; A.rows_ptr = rows_ptr;
         sac_loss_kernel<<<1, kThreads, 0, st>>>(A);
         RRL_CHECK_LAUNCH();
     }
     const HeadW c1 = head_w(L, arena, RRL_NET_CRITIC, 0), c2 = head_w(L, arena, RRL_NET_CRITIC, 1);
     const HeadG g1 = head_g(L, arena, RRL_NET_CRITIC, 0), g2 = head_g(L, arena, RRL_NET_CRITIC, 1);
-    {  // head backward of the four critic passes
+    const HeadW k1 = head_w(L, arena, RRL_NET_QRISK, 0), k2 = head_w(L, arena, RRL_NET_QRISK, 1);
+    const int nq = dgd ? 6 : 4;  // passes whose gradient flows back: critic x4 [+ Q_risk(s, pi) x2 into the action]
+    const int slot[6] = {0, 1, 2, 3, 5, 6};
+    {  // head backward of the critic passes (weight grads only for the (s, a) passes)
         HeadBwdArgs A;
         memset(&A, 0, sizeof(A));
         A.rows_ptr = rows_ptr; A.R = R;
-        const float* dout[4] = {RA(RA_DQF1), RA(RA_DQF2), RA(RA_DQP1), RA(RA_DQP2)};
-        for (int q = 0; q < 4; ++q) {
+        const float* dout[6] = {RA(RA_DQF1), RA(RA_DQF2), RA(RA_DQP1), RA(RA_DQP2), RA(RA_DSQ1), RA(RA_DSQ2)};
+        for (int q = 0; q < nq; ++q) {
             HeadBwdPass& p = A.p[q];
-            const HeadW& w = (q & 1) ? c2 : c1;
+            const HeadW& w = q < 4 ? ((q & 1) ? c2 : c1) : ((q & 1) ? k2 : k1);
             const HeadG& g = (q & 1) ? g2 : g1;
             p.dout = dout[q]; p.stride = 1; p.n_out = 1; p.na = 1;
-            p.W3a = w.W3a; p.h2 = arena + L.h2[q]; p.dh2 = arena + L.dh2[q];
+            p.W3a = w.W3a; p.h2 = arena + L.h2[slot[q]]; p.dh2 = arena + L.dh2[slot[q]];
             if (q < 2) { p.gW3a = g.W3a; p.gb3a = g.b3a; p.gb2 = g.b2; }
         }
-        head_backward_kernel<<<dim3(H / 32, 4), kThreads, 0, st>>>(A);
+        head_backward_kernel<<<dim3(H / 32, nq), kThreads, 0, st>>>(A);
         RRL_CHECK_LAUNCH();
     }
-    {  // dh1 for all four passes + gW2 for the (s, a) passes
+    {  // dh1 for all passes + gW2 for the (s, a) passes
         GemmArgs G;
         memset(&G, 0, sizeof(G));
         G.rows_ptr = rows_ptr;
-        for (int q = 0; q < 4; ++q) {
-            GemmPass& p = G.p[q];
-            p.A = arena + L.dh2[q]; p.lda = H; p.B = ((q & 1) ? c2 : c1).W2; p.k_is_rows = 0;
-            p.mask = arena + L.h1[q]; p.C = arena + L.dh1[q];
+        int n = 0;
+        for (int q = 0; q < nq; ++q) {
+            GemmPass& p = G.p[n++];
+            const HeadW& w = q < 4 ? ((q & 1) ? c2 : c1) : ((q & 1) ? k2 : k1);
+            p.A = arena + L.dh2[slot[q]]; p.lda = H; p.B = w.W2; p.k_is_rows = 0;
+            p.mask = arena + L.h1[slot[q]]; p.C = arena + L.dh1[slot[q]];
         }
         for (int q = 0; q < 2; ++q) {
-            GemmPass& p = G.p[4 + q];
+            GemmPass& p = G.p[n++];
             p.A = arena + L.dh2[q]; p.lda = H; p.B = arena + L.h1[q]; p.k_is_rows = 1; p.C = (q ? g2 : g1).W2;
         }
         const int mt = (int)((R > H ? R : H) / 32);
-        gemm_stream_kernel<<<dim3(mt, 6), kThreads, 0, st>>>(G);
+        gemm_stream_kernel<<<dim3(mt, n), kThreads, 0, st>>>(G);
         RRL_CHECK_LAUNCH();
     }
     {  // layer-1 backward: weight grads for (s, a); d/d(pi) for (s, pi)
         L1BwdArgs A;
         memset(&A, 0, sizeof(A));
         A.rows_ptr = rows_ptr;
-        for (int q = 0; q < 4; ++q) {
+        float* dxa[6] = {nullptr, nullptr, R2(R2_DPI), R2(R2_DPI_B), R2(R2_DPI_S1), R2(R2_DPI_S2)};
+        for (int q = 0; q < nq; ++q) {
             L1BwdPass& p = A.p[q];
-            const HeadW& w = (q & 1) ? c2 : c1;
+            const HeadW& w = q < 4 ? ((q & 1) ? c2 : c1) : ((q & 1) ? k2 : k1);
             const HeadG& g = (q & 1) ? g2 : g1;
-            p.dh1 = arena + L.dh1[q]; p.xs = s; p.xa = q < 2 ? a : R2(R2_PI); p.W1 = w.W1; p.n_in = 4;
+            p.dh1 = arena + L.dh1[slot[q]]; p.xs = s; p.xa = q < 2 ? a : R2(R2_PI); p.W1 = w.W1; p.n_in = 4;
             if (q < 2) { p.gW1 = g.W1; p.gb1 = g.b1; }
-            else p.dxa = q == 2 ? R2(R2_DPI) : arena + L.rows2_f[R2_REC_DPI];  // second head: borrowed scratch
+            else p.dxa = dxa[q];
         }
-        layer1_backward_kernel<<<dim3(kL1ColBlocks + kL1RowBlocks, 4), kThreads, 0, st>>>(A);
+        layer1_backward_kernel<<<dim3(kL1ColBlocks + kL1RowBlocks, nq), kThreads, 0, st>>>(A);
         RRL_CHECK_LAUNCH();
     }
-    const HeadW pw = head_w(L, arena, RRL_NET_POLICY, 0);
-    const HeadG pg = head_g(L, arena, RRL_NET_POLICY, 0);
-    {
+    if (!det) {
         GaussBwdArgs A;
-        A.raw = R4(R4_RAW_POL); A.eps = R2(R2_EPS_CUR); A.dxa1 = R2(R2_DPI); A.dxa2 = arena + L.rows2_f[R2_REC_DPI];
-        A.draw = R4(R4_DRAW_POL); A.alpha = cfg->alpha; A.sp = sp; A.rows_ptr = rows_ptr;
+        memset(&A, 0, sizeof(A));
+        A.raw = R4(R4_RAW_POL); A.eps = R2(R2_EPS_CUR); A.dxa1 = R2(R2_DPI); A.dxa2 = R2(R2_DPI_B);
+        if (dgd) { A.dxa3 = R2(R2_DPI_S1); A.dxa4 = R2(R2_DPI_S2); }
+        A.draw = R4(R4_DRAW_POL); A.scal = scal; A.sp = sp; A.rows_ptr = rows_ptr;
         gauss_backward_kernel<<<(unsigned)((R + kThreads - 1) / kThreads), kThreads, 0, st>>>(A);
+        RRL_CHECK_LAUNCH();
+    } else {  // DeterministicPolicy: a = tanh(raw)*scale + bias + noise
+        StochBwdArgs A;
+        memset(&A, 0, sizeof(A));
+        A.raw = R4(R4_RAW_POL); A.eps = R2(R2_EPS_CUR); A.dxa1 = R2(R2_DPI); A.dxa2 = R2(R2_DPI_B);
+        if (dgd) { A.dxa3 = R2(R2_DPI_S1); A.dxa4 = R2(R2_DPI_S2); }
+        A.log_std = pw.log_std; A.draw = R4(R4_DRAW_POL); A.g_log_std = nullptr; A.sp = sp; A.rows_ptr = rows_ptr;
+        stoch_backward_kernel<<<1, kThreads, 0, st>>>(A);
         RRL_CHECK_LAUNCH();
     }
     {
@@ -1264,9 +1439,10 @@ extern "C" int rrl_sac_backward(const rrl_agent_config_t* cfg, float* arena, con
         memset(&A, 0, sizeof(A));
         A.rows_ptr = rows_ptr; A.R = R;
         HeadBwdPass& p = A.p[0];
-        p.dout = R4(R4_DRAW_POL); p.stride = 4; p.n_out = 4; p.na = 2;
+        p.dout = R4(R4_DRAW_POL); p.stride = 4; p.n_out = det ? 2 : 4; p.na = 2;
         p.W3a = pw.W3a; p.W3b = pw.W3b; p.h2 = arena + L.h2[4]; p.dh2 = arena + L.dh2[4];
-        p.gW3a = pg.W3a; p.gW3b = pg.W3b; p.gb3a = pg.b3a; p.gb3b = pg.b3b; p.gb2 = pg.b2;
+        p.gW3a = pg.W3a; p.gb3a = pg.b3a; p.gb2 = pg.b2;
+        if (!det) { p.gW3b = pg.W3b; p.gb3b = pg.b3b; }
         head_backward_kernel<<<dim3(H / 32, 1), kThreads, 0, st>>>(A);
         RRL_CHECK_LAUNCH();
     }
@@ -1305,6 +1481,15 @@ extern "C" int rrl_sac_apply(const rrl_agent_config_t* cfg, float* arena, int64_
     rc = launch_polyak(L, arena, counters, RRL_NET_CRITIC_TARGET, RRL_NET_CRITIC, cfg->tau, RRL_C_SAC_ROWS,
                        RRL_C_SAC_UPDATES, cfg->target_update_interval, st);
     if (rc) return rc;
+    if (cfg->algo_flags & (RRL_ALGO_AUTO_ALPHA | RRL_ALGO_UPDATE_NU | RRL_ALGO_RCPO)) {  // sac.py:241-271
+        ScalarAdamArgs A;
+        A.scal = arena + L.scalars; A.counters = counters;
+        A.lr = cfg->lr64 > 0.0 ? cfg->lr64 : (double)cfg->lr;
+        A.b1 = (double)cfg->beta1; A.b2 = (double)cfg->beta2; A.eps = (double)cfg->adam_eps;
+        A.grad_scale = (double)cfg->grad_scale; A.flags = cfg->algo_flags; A.rows_counter = RRL_C_SAC_ROWS;
+        scalar_adam_kernel<<<1, 32, 0, st>>>(A);
+        RRL_CHECK_LAUNCH();
+    }
     bump_kernel<<<1, 32, 0, st>>>(counters, RRL_C_SAC_ROWS, RRL_C_ADAM_T0 + 0, RRL_C_ADAM_T0 + 1, RRL_C_SAC_UPDATES);
     RRL_CHECK_LAUNCH();
     return 0;
@@ -1331,7 +1516,8 @@ extern "C" int rrl_qrisk_backward(const rrl_agent_config_t* cfg, float* arena, c
         A.n_pass = 1; A.rows_ptr = rows_ptr; A.sp = sp; A.seed = seed; A.stream_id = (uint32_t)stream_id;
         A.counters = counters; A.step_counter = RRL_C_QRISK_UPDATES;
         FwdPass& p0 = A.p[0];
-        p0.w = head_w(L, arena, RRL_NET_POLICY, 0); p0.head = HEAD_GAUSS; p0.xs = s2; p0.eps = eps_next;
+        p0.w = task_policy_w(L, arena, cfg, &p0.head); p0.xs = s2; p0.eps = eps_next;
+        RRL_CHECK_ARG(p0.head != HEAD_DET || eps_next, "the Deterministic policy needs its noise as an input");
         p0.draw_id = RRL_DRAW_QR_NEXT; p0.out_a = R2(R2_QR_NEXT_A); p0.out_logp = RA(RA_QR_NEXT_LOGP);
         int rc = launch_forward<32>(A, R, st);
         if (rc) return rc;

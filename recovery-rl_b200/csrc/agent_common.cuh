@@ -5,7 +5,7 @@
 
 namespace rrl {
 
-enum Head { HEAD_Q = 0, HEAD_QRISK = 1, HEAD_GAUSS = 2, HEAD_STOCH = 3 };
+enum Head { HEAD_Q = 0, HEAD_QRISK = 1, HEAD_GAUSS = 2, HEAD_STOCH = 3, HEAD_DET = 4 };
 
 #define LOG_SIG_MAX 2.0f
 #define LOG_SIG_MIN (-20.0f)
@@ -46,6 +46,20 @@ inline HeadW head_w(const Layout& L, const float* arena, int net, int head) {
         w.n_in = 4; w.na = 1; w.nb = 0;
     }
     w.W2T = arena + L.img_off[image_index(net, head)];
+    return w;
+}
+// the task policy as configured: GaussianPolicy (two heads) or, with RRL_ALGO_DETERMINISTIC, DeterministicPolicy
+// (model.py:447-485): the mean head only (the arena keeps the Gaussian layout; the log_std head stays unused and
+// its gradients stay zero), action = tanh(mean)*scale + bias + noise, i.e. the StochasticPolicy arithmetic with a
+// constant log_std of 0 and the caller's pre-scaled noise.
+inline HeadW task_policy_w(const Layout& L, const float* arena, const rrl_agent_config_t* cfg, int* head_kind) {
+    HeadW w = head_w(L, arena, RRL_NET_POLICY, 0);
+    *head_kind = HEAD_GAUSS;
+    if (cfg->algo_flags & RRL_ALGO_DETERMINISTIC) {
+        w.nb = 0; w.W3b = nullptr; w.b3b = nullptr;
+        w.log_std = arena + L.scalars + RRL_S_F64_BASE + 2 * RRL_D_ZERO;
+        *head_kind = HEAD_DET;
+    }
     return w;
 }
 inline HeadG head_g(const Layout& L, float* arena, int net, int head) {

@@ -19,7 +19,7 @@ constexpr int H = 256;  // hidden width (arg_utils.py:89-92); all kernels are sp
 constexpr int kMaxTensors = 14;
 constexpr int kNumImages = 10;
 constexpr int kTcHeads = 4;    // policy, qrisk head 1, qrisk head 2, recovery (the nets the acting kernel runs)
-constexpr int kPassSlots = 5;  // activation slots shared by the SAC and Q_risk updates
+constexpr int kPassSlots = 7;  // activation slots shared by the SAC and Q_risk updates (5, 6: Q_risk(s, pi) of the DGD branch)
 
 struct TDesc {
     int rows, cols;  // cols == 0: 1-D tensor of `rows` elements
@@ -85,10 +85,11 @@ struct Layout {
     // scratch
     int64_t batch_off[2][5];               // [sac|qr][s,a,r,s2,m]
     int64_t h1[kPassSlots], h2[kPassSlots], dh2[kPassSlots], dh2t[kPassSlots], dh1[kPassSlots];
-    int64_t rows_f[32];                    // per-row float arrays of R (see names in agent.cu)
-    int64_t rows2_f[8];                    // per-row [R][2] arrays
+    int64_t rows_f[40];                    // per-row float arrays of R (see names in agent.cu)
+    int64_t rows2_f[12];                   // per-row [R][2] arrays
     int64_t rows4_f[4];                    // per-row [R][4] arrays
     int64_t losses;                        // 16 floats
+    int64_t scalars;                       // 32 floats, 8-byte aligned (RRL_S_* / RRL_D_* of rrl.h)
     int64_t total;
     Scratch names[96];
     int n_names;
@@ -121,9 +122,15 @@ inline int w2_tensor(int net, int head) {
 enum RowArr {
     RA_NEXT_LOGP = 0, RA_LOGP, RA_QT1, RA_QT2, RA_QF1, RA_QF2, RA_QP1, RA_QP2, RA_TARGET, RA_DQF1, RA_DQF2, RA_DQP1,
     RA_DQP2, RA_MINQ, RA_QR_QT1, RA_QR_QT2, RA_QR_Q1, RA_QR_Q2, RA_QR_TARGET, RA_QR_DQ1, RA_QR_DQ2, RA_QR_NEXT_LOGP,
-    RA_REC_Q1, RA_REC_Q2, RA_REC_DQ1, RA_REC_DQ2, RA_REC_LOGP, RA_COUNT
+    RA_REC_Q1, RA_REC_Q2, RA_REC_DQ1, RA_REC_DQ2, RA_REC_LOGP,
+    RA_SQ1, RA_SQ2, RA_DSQ1, RA_DSQ2,  // Q_risk(s, pi) of the DGD / update_nu branch (sac.py:221-228) and d/d(raw)
+    RA_QS1, RA_QS2,                    // Q_risk(s, a) of the RCPO branch (sac.py:202-205)
+    RA_COUNT
 };
-enum Row2Arr { R2_NEXT_A = 0, R2_PI, R2_EPS_CUR, R2_DPI, R2_QR_NEXT_A, R2_REC_PI, R2_REC_EPS, R2_REC_DPI, R2_COUNT };
+static_assert(RA_COUNT <= 40, "rows_f too small");
+enum Row2Arr { R2_NEXT_A = 0, R2_PI, R2_EPS_CUR, R2_DPI, R2_QR_NEXT_A, R2_REC_PI, R2_REC_EPS, R2_REC_DPI, R2_DPI_B, R2_DPI_S1,
+               R2_DPI_S2, R2_COUNT };
+static_assert(R2_COUNT <= 12, "rows2_f too small");
 enum Row4Arr { R4_RAW_POL = 0, R4_DRAW_POL, R4_RAW_REC, R4_DRAW_REC, R4_COUNT };
 
 inline void add_name(Layout& L, const char* name, int64_t off, int64_t count) {
@@ -181,13 +188,15 @@ inline Layout make_layout(const rrl_agent_config_t* cfg) {
     }
     static const char* ra[RA_COUNT] = {"next_logp", "logp", "qt1", "qt2", "qf1", "qf2", "qp1", "qp2", "target", "dqf1", "dqf2",
                                        "dqp1", "dqp2", "minq", "qr_qt1", "qr_qt2", "qr_q1", "qr_q2", "qr_target", "qr_dq1",
-                                       "qr_dq2", "qr_next_logp", "rec_q1", "rec_q2", "rec_dq1", "rec_dq2", "rec_logp"};
+                                       "qr_dq2", "qr_next_logp", "rec_q1", "rec_q2", "rec_dq1", "rec_dq2", "rec_logp",
+                                       "sq1", "sq2", "dsq1", "dsq2", "qs1", "qs2"};
     for (int i = 0; i < RA_COUNT; ++i) {
         L.rows_f[i] = off;
         add_name(L, ra[i], off, R);
         off += pad4(R);
     }
-    static const char* r2[R2_COUNT] = {"next_a", "pi", "eps_cur", "dpi", "qr_next_a", "rec_pi", "rec_eps", "rec_dpi"};
+    static const char* r2[R2_COUNT] = {"next_a", "pi", "eps_cur", "dpi", "qr_next_a", "rec_pi", "rec_eps", "rec_dpi", "dpi_b",
+                                       "dpi_s1", "dpi_s2"};
     for (int i = 0; i < R2_COUNT; ++i) {
         L.rows2_f[i] = off;
         add_name(L, r2[i], off, 2 * R);
@@ -202,6 +211,10 @@ inline Layout make_layout(const rrl_agent_config_t* cfg) {
     L.losses = off;
     add_name(L, "losses", off, 16);
     off += 16;
+    off = (off + 1) & ~(int64_t)1;  // 8-byte alignment for the float64 slots
+    L.scalars = off;
+    add_name(L, "scalars", off, 32);
+    off += 32;
     L.total = off;
     return L;
 }

@@ -27,6 +27,7 @@ class AgentArena(object):
         self.counters = torch.zeros(native.NUM_COUNTERS, dtype=torch.int64, device=self.device)
         self._views = {}
         self.grad_off, self.grad_count = native.agent_grad_range(self.cfg, -1)
+        native.agent_init_scalars(self.cfg, self.arena)       # alpha / nu / lambda and their logs (sac.py:48,56-72,99-101)
 
     # ---- views ---------------------------------------------------------------------------------
     def tensor(self, net, i):
@@ -77,6 +78,16 @@ class AgentArena(object):
             self._views[name] = self.arena[off:off + cnt]
         v = self._views[name]
         return v.view(-1, width) if width else v
+
+    # ---- scalar multipliers of the comparison branches (sac.py:56-72, 95-101) --------------------------
+    def scalars(self):
+        """(float32 view, float64 view) of the scalar block: indices native.S_* / native.D_*."""
+        v = self.scratch("scalars")
+        return v, v[native.S_F64_BASE:].view(torch.float64)
+
+    def set_nu_arg(self, nu):
+        """the `nu` argument of SAC.update_parameters (experiment.py:406: nu_schedule(i_episode))."""
+        self.scratch("scalars")[native.S_NU_ARG] = float(nu)
 
     def flat_grads(self):
         """the contiguous gradient block [critic | policy | qrisk | recovery] (NCCL all-reduce payload)."""

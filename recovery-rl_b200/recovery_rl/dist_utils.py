@@ -27,6 +27,12 @@ def all_reduce_grads(arena, ranges, names, group=None):
     dist.all_reduce(arena[lo:hi], op=dist.ReduceOp.SUM, group=group)
 
 
+def all_reduce_sum(view, group=None):
+    """in-place SUM of a small contiguous view (the scalar-multiplier gradients of the comparison branches)."""
+    import torch.distributed as dist
+    dist.all_reduce(view, op=dist.ReduceOp.SUM, group=group)
+
+
 def sync_gate_counts(counters, group=None):
     """The Q_risk online gate (experiment.py:407-410) must open on every rank in the same step, so each rank adds
     the violations seen elsewhere: EXT_VIOLS = sum over other ranks of (num_viols + offline_viols)."""

@@ -30,7 +30,8 @@ class VecEngine(object):
                  target_update_interval=1, use_recovery=True, mf_recovery=True, pos_fraction=-1.0,
                  disable_online_updates=False, constraint_reward_penalty=0.0, start_steps=100, seed=0,
                  device="cuda:0", rank=0, world_size=1, process_group=None, host_inputs=False, log_outputs=False,
-                 use_tensor_cores=0, maze_substeps=500):
+                 use_tensor_cores=0, maze_substeps=500, dgd=False, update_nu=False, rcpo=False, auto_alpha=False,
+                 nu=0.01, lambda_rcpo=0.01):
         native.require_cuda()
         self.device = torch.device(device)
         torch.cuda.set_device(self.device)
@@ -43,7 +44,11 @@ class VecEngine(object):
         self.seed = int(seed)
         self.use_recovery = bool(use_recovery)
         self.mf_recovery = bool(mf_recovery)
-        self.online_qrisk = self.use_recovery and not disable_online_updates
+        # the safety critic is trained (and the constraint buffer filled) for Recovery RL and for the LR / RSPO /
+        # SQRL / RCPO comparisons (experiment.py:407-415, 443-445)
+        self.uses_qrisk = self.use_recovery or bool(dgd) or bool(rcpo)
+        self.online_qrisk = self.uses_qrisk and not disable_online_updates
+        self.scalar_algos = bool(update_nu) or bool(rcpo) or bool(auto_alpha)
         self.gate_pos_fraction = float(pos_fraction)                          # experiment.py:410
         self.pos_fraction = pos_fraction if pos_fraction >= 0 else None        # qrisk.py:77
         self.start_steps = int(start_steps)
@@ -54,7 +59,8 @@ class VecEngine(object):
                                 gamma_safe=gamma_safe, tau_safe=tau_safe, eps_safe=eps_safe,
                                 target_update_interval=target_update_interval, mf_recovery=mf_recovery,
                                 action_scale=(sc, sc), grad_scale=1.0 / self.world,
-                                use_tensor_cores=use_tensor_cores)
+                                use_tensor_cores=use_tensor_cores, dgd=dgd, update_nu=update_nu, rcpo=rcpo,
+                                auto_alpha=auto_alpha, nu=nu, lambda_rcpo=lambda_rcpo)
         self.cfg = self.agent.cfg
         self.arena = self.agent.arena
         self.counters = self.agent.counters
@@ -139,6 +145,10 @@ class VecEngine(object):
             modules = build_reference_modules(hidden=256, action_scale=(sc, sc))
         self.agent.load_modules(modules)
 
+    def set_nu(self, nu):
+        """the `nu` argument of SAC.update_parameters (experiment.py:406); a device scalar the captured graph reads."""
+        self.agent.set_nu_arg(nu)
+
     def reset(self, draws=None):
         """env.reset() for every env copy (experiment.py:383)."""
         native.env_reset(self.env_cfg, self.state, self.ep_steps, self.ep_return, self.counters, draws=draws)
@@ -207,8 +217,12 @@ class VecEngine(object):
         native.sac_backward(cfg, ar, cn, self.losses, self._in("sac_eps_next"), self._in("sac_eps_cur"), seed=self.seed,
                             stream_id=self.rank)
         self._all_reduce(["critic", "policy"])
+        if self.world > 1 and self.scalar_algos:      # gradients of log_alpha (f32) and log_nu / log_lambda (f64)
+            f32, f64 = self.agent.scalars()
+            dist_utils.all_reduce_sum(f32[native.S_G_LOG_ALPHA:native.S_G_LOG_ALPHA + 1], self.pg)
+            dist_utils.all_reduce_sum(f64[native.D_G_LOG_NU:native.D_G_LOG_LAMBDA + 1], self.pg)
         native.sac_apply(cfg, ar, cn)
-        return 10 + 3
+        return 10 + 3 + (1 if self.scalar_algos else 0)
 
     def sac_update(self):
         return self._sac_sample() + self._sac_compute()
@@ -249,12 +263,12 @@ class VecEngine(object):
         native.env_step(self.env_cfg, self.action_task, self.action_real, self.state, self.ep_steps, self.ep_return,
                         self.counters, recovery=self.recovery, noise=self._in("env_noise"),
                         reset_draws=self._in("reset_draws"), task_ring=self.task_ring, task_capacity=self.task_cap,
-                        cons_ring=self.cons_ring if self.use_recovery else None,
-                        cons_flags=self.cons_flags if self.use_recovery else None,
-                        cons_capacity=self.cons_cap if self.use_recovery else 0, out_next_state=self.out_next,
+                        cons_ring=self.cons_ring if self.uses_qrisk else None,
+                        cons_flags=self.cons_flags if self.uses_qrisk else None,
+                        cons_capacity=self.cons_cap if self.uses_qrisk else 0, out_next_state=self.out_next,
                         out_reward=self.out_reward, out_done=self.out_done, out_constraint=self.out_cons,
                         out_success=self.out_succ)                                 # experiment.py:420-461
-        native.counters_advance(self.counters, self.n, self.task_cap, self.cons_cap, True, self.use_recovery)
+        native.counters_advance(self.counters, self.n, self.task_cap, self.cons_cap, True, self.uses_qrisk)
         self.launches_per_step = k + 3
         return self.launches_per_step
 

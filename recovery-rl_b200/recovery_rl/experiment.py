@@ -102,6 +102,9 @@ class Experiment:
                 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
             pg = dist.group.WORLD
         dev = torch.device("cuda", torch.cuda.current_device())
+        if c.use_constraint_sampling or c.policy != "Gaussian" or (c.use_recovery and c.Q_sampling_recovery):
+            raise NotImplementedError("--use_constraint_sampling (SQRL), --policy Deterministic and --Q_sampling_recovery "
+                                      "run on the --num_envs 1 path only")
         eng = VecEngine(c.env_name, self.num_envs, batch_size=c.batch_size, replay_size=c.replay_size,
                         safe_replay_size=c.safe_replay_size, gamma=c.gamma, alpha=c.alpha, tau=c.tau, lr=c.lr,
                         gamma_safe=c.gamma_safe, tau_safe=c.tau_safe, eps_safe=c.eps_safe,
@@ -110,7 +113,9 @@ class Experiment:
                         disable_online_updates=c.disable_online_updates,
                         constraint_reward_penalty=c.constraint_reward_penalty, start_steps=c.start_steps, seed=c.seed,
                         device=dev, rank=rank, world_size=world, process_group=pg,
-                        log_outputs=getattr(c, "log_envs", 1) > 0, use_tensor_cores=getattr(c, "tensor_cores", 1))
+                        log_outputs=getattr(c, "log_envs", 1) > 0, use_tensor_cores=getattr(c, "tensor_cores", 1),
+                        dgd=c.DGD_constraints, update_nu=c.update_nu, rcpo=c.RCPO,
+                        auto_alpha=bool(c.automatic_entropy_tuning), nu=c.nu, lambda_rcpo=c.lambda_RCPO)
         eng.init_agent()          # same torch seed on every rank -> identical replicas
         return eng
 
@@ -313,6 +318,7 @@ class Experiment:
                 self.num_viols, self.num_successes = cn["num_viols"], cn["num_successes"]
                 self.viol_and_recovery, self.viol_and_no_recovery = cn["viol_and_recovery"], cn["viol_and_no_recovery"]
                 self.updates = cn["sac_updates"]
+                eng.set_nu(self.nu_schedule(1 + cn["episodes"] * eng.world))     # experiment.py:406
                 if True:
                     vec_stats.append(cn)
                     if eng.rank == 0:

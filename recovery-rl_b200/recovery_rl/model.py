@@ -53,6 +53,22 @@ class GaussianPolicy(nn.Module):
         self.apply(weights_init_)
 
 
+class DeterministicPolicy(nn.Module):
+    """model.py:447-485 (`--policy Deterministic`): three Linear layers; the arena keeps the Gaussian layout with
+    the log_std head unused, so the parameter list is padded with two zero tensors for the loader."""
+
+    def __init__(self, num_inputs, num_actions, hidden_dim, action_space=None):
+        super().__init__()
+        self.linear1 = nn.Linear(num_inputs, hidden_dim)
+        self.linear2 = nn.Linear(hidden_dim, hidden_dim)
+        self.mean = nn.Linear(hidden_dim, num_actions)
+        self.apply(weights_init_)
+        self._pad = [torch.zeros(num_actions, hidden_dim), torch.zeros(num_actions)]
+
+    def parameters(self, recurse=True):
+        return list(super().parameters(recurse)) + self._pad
+
+
 class StochasticPolicy(nn.Module):
     def __init__(self, num_inputs, num_actions, hidden_dim, action_space=None):
         super().__init__()
@@ -64,13 +80,13 @@ class StochasticPolicy(nn.Module):
         self.apply(weights_init_)
 
 
-def build_reference_modules(hidden=256, action_scale=(1.0, 1.0), obs_dim=2, act_dim=2):
+def build_reference_modules(hidden=256, action_scale=(1.0, 1.0), obs_dim=2, act_dim=2, deterministic=False):
     """{net name: module}, constructed in the reference's order: critic, critic_target, policy (sac.py:82-114),
     then safety_critic, safety_critic_target, recovery policy (qrisk.py:36-75).  Targets are hard copies."""
     critic = QNetwork(obs_dim, act_dim, hidden)
     critic_target = QNetwork(obs_dim, act_dim, hidden)
     critic_target.load_state_dict(critic.state_dict())
-    policy = GaussianPolicy(obs_dim, act_dim, hidden)
+    policy = (DeterministicPolicy if deterministic else GaussianPolicy)(obs_dim, act_dim, hidden)
     qrisk = QNetworkConstraint(obs_dim, act_dim, hidden)
     qrisk_target = QNetworkConstraint(obs_dim, act_dim, hidden)
     qrisk_target.load_state_dict(qrisk.state_dict())

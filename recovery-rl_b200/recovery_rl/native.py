@@ -21,6 +21,11 @@ C_TOTAL_NUMSTEPS, C_EPISODES, C_NUM_VIOLS, C_NUM_SUCCESSES, C_VIOL_RECOVERY, C_V
 C_OFFLINE_VIOLS, C_VEC_STEP, C_SAC_UPDATES, C_QRISK_UPDATES = 6, 7, 8, 9
 C_TASK_POS, C_TASK_LEN, C_CONS_POS, C_CONS_LEN, C_SAC_ROWS, C_QRISK_ROWS, C_ADAM_T0 = 10, 11, 12, 13, 14, 15, 16
 C_EXT_VIOLS, C_RETURN_SUM_BITS, C_ERROR, NUM_COUNTERS = 20, 21, 22, 32
+C_ADAM_T_ALPHA, C_ADAM_T_NU, C_ADAM_T_LAMBDA = 23, 24, 25
+# comparison-algorithm branches (rrl_agent_config_t.algo_flags) and the scalar block ("scalars" scratch region)
+ALGO_DGD, ALGO_UPDATE_NU, ALGO_RCPO, ALGO_AUTO_ALPHA, ALGO_DETERMINISTIC = 1, 2, 4, 8, 16
+S_ALPHA, S_NU_ARG, S_LOG_ALPHA, S_G_LOG_ALPHA, S_M_ALPHA, S_V_ALPHA, S_ALPHA_LOSS, S_F64_BASE = 0, 1, 2, 3, 4, 5, 6, 8
+D_G_LOG_NU, D_G_LOG_LAMBDA, D_LOG_NU, D_M_NU, D_V_NU, D_LOG_LAMBDA, D_M_LAMBDA, D_V_LAMBDA, D_LAMBDA, D_NU_LEARNED = range(10)
 
 NET_CRITIC, NET_CRITIC_TARGET, NET_POLICY, NET_QRISK, NET_QRISK_TARGET, NET_RECOVERY = range(6)
 NUM_NETS = 6
@@ -46,7 +51,9 @@ class AgentConfig(C.Structure):
                 ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("adam_eps", C.c_float),
                 ("action_scale", C.c_float * 2), ("action_bias", C.c_float * 2),
                 ("target_update_interval", C.c_int32), ("mf_recovery", C.c_int32),
-                ("grad_scale", C.c_float), ("use_tensor_cores", C.c_int32)]
+                ("grad_scale", C.c_float), ("use_tensor_cores", C.c_int32),
+                ("algo_flags", C.c_int32), ("target_entropy", C.c_float), ("nu", C.c_double), ("lambda_rcpo", C.c_double),
+                ("lr64", C.c_double)]
 
 
 class RRLError(RuntimeError):
@@ -188,7 +195,8 @@ def replay_sample(cfg, ring, mt_state, counters, rows_counter, out_s, out_a, out
 # ------------------------------------------------------------------------------------------------
 def agent_config(hidden=256, max_batch=256, gamma=0.99, alpha=0.2, tau=0.005, gamma_safe=0.5, tau_safe=0.0002,
                  eps_safe=0.1, lr=3e-4, action_scale=(1.0, 1.0), action_bias=(0.0, 0.0), target_update_interval=1,
-                 mf_recovery=True, grad_scale=1.0, use_tensor_cores=0):
+                 mf_recovery=True, grad_scale=1.0, use_tensor_cores=0, dgd=False, update_nu=False, rcpo=False,
+                 auto_alpha=False, deterministic=False, nu=0.01, lambda_rcpo=0.01, target_entropy=-2.0):
     c = AgentConfig()
     c.hidden, c.max_batch = hidden, max_batch
     c.gamma, c.alpha, c.tau = gamma, alpha, tau
@@ -200,6 +208,10 @@ def agent_config(hidden=256, max_batch=256, gamma=0.99, alpha=0.2, tau=0.005, ga
     c.mf_recovery = int(bool(mf_recovery))
     c.grad_scale = grad_scale
     c.use_tensor_cores = int(use_tensor_cores)
+    c.algo_flags = (ALGO_DGD * bool(dgd) | ALGO_UPDATE_NU * bool(update_nu) | ALGO_RCPO * bool(rcpo) |
+                    ALGO_AUTO_ALPHA * (bool(auto_alpha) and not deterministic) | ALGO_DETERMINISTIC * bool(deterministic))
+    c.target_entropy = float(target_entropy)
+    c.nu, c.lambda_rcpo, c.lr64 = float(nu), float(lambda_rcpo), float(lr)
     return c
 
 
@@ -229,6 +241,10 @@ def agent_scratch_info(cfg, name):
     _check(lib().rrl_agent_scratch_info(C.byref(cfg), name.encode(), C.byref(off), C.byref(cnt)),
            "rrl_agent_scratch_info(%s)" % name)
     return off.value, cnt.value
+
+
+def agent_init_scalars(cfg, arena, stream=None):
+    _check(lib().rrl_agent_init_scalars(C.byref(cfg), p(arena, "f32"), _stream(stream)), "rrl_agent_init_scalars")
 
 
 def agent_refresh(cfg, arena, stream=None):

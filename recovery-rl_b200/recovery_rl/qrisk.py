@@ -38,7 +38,13 @@ class QRiskWrapper(object):
             batch_size = min(batch_size, len(memory))
         ar = self.arena
         memory.sample_into(ar, "qr", batch_size, pos_fraction=self.pos_fraction)
-        eps_next = torch.randn(batch_size, 2).to(self.device)
+        # a' ~ policy.sample(next_state_batch): the TASK policy's own noise (Normal.rsample, or the broadcast
+        # noise vector of DeterministicPolicy.sample)
+        if ar.cfg.algo_flags & native.ALGO_DETERMINISTIC:
+            eps_next = torch.Tensor(2).normal_(0., std=0.1).clamp(-0.25, 0.25).unsqueeze(0).repeat(batch_size, 1) \
+                .contiguous().to(self.device)
+        else:
+            eps_next = torch.randn(batch_size, 2).to(self.device)
         ar.counters[native.C_QRISK_UPDATES] = int(self.updates)
         native.qrisk_backward(ar.cfg, ar.arena, ar.counters, self._losses, eps_next)
         native.qrisk_apply(ar.cfg, ar.arena, ar.counters)
