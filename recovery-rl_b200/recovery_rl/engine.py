@@ -31,7 +31,7 @@ class VecEngine(object):
                  disable_online_updates=False, constraint_reward_penalty=0.0, start_steps=100, seed=0,
                  device="cuda:0", rank=0, world_size=1, process_group=None, host_inputs=False, log_outputs=False,
                  use_tensor_cores=0, maze_substeps=500, dgd=False, update_nu=False, rcpo=False, auto_alpha=False,
-                 nu=0.01, lambda_rcpo=0.01):
+                 nu=0.01, lambda_rcpo=0.01, disable_action_relabeling=False):
         native.require_cuda()
         self.device = torch.device(device)
         torch.cuda.set_device(self.device)
@@ -52,6 +52,7 @@ class VecEngine(object):
         self.gate_pos_fraction = float(pos_fraction)                          # experiment.py:410
         self.pos_fraction = pos_fraction if pos_fraction >= 0 else None        # qrisk.py:77
         self.start_steps = int(start_steps)
+        self.relabel = not disable_action_relabeling            # experiment.py:438-441
         self.host_inputs = bool(host_inputs)
         self.log_outputs = bool(log_outputs) or self.host_inputs
         sc = ACTION_SCALE[env_name]
@@ -260,7 +261,8 @@ class VecEngine(object):
                          self.recovery, self.qrisk, self._in("eps_task"), self._in("eps_rec"), self._in("rand_u"),
                          use_recovery=self.use_recovery, start_steps=self.start_steps, seed=self.seed,
                          stream_id=self.rank)                                      # experiment.py:419
-        native.env_step(self.env_cfg, self.action_task, self.action_real, self.state, self.ep_steps, self.ep_return,
+        native.env_step(self.env_cfg, self.action_task if self.relabel else self.action_real, self.action_real,
+                        self.state, self.ep_steps, self.ep_return,
                         self.counters, recovery=self.recovery, noise=self._in("env_noise"),
                         reset_draws=self._in("reset_draws"), task_ring=self.task_ring, task_capacity=self.task_cap,
                         cons_ring=self.cons_ring if self.uses_qrisk else None,

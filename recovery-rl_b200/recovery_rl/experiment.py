@@ -105,6 +105,9 @@ class Experiment:
         if c.use_constraint_sampling or c.policy != "Gaussian" or (c.use_recovery and c.Q_sampling_recovery):
             raise NotImplementedError("--use_constraint_sampling (SQRL), --policy Deterministic and --Q_sampling_recovery "
                                       "run on the --num_envs 1 path only")
+        if c.add_both_transitions:
+            raise NotImplementedError("--add_both_transitions (a data-dependent number of pushes per step) runs on the "
+                                      "--num_envs 1 path only")
         eng = VecEngine(c.env_name, self.num_envs, batch_size=c.batch_size, replay_size=c.replay_size,
                         safe_replay_size=c.safe_replay_size, gamma=c.gamma, alpha=c.alpha, tau=c.tau, lr=c.lr,
                         gamma_safe=c.gamma_safe, tau_safe=c.tau_safe, eps_safe=c.eps_safe,
@@ -115,7 +118,8 @@ class Experiment:
                         device=dev, rank=rank, world_size=world, process_group=pg,
                         log_outputs=getattr(c, "log_envs", 1) > 0, use_tensor_cores=getattr(c, "tensor_cores", 1),
                         dgd=c.DGD_constraints, update_nu=c.update_nu, rcpo=c.RCPO,
-                        auto_alpha=bool(c.automatic_entropy_tuning), nu=c.nu, lambda_rcpo=c.lambda_RCPO)
+                        auto_alpha=bool(c.automatic_entropy_tuning), nu=c.nu, lambda_rcpo=c.lambda_RCPO,
+                        disable_action_relabeling=c.disable_action_relabeling)
         eng.init_agent()          # same torch seed on every rank -> identical replicas
         return eng
 

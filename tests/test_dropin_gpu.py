@@ -121,3 +121,54 @@ def test_vectorised_experiment_runs(native, cuda, tmp_path):
     assert stats[-1]["total_numsteps"] > 60000 and stats[-1]["error"] == 0
     assert stats[-1]["sac_updates"] > 40 and stats[-1]["qrisk_updates"] > 40
     assert os.path.exists(os.path.join(exp.logdir, "run_stats.pkl")) and os.path.exists(os.path.join(exp.logdir, "args.pkl"))
+
+
+# the algorithm lines of the reference's scripts/navigation1.sh / maze.sh (flags verbatim, incl. the `--lambda`
+# prefix abbreviation of --lambda_RCPO); the model-based RRL_MB line is outside this build
+SCRIPT_LINES = {
+    "RRL_MF": ["--use_recovery", "--MF_recovery"],
+    "unconstrained": [],
+    "LR": ["--DGD_constraints", "--nu", "5000", "--update_nu"],
+    "RSPO": ["--DGD_constraints", "--nu_schedule", "--nu_start", "10000"],
+    "SQRL": ["--DGD_constraints", "--use_constraint_sampling", "--nu", "5000", "--update_nu"],
+    "RP": ["--constraint_reward_penalty", "1000"],
+    "RCPO": ["--RCPO", "--lambda", "1000"],
+}
+
+
+@pytest.mark.parametrize("algo", sorted(SCRIPT_LINES))
+@pytest.mark.parametrize("env_name", ["navigation1", "maze"])
+def test_script_algorithm_lines_run(native, cuda, tmp_path, algo, env_name):
+    """every algorithm of the shipped scripts runs through rrl_main's surface on the CUDA path (N = 1 loop)."""
+    import arg_utils
+    from recovery_rl.experiment import Experiment
+    extra = ["--gamma_safe", "0.8", "--eps_safe", "0.3"] if env_name == "navigation1" else \
+        ["--gamma_safe", "0.5", "--eps_safe", "0.15", "--pos_fraction=0.3"]
+    argv = ["--cuda", "--env-name", env_name] + SCRIPT_LINES[algo] + (extra if algo not in ("unconstrained", "RP") else []) + \
+        ["--logdir", str(tmp_path), "--logdir_suffix", algo, "--num_eps", "3", "--num_unsafe_transitions", "600",
+         "--critic_safe_pretraining_steps", "10", "--batch_size", "16", "--seed", "2"]
+    exp = Experiment(arg_utils.get_args(argv))
+    exp.run()
+    assert exp.total_numsteps > 3 and exp.updates > 0
+    l = exp.agent._losses[:3].cpu().numpy()
+    assert np.isfinite(l).all()
+    if algo in ("LR", "SQRL"):
+        assert exp.agent.arena.counters[native.C_ADAM_T_NU].item() == exp.updates
+    if algo == "RCPO":
+        assert exp.agent.arena.counters[native.C_ADAM_T_LAMBDA].item() == exp.updates and exp.agent.lambda_RCPO != 1000
+
+
+@pytest.mark.parametrize("algo", ["LR", "RSPO", "RCPO", "RP", "unconstrained"])
+def test_vectorised_comparison_algorithms_run(native, cuda, tmp_path, algo):
+    import arg_utils
+    from recovery_rl.experiment import Experiment
+    argv = ["--env-name", "navigation1", "--gamma_safe", "0.8", "--eps_safe", "0.3"] + SCRIPT_LINES[algo] + \
+        ["--num_unsafe_transitions", "2000", "--critic_safe_pretraining_steps", "20", "--batch_size", "64",
+         "--num_envs", "512", "--num_steps", "30000", "--seed", "3", "--logdir", str(tmp_path), "--replay_size", "60000",
+         "--safe_replay_size", "60000"]
+    exp = Experiment(arg_utils.get_args(argv))
+    stats = exp.run()
+    assert stats[-1]["total_numsteps"] > 30000 and stats[-1]["error"] == 0 and stats[-1]["sac_updates"] > 20
+    uses_qrisk = algo in ("LR", "RSPO", "RCPO")
+    assert (stats[-1]["qrisk_updates"] > 20) == uses_qrisk
+    assert torch.isfinite(exp.engine.arena[:exp.engine.agent.grad_off]).all()
