@@ -7,6 +7,7 @@ unmodified scripts can be vectorised):
   --num_envs N      env copies stepped per vector step on each GPU     (RRL_NUM_ENVS, default 1)
   --tensor_cores b  run the acting 256x256 contractions on tcgen05     (RRL_TENSOR_CORES, default 1)
   --log_envs k      env copies whose per-step info is logged at N > 1  (RRL_LOG_ENVS, default 1)
+  --checkpoint_every k / --resume path   agent (+ engine) checkpoints in the logdir (recovery_rl/checkpoint.py)
 """
 import argparse
 import os
@@ -80,4 +81,7 @@ def get_args(argv=None):
     parser.add_argument('--num_envs', type=int, default=int(os.environ.get('RRL_NUM_ENVS', '1')))
     parser.add_argument('--tensor_cores', type=int, default=int(os.environ.get('RRL_TENSOR_CORES', '1')))
     parser.add_argument('--log_envs', type=int, default=int(os.environ.get('RRL_LOG_ENVS', '1')))
+    parser.add_argument('--checkpoint_every', type=int, default=0,
+                        help='write <logdir>/checkpoint.pt every k episodes (k reports at --num_envs > 1); 0 = off')
+    parser.add_argument('--resume', default='', help='checkpoint to load before training')
     return parser.parse_args(argv)

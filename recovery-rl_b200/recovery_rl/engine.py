@@ -344,6 +344,15 @@ class VecEngine(object):
         self.ep_steps.copy_(s["ep_steps"]); self.ep_return.copy_(s["ep_return"]); self.mt_state.copy_(s["mt"])
         self.cons_flags.copy_(s["flags"])
 
+    def save(self, path):
+        """checkpoint (networks with the reference's state_dict names, Adam, multipliers, replay, sampler, env state)."""
+        from . import checkpoint
+        return checkpoint.save(path, self)
+
+    def load(self, path):
+        from . import checkpoint
+        return checkpoint.load(path, self)
+
     def read_counters(self):
         c = self.counters.cpu().numpy()
         names = dict(total_numsteps=native.C_TOTAL_NUMSTEPS, episodes=native.C_EPISODES, num_viols=native.C_NUM_VIOLS,

@@ -163,12 +163,18 @@ class Experiment:
         if not self.exp_cfg.disable_offline_updates and (self.exp_cfg.use_recovery or self.exp_cfg.DGD_constraints
                                                           or self.exp_cfg.RCPO):
             self.pretrain_critic_recovery()
+        resume = getattr(self.exp_cfg, "resume", "")
         if self.engine is not None:
             return self.run_vectorised()
+        if resume:
+            self.agent.load(resume)
         train_rollouts = []
         test_rollouts = []
+        ck = int(getattr(self.exp_cfg, "checkpoint_every", 0))
         for i_episode in itertools.count(1):
             train_rollouts.append(self.get_train_rollout(i_episode))
+            if ck and i_episode % ck == 0:
+                self.agent.save(osp.join(self.logdir, "checkpoint.pt"))
             if i_episode % 10 == 0 and self.exp_cfg.eval:
                 test_rollouts.append(self.get_test_rollout(i_episode))
             if self.total_numsteps > self.exp_cfg.num_steps or i_episode > self.exp_cfg.num_eps:
@@ -290,6 +296,8 @@ class Experiment:
         eng = self.engine
         c = self.exp_cfg
         eng.reset()
+        if getattr(c, "resume", ""):
+            eng.load(c.resume)             # env state, replay, sampler and counters continue where the checkpoint stopped
         eng.capture()
         k = min(max(int(getattr(c, "log_envs", 1)), 0), eng.n)
         train_rollouts, open_eps, vec_stats = [], [[] for _ in range(k)], []
@@ -331,6 +339,9 @@ class Experiment:
                     data = {"test_stats": [], "train_stats": train_rollouts, "vec_stats": vec_stats}
                     with open(osp.join(self.logdir, "run_stats.pkl"), "wb") as f:
                         pickle.dump(data, f)
+                ck = int(getattr(c, "checkpoint_every", 0))
+                if ck and (step // report_every) % ck == 0 and eng.rank == 0:
+                    eng.save(osp.join(self.logdir, "checkpoint.pt"))
                 if cn["total_numsteps"] * eng.world > c.num_steps or cn["episodes"] * eng.world > c.num_eps:
                     break
         return vec_stats

@@ -80,6 +80,15 @@ class SAC(object):
         self._a_real = torch.zeros(n, 2, device=self.device)
         self._losses = torch.zeros(16, device=self.device)
 
+    def save(self, path):
+        """state_dict-compatible checkpoint of the six networks + Adam state + multipliers (recovery_rl/checkpoint.py)."""
+        from . import checkpoint
+        return checkpoint.save(path, self.arena)
+
+    def load(self, path):
+        from . import checkpoint
+        return checkpoint.load(path, self.arena)
+
     def _policy_noise(self, rows):
         """the draw of policy.sample for `rows` rows, from the torch global (CPU) generator like the reference:
         Normal.rsample -> randn [rows, 2] (model.py:329); DeterministicPolicy: ONE N(0, 0.1) vector clamped to
