@@ -17,6 +17,8 @@ struct EnvParams {
     double c_a, c_b, h, gear;
     double plane_lo, plane_hi;  // x <= plane_lo  <=>  fl(x - R) <= -0.3 ;  x >= plane_hi  <=>  fl(x + R) >= 0.3
     double wx0[4], wx1[4], wy0[4], wy1[4];  // 1A, 1B, 2A, 2B rectangles
+    float f_wx0[4], f_wx1[4], f_wy0[4], f_wy1[4];  // fp32 copies for the conservative pre-test (maze_may_touch)
+    float f_plane_lo, f_plane_hi, f_rm, f_rm2;
 };
 
 // ---- obstacle.py:13-15, 44-45 : closed-interval rectangles ---------------------------------
@@ -40,7 +42,7 @@ __device__ __forceinline__ bool nav_obstacle(int kind, double x, double y) {
 //     other three planes -> four compares, no arithmetic;
 //   * dx >= R  =>  fl(dx*dx) >= fl(R*R)  =>  fl(dx*dx + dy*dy) >= fl(R*R): no touch, so dy is only needed
 //     inside the wall's x band; walls 1A/1B and 2A/2B share their x range;
-//   * tests that provably fail are skipped altogether (clearance argument in env_step_kernel).
+//   * tests that provably fail are skipped altogether (speculative chunks, see maze_substeps_warp).
 #define MAZE_R 0.025
 __device__ __forceinline__ bool maze_rect_touch_y(double dx, double y, double y0, double y1) {
     double dy = fmax(fmax(__dsub_rn(y0, y), 0.0), __dsub_rn(y, y1));
@@ -57,74 +59,76 @@ __device__ __forceinline__ bool maze_touch(const EnvParams& P, double x, double 
     return hit;
 }
 // 500 substeps for one warp of envs.  Per-substep semantics (oracle/envs.py): contact test on the
-// pre-integration position, then one semi-implicit Euler substep; contact freezes the disc.  Tests whose outcome
-// is provably "no contact" are skipped: a coordinate moves at most dmax per substep (|v| <= nsub * |fb| since
-// c_a < 1), the max-norm clearance to every solid is 1-Lipschitz in each coordinate, and a disc with clearance
-// > R + 1e-9 cannot satisfy any of the exact tests -- so after measuring the clearance once, the largest j with
-// j*h*(vmax + j*fbmax) <= clearance - R substeps run test-free.  The trip counts are made WARP-UNIFORM (min over the
-// lanes) so the 32 envs of a warp advance in lockstep instead of serialising their different schedules.
+// pre-integration position, then one semi-implicit Euler substep; contact freezes the disc.
+//
+// Speculative chunks: v starts at 0 and v <- c_a*v + fb keeps the sign of fb, so every coordinate moves
+// MONOTONICALLY during one env step (rounding is monotone).  The positions tested inside a chunk of MAZE_CHUNK
+// substeps therefore lie in the box spanned by the chunk's first and last position.  A chunk is integrated
+// test-free; only if that box comes within R + 2e-6 of a solid (maze_may_touch) the lane rewinds and replays the
+// chunk with the exact per-substep test.  A lane replays the chunk in which it touches (plus, rarely, chunks
+// spent within 2e-6 of a solid without touching), so all 32 envs of a warp run the same 500-substep schedule
+// instead of serialising divergent test paths.
+constexpr int MAZE_CHUNK = 10;
+// Conservative pre-test in fp32 (FMA/ALU pipes, the fp64 pipe is the busy one): can ANY point of the box
+// [xl,xh]x[yl,yh] touch a solid?  Planes: threshold + 1e-6.  Walls: the distance from the box to the rectangle
+// (exact rounded corners, not the inflated bounding box, so that a disc resting in a corner pocket does not keep
+// replaying chunks) against R + 2e-6.  fp32 conversion and arithmetic errors are < 1e-7 for |x| <= 0.3, far inside
+// the margins; the exact fp64 tests need distance < R(1 + 1e-15).
+__device__ __forceinline__ bool maze_may_touch(const EnvParams& P, float xl, float xh, float yl, float yh) {
+    if ((xl <= P.f_plane_lo) || (xh >= P.f_plane_hi) || (yl <= P.f_plane_lo) || (yh >= P.f_plane_hi)) return true;
+    const float dx1 = fmaxf(fmaxf(P.f_wx0[0] - xh, xl - P.f_wx1[0]), 0.f);  // walls 1A / 1B share their x range
+    const float dx2 = fmaxf(fmaxf(P.f_wx0[2] - xh, xl - P.f_wx1[2]), 0.f);  // walls 2A / 2B
+    bool hit = false;
+    if (dx1 < P.f_rm) {
+        const float da = fmaxf(fmaxf(P.f_wy0[0] - yh, yl - P.f_wy1[0]), 0.f);
+        const float db = fmaxf(fmaxf(P.f_wy0[1] - yh, yl - P.f_wy1[1]), 0.f);
+        hit = (fmaf(dx1, dx1, da * da) < P.f_rm2) || (fmaf(dx1, dx1, db * db) < P.f_rm2);
+    }
+    if (dx2 < P.f_rm) {
+        const float da = fmaxf(fmaxf(P.f_wy0[2] - yh, yl - P.f_wy1[2]), 0.f);
+        const float db = fmaxf(fmaxf(P.f_wy0[3] - yh, yl - P.f_wy1[3]), 0.f);
+        hit = hit || (fmaf(dx2, dx2, da * da) < P.f_rm2) || (fmaf(dx2, dx2, db * db) < P.f_rm2);
+    }
+    return hit;
+}
+__device__ __forceinline__ void maze_integrate(const EnvParams& P, double fbx, double fby, double& x, double& y, double& vx,
+                                               double& vy) {
+    vx = __dadd_rn(__dmul_rn(P.c_a, vx), fbx);
+    vy = __dadd_rn(__dmul_rn(P.c_a, vy), fby);
+    x = __dadd_rn(x, __dmul_rn(P.h, vx));
+    y = __dadd_rn(y, __dmul_rn(P.h, vy));
+}
 __device__ __forceinline__ void maze_substeps_warp(const EnvParams& P, bool idle, double fbx, double fby, double& x,
                                                    double& y, bool& contact) {
     const int nsub = P.cfg.maze_substeps;
-    const double fbmax = fmax(fabs(fbx), fabs(fby)) * (1.0 + 1e-9) + 1e-300;
     double vx = 0.0, vy = 0.0;
     bool frozen = idle;  // idle lanes (beyond n) and lanes in contact do not move
-    int k = 0;
-    while (k < nsub) {
-        // number of substeps this lane can take before ANY exact contact test could fire:
-        // after j more substeps each coordinate has moved at most j*h*(vmax + j*fbmax)  (|v| grows by <= |fb| per substep)
-        int safe_lane = nsub - k;
+    for (int k = 0; k < nsub; k += MAZE_CHUNK) {
+        const int c = min(MAZE_CHUNK, nsub - k);
+        const double sx = x, sy = y, svx = vx, svy = vy;
+        bool may = false;
         if (!frozen) {
-            // max-norm clearance of the disc CENTRE to the solids (a lower bound of the Euclidean distance): the
-            // outer planes at +-0.3 and the two wall slabs x in -0.1 +- 0.005 (walls 1A/1B leave the y gap
-            // (-0.13, 0.22)) and x in 0.1 +- 0.005 (2A/2B leave (0.03, 0.28))
-            const double dxl = fmax(fabs(x + 0.1) - 0.005, 0.0), dxr = fmax(fabs(x - 0.1) - 0.005, 0.0);
-            const double dyl = fmax(fmin(y - P.wy1[1], P.wy0[0] - y), 0.0);
-            const double dyr = fmax(fmin(y - P.wy1[3], P.wy0[2] - y), 0.0);
-            const double cl = fmin(fmin(0.3 - fabs(x), 0.3 - fabs(y)), fmin(fmax(dxl, dyl), fmax(dxr, dyr)));
-            const double room = cl - MAZE_R - 1e-9;
-            safe_lane = 0;
-            if (room > 0.0) {
-                // largest j with j * (vmax + j * fbmax) <= room / h, estimated in fp32 (fast sqrt/div), then
-                // VERIFIED in fp64 -- the estimate only has to be a guess, the check makes the skip exact
-                const double vmax = fmax(fabs(vx), fabs(vy)) * (1.0 + 1e-9);
-                const double q = room / P.h;
-                const float vf = (float)vmax, ff = (float)fbmax, qf = (float)q;
-                float jf = floorf(0.999f * (sqrtf(vf * vf + 4.0f * ff * qf) - vf) / (2.0f * ff)) - 1.0f;
-                jf = fminf(fmaxf(jf, 0.0f), (float)(nsub - k));
-                const double j = (double)jf;
-                safe_lane = (j * (vmax + j * fbmax) <= q) ? (int)jf : 0;
+            if (c == MAZE_CHUNK) {
+#pragma unroll
+                for (int j = 0; j < MAZE_CHUNK; ++j) maze_integrate(P, fbx, fby, x, y, vx, vy);
+            } else {
+                for (int j = 0; j < c; ++j) maze_integrate(P, fbx, fby, x, y, vx, vy);
             }
+            const float fx0 = (float)sx, fx1 = (float)x, fy0 = (float)sy, fy1 = (float)y;
+            may = maze_may_touch(P, fminf(fx0, fx1), fmaxf(fx0, fx1), fminf(fy0, fy1), fmaxf(fy0, fy1));
         }
-        const int safe = __reduce_min_sync(0xffffffffu, safe_lane);
-        if (safe >= 1) {
-            for (int j = 0; j < safe; ++j) {
-                if (!frozen) {
-                    vx = __dadd_rn(__dmul_rn(P.c_a, vx), fbx);
-                    vy = __dadd_rn(__dmul_rn(P.c_a, vy), fby);
-                    x = __dadd_rn(x, __dmul_rn(P.h, vx));
-                    y = __dadd_rn(y, __dmul_rn(P.h, vy));
-                }
-            }
-            k += safe;
-        } else {
-            // some lane is too close to a solid: up to 8 substeps with the exact test, only for the lanes that need it
-            const int burst = min(8, nsub - k);
-            const bool needs_test = safe_lane < burst;
-            for (int j = 0; j < burst; ++j) {
-                if (!frozen) {
-                    if (needs_test && maze_touch(P, x, y)) {
+        if (__any_sync(0xffffffffu, may)) {
+            if (may) {  // rewind, replay the chunk with the exact test before every substep
+                x = sx; y = sy; vx = svx; vy = svy;
+                for (int j = 0; j < c; ++j) {
+                    if (maze_touch(P, x, y)) {
                         frozen = true;
                         contact = true;
-                    } else {
-                        vx = __dadd_rn(__dmul_rn(P.c_a, vx), fbx);
-                        vy = __dadd_rn(__dmul_rn(P.c_a, vy), fby);
-                        x = __dadd_rn(x, __dmul_rn(P.h, vx));
-                        y = __dadd_rn(y, __dmul_rn(P.h, vy));
+                        break;
                     }
+                    maze_integrate(P, fbx, fby, x, y, vx, vy);
                 }
             }
-            k += burst;
             if (__all_sync(0xffffffffu, frozen)) break;
         }
     }
@@ -358,7 +362,11 @@ EnvParams make_params(const rrl_env_config_t* cfg) {
         P.wx1[w] = cx[w] + 0.005;
         P.wy0[w] = cy[w] - 0.2;
         P.wy1[w] = cy[w] + 0.2;
+        P.f_wx0[w] = (float)P.wx0[w]; P.f_wx1[w] = (float)P.wx1[w];
+        P.f_wy0[w] = (float)P.wy0[w]; P.f_wy1[w] = (float)P.wy1[w];
     }
+    P.f_rm = (float)(MAZE_R + 2e-6);
+    P.f_rm2 = P.f_rm * P.f_rm;
     // exact thresholds of the plane tests (see maze_touch): walk to the boundary of the monotone predicate
     {
         double c = -0.3 + MAZE_R;
@@ -369,6 +377,8 @@ EnvParams make_params(const rrl_env_config_t* cfg) {
         while (c + MAZE_R >= 0.3) c = nextafter(c, -1.0);
         while (!(c + MAZE_R >= 0.3)) c = nextafter(c, 1.0);
         P.plane_hi = c;  // smallest x with fl(x + R) >= 0.3
+        P.f_plane_lo = (float)(P.plane_lo + 1e-6);
+        P.f_plane_hi = (float)(P.plane_hi - 1e-6);
     }
     return P;
 }

@@ -335,14 +335,23 @@ class VecEngine(object):
 
     # ---- state snapshots (capture warm-up, tests) -----------------------------------------------------
     def snapshot(self):
+        """everything one vector step mutates, incl. the ring slots its pushes will overwrite (they hold live
+        transitions once a ring has wrapped, e.g. after a resume)."""
+        c = self.counters.cpu()
+        ar = torch.arange(self.n, device=self.device)
+        t_idx = (int(c[native.C_TASK_POS]) + ar) % self.task_cap
+        c_idx = (int(c[native.C_CONS_POS]) + ar) % self.cons_cap
         return dict(arena=self.arena.clone(), counters=self.counters.clone(), state=self.state.clone(),
                     ep_steps=self.ep_steps.clone(), ep_return=self.ep_return.clone(), mt=self.mt_state.clone(),
-                    flags=self.cons_flags.clone())
+                    flags=self.cons_flags.clone(), t_idx=t_idx, c_idx=c_idx, t_rows=self.task_ring[t_idx].clone(),
+                    c_rows=self.cons_ring[c_idx].clone())
 
     def restore(self, s):
         self.arena.copy_(s["arena"]); self.counters.copy_(s["counters"]); self.state.copy_(s["state"])
         self.ep_steps.copy_(s["ep_steps"]); self.ep_return.copy_(s["ep_return"]); self.mt_state.copy_(s["mt"])
         self.cons_flags.copy_(s["flags"])
+        self.task_ring[s["t_idx"]] = s["t_rows"]
+        self.cons_ring[s["c_idx"]] = s["c_rows"]
 
     def save(self, path):
         """checkpoint (networks with the reference's state_dict names, Adam, multipliers, replay, sampler, env state)."""

@@ -148,3 +148,40 @@ def test_philox_noise_statistics(native, cuda):
     assert abs(e.mean()) < 5e-3 and abs(e.std() - 1.0) < 5e-3
     assert abs(np.corrcoef(e[:, 0], e[:, 1])[0, 1]) < 5e-3
     assert abs((e ** 4).mean() - 3.0) < 0.05
+
+
+def test_maze_contact_edges_and_corners_bit_exact(native, cuda):
+    """adversarial placements for the speculative-chunk substep loop: discs within a few ulps .. 1e-7 of touching a
+    plane, a wall face or a rounded wall corner, moving towards / along / away from it, and tiny actions."""
+    rs = np.random.RandomState(3)
+    R = envs.MAZE_R
+    pts = []
+    for x0, x1, y0, y1 in envs.maze_walls():
+        for cx in (x0, x1):
+            for cy in (y0, y1):
+                if abs(cy) > 0.29:
+                    continue
+                ang = rs.uniform(0, 2 * np.pi, 300)
+                rad = R + rs.choice([0.0, 1e-15, -1e-15, 1e-12, 1e-9, 3e-9, 1e-7, 1e-4, 2e-3], 300)
+                pts.append(np.stack([cx + rad * np.cos(ang), cy + rad * np.sin(ang)], 1))      # rounded corners
+        for xf, sgn in ((x0, -1.0), (x1, 1.0)):                                                # wall faces
+            yy = rs.uniform(max(y0, -0.27), min(y1, 0.27), 300)
+            off = R + rs.choice([0.0, 1e-15, 1e-12, 1e-9, 2e-9, 1e-7, 1e-5, 1e-3, 2e-2], 300)
+            pts.append(np.stack([xf + sgn * off, yy], 1))
+    for sgn in (-1.0, 1.0):                                                                    # outer planes
+        off = 0.3 - R - rs.choice([0.0, 1e-16, 1e-13, 1e-9, 1e-6, 1e-3, 2e-2], 300)
+        pts.append(np.stack([sgn * off, rs.uniform(-0.27, 0.27, 300)], 1))
+        pts.append(np.stack([rs.uniform(-0.27, 0.27, 300), sgn * off], 1))
+    s = np.clip(np.concatenate(pts), -0.2999, 0.2999)
+    n = len(s)
+    a = rs.uniform(-0.12, 0.12, (n, 2)).astype(np.float32)
+    a[::7] *= np.float32(1e-3)                  # crawling
+    a[::11, 0] = 0.0                            # axis-aligned motion
+    a[::13, 1] = 0.0
+    steps = rs.randint(0, 100, n)
+    o = _step(native, cuda, 2, s, a, ep_steps=steps, reset_draws=rs.rand(n, 2))
+    ns, r, d, c, su = envs.maze_step(s, a, steps)
+    assert np.array_equal(o["constraint"], c)
+    assert np.array_equal(o["next_state"], ns)
+    assert np.array_equal(o["reward"], r) and np.array_equal(o["done"], d) and np.array_equal(o["success"], su)
+    assert 0.2 * n < c.sum() < 0.9 * n
