@@ -60,6 +60,7 @@ enum {
     RRL_C_ADAM_T_ALPHA   = 23, /* Adam step counts of the scalar multipliers: log_alpha (sac.py:245-247),  */
     RRL_C_ADAM_T_NU      = 24, /*   log_nu (sac.py:259-261),                                                */
     RRL_C_ADAM_T_LAMBDA  = 25, /*   log_lambda_RCPO (sac.py:268-270)                                        */
+    RRL_C_TICKET         = 26, /* scratch: CTA arrival ticket of the fused optimizer-step kernel (always 0 between launches) */
     RRL_NUM_COUNTERS     = 32
 };
 

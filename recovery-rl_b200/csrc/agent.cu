@@ -350,89 +350,21 @@ __global__ void __launch_bounds__(kThreads, 2) act_kernel(const __grid_constant_
 // ---------------------------------------------------------------------------------------------
 // backward building blocks (training batches: rows <= max_batch)
 // ---------------------------------------------------------------------------------------------
-// (1) head backward: dh2 = (dout W3) * relu'(h2), dW3, db3, db2
-struct HeadBwdPass {
+// (1)+(2) head backward fused into the streamed GEMM.  dh2 = (dout W3) * relu'(h2) is never materialised: the
+//     CTAs rebuild their A tile from h2 / dout / W3 while staging it.
+//     C[m][n] = sum_k A[k][m] * B[k][n], n = 0..255, m tile of 32, both operands k-major.
+//     DATA  : A(k = hidden, m = row) = dh2[m][k], B = W2 [H][H], C = dh1 [row][H] masked by h1 > 0
+//     WEIGHT: A(k = row, m = out unit) = dh2[k][m], B = h1 [rows][H], C = gW2 [H][H]; the same CTAs also reduce
+//             gb2[m] = sum_r dh2[r][m], gW3[o][m] = sum_r dout[r][o] h2[r][m] and (m0 == 0) gb3[o] = sum_r dout[r][o]
+struct GemmPass {
     const float* dout;  // [rows][stride]
     int stride, n_out, na;
     const float *W3a, *W3b, *h2;
-    float* dh2;                   // [rows][H]
-    float *gW3a, *gW3b, *gb3a, *gb3b, *gb2;  // NULL when no weight grads are needed
-};
-struct HeadBwdArgs {
-    HeadBwdPass p[6];
-    const int64_t* rows_ptr;
-    int64_t R;
-};
-
-__global__ void __launch_bounds__(kThreads) head_backward_kernel(const __grid_constant__ HeadBwdArgs A) {
-    const int64_t rows = *A.rows_ptr;
-    if (rows <= 0) return;
-    const HeadBwdPass& P = A.p[blockIdx.y];
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const int j = blockIdx.x * 32 + tx;
-    __shared__ float red[5][8][32];
-    float w3[4];
-#pragma unroll
-    for (int o = 0; o < 4; ++o) w3[o] = o < P.na ? P.W3a[o * H + j] : (o < P.n_out ? P.W3b[(o - P.na) * H + j] : 0.f);
-    float gb2 = 0.f, gw[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int64_t r = ty; r < rows; r += 8) {
-        float d[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int o = 0; o < 4; ++o)
-            if (o < P.n_out) d[o] = P.dout[r * P.stride + o];
-        const float h = P.h2[r * H + j];
-        float g = d[0] * w3[0];
-        g = fmaf(d[1], w3[1], g); g = fmaf(d[2], w3[2], g); g = fmaf(d[3], w3[3], g);
-        g = h > 0.f ? g : 0.f;
-        P.dh2[r * H + j] = g;
-        gb2 += g;
-#pragma unroll
-        for (int o = 0; o < 4; ++o) gw[o] = fmaf(d[o], h, gw[o]);
-    }
-    if (P.gb2 == nullptr) return;
-    red[0][ty][tx] = gb2;
-#pragma unroll
-    for (int o = 0; o < 4; ++o) red[1 + o][ty][tx] = gw[o];
-    __syncthreads();
-    if (ty == 0) {
-        float s[5];
-#pragma unroll
-        for (int q = 0; q < 5; ++q) {
-            float v = 0.f;
-#pragma unroll
-            for (int y = 0; y < 8; ++y) v += red[q][y][tx];
-            s[q] = v;
-        }
-        P.gb2[j] = s[0];
-#pragma unroll
-        for (int o = 0; o < 4; ++o) {
-            if (o < P.na) P.gW3a[o * H + j] = s[1 + o];
-            else if (o < P.n_out) P.gW3b[(o - P.na) * H + j] = s[1 + o];
-        }
-    }
-    if (blockIdx.x == 0 && ty == 1) {  // db3[o] = sum_r dout[r][o]
-        for (int o = 0; o < P.n_out; ++o) {
-            float v = 0.f;
-            for (int64_t r = tx; r < rows; r += 32) v += P.dout[r * P.stride + o];
-#pragma unroll
-            for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
-            if (tx == 0) {
-                if (o < P.na) P.gb3a[o] = v;
-                else P.gb3b[o - P.na] = v;
-            }
-        }
-    }
-}
-
-// (2) streamed GEMM: C[m][n] = sum_k A[k][m] * B[k][n], n = 0..255, m tile of 32, both operands k-major.
-//     DATA  : A = dh2 [rows][H] read TRANSPOSED (k = hidden, m = row), B = W2 [H][H], C = dh1 [row][H] masked by h1 > 0
-//     WEIGHT: A = dh2 [rows][H] (k = row, m = out unit), B = h1 [rows][H], C = gW2 [H][H]
-struct GemmPass {
-    const float *A, *B;
-    int lda;
+    const float* B;
     int k_is_rows;      // K = rows (WEIGHT) else K = H
     const float* mask;  // DATA: h1
     float* C;
+    float *gW3a, *gW3b, *gb3a, *gb3b, *gb2;  // WEIGHT only
 };
 struct GemmArgs {
     GemmPass p[8];
@@ -450,30 +382,93 @@ __global__ void __launch_bounds__(kThreads) gemm_stream_kernel(const __grid_cons
     const int K = P.k_is_rows ? (int)rows : H;
     __shared__ __align__(16) float As[2][KC][BM];
     __shared__ __align__(16) float Bs[2][KC][H];
+    __shared__ __align__(16) float w3s[4][H];
+    __shared__ __align__(16) float ds[BM][4];       // DATA: dout of the CTA's 32 rows
+    float (*red)[8][21] = reinterpret_cast<float (*)[8][21]>(&Bs[0][0][0]);  // WEIGHT epilogue: partial sums of the
+                                                                             // 16 row-lanes (Bs is free by then)
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    auto load = [&](int c, int buf) {
+    const bool weight = P.k_is_rows != 0;
+    {   // stage W3 (zero rows beyond n_out) and, for DATA passes, the tile's dout
+#pragma unroll
+        for (int o = 0; o < 4; ++o)
+            w3s[o][t] = o < P.na ? P.W3a[o * H + t] : (o < P.n_out ? P.W3b[(o - P.na) * H + t] : 0.f);
+        if (!weight && t < BM * 4) {
+            const int m = t >> 2, o = t & 3;
+            ds[m][o] = (m0 + m < M && o < P.n_out) ? P.dout[(size_t)(m0 + m) * P.stride + o] : 0.f;
+        }
+    }
+    __syncthreads();
+    // per-thread A staging role (threads 0..127):
+    //   DATA  : row m = t >> 2, four consecutive k (kq = t & 3)       WEIGHT: row kk = t >> 3, four consecutive m (m4 = t & 7)
+    float4 hreg = make_float4(0.f, 0.f, 0.f, 0.f);
+    float dreg[4] = {0.f, 0.f, 0.f, 0.f};
+    float acc_gb2[4] = {0.f, 0.f, 0.f, 0.f}, acc_gw[4][4], acc_gb3[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int o = 0; o < 4; ++o)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc_gw[o][j] = 0.f;
+    auto fetch = [&](int c) {   // global loads of chunk c into registers (consumed by stage_a after the FMAs of chunk c-1)
         const int k0 = c * KC;
         if (t < 128) {
-            if (P.k_is_rows) {  // WEIGHT: A is k-major already
+            if (weight) {
                 const int kk = t >> 3, m4 = t & 7;
-                if (k0 + kk < K) cp_async16(&As[buf][kk][m4 * 4], P.A + (size_t)(k0 + kk) * P.lda + m0 + m4 * 4);
-                else *reinterpret_cast<float4*>(&As[buf][kk][m4 * 4]) = make_float4(0.f, 0.f, 0.f, 0.f);
-            } else {            // DATA: A(k, m) = dh2[m][k] -> transposing load (4 consecutive k of one row)
+                if (k0 + kk < K) {
+                    hreg = *reinterpret_cast<const float4*>(P.h2 + (size_t)(k0 + kk) * H + m0 + m4 * 4);
+#pragma unroll
+                    for (int o = 0; o < 4; ++o) dreg[o] = o < P.n_out ? P.dout[(size_t)(k0 + kk) * P.stride + o] : 0.f;
+                } else {
+                    hreg = make_float4(0.f, 0.f, 0.f, 0.f);
+                    dreg[0] = dreg[1] = dreg[2] = dreg[3] = 0.f;
+                }
+            } else {
                 const int m = t >> 2, kq = t & 3;
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (m0 + m < M) v = *reinterpret_cast<const float4*>(P.A + (size_t)(m0 + m) * H + k0 + kq * 4);
-                As[buf][kq * 4 + 0][m] = v.x; As[buf][kq * 4 + 1][m] = v.y;
-                As[buf][kq * 4 + 2][m] = v.z; As[buf][kq * 4 + 3][m] = v.w;
+                hreg = (m0 + m < M) ? *reinterpret_cast<const float4*>(P.h2 + (size_t)(m0 + m) * H + k0 + kq * 4)
+                                    : make_float4(0.f, 0.f, 0.f, 0.f);
             }
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int idx = t + kThreads * j;
             const int kk = idx >> 6, c4 = idx & 63;
-            if (k0 + kk < K) cp_async16(&Bs[buf][kk][c4 * 4], P.B + (size_t)(k0 + kk) * H + c4 * 4);
-            else *reinterpret_cast<float4*>(&Bs[buf][kk][c4 * 4]) = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (k0 + kk < K) cp_async16(&Bs[c & 1][kk][c4 * 4], P.B + (size_t)(k0 + kk) * H + c4 * 4);
+            else *reinterpret_cast<float4*>(&Bs[c & 1][kk][c4 * 4]) = make_float4(0.f, 0.f, 0.f, 0.f);
         }
         cp_async_commit();
+    };
+    auto stage_a = [&](int c) {  // dh2 of the fetched elements -> As[c & 1]
+        if (t >= 128) return;
+        const int buf = c & 1;
+        const float hv[4] = {hreg.x, hreg.y, hreg.z, hreg.w};
+        if (weight) {
+            const int kk = t >> 3, m4 = t & 7;
+            float g[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int col = m0 + m4 * 4 + j;
+                float v = dreg[0] * w3s[0][col];
+                v = fmaf(dreg[1], w3s[1][col], v); v = fmaf(dreg[2], w3s[2][col], v); v = fmaf(dreg[3], w3s[3][col], v);
+                g[j] = hv[j] > 0.f ? v : 0.f;
+                acc_gb2[j] += g[j];
+#pragma unroll
+                for (int o = 0; o < 4; ++o) acc_gw[o][j] = fmaf(dreg[o], hv[j], acc_gw[o][j]);
+            }
+            if (m4 == 0) {
+#pragma unroll
+                for (int o = 0; o < 4; ++o) acc_gb3[o] += dreg[o];
+            }
+            *reinterpret_cast<float4*>(&As[buf][kk][m4 * 4]) = make_float4(g[0], g[1], g[2], g[3]);
+        } else {
+            const int m = t >> 2, kq = t & 3;
+            const int k0 = c * KC;
+            const float4 dv = *reinterpret_cast<const float4*>(ds[m]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int col = k0 + kq * 4 + j;
+                float v = dv.x * w3s[0][col];
+                v = fmaf(dv.y, w3s[1][col], v); v = fmaf(dv.z, w3s[2][col], v); v = fmaf(dv.w, w3s[3][col], v);
+                As[buf][kq * 4 + j][m] = hv[j] > 0.f ? v : 0.f;
+            }
+        }
     };
     float acc[4][8];
 #pragma unroll
@@ -481,15 +476,16 @@ __global__ void __launch_bounds__(kThreads) gemm_stream_kernel(const __grid_cons
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[r][j] = 0.f;
     const int nchunks = (K + KC - 1) / KC;
-    load(0, 0);
+    fetch(0);
+    stage_a(0);
     for (int c = 0; c < nchunks; ++c) {
         if (c + 1 < nchunks) {
-            load(c + 1, (c + 1) & 1);
+            fetch(c + 1);
             cp_async_wait<1>();
         } else {
             cp_async_wait<0>();
         }
-        __syncthreads();
+        __syncthreads();   // chunk c staged (A by stage_a, B by cp.async); buffer (c+1)&1 free since the sync below
         const int buf = c & 1;
 #pragma unroll
         for (int kk = 0; kk < KC; ++kk) {
@@ -505,6 +501,7 @@ __global__ void __launch_bounds__(kThreads) gemm_stream_kernel(const __grid_cons
                 acc[r][6] = fmaf(a[r], b1.z, acc[r][6]); acc[r][7] = fmaf(a[r], b1.w, acc[r][7]);
             }
         }
+        if (c + 1 < nchunks) stage_a(c + 1);   // writes As[(c+1)&1]: last read before the previous end-of-iteration sync
         __syncthreads();
     }
 #pragma unroll
@@ -523,6 +520,42 @@ __global__ void __launch_bounds__(kThreads) gemm_stream_kernel(const __grid_cons
         }
         *reinterpret_cast<float4*>(P.C + (size_t)m * H + lane * 4) = o0;
         *reinterpret_cast<float4*>(P.C + (size_t)m * H + 128 + lane * 4) = o1;
+    }
+    if (weight && P.gb2) {   // head-layer gradients: deterministic reduction over the 16 row-lanes
+        if (t < 128) {
+            const int kk = t >> 3, m4 = t & 7;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                red[kk][m4][j] = acc_gb2[j];
+#pragma unroll
+                for (int o = 0; o < 4; ++o) red[kk][m4][4 + o * 4 + j] = acc_gw[o][j];
+            }
+            if (m4 == 0) {  // gb3 partials: column 20 of slots 0..3 (one head output each), written by this thread only
+#pragma unroll
+                for (int o = 0; o < 4; ++o) red[kk][o][20] = acc_gb3[o];
+            }
+        }
+        __syncthreads();
+        if (t < 32 * 5) {   // 32 columns x {gb2, gW3[0..3]}
+            const int q = t >> 5, mm = t & 31;  // q = 0: gb2, 1..4: gW3 row q-1
+            float v = 0.f;
+#pragma unroll
+            for (int kk = 0; kk < 16; ++kk) v += red[kk][mm >> 2][q == 0 ? (mm & 3) : (4 + (q - 1) * 4 + (mm & 3))];
+            const int col = m0 + mm;
+            if (q == 0) P.gb2[col] = v;
+            else {
+                const int o = q - 1;
+                if (o < P.na) P.gW3a[o * H + col] = v;
+                else if (o < P.n_out) P.gW3b[(o - P.na) * H + col] = v;
+            }
+        } else if (t >= 192 && t < 196 && m0 == 0) {
+            const int o = t - 192;
+            float v = 0.f;
+#pragma unroll
+            for (int kk = 0; kk < 16; ++kk) v += red[kk][o][20];
+            if (o < P.na) P.gb3a[o] = v;
+            else if (o < P.n_out) P.gb3b[o - P.na] = v;
+        }
     }
 }
 
@@ -860,7 +893,10 @@ __global__ void __launch_bounds__(kThreads) stoch_backward_kernel(const __grid_c
     }
 }
 
-// (9) Adam (torch.optim.Adam defaults: sac.py:84,114; qrisk.py:58,75) over a flat range + W2T image refresh
+// (9) optimizer step, fused: Adam (torch.optim.Adam defaults: sac.py:84,114; qrisk.py:58,75) over a flat range,
+//     refresh of the k-major W2 images, the soft target update of the net's target copy (utils.py:46-49:
+//     target = target*(1-tau) + new_param*tau, sac.py:273-274 / qrisk.py:160-162) and the step bookkeeping
+//     (Adam step counts, update counters) done by the last CTA to finish.
 struct ImgRef {
     int64_t off;  // offset of a 256x256 tensor inside the arena
     int64_t img;  // offset of its transposed image
@@ -870,35 +906,73 @@ struct AdamArgs {
     int64_t off, count, grad_off, m_off, v_off;
     float lr, b1, b2, eps, grad_scale;
     double lr64;
-    const int64_t* counters;
+    int64_t* counters;
     int t_counter, rows_counter;
-    ImgRef img[4];
+    ImgRef img[6];
     int n_img;
+    // soft target update of [tgt_src_off, tgt_src_off + tgt_count) into tgt_off (tgt_count == 0: none)
+    int64_t tgt_src_off, tgt_off, tgt_count;
+    float tau;
+    int upd_counter, interval;       // polyak only if counters[upd_counter] % interval == 0
+    ImgRef timg[2];
+    int n_timg;
+    // bookkeeping by the last CTA: counters[bump[i]] += 1 (i < n_bump)
+    int bump[3];
+    int n_bump;
 };
 __global__ void __launch_bounds__(kThreads) adam_kernel(const __grid_constant__ AdamArgs A) {
     if (A.counters[A.rows_counter] <= 0) return;
     __shared__ float s_bc[2];
+    __shared__ int s_polyak;
     if (threadIdx.x == 0) {  // bias corrections and step size in double (python floats in torch), once per block
         const double tstep = (double)(A.counters[A.t_counter] + 1);
         s_bc[0] = (float)(A.lr64 / (1.0 - pow((double)A.b1, tstep)));
         s_bc[1] = (float)sqrt(1.0 - pow((double)A.b2, tstep));
+        s_polyak = A.tgt_count > 0 && (A.interval <= 1 || (A.counters[A.upd_counter] % A.interval) == 0);
     }
     __syncthreads();
     const float step_size = s_bc[0], bc2s = s_bc[1];
+    const bool polyak = s_polyak != 0;
+    const float omt = (float)(1.0 - (double)A.tau);
     for (int64_t i = blockIdx.x * (int64_t)kThreads + threadIdx.x; i < A.count; i += (int64_t)gridDim.x * kThreads) {
         const int64_t o = A.off + i;
-        const float g = A.arena[A.grad_off + o] * A.grad_scale;
-        float m = A.arena[A.m_off + o], v = A.arena[A.v_off + o];
-        m = m + (g - m) * (1.0f - A.b1);               // exp_avg.lerp_(grad, 1 - beta1)
-        v = v * A.b2 + (1.0f - A.b2) * g * g;           // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
-        const float denom = sqrtf(v) / bc2s + A.eps;
-        const float p = A.arena[o] - step_size * (m / denom);
-        A.arena[A.m_off + o] = m;
-        A.arena[A.v_off + o] = v;
-        A.arena[o] = p;
-        for (int q = 0; q < A.n_img; ++q) {
-            const int64_t d = o - A.img[q].off;
-            if (d >= 0 && d < (int64_t)H * H) A.arena[A.img[q].img + (d & (H - 1)) * H + (d >> 8)] = p;
+        float p = A.arena[o];
+        if (A.lr64 > 0.0) {
+            const float g = A.arena[A.grad_off + o] * A.grad_scale;
+            float m = A.arena[A.m_off + o], v = A.arena[A.v_off + o];
+            m = m + (g - m) * (1.0f - A.b1);               // exp_avg.lerp_(grad, 1 - beta1)
+            v = v * A.b2 + (1.0f - A.b2) * g * g;           // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+            const float denom = sqrtf(v) / bc2s + A.eps;
+            p = p - step_size * (m / denom);
+            A.arena[A.m_off + o] = m;
+            A.arena[A.v_off + o] = v;
+            A.arena[o] = p;
+            for (int q = 0; q < A.n_img; ++q) {
+                const int64_t d = o - A.img[q].off;
+                if (d >= 0 && d < (int64_t)H * H) A.arena[A.img[q].img + (d & (H - 1)) * H + (d >> 8)] = p;
+            }
+        }
+        if (polyak) {
+            const int64_t d0 = o - A.tgt_src_off;
+            if (d0 >= 0 && d0 < A.tgt_count) {
+                const int64_t to = A.tgt_off + d0;
+                const float tp = A.arena[to] * omt + p * A.tau;
+                A.arena[to] = tp;
+                for (int q = 0; q < A.n_timg; ++q) {
+                    const int64_t d = to - A.timg[q].off;
+                    if (d >= 0 && d < (int64_t)H * H) A.arena[A.timg[q].img + (d & (H - 1)) * H + (d >> 8)] = tp;
+                }
+            }
+        }
+    }
+    // every CTA has read the counters above; the last one to arrive bumps them
+    __syncthreads();
+    if (threadIdx.x == 0 && A.n_bump > 0) {
+        __threadfence();
+        const unsigned long long ticket = atomicAdd(reinterpret_cast<unsigned long long*>(A.counters + RRL_C_TICKET), 1ull);
+        if (ticket == (unsigned long long)gridDim.x - 1) {
+            A.counters[RRL_C_TICKET] = 0;
+            for (int i = 0; i < A.n_bump; ++i) A.counters[A.bump[i]] += 1;
         }
     }
 }
@@ -1053,29 +1127,40 @@ int imgs_of_net(const Layout& L, int net, ImgRef* out) {
     return heads;
 }
 
+// nets a (and b, contiguous after a in storage order) share one launch.  net_a < 0 with polyak_src >= 0: no Adam
+// (lr64 = 0), only the soft update of polyak_src into polyak_dst and the bookkeeping.
 int launch_adam(const rrl_agent_config_t* cfg, const Layout& L, float* arena, int64_t* counters, int net_a, int net_b,
-                int t_counter, int rows_counter, cudaStream_t st) {
-    // nets a (and b, contiguous after a in storage order) share one launch
+                int t_counter, int rows_counter, cudaStream_t st, int polyak_dst = -1, int polyak_src = -1, float tau = 0.f,
+                int upd_counter = -1, const int* bump = nullptr, int n_bump = 0) {
     AdamArgs A;
     memset(&A, 0, sizeof(A));
     A.arena = arena;
-    A.off = L.net_off[net_a];
-    A.count = L.net_size[net_a] + (net_b >= 0 ? L.net_size[net_b] : 0);
+    const int first = net_a >= 0 ? net_a : polyak_src;
+    A.off = L.net_off[first];
+    A.count = L.net_size[first] + ((net_a >= 0 && net_b >= 0) ? L.net_size[net_b] : 0);
     A.grad_off = L.grad_off; A.m_off = L.m_off; A.v_off = L.v_off;
     A.lr = cfg->lr; A.b1 = cfg->beta1; A.b2 = cfg->beta2; A.eps = cfg->adam_eps;
-    A.lr64 = cfg->lr64 > 0.0 ? cfg->lr64 : (double)cfg->lr;
+    A.lr64 = net_a >= 0 ? (cfg->lr64 > 0.0 ? cfg->lr64 : (double)cfg->lr) : 0.0;
     A.grad_scale = cfg->grad_scale;
     A.counters = counters;
-    A.t_counter = t_counter;
+    A.t_counter = t_counter >= 0 ? t_counter : RRL_C_ADAM_T0;
     A.rows_counter = rows_counter;
-    A.n_img = imgs_of_net(L, net_a, A.img);
-    if (net_b >= 0) A.n_img += imgs_of_net(L, net_b, A.img + A.n_img);
+    if (net_a >= 0) {
+        A.n_img = imgs_of_net(L, net_a, A.img);
+        if (net_b >= 0) A.n_img += imgs_of_net(L, net_b, A.img + A.n_img);
+    }
+    if (polyak_dst >= 0) {
+        A.tgt_src_off = L.net_off[polyak_src]; A.tgt_off = L.net_off[polyak_dst]; A.tgt_count = L.net_size[polyak_dst];
+        A.tau = tau; A.upd_counter = upd_counter; A.interval = cfg->target_update_interval;
+        A.n_timg = imgs_of_net(L, polyak_dst, A.timg);
+    }
+    for (int i = 0; i < n_bump && i < 3; ++i) A.bump[i] = bump[i];
+    A.n_bump = n_bump < 3 ? n_bump : 3;
     const int blocks = (int)((A.count + kThreads * 4 - 1) / (kThreads * 4));
     adam_kernel<<<blocks, kThreads, 0, st>>>(A);
     RRL_CHECK_LAUNCH();
     return 0;
 }
-
 int launch_polyak(const Layout& L, float* arena, const int64_t* counters, int dst, int src, float tau, int rows_counter,
                   int upd_counter, int interval, cudaStream_t st) {
     PolyakArgs A;
@@ -1366,36 +1451,25 @@ extern "C" int rrl_sac_backward(const rrl_agent_config_t* cfg, float* arena, con
     const HeadW k1 = head_w(L, arena, RRL_NET_QRISK, 0), k2 = head_w(L, arena, RRL_NET_QRISK, 1);
     const int nq = dgd ? 6 : 4;  // passes whose gradient flows back: critic x4 [+ Q_risk(s, pi) x2 into the action]
     const int slot[6] = {0, 1, 2, 3, 5, 6};
-    {  // head backward of the critic passes (weight grads only for the (s, a) passes)
-        HeadBwdArgs A;
-        memset(&A, 0, sizeof(A));
-        A.rows_ptr = rows_ptr; A.R = R;
-        const float* dout[6] = {RA(RA_DQF1), RA(RA_DQF2), RA(RA_DQP1), RA(RA_DQP2), RA(RA_DSQ1), RA(RA_DSQ2)};
-        for (int q = 0; q < nq; ++q) {
-            HeadBwdPass& p = A.p[q];
-            const HeadW& w = q < 4 ? ((q & 1) ? c2 : c1) : ((q & 1) ? k2 : k1);
-            const HeadG& g = (q & 1) ? g2 : g1;
-            p.dout = dout[q]; p.stride = 1; p.n_out = 1; p.na = 1;
-            p.W3a = w.W3a; p.h2 = arena + L.h2[slot[q]]; p.dh2 = arena + L.dh2[slot[q]];
-            if (q < 2) { p.gW3a = g.W3a; p.gb3a = g.b3a; p.gb2 = g.b2; }
-        }
-        head_backward_kernel<<<dim3(H / 32, nq), kThreads, 0, st>>>(A);
-        RRL_CHECK_LAUNCH();
-    }
-    {  // dh1 for all passes + gW2 for the (s, a) passes
+    {  // head backward + dh1 for all passes + gW2 / gW3 / gb3 / gb2 for the (s, a) passes, one launch
         GemmArgs G;
         memset(&G, 0, sizeof(G));
         G.rows_ptr = rows_ptr;
+        const float* dout[6] = {RA(RA_DQF1), RA(RA_DQF2), RA(RA_DQP1), RA(RA_DQP2), RA(RA_DSQ1), RA(RA_DSQ2)};
         int n = 0;
         for (int q = 0; q < nq; ++q) {
             GemmPass& p = G.p[n++];
             const HeadW& w = q < 4 ? ((q & 1) ? c2 : c1) : ((q & 1) ? k2 : k1);
-            p.A = arena + L.dh2[slot[q]]; p.lda = H; p.B = w.W2; p.k_is_rows = 0;
-            p.mask = arena + L.h1[slot[q]]; p.C = arena + L.dh1[slot[q]];
+            p.dout = dout[q]; p.stride = 1; p.n_out = 1; p.na = 1; p.W3a = w.W3a; p.h2 = arena + L.h2[slot[q]];
+            p.B = w.W2; p.k_is_rows = 0; p.mask = arena + L.h1[slot[q]]; p.C = arena + L.dh1[slot[q]];
         }
         for (int q = 0; q < 2; ++q) {
             GemmPass& p = G.p[n++];
-            p.A = arena + L.dh2[q]; p.lda = H; p.B = arena + L.h1[q]; p.k_is_rows = 1; p.C = (q ? g2 : g1).W2;
+            const HeadW& w = q ? c2 : c1;
+            const HeadG& g = q ? g2 : g1;
+            p.dout = dout[q]; p.stride = 1; p.n_out = 1; p.na = 1; p.W3a = w.W3a; p.h2 = arena + L.h2[q];
+            p.B = arena + L.h1[q]; p.k_is_rows = 1; p.C = g.W2;
+            p.gW3a = g.W3a; p.gb3a = g.b3a; p.gb2 = g.b2;
         }
         const int mt = (int)((R > H ? R : H) / 32);
         gemm_stream_kernel<<<dim3(mt, n), kThreads, 0, st>>>(G);
@@ -1434,25 +1508,19 @@ extern "C" int rrl_sac_backward(const rrl_agent_config_t* cfg, float* arena, con
         stoch_backward_kernel<<<1, kThreads, 0, st>>>(A);
         RRL_CHECK_LAUNCH();
     }
-    {
-        HeadBwdArgs A;
-        memset(&A, 0, sizeof(A));
-        A.rows_ptr = rows_ptr; A.R = R;
-        HeadBwdPass& p = A.p[0];
-        p.dout = R4(R4_DRAW_POL); p.stride = 4; p.n_out = det ? 2 : 4; p.na = 2;
-        p.W3a = pw.W3a; p.W3b = pw.W3b; p.h2 = arena + L.h2[4]; p.dh2 = arena + L.dh2[4];
-        p.gW3a = pg.W3a; p.gb3a = pg.b3a; p.gb2 = pg.b2;
-        if (!det) { p.gW3b = pg.W3b; p.gb3b = pg.b3b; }
-        head_backward_kernel<<<dim3(H / 32, 1), kThreads, 0, st>>>(A);
-        RRL_CHECK_LAUNCH();
-    }
-    {
+    {  // policy: head backward + dh1 + gW2 / gW3 / gb3 / gb2
         GemmArgs G;
         memset(&G, 0, sizeof(G));
         G.rows_ptr = rows_ptr;
-        G.p[0].A = arena + L.dh2[4]; G.p[0].lda = H; G.p[0].B = pw.W2; G.p[0].mask = arena + L.h1[4];
-        G.p[0].C = arena + L.dh1[4];
-        G.p[1].A = arena + L.dh2[4]; G.p[1].lda = H; G.p[1].B = arena + L.h1[4]; G.p[1].k_is_rows = 1; G.p[1].C = pg.W2;
+        for (int q = 0; q < 2; ++q) {
+            GemmPass& p = G.p[q];
+            p.dout = R4(R4_DRAW_POL); p.stride = 4; p.n_out = det ? 2 : 4; p.na = 2; p.W3a = pw.W3a; p.W3b = pw.W3b;
+            p.h2 = arena + L.h2[4];
+        }
+        G.p[0].B = pw.W2; G.p[0].mask = arena + L.h1[4]; G.p[0].C = arena + L.dh1[4];
+        G.p[1].B = arena + L.h1[4]; G.p[1].k_is_rows = 1; G.p[1].C = pg.W2;
+        G.p[1].gW3a = pg.W3a; G.p[1].gb3a = pg.b3a; G.p[1].gb2 = pg.b2;
+        if (!det) { G.p[1].gW3b = pg.W3b; G.p[1].gb3b = pg.b3b; }
         const int mt = (int)((R > H ? R : H) / 32);
         gemm_stream_kernel<<<dim3(mt, 2), kThreads, 0, st>>>(G);
         RRL_CHECK_LAUNCH();
@@ -1474,12 +1542,12 @@ extern "C" int rrl_sac_apply(const rrl_agent_config_t* cfg, float* arena, int64_
     RRL_CHECK_ARG(arena && counters, "null argument");
     const Layout L = make_layout(cfg);
     cudaStream_t st = (cudaStream_t)stream;
-    // critic_optim.step(); policy_optim.step()  (sac.py:233-239).  Both Adams have the same step count.
-    int rc = launch_adam(cfg, L, arena, counters, RRL_NET_CRITIC, RRL_NET_POLICY, RRL_C_ADAM_T0 + 0, RRL_C_SAC_ROWS, st);
-    if (rc) return rc;
-    // soft_update(critic_target, critic, tau) if updates % target_update_interval == 0  (sac.py:273-274)
-    rc = launch_polyak(L, arena, counters, RRL_NET_CRITIC_TARGET, RRL_NET_CRITIC, cfg->tau, RRL_C_SAC_ROWS,
-                       RRL_C_SAC_UPDATES, cfg->target_update_interval, st);
+    // critic_optim.step(); policy_optim.step()  (sac.py:233-239; both Adams have the same step count), then
+    // soft_update(critic_target, critic, tau) if updates % target_update_interval == 0  (sac.py:273-274), then the
+    // step bookkeeping -- one launch
+    const int bump[3] = {RRL_C_ADAM_T0 + 0, RRL_C_ADAM_T0 + 1, RRL_C_SAC_UPDATES};
+    int rc = launch_adam(cfg, L, arena, counters, RRL_NET_CRITIC, RRL_NET_POLICY, RRL_C_ADAM_T0 + 0, RRL_C_SAC_ROWS, st,
+                         RRL_NET_CRITIC_TARGET, RRL_NET_CRITIC, cfg->tau, RRL_C_SAC_UPDATES, bump, 3);
     if (rc) return rc;
     if (cfg->algo_flags & (RRL_ALGO_AUTO_ALPHA | RRL_ALGO_UPDATE_NU | RRL_ALGO_RCPO)) {  // sac.py:241-271
         ScalarAdamArgs A;
@@ -1490,8 +1558,6 @@ extern "C" int rrl_sac_apply(const rrl_agent_config_t* cfg, float* arena, int64_
         scalar_adam_kernel<<<1, 32, 0, st>>>(A);
         RRL_CHECK_LAUNCH();
     }
-    bump_kernel<<<1, 32, 0, st>>>(counters, RRL_C_SAC_ROWS, RRL_C_ADAM_T0 + 0, RRL_C_ADAM_T0 + 1, RRL_C_SAC_UPDATES);
-    RRL_CHECK_LAUNCH();
     return 0;
 }
 
@@ -1543,30 +1609,20 @@ extern "C" int rrl_qrisk_backward(const rrl_agent_config_t* cfg, float* arena, c
     }
     const HeadW c1 = head_w(L, arena, RRL_NET_QRISK, 0), c2 = head_w(L, arena, RRL_NET_QRISK, 1);
     const HeadG g1 = head_g(L, arena, RRL_NET_QRISK, 0), g2 = head_g(L, arena, RRL_NET_QRISK, 1);
-    {
-        HeadBwdArgs A;
-        memset(&A, 0, sizeof(A));
-        A.rows_ptr = rows_ptr; A.R = R;
-        for (int q = 0; q < 2; ++q) {
-            HeadBwdPass& p = A.p[q];
-            const HeadW& w = q ? c2 : c1;
-            const HeadG& g = q ? g2 : g1;
-            p.dout = q ? RA(RA_QR_DQ2) : RA(RA_QR_DQ1); p.stride = 1; p.n_out = 1; p.na = 1;
-            p.W3a = w.W3a; p.h2 = arena + L.h2[q]; p.dh2 = arena + L.dh2[q];
-            p.gW3a = g.W3a; p.gb3a = g.b3a; p.gb2 = g.b2;
-        }
-        head_backward_kernel<<<dim3(H / 32, 2), kThreads, 0, st>>>(A);
-        RRL_CHECK_LAUNCH();
-    }
-    {
+    {  // head backward + dh1 + gW2 / gW3 / gb3 / gb2 of both heads
         GemmArgs G;
         memset(&G, 0, sizeof(G));
         G.rows_ptr = rows_ptr;
         for (int q = 0; q < 2; ++q) {
+            const HeadW& w = q ? c2 : c1;
+            const HeadG& g = q ? g2 : g1;
             GemmPass& p = G.p[q];
-            p.A = arena + L.dh2[q]; p.lda = H; p.B = (q ? c2 : c1).W2; p.mask = arena + L.h1[q]; p.C = arena + L.dh1[q];
-            GemmPass& w = G.p[2 + q];
-            w.A = arena + L.dh2[q]; w.lda = H; w.B = arena + L.h1[q]; w.k_is_rows = 1; w.C = (q ? g2 : g1).W2;
+            p.dout = q ? RA(RA_QR_DQ2) : RA(RA_QR_DQ1); p.stride = 1; p.n_out = 1; p.na = 1; p.W3a = w.W3a;
+            p.h2 = arena + L.h2[q]; p.B = w.W2; p.mask = arena + L.h1[q]; p.C = arena + L.dh1[q];
+            GemmPass& ww = G.p[2 + q];
+            ww = p;
+            ww.B = arena + L.h1[q]; ww.k_is_rows = 1; ww.mask = nullptr; ww.C = g.W2;
+            ww.gW3a = g.W3a; ww.gb3a = g.b3a; ww.gb2 = g.b2;
         }
         const int mt = (int)((R > H ? R : H) / 32);
         gemm_stream_kernel<<<dim3(mt, 4), kThreads, 0, st>>>(G);
@@ -1592,11 +1648,11 @@ extern "C" int rrl_qrisk_apply(const rrl_agent_config_t* cfg, float* arena, int6
     RRL_CHECK_ARG(arena && counters, "null argument");
     const Layout L = make_layout(cfg);
     cudaStream_t st = (cudaStream_t)stream;
-    int rc = launch_adam(cfg, L, arena, counters, RRL_NET_QRISK, -1, RRL_C_ADAM_T0 + 2, RRL_C_QRISK_ROWS, st);
-    if (rc) return rc;
-    bump_kernel<<<1, 32, 0, st>>>(counters, RRL_C_QRISK_ROWS, RRL_C_ADAM_T0 + 2, -1, -1);
-    RRL_CHECK_LAUNCH();
-    return 0;
+    // safety_critic_optim.step() (qrisk.py:146-148) and, in the same launch, the soft update of the target
+    // (qrisk.py:160-162: it reads the post-step critic, which the recovery-policy update in between does not touch)
+    const int bump[1] = {RRL_C_ADAM_T0 + 2};
+    return launch_adam(cfg, L, arena, counters, RRL_NET_QRISK, -1, RRL_C_ADAM_T0 + 2, RRL_C_QRISK_ROWS, st,
+                       RRL_NET_QRISK_TARGET, RRL_NET_QRISK, cfg->tau_safe, RRL_C_QRISK_UPDATES, bump, 1);
 }
 
 // recovery policy on the POST-step safety critic (qrisk.py:150-158), then Polyak (qrisk.py:160-163)
@@ -1644,26 +1700,14 @@ extern "C" int rrl_recovery_backward(const rrl_agent_config_t* cfg, float* arena
         RRL_CHECK_LAUNCH();
     }
     const HeadW c1 = head_w(L, arena, RRL_NET_QRISK, 0), c2 = head_w(L, arena, RRL_NET_QRISK, 1);
-    {
-        HeadBwdArgs A;
-        memset(&A, 0, sizeof(A));
-        A.rows_ptr = rows_ptr; A.R = R;
-        for (int q = 0; q < 2; ++q) {
-            HeadBwdPass& p = A.p[q];
-            p.dout = q ? RA(RA_REC_DQ2) : RA(RA_REC_DQ1); p.stride = 1; p.n_out = 1; p.na = 1;
-            p.W3a = (q ? c2 : c1).W3a; p.h2 = arena + L.h2[2 + q]; p.dh2 = arena + L.dh2[2 + q];
-        }
-        head_backward_kernel<<<dim3(H / 32, 2), kThreads, 0, st>>>(A);
-        RRL_CHECK_LAUNCH();
-    }
-    {
+    {  // back through the (post-step) safety critic into the action: head backward + dh1
         GemmArgs G;
         memset(&G, 0, sizeof(G));
         G.rows_ptr = rows_ptr;
         for (int q = 0; q < 2; ++q) {
             GemmPass& p = G.p[q];
-            p.A = arena + L.dh2[2 + q]; p.lda = H; p.B = (q ? c2 : c1).W2; p.mask = arena + L.h1[2 + q];
-            p.C = arena + L.dh1[2 + q];
+            p.dout = q ? RA(RA_REC_DQ2) : RA(RA_REC_DQ1); p.stride = 1; p.n_out = 1; p.na = 1; p.W3a = (q ? c2 : c1).W3a;
+            p.h2 = arena + L.h2[2 + q]; p.B = (q ? c2 : c1).W2; p.mask = arena + L.h1[2 + q]; p.C = arena + L.dh1[2 + q];
         }
         gemm_stream_kernel<<<dim3((int)(R / 32), 2), kThreads, 0, st>>>(G);
         RRL_CHECK_LAUNCH();
@@ -1689,24 +1733,17 @@ extern "C" int rrl_recovery_backward(const rrl_agent_config_t* cfg, float* arena
         stoch_backward_kernel<<<1, kThreads, 0, st>>>(A);
         RRL_CHECK_LAUNCH();
     }
-    {
-        HeadBwdArgs A;
-        memset(&A, 0, sizeof(A));
-        A.rows_ptr = rows_ptr; A.R = R;
-        HeadBwdPass& p = A.p[0];
-        p.dout = R4(R4_DRAW_REC); p.stride = 4; p.n_out = 2; p.na = 2;
-        p.W3a = pw.W3a; p.h2 = arena + L.h2[4]; p.dh2 = arena + L.dh2[4];
-        p.gW3a = pg.W3a; p.gb3a = pg.b3a; p.gb2 = pg.b2;
-        head_backward_kernel<<<dim3(H / 32, 1), kThreads, 0, st>>>(A);
-        RRL_CHECK_LAUNCH();
-    }
-    {
+    {  // recovery policy: head backward + dh1 + gW2 / gW3 / gb3 / gb2
         GemmArgs G;
         memset(&G, 0, sizeof(G));
         G.rows_ptr = rows_ptr;
-        G.p[0].A = arena + L.dh2[4]; G.p[0].lda = H; G.p[0].B = pw.W2; G.p[0].mask = arena + L.h1[4];
-        G.p[0].C = arena + L.dh1[4];
-        G.p[1].A = arena + L.dh2[4]; G.p[1].lda = H; G.p[1].B = arena + L.h1[4]; G.p[1].k_is_rows = 1; G.p[1].C = pg.W2;
+        for (int q = 0; q < 2; ++q) {
+            GemmPass& p = G.p[q];
+            p.dout = R4(R4_DRAW_REC); p.stride = 4; p.n_out = 2; p.na = 2; p.W3a = pw.W3a; p.h2 = arena + L.h2[4];
+        }
+        G.p[0].B = pw.W2; G.p[0].mask = arena + L.h1[4]; G.p[0].C = arena + L.dh1[4];
+        G.p[1].B = arena + L.h1[4]; G.p[1].k_is_rows = 1; G.p[1].C = pg.W2;
+        G.p[1].gW3a = pg.W3a; G.p[1].gb3a = pg.b3a; G.p[1].gb2 = pg.b2;
         const int mt = (int)((R > H ? R : H) / 32);
         gemm_stream_kernel<<<dim3(mt, 2), kThreads, 0, st>>>(G);
         RRL_CHECK_LAUNCH();
@@ -1728,17 +1765,13 @@ extern "C" int rrl_recovery_apply(const rrl_agent_config_t* cfg, float* arena, i
     RRL_CHECK_ARG(arena && counters, "null argument");
     const Layout L = make_layout(cfg);
     cudaStream_t st = (cudaStream_t)stream;
-    int rc = 0;
+    // policy_optim.step() (qrisk.py:156-158); self.updates += 1 (qrisk.py:163)
     if (cfg->mf_recovery) {
-        rc = launch_adam(cfg, L, arena, counters, RRL_NET_RECOVERY, -1, RRL_C_ADAM_T0 + 3, RRL_C_QRISK_ROWS, st);
-        if (rc) return rc;
+        const int bump[2] = {RRL_C_ADAM_T0 + 3, RRL_C_QRISK_UPDATES};
+        return launch_adam(cfg, L, arena, counters, RRL_NET_RECOVERY, -1, RRL_C_ADAM_T0 + 3, RRL_C_QRISK_ROWS, st, -1, -1,
+                           0.f, -1, bump, 2);
     }
-    // soft_update(safety_critic_target, safety_critic, tau_safe) if self.updates % interval == 0; self.updates += 1
-    rc = launch_polyak(L, arena, counters, RRL_NET_QRISK_TARGET, RRL_NET_QRISK, cfg->tau_safe, RRL_C_QRISK_ROWS,
-                       RRL_C_QRISK_UPDATES, cfg->target_update_interval, st);
-    if (rc) return rc;
-    bump_kernel<<<1, 32, 0, st>>>(counters, RRL_C_QRISK_ROWS, cfg->mf_recovery ? RRL_C_ADAM_T0 + 3 : -1, -1,
-                                  RRL_C_QRISK_UPDATES);
+    bump_kernel<<<1, 32, 0, st>>>(counters, RRL_C_QRISK_ROWS, -1, -1, RRL_C_QRISK_UPDATES);
     RRL_CHECK_LAUNCH();
     return 0;
 }

@@ -201,7 +201,7 @@ class VecEngine(object):
         native.recovery_backward(cfg, ar, cn, self.losses[8:], self._in("qr_eps_rec"), seed=self.seed, stream_id=self.rank)
         self._all_reduce(["recovery"])
         native.recovery_apply(cfg, ar, cn)
-        return 6 + 2 + (10 if self.mf_recovery else 0) + (3 if self.mf_recovery else 2)
+        return 5 + 1 + (8 if self.mf_recovery else 0) + 1     # kernels launched (gpu_launches bookkeeping)
 
     def qrisk_update(self, sample_cfg=None):
         return self._qr_sample(sample_cfg) + self._qr_compute()
@@ -223,7 +223,7 @@ class VecEngine(object):
             dist_utils.all_reduce_sum(f32[native.S_G_LOG_ALPHA:native.S_G_LOG_ALPHA + 1], self.pg)
             dist_utils.all_reduce_sum(f64[native.D_G_LOG_NU:native.D_G_LOG_LAMBDA + 1], self.pg)
         native.sac_apply(cfg, ar, cn)
-        return 10 + 3 + (1 if self.scalar_algos else 0)
+        return 8 + 1 + (1 if self.scalar_algos else 0)
 
     def sac_update(self):
         return self._sac_sample() + self._sac_compute()
