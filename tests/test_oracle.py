@@ -218,3 +218,76 @@ def test_oracle_comparison_branches_match_reference(golden_dir, tag):
             torch.manual_seed(7000 + i)
             a = ag.select_action_sqrl(z["sqrl_sel_s"][i], z["sqrl_sel_eps"][i], eps_safe=float(z["sqrl_sel_thresh"][i]))
             assert np.allclose(a, z["sqrl_sel_action"][i], rtol=1e-5, atol=1e-7), i
+
+
+# ---- model-based recovery (PETS ensemble + CEM, BASELINE config 5) ---------------------------------------------
+def mpc_noise(z, tag):
+    """the planner's random inputs, regenerated from RandomState(8) in the golden script's order."""
+    P = tag + "_"
+    pop, hor, npart = int(z[P + "popsize"]), int(z[P + "plan_hor"]), int(z[P + "npart"])
+    scale = float(z[P + "scale"])
+    rs = np.random.RandomState(int(z[P + "cost_rng_seed"]))
+    ac_seqs = rs.uniform(-scale, scale, (pop, hor * 2)).astype(np.float32)
+    eps = rs.randn(hor, 5, pop * npart // 5, 2).astype(np.float32)
+    zs = np.clip(rs.standard_normal((2, 5, pop, hor * 2)), -2, 2)
+    eps2 = rs.randn(2, 5, hor, 5, pop * npart // 5, 2).astype(np.float32)
+    assert np.isclose(ac_seqs.astype(np.float64).sum(), float(z[P + "cost_ac_seqs_sum"]))
+    assert np.isclose(eps2.astype(np.float64).sum(), float(z[P + "act_eps_sum"]))
+    return ac_seqs, eps, zs, eps2
+
+
+def mpc_oracle(z, za, tag, trained=True):
+    """oracle MPC of golden case `tag`: PtModel init / training from the numpy RNG like the reference, safety
+    critic = oracle Agent after the warm-up updates of the algos fixture."""
+    import torch
+    from oracle import mpc as ompc
+    P = tag + "_"
+    atag = str(z[P + "algos_tag"])
+    ag = algo_oracle_agent(za, atag)
+    for u in range(int(za["n_qr"])):
+        q = "%s_qr%d_" % (atag, u)
+        e_next, _ = algo_noise(za, atag, "qr", 500, u)
+        ag.qrisk_update([za[q + k] for k in ("s", "a", "c", "s2", "m")], e_next, None)
+
+    def value(obs, acs):
+        with torch.no_grad():
+            q1, q2 = ag.qrisk(obs, acs)
+            return torch.max(q1, q2).squeeze()
+
+    sc = np.float32(float(z[P + "scale"]))
+    np.random.seed(int(z[P + "model_seed"]))
+    m = ompc.MPC(-np.ones(2, np.float32) * sc, np.ones(2, np.float32) * sc, int(z[P + "plan_hor"]), int(z[P + "popsize"]),
+                 int(z[P + "num_elites"]), npart=int(z[P + "npart"]), value_func=value)
+    if trained:
+        np.random.seed(int(z[P + "train_seed"]))
+        m.train(z[P + "train_obs"], z[P + "train_acs"], z[P + "train_next"], int(z[P + "train_epochs"]))
+    return m, ag
+
+
+@pytest.mark.parametrize("tag", ["nav", "maze"])
+def test_oracle_mpc_matches_reference(golden_dir, tag):
+    import torch
+    z = np.load(os.path.join(golden_dir, "mpc.npz"))
+    za = np.load(os.path.join(golden_dir, "agent_algos_b64.npz"))
+    P = tag + "_"
+    stride = int(z["stride"])
+    m, _ = mpc_oracle(z, za, tag, trained=False)
+    for n, p in m.model.named():
+        assert np.array_equal(p.detach().numpy().ravel()[::stride], z[P + "init_" + n]), n     # same scipy / numpy stream
+    np.random.seed(int(z[P + "train_seed"]))
+    m.train(z[P + "train_obs"], z[P + "train_acs"], z[P + "train_next"], int(z[P + "train_epochs"]))
+    for n, p in m.model.named():
+        assert np.allclose(p.detach().numpy().ravel()[::stride], z[P + "trained_" + n], rtol=1e-4, atol=1e-6), n
+    with torch.no_grad():
+        xin = torch.from_numpy(np.concatenate([z[P + "train_obs"], z[P + "train_acs"]], 1)[None].repeat(5, 0)).float()
+        mean, var = m.model.forward(xin)
+    assert np.allclose(mean.numpy(), z[P + "fwd_mean"], rtol=1e-4, atol=1e-6)
+    assert np.allclose(var.numpy(), z[P + "fwd_var"], rtol=1e-4, atol=1e-9)
+    ac_seqs, eps, zs, eps2 = mpc_noise(z, tag)
+    costs = m.compile_cost(z[P + "cost_obs"], ac_seqs, eps)
+    assert np.allclose(costs, z[P + "cost_out"], rtol=1e-5, atol=1e-6)
+    for i in range(2):
+        a = m.act(z[P + "act_states"][i], zs[i], eps2[i])
+        assert np.allclose(a, z[P + "act_actions"][i], rtol=1e-5, atol=1e-7)
+        assert np.allclose(m.prev_sol, z[P + "act_prev_sol"][i], rtol=1e-5, atol=1e-7)
+    assert np.allclose(np.array(m.iter_costs), z[P + "act_iter_costs"], rtol=1e-5, atol=1e-6)
