@@ -274,6 +274,58 @@ int rrl_policy_sample(const rrl_agent_config_t* cfg, const float* arena, int net
 /* utils.soft_update / hard_update (utils.py:46-54) on whole nets. */
 int rrl_hard_update(const rrl_agent_config_t* cfg, float* arena, int dst_net, int src_net, void* stream);
 
+/* ------------------------------------------------------------------ model-based recovery (PETS / CEM) ---- */
+/* BASELINE config 5.  The planner of recovery_rl/MPC.py:322-467 + recovery_rl/optimizers.py:73-124 over the
+ * probabilistic ensemble of config/maze.py:23-96 (PtModel; identical class in config/navigation1.py, navigation2.py). */
+typedef struct {
+    int32_t plan_hor;      /* config/maze.py:110 (15), navigation1.py:110 (5)                      */
+    int32_t popsize;       /* config/maze.py:122-127: 400 candidates ...                           */
+    int32_t num_elites;    /*   ... 40 elites                                                      */
+    int32_t npart;         /* config/default.py:109: 20 particles per candidate (multiple of num_nets, MPC.py:160) */
+    int32_t num_nets;      /* config/default.py:91: 5 bootstrap nets                               */
+    int32_t max_iters;     /* 5                                                                    */
+    double  alpha;         /* 0.1: mean/var smoothing, optimizers.py:115-116                        */
+    double  epsilon;       /* 0.001: stop when max(var) <= epsilon, optimizers.py:91                */
+    float   ac_lb[2], ac_ub[2];  /* env.action_space.low / high (MPC.py:119-122)                    */
+    uint64_t seed;         /* Philox key (production RNG mode)                                      */
+    int32_t stream_id;
+    int32_t reserved;
+} rrl_mpc_config_t;
+
+/* Packed ensemble ("dyn image"): hidden width zero-padded to 256, every matrix k-major.  rrl_dyn_pack builds it
+ * from tensors in the reference's layout (lin*_w [nets][in][out], lin*_b [nets][1][out], inputs_mu/sigma [1][4],
+ * max/min_logvar [1][2]; all fp32 device pointers). */
+int64_t rrl_dyn_image_floats(void);
+int rrl_dyn_pack(const float* lin0_w, const float* lin0_b, const float* lin1_w, const float* lin1_b,
+                 const float* lin2_w, const float* lin2_b, const float* lin3_w, const float* lin3_b,
+                 const float* inputs_mu, const float* inputs_sigma, const float* max_logvar,
+                 const float* min_logvar, int hidden, float* image, void* stream);
+
+/* One MPC.act() for n_envs env copies = rrl_mpc_begin, then max_iters x (rrl_mpc_sample, rrl_mpc_rollout,
+ * rrl_mpc_update), then rrl_mpc_finish.  All state is caller-owned device memory:
+ *   prev_sol, mean, var : fp64 [n_envs][plan_hor*2]      active : i32 [n_envs] (CEM loop still running)
+ *   samples : fp32 [n_envs][popsize][plan_hor*2]          row_cost : fp32 [n_envs][popsize][npart]
+ * begin  : mean = prev_sol, var = (ub - lb)^2 / 16                                          (MPC.py:179-181,340)
+ * sample : active &= iter < max_iters && max(var) > epsilon; candidates = z * sqrt(min(var, (dist/2)^2)) + mean as fp32
+ *          z: fp64 [n_envs][popsize][sol] truncated-normal draws in [-2, 2], or NULL (Philox, inverse CDF)  (optimizers.py:91-101)
+ * rollout: every (candidate, particle) through its bootstrap net for plan_hor steps, cost = sum_t max(Q1,Q2)_risk(obs_t, a_t),
+ *          NaN -> 1e6; eps: fp32 [n_envs][plan_hor][nets][popsize*npart/nets][2] or NULL (Philox)           (MPC.py:374-439)
+ *          state: fp64 [2][n_envs] current observations; the safety critic is read from the agent arena
+ * update : cost = mean over particles; elites = num_elites lowest; mean/var <- alpha*old + (1-alpha)*elite stats  (optimizers.py:110-116)
+ * finish : action[e] = mean[e][0:2] (fp64); prev_sol[e] = shift(mean[e]) for envs with mask[e] != 0 (NULL = all) (MPC.py:341-345) */
+int rrl_mpc_begin(const rrl_mpc_config_t* cfg, int64_t n_envs, const double* prev_sol, double* mean, double* var,
+                  int32_t* active, void* stream);
+int rrl_mpc_sample(const rrl_mpc_config_t* cfg, int64_t n_envs, int iter, const double* mean, const double* var,
+                   const double* z, const int64_t* counters, float* samples, int32_t* active, void* stream);
+int rrl_mpc_rollout(const rrl_mpc_config_t* cfg, const rrl_agent_config_t* agent_cfg, const float* arena,
+                    const float* dyn_image, int64_t n_envs, const double* state, const float* samples,
+                    const float* eps, const int32_t* active, int iter, const int64_t* counters, float* row_cost,
+                    void* stream);
+int rrl_mpc_update(const rrl_mpc_config_t* cfg, int64_t n_envs, int iter, const float* samples,
+                   const float* row_cost, const int32_t* active, double* mean, double* var, void* stream);
+int rrl_mpc_finish(const rrl_mpc_config_t* cfg, int64_t n_envs, const double* mean, const uint8_t* mask,
+                   double* prev_sol, double* action, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -64,7 +64,9 @@ enum {
     RRL_DRAW_SAC_CUR = 7,
     RRL_DRAW_QR_NEXT = 8,
     RRL_DRAW_QR_REC = 9,
-    RRL_DRAW_INIT_RESET = 10
+    RRL_DRAW_INIT_RESET = 10,
+    RRL_DRAW_MPC_EPS = 11,  // + 16 * CEM iteration
+    RRL_DRAW_MPC_Z = 12     // + 16 * CEM iteration
 };
 
 struct Philox4 {

@@ -306,3 +306,62 @@ def policy_sample(cfg, arena, net, n, s, eps, action, log_prob=None, mean_action
 def hard_update(cfg, arena, dst_net, src_net, stream=None):
     _check(lib().rrl_hard_update(C.byref(cfg), p(arena, "f32"), int(dst_net), int(src_net), _stream(stream)),
            "rrl_hard_update")
+
+
+# ------------------------------------------------------------------------------------------------
+# model-based recovery (PETS / CEM planner, csrc/mpc.cu)
+# ------------------------------------------------------------------------------------------------
+class MpcConfig(C.Structure):
+    _fields_ = [("plan_hor", C.c_int32), ("popsize", C.c_int32), ("num_elites", C.c_int32), ("npart", C.c_int32),
+                ("num_nets", C.c_int32), ("max_iters", C.c_int32), ("alpha", C.c_double), ("epsilon", C.c_double),
+                ("ac_lb", C.c_float * 2), ("ac_ub", C.c_float * 2), ("seed", C.c_uint64), ("stream_id", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
+def mpc_config(plan_hor, popsize, num_elites, npart=20, num_nets=5, max_iters=5, alpha=0.1, epsilon=0.001,
+               ac_lb=(-1.0, -1.0), ac_ub=(1.0, 1.0), seed=0, stream_id=0):
+    c = MpcConfig()
+    c.plan_hor, c.popsize, c.num_elites, c.npart, c.num_nets, c.max_iters = plan_hor, popsize, num_elites, npart, num_nets, max_iters
+    c.alpha, c.epsilon = float(alpha), float(epsilon)
+    c.ac_lb[0], c.ac_lb[1] = float(ac_lb[0]), float(ac_lb[1])
+    c.ac_ub[0], c.ac_ub[1] = float(ac_ub[0]), float(ac_ub[1])
+    c.seed, c.stream_id = seed & 0xFFFFFFFFFFFFFFFF, stream_id
+    return c
+
+
+def dyn_image_floats():
+    lib().rrl_dyn_image_floats.restype = C.c_int64
+    return int(lib().rrl_dyn_image_floats())
+
+
+def dyn_pack(tensors, hidden, image, stream=None):
+    """tensors: the 12 fp32 CUDA tensors lin0_w, lin0_b, ..., lin3_b, inputs_mu, inputs_sigma, max_logvar, min_logvar."""
+    args = [p(t.contiguous(), "f32") for t in tensors]
+    _check(lib().rrl_dyn_pack(*args, C.c_int(hidden), p(image, "f32"), _stream(stream)), "rrl_dyn_pack")
+
+
+def mpc_begin(cfg, n, prev_sol, mean, var, active, stream=None):
+    _check(lib().rrl_mpc_begin(C.byref(cfg), C.c_int64(n), p(prev_sol, "f64"), p(mean, "f64"), p(var, "f64"), p(active, "i32"),
+                               _stream(stream)), "rrl_mpc_begin")
+
+
+def mpc_sample(cfg, n, it, mean, var, samples, active, z=None, counters=None, stream=None):
+    _check(lib().rrl_mpc_sample(C.byref(cfg), C.c_int64(n), C.c_int(it), p(mean, "f64"), p(var, "f64"), p(z, "f64"),
+                                p(counters, "i64"), p(samples, "f32"), p(active, "i32"), _stream(stream)), "rrl_mpc_sample")
+
+
+def mpc_rollout(cfg, agent_cfg, arena, dyn_image, n, state, samples, row_cost, active=None, eps=None, it=0, counters=None,
+                stream=None):
+    _check(lib().rrl_mpc_rollout(C.byref(cfg), C.byref(agent_cfg), p(arena, "f32"), p(dyn_image, "f32"), C.c_int64(n),
+                                 p(state, "f64"), p(samples, "f32"), p(eps, "f32"), p(active, "i32"), C.c_int(it),
+                                 p(counters, "i64"), p(row_cost, "f32"), _stream(stream)), "rrl_mpc_rollout")
+
+
+def mpc_update(cfg, n, it, samples, row_cost, active, mean, var, stream=None):
+    _check(lib().rrl_mpc_update(C.byref(cfg), C.c_int64(n), C.c_int(it), p(samples, "f32"), p(row_cost, "f32"),
+                                p(active, "i32"), p(mean, "f64"), p(var, "f64"), _stream(stream)), "rrl_mpc_update")
+
+
+def mpc_finish(cfg, n, mean, prev_sol, action, mask=None, stream=None):
+    _check(lib().rrl_mpc_finish(C.byref(cfg), C.c_int64(n), p(mean, "f64"), p(mask, "u8"), p(prev_sol, "f64"),
+                                p(action, "f64"), _stream(stream)), "rrl_mpc_finish")

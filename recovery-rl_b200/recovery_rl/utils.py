@@ -22,5 +22,9 @@ def get_required_argument(dotmap, key, message, default=None):
 
 
 def recovery_config_setup(exp_cfg, logdir):
-    raise NotImplementedError("model-based (PETS/CEM) recovery is outside this build's hot path: pass --MF_recovery "
-                              "(see DESIGN.md, 'Out of scope / next')")
+    """utils.py:84-88: controller configuration of the model-based recovery policy."""
+    from config import create_config
+    from recovery_rl.dotmap_lite import DotMap
+    ctrl_args = DotMap(**{key: val for (key, val) in exp_cfg.ctrl_arg})
+    cfg = create_config(exp_cfg.env_name, "MPC", ctrl_args, exp_cfg.override, logdir)
+    return cfg
