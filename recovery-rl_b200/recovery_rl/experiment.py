@@ -7,7 +7,8 @@ Two execution modes behind the same surface:
     (env.step, SAC, QRiskWrapper, ReplayMemory) whose arithmetic runs in the CUDA kernels;
   * --num_envs N > 1: the vectorised engine (recovery_rl/engine.py) -- N env copies per GPU, the whole
     step replayed as one CUDA graph, per-step host traffic only for the env copies that are logged.
-Model-based (PETS / visual MPC) recovery, image observations and task demos are outside this build.
+Model-based recovery (PETS ensemble + CEM, recovery_rl/MPC.py) runs on the --num_envs 1 path; visual MPC, image
+observations and task demos are outside this build.
 """
 import datetime
 import itertools
@@ -20,7 +21,7 @@ import torch
 
 from recovery_rl.sac import SAC
 from recovery_rl.replay_memory import ReplayMemory, ConstraintReplayMemory
-from recovery_rl.utils import linear_schedule
+from recovery_rl.utils import linear_schedule, recovery_config_setup
 from env.make_utils import register_env, make_env
 
 
@@ -40,8 +41,10 @@ class Experiment:
         print("LOGDIR: ", self.logdir)
         pickle.dump(self.exp_cfg, open(os.path.join(self.logdir, "args.pkl"), "wb"))
         self.num_envs = int(getattr(self.exp_cfg, "num_envs", 1))
-        if self.exp_cfg.use_recovery and not (self.exp_cfg.MF_recovery or self.exp_cfg.Q_sampling_recovery):
-            raise NotImplementedError("model-based (PETS/CEM) recovery is outside this build: pass --MF_recovery")
+        self.mb_recovery = self.exp_cfg.use_recovery and not (self.exp_cfg.MF_recovery or self.exp_cfg.Q_sampling_recovery)
+        if self.mb_recovery and (self.num_envs != 1 or self.exp_cfg.vismpc_recovery):
+            raise NotImplementedError("model-based recovery runs on the --num_envs 1 path (batched planning is available "
+                                      "through recovery_rl.MPC.MPC(n_envs=...)); visual MPC is outside this build")
         if self.exp_cfg.task_demos:
             raise NotImplementedError("--task_demos is outside this build (DESIGN.md, 'next')")
 
@@ -71,15 +74,25 @@ class Experiment:
     def experiment_setup(self):
         torch.manual_seed(self.exp_cfg.seed)
         np.random.seed(self.exp_cfg.seed)
-        register_env(self.exp_cfg.env_name)
-        env = make_env(self.exp_cfg.env_name)
+        if self.mb_recovery:                                       # experiment.py:92-99
+            from recovery_rl.MPC import MPC
+            register_env(self.exp_cfg.env_name)
+            cfg = recovery_config_setup(self.exp_cfg, self.logdir)
+            env = cfg.ctrl_cfg.env
+            recovery_policy = MPC(cfg.ctrl_cfg, seed=self.exp_cfg.seed)
+        else:
+            recovery_policy = None
+            register_env(self.exp_cfg.env_name)
+            env = make_env(self.exp_cfg.env_name)
         self.env = env
-        self.recovery_policy = None
+        self.recovery_policy = recovery_policy
         self.env.seed(self.exp_cfg.seed)
         self.env.action_space.seed(self.exp_cfg.seed)
         if self.num_envs == 1:
             self.agent = self.agent_setup(env)
             self.engine = None
+            if self.mb_recovery:                                   # experiment.py:164-167
+                recovery_policy.update_value_func(self.agent.safety_critic)
         else:
             self.agent = None
             self.engine = self.engine_setup()
@@ -157,6 +170,16 @@ class Experiment:
                 print("CRITIC SAFE UPDATE STEP: ", i)
             self.agent.safety_critic.update_parameters(memory=self.recovery_memory, policy=self.agent.policy,
                                                        batch_size=bs)
+        if self.mb_recovery:                                       # experiment.py:298-305: train the PETS recovery policy
+            self.train_MB_recovery(np.array([d[0] for d in demos]), np.array([d[1] for d in demos]),
+                                   np.array([d[3] for d in demos]), epochs=50)
+
+    def train_MB_recovery(self, states, actions, next_states=None, epochs=50):
+        """experiment.py:251-259."""
+        if next_states is not None:
+            self.recovery_policy.train(states, actions, random=True, next_obs=next_states, epochs=epochs)
+        else:
+            self.recovery_policy.train(states, actions)
 
     # ------------------------------------------------------------------------------------------------
     def run(self):
@@ -188,6 +211,9 @@ class Experiment:
         done = False
         state = self.env.reset()
         train_rollout_info = []
+        ep_states = [state]
+        ep_actions = []
+        ep_constraints = []
         if i_episode % 10 == 0:
             print("SEED: ", self.exp_cfg.seed)
             print("LOGDIR: ", self.logdir)
@@ -223,6 +249,9 @@ class Experiment:
                 if recovery_used and self.exp_cfg.add_both_transitions:
                     self.memory.push(state, real_action, reward, next_state, mask)
             state = next_state
+            ep_states.append(state)
+            ep_actions.append(real_action)
+            ep_constraints.append([info['constraint']])
         if info['constraint']:
             self.num_viols += 1
             if info['recovery']:
@@ -230,6 +259,14 @@ class Experiment:
             else:
                 self.viol_and_no_recovery += 1
         self.num_successes += int(info['success'])
+        # experiment.py:464-478: update the model-based recovery policy with the online data
+        if self.exp_cfg.use_recovery and not self.exp_cfg.disable_online_updates:
+            self.all_ep_data.append({'obs': np.array(ep_states), 'ac': np.array(ep_actions),
+                                     'constraint': np.array(ep_constraints)})
+            if i_episode % self.exp_cfg.recovery_policy_update_freq == 0 and self.mb_recovery:
+                self.train_MB_recovery([ep_data['obs'] for ep_data in self.all_ep_data],
+                                       [ep_data['ac'] for ep_data in self.all_ep_data])
+                self.all_ep_data = []
         print("Episode: {}, total numsteps: {}, episode steps: {}, reward: {}".format(
             i_episode, self.total_numsteps, episode_steps, round(episode_reward, 2)))
         print("Num Violations So Far: %d" % self.num_viols)
@@ -282,7 +319,10 @@ class Experiment:
             action = self.agent.select_action(state, eval=True)
         if recovery_thresh(state, action):
             recovery = True
-            real_action = self.agent.safety_critic.select_action(state)
+            if self.exp_cfg.MF_recovery or self.exp_cfg.Q_sampling_recovery:
+                real_action = self.agent.safety_critic.select_action(state)
+            else:
+                real_action = self.recovery_policy.act(state, 0)
         else:
             recovery = False
             real_action = np.copy(action)

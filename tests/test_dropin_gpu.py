@@ -124,9 +124,10 @@ def test_vectorised_experiment_runs(native, cuda, tmp_path):
 
 
 # the algorithm lines of the reference's scripts/navigation1.sh / maze.sh (flags verbatim, incl. the `--lambda`
-# prefix abbreviation of --lambda_RCPO); the model-based RRL_MB line is outside this build
+# prefix abbreviation of --lambda_RCPO)
 SCRIPT_LINES = {
     "RRL_MF": ["--use_recovery", "--MF_recovery"],
+    "RRL_MB": ["--use_recovery", "--recovery_policy_update_freq", "2"],
     "unconstrained": [],
     "LR": ["--DGD_constraints", "--nu", "5000", "--update_nu"],
     "RSPO": ["--DGD_constraints", "--nu_schedule", "--nu_start", "10000"],
@@ -156,6 +157,10 @@ def test_script_algorithm_lines_run(native, cuda, tmp_path, algo, env_name):
         assert exp.agent.arena.counters[native.C_ADAM_T_NU].item() == exp.updates
     if algo == "RCPO":
         assert exp.agent.arena.counters[native.C_ADAM_T_LAMBDA].item() == exp.updates and exp.agent.lambda_RCPO != 1000
+    if algo == "RRL_MB":        # PETS ensemble trained on the demos + online episodes, CEM planner used for recovery
+        rp = exp.recovery_policy
+        assert rp.has_been_trained and len(rp.train_in) > 600 and np.isfinite(rp.last_train_loss)
+        assert torch.isfinite(rp.dyn_image).all()
 
 
 @pytest.mark.parametrize("algo", ["LR", "RSPO", "RCPO", "RP", "unconstrained"])
