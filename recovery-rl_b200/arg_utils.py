@@ -81,6 +81,9 @@ def get_args(argv=None):
     parser.add_argument('--num_envs', type=int, default=int(os.environ.get('RRL_NUM_ENVS', '1')))
     parser.add_argument('--tensor_cores', type=int, default=int(os.environ.get('RRL_TENSOR_CORES', '1')))
     parser.add_argument('--log_envs', type=int, default=int(os.environ.get('RRL_LOG_ENVS', '1')))
+    parser.add_argument('--mpc_popsize', type=int, default=None,
+                        help='CEM candidates per env copy for the model-based recovery policy at --num_envs > 1 '
+                             '(default: the reference\'s 400; BASELINE config 5 uses 50 x 20 particles)')
     parser.add_argument('--checkpoint_every', type=int, default=0,
                         help='write <logdir>/checkpoint.pt every k episodes (k reports at --num_envs > 1); 0 = off')
     parser.add_argument('--resume', default='', help='checkpoint to load before training')

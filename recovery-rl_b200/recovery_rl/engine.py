@@ -31,7 +31,8 @@ class VecEngine(object):
                  disable_online_updates=False, constraint_reward_penalty=0.0, start_steps=100, seed=0,
                  device="cuda:0", rank=0, world_size=1, process_group=None, host_inputs=False, log_outputs=False,
                  use_tensor_cores=0, maze_substeps=500, dgd=False, update_nu=False, rcpo=False, auto_alpha=False,
-                 nu=0.01, lambda_rcpo=0.01, disable_action_relabeling=False):
+                 nu=0.01, lambda_rcpo=0.01, disable_action_relabeling=False, mb_recovery=False, mpc_popsize=None,
+                 mpc_num_elites=None):
         native.require_cuda()
         self.device = torch.device(device)
         torch.cuda.set_device(self.device)
@@ -120,6 +121,27 @@ class VecEngine(object):
                 action=torch.zeros(n, 2).pin_memory())
         else:
             self.in_dev = {}
+        # model-based recovery (BASELINE config 5): the PETS / CEM planner proposes the recovery action for every env
+        # copy (recovery_rl/MPC.py, csrc/mpc.cu); only the copies whose Q_risk exceeds eps_safe use it
+        self.mpc = None
+        if mb_recovery:
+            if not self.use_recovery or self.mf_recovery:
+                raise ValueError("mb_recovery needs use_recovery=True and mf_recovery=False")
+            from config import create_config
+            from .dotmap_lite import DotMap
+            from .MPC import MPC
+            cc = create_config(env_name, "MPC", DotMap(), [], "").ctrl_cfg
+            if mpc_popsize is not None:
+                cc.opt_cfg.cfg = dict(cc.opt_cfg.cfg, popsize=int(mpc_popsize),
+                                      num_elites=int(mpc_num_elites or max(1, mpc_popsize // 10)))
+            self.mpc = MPC(cc, n_envs=n, seed=self.seed, stream_id=self.rank)
+
+            class _VF(object):
+                arena = self.agent
+            self.mpc.update_value_func(_VF())
+            self.mpc.state = self.state                      # the planner reads the env state in place
+            self.mpc.counters = self.counters                # Philox step counter
+            self.action64 = torch.zeros(n, 2, dtype=torch.float64, device=dev)
         self.graph = None
         self._side = torch.cuda.Stream(device=dev)
         self._ev_fork = torch.cuda.Event()
@@ -145,6 +167,27 @@ class VecEngine(object):
             sc = ACTION_SCALE[self.env_name]
             modules = build_reference_modules(hidden=256, action_scale=(sc, sc))
         self.agent.load_modules(modules)
+
+    def train_mb(self, transitions=None, n_recent=50000, epochs=None):
+        """MPC.train for the engine.  transitions: list of (s, a, c, s', mask) demos (experiment.py:298-305), or None:
+        the most recent `n_recent` transitions of the constraint ring (stands in for experiment.py:464-478, which
+        appends every finished episode; with thousands of env copies the data set is capped to a recent window)."""
+        if self.mpc is None:
+            return
+        if transitions is not None:
+            s = np.array([t[0] for t in transitions]); a = np.array([t[1] for t in transitions])
+            s2 = np.array([t[3] for t in transitions])
+            self.mpc.train(s, a, random=True, next_obs=s2, epochs=50 if epochs is None else epochs)
+            return
+        c = self.counters.cpu()
+        ln, pos = int(c[native.C_CONS_LEN]), int(c[native.C_CONS_POS])
+        k = min(int(n_recent), ln)
+        if k == 0:
+            return
+        idx = (pos - 1 - torch.arange(k, device=self.device)) % self.cons_cap
+        rec = self.cons_ring[idx].cpu().numpy().astype(np.float64)
+        self.mpc.train_in = np.zeros((0, 4)); self.mpc.train_targs = np.zeros((0, 2))     # recent window, not cumulative
+        self.mpc.train(rec[:, 0:2], rec[:, 2:4], random=True, next_obs=rec[:, 5:7], epochs=epochs)
 
     def set_nu(self, nu):
         """the `nu` argument of SAC.update_parameters (experiment.py:406); a device scalar the captured graph reads."""
@@ -261,6 +304,14 @@ class VecEngine(object):
                          self.recovery, self.qrisk, self._in("eps_task"), self._in("eps_rec"), self._in("rand_u"),
                          use_recovery=self.use_recovery, start_steps=self.start_steps, seed=self.seed,
                          stream_id=self.rank)                                      # experiment.py:419
+        a64 = None
+        if self.mpc is not None:                                                   # experiment.py:568-573
+            plan = self.mpc.plan(mask=self.recovery)
+            rec = self.recovery.bool().unsqueeze(1)
+            self.action64.copy_(torch.where(rec, plan, self.action_task.double()))   # MPC actions stay float64
+            self.action_real.copy_(self.action64)
+            a64 = self.action64
+            k += 2 + 3 * self.mpc.optimizer.max_iters
         native.env_step(self.env_cfg, self.action_task if self.relabel else self.action_real, self.action_real,
                         self.state, self.ep_steps, self.ep_return,
                         self.counters, recovery=self.recovery, noise=self._in("env_noise"),
@@ -269,7 +320,7 @@ class VecEngine(object):
                         cons_flags=self.cons_flags if self.uses_qrisk else None,
                         cons_capacity=self.cons_cap if self.uses_qrisk else 0, out_next_state=self.out_next,
                         out_reward=self.out_reward, out_done=self.out_done, out_constraint=self.out_cons,
-                        out_success=self.out_succ)                                 # experiment.py:420-461
+                        out_success=self.out_succ, action_f64=a64)                 # experiment.py:420-461
         native.counters_advance(self.counters, self.n, self.task_cap, self.cons_cap, True, self.uses_qrisk)
         self.launches_per_step = k + 3
         return self.launches_per_step

@@ -42,9 +42,8 @@ class Experiment:
         pickle.dump(self.exp_cfg, open(os.path.join(self.logdir, "args.pkl"), "wb"))
         self.num_envs = int(getattr(self.exp_cfg, "num_envs", 1))
         self.mb_recovery = self.exp_cfg.use_recovery and not (self.exp_cfg.MF_recovery or self.exp_cfg.Q_sampling_recovery)
-        if self.mb_recovery and (self.num_envs != 1 or self.exp_cfg.vismpc_recovery):
-            raise NotImplementedError("model-based recovery runs on the --num_envs 1 path (batched planning is available "
-                                      "through recovery_rl.MPC.MPC(n_envs=...)); visual MPC is outside this build")
+        if self.mb_recovery and self.exp_cfg.vismpc_recovery:
+            raise NotImplementedError("visual MPC (image observations) is outside this build")
         if self.exp_cfg.task_demos:
             raise NotImplementedError("--task_demos is outside this build (DESIGN.md, 'next')")
 
@@ -74,7 +73,7 @@ class Experiment:
     def experiment_setup(self):
         torch.manual_seed(self.exp_cfg.seed)
         np.random.seed(self.exp_cfg.seed)
-        if self.mb_recovery:                                       # experiment.py:92-99
+        if self.mb_recovery and self.num_envs == 1:                # experiment.py:92-99
             from recovery_rl.MPC import MPC
             register_env(self.exp_cfg.env_name)
             cfg = recovery_config_setup(self.exp_cfg, self.logdir)
@@ -132,7 +131,8 @@ class Experiment:
                         log_outputs=getattr(c, "log_envs", 1) > 0, use_tensor_cores=getattr(c, "tensor_cores", 1),
                         dgd=c.DGD_constraints, update_nu=c.update_nu, rcpo=c.RCPO,
                         auto_alpha=bool(c.automatic_entropy_tuning), nu=c.nu, lambda_rcpo=c.lambda_RCPO,
-                        disable_action_relabeling=c.disable_action_relabeling)
+                        disable_action_relabeling=c.disable_action_relabeling, mb_recovery=self.mb_recovery,
+                        mpc_popsize=getattr(c, "mpc_popsize", None))
         eng.init_agent()          # same torch seed on every rank -> identical replicas
         return eng
 
@@ -162,6 +162,8 @@ class Experiment:
         if self.engine is not None:
             self.engine.push_offline(demos)
             self.engine.pretrain_qrisk(self.exp_cfg.critic_safe_pretraining_steps, n_demos=len(self.constraint_demo_data))
+            if self.mb_recovery:
+                self.engine.train_mb(demos)                        # experiment.py:298-305
             return
         for transition in demos:
             self.recovery_memory.push(*transition)
@@ -371,6 +373,9 @@ class Experiment:
                 self.viol_and_recovery, self.viol_and_no_recovery = cn["viol_and_recovery"], cn["viol_and_no_recovery"]
                 self.updates = cn["sac_updates"]
                 eng.set_nu(self.nu_schedule(1 + cn["episodes"] * eng.world))     # experiment.py:406
+                if self.mb_recovery and not c.disable_online_updates and \
+                        (step // report_every) % max(1, c.recovery_policy_update_freq) == 0:
+                    eng.train_mb()                                               # experiment.py:464-478
                 if True:
                     vec_stats.append(cn)
                     if eng.rank == 0:

@@ -112,3 +112,23 @@ def test_planner_batched_envs_equal_single(native, cuda, golden_dir):
         a = ms[e].act(states[e], 0, z=[torch.from_numpy(zs[k][e][None]).to(cuda).contiguous() for k in range(5)],
                       eps=[torch.from_numpy(eps[k][e]).to(cuda).contiguous() for k in range(5)])
         assert np.array_equal(a, act[e]), (e, a, act[e])
+
+
+def test_vectorised_model_based_recovery_runs(native, cuda, tmp_path):
+    """BASELINE config 5 in small: Maze, model-based recovery, N env copies x (popsize x 20) CEM particles through
+    the vector engine (planner inside the captured CUDA graph), ensemble pre-trained on the demos."""
+    import arg_utils
+    from recovery_rl.experiment import Experiment
+    args = arg_utils.get_args(["--env-name", "maze", "--use_recovery", "--gamma_safe", "0.5", "--eps_safe", "0.15",
+                               "--pos_fraction", "0.3", "--num_unsafe_transitions", "1500", "--critic_safe_pretraining_steps", "20",
+                               "--batch_size", "64", "--num_envs", "128", "--mpc_popsize", "20", "--num_steps", "7000",
+                               "--seed", "3", "--logdir", str(tmp_path), "--replay_size", "50000", "--safe_replay_size", "50000",
+                               "--recovery_policy_update_freq", "1"])
+    exp = Experiment(args)
+    stats = exp.run()
+    eng = exp.engine
+    assert eng.mpc is not None and eng.mpc.has_been_trained and eng.graph is not None
+    assert stats[-1]["total_numsteps"] > 7000 and stats[-1]["error"] == 0
+    assert stats[-1]["viol_and_recovery"] + stats[-1]["viol_and_no_recovery"] == stats[-1]["num_viols"]
+    assert torch.isfinite(eng.arena[:eng.agent.grad_off]).all() and torch.isfinite(eng.mpc.dyn_image).all()
+    assert (eng.action_real.abs() <= 0.1 + 1e-6).all()
