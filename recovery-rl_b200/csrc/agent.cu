@@ -16,28 +16,6 @@ namespace {
 // ---------------------------------------------------------------------------------------------
 // grouped forward kernel (training batches and the stand-alone forward entry points)
 // ---------------------------------------------------------------------------------------------
-struct FwdPass {
-    HeadW w;
-    int head;
-    const float* xs;  // [rows][2]
-    const float* xa;  // [rows][2] (n_in == 4)
-    float *h1, *h2;
-    const float* eps;  // [rows][2] or NULL (Philox)
-    uint32_t draw_id;
-    float *out_q, *out_a, *out_logp, *out_mean, *out_raw, *out_eps;
-};
-struct FwdArgs {
-    FwdPass p[10];
-    int n_pass;
-    const int64_t* rows_ptr;
-    int64_t rows_const;
-    ActionSpace sp;
-    uint64_t seed;
-    uint32_t stream_id;
-    const int64_t* counters;
-    int step_counter;  // which counter supplies the Philox step
-};
-
 template <int BM>
 __global__ void __launch_bounds__(kThreads, (BM == 64) ? 2 : 3) mlp_forward_kernel(const __grid_constant__ FwdArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -62,28 +40,7 @@ __global__ void __launch_bounds__(kThreads, (BM == 64) ? 2 : 3) mlp_forward_kern
         if (row < rows) {
             const float4 rv = *reinterpret_cast<const float4*>(S.raw[t]);
             const float raw[4] = {rv.x, rv.y, rv.z, rv.w};
-            if (P.out_raw) *reinterpret_cast<float4*>(P.out_raw + row * 4) = rv;
-            if (P.head == HEAD_Q) {
-                P.out_q[row] = raw[0];
-            } else if (P.head == HEAD_QRISK) {
-                P.out_q[row] = sigmoidf_(raw[0]);
-            } else {
-                float e[2];
-                if (P.eps) {
-                    const float2 ev = reinterpret_cast<const float2*>(P.eps)[row];
-                    e[0] = ev.x; e[1] = ev.y;
-                } else {
-                    philox_eps(A.seed, A.stream_id, (uint64_t)row, (uint64_t)A.counters[A.step_counter], P.draw_id, e);
-                }
-                float a[2], mean_a[2], lp;
-                if (P.head == HEAD_GAUSS) gauss_sample(raw, e, A.sp, a, &lp, mean_a);
-                else stoch_sample(raw, P.w.log_std, e, A.sp, a, mean_a, &lp);
-                if (P.head == HEAD_DET) lp = 0.f;  // DeterministicPolicy.sample returns torch.tensor(0.) (model.py:481)
-                if (P.out_a) reinterpret_cast<float2*>(P.out_a)[row] = make_float2(a[0], a[1]);
-                if (P.out_logp) P.out_logp[row] = lp;
-                if (P.out_mean) reinterpret_cast<float2*>(P.out_mean)[row] = make_float2(mean_a[0], mean_a[1]);
-                if (P.out_eps) reinterpret_cast<float2*>(P.out_eps)[row] = make_float2(e[0], e[1]);
-            }
+            forward_tail(P, A, row, raw);
         }
     }
 }
@@ -733,8 +690,18 @@ __global__ void __launch_bounds__(kThreads) stoch_backward_kernel(const __grid_c
 //     (Adam step counts, update counters) done by the last CTA to finish.
 struct ImgRef {
     int64_t off;  // offset of a 256x256 tensor inside the arena
-    int64_t img;  // offset of its transposed image
+    int64_t img;  // offset of its transposed (k-major) image
+    int64_t tc;   // offset of its fp16 hi/lo tcgen05 operand image
 };
+__device__ __forceinline__ void refresh_images(float* arena, const ImgRef* img, int n_img, int64_t o, float p) {
+    for (int q = 0; q < n_img; ++q) {
+        const int64_t d = o - img[q].off;
+        if (d >= 0 && d < (int64_t)H * H) {
+            arena[img[q].img + (d & (H - 1)) * H + (d >> 8)] = p;
+            tc_image_store(reinterpret_cast<__half*>(arena + img[q].tc), (int)(d >> 8), (int)(d & (H - 1)), p);
+        }
+    }
+}
 struct AdamArgs {
     float* arena;
     int64_t off, count, grad_off, m_off, v_off;
@@ -781,10 +748,7 @@ __global__ void __launch_bounds__(kThreads) adam_kernel(const __grid_constant__ 
             A.arena[A.m_off + o] = m;
             A.arena[A.v_off + o] = v;
             A.arena[o] = p;
-            for (int q = 0; q < A.n_img; ++q) {
-                const int64_t d = o - A.img[q].off;
-                if (d >= 0 && d < (int64_t)H * H) A.arena[A.img[q].img + (d & (H - 1)) * H + (d >> 8)] = p;
-            }
+            refresh_images(A.arena, A.img, A.n_img, o, p);
         }
         if (polyak) {
             const int64_t d0 = o - A.tgt_src_off;
@@ -792,10 +756,7 @@ __global__ void __launch_bounds__(kThreads) adam_kernel(const __grid_constant__ 
                 const int64_t to = A.tgt_off + d0;
                 const float tp = A.arena[to] * omt + p * A.tau;
                 A.arena[to] = tp;
-                for (int q = 0; q < A.n_timg; ++q) {
-                    const int64_t d = to - A.timg[q].off;
-                    if (d >= 0 && d < (int64_t)H * H) A.arena[A.timg[q].img + (d & (H - 1)) * H + (d >> 8)] = tp;
-                }
+                refresh_images(A.arena, A.timg, A.n_timg, to, tp);
             }
         }
     }
@@ -885,10 +846,7 @@ __global__ void __launch_bounds__(kThreads) polyak_kernel(const __grid_constant_
         const float s = A.arena[A.src_off + i];
         const float p = A.tau >= 1.0f ? s : (A.arena[A.dst_off + i] * omt + s * A.tau);
         A.arena[A.dst_off + i] = p;
-        for (int q = 0; q < A.n_img; ++q) {
-            const int64_t d = A.dst_off + i - A.img[q].off;
-            if (d >= 0 && d < (int64_t)H * H) A.arena[A.img[q].img + (d & (H - 1)) * H + (d >> 8)] = p;
-        }
+        refresh_images(A.arena, A.img, A.n_img, A.dst_off + i, p);
     }
 }
 
@@ -943,6 +901,7 @@ ActionSpace action_space(const rrl_agent_config_t* cfg) {
 
 template <int BM>
 int launch_forward(const FwdArgs& A, int64_t max_rows, cudaStream_t st) {
+    if (A.use_tc) return fwd_tc_launch(A, max_rows, st);
     static bool configured = false;
     const size_t smem = sizeof(FwdSmem<BM>);
     if (!configured) {
@@ -957,7 +916,8 @@ int launch_forward(const FwdArgs& A, int64_t max_rows, cudaStream_t st) {
 
 int imgs_of_net(const Layout& L, int net, ImgRef* out) {
     const int heads = (net == RRL_NET_POLICY || net == RRL_NET_RECOVERY) ? 1 : 2;
-    for (int h = 0; h < heads; ++h) out[h] = ImgRef{L.t_off[net][w2_tensor(net, h)], L.img_off[image_index(net, h)]};
+    for (int h = 0; h < heads; ++h)
+        out[h] = ImgRef{L.t_off[net][w2_tensor(net, h)], L.img_off[image_index(net, h)], L.tc_img_off[image_index(net, h)]};
     return heads;
 }
 
@@ -1015,6 +975,7 @@ FwdPass q_pass(const Layout& L, float* arena, int net, int head, const float* xs
     FwdPass p;
     memset(&p, 0, sizeof(p));
     p.w = head_w(L, arena, net, head);
+    p.tc_img = tc_img_of(L, arena, net, head);
     p.head = (net == RRL_NET_QRISK || net == RRL_NET_QRISK_TARGET) ? HEAD_QRISK : HEAD_Q;
     p.xs = xs; p.xa = xa;
     if (slot >= 0) { p.h1 = arena + L.h1[slot]; p.h2 = arena + L.h2[slot]; }
@@ -1231,13 +1192,13 @@ extern "C" int rrl_sac_backward(const rrl_agent_config_t* cfg, float* arena, con
     {  // policy on s' (no grad, sac.py:192-194) and on s (sac.py:216)
         FwdArgs A;
         memset(&A, 0, sizeof(A));
-        A.n_pass = 2; A.rows_ptr = rows_ptr; A.sp = sp; A.seed = seed; A.stream_id = (uint32_t)stream_id;
+        A.n_pass = 2; A.rows_ptr = rows_ptr; A.sp = sp; A.use_tc = cfg->use_tensor_cores; A.seed = seed; A.stream_id = (uint32_t)stream_id;
         A.counters = counters; A.step_counter = RRL_C_SAC_UPDATES;
         FwdPass& p0 = A.p[0];
-        p0.w = pw; p0.head = pol_head; p0.xs = s2; p0.eps = eps_next;
+        p0.w = pw; p0.head = pol_head; p0.xs = s2; p0.eps = eps_next; p0.tc_img = tc_img_of(L, arena, RRL_NET_POLICY, 0);
         p0.draw_id = RRL_DRAW_SAC_NEXT; p0.out_a = R2(R2_NEXT_A); p0.out_logp = RA(RA_NEXT_LOGP);
         FwdPass& p1 = A.p[1];
-        p1.w = pw; p1.head = pol_head; p1.xs = s; p1.eps = eps_cur; p1.draw_id = RRL_DRAW_SAC_CUR;
+        p1.w = pw; p1.head = pol_head; p1.xs = s; p1.eps = eps_cur; p1.draw_id = RRL_DRAW_SAC_CUR; p1.tc_img = p0.tc_img;
         p1.h1 = arena + L.h1[4]; p1.h2 = arena + L.h2[4];
         p1.out_a = R2(R2_PI); p1.out_logp = RA(RA_LOGP); p1.out_raw = R4(R4_RAW_POL); p1.out_eps = R2(R2_EPS_CUR);
         int rc = launch_forward<32>(A, R, st);
@@ -1247,7 +1208,7 @@ extern "C" int rrl_sac_backward(const rrl_agent_config_t* cfg, float* arena, con
        // [+ Q_risk(s, pi) (sac.py:221) for DGD / update_nu, + Q_risk(s, a) (sac.py:203-204) for RCPO]
         FwdArgs A;
         memset(&A, 0, sizeof(A));
-        A.rows_ptr = rows_ptr; A.sp = sp;
+        A.rows_ptr = rows_ptr; A.sp = sp; A.use_tc = cfg->use_tensor_cores;
         int n = 0;
         A.p[n++] = q_pass(L, arena, RRL_NET_CRITIC_TARGET, 0, s2, R2(R2_NEXT_A), -1, RA(RA_QT1));
         A.p[n++] = q_pass(L, arena, RRL_NET_CRITIC_TARGET, 1, s2, R2(R2_NEXT_A), -1, RA(RA_QT2));
@@ -1413,10 +1374,11 @@ extern "C" int rrl_qrisk_backward(const rrl_agent_config_t* cfg, float* arena, c
     {  // a' ~ TASK policy(s')  (qrisk.py:118-120; policy = agent.policy, experiment.py:413)
         FwdArgs A;
         memset(&A, 0, sizeof(A));
-        A.n_pass = 1; A.rows_ptr = rows_ptr; A.sp = sp; A.seed = seed; A.stream_id = (uint32_t)stream_id;
+        A.n_pass = 1; A.rows_ptr = rows_ptr; A.sp = sp; A.use_tc = cfg->use_tensor_cores; A.seed = seed; A.stream_id = (uint32_t)stream_id;
         A.counters = counters; A.step_counter = RRL_C_QRISK_UPDATES;
         FwdPass& p0 = A.p[0];
         p0.w = task_policy_w(L, arena, cfg, &p0.head); p0.xs = s2; p0.eps = eps_next;
+        p0.tc_img = tc_img_of(L, arena, RRL_NET_POLICY, 0);
         RRL_CHECK_ARG(p0.head != HEAD_DET || eps_next, "the Deterministic policy needs its noise as an input");
         p0.draw_id = RRL_DRAW_QR_NEXT; p0.out_a = R2(R2_QR_NEXT_A); p0.out_logp = RA(RA_QR_NEXT_LOGP);
         int rc = launch_forward<32>(A, R, st);
@@ -1425,7 +1387,7 @@ extern "C" int rrl_qrisk_backward(const rrl_agent_config_t* cfg, float* arena, c
     {
         FwdArgs A;
         memset(&A, 0, sizeof(A));
-        A.n_pass = 4; A.rows_ptr = rows_ptr; A.sp = sp;
+        A.n_pass = 4; A.rows_ptr = rows_ptr; A.sp = sp; A.use_tc = cfg->use_tensor_cores;
         A.p[0] = q_pass(L, arena, RRL_NET_QRISK_TARGET, 0, s2, R2(R2_QR_NEXT_A), -1, RA(RA_QR_QT1));
         A.p[1] = q_pass(L, arena, RRL_NET_QRISK_TARGET, 1, s2, R2(R2_QR_NEXT_A), -1, RA(RA_QR_QT2));
         A.p[2] = q_pass(L, arena, RRL_NET_QRISK, 0, s, a, 0, RA(RA_QR_Q1));
@@ -1508,10 +1470,11 @@ extern "C" int rrl_recovery_backward(const rrl_agent_config_t* cfg, float* arena
     {
         FwdArgs A;
         memset(&A, 0, sizeof(A));
-        A.n_pass = 1; A.rows_ptr = rows_ptr; A.sp = sp; A.seed = seed; A.stream_id = (uint32_t)stream_id;
+        A.n_pass = 1; A.rows_ptr = rows_ptr; A.sp = sp; A.use_tc = cfg->use_tensor_cores; A.seed = seed; A.stream_id = (uint32_t)stream_id;
         A.counters = counters; A.step_counter = RRL_C_QRISK_UPDATES;
         FwdPass& p0 = A.p[0];
         p0.w = head_w(L, arena, RRL_NET_RECOVERY, 0); p0.head = HEAD_STOCH; p0.xs = s; p0.eps = eps_rec;
+        p0.tc_img = tc_img_of(L, arena, RRL_NET_RECOVERY, 0);
         p0.draw_id = RRL_DRAW_QR_REC; p0.h1 = arena + L.h1[4]; p0.h2 = arena + L.h2[4];
         p0.out_a = R2(R2_REC_PI); p0.out_logp = RA(RA_REC_LOGP); p0.out_raw = R4(R4_RAW_REC); p0.out_eps = R2(R2_REC_EPS);
         int rc = launch_forward<32>(A, R, st);
@@ -1520,7 +1483,7 @@ extern "C" int rrl_recovery_backward(const rrl_agent_config_t* cfg, float* arena
     {
         FwdArgs A;
         memset(&A, 0, sizeof(A));
-        A.n_pass = 2; A.rows_ptr = rows_ptr; A.sp = sp;
+        A.n_pass = 2; A.rows_ptr = rows_ptr; A.sp = sp; A.use_tc = cfg->use_tensor_cores;
         A.p[0] = q_pass(L, arena, RRL_NET_QRISK, 0, s, R2(R2_REC_PI), 2, RA(RA_REC_Q1));
         A.p[1] = q_pass(L, arena, RRL_NET_QRISK, 1, s, R2(R2_REC_PI), 3, RA(RA_REC_Q2));
         int rc = launch_forward<32>(A, R, st);

@@ -2,6 +2,7 @@
 // weight views into the arena, the head post-processing of the four network families, acting arguments.
 #pragma once
 #include "agent_layout.cuh"
+#include <cuda_fp16.h>
 
 namespace rrl {
 
@@ -14,6 +15,10 @@ enum Head { HEAD_Q = 0, HEAD_QRISK = 1, HEAD_GAUSS = 2, HEAD_STOCH = 3, HEAD_DET
 
 static __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 
+
+struct ActionSpace {
+    float scale[2], bias[2];
+};
 
 // ---------------------------------------------------------------------------------------------
 // weights of one single-head MLP (pointers into the arena)
@@ -78,9 +83,6 @@ inline HeadG head_g(const Layout& L, float* arena, int net, int head) {
 // ---------------------------------------------------------------------------------------------
 // head post-processing
 // ---------------------------------------------------------------------------------------------
-struct ActionSpace {
-    float scale[2], bias[2];
-};
 
 // GaussianPolicy.sample (model.py:325-338)
 static __device__ __forceinline__ void gauss_sample(const float raw[4], const float eps[2], const ActionSpace& sp, float a[2],
@@ -126,6 +128,74 @@ static __device__ __forceinline__ void philox_eps(uint64_t seed, uint32_t stream
     rrl_normal2_f32(p.x, p.y, &e[0], &e[1]);
 }
 
+// ---------------------------------------------------------------------------------------------
+// tcgen05 operand images: element (n, k) of W2[n][k] * 64 as fp16 hi / lo in the UMMA canonical K-major layout
+//   halves index (((c*2 + hl)*4 + kc)*32 + g)*64 + r*8 + e,  c = k/32, kc = (k%32)/8, e = k%8, g = n/8, r = n%8
+// ---------------------------------------------------------------------------------------------
+constexpr float kTcScaleB = 64.0f;
+static __device__ __forceinline__ void tc_image_store(__half* __restrict__ img, int n, int k, float w) {
+    const float s = fmaxf(fminf(w * kTcScaleB, 60000.0f), -60000.0f);
+    const __half h = __float2half_rn(s);
+    const __half l = __float2half_rn(s - __half2float(h));
+    const int c = k >> 5, kc = (k & 31) >> 3, e = k & 7, g = n >> 3, r = n & 7;
+    const size_t base = ((((size_t)c * 2) * 4 + kc) * 32 + g) * 64 + r * 8 + e;
+    img[base] = h;
+    img[base + (size_t)4 * 32 * 64] = l;   // hl = 1
+}
+
+// ---------------------------------------------------------------------------------------------
+// grouped forward passes (training batches and the stand-alone forward entry points)
+// ---------------------------------------------------------------------------------------------
+struct FwdPass {
+    HeadW w;
+    int head;
+    const float* xs;  // [rows][2]
+    const float* xa;  // [rows][2] (n_in == 4)
+    float *h1, *h2;
+    const float* eps;  // [rows][2] or NULL (Philox)
+    uint32_t draw_id;
+    float *out_q, *out_a, *out_logp, *out_mean, *out_raw, *out_eps;
+    const __half* tc_img;  // fp16 hi/lo image of w.W2 (tcgen05 path)
+};
+struct FwdArgs {
+    FwdPass p[10];
+    int n_pass;
+    const int64_t* rows_ptr;
+    int64_t rows_const;
+    ActionSpace sp;
+    uint64_t seed;
+    uint32_t stream_id;
+    const int64_t* counters;
+    int step_counter;  // which counter supplies the Philox step
+    int use_tc;        // run the 256x256 contraction on tcgen05 (agent_tc.cu) instead of the fp32 SIMT tile
+};
+
+// head-specific tail of one row: raw[0..3] = W3 h2 + b3 -> Q value / sigmoid / sampled action + log-prob
+static __device__ __forceinline__ void forward_tail(const FwdPass& P, const FwdArgs& A, int64_t row, const float raw[4]) {
+    if (P.out_raw) *reinterpret_cast<float4*>(P.out_raw + row * 4) = make_float4(raw[0], raw[1], raw[2], raw[3]);
+    if (P.head == HEAD_Q) {
+        P.out_q[row] = raw[0];
+    } else if (P.head == HEAD_QRISK) {
+        P.out_q[row] = sigmoidf_(raw[0]);
+    } else {
+        float e[2];
+        if (P.eps) {
+            const float2 ev = reinterpret_cast<const float2*>(P.eps)[row];
+            e[0] = ev.x; e[1] = ev.y;
+        } else {
+            philox_eps(A.seed, A.stream_id, (uint64_t)row, (uint64_t)A.counters[A.step_counter], P.draw_id, e);
+        }
+        float a[2], mean_a[2], lp;
+        if (P.head == HEAD_GAUSS) gauss_sample(raw, e, A.sp, a, &lp, mean_a);
+        else stoch_sample(raw, P.w.log_std, e, A.sp, a, mean_a, &lp);
+        if (P.head == HEAD_DET) lp = 0.f;  // DeterministicPolicy.sample returns torch.tensor(0.) (model.py:481)
+        if (P.out_a) reinterpret_cast<float2*>(P.out_a)[row] = make_float2(a[0], a[1]);
+        if (P.out_logp) P.out_logp[row] = lp;
+        if (P.out_mean) reinterpret_cast<float2*>(P.out_mean)[row] = make_float2(mean_a[0], mean_a[1]);
+        if (P.out_eps) reinterpret_cast<float2*>(P.out_eps)[row] = make_float2(e[0], e[1]);
+    }
+}
+
 struct ActArgs {
     HeadW pol, qr1, qr2, rec;
     int64_t n;
@@ -146,5 +216,9 @@ struct ActArgs {
 // agent_tc.cu
 int act_tc_launch(const ActArgs& A, const float* arena, const Layout& L, cudaStream_t st);
 int tc_images_launch(float* arena, const Layout& L, cudaStream_t st);
+int fwd_tc_launch(const FwdArgs& A, int64_t max_rows, cudaStream_t st);
+inline const __half* tc_img_of(const Layout& L, const float* arena, int net, int head) {
+    return reinterpret_cast<const __half*>(arena + L.tc_img_off[image_index(net, head)]);
+}
 
 }  // namespace rrl

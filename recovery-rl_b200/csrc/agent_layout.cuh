@@ -4,7 +4,7 @@
 //   [ grads : critic | policy | qrisk | recovery ]      <- ONE contiguous block = the NCCL all-reduce payload
 //   [ adam m: same 4 nets ] [ adam v: same 4 nets ]
 //   [ W2T images: the ten 256x256 hidden matrices transposed to k-major (operand B of the forward GEMM) ]
-//   [ tcgen05 images: fp16 hi/lo split of the four acting matrices in UMMA canonical K-major layout ]
+//   [ tcgen05 images: fp16 hi/lo split of the ten hidden matrices in UMMA canonical K-major layout ]
 //   [ scratch: sampled batches, activations, per-row outputs, losses ]
 //
 // Within a net the tensors follow torch's parameters() order of the reference module
@@ -18,7 +18,7 @@ namespace rrl {
 constexpr int H = 256;  // hidden width (arg_utils.py:89-92); all kernels are specialised for it
 constexpr int kMaxTensors = 14;
 constexpr int kNumImages = 10;
-constexpr int kTcHeads = 4;    // policy, qrisk head 1, qrisk head 2, recovery (the nets the acting kernel runs)
+constexpr int kTcHeads = kNumImages;  // one fp16 hi/lo tcgen05 operand image per 256x256 hidden matrix (index = image_index)
 constexpr int kPassSlots = 7;  // activation slots shared by the SAC and Q_risk updates (5, 6: Q_risk(s, pi) of the DGD branch)
 
 struct TDesc {

@@ -36,7 +36,7 @@ constexpr int B_IMG = H * KCH * 2;       // 16 KB
 constexpr int STAGE_BYTES = 2 * A_IMG + 2 * B_IMG;  // 48 KB: [A hi][A lo][B hi][B lo]
 constexpr int kProd = 512;                // producer/epilogue threads: 4 per row (16 warps)
 constexpr int kTcThreads = kProd + 64;    // + MMA warp + loader warp
-constexpr float SA = 16.0f, SB = 64.0f;  // power-of-two operand scales
+constexpr float SA = 16.0f, SB = kTcScaleB;  // power-of-two operand scales (SB: see tc_image_store)
 constexpr float INV_SCALE = 1.0f / (SA * SB);
 // canonical K-major, no swizzle: core matrix = 8 rows x 16 B (128 B contiguous)
 //   A chunk [128 x 32]: core (kc, g) at (kc * 16 + g) * 128  -> LBO (next core along K) = 2048, SBO (next 8 rows) = 128
@@ -474,17 +474,232 @@ __global__ void __launch_bounds__(kTcThreads, 1) act_tc_kernel(const __grid_cons
     if (warp == kProd / 32) tmem_dealloc(tmem_base, 512);
 }
 
+
+// ---- grouped forward passes of the updates on tcgen05 -------------------------------------------------
+// One CTA = one (pass, 128-row tile): the same producer / MMA / loader / epilogue pipeline as the acting kernel,
+// for the batched forward passes of SAC.update_parameters / QRiskWrapper.update_parameters (rows = batch size).
+// Producers also store h1, the epilogue h2 (fp32, [row][256]) when the backward pass needs them.
+struct FwdTcSmem {
+    unsigned char stage[NSTAGE][STAGE_BYTES];
+    float W1[H][4];
+    float b1[H], b2[H];
+    float w3[4][H];
+    float b3[4];
+    float4 part[4][TM];
+    unsigned long long full[NSTAGE], empty[NSTAGE], acc_full;
+    uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_constant__ FwdArgs A) {
+    extern __shared__ unsigned char smem_raw[];
+    FwdTcSmem& S = *reinterpret_cast<FwdTcSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+    const int64_t rows = A.rows_ptr ? *A.rows_ptr : A.rows_const;
+    const int64_t row0 = (int64_t)blockIdx.x * TM;
+    if (row0 >= rows) return;                       // uniform: before any barrier / TMEM allocation
+    const FwdPass& P = A.p[blockIdx.y];
+    const HeadW& w = P.w;
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    for (int k = t; k < H; k += kTcThreads) {
+        float4 w1 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (w.n_in == 4) {
+            w1 = *reinterpret_cast<const float4*>(w.W1 + k * 4);
+        } else {
+            const float2 v = *reinterpret_cast<const float2*>(w.W1 + k * 2);
+            w1.x = v.x; w1.y = v.y;
+        }
+        w1.x *= SA; w1.y *= SA; w1.z *= SA; w1.w *= SA;
+        *reinterpret_cast<float4*>(S.W1[k]) = w1;
+        S.b1[k] = w.b1[k] * SA;
+        S.b2[k] = w.b2[k];
+        for (int o = 0; o < 4; ++o) {
+            float v = 0.f;
+            if (o < w.na) v = w.W3a[o * H + k];
+            else if (o < w.na + w.nb) v = w.W3b[(o - w.na) * H + k];
+            S.w3[o][k] = v;
+        }
+    }
+    if (t < 4) {
+        float v = 0.f;
+        if (t < w.na) v = w.b3a[t];
+        else if (t < w.na + w.nb) v = w.b3b[t - w.na];
+        S.b3[t] = v;
+    }
+    if (t == 0) {
+        for (int s = 0; s < NSTAGE; ++s) {
+            mbar_init(smem_u32(&S.full[s]), kProd + 1);
+            mbar_init(smem_u32(&S.empty[s]), 1);
+        }
+        mbar_init(smem_u32(&S.acc_full), 1);
+        fence_barrier_init();
+    }
+    if (warp == kProd / 32) {
+        tmem_alloc(smem_u32(&S.tmem_base), 256);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = S.tmem_base;
+
+    if (warp < kProd / 32) {
+        const int q = warp >> 2, r = (warp & 3) * 32 + lane;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+        const int64_t row = row0 + r;
+        const bool live = row < rows;
+        float x0 = 0.f, x1 = 0.f, x2 = 0.f, x3 = 0.f;
+        if (live) {
+            const float2 sv = reinterpret_cast<const float2*>(P.xs)[row];
+            x0 = sv.x; x1 = sv.y;
+            if (P.xa) {
+                const float2 av = reinterpret_cast<const float2*>(P.xa)[row];
+                x2 = av.x; x3 = av.y;
+            }
+        }
+        const bool four = w.n_in == 4;
+        for (int c = 0; c < NCHUNK; ++c) {
+            const int stage = c % NSTAGE;
+            mbar_wait(smem_u32(&S.empty[stage]), ((c / NSTAGE) & 1) ^ 1);
+            unsigned char* a_hi = S.stage[stage];
+            unsigned char* a_lo = a_hi + A_IMG;
+            __align__(16) __half hi[8], lo[8];
+            float hv[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int k = c * KCH + q * 8 + e;
+                const float4 wv = *reinterpret_cast<const float4*>(S.W1[k]);
+                float h = fmaf(wv.x, x0, S.b1[k]);
+                h = fmaf(wv.y, x1, h);
+                if (four) {
+                    h = fmaf(wv.z, x2, h);
+                    h = fmaf(wv.w, x3, h);
+                }
+                h = fmaxf(h, 0.f);
+                hv[e] = h * (1.0f / SA);      // exact: SA is a power of two
+                split_f16(h, &hi[e], &lo[e]);
+            }
+            *reinterpret_cast<uint4*>(a_hi + q * LBO_A + r * 16) = *reinterpret_cast<const uint4*>(hi);
+            *reinterpret_cast<uint4*>(a_lo + q * LBO_A + r * 16) = *reinterpret_cast<const uint4*>(lo);
+            if (P.h1 && live) {
+                float4* dst = reinterpret_cast<float4*>(P.h1 + row * H + c * KCH + q * 8);
+                dst[0] = make_float4(hv[0], hv[1], hv[2], hv[3]);
+                dst[1] = make_float4(hv[4], hv[5], hv[6], hv[7]);
+            }
+            fence_proxy_async();
+            mbar_arrive(smem_u32(&S.full[stage]));
+        }
+        // ---- epilogue: columns [64 q, 64 q + 64) of this row ----
+        mbar_wait(smem_u32(&S.acc_full), 0);
+        tc_fence_after();
+        float out[4] = {0.f, 0.f, 0.f, 0.f};
+        const int n_out = w.na + w.nb;
+#pragma unroll 1
+        for (int cc = 0; cc < 2; ++cc) {
+            float v[32];
+            const int col0 = q * 64 + cc * 32;
+            tmem_ld32(lane_addr + col0, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+                const int i4 = (col0 >> 2) + j4;
+                const float4 b = reinterpret_cast<const float4*>(S.b2)[i4];
+                const float h0 = fmaxf(fmaf(v[4 * j4 + 0], INV_SCALE, b.x), 0.f);
+                const float h1 = fmaxf(fmaf(v[4 * j4 + 1], INV_SCALE, b.y), 0.f);
+                const float h2 = fmaxf(fmaf(v[4 * j4 + 2], INV_SCALE, b.z), 0.f);
+                const float h3 = fmaxf(fmaf(v[4 * j4 + 3], INV_SCALE, b.w), 0.f);
+                if (P.h2 && live) *reinterpret_cast<float4*>(P.h2 + row * H + col0 + 4 * j4) = make_float4(h0, h1, h2, h3);
+#pragma unroll
+                for (int o = 0; o < 4; ++o) {
+                    if (o < n_out) {
+                        const float4 wv = reinterpret_cast<const float4*>(S.w3[o])[i4];
+                        out[o] = fmaf(h3, wv.w, fmaf(h2, wv.z, fmaf(h1, wv.y, fmaf(h0, wv.x, out[o]))));
+                    }
+                }
+            }
+        }
+        tc_fence_before();
+        S.part[q][r] = make_float4(out[0], out[1], out[2], out[3]);
+        asm volatile("bar.sync 1, %0;" ::"n"(kProd) : "memory");
+        if (q == 0 && live) {
+            const float4 p0 = S.part[0][r], p1 = S.part[1][r], p2 = S.part[2][r], p3 = S.part[3][r];
+            float raw[4];
+            raw[0] = ((p0.x + p1.x) + (p2.x + p3.x)) + S.b3[0];
+            raw[1] = ((p0.y + p1.y) + (p2.y + p3.y)) + S.b3[1];
+            raw[2] = ((p0.z + p1.z) + (p2.z + p3.z)) + S.b3[2];
+            raw[3] = ((p0.w + p1.w) + (p2.w + p3.w)) + S.b3[3];
+            forward_tail(P, A, row, raw);
+        }
+    } else if (warp == kProd / 32) {
+        if (lane == 0) {
+            for (int c = 0; c < NCHUNK; ++c) {
+                const int stage = c % NSTAGE;
+                mbar_wait(smem_u32(&S.full[stage]), (c / NSTAGE) & 1);
+                tc_fence_after();
+                const uint32_t a_hi = smem_u32(S.stage[stage]);
+                const uint32_t a_lo = a_hi + A_IMG, b_hi = a_hi + 2 * A_IMG, b_lo = b_hi + B_IMG;
+#pragma unroll
+                for (int j = 0; j < KCH / 16; ++j) {
+                    const uint64_t dah = make_desc(a_hi + j * 2 * LBO_A, LBO_A, SBO);
+                    const uint64_t dal = make_desc(a_lo + j * 2 * LBO_A, LBO_A, SBO);
+                    const uint64_t dbh = make_desc(b_hi + j * 2 * LBO_B, LBO_B, SBO);
+                    const uint64_t dbl = make_desc(b_lo + j * 2 * LBO_B, LBO_B, SBO);
+                    umma_f16(tmem_base, dah, dbh, (c | j) ? 1u : 0u);
+                    umma_f16(tmem_base, dah, dbl, 1u);
+                    umma_f16(tmem_base, dal, dbh, 1u);
+                }
+                umma_commit(smem_u32(&S.empty[stage]));
+            }
+            umma_commit(smem_u32(&S.acc_full));
+        }
+    } else {
+        if (lane == 0) {
+            const unsigned char* img = reinterpret_cast<const unsigned char*>(P.tc_img);
+            for (int c = 0; c < NCHUNK; ++c) {
+                const int stage = c % NSTAGE;
+                mbar_wait(smem_u32(&S.empty[stage]), ((c / NSTAGE) & 1) ^ 1);
+                const uint32_t bar = smem_u32(&S.full[stage]);
+                const uint32_t dst = smem_u32(S.stage[stage]) + 2 * A_IMG;
+                mbar_arrive_expect_tx(bar, 2 * B_IMG);
+                bulk_g2s(dst, img + (size_t)c * 2 * B_IMG, B_IMG, bar);
+                bulk_g2s(dst + B_IMG, img + (size_t)c * 2 * B_IMG + B_IMG, B_IMG, bar);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kProd / 32) tmem_dealloc(tmem_base, 256);
+}
+
 }  // namespace
 
 namespace rrl {
 
+int fwd_tc_launch(const FwdArgs& A, int64_t max_rows, cudaStream_t st) {
+    static bool configured = false;
+    const size_t smem = sizeof(FwdTcSmem) + 128;
+    if (!configured) {
+        RRL_CUDA(cudaFuncSetAttribute(fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    for (int i = 0; i < A.n_pass; ++i)
+        if (!A.p[i].tc_img) { rrl_set_error("fwd_tc_launch: pass %d has no tcgen05 weight image", i); return -2; }
+    dim3 grid((unsigned)((max_rows + TM - 1) / TM), (unsigned)A.n_pass);
+    fwd_tc_kernel<<<grid, kTcThreads, smem, st>>>(A);
+    RRL_CHECK_LAUNCH();
+    return 0;
+}
+
 int tc_images_launch(float* arena, const Layout& L, cudaStream_t st) {
     TcImgArgs A;
-    static const int nets[kTcHeads] = {RRL_NET_POLICY, RRL_NET_QRISK, RRL_NET_QRISK, RRL_NET_RECOVERY};
-    static const int heads[kTcHeads] = {0, 0, 1, 0};
-    for (int i = 0; i < kTcHeads; ++i) {
-        A.W2[i] = arena + L.t_off[nets[i]][w2_tensor(nets[i], heads[i])];
-        A.img[i] = reinterpret_cast<__half*>(arena + L.tc_img_off[i]);
+    static const int nets[6] = {RRL_NET_CRITIC, RRL_NET_CRITIC_TARGET, RRL_NET_POLICY, RRL_NET_QRISK, RRL_NET_QRISK_TARGET,
+                                RRL_NET_RECOVERY};
+    for (int ni = 0; ni < 6; ++ni) {
+        const int net = nets[ni];
+        const int heads = (net == RRL_NET_POLICY || net == RRL_NET_RECOVERY) ? 1 : 2;
+        for (int h = 0; h < heads; ++h) {
+            const int i = image_index(net, h);
+            A.W2[i] = arena + L.t_off[net][w2_tensor(net, h)];
+            A.img[i] = reinterpret_cast<__half*>(arena + L.tc_img_off[i]);
+        }
     }
     tc_images_kernel<<<dim3(H * 32 / 256, kTcHeads), 256, 0, st>>>(A);
     RRL_CHECK_LAUNCH();
@@ -494,11 +709,10 @@ int tc_images_launch(float* arena, const Layout& L, cudaStream_t st) {
 int act_tc_launch(const ActArgs& A, const float* arena, const Layout& L, cudaStream_t st) {
     TcActArgs T;
     T.a = A;
-    // image slots: 0 policy, 1 qrisk h1, 2 qrisk h2, 3 recovery ; pass order: POL, REC, QR1, QR2
-    T.img[PASS_POL] = reinterpret_cast<const __half*>(arena + L.tc_img_off[0]);
-    T.img[PASS_REC] = reinterpret_cast<const __half*>(arena + L.tc_img_off[3]);
-    T.img[PASS_QR1] = reinterpret_cast<const __half*>(arena + L.tc_img_off[1]);
-    T.img[PASS_QR2] = reinterpret_cast<const __half*>(arena + L.tc_img_off[2]);
+    T.img[PASS_POL] = tc_img_of(L, arena, RRL_NET_POLICY, 0);   // pass order: POL, REC, QR1, QR2
+    T.img[PASS_REC] = tc_img_of(L, arena, RRL_NET_RECOVERY, 0);
+    T.img[PASS_QR1] = tc_img_of(L, arena, RRL_NET_QRISK, 0);
+    T.img[PASS_QR2] = tc_img_of(L, arena, RRL_NET_QRISK, 1);
     T.n_pass = A.use_recovery ? 4 : 1;
     static bool configured = false;
     const size_t smem = sizeof(TcSmem) + 128;

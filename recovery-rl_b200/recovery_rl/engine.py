@@ -298,8 +298,7 @@ class VecEngine(object):
         if self.online_qrisk:
             main.wait_event(self._ev_join)
             k += self._qr_compute()                                                # experiment.py:407-415
-        if self.cfg.use_tensor_cores:
-            native.agent_tc_refresh(self.cfg, self.arena); k += 1   # fp16 hi/lo images of the freshly updated weights
+        # (the fp16 hi/lo tcgen05 operand images are refreshed by the optimizer-step kernels themselves)
         native.agent_act(self.cfg, self.arena, self.n, self.state, self.counters, self.action_task, self.action_real,
                          self.recovery, self.qrisk, self._in("eps_task"), self._in("eps_rec"), self._in("rand_u"),
                          use_recovery=self.use_recovery, start_steps=self.start_steps, seed=self.seed,

@@ -67,14 +67,17 @@ def _dev(x, dev):
     return torch.as_tensor(np.ascontiguousarray(x), dtype=torch.float32).to(dev)
 
 
+@pytest.mark.parametrize("tc_updates", [0, 1])
 @pytest.mark.parametrize("tag", ["nav1_b256", "maze_b64"])
-def test_updates_and_acting_vs_reference(native, cuda, golden_dir, tag):
+def test_updates_and_acting_vs_reference(native, cuda, golden_dir, tag, tc_updates):
+    """tc_updates = 1: the forward passes of the updates run their 256x256 contractions on tcgen05 (fp16 hi/lo
+    split, fwd_tc_kernel) and must meet the same 1e-4 bar as the fp32 SIMT tiles."""
     z = np.load(os.path.join(golden_dir, "agent_%s.npz" % tag))
     B = int(z["B"])
     stride = int(z["stride"])
     n_upd = int(z["n_updates"])
     ora = _oracle_agent(z)                       # bit-identical init to the reference (same torch RNG order)
-    ar = _arena(native, cuda, z, B)
+    ar = _arena(native, cuda, z, B, use_tensor_cores=tc_updates)
     ar.load_modules(ora.nets())
     if tag == "nav1_b256":                       # the dumped reference init must equal what we loaded
         for net in ("critic", "policy", "qrisk", "recovery"):
@@ -142,6 +145,7 @@ def test_updates_and_acting_vs_reference(native, cuda, golden_dir, tag):
 
     for tc in (0, 1):
         _check_acting(native, cuda, ar, z, tc)
+    ar.cfg.use_tensor_cores = tc_updates
 
 
 def _check_acting(native, cuda, ar, z, tc):

@@ -24,7 +24,7 @@ def _arena(native, dev, z, tag, B):
                       eps_safe=float(z[P + "eps_safe"]), lr=float(z[P + "lr"]), action_scale=(sc, sc),
                       mf_recovery=bool(int(z[P + "mf_recovery"])), dgd=bool(f[0]), update_nu=bool(f[1]), rcpo=bool(f[2]),
                       auto_alpha=bool(f[3]), deterministic=bool(f[4]), nu=float(z[P + "nu"]),
-                      lambda_rcpo=float(z[P + "lambda_RCPO"]))
+                      lambda_rcpo=float(z[P + "lambda_RCPO"]), use_tensor_cores=1)   # update forwards on tcgen05
 
 
 def _pad_det(mods):
