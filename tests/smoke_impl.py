@@ -14,7 +14,8 @@ def _close(a, b, what, rtol=1e-4, atol=1e-5):
         raise AssertionError("%s: %d/%d mismatches, max abs err %.3e" % (what, bad.sum(), bad.size, np.abs(a - b).max()))
 
 
-def run(env_name="navigation1", n=512, B=64, steps=4, seed=3, verbose=True):
+def run(env_name="navigation1", n=512, B=64, steps=4, seed=3, verbose=True, gamma_safe=0.8, eps_safe=0.3, pos_fraction=-1.0,
+        replay=8192, demos_n=400, tensor_cores=0):
     from oracle import envs as oenvs
     from oracle.agent import Agent
     from recovery_rl import native
@@ -25,15 +26,16 @@ def run(env_name="navigation1", n=512, B=64, steps=4, seed=3, verbose=True):
     sc = ACTION_SCALE[env_name]
     torch.manual_seed(seed)
     np.random.seed(seed)
-    ora = Agent(action_scale=(np.float32(sc),) * 2, gamma_safe=0.8, eps_safe=0.3)
-    eng = VecEngine(env_name, n, batch_size=B, replay_size=8192, safe_replay_size=8192, gamma_safe=0.8, eps_safe=0.3,
-                    seed=seed, host_inputs=True, start_steps=0)
+    ora = Agent(action_scale=(np.float32(sc),) * 2, gamma_safe=gamma_safe, eps_safe=eps_safe)
+    eng = VecEngine(env_name, n, batch_size=B, replay_size=max(replay, 2 * n), safe_replay_size=max(replay, 2 * n),
+                    gamma_safe=gamma_safe, eps_safe=eps_safe, pos_fraction=pos_fraction, seed=seed, host_inputs=True,
+                    start_steps=0, use_tensor_cores=tensor_cores)
     eng.init_agent(ora.nets())
     rs = np.random.RandomState(seed)
     if kind == oenvs.MAZE:
-        demos = oenvs.maze_offline_data(400, rs)
+        demos = oenvs.maze_offline_data(demos_n, rs)
     else:
-        demos = oenvs.nav_offline_data(kind, 400)
+        demos = oenvs.nav_offline_data(kind, demos_n)
     eng.push_offline(demos)
     eng.pretrain_qrisk(3, n_demos=len(demos))
     # mirror the pre-trained weights into the oracle so that both sides start the rollout identically
@@ -65,7 +67,7 @@ def run(env_name="navigation1", n=512, B=64, steps=4, seed=3, verbose=True):
             L = ora.sac_update(batch, inp["sac_eps_next"], inp["sac_eps_cur"], before["sac_updates"])
             _close(out["losses"][:3].numpy(), L[:3], "SAC losses", atol=1e-4)
             assert cn["sac_updates"] == before["sac_updates"] + 1
-            if before["cons_len"] > B:
+            if cn["qrisk_updates"] > before["qrisk_updates"]:     # the online gate (experiment.py:407-410) opened
                 batch = [a.scratch(k, w)[:B].cpu().numpy() for k, w in (("qr_s", 2), ("qr_a", 2), ("qr_c", None),
                                                                          ("qr_s2", 2), ("qr_m", None))]
                 Lq = ora.qrisk_update(batch, inp["qr_eps_next"], inp["qr_eps_rec"])
@@ -75,11 +77,11 @@ def run(env_name="navigation1", n=512, B=64, steps=4, seed=3, verbose=True):
         else:
             assert cn["sac_updates"] == before["sac_updates"]
         # ---- composite action (experiment.py:546-577) ----
-        a_task, a_real, rec, qv = ora.act(state, inp["eps_task"], inp["eps_rec"], eps_safe=0.3)
+        a_task, a_real, rec, qv = ora.act(state, inp["eps_task"], inp["eps_rec"], eps_safe=eps_safe)
         _close(eng.action_task.cpu().numpy(), a_task, "task action")
         _close(eng.qrisk.cpu().numpy(), qv, "Q_risk value")
         g_rec = out["recovery"].numpy().astype(bool)
-        sure = np.abs(qv - 0.3) > 1e-4
+        sure = np.abs(qv - eps_safe) > 1e-4
         assert np.array_equal(g_rec[sure], rec[sure]), "recovery flags"
         same = g_rec == rec
         _close(out["action"].numpy()[same], a_real[same], "executed action")

@@ -22,6 +22,25 @@ def test_vector_step_matches_oracle(native, cuda, env_name):
     assert _smoke().run(env_name=env_name, n=384, B=64, steps=4, seed=5, verbose=False)
 
 
+# BASELINE.json configs 2-4 at their own sizes: every stage of the vector step against the oracle
+BASELINE_CASES = {
+    "C2_nav1_4096_b256": dict(env_name="navigation1", n=4096, B=256, gamma_safe=0.8, eps_safe=0.3, demos_n=2000),
+    "C3_nav2_8192_b1024": dict(env_name="navigation2", n=8192, B=1024, gamma_safe=0.65, eps_safe=0.2, demos_n=4000),
+    "C4_maze_shard_8192_b256": dict(env_name="maze", n=8192, B=256, gamma_safe=0.5, eps_safe=0.15, pos_fraction=0.3,
+                                    demos_n=2000),
+    "C4_maze_65536_b256": dict(env_name="maze", n=65536, B=256, gamma_safe=0.5, eps_safe=0.15, pos_fraction=0.3,
+                               demos_n=2000, steps=2),
+}
+
+
+@pytest.mark.parametrize("tensor_cores", [0, 1])
+@pytest.mark.parametrize("case", sorted(BASELINE_CASES))
+def test_baseline_configs_match_oracle(native, cuda, case, tensor_cores):
+    kw = dict(steps=3, seed=11, verbose=False, tensor_cores=tensor_cores)
+    kw.update(BASELINE_CASES[case])
+    assert _smoke().run(**kw)
+
+
 def test_graph_replay_equals_eager(native, cuda):
     """the captured CUDA graph replays to exactly the state an eager run reaches (Philox mode, same seed)."""
     from recovery_rl.engine import VecEngine
