@@ -147,21 +147,6 @@ __global__ void __launch_bounds__(kThreads, 2) act_kernel(const __grid_constant_
 //     DATA  : A(k = hidden, m = row) = dh2[m][k], B = W2 [H][H], C = dh1 [row][H] masked by h1 > 0
 //     WEIGHT: A(k = row, m = out unit) = dh2[k][m], B = h1 [rows][H], C = gW2 [H][H]; the same CTAs also reduce
 //             gb2[m] = sum_r dh2[r][m], gW3[o][m] = sum_r dout[r][o] h2[r][m] and (m0 == 0) gb3[o] = sum_r dout[r][o]
-struct GemmPass {
-    const float* dout;  // [rows][stride]
-    int stride, n_out, na;
-    const float *W3a, *W3b, *h2;
-    const float* B;
-    int k_is_rows;      // K = rows (WEIGHT) else K = H
-    const float* mask;  // DATA: h1
-    float* C;
-    float *gW3a, *gW3b, *gb3a, *gb3b, *gb2;  // WEIGHT only
-};
-struct GemmArgs {
-    GemmPass p[8];
-    const int64_t* rows_ptr;
-};
-
 __global__ void __launch_bounds__(kThreads) gemm_stream_kernel(const __grid_constant__ GemmArgs G) {
     constexpr int BM = 32;
     const int64_t rows = *G.rows_ptr;
@@ -692,6 +677,7 @@ struct ImgRef {
     int64_t off;  // offset of a 256x256 tensor inside the arena
     int64_t img;  // offset of its transposed (k-major) image
     int64_t tc;   // offset of its fp16 hi/lo tcgen05 operand image
+    int64_t tcT;  // ... and of the image of its transpose
 };
 __device__ __forceinline__ void refresh_images(float* arena, const ImgRef* img, int n_img, int64_t o, float p) {
     for (int q = 0; q < n_img; ++q) {
@@ -699,6 +685,7 @@ __device__ __forceinline__ void refresh_images(float* arena, const ImgRef* img, 
         if (d >= 0 && d < (int64_t)H * H) {
             arena[img[q].img + (d & (H - 1)) * H + (d >> 8)] = p;
             tc_image_store(reinterpret_cast<__half*>(arena + img[q].tc), (int)(d >> 8), (int)(d & (H - 1)), p);
+            tc_image_store(reinterpret_cast<__half*>(arena + img[q].tcT), (int)(d & (H - 1)), (int)(d >> 8), p);
         }
     }
 }
@@ -917,7 +904,8 @@ int launch_forward(const FwdArgs& A, int64_t max_rows, cudaStream_t st) {
 int imgs_of_net(const Layout& L, int net, ImgRef* out) {
     const int heads = (net == RRL_NET_POLICY || net == RRL_NET_RECOVERY) ? 1 : 2;
     for (int h = 0; h < heads; ++h)
-        out[h] = ImgRef{L.t_off[net][w2_tensor(net, h)], L.img_off[image_index(net, h)], L.tc_img_off[image_index(net, h)]};
+        out[h] = ImgRef{L.t_off[net][w2_tensor(net, h)], L.img_off[image_index(net, h)], L.tc_img_off[image_index(net, h)],
+                        L.tc_imgT_off[image_index(net, h)]};
     return heads;
 }
 
@@ -967,6 +955,15 @@ int launch_polyak(const Layout& L, float* arena, const int64_t* counters, int ds
     A.n_img = imgs_of_net(L, dst, A.img);
     const int blocks = (int)((A.count + kThreads * 4 - 1) / (kThreads * 4));
     polyak_kernel<<<blocks, kThreads, 0, st>>>(A);
+    RRL_CHECK_LAUNCH();
+    return 0;
+}
+
+int launch_gemm(GemmArgs& G, int n_pass, int mt, int64_t max_rows, int use_tc, cudaStream_t st) {
+    G.n_pass = n_pass;
+    G.use_tc = use_tc;
+    if (use_tc) return bwd_tc_launch(G, max_rows, st);
+    gemm_stream_kernel<<<dim3(mt, n_pass), kThreads, 0, st>>>(G);
     RRL_CHECK_LAUNCH();
     return 0;
 }
@@ -1256,7 +1253,7 @@ extern "C" int rrl_sac_backward(const rrl_agent_config_t* cfg, float* arena, con
             GemmPass& p = G.p[n++];
             const HeadW& w = q < 4 ? ((q & 1) ? c2 : c1) : ((q & 1) ? k2 : k1);
             p.dout = dout[q]; p.stride = 1; p.n_out = 1; p.na = 1; p.W3a = w.W3a; p.h2 = arena + L.h2[slot[q]];
-            p.B = w.W2; p.k_is_rows = 0; p.mask = arena + L.h1[slot[q]]; p.C = arena + L.dh1[slot[q]];
+            p.B = w.W2; p.tc_imgT = w.tc_imgT; p.k_is_rows = 0; p.mask = arena + L.h1[slot[q]]; p.C = arena + L.dh1[slot[q]];
         }
         for (int q = 0; q < 2; ++q) {
             GemmPass& p = G.p[n++];
@@ -1267,8 +1264,7 @@ extern "C" int rrl_sac_backward(const rrl_agent_config_t* cfg, float* arena, con
             p.gW3a = g.W3a; p.gb3a = g.b3a; p.gb2 = g.b2;
         }
         const int mt = (int)((R > H ? R : H) / 32);
-        gemm_stream_kernel<<<dim3(mt, n), kThreads, 0, st>>>(G);
-        RRL_CHECK_LAUNCH();
+        { int rc = launch_gemm(G, n, mt, R, cfg->use_tensor_cores, st); if (rc) return rc; }
     }
     {  // layer-1 backward: weight grads for (s, a); d/d(pi) for (s, pi)
         L1BwdArgs A;
@@ -1312,13 +1308,12 @@ extern "C" int rrl_sac_backward(const rrl_agent_config_t* cfg, float* arena, con
             p.dout = R4(R4_DRAW_POL); p.stride = 4; p.n_out = det ? 2 : 4; p.na = 2; p.W3a = pw.W3a; p.W3b = pw.W3b;
             p.h2 = arena + L.h2[4];
         }
-        G.p[0].B = pw.W2; G.p[0].mask = arena + L.h1[4]; G.p[0].C = arena + L.dh1[4];
+        G.p[0].B = pw.W2; G.p[0].tc_imgT = pw.tc_imgT; G.p[0].mask = arena + L.h1[4]; G.p[0].C = arena + L.dh1[4];
         G.p[1].B = arena + L.h1[4]; G.p[1].k_is_rows = 1; G.p[1].C = pg.W2;
         G.p[1].gW3a = pg.W3a; G.p[1].gb3a = pg.b3a; G.p[1].gb2 = pg.b2;
         if (!det) { G.p[1].gW3b = pg.W3b; G.p[1].gb3b = pg.b3b; }
         const int mt = (int)((R > H ? R : H) / 32);
-        gemm_stream_kernel<<<dim3(mt, 2), kThreads, 0, st>>>(G);
-        RRL_CHECK_LAUNCH();
+        { int rc = launch_gemm(G, 2, mt, R, cfg->use_tensor_cores, st); if (rc) return rc; }
     }
     {
         L1BwdArgs A;
@@ -1414,15 +1409,14 @@ extern "C" int rrl_qrisk_backward(const rrl_agent_config_t* cfg, float* arena, c
             const HeadG& g = q ? g2 : g1;
             GemmPass& p = G.p[q];
             p.dout = q ? RA(RA_QR_DQ2) : RA(RA_QR_DQ1); p.stride = 1; p.n_out = 1; p.na = 1; p.W3a = w.W3a;
-            p.h2 = arena + L.h2[q]; p.B = w.W2; p.mask = arena + L.h1[q]; p.C = arena + L.dh1[q];
+            p.h2 = arena + L.h2[q]; p.B = w.W2; p.tc_imgT = w.tc_imgT; p.mask = arena + L.h1[q]; p.C = arena + L.dh1[q];
             GemmPass& ww = G.p[2 + q];
             ww = p;
             ww.B = arena + L.h1[q]; ww.k_is_rows = 1; ww.mask = nullptr; ww.C = g.W2;
             ww.gW3a = g.W3a; ww.gb3a = g.b3a; ww.gb2 = g.b2;
         }
         const int mt = (int)((R > H ? R : H) / 32);
-        gemm_stream_kernel<<<dim3(mt, 4), kThreads, 0, st>>>(G);
-        RRL_CHECK_LAUNCH();
+        { int rc = launch_gemm(G, 4, mt, R, cfg->use_tensor_cores, st); if (rc) return rc; }
     }
     {
         L1BwdArgs A;
@@ -1504,10 +1498,10 @@ extern "C" int rrl_recovery_backward(const rrl_agent_config_t* cfg, float* arena
         for (int q = 0; q < 2; ++q) {
             GemmPass& p = G.p[q];
             p.dout = q ? RA(RA_REC_DQ2) : RA(RA_REC_DQ1); p.stride = 1; p.n_out = 1; p.na = 1; p.W3a = (q ? c2 : c1).W3a;
-            p.h2 = arena + L.h2[2 + q]; p.B = (q ? c2 : c1).W2; p.mask = arena + L.h1[2 + q]; p.C = arena + L.dh1[2 + q];
+            p.h2 = arena + L.h2[2 + q]; p.B = (q ? c2 : c1).W2; p.tc_imgT = (q ? c2 : c1).tc_imgT;
+            p.mask = arena + L.h1[2 + q]; p.C = arena + L.dh1[2 + q];
         }
-        gemm_stream_kernel<<<dim3((int)(R / 32), 2), kThreads, 0, st>>>(G);
-        RRL_CHECK_LAUNCH();
+        { int rc = launch_gemm(G, 2, (int)(R / 32), R, cfg->use_tensor_cores, st); if (rc) return rc; }
     }
     {
         L1BwdArgs A;
@@ -1538,12 +1532,11 @@ extern "C" int rrl_recovery_backward(const rrl_agent_config_t* cfg, float* arena
             GemmPass& p = G.p[q];
             p.dout = R4(R4_DRAW_REC); p.stride = 4; p.n_out = 2; p.na = 2; p.W3a = pw.W3a; p.h2 = arena + L.h2[4];
         }
-        G.p[0].B = pw.W2; G.p[0].mask = arena + L.h1[4]; G.p[0].C = arena + L.dh1[4];
+        G.p[0].B = pw.W2; G.p[0].tc_imgT = pw.tc_imgT; G.p[0].mask = arena + L.h1[4]; G.p[0].C = arena + L.dh1[4];
         G.p[1].B = arena + L.h1[4]; G.p[1].k_is_rows = 1; G.p[1].C = pg.W2;
         G.p[1].gW3a = pg.W3a; G.p[1].gb3a = pg.b3a; G.p[1].gb2 = pg.b2;
         const int mt = (int)((R > H ? R : H) / 32);
-        gemm_stream_kernel<<<dim3(mt, 2), kThreads, 0, st>>>(G);
-        RRL_CHECK_LAUNCH();
+        { int rc = launch_gemm(G, 2, mt, R, cfg->use_tensor_cores, st); if (rc) return rc; }
     }
     {
         L1BwdArgs A;

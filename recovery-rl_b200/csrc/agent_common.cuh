@@ -26,6 +26,7 @@ struct ActionSpace {
 struct HeadW {
     const float *W1, *b1, *W2, *W2T, *b2, *W3a, *b3a, *W3b, *b3b, *log_std;
     int n_in, na, nb;  // inputs (2|4); rows of W3a / W3b
+    const __half *tc_img, *tc_imgT;  // fp16 hi/lo tcgen05 operand images of W2 and W2^T
 };
 struct HeadG {  // gradient pointers (same shapes); NULL = not needed
     float *W1, *b1, *W2, *b2, *W3a, *b3a, *W3b, *b3b, *log_std;
@@ -51,6 +52,8 @@ inline HeadW head_w(const Layout& L, const float* arena, int net, int head) {
         w.n_in = 4; w.na = 1; w.nb = 0;
     }
     w.W2T = arena + L.img_off[image_index(net, head)];
+    w.tc_img = reinterpret_cast<const __half*>(arena + L.tc_img_off[image_index(net, head)]);
+    w.tc_imgT = reinterpret_cast<const __half*>(arena + L.tc_imgT_off[image_index(net, head)]);
     return w;
 }
 // the task policy as configured: GaussianPolicy (two heads) or, with RRL_ALGO_DETERMINISTIC, DeterministicPolicy
@@ -220,5 +223,33 @@ int fwd_tc_launch(const FwdArgs& A, int64_t max_rows, cudaStream_t st);
 inline const __half* tc_img_of(const Layout& L, const float* arena, int net, int head) {
     return reinterpret_cast<const __half*>(arena + L.tc_img_off[image_index(net, head)]);
 }
+inline const __half* tc_imgT_of(const Layout& L, const float* arena, int net, int head) {
+    return reinterpret_cast<const __half*>(arena + L.tc_imgT_off[image_index(net, head)]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward GEMM passes (head backward fused): see gemm_stream_kernel (agent.cu) / bwd_tc_kernel (agent_tc.cu)
+//     DATA  : dh1[row][n] = (sum_k dh2[row][k] W2[k][n]) * relu'(h1[row][n])
+//     WEIGHT: gW2[m][n] = sum_row dh2[row][m] h1[row][n];  gb2, gW3, gb3 from the same staged dh2 / h2 / dout
+// with dh2[row][k] = (sum_o dout[row][o] W3[o][k]) * relu'(h2[row][k]) rebuilt on the fly.
+// ---------------------------------------------------------------------------------------------
+struct GemmPass {
+    const float* dout;  // [rows][stride]
+    int stride, n_out, na;
+    const float *W3a, *W3b, *h2;
+    const float* B;     // SIMT: W2 [H][H] (DATA) or h1 [rows][H] (WEIGHT)
+    int k_is_rows;      // K = rows (WEIGHT) else K = H (DATA)
+    const float* mask;  // DATA: h1
+    float* C;
+    float *gW3a, *gW3b, *gb3a, *gb3b, *gb2;  // WEIGHT only
+    const __half* tc_imgT;  // DATA on tcgen05: fp16 hi/lo image of W2^T
+};
+struct GemmArgs {
+    GemmPass p[8];
+    const int64_t* rows_ptr;
+    int n_pass;
+    int use_tc;
+};
+int bwd_tc_launch(const GemmArgs& G, int64_t max_rows, cudaStream_t st);
 
 }  // namespace rrl

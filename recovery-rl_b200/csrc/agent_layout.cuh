@@ -81,6 +81,7 @@ struct Layout {
     int64_t grad_off, m_off, v_off;
     int64_t img_off[kNumImages];
     int64_t tc_img_off[kTcHeads];          // fp16 hi/lo operand images for tcgen05 (agent_tc.cu), 65536 floats each
+    int64_t tc_imgT_off[kTcHeads];         // the same for W2^T (operand B of the backward dh1 = dh2 W2)
     int64_t R;  // max_batch
     // scratch
     int64_t batch_off[2][5];               // [sac|qr][s,a,r,s2,m]
@@ -169,6 +170,10 @@ inline Layout make_layout(const rrl_agent_config_t* cfg) {
     for (int i = 0; i < kTcHeads; ++i) {
         L.tc_img_off[i] = off;
         off += (int64_t)H * H;  // 2 images (hi, lo) x 65536 halves = 65536 floats
+    }
+    for (int i = 0; i < kTcHeads; ++i) {
+        L.tc_imgT_off[i] = off;
+        off += (int64_t)H * H;
     }
     const int64_t R = L.R;
     static const char* bn[2][5] = {{"sac_s", "sac_a", "sac_r", "sac_s2", "sac_m"}, {"qr_s", "qr_a", "qr_c", "qr_s2", "qr_m"}};

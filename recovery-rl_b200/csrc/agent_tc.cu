@@ -669,6 +669,308 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
     if (warp == kProd / 32) tmem_dealloc(tmem_base, 256);
 }
 
+
+// ---- backward GEMMs of the updates on tcgen05 (head backward fused) -------------------------------------
+// DATA   CTA (128-row tile): A = dh2 tile (rebuilt by the producers from h2 / dout / W3, scaled per ROW by a power
+//        of two so that fp16 hi/lo covers it), B = image of W2^T streamed with cp.async.bulk, D -> dh1 (masked by h1).
+// WEIGHT CTA (128 out-units m): A[m][k = row] = dh2[row][m] (scaled per COLUMN m), B[n][k = row] = h1[row][n] * 16,
+//        both written transposed into the canonical K-major layout by the producers, D -> gW2; the A producers also
+//        reduce gb2 / gW3 (and the m-tile 0 CTA gb3) deterministically.
+struct BwdTcSmem {
+    unsigned char stage[NSTAGE][STAGE_BYTES];
+    float w3[4][H];
+    float red[kProd][6];            // WEIGHT: per-thread partial sums (gb2, gW3[0..3])
+    float wmax[4], dmax[4], gb3[4];
+    float red4[kProd / 32][8];
+    unsigned long long full[NSTAGE], empty[NSTAGE], acc_full;
+    uint32_t tmem_base;
+};
+
+__device__ __forceinline__ float pow2_scale(float bound) {
+    // largest power of two s with s * bound <= 8192 (fp16 max 65504; hi/lo split keeps ~22 bits below that)
+    if (!(bound > 0.f) || !isfinite(bound)) return 1.0f;
+    int e;
+    frexpf(bound, &e);                 // bound = f * 2^e, f in [0.5, 1)
+    e = 13 - e;
+    e = e > 100 ? 100 : (e < -100 ? -100 : e);
+    return ldexpf(1.0f, e);
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const __grid_constant__ GemmArgs G) {
+    extern __shared__ unsigned char smem_raw[];
+    BwdTcSmem& S = *reinterpret_cast<BwdTcSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+    const int64_t rows = *G.rows_ptr;
+    if (rows <= 0) return;
+    const GemmPass& P = G.p[blockIdx.y];
+    const bool weight = P.k_is_rows != 0;
+    const int tile = blockIdx.x;
+    if (weight ? (tile >= H / TM) : ((int64_t)tile * TM >= rows)) return;   // uniform exit
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const int n_chunks = weight ? (int)((rows + KCH - 1) / KCH) : NCHUNK;
+
+    // ---- setup ----
+    for (int k = t; k < H; k += kTcThreads)
+#pragma unroll
+        for (int o = 0; o < 4; ++o)
+            S.w3[o][k] = o < P.na ? P.W3a[o * H + k] : (o < P.n_out ? P.W3b[(o - P.na) * H + k] : 0.f);
+    if (t == 0) {
+        for (int s = 0; s < NSTAGE; ++s) {
+            mbar_init(smem_u32(&S.full[s]), weight ? kProd : kProd + 1);
+            mbar_init(smem_u32(&S.empty[s]), 1);
+        }
+        mbar_init(smem_u32(&S.acc_full), 1);
+        fence_barrier_init();
+    }
+    if (warp == kProd / 32) {
+        tmem_alloc(smem_u32(&S.tmem_base), 256);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = S.tmem_base;
+    // column maxima of |W3| (DATA: per-row bound) / maxima and sums of dout over the batch (WEIGHT: per-column bound, gb3)
+    if (warp < 4) {
+        const int o = warp;
+        float m = 0.f, dm = 0.f, ds = 0.f;
+        if (o < P.n_out) {
+            for (int k = lane; k < H; k += 32) m = fmaxf(m, fabsf(S.w3[o][k]));
+            if (weight)
+                for (int64_t r = lane; r < rows; r += 32) {
+                    const float d = P.dout[r * P.stride + o];
+                    dm = fmaxf(dm, fabsf(d));
+                    ds += d;
+                }
+        }
+#pragma unroll
+        for (int sft = 16; sft > 0; sft >>= 1) {
+            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, sft));
+            dm = fmaxf(dm, __shfl_xor_sync(0xffffffffu, dm, sft));
+            ds += __shfl_xor_sync(0xffffffffu, ds, sft);
+        }
+        if (lane == 0) { S.wmax[o] = m; S.dmax[o] = dm; S.gb3[o] = ds; }
+    }
+    __syncthreads();
+
+    if (warp < kProd / 32) {
+        const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+        if (!weight) {
+            // ================= DATA: 4 threads per row (q = quarter of the 32-wide k chunk) =================
+            const int q = warp >> 2, r = (warp & 3) * 32 + lane;
+            const int64_t row = (int64_t)tile * TM + r;
+            const bool live = row < rows;
+            float d[4] = {0.f, 0.f, 0.f, 0.f};
+            float bound = 0.f;
+            if (live)
+#pragma unroll
+                for (int o = 0; o < 4; ++o)
+                    if (o < P.n_out) {
+                        d[o] = P.dout[row * P.stride + o];
+                        bound = fmaf(fabsf(d[o]), S.wmax[o], bound);
+                    }
+            const float sc = pow2_scale(bound);
+            for (int c = 0; c < NCHUNK; ++c) {
+                const int stage = c % NSTAGE;
+                const int k0 = c * KCH + q * 8;
+                float4 h0 = make_float4(0.f, 0.f, 0.f, 0.f), h1v = h0;
+                if (live) {
+                    h0 = *reinterpret_cast<const float4*>(P.h2 + row * H + k0);
+                    h1v = *reinterpret_cast<const float4*>(P.h2 + row * H + k0 + 4);
+                }
+                const float hv[8] = {h0.x, h0.y, h0.z, h0.w, h1v.x, h1v.y, h1v.z, h1v.w};
+                __align__(16) __half hi[8], lo[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    float v = d[0] * S.w3[0][k0 + e];
+                    v = fmaf(d[1], S.w3[1][k0 + e], v); v = fmaf(d[2], S.w3[2][k0 + e], v); v = fmaf(d[3], S.w3[3][k0 + e], v);
+                    v = hv[e] > 0.f ? v * sc : 0.f;
+                    const __half h = __float2half_rn(v);
+                    hi[e] = h;
+                    lo[e] = __float2half_rn(v - __half2float(h));
+                }
+                mbar_wait(smem_u32(&S.empty[stage]), ((c / NSTAGE) & 1) ^ 1);
+                unsigned char* a_hi = S.stage[stage];
+                *reinterpret_cast<uint4*>(a_hi + q * LBO_A + r * 16) = *reinterpret_cast<const uint4*>(hi);
+                *reinterpret_cast<uint4*>(a_hi + A_IMG + q * LBO_A + r * 16) = *reinterpret_cast<const uint4*>(lo);
+                fence_proxy_async();
+                mbar_arrive(smem_u32(&S.full[stage]));
+            }
+            mbar_wait(smem_u32(&S.acc_full), 0);
+            tc_fence_after();
+            const float inv = 1.0f / (sc * SB);
+#pragma unroll 1
+            for (int cc = 0; cc < 2; ++cc) {
+                float v[32];
+                const int col0 = q * 64 + cc * 32;
+                tmem_ld32(lane_addr + col0, v);
+                tmem_ld_wait();
+                if (live) {
+#pragma unroll
+                    for (int j4 = 0; j4 < 8; ++j4) {
+                        const float4 mk = *reinterpret_cast<const float4*>(P.mask + row * H + col0 + 4 * j4);
+                        float4 o4;
+                        o4.x = mk.x > 0.f ? v[4 * j4 + 0] * inv : 0.f;
+                        o4.y = mk.y > 0.f ? v[4 * j4 + 1] * inv : 0.f;
+                        o4.z = mk.z > 0.f ? v[4 * j4 + 2] * inv : 0.f;
+                        o4.w = mk.w > 0.f ? v[4 * j4 + 3] * inv : 0.f;
+                        *reinterpret_cast<float4*>(P.C + row * H + col0 + 4 * j4) = o4;
+                    }
+                }
+            }
+            tc_fence_before();
+        } else {
+            // ================= WEIGHT: thread (m, kc) stages A, threads (n, kc) x2 stage B =================
+            const int m = t & (TM - 1), kc = t >> 7;             // A role: out unit m0 + m, core column kc (8 rows)
+            const int mcol = tile * TM + m;
+            float bound = 0.f;
+#pragma unroll
+            for (int o = 0; o < 4; ++o) bound = fmaf(S.dmax[o], fabsf(S.w3[o][mcol]), bound);
+            const float sc = pow2_scale(bound);
+            float w3m[4];
+#pragma unroll
+            for (int o = 0; o < 4; ++o) w3m[o] = S.w3[o][mcol];
+            float gb2 = 0.f, gw[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int c = 0; c < n_chunks; ++c) {
+                const int stage = c % NSTAGE;
+                const int64_t r0 = (int64_t)c * KCH + kc * 8;
+                __align__(16) __half ahi[8], alo[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const int64_t r = r0 + e;
+                    float v = 0.f;
+                    if (r < rows) {
+                        const float h = P.h2[r * H + mcol];
+                        float dd[4];
+#pragma unroll
+                        for (int o = 0; o < 4; ++o) dd[o] = o < P.n_out ? P.dout[r * P.stride + o] : 0.f;
+                        float g = dd[0] * w3m[0];
+                        g = fmaf(dd[1], w3m[1], g); g = fmaf(dd[2], w3m[2], g); g = fmaf(dd[3], w3m[3], g);
+                        g = h > 0.f ? g : 0.f;
+                        gb2 += g;
+#pragma unroll
+                        for (int o = 0; o < 4; ++o) gw[o] = fmaf(dd[o], h, gw[o]);
+                        v = g * sc;
+                    }
+                    const __half hh = __float2half_rn(v);
+                    ahi[e] = hh;
+                    alo[e] = __float2half_rn(v - __half2float(hh));
+                }
+                __align__(16) __half bhi[2][8], blo[2][8];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int pidx = t + u * kProd;              // (n, kcb): n = pidx & 255, kcb = pidx >> 8
+                    const int n = pidx & (H - 1), kcb = pidx >> 8;
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const int64_t r = (int64_t)c * KCH + kcb * 8 + e;
+                        float v = r < rows ? P.B[r * H + n] * SA : 0.f;
+                        v = fminf(v, 60000.0f);
+                        const __half hh = __float2half_rn(v);
+                        bhi[u][e] = hh;
+                        blo[u][e] = __float2half_rn(v - __half2float(hh));
+                    }
+                }
+                mbar_wait(smem_u32(&S.empty[stage]), ((c / NSTAGE) & 1) ^ 1);
+                unsigned char* a_hi = S.stage[stage];
+                unsigned char* b_hi = a_hi + 2 * A_IMG;
+                *reinterpret_cast<uint4*>(a_hi + kc * LBO_A + m * 16) = *reinterpret_cast<const uint4*>(ahi);
+                *reinterpret_cast<uint4*>(a_hi + A_IMG + kc * LBO_A + m * 16) = *reinterpret_cast<const uint4*>(alo);
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int pidx = t + u * kProd;
+                    const int n = pidx & (H - 1), kcb = pidx >> 8;
+                    *reinterpret_cast<uint4*>(b_hi + kcb * LBO_B + n * 16) = *reinterpret_cast<const uint4*>(bhi[u]);
+                    *reinterpret_cast<uint4*>(b_hi + B_IMG + kcb * LBO_B + n * 16) = *reinterpret_cast<const uint4*>(blo[u]);
+                }
+                fence_proxy_async();
+                mbar_arrive(smem_u32(&S.full[stage]));
+            }
+            // head-layer gradients: reduce the four kc partials of each out unit
+            if (P.gb2) {
+                S.red[t][0] = gb2;
+#pragma unroll
+                for (int o = 0; o < 4; ++o) S.red[t][1 + o] = gw[o];
+            }
+            // epilogue: D[m][64 q .. 64 q + 63] -> gW2   (TMEM lane = m: warp & 3 selects the lane quadrant)
+            const int q = warp >> 2, mr = (warp & 3) * 32 + lane;
+            const int mrow = tile * TM + mr;
+            float bound2 = 0.f;
+#pragma unroll
+            for (int o = 0; o < 4; ++o) bound2 = fmaf(S.dmax[o], fabsf(S.w3[o][mrow]), bound2);
+            const float inv = 1.0f / (pow2_scale(bound2) * SA);
+            mbar_wait(smem_u32(&S.acc_full), 0);
+            tc_fence_after();
+#pragma unroll 1
+            for (int cc = 0; cc < 2; ++cc) {
+                float v[32];
+                const int col0 = q * 64 + cc * 32;
+                tmem_ld32(lane_addr + col0, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j4 = 0; j4 < 8; ++j4)
+                    *reinterpret_cast<float4*>(P.C + (size_t)mrow * H + col0 + 4 * j4) =
+                        make_float4(v[4 * j4 + 0] * inv, v[4 * j4 + 1] * inv, v[4 * j4 + 2] * inv, v[4 * j4 + 3] * inv);
+            }
+            tc_fence_before();
+            asm volatile("bar.sync 1, %0;" ::"n"(kProd) : "memory");
+            if (P.gb2 && t < TM) {
+                float s5[5];
+#pragma unroll
+                for (int j = 0; j < 5; ++j) s5[j] = (S.red[t][j] + S.red[t + TM][j]) + (S.red[t + 2 * TM][j] + S.red[t + 3 * TM][j]);
+                const int col = tile * TM + t;
+                P.gb2[col] = s5[0];
+#pragma unroll
+                for (int o = 0; o < 4; ++o) {
+                    if (o < P.na) P.gW3a[o * H + col] = s5[1 + o];
+                    else if (o < P.n_out) P.gW3b[(o - P.na) * H + col] = s5[1 + o];
+                }
+                if (tile == 0 && t < P.n_out) {
+                    if (t < P.na) P.gb3a[t] = S.gb3[t];
+                    else P.gb3b[t - P.na] = S.gb3[t];
+                }
+            }
+        }
+    } else if (warp == kProd / 32) {
+        if (lane == 0) {
+            for (int c = 0; c < n_chunks; ++c) {
+                const int stage = c % NSTAGE;
+                mbar_wait(smem_u32(&S.full[stage]), (c / NSTAGE) & 1);
+                tc_fence_after();
+                const uint32_t a_hi = smem_u32(S.stage[stage]);
+                const uint32_t a_lo = a_hi + A_IMG, b_hi = a_hi + 2 * A_IMG, b_lo = b_hi + B_IMG;
+#pragma unroll
+                for (int j = 0; j < KCH / 16; ++j) {
+                    const uint64_t dah = make_desc(a_hi + j * 2 * LBO_A, LBO_A, SBO);
+                    const uint64_t dal = make_desc(a_lo + j * 2 * LBO_A, LBO_A, SBO);
+                    const uint64_t dbh = make_desc(b_hi + j * 2 * LBO_B, LBO_B, SBO);
+                    const uint64_t dbl = make_desc(b_lo + j * 2 * LBO_B, LBO_B, SBO);
+                    umma_f16(tmem_base, dah, dbh, (c | j) ? 1u : 0u);
+                    umma_f16(tmem_base, dah, dbl, 1u);
+                    umma_f16(tmem_base, dal, dbh, 1u);
+                }
+                umma_commit(smem_u32(&S.empty[stage]));
+            }
+            umma_commit(smem_u32(&S.acc_full));
+        }
+    } else if (!weight) {
+        if (lane == 0) {
+            const unsigned char* img = reinterpret_cast<const unsigned char*>(P.tc_imgT);
+            for (int c = 0; c < NCHUNK; ++c) {
+                const int stage = c % NSTAGE;
+                mbar_wait(smem_u32(&S.empty[stage]), ((c / NSTAGE) & 1) ^ 1);
+                const uint32_t bar = smem_u32(&S.full[stage]);
+                const uint32_t dst = smem_u32(S.stage[stage]) + 2 * A_IMG;
+                mbar_arrive_expect_tx(bar, 2 * B_IMG);
+                bulk_g2s(dst, img + (size_t)c * 2 * B_IMG, B_IMG, bar);
+                bulk_g2s(dst + B_IMG, img + (size_t)c * 2 * B_IMG + B_IMG, B_IMG, bar);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kProd / 32) tmem_dealloc(tmem_base, 256);
+}
+
 }  // namespace
 
 namespace rrl {
@@ -688,8 +990,24 @@ int fwd_tc_launch(const FwdArgs& A, int64_t max_rows, cudaStream_t st) {
     return 0;
 }
 
+int bwd_tc_launch(const GemmArgs& G, int64_t max_rows, cudaStream_t st) {
+    static bool configured = false;
+    const size_t smem = sizeof(BwdTcSmem) + 128;
+    if (!configured) {
+        RRL_CUDA(cudaFuncSetAttribute(bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    for (int i = 0; i < G.n_pass; ++i)
+        if (!G.p[i].k_is_rows && !G.p[i].tc_imgT) { rrl_set_error("bwd_tc_launch: pass %d has no W2^T image", i); return -2; }
+    int64_t tiles = (max_rows + TM - 1) / TM;
+    if (tiles < H / TM) tiles = H / TM;
+    bwd_tc_kernel<<<dim3((unsigned)tiles, (unsigned)G.n_pass), kTcThreads, smem, st>>>(G);
+    RRL_CHECK_LAUNCH();
+    return 0;
+}
+
 int tc_images_launch(float* arena, const Layout& L, cudaStream_t st) {
-    TcImgArgs A;
+    TcImgArgs A, T;
     static const int nets[6] = {RRL_NET_CRITIC, RRL_NET_CRITIC_TARGET, RRL_NET_POLICY, RRL_NET_QRISK, RRL_NET_QRISK_TARGET,
                                 RRL_NET_RECOVERY};
     for (int ni = 0; ni < 6; ++ni) {
@@ -699,9 +1017,13 @@ int tc_images_launch(float* arena, const Layout& L, cudaStream_t st) {
             const int i = image_index(net, h);
             A.W2[i] = arena + L.t_off[net][w2_tensor(net, h)];
             A.img[i] = reinterpret_cast<__half*>(arena + L.tc_img_off[i]);
+            T.W2[i] = arena + L.img_off[i];          // W2^T row-major == the k-major image (must be fresh)
+            T.img[i] = reinterpret_cast<__half*>(arena + L.tc_imgT_off[i]);
         }
     }
     tc_images_kernel<<<dim3(H * 32 / 256, kTcHeads), 256, 0, st>>>(A);
+    RRL_CHECK_LAUNCH();
+    tc_images_kernel<<<dim3(H * 32 / 256, kTcHeads), 256, 0, st>>>(T);
     RRL_CHECK_LAUNCH();
     return 0;
 }
