@@ -1136,6 +1136,7 @@ extern "C" int rrl_twin_q_forward(const rrl_agent_config_t* cfg, const float* ar
     A.n_pass = 2;
     A.rows_const = n;
     A.sp = action_space(cfg);
+    A.use_tc = cfg->use_tensor_cores;
     return launch_forward<64>(A, n, (cudaStream_t)stream);
 }
 

@@ -27,6 +27,14 @@ using namespace rrl;
 
 namespace {
 
+#ifdef RRL_TC_TIMING
+__device__ unsigned long long g_tc_time[64][8];
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define TSTAMP(i) do { if ((threadIdx.x & 127) == 0 && threadIdx.x < 512) g_tc_time[(blockIdx.y * 4 + blockIdx.x) & 63][i] = gtime(); } while (0)
+#else
+#define TSTAMP(i)
+#endif
+
 constexpr int TM = 128;                  // rows per tile == TMEM lanes
 constexpr int KCH = 32;                  // k per stage
 constexpr int NSTAGE = 3;
@@ -137,11 +145,41 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint
            ((uint64_t)1 << 46);
 }
 
-__device__ __forceinline__ void split_f16(float v, __half* hi, __half* lo) {
-    v = fminf(v, 60000.0f);
-    const __half h = __float2half_rn(v);
-    *hi = h;
-    *lo = __float2half_rn(v - __half2float(h));
+// x = hi + lo with both terms fp16, for 8 values at once: hi = x with the mantissa TRUNCATED to 10 bits (a bit mask, exactly
+// representable in fp16, so no fp16 -> fp32 round trip is needed for the residual), lo = fp16(x - hi); packed
+// cvt.rn.f16x2.f32 conversions.  hi + lo carries ~21 significand bits.  Inputs must be within the fp16 range.
+__device__ __forceinline__ void split8(const float (&v)[8], uint4* hi, uint4* lo) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float a = v[2 * i], b = v[2 * i + 1];
+        const float ah = __uint_as_float(__float_as_uint(a) & 0xFFFFE000u);
+        const float bh = __uint_as_float(__float_as_uint(b) & 0xFFFFE000u);
+        const __half2 hh = __floats2half2_rn(ah, bh);
+        const __half2 ll = __floats2half2_rn(a - ah, b - bh);
+        h[i] = *reinterpret_cast<const uint32_t*>(&hh);
+        l[i] = *reinterpret_cast<const uint32_t*>(&ll);
+    }
+    *hi = make_uint4(h[0], h[1], h[2], h[3]);
+    *lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+// The 32 x 32 block a warp holds after tcgen05.ld (lane = row, v[j] = column j) -> row-major float4 pieces so that the
+// global accesses that follow are coalesced (4 rows x 128 B per warp instruction): f(row_in_block, c4, value).
+// scratch: 32 x 36 floats private to the warp (stride 36: both phases are bank-conflict free).
+constexpr int kXposeFloats = 32 * 36;
+template <typename F>
+__device__ __forceinline__ void warp_block_rows(float* scratch, const float (&v)[32], int lane, F&& f) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<float4*>(scratch + lane * 36 + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int rl = i * 4 + (lane >> 3), c4 = lane & 7;
+        f(rl, c4, *reinterpret_cast<const float4*>(scratch + rl * 36 + 4 * c4));
+    }
+    __syncwarp();
 }
 
 // ---- weight images -----------------------------------------------------------------------------------
@@ -193,7 +231,7 @@ __device__ __forceinline__ void produce_chunk(TcSmem& S, int pass, int c, int st
                                               float x2, float x3, bool four) {
     unsigned char* a_hi = S.stage[stage];
     unsigned char* a_lo = a_hi + A_IMG;
-    __align__(16) __half hi[8], lo[8];
+    float hv[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
         const int k = c * KCH + q * 8 + e;
@@ -204,10 +242,12 @@ __device__ __forceinline__ void produce_chunk(TcSmem& S, int pass, int c, int st
             h = fmaf(wv.z, x2, h);
             h = fmaf(wv.w, x3, h);
         }
-        split_f16(fmaxf(h, 0.f), &hi[e], &lo[e]);
+        hv[e] = fminf(fmaxf(h, 0.f), 60000.0f);
     }
-    *reinterpret_cast<uint4*>(a_hi + q * LBO_A + r * 16) = *reinterpret_cast<const uint4*>(hi);
-    *reinterpret_cast<uint4*>(a_lo + q * LBO_A + r * 16) = *reinterpret_cast<const uint4*>(lo);
+    uint4 hi, lo;
+    split8(hv, &hi, &lo);
+    *reinterpret_cast<uint4*>(a_hi + q * LBO_A + r * 16) = hi;
+    *reinterpret_cast<uint4*>(a_lo + q * LBO_A + r * 16) = lo;
 }
 
 // epilogue: columns [64 q, 64 q + 64) of this thread's row of accumulator `d` -> partial head sums
@@ -561,8 +601,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
             mbar_wait(smem_u32(&S.empty[stage]), ((c / NSTAGE) & 1) ^ 1);
             unsigned char* a_hi = S.stage[stage];
             unsigned char* a_lo = a_hi + A_IMG;
-            __align__(16) __half hi[8], lo[8];
-            float hv[8];
+            float hv[8], hs[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
                 const int k = c * KCH + q * 8 + e;
@@ -575,10 +614,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
                 }
                 h = fmaxf(h, 0.f);
                 hv[e] = h * (1.0f / SA);      // exact: SA is a power of two
-                split_f16(h, &hi[e], &lo[e]);
+                hs[e] = fminf(h, 60000.0f);
             }
-            *reinterpret_cast<uint4*>(a_hi + q * LBO_A + r * 16) = *reinterpret_cast<const uint4*>(hi);
-            *reinterpret_cast<uint4*>(a_lo + q * LBO_A + r * 16) = *reinterpret_cast<const uint4*>(lo);
+            uint4 hi, lo;
+            split8(hs, &hi, &lo);
+            *reinterpret_cast<uint4*>(a_hi + q * LBO_A + r * 16) = hi;
+            *reinterpret_cast<uint4*>(a_lo + q * LBO_A + r * 16) = lo;
             if (P.h1 && live) {
                 float4* dst = reinterpret_cast<float4*>(P.h1 + row * H + c * KCH + q * 8);
                 dst[0] = make_float4(hv[0], hv[1], hv[2], hv[3]);
@@ -592,6 +633,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
         tc_fence_after();
         float out[4] = {0.f, 0.f, 0.f, 0.f};
         const int n_out = w.na + w.nb;
+        // all MMAs have completed (acc_full): the operand stages are free and serve as per-warp transpose scratch
+        float* scratch = reinterpret_cast<float*>(S.stage) + warp * kXposeFloats;
+        const int64_t wrow0 = row0 + (warp & 3) * 32;     // first row of this warp's TMEM lane quadrant
 #pragma unroll 1
         for (int cc = 0; cc < 2; ++cc) {
             float v[32];
@@ -606,7 +650,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
                 const float h1 = fmaxf(fmaf(v[4 * j4 + 1], INV_SCALE, b.y), 0.f);
                 const float h2 = fmaxf(fmaf(v[4 * j4 + 2], INV_SCALE, b.z), 0.f);
                 const float h3 = fmaxf(fmaf(v[4 * j4 + 3], INV_SCALE, b.w), 0.f);
-                if (P.h2 && live) *reinterpret_cast<float4*>(P.h2 + row * H + col0 + 4 * j4) = make_float4(h0, h1, h2, h3);
+                v[4 * j4 + 0] = h0; v[4 * j4 + 1] = h1; v[4 * j4 + 2] = h2; v[4 * j4 + 3] = h3;
 #pragma unroll
                 for (int o = 0; o < 4; ++o) {
                     if (o < n_out) {
@@ -615,6 +659,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
                     }
                 }
             }
+            if (P.h2)
+                warp_block_rows(scratch, v, lane, [&](int rl, int c4, float4 hv) {
+                    if (wrow0 + rl < rows) *reinterpret_cast<float4*>(P.h2 + (wrow0 + rl) * H + col0 + 4 * c4) = hv;
+                });
         }
         tc_fence_before();
         S.part[q][r] = make_float4(out[0], out[1], out[2], out[3]);
@@ -664,9 +712,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
             }
         }
     }
+    TSTAMP(4);
     tc_fence_before();
     __syncthreads();
     if (warp == kProd / 32) tmem_dealloc(tmem_base, 256);
+    TSTAMP(5);
 }
 
 
@@ -676,10 +726,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
 // WEIGHT CTA (128 out-units m): A[m][k = row] = dh2[row][m] (scaled per COLUMN m), B[n][k = row] = h1[row][n] * 16,
 //        both written transposed into the canonical K-major layout by the producers, D -> gW2; the A producers also
 //        reduce gb2 / gW3 (and the m-tile 0 CTA gb3) deterministically.
+constexpr int kDoutRows = 1024;
 struct BwdTcSmem {
     unsigned char stage[NSTAGE][STAGE_BYTES];
     float w3[4][H];
     float red[kProd][6];            // WEIGHT: per-thread partial sums (gb2, gW3[0..3])
+    float4 douts[kDoutRows];        // WEIGHT: dout of the whole batch (rows <= kDoutRows), zero-padded to 4 outputs
     float wmax[4], dmax[4], gb3[4];
     float red4[kProd / 32][8];
     unsigned long long full[NSTAGE], empty[NSTAGE], acc_full;
@@ -698,6 +750,7 @@ __device__ __forceinline__ float pow2_scale(float bound) {
 
 __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const __grid_constant__ GemmArgs G) {
     extern __shared__ unsigned char smem_raw[];
+    TSTAMP(0);
     BwdTcSmem& S = *reinterpret_cast<BwdTcSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
     const int64_t rows = *G.rows_ptr;
     if (rows <= 0) return;
@@ -729,6 +782,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const __grid_cons
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = S.tmem_base;
+    const bool dout_smem = weight && rows <= kDoutRows;
+    if (dout_smem)
+        for (int r = t; r < (int)rows; r += kTcThreads) {
+            float4 d4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            d4.x = P.dout[(size_t)r * P.stride];
+            if (P.n_out > 1) d4.y = P.dout[(size_t)r * P.stride + 1];
+            if (P.n_out > 2) d4.z = P.dout[(size_t)r * P.stride + 2];
+            if (P.n_out > 3) d4.w = P.dout[(size_t)r * P.stride + 3];
+            S.douts[r] = d4;
+        }
     // column maxima of |W3| (DATA: per-row bound) / maxima and sums of dout over the batch (WEIGHT: per-column bound, gb3)
     if (warp < 4) {
         const int o = warp;
@@ -752,6 +815,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const __grid_cons
     }
     __syncthreads();
 
+    TSTAMP(1);
     if (warp < kProd / 32) {
         const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
         if (!weight) {
@@ -769,53 +833,60 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const __grid_cons
                         bound = fmaf(fabsf(d[o]), S.wmax[o], bound);
                     }
             const float sc = pow2_scale(bound);
+            float4 hn0 = make_float4(0.f, 0.f, 0.f, 0.f), hn1 = hn0;
+            if (live) {
+                hn0 = *reinterpret_cast<const float4*>(P.h2 + row * H + q * 8);
+                hn1 = *reinterpret_cast<const float4*>(P.h2 + row * H + q * 8 + 4);
+            }
             for (int c = 0; c < NCHUNK; ++c) {
                 const int stage = c % NSTAGE;
                 const int k0 = c * KCH + q * 8;
-                float4 h0 = make_float4(0.f, 0.f, 0.f, 0.f), h1v = h0;
-                if (live) {
-                    h0 = *reinterpret_cast<const float4*>(P.h2 + row * H + k0);
-                    h1v = *reinterpret_cast<const float4*>(P.h2 + row * H + k0 + 4);
+                const float4 h0 = hn0, h1v = hn1;
+                if (live && c + 1 < NCHUNK) {          // next chunk's h2 in flight while this one is converted
+                    hn0 = *reinterpret_cast<const float4*>(P.h2 + row * H + k0 + KCH);
+                    hn1 = *reinterpret_cast<const float4*>(P.h2 + row * H + k0 + KCH + 4);
                 }
                 const float hv[8] = {h0.x, h0.y, h0.z, h0.w, h1v.x, h1v.y, h1v.z, h1v.w};
-                __align__(16) __half hi[8], lo[8];
+                float gv[8];
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
                     float v = d[0] * S.w3[0][k0 + e];
                     v = fmaf(d[1], S.w3[1][k0 + e], v); v = fmaf(d[2], S.w3[2][k0 + e], v); v = fmaf(d[3], S.w3[3][k0 + e], v);
-                    v = hv[e] > 0.f ? v * sc : 0.f;
-                    const __half h = __float2half_rn(v);
-                    hi[e] = h;
-                    lo[e] = __float2half_rn(v - __half2float(h));
+                    gv[e] = hv[e] > 0.f ? v * sc : 0.f;
                 }
+                uint4 hi, lo;
+                split8(gv, &hi, &lo);
                 mbar_wait(smem_u32(&S.empty[stage]), ((c / NSTAGE) & 1) ^ 1);
                 unsigned char* a_hi = S.stage[stage];
-                *reinterpret_cast<uint4*>(a_hi + q * LBO_A + r * 16) = *reinterpret_cast<const uint4*>(hi);
-                *reinterpret_cast<uint4*>(a_hi + A_IMG + q * LBO_A + r * 16) = *reinterpret_cast<const uint4*>(lo);
+                *reinterpret_cast<uint4*>(a_hi + q * LBO_A + r * 16) = hi;
+                *reinterpret_cast<uint4*>(a_hi + A_IMG + q * LBO_A + r * 16) = lo;
                 fence_proxy_async();
                 mbar_arrive(smem_u32(&S.full[stage]));
             }
+            TSTAMP(2);
             mbar_wait(smem_u32(&S.acc_full), 0);
+            TSTAMP(3);
             tc_fence_after();
             const float inv = 1.0f / (sc * SB);
+            float* scratch = reinterpret_cast<float*>(S.stage) + warp * kXposeFloats;   // stages are free after acc_full
+            const int64_t wrow0 = (int64_t)tile * TM + (warp & 3) * 32;
 #pragma unroll 1
             for (int cc = 0; cc < 2; ++cc) {
                 float v[32];
                 const int col0 = q * 64 + cc * 32;
                 tmem_ld32(lane_addr + col0, v);
                 tmem_ld_wait();
-                if (live) {
 #pragma unroll
-                    for (int j4 = 0; j4 < 8; ++j4) {
-                        const float4 mk = *reinterpret_cast<const float4*>(P.mask + row * H + col0 + 4 * j4);
-                        float4 o4;
-                        o4.x = mk.x > 0.f ? v[4 * j4 + 0] * inv : 0.f;
-                        o4.y = mk.y > 0.f ? v[4 * j4 + 1] * inv : 0.f;
-                        o4.z = mk.z > 0.f ? v[4 * j4 + 2] * inv : 0.f;
-                        o4.w = mk.w > 0.f ? v[4 * j4 + 3] * inv : 0.f;
-                        *reinterpret_cast<float4*>(P.C + row * H + col0 + 4 * j4) = o4;
+                for (int j = 0; j < 32; ++j) v[j] *= inv;      // this row's scale
+                warp_block_rows(scratch, v, lane, [&](int rl, int c4, float4 g) {
+                    const int64_t rr = wrow0 + rl;
+                    if (rr < rows) {
+                        const float4 mk = *reinterpret_cast<const float4*>(P.mask + rr * H + col0 + 4 * c4);
+                        g.x = mk.x > 0.f ? g.x : 0.f; g.y = mk.y > 0.f ? g.y : 0.f;
+                        g.z = mk.z > 0.f ? g.z : 0.f; g.w = mk.w > 0.f ? g.w : 0.f;
+                        *reinterpret_cast<float4*>(P.C + rr * H + col0 + 4 * c4) = g;
                     }
-                }
+                });
             }
             tc_fence_before();
         } else {
@@ -830,19 +901,42 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const __grid_cons
 #pragma unroll
             for (int o = 0; o < 4; ++o) w3m[o] = S.w3[o][mcol];
             float gb2 = 0.f, gw[4] = {0.f, 0.f, 0.f, 0.f};
+            const int nB0 = t & (H - 1), kcB0 = t >> 8;                 // B role, item 0: (n, kc)
+            const int nB1 = (t + kProd) & (H - 1), kcB1 = (t + kProd) >> 8;
+            float h2n[8], h1n[2][8];                                     // prefetched operands of the NEXT chunk
+            auto prefetch = [&](int c) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const int64_t ra = (int64_t)c * KCH + kc * 8 + e;
+                    h2n[e] = ra < rows ? P.h2[ra * H + mcol] : 0.f;
+                    const int64_t rb0 = (int64_t)c * KCH + kcB0 * 8 + e, rb1 = (int64_t)c * KCH + kcB1 * 8 + e;
+                    h1n[0][e] = rb0 < rows ? P.B[rb0 * H + nB0] : 0.f;
+                    h1n[1][e] = rb1 < rows ? P.B[rb1 * H + nB1] : 0.f;
+                }
+            };
+            prefetch(0);
             for (int c = 0; c < n_chunks; ++c) {
                 const int stage = c % NSTAGE;
                 const int64_t r0 = (int64_t)c * KCH + kc * 8;
-                __align__(16) __half ahi[8], alo[8];
+                float h2c[8], h1c[2][8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) { h2c[e] = h2n[e]; h1c[0][e] = h1n[0][e]; h1c[1][e] = h1n[1][e]; }
+                if (c + 1 < n_chunks) prefetch(c + 1);                   // in flight while this chunk is converted
+                float av[8];
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
                     const int64_t r = r0 + e;
                     float v = 0.f;
                     if (r < rows) {
-                        const float h = P.h2[r * H + mcol];
+                        const float h = h2c[e];
                         float dd[4];
+                        if (dout_smem) {
+                            const float4 d4 = S.douts[r];
+                            dd[0] = d4.x; dd[1] = d4.y; dd[2] = d4.z; dd[3] = d4.w;
+                        } else {
 #pragma unroll
-                        for (int o = 0; o < 4; ++o) dd[o] = o < P.n_out ? P.dout[r * P.stride + o] : 0.f;
+                            for (int o = 0; o < 4; ++o) dd[o] = o < P.n_out ? P.dout[r * P.stride + o] : 0.f;
+                        }
                         float g = dd[0] * w3m[0];
                         g = fmaf(dd[1], w3m[1], g); g = fmaf(dd[2], w3m[2], g); g = fmaf(dd[3], w3m[3], g);
                         g = h > 0.f ? g : 0.f;
@@ -851,37 +945,26 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const __grid_cons
                         for (int o = 0; o < 4; ++o) gw[o] = fmaf(dd[o], h, gw[o]);
                         v = g * sc;
                     }
-                    const __half hh = __float2half_rn(v);
-                    ahi[e] = hh;
-                    alo[e] = __float2half_rn(v - __half2float(hh));
+                    av[e] = v;
                 }
-                __align__(16) __half bhi[2][8], blo[2][8];
+                uint4 ahi, alo, bhi[2], blo[2];
+                split8(av, &ahi, &alo);
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
-                    const int pidx = t + u * kProd;              // (n, kcb): n = pidx & 255, kcb = pidx >> 8
-                    const int n = pidx & (H - 1), kcb = pidx >> 8;
+                    float bv[8];
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        const int64_t r = (int64_t)c * KCH + kcb * 8 + e;
-                        float v = r < rows ? P.B[r * H + n] * SA : 0.f;
-                        v = fminf(v, 60000.0f);
-                        const __half hh = __float2half_rn(v);
-                        bhi[u][e] = hh;
-                        blo[u][e] = __float2half_rn(v - __half2float(hh));
-                    }
+                    for (int e = 0; e < 8; ++e) bv[e] = fminf(h1c[u][e] * SA, 60000.0f);
+                    split8(bv, &bhi[u], &blo[u]);
                 }
                 mbar_wait(smem_u32(&S.empty[stage]), ((c / NSTAGE) & 1) ^ 1);
                 unsigned char* a_hi = S.stage[stage];
                 unsigned char* b_hi = a_hi + 2 * A_IMG;
-                *reinterpret_cast<uint4*>(a_hi + kc * LBO_A + m * 16) = *reinterpret_cast<const uint4*>(ahi);
-                *reinterpret_cast<uint4*>(a_hi + A_IMG + kc * LBO_A + m * 16) = *reinterpret_cast<const uint4*>(alo);
-#pragma unroll
-                for (int u = 0; u < 2; ++u) {
-                    const int pidx = t + u * kProd;
-                    const int n = pidx & (H - 1), kcb = pidx >> 8;
-                    *reinterpret_cast<uint4*>(b_hi + kcb * LBO_B + n * 16) = *reinterpret_cast<const uint4*>(bhi[u]);
-                    *reinterpret_cast<uint4*>(b_hi + B_IMG + kcb * LBO_B + n * 16) = *reinterpret_cast<const uint4*>(blo[u]);
-                }
+                *reinterpret_cast<uint4*>(a_hi + kc * LBO_A + m * 16) = ahi;
+                *reinterpret_cast<uint4*>(a_hi + A_IMG + kc * LBO_A + m * 16) = alo;
+                *reinterpret_cast<uint4*>(b_hi + kcB0 * LBO_B + nB0 * 16) = bhi[0];
+                *reinterpret_cast<uint4*>(b_hi + B_IMG + kcB0 * LBO_B + nB0 * 16) = blo[0];
+                *reinterpret_cast<uint4*>(b_hi + kcB1 * LBO_B + nB1 * 16) = bhi[1];
+                *reinterpret_cast<uint4*>(b_hi + B_IMG + kcB1 * LBO_B + nB1 * 16) = blo[1];
                 fence_proxy_async();
                 mbar_arrive(smem_u32(&S.full[stage]));
             }
@@ -898,8 +981,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const __grid_cons
 #pragma unroll
             for (int o = 0; o < 4; ++o) bound2 = fmaf(S.dmax[o], fabsf(S.w3[o][mrow]), bound2);
             const float inv = 1.0f / (pow2_scale(bound2) * SA);
+            TSTAMP(2);
             mbar_wait(smem_u32(&S.acc_full), 0);
+            TSTAMP(3);
             tc_fence_after();
+            float* scratch = reinterpret_cast<float*>(S.stage) + warp * kXposeFloats;   // stages are free after acc_full
+            const int wm0 = tile * TM + (warp & 3) * 32;
 #pragma unroll 1
             for (int cc = 0; cc < 2; ++cc) {
                 float v[32];
@@ -907,9 +994,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const __grid_cons
                 tmem_ld32(lane_addr + col0, v);
                 tmem_ld_wait();
 #pragma unroll
-                for (int j4 = 0; j4 < 8; ++j4)
-                    *reinterpret_cast<float4*>(P.C + (size_t)mrow * H + col0 + 4 * j4) =
-                        make_float4(v[4 * j4 + 0] * inv, v[4 * j4 + 1] * inv, v[4 * j4 + 2] * inv, v[4 * j4 + 3] * inv);
+                for (int j = 0; j < 32; ++j) v[j] *= inv;      // this out unit's scale
+                warp_block_rows(scratch, v, lane, [&](int rl, int c4, float4 g) {
+                    *reinterpret_cast<float4*>(P.C + (size_t)(wm0 + rl) * H + col0 + 4 * c4) = g;
+                });
             }
             tc_fence_before();
             asm volatile("bar.sync 1, %0;" ::"n"(kProd) : "memory");
@@ -966,9 +1054,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const __grid_cons
             }
         }
     }
+    TSTAMP(4);
     tc_fence_before();
     __syncthreads();
     if (warp == kProd / 32) tmem_dealloc(tmem_base, 256);
+    TSTAMP(5);
 }
 
 }  // namespace
@@ -990,6 +1080,11 @@ int fwd_tc_launch(const FwdArgs& A, int64_t max_rows, cudaStream_t st) {
     return 0;
 }
 
+#ifdef RRL_TC_TIMING
+extern "C" int rrl_debug_tc_times(unsigned long long* out) {
+    return (int)cudaMemcpyFromSymbol(out, g_tc_time, sizeof(unsigned long long) * 64 * 8);
+}
+#endif
 int bwd_tc_launch(const GemmArgs& G, int64_t max_rows, cudaStream_t st) {
     static bool configured = false;
     const size_t smem = sizeof(BwdTcSmem) + 128;
