@@ -78,6 +78,14 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
+// one arrival per WARP: every lane has fenced its own shared-memory writes, __syncwarp orders them before lane 0's
+// arrive (512 per-thread arrivals on one mbarrier per k-chunk serialise in the barrier unit)
+constexpr int kProdWarps = 16;
+__device__ __forceinline__ void mbar_arrive(uint32_t bar);
+__device__ __forceinline__ void mbar_arrive_warp(uint32_t bar) {
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(bar);
+}
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
@@ -328,12 +336,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) act_tc_kernel(const __grid_cons
     if (t < 2 && n_pass > 1) S.sm.log_std[t] = A.rec.log_std[t];
     if (t == 0) {
         for (int s = 0; s < NSTAGE; ++s) {
-            mbar_init(smem_u32(&S.full[s]), kProd + 1);  // producer arrivals + the loader's expect_tx arrival
+            mbar_init(smem_u32(&S.full[s]), kProdWarps + 1);  // one arrival per producer warp + the loader's expect_tx arrival
             mbar_init(smem_u32(&S.empty[s]), 1);      // tcgen05.commit
         }
         for (int d = 0; d < 2; ++d) {
             mbar_init(smem_u32(&S.acc_full[d]), 1);   // tcgen05.commit
-            mbar_init(smem_u32(&S.acc_empty[d]), kProd); // epilogue arrivals
+            mbar_init(smem_u32(&S.acc_empty[d]), kProdWarps); // one arrival per epilogue warp
         }
         fence_barrier_init();
     }
@@ -374,7 +382,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) act_tc_kernel(const __grid_cons
                     mbar_wait(smem_u32(&S.empty[stage]), ((it / NSTAGE) & 1) ^ 1);
                     produce_chunk(S, pass, c, stage, r, q, sx, sy, x2, x3, four);
                     fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
-                    mbar_arrive(smem_u32(&S.full[stage]));
+                    mbar_arrive_warp(smem_u32(&S.full[stage]));
                 }
             };
             auto epilogue_pass = [&](int pass, int d, int n_out, float raw[4]) {
@@ -382,7 +390,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) act_tc_kernel(const __grid_cons
                 tc_fence_after();
                 const float4 mine = epilogue_quarter(S, pass, n_out, lane_addr + d * H, q);
                 tc_fence_before();
-                mbar_arrive(smem_u32(&S.acc_empty[d]));
+                mbar_arrive_warp(smem_u32(&S.acc_empty[d]));
                 ++acc_use[d];
                 // exchange the four column quarters of the row; every thread of the row then holds the full sums
                 const int pb = n_epi & 1;
@@ -566,7 +574,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
     }
     if (t == 0) {
         for (int s = 0; s < NSTAGE; ++s) {
-            mbar_init(smem_u32(&S.full[s]), kProd + 1);
+            mbar_init(smem_u32(&S.full[s]), kProdWarps + 1);
             mbar_init(smem_u32(&S.empty[s]), 1);
         }
         mbar_init(smem_u32(&S.acc_full), 1);
@@ -626,7 +634,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
                 dst[1] = make_float4(hv[4], hv[5], hv[6], hv[7]);
             }
             fence_proxy_async();
-            mbar_arrive(smem_u32(&S.full[stage]));
+            mbar_arrive_warp(smem_u32(&S.full[stage]));
         }
         // ---- epilogue: columns [64 q, 64 q + 64) of this row ----
         mbar_wait(smem_u32(&S.acc_full), 0);
@@ -768,7 +776,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const __grid_cons
             S.w3[o][k] = o < P.na ? P.W3a[o * H + k] : (o < P.n_out ? P.W3b[(o - P.na) * H + k] : 0.f);
     if (t == 0) {
         for (int s = 0; s < NSTAGE; ++s) {
-            mbar_init(smem_u32(&S.full[s]), weight ? kProd : kProd + 1);
+            mbar_init(smem_u32(&S.full[s]), weight ? kProdWarps : kProdWarps + 1);
             mbar_init(smem_u32(&S.empty[s]), 1);
         }
         mbar_init(smem_u32(&S.acc_full), 1);
@@ -861,7 +869,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const __grid_cons
                 *reinterpret_cast<uint4*>(a_hi + q * LBO_A + r * 16) = hi;
                 *reinterpret_cast<uint4*>(a_hi + A_IMG + q * LBO_A + r * 16) = lo;
                 fence_proxy_async();
-                mbar_arrive(smem_u32(&S.full[stage]));
+                mbar_arrive_warp(smem_u32(&S.full[stage]));
             }
             TSTAMP(2);
             mbar_wait(smem_u32(&S.acc_full), 0);
@@ -966,7 +974,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const __grid_cons
                 *reinterpret_cast<uint4*>(b_hi + kcB1 * LBO_B + nB1 * 16) = bhi[1];
                 *reinterpret_cast<uint4*>(b_hi + B_IMG + kcB1 * LBO_B + nB1 * 16) = blo[1];
                 fence_proxy_async();
-                mbar_arrive(smem_u32(&S.full[stage]));
+                mbar_arrive_warp(smem_u32(&S.full[stage]));
             }
             // head-layer gradients: reduce the four kc partials of each out unit
             if (P.gb2) {
