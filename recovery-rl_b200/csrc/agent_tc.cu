@@ -297,8 +297,10 @@ __device__ __forceinline__ float4 epilogue_quarter(TcSmem& S, int pass, int n_ou
 }
 
 __global__ void __launch_bounds__(kTcThreads, 1) act_tc_kernel(const __grid_constant__ TcActArgs T) {
-    extern __shared__ unsigned char smem_raw[];
-    TcSmem& S = *reinterpret_cast<TcSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+    // declared aligned and used WITHOUT pointer arithmetic: rounding the address up through uintptr_t makes the
+    // compiler lose the shared address space and emit generic LD / ST (long-scoreboard) instead of LDS / STS
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    TcSmem& S = *reinterpret_cast<TcSmem*>(smem_raw);
     const ActArgs& A = T.a;
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
     const int n_pass = T.n_pass;
@@ -539,8 +541,10 @@ struct FwdTcSmem {
 };
 
 __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_constant__ FwdArgs A) {
-    extern __shared__ unsigned char smem_raw[];
-    FwdTcSmem& S = *reinterpret_cast<FwdTcSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+    // declared aligned and used WITHOUT pointer arithmetic: rounding the address up through uintptr_t makes the
+    // compiler lose the shared address space and emit generic LD / ST (long-scoreboard) instead of LDS / STS
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    FwdTcSmem& S = *reinterpret_cast<FwdTcSmem*>(smem_raw);
     const int64_t rows = A.rows_ptr ? *A.rows_ptr : A.rows_const;
     const int64_t row0 = (int64_t)blockIdx.x * TM;
     if (row0 >= rows) return;                       // uniform: before any barrier / TMEM allocation
@@ -757,9 +761,9 @@ __device__ __forceinline__ float pow2_scale(float bound) {
 }
 
 __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const __grid_constant__ GemmArgs G) {
-    extern __shared__ unsigned char smem_raw[];
+    extern __shared__ __align__(1024) unsigned char smem_raw[];   // see act_tc_kernel: no pointer arithmetic on the base
     TSTAMP(0);
-    BwdTcSmem& S = *reinterpret_cast<BwdTcSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+    BwdTcSmem& S = *reinterpret_cast<BwdTcSmem*>(smem_raw);
     const int64_t rows = *G.rows_ptr;
     if (rows <= 0) return;
     const GemmPass& P = G.p[blockIdx.y];
