@@ -235,10 +235,9 @@ __device__ __forceinline__ const HeadW& pass_head(const ActArgs& a, int p) {
 
 // producer: layer 1 of `pass`, row r, the 8 hidden units of core column q of k-chunk c -> stage (fp16 hi/lo,
 // canonical layout).  W1/b1 are staged pre-multiplied by SA (a power of two: exact).
-__device__ __forceinline__ void produce_chunk(TcSmem& S, int pass, int c, int stage, int r, int q, float x0, float x1,
-                                              float x2, float x3, bool four) {
-    unsigned char* a_hi = S.stage[stage];
-    unsigned char* a_lo = a_hi + A_IMG;
+// layer 1 of `pass`, one row, the 8 hidden units of core column q of k-chunk c, as fp16 hi/lo (registers)
+__device__ __forceinline__ void layer1_chunk(const TcSmem& S, int pass, int c, int q, float x0, float x1, float x2, float x3,
+                                             bool four, uint4* hi, uint4* lo) {
     float hv[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
@@ -252,10 +251,7 @@ __device__ __forceinline__ void produce_chunk(TcSmem& S, int pass, int c, int st
         }
         hv[e] = fminf(fmaxf(h, 0.f), 60000.0f);
     }
-    uint4 hi, lo;
-    split8(hv, &hi, &lo);
-    *reinterpret_cast<uint4*>(a_hi + q * LBO_A + r * 16) = hi;
-    *reinterpret_cast<uint4*>(a_lo + q * LBO_A + r * 16) = lo;
+    split8(hv, hi, lo);
 }
 
 // epilogue: columns [64 q, 64 q + 64) of this thread's row of accumulator `d` -> partial head sums
@@ -379,10 +375,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) act_tc_kernel(const __grid_cons
             bool rec = false;
             auto produce_pass = [&](int pass, float x2, float x3) {
                 const bool four = pass >= PASS_QR1;
+                // software pipeline: chunk c + 1 is computed between the stores of chunk c and their proxy fence
+                uint4 hi, lo;
+                layer1_chunk(S, pass, 0, q, sx, sy, x2, x3, four, &hi, &lo);
                 for (int c = 0; c < NCHUNK; ++c, ++it) {
                     const int stage = it % NSTAGE;
                     mbar_wait(smem_u32(&S.empty[stage]), ((it / NSTAGE) & 1) ^ 1);
-                    produce_chunk(S, pass, c, stage, r, q, sx, sy, x2, x3, four);
+                    unsigned char* a_hi = S.stage[stage];
+                    *reinterpret_cast<uint4*>(a_hi + q * LBO_A + r * 16) = hi;
+                    *reinterpret_cast<uint4*>(a_hi + A_IMG + q * LBO_A + r * 16) = lo;
+                    if (c + 1 < NCHUNK) layer1_chunk(S, pass, c + 1, q, sx, sy, x2, x3, four, &hi, &lo);
                     fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
                     mbar_arrive_warp(smem_u32(&S.full[stage]));
                 }
