@@ -301,6 +301,21 @@ int rrl_dyn_pack(const float* lin0_w, const float* lin0_b, const float* lin1_w, 
                  const float* inputs_mu, const float* inputs_sigma, const float* max_logvar,
                  const float* min_logvar, int hidden, float* image, void* stream);
 
+/* Ensemble training (MPC.train, MPC.py:268-296).  The trainable parameters live in one flat fp32 "train arena" in the
+ * reference's layout, in this order: lin0_w [5][4][200], lin0_b [5][1][200], lin1_w [5][200][200], lin1_b, lin2_w,
+ * lin2_b, lin3_w [5][200][4], lin3_b [5][1][4], max_logvar [1][2], min_logvar [1][2]  (rrl_dyn_train_floats() floats);
+ * adam_m / adam_v mirror it.  wt: 2*5*200*200 floats (transposed lin1_w / lin2_w, kept by the kernel; rebuild with
+ * rrl_dyn_train_sync after the host wrote parameters).  partial: 32 floats scratch.  One rrl_dyn_train_step = one
+ * mini-batch of MPC.py:275-296 for all five nets: rows = idx[net][col0 .. col0+rows) of inputs [n][4] / targets [n][2]
+ * (device arrays, idx int64 [5][n_idx]); loss = NLL + 0.01*(sum max_logvar - sum min_logvar) + weight decays; torch Adam
+ * (lr, 0.9, 0.999, 1e-8); *step (device int64) counts the Adam steps; *ticket (device u32) must be 0. */
+int64_t rrl_dyn_train_floats(void);
+int rrl_dyn_train_sync(const float* params, float* wt, void* stream);
+int rrl_dyn_train_step(float* params, float* adam_m, float* adam_v, float* wt, float* partial, const float* mu,
+                       const float* sigma, const float* inputs, const float* targets, const int64_t* idx,
+                       int64_t n_idx, int64_t col0, int rows, float lr, int64_t* step, uint32_t* ticket,
+                       float* loss_out, void* stream);
+
 /* One MPC.act() for n_envs env copies = rrl_mpc_begin, then max_iters x (rrl_mpc_sample, rrl_mpc_rollout,
  * rrl_mpc_update), then rrl_mpc_finish.  All state is caller-owned device memory:
  *   prev_sol, mean, var : fp64 [n_envs][plan_hor*2]      active : i32 [n_envs] (CEM loop still running)

@@ -530,3 +530,326 @@ extern "C" int rrl_mpc_finish(const rrl_mpc_config_t* cfg, int64_t n_envs, const
     RRL_CHECK_LAUNCH();
     return 0;
 }
+
+// =====================================================================================================================
+// Ensemble training step (MPC.train, recovery_rl/MPC.py:268-296; PtModel.forward / compute_decays, config/maze.py:52-96):
+// ONE launch per mini-batch does, for all five bootstrap nets, the forward pass on the net's own bootstrap batch, the
+// Gaussian NLL + log-variance-bound + weight-decay loss, the backward pass and the torch-Adam update of every parameter.
+//   * one CTA per net (the nets share nothing but max/min_logvar, whose gradient partials are summed, in net order, by
+//     the last CTA to finish); activations of the <= 32-row batch stay in shared memory;
+//   * thread j owns output column j: forward  z[:, j] = sum_k in[:, k] W[k][j]  (W rows are contiguous: coalesced),
+//     weight gradient dW[k][j] = sum_r in[r][k] dz[r][j] computed straight into the Adam update (never materialised),
+//     input gradient through a maintained transposed copy W^T so that it has the same coalesced access pattern.
+// Parameters live in a flat "train arena" in the reference's layout (the torch PtModel parameters are views of it).
+// =====================================================================================================================
+namespace {
+
+constexpr int TB = 32;        // MPC.py:263 batch_size
+constexpr int HID = 200;      // hidden width of the reference ensemble
+constexpr int kTrainThreads = 256;
+
+struct DynTrainArgs {
+    float* P;            // params:  [w0 5x4x200][b0 5x200][w1 5x200x200][b1][w2][b2][w3 5x200x4][b3 5x4][max_lv 2][min_lv 2]
+    float* M;            // Adam exp_avg, same layout
+    float* V;            // Adam exp_avg_sq
+    float* WT;           // transposed copies: [w1T 5x200x200][w2T 5x200x200]
+    float* partial;      // [5][4] gradient partials of (max_lv[2], min_lv[2]) + [5] loss partials at offset 20
+    const float* mu;     // [4] input normalisation
+    const float* sigma;  // [4]
+    const float* inputs; // all training inputs  [n_data][4]
+    const float* targets;// all training targets [n_data][2]
+    const int64_t* idx;  // bootstrap indices [5][n_idx]
+    int64_t n_idx;       // columns of idx
+    int64_t col0;        // first column of this batch
+    int rows;            // rows of this batch (<= 32)
+    float lr, b1, b2, eps;
+    int64_t* step;       // device: Adam step count (incremented by the last CTA)
+    unsigned int* ticket;
+    float* loss_out;     // optional: total loss of this batch
+};
+
+constexpr int64_t oW0 = 0, oB0 = oW0 + 5 * 4 * HID, oW1 = oB0 + 5 * HID, oB1 = oW1 + 5 * HID * HID, oW2 = oB1 + 5 * HID,
+                  oB2 = oW2 + 5 * HID * HID, oW3 = oB2 + 5 * HID, oB3 = oW3 + 5 * HID * 4, oMax = oB3 + 5 * 4, oMin = oMax + 2,
+                  kTrainFloats = oMin + 2;
+
+struct TrainSmem {
+    float x[TB][4];
+    float z[3][TB][HID];      // pre-activations of the three hidden layers
+    float a[TB][HID];         // current activation (input of the layer being processed)
+    float d[TB][HID];         // current dz
+    float out[TB][4], dout[TB][4];
+    float red[8][8];
+};
+
+__device__ __forceinline__ float sigm(float x) { return 1.0f / (1.0f + expf(-x)); }
+__device__ __forceinline__ float dswish(float z) { const float s = sigm(z); return s * (1.0f + z * (1.0f - s)); }
+
+struct AdamC { float lr_bc1, bc2s, b1, b2, eps; };
+__device__ __forceinline__ float adam_apply(float* P, float* M, float* V, int64_t o, float g, const AdamC& c) {
+    float m = M[o], v = V[o];
+    m = m + (g - m) * (1.0f - c.b1);
+    v = v * c.b2 + (1.0f - c.b2) * g * g;
+    const float p = P[o] - c.lr_bc1 * (m / (sqrtf(v) / c.bc2s + c.eps));
+    M[o] = m; V[o] = v; P[o] = p;
+    return p;
+}
+
+__global__ void __launch_bounds__(kTrainThreads, 1) dyn_train_kernel(const DynTrainArgs A) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    TrainSmem& S = *reinterpret_cast<TrainSmem*>(smem_raw);
+    const int net = blockIdx.x, t = threadIdx.x, R = A.rows;
+    const float invR2 = 1.0f / (2.0f * (float)R);          // .mean(-1).mean(-1): 2 output dims x R rows
+    const double tstep = (double)(*A.step + 1);
+    AdamC ad;
+    ad.lr_bc1 = (float)((double)A.lr / (1.0 - pow((double)A.b1, tstep)));
+    ad.bc2s = (float)sqrt(1.0 - pow((double)A.b2, tstep));
+    ad.b1 = A.b1; ad.b2 = A.b2; ad.eps = A.eps;
+    float* W0 = A.P + oW0 + net * 4 * HID; float* B0 = A.P + oB0 + net * HID;
+    float* W1 = A.P + oW1 + (int64_t)net * HID * HID; float* B1 = A.P + oB1 + net * HID;
+    float* W2 = A.P + oW2 + (int64_t)net * HID * HID; float* B2 = A.P + oB2 + net * HID;
+    float* W3 = A.P + oW3 + net * HID * 4; float* B3 = A.P + oB3 + net * 4;
+    float* W1T = A.WT + (int64_t)net * HID * HID; float* W2T = A.WT + (int64_t)(5 + net) * HID * HID;
+    const float mxl[2] = {A.P[oMax], A.P[oMax + 1]}, mnl[2] = {A.P[oMin], A.P[oMin + 1]};
+    // ---- gather + normalise the batch (MPC.py:283-286, config/maze.py:74) ----
+    if (t < TB * 4) {
+        const int r = t >> 2, i = t & 3;
+        float v = 0.f;
+        if (r < R) {
+            const int64_t row = A.idx[(int64_t)net * A.n_idx + A.col0 + r];
+            v = (A.inputs[row * 4 + i] - A.mu[i]) / A.sigma[i];
+        }
+        S.x[r][i] = v;
+    }
+    __syncthreads();
+    const int j = t;                 // output column owned by this thread (t < HID)
+    // ---- forward ----
+    if (j < HID) {
+        const float w0 = W0[j], w1 = W0[HID + j], w2 = W0[2 * HID + j], w3 = W0[3 * HID + j], b = B0[j];
+        for (int r = 0; r < TB; ++r) {
+            const float z = fmaf(S.x[r][3], w3, fmaf(S.x[r][2], w2, fmaf(S.x[r][1], w1, fmaf(S.x[r][0], w0, b))));
+            S.z[0][r][j] = z;
+            S.a[r][j] = swishf(z);
+        }
+    }
+    __syncthreads();
+    for (int l = 1; l <= 2; ++l) {
+        const float* W = l == 1 ? W1 : W2;
+        const float* Bv = l == 1 ? B1 : B2;
+        float acc[TB];
+        if (j < HID) {
+#pragma unroll
+            for (int r = 0; r < TB; ++r) acc[r] = 0.f;
+            for (int k = 0; k < HID; k += 4) {
+                const float wa = W[(k + 0) * HID + j], wb = W[(k + 1) * HID + j], wc = W[(k + 2) * HID + j], wd = W[(k + 3) * HID + j];
+#pragma unroll
+                for (int r = 0; r < TB; ++r) {
+                    const float4 av = *reinterpret_cast<const float4*>(&S.a[r][k]);
+                    acc[r] = fmaf(av.w, wd, fmaf(av.z, wc, fmaf(av.y, wb, fmaf(av.x, wa, acc[r]))));
+                }
+            }
+        }
+        __syncthreads();             // everyone has finished reading S.a
+        if (j < HID) {
+            const float b = Bv[j];
+#pragma unroll
+            for (int r = 0; r < TB; ++r) {
+                const float z = acc[r] + b;
+                S.z[l][r][j] = z;
+                S.a[r][j] = swishf(z);
+            }
+        }
+        __syncthreads();
+    }
+    // output layer (4 outputs) + loss gradients; thread (r, o)
+    if (t < TB * 4) {
+        const int r = t >> 2, o = t & 3;
+        float acc = B3[o];
+        for (int k = 0; k < HID; ++k) acc = fmaf(S.a[r][k], W3[k * 4 + o], acc);
+        S.out[r][o] = acc;
+    }
+    __syncthreads();
+    if (t < TB * 2) {                // thread (r, dim): mean / log-variance pair of one output dimension
+        const int r = t >> 1, dm = t & 1;
+        float dmean = 0.f, draw = 0.f;
+        if (r < R) {
+            const int64_t row = A.idx[(int64_t)net * A.n_idx + A.col0 + r];
+            const float mean = S.out[r][dm], raw = S.out[r][2 + dm], targ = A.targets[row * 2 + dm];
+            const float lv1 = mxl[dm] - softplusf(mxl[dm] - raw);
+            const float lv = mnl[dm] + softplusf(lv1 - mnl[dm]);
+            const float inv_var = expf(-lv), e = mean - targ;
+            dmean = 2.0f * e * inv_var * invR2;
+            const float dlv = (1.0f - e * e * inv_var) * invR2;
+            const float s_min = sigm(lv1 - mnl[dm]);       // d lv / d lv1
+            const float s_max = sigm(mxl[dm] - raw);       // d lv1 / d raw
+            draw = dlv * s_min * s_max;
+        }
+        S.dout[r][dm] = dmean;
+        S.dout[r][2 + dm] = draw;
+    }
+    __syncthreads();
+    // per-net partials of the shared log-variance bounds and of the loss (fixed order: deterministic)
+    if (t == 0) {
+        float g[4] = {0.f, 0.f, 0.f, 0.f}, ls = 0.f;
+        for (int r = 0; r < R; ++r)
+            for (int dm = 0; dm < 2; ++dm) {
+                const int64_t row = A.idx[(int64_t)net * A.n_idx + A.col0 + r];
+                const float mean = S.out[r][dm], raw = S.out[r][2 + dm], targ = A.targets[row * 2 + dm];
+                const float lv1 = mxl[dm] - softplusf(mxl[dm] - raw);
+                const float lv = mnl[dm] + softplusf(lv1 - mnl[dm]);
+                const float inv_var = expf(-lv), e = mean - targ;
+                const float dlv = (1.0f - e * e * inv_var) * invR2;
+                const float s_min = sigm(lv1 - mnl[dm]), s_max = sigm(mxl[dm] - raw);
+                g[dm] += dlv * s_min * (1.0f - s_max);      // d loss / d max_logvar[dm]
+                g[2 + dm] += dlv * (1.0f - s_min);          // d loss / d min_logvar[dm]
+                ls += (e * e * inv_var + lv) * invR2;
+            }
+        for (int i = 0; i < 4; ++i) A.partial[net * 4 + i] = g[i];
+        A.partial[20 + net] = ls;
+    }
+    // ---- backward: layer 3 ----
+    // da2[r][k] = sum_o dout[r][o] W3[k][o];  dz2 = da2 * swish'(z2)   (old W3), then dW3 / db3 -> Adam
+    if (j < HID) {
+        const float4 w = *reinterpret_cast<const float4*>(W3 + j * 4);
+        float g[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int r = 0; r < TB; ++r) {
+            const float4 dv = *reinterpret_cast<const float4*>(S.dout[r]);
+            const float da = dv.x * w.x + dv.y * w.y + dv.z * w.z + dv.w * w.w;
+            const float a2 = S.a[r][j];
+            g[0] = fmaf(a2, dv.x, g[0]); g[1] = fmaf(a2, dv.y, g[1]); g[2] = fmaf(a2, dv.z, g[2]); g[3] = fmaf(a2, dv.w, g[3]);
+            S.d[r][j] = da * dswish(S.z[2][r][j]);
+        }
+        const float wv[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+        for (int o = 0; o < 4; ++o) adam_apply(A.P, A.M, A.V, oW3 + net * HID * 4 + j * 4 + o, g[o] + 0.00075f * wv[o], ad);
+    }
+    if (t >= 224 && t < 228) {       // db3
+        const int o = t - 224;
+        float g = 0.f;
+        for (int r = 0; r < TB; ++r) g += S.dout[r][o];
+        adam_apply(A.P, A.M, A.V, oB3 + net * 4 + o, g, ad);
+    }
+    __syncthreads();
+    // ---- backward: layers 2 and 1 ----
+    for (int l = 2; l >= 1; --l) {
+        float* W = l == 2 ? W2 : W1;
+        float* WT = l == 2 ? W2T : W1T;
+        const int64_t oW = (l == 2 ? oW2 : oW1) + (int64_t)net * HID * HID, oB = (l == 2 ? oB2 : oB1) + net * HID;
+        // input of layer l = swish(z[l-1]); rebuild it in S.a
+        if (j < HID)
+            for (int r = 0; r < TB; ++r) S.a[r][j] = swishf(S.z[l - 1][r][j]);
+        // da[r][k] = sum_j dz[r][j] W[k][j] = sum_j dz[r][j] WT[j][k]: thread k, coalesced over WT rows
+        float acc[TB];
+        if (j < HID) {
+#pragma unroll
+            for (int r = 0; r < TB; ++r) acc[r] = 0.f;
+            for (int q = 0; q < HID; q += 4) {
+                const float wa = WT[(q + 0) * HID + j], wb = WT[(q + 1) * HID + j], wc = WT[(q + 2) * HID + j], wd = WT[(q + 3) * HID + j];
+#pragma unroll
+                for (int r = 0; r < TB; ++r) {
+                    const float4 dv = *reinterpret_cast<const float4*>(&S.d[r][q]);
+                    acc[r] = fmaf(dv.w, wd, fmaf(dv.z, wc, fmaf(dv.y, wb, fmaf(dv.x, wa, acc[r]))));
+                }
+            }
+        }
+        __syncthreads();             // S.a rebuilt; every thread has its da column in registers
+        // dW[k][j] = sum_r a[r][k] dz[r][j] (+ decay) -> Adam on W[k][j] and its transposed copy; db[j] = sum_r dz[r][j]
+        if (j < HID) {
+            float dz[TB], gb = 0.f;
+#pragma unroll
+            for (int r = 0; r < TB; ++r) { dz[r] = S.d[r][j]; gb += dz[r]; }
+            for (int k = 0; k < HID; ++k) {
+                float g = 0.f;
+#pragma unroll
+                for (int r = 0; r < TB; ++r) g = fmaf(S.a[r][k], dz[r], g);
+                const float w = W[k * HID + j];
+                const float p = adam_apply(A.P, A.M, A.V, oW + (int64_t)k * HID + j, g + 0.0005f * w, ad);
+                WT[(int64_t)j * HID + k] = p;
+            }
+            adam_apply(A.P, A.M, A.V, oB + j, gb, ad);
+        }
+        __syncthreads();             // all reads of S.d done
+        if (j < HID)
+#pragma unroll
+            for (int r = 0; r < TB; ++r) S.d[r][j] = acc[r] * dswish(S.z[l - 1][r][j]);
+        __syncthreads();
+    }
+    // ---- backward: layer 0 (K = 4) ----
+    if (j < HID) {
+        float g[4] = {0.f, 0.f, 0.f, 0.f}, gb = 0.f;
+        for (int r = 0; r < TB; ++r) {
+            const float dz = S.d[r][j];
+            g[0] = fmaf(S.x[r][0], dz, g[0]); g[1] = fmaf(S.x[r][1], dz, g[1]);
+            g[2] = fmaf(S.x[r][2], dz, g[2]); g[3] = fmaf(S.x[r][3], dz, g[3]);
+            gb += dz;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int64_t o = oW0 + net * 4 * HID + i * HID + j;
+            adam_apply(A.P, A.M, A.V, o, g[i] + 0.00025f * A.P[o], ad);
+        }
+        adam_apply(A.P, A.M, A.V, oB0 + net * HID + j, gb, ad);
+    }
+    // ---- shared log-variance bounds + step count: last CTA to finish ----
+    __syncthreads();
+    if (t == 0) {
+        __threadfence();
+        const unsigned int tk = atomicAdd(A.ticket, 1u);
+        if (tk == gridDim.x - 1) {
+            __threadfence();
+            float g[4] = {0.01f, 0.01f, -0.01f, -0.01f};     // loss = 0.01 * (max_logvar.sum() - min_logvar.sum()) + ...
+            float ls = 0.f;
+            for (int n = 0; n < 5; ++n) {
+                for (int i = 0; i < 4; ++i) g[i] += A.partial[n * 4 + i];
+                ls += A.partial[20 + n];
+            }
+            for (int i = 0; i < 4; ++i) adam_apply(A.P, A.M, A.V, oMax + i, g[i], ad);
+            if (A.loss_out) *A.loss_out = ls;
+            *A.step += 1;
+            *A.ticket = 0;
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" int64_t rrl_dyn_train_floats(void) { return kTrainFloats; }
+
+extern "C" int rrl_dyn_train_step(float* params, float* adam_m, float* adam_v, float* wt, float* partial, const float* mu,
+                                  const float* sigma, const float* inputs, const float* targets, const int64_t* idx,
+                                  int64_t n_idx, int64_t col0, int rows, float lr, int64_t* step, uint32_t* ticket,
+                                  float* loss_out, void* stream) {
+    RRL_CHECK_ARG(params && adam_m && adam_v && wt && partial && mu && sigma && inputs && targets && idx && step && ticket,
+                  "null argument");
+    RRL_CHECK_ARG(rows > 0 && rows <= TB && col0 >= 0 && col0 + rows <= n_idx, "bad batch window");
+    DynTrainArgs A;
+    A.P = params; A.M = adam_m; A.V = adam_v; A.WT = wt; A.partial = partial; A.mu = mu; A.sigma = sigma;
+    A.inputs = inputs; A.targets = targets; A.idx = idx; A.n_idx = n_idx; A.col0 = col0; A.rows = rows;
+    A.lr = lr; A.b1 = 0.9f; A.b2 = 0.999f; A.eps = 1e-8f; A.step = step; A.ticket = ticket; A.loss_out = loss_out;
+    static bool configured = false;
+    const size_t smem = sizeof(TrainSmem);
+    if (!configured) {
+        RRL_CUDA(cudaFuncSetAttribute(dyn_train_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    dyn_train_kernel<<<5, kTrainThreads, smem, (cudaStream_t)stream>>>(A);
+    RRL_CHECK_LAUNCH();
+    return 0;
+}
+
+// transposed copies of lin1_w / lin2_w (operand of the input-gradient pass); call after the host wrote the parameters
+namespace {
+__global__ void dyn_transpose_kernel(const float* __restrict__ P, float* __restrict__ WT) {
+    const int64_t i = blockIdx.x * 256ll + threadIdx.x;
+    if (i >= 2ll * 5 * HID * HID) return;
+    const int l = (int)(i / (5ll * HID * HID));
+    const int64_t rem = i % (5ll * HID * HID);
+    const int net = (int)(rem / (HID * HID)), k = (int)((rem % (HID * HID)) / HID), j = (int)(rem % HID);
+    WT[(int64_t)(l * 5 + net) * HID * HID + (int64_t)j * HID + k] = P[(l == 0 ? oW1 : oW2) + (int64_t)net * HID * HID + (int64_t)k * HID + j];
+}
+}  // namespace
+extern "C" int rrl_dyn_train_sync(const float* params, float* wt, void* stream) {
+    RRL_CHECK_ARG(params && wt, "null argument");
+    dyn_transpose_kernel<<<(unsigned)((2ll * 5 * HID * HID + 255) / 256), 256, 0, (cudaStream_t)stream>>>(params, wt);
+    RRL_CHECK_LAUNCH();
+    return 0;
+}

@@ -6,10 +6,11 @@ where:
   * `act` -- the hot part (5 CEM iterations x plan_hor steps x popsize x npart particles through the ensemble and
     the safety critic) -- runs entirely in the CUDA kernels of csrc/mpc.cu, for `n_envs` env copies at once; the
     ensemble is packed once per `train` into a padded k-major image the planner streams.
-  * `train` (MPC.py:213-309: bootstrapped NLL fit, batch 32, Adam 1e-3) is the rare step (once per
-    `recovery_policy_update_freq` episodes).  It keeps the reference's data handling and numpy RNG calls and runs
-    the ensemble's forward / backward / Adam through torch on the GPU (library kernels, not hand-written ones --
-    DESIGN.md lists the hand-written training kernels as the next step of this row).
+  * `train` (MPC.py:213-309: bootstrapped NLL fit, batch 32, Adam 1e-3) keeps the reference's data handling and
+    numpy RNG calls; every mini-batch is ONE launch of `dyn_train_kernel` (csrc/mpc.cu: forward, Gaussian NLL +
+    log-variance bounds + weight decays, backward and torch-Adam for all five nets).  The PtModel parameters are
+    views of the flat train arena that kernel updates.  (`train(..., use_torch=True)` runs the same schedule through
+    torch autograd on the GPU: kept as a cross-check, not the product path.)
 There is no CPU path: construction raises without a CUDA device.
 """
 import numpy as np
@@ -34,17 +35,37 @@ class PtModel(nn.Module):
     def __init__(self, ensemble_size, in_features, out_features):
         super().__init__()
         from config.utils import get_affine_params
+        native.require_cuda()
+        dev = torch.device("cuda", torch.cuda.current_device())
         self.num_nets = ensemble_size
         self.in_features = in_features
         self.out_features = out_features
-        self.lin0_w, self.lin0_b = get_affine_params(ensemble_size, in_features, HIDDEN)
-        self.lin1_w, self.lin1_b = get_affine_params(ensemble_size, HIDDEN, HIDDEN)
-        self.lin2_w, self.lin2_b = get_affine_params(ensemble_size, HIDDEN, HIDDEN)
-        self.lin3_w, self.lin3_b = get_affine_params(ensemble_size, HIDDEN, out_features)
-        self.inputs_mu = nn.Parameter(torch.zeros(in_features), requires_grad=False)
-        self.inputs_sigma = nn.Parameter(torch.zeros(in_features), requires_grad=False)
-        self.max_logvar = nn.Parameter(torch.ones(1, out_features // 2, dtype=torch.float32) / 2.0)
-        self.min_logvar = nn.Parameter(-torch.ones(1, out_features // 2, dtype=torch.float32) * 10.0)
+        # the reference's init draws, in its order (scipy truncnorm on the numpy global RNG) ...
+        init = []
+        for n_in, n_out in ((in_features, HIDDEN), (HIDDEN, HIDDEN), (HIDDEN, HIDDEN), (HIDDEN, out_features)):
+            w, b = get_affine_params(ensemble_size, n_in, n_out)
+            init += [w.data, b.data]
+        init += [torch.ones(1, out_features // 2, dtype=torch.float32) / 2.0,
+                 -torch.ones(1, out_features // 2, dtype=torch.float32) * 10.0]
+        # ... stored in ONE flat device arena (the layout dyn_train_kernel updates); the parameters are views of it
+        self.train_arena = torch.zeros(native.dyn_train_floats(), device=dev)
+        names = ["lin0_w", "lin0_b", "lin1_w", "lin1_b", "lin2_w", "lin2_b", "lin3_w", "lin3_b", "max_logvar", "min_logvar"]
+        off = 0
+        for name, t in zip(names, init):
+            view = self.train_arena[off:off + t.numel()].view(t.shape)
+            view.copy_(t)
+            self.register_parameter(name, nn.Parameter(view))
+            off += t.numel()
+        assert off == self.train_arena.numel()
+        self.inputs_mu = nn.Parameter(torch.zeros(in_features, device=dev), requires_grad=False)
+        self.inputs_sigma = nn.Parameter(torch.zeros(in_features, device=dev), requires_grad=False)
+        self.adam_m = torch.zeros_like(self.train_arena)
+        self.adam_v = torch.zeros_like(self.train_arena)
+        self.wt = torch.zeros(2 * ensemble_size * HIDDEN * HIDDEN, device=dev)
+        self.partial = torch.zeros(32, device=dev)
+        self.adam_step = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.ticket = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.loss_dev = torch.zeros(1, device=dev)
 
     def compute_decays(self):
         return (0.00025 * (self.lin0_w ** 2).sum() / 2.0 + 0.0005 * (self.lin1_w ** 2).sum() / 2.0 +
@@ -146,7 +167,7 @@ class MPC(Controller):
         return self.prev_sol_dev[0].cpu().numpy()
 
     # ---- MPC.py:213-309 -----------------------------------------------------------------------------------
-    def train(self, obs_trajs, acs_trajs, random=False, next_obs=False, epochs=None):
+    def train(self, obs_trajs, acs_trajs, random=False, next_obs=False, epochs=None, use_torch=False):
         new_train_in, new_train_targs = [], []
         if random:
             assert next_obs is not None
@@ -166,8 +187,23 @@ class MPC(Controller):
             epochs = self.model_train_cfg['epochs']
         batch_size = 32
         num_batch = int(np.ceil(idxs.shape[-1] / batch_size))
-        tin_all = torch.from_numpy(self.train_in).to(self.device).float()
-        ttg_all = torch.from_numpy(self.train_targs).to(self.device).float()
+        tin_all = torch.from_numpy(self.train_in).to(self.device).float().contiguous()
+        ttg_all = torch.from_numpy(self.train_targs).to(self.device).float().contiguous()
+        if not use_torch:
+            native.dyn_train_sync(m.train_arena, m.wt)
+            mu, sigma = m.inputs_mu.data.reshape(-1).contiguous(), m.inputs_sigma.data.reshape(-1).contiguous()
+            n_idx = idxs.shape[-1]
+            for _ in range(epochs):
+                idx_dev = torch.from_numpy(np.ascontiguousarray(idxs)).to(self.device)
+                for b in range(num_batch):
+                    rows = min(batch_size, n_idx - b * batch_size)
+                    native.dyn_train_step(m.train_arena, m.adam_m, m.adam_v, m.wt, m.partial, mu, sigma, tin_all, ttg_all,
+                                          idx_dev, b * batch_size, rows, 0.001, m.adam_step, m.ticket, loss_out=m.loss_dev)
+                idxs = shuffle_rows(idxs)
+            self.last_train_loss = float(m.loss_dev.item()) + float(
+                (0.01 * (m.max_logvar.sum() - m.min_logvar.sum()) + m.compute_decays()).item())
+            self.pack_model()
+            return
         for _ in range(epochs):
             idx_dev = torch.from_numpy(idxs).to(self.device)
             for b in range(num_batch):

@@ -365,3 +365,20 @@ def mpc_update(cfg, n, it, samples, row_cost, active, mean, var, stream=None):
 def mpc_finish(cfg, n, mean, prev_sol, action, mask=None, stream=None):
     _check(lib().rrl_mpc_finish(C.byref(cfg), C.c_int64(n), p(mean, "f64"), p(mask, "u8"), p(prev_sol, "f64"),
                                 p(action, "f64"), _stream(stream)), "rrl_mpc_finish")
+
+
+def dyn_train_floats():
+    lib().rrl_dyn_train_floats.restype = C.c_int64
+    return int(lib().rrl_dyn_train_floats())
+
+
+def dyn_train_sync(params, wt, stream=None):
+    _check(lib().rrl_dyn_train_sync(p(params, "f32"), p(wt, "f32"), _stream(stream)), "rrl_dyn_train_sync")
+
+
+def dyn_train_step(params, adam_m, adam_v, wt, partial, mu, sigma, inputs, targets, idx, col0, rows, lr, step, ticket,
+                   loss_out=None, stream=None):
+    _check(lib().rrl_dyn_train_step(p(params, "f32"), p(adam_m, "f32"), p(adam_v, "f32"), p(wt, "f32"), p(partial, "f32"),
+                                    p(mu, "f32"), p(sigma, "f32"), p(inputs, "f32"), p(targets, "f32"), p(idx, "i64"),
+                                    C.c_int64(idx.shape[1]), C.c_int64(col0), C.c_int(rows), C.c_float(lr), p(step, "i64"),
+                                    p(ticket, "i32"), p(loss_out, "f32"), _stream(stream)), "rrl_dyn_train_step")

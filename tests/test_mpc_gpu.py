@@ -37,6 +37,15 @@ def _agent_arena(native, cuda, ag, z, tag):
     return VF()
 
 
+def _load_ensemble(mpc, ora, cuda):
+    """copy the oracle's (== the reference's) ensemble into the product model, by parameter name."""
+    src = dict(ora.model.named())
+    with torch.no_grad():
+        for n, p in mpc.model.named_parameters():
+            p.copy_(src[n].detach().reshape(p.shape).to(cuda))
+    mpc.pack_model()
+
+
 @pytest.mark.parametrize("tag", ["nav", "maze"])
 def test_planner_matches_reference(native, cuda, golden_dir, tag):
     z = np.load(os.path.join(golden_dir, "mpc.npz"))
@@ -47,18 +56,30 @@ def test_planner_matches_reference(native, cuda, golden_dir, tag):
     mpc = _product_mpc(z, tag)
     for n, p in mpc.model.named_parameters():                       # same scipy / numpy stream as the reference
         assert np.array_equal(p.detach().cpu().numpy().ravel()[::stride], z[P + "init_" + n]), n
-    # MPC.train through the drop-in class (torch on the GPU): same bootstrap indices, same schedule
+    # MPC.train through the drop-in class: same bootstrap indices, same schedule; every mini-batch is one launch of
+    # dyn_train_kernel (forward + NLL + backward + Adam for the five nets)
     np.random.seed(int(z[P + "train_seed"]))
     mpc.train(z[P + "train_obs"], z[P + "train_acs"], random=True, next_obs=z[P + "train_next"],
               epochs=int(z[P + "train_epochs"]))
+    n_steps = int(z[P + "train_epochs"]) * int(np.ceil(len(z[P + "train_obs"]) / 32))
+    assert int(mpc.model.adam_step.item()) == n_steps and int(mpc.model.ticket.item()) == 0
     for n, p in mpc.model.named_parameters():
         got = p.detach().cpu().numpy().ravel()[::stride]
         assert np.allclose(got, z[P + "trained_" + n], rtol=2e-3, atol=2e-5), (n, np.abs(got - z[P + "trained_" + n]).max())
+    assert abs(mpc.last_train_loss - ora.losses[-1]) < 1e-3 * (1 + abs(ora.losses[-1])), (mpc.last_train_loss, ora.losses[-1])
+    # cross-check: the same schedule through torch autograd on the GPU lands on the same parameters
+    mpc_t = _product_mpc(z, tag)
+    np.random.seed(int(z[P + "train_seed"]))
+    mpc_t.train(z[P + "train_obs"], z[P + "train_acs"], random=True, next_obs=z[P + "train_next"],
+                epochs=int(z[P + "train_epochs"]), use_torch=True)
+    # (Adam turns a near-zero gradient into a step of up to lr regardless of its size, so isolated entries may differ
+    # by a few lr = 1e-3 steps between two fp32 evaluation orders: bound those, require the bulk to agree tightly)
+    for (n, p), (_, pt) in zip(mpc.model.named_parameters(), mpc_t.model.named_parameters()):
+        diff = (p - pt).abs()
+        ok = diff <= 2e-5 + 2e-3 * pt.abs()
+        assert ok.float().mean().item() > 0.999 and diff.max().item() < 5e-3, (n, ok.float().mean().item(), diff.max().item())
     # the planner kernels on the reference's exact ensemble (teacher forcing) and safety critic
-    with torch.no_grad():
-        for (n, p), (_, q) in zip(mpc.model.named_parameters(), ora.model.named()):
-            p.copy_(q.detach().reshape(p.shape).to(cuda))
-    mpc.pack_model()
+    _load_ensemble(mpc, ora, cuda)
     mpc.update_value_func(_agent_arena(native, cuda, ag, z, tag))
     ac_seqs, eps, zs, eps2 = mpc_noise(z, tag)
     pop, npart = int(z[P + "popsize"]), int(z[P + "npart"])
@@ -93,10 +114,7 @@ def test_planner_batched_envs_equal_single(native, cuda, golden_dir):
     E = 3
     ms = [_product_mpc(z, tag, n_envs=1) for _ in range(E)] + [_product_mpc(z, tag, n_envs=E)]
     for m in ms:
-        with torch.no_grad():
-            for (n, p), (_, q) in zip(m.model.named_parameters(), ora.model.named()):
-                p.copy_(q.detach().reshape(p.shape).to(cuda))
-        m.pack_model()
+        _load_ensemble(m, ora, cuda)
         m.update_value_func(vf)
         m.has_been_trained = True
     rs = np.random.RandomState(0)
