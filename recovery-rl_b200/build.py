@@ -24,6 +24,7 @@ SOURCES = [
     ("agent.cu", []),
     ("agent_tc.cu", []),
     ("mpc.cu", []),
+    ("mpc_tc.cu", []),
 ]
 
 

@@ -216,6 +216,25 @@ struct ActArgs {
 };
 
 
+// mpc_tc.cu: the model-based planner's rollout on tcgen05
+struct MpcTcArgs {
+    const float* dyn;      // packed ensemble incl. its tcgen05 images (mpc_layout.cuh)
+    HeadW qr1, qr2;
+    const double* state;   // [2][E]
+    const float* samples;  // [E][pop][hor*2]
+    const float* eps;      // NULL (Philox) or [E][hor][nets][pop*npn][2]
+    const int32_t* active; // [E] or NULL
+    float* row_cost;       // [E][pop][npart]
+    int64_t E;
+    int pop, hor, npart, npn;
+    uint64_t seed;
+    uint32_t stream_id;
+    const int64_t* counters;
+    int iter;
+};
+int mpc_rollout_tc_launch(const MpcTcArgs& T, cudaStream_t st);
+int dyn_tc_images_launch(float* dyn_image, cudaStream_t st);
+
 // agent_tc.cu
 int act_tc_launch(const ActArgs& A, const float* arena, const Layout& L, cudaStream_t st);
 int tc_images_launch(float* arena, const Layout& L, cudaStream_t st);

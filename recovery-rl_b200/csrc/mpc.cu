@@ -15,29 +15,12 @@
 // horizon (TS-infinity, MPC.py:441-467), so a 64-row tile shares one net's weights.
 // This file is the fp32 SIMT implementation (4 tile GEMMs per horizon step: Q_risk head 1 / 2, ensemble layers 1 / 2).
 #include "mlp_tile.cuh"
+#include "mpc_layout.cuh"
 
 using namespace rrl;
+using namespace rrl::dyn;
 
 namespace {
-
-constexpr int PBM = 64;   // rows per tile
-constexpr int NETS = 5;   // config/default.py:91
-constexpr int DYN_IN = 4, DYN_OUT = 4;
-
-// ---- dyn image offsets (floats) ----
-constexpr int64_t kW0 = 0;                                  // [5][4][256]   k-major layer 0
-constexpr int64_t kB0 = kW0 + (int64_t)NETS * DYN_IN * H;   // [5][256]
-constexpr int64_t kW1 = kB0 + (int64_t)NETS * H;            // [5][256][256] k-major
-constexpr int64_t kB1 = kW1 + (int64_t)NETS * H * H;
-constexpr int64_t kW2 = kB1 + (int64_t)NETS * H;
-constexpr int64_t kB2 = kW2 + (int64_t)NETS * H * H;
-constexpr int64_t kW3 = kB2 + (int64_t)NETS * H;            // [5][4][256]   w3[o][k] = lin3_w[k][o]
-constexpr int64_t kB3 = kW3 + (int64_t)NETS * DYN_OUT * H;  // [5][4]
-constexpr int64_t kMu = kB3 + NETS * DYN_OUT;               // [4]
-constexpr int64_t kSigma = kMu + 4;                         // [4]
-constexpr int64_t kMaxLv = kSigma + 4;                      // [2]
-constexpr int64_t kMinLv = kMaxLv + 2;                      // [2]
-constexpr int64_t kDynFloats = ((kMinLv + 2 + 3) / 4) * 4;
 
 struct PlanSmem {
     FwdSmem<PBM> f;
@@ -58,7 +41,7 @@ struct PackArgs {
 };
 __global__ void __launch_bounds__(256) dyn_pack_kernel(const PackArgs A) {
     const int64_t i = blockIdx.x * 256ll + threadIdx.x;
-    if (i >= kDynFloats) return;
+    if (i >= kDynSimtFloats) return;
     const int hid = A.hid;
     float v = 0.f;
     if (i < kB0) {
@@ -438,9 +421,9 @@ extern "C" int rrl_dyn_pack(const float* lin0_w, const float* lin0_b, const floa
     RRL_CHECK_ARG(hidden > 0 && hidden <= H, "hidden width must be in [1, 256]");
     PackArgs A = {lin0_w, lin0_b, lin1_w, lin1_b, lin2_w, lin2_b, lin3_w, lin3_b, inputs_mu, inputs_sigma, max_logvar,
                   min_logvar, image, hidden};
-    dyn_pack_kernel<<<(unsigned)((kDynFloats + 255) / 256), 256, 0, (cudaStream_t)stream>>>(A);
+    dyn_pack_kernel<<<(unsigned)((kDynSimtFloats + 255) / 256), 256, 0, (cudaStream_t)stream>>>(A);
     RRL_CHECK_LAUNCH();
-    return 0;
+    return rrl::dyn_tc_images_launch(image, (cudaStream_t)stream);   // fp16 hi/lo operand images of lin1 / lin2 (mpc_tc.cu)
 }
 
 extern "C" int rrl_mpc_begin(const rrl_mpc_config_t* cfg, int64_t n_envs, const double* prev_sol, double* mean, double* var,
@@ -489,6 +472,13 @@ extern "C" int rrl_mpc_rollout(const rrl_mpc_config_t* cfg, const rrl_agent_conf
     A.E = n_envs; A.pop = cfg->popsize; A.hor = cfg->plan_hor; A.npart = cfg->npart; A.npn = cfg->npart / NETS;
     A.tiles_per_net = (A.pop * A.npn + PBM - 1) / PBM;
     A.seed = cfg->seed; A.stream_id = (uint32_t)cfg->stream_id; A.counters = counters; A.iter = iter;
+    if (agent_cfg->use_tensor_cores) {   // tcgen05 planner (mpc_tc.cu): same rows, same noise indexing
+        rrl::MpcTcArgs T;
+        T.dyn = dyn_image; T.qr1 = A.qr1; T.qr2 = A.qr2; T.state = state; T.samples = samples; T.eps = eps; T.active = active;
+        T.row_cost = row_cost; T.E = n_envs; T.pop = A.pop; T.hor = A.hor; T.npart = A.npart; T.npn = A.npn;
+        T.seed = A.seed; T.stream_id = A.stream_id; T.counters = counters; T.iter = iter;
+        return rrl::mpc_rollout_tc_launch(T, (cudaStream_t)stream);
+    }
     static bool configured = false;
     const size_t smem = sizeof(PlanSmem);
     if (!configured) {

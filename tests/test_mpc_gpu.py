@@ -26,10 +26,10 @@ def _product_mpc(z, tag, n_envs=1):
     return MPC(cc, n_envs=n_envs)
 
 
-def _agent_arena(native, cuda, ag, z, tag):
+def _agent_arena(native, cuda, ag, z, tag, tensor_cores=0):
     from recovery_rl.arena import AgentArena
     sc = float(np.float32(float(z[tag + "_scale"])))
-    ar = AgentArena(cuda, max_batch=64, action_scale=(sc, sc))
+    ar = AgentArena(cuda, max_batch=64, action_scale=(sc, sc), use_tensor_cores=tensor_cores)
     ar.load_modules(ag.nets())
 
     class VF(object):
@@ -46,8 +46,10 @@ def _load_ensemble(mpc, ora, cuda):
     mpc.pack_model()
 
 
+@pytest.mark.parametrize("tensor_cores", [0, 1])
 @pytest.mark.parametrize("tag", ["nav", "maze"])
-def test_planner_matches_reference(native, cuda, golden_dir, tag):
+def test_planner_matches_reference(native, cuda, golden_dir, tag, tensor_cores):
+    """tensor_cores = 1: the rollout's 256x256 contractions run on tcgen05 (mpc_tc.cu) and meet the same bar."""
     z = np.load(os.path.join(golden_dir, "mpc.npz"))
     za = np.load(os.path.join(golden_dir, "agent_algos_b64.npz"))
     P = tag + "_"
@@ -80,7 +82,7 @@ def test_planner_matches_reference(native, cuda, golden_dir, tag):
         assert ok.float().mean().item() > 0.999 and diff.max().item() < 5e-3, (n, ok.float().mean().item(), diff.max().item())
     # the planner kernels on the reference's exact ensemble (teacher forcing) and safety critic
     _load_ensemble(mpc, ora, cuda)
-    mpc.update_value_func(_agent_arena(native, cuda, ag, z, tag))
+    mpc.update_value_func(_agent_arena(native, cuda, ag, z, tag, tensor_cores))
     ac_seqs, eps, zs, eps2 = mpc_noise(z, tag)
     pop, npart = int(z[P + "popsize"]), int(z[P + "npart"])
     # _compile_cost (MPC.py:374-416)
@@ -104,13 +106,14 @@ def test_planner_matches_reference(native, cuda, golden_dir, tag):
     assert np.isfinite(a).all() and (np.abs(a) <= scale + 1e-6).all()
 
 
-def test_planner_batched_envs_equal_single(native, cuda, golden_dir):
+@pytest.mark.parametrize("tensor_cores", [0, 1])
+def test_planner_batched_envs_equal_single(native, cuda, golden_dir, tensor_cores):
     """n_envs copies planned in one launch == each env planned alone (rows of different envs never mix)."""
     z = np.load(os.path.join(golden_dir, "mpc.npz"))
     za = np.load(os.path.join(golden_dir, "agent_algos_b64.npz"))
     tag, P = "maze", "maze_"
     ora, ag = mpc_oracle(z, za, tag, trained=True)
-    vf = _agent_arena(native, cuda, ag, z, tag)
+    vf = _agent_arena(native, cuda, ag, z, tag, tensor_cores)
     E = 3
     ms = [_product_mpc(z, tag, n_envs=1) for _ in range(E)] + [_product_mpc(z, tag, n_envs=E)]
     for m in ms:
