@@ -17,13 +17,15 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--envs", type=int, default=2048)
     ap.add_argument("--popsize", type=int, default=50)
+    ap.add_argument("--tc", type=int, default=1, help="rollout contractions on tcgen05 (1) or fp32 SIMT (0)")
     args = ap.parse_args()
     from recovery_rl.engine import VecEngine
     from env.maze import get_offline_data
     torch.manual_seed(1)
     np.random.seed(1)
     eng = VecEngine("maze", args.envs, batch_size=256, gamma_safe=0.5, eps_safe=0.15, pos_fraction=0.3, seed=1,
-                    mf_recovery=False, mb_recovery=True, mpc_popsize=args.popsize, replay_size=200000, safe_replay_size=200000)
+                    mf_recovery=False, mb_recovery=True, mpc_popsize=args.popsize, replay_size=200000, safe_replay_size=200000,
+                    use_tensor_cores=args.tc)
     eng.init_agent()
     demos = get_offline_data(4000, rng=np.random.RandomState(1))
     eng.push_offline(demos)
@@ -43,6 +45,7 @@ def main():
     ms = [ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])]
     rows = args.envs * args.popsize * 20
     flop = rows * 15 * 5 * 2.0 * (4 * 200 + 200 * 200 * 2 + 200 * 4 + 2 * (4 * 256 + 256 * 256 + 256))
+    print("tensor cores: %d" % args.tc)
     print("MPC.plan: %d envs x %d particles, %.1f ms per call (%.1f / %.1f), %.1f TFLOP/s algorithmic, %.0f planned env-steps/s"
           % (args.envs, args.popsize * 20, np.mean(ms), ms[0], ms[1], flop / (np.mean(ms) * 1e-3) / 1e12, args.envs / (np.mean(ms) * 1e-3)))
     for _ in range(3):
