@@ -49,8 +49,14 @@ def parse():
     ap.add_argument("--env-name", default="maze")
     ap.add_argument("--pretrain", type=int, default=1000, help="Q_risk pre-training updates (untimed)")
     ap.add_argument("--demos", type=int, default=10000)
+    ap.add_argument("--replay", type=int, default=1 << 23,
+                    help="ring capacity per GPU (transitions). The reference's 1e6 is sized for ONE env; 65536 env copies "
+                         "turn that over in 15 vector steps, and once the agent has become safe the constraint ring holds "
+                         "fewer violations than one stratified batch needs (random.sample would raise).")
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--tc", type=int, default=int(os.environ.get("RRL_TENSOR_CORES", "1")))
+    ap.add_argument("--peer-grads", type=int, default=int(os.environ.get("RRL_PEER_GRADS", "1")),
+                    help="N>1: sum the ranks' gradients inside the optimizer-step kernel over NVLink peer memory (0: NCCL)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-steps", type=int, default=400)
     return ap.parse_args()
@@ -185,9 +191,11 @@ def build_engine(args, rank, world, pg, host_inputs, dev):
     from recovery_rl.engine import VecEngine
     torch.manual_seed(args.seed)                  # identical xavier init on every rank
     maze = args.env_name == "maze"
-    eng = VecEngine(args.env_name, args.envs, batch_size=args.batch, gamma_safe=0.5 if maze else 0.8,
+    cap = int(getattr(args, "replay", 1000000))
+    eng = VecEngine(args.env_name, args.envs, batch_size=args.batch, replay_size=cap, safe_replay_size=cap, gamma_safe=0.5 if maze else 0.8,
                     eps_safe=0.15 if maze else 0.3, pos_fraction=0.3 if maze else -1.0, seed=args.seed, device=dev,
-                    rank=rank, world_size=world, process_group=pg, host_inputs=host_inputs, use_tensor_cores=args.tc)
+                    rank=rank, world_size=world, process_group=pg, host_inputs=host_inputs, use_tensor_cores=args.tc,
+                    peer_grads=bool(args.peer_grads))
     eng.init_agent()
     rng = np.random.RandomState(args.seed + 1000 * rank)
     if maze:
@@ -201,6 +209,14 @@ def build_engine(args, rank, world, pg, host_inputs, dev):
     eng.pretrain_qrisk(args.pretrain, n_demos=len(demos))
     eng.reset()
     return eng
+
+
+def grad_mode(eng, world):
+    if world == 1:
+        return "none (1 GPU)"
+    if eng.peer_arena is not None:
+        return "peer-memory sum inside the optimizer-step kernel (NVLink loads, 1 flag barrier per optimizer step)"
+    return "nccl, flat grad block, 3 per step" + (" (peer mode unavailable: %s)" % eng.peer_error if eng.peer_error else "")
 
 
 def timed_steps(eng, K, flush, world, barrier):
@@ -265,7 +281,7 @@ def run_ours(args, rank, world, local_rank):
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
     total_ms = float(total_ms.item())
     c = eng.read_counters()
-    assert c["error"] == 0, "device-side sampler error"
+    assert c["error"] == 0, "device-side error %r" % (c,)
     value = world * args.envs * K / (total_ms * 1e-3)
 
     # ---- dominant kernels, timed alone with CUDA events on the launching stream (live) ----
@@ -352,7 +368,7 @@ def run_ours(args, rank, world, local_rank):
                            "timing": "sum of per-step CUDA-event intervals on the launching stream, max over ranks",
                            "rng": "Philox4x32-10 on device (value); host draws uploaded (e2e)",
                            "cuda_graph": eng.graph is not None, "tensor_cores": bool(args.tc),
-                           "grad_allreduce": "nccl, flat grad block, 3 per step" if world > 1 else "none (1 GPU)"},
+                           "grad_allreduce": grad_mode(eng, world)},
                 "roofline": roofline, "roofline_env": roofline_env, "cpu_baseline": cpu_baseline, "e2e": e2e,
                 "gpu_launches": eng.launches_per_step * K, "launches_per_step": eng.launches_per_step, "clocks": clocks,
                 "counters": {k: c[k] for k in ("total_numsteps", "episodes", "num_viols", "num_successes", "sac_updates",

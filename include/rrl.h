@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define RRL_VERSION 2
+#define RRL_VERSION 3
 
 const char* rrl_last_error(void);
 int rrl_version(void);
@@ -56,7 +56,7 @@ enum {
     RRL_C_ADAM_T0        = 16, /* Adam step counts: critic, policy, qrisk, recovery        */
     RRL_C_EXT_VIOLS      = 20, /* violations seen on OTHER ranks (multi-GPU gate), host/NCCL-set */
     RRL_C_RETURN_SUM_BITS= 21, /* double bit pattern: sum of finished-episode returns      */
-    RRL_C_ERROR          = 22, /* sticky device-side error code (1: sample larger than population) */
+    RRL_C_ERROR          = 22, /* sticky device-side error code (1: sample larger than population, 2: a peer never reached a barrier) */
     RRL_C_ADAM_T_ALPHA   = 23, /* Adam step counts of the scalar multipliers: log_alpha (sac.py:245-247),  */
     RRL_C_ADAM_T_NU      = 24, /*   log_nu (sac.py:259-261),                                                */
     RRL_C_ADAM_T_LAMBDA  = 25, /*   log_lambda_RCPO (sac.py:268-270)                                        */
@@ -261,6 +261,29 @@ int rrl_recovery_backward(const rrl_agent_config_t* cfg, float* arena, const flo
                           uint64_t seed, int32_t stream_id, int64_t* counters, float* losses,
                           void* stream);
 int rrl_recovery_apply(const rrl_agent_config_t* cfg, float* arena, int64_t* counters, void* stream);
+
+/* ---- multi-GPU: gradient sum fused into the optimizer step over NVLink peer memory --------------------------------
+ * With the agent arena of every rank allocated in symmetric (peer-mapped) memory, the NCCL all-reduce between
+ * rrl_*_backward and rrl_*_apply is replaced by: rrl_peer_barrier (every rank has finished writing its gradients),
+ * then rrl_*_apply_p2p, whose optimizer-step kernel reads the gradient block of EVERY rank through the peer pointers
+ * and sums them in rank order (identical result on all ranks) before Adam -- no staging buffer, no collective launch.
+ * One barrier per optimizer step suffices: a gradient region is rewritten only after two later barriers of the cycle.
+ *   arena[r]  : device pointer to rank r's arena as mapped in THIS process (arena[rank] == the local arena)
+ *   signal[r] : device pointer to rank r's uint32 signal pad (>= 2 KB, zero-initialised); words [256, 256 + 32) are used
+ *   epoch     : device int64, private to the rank, zero-initialised, NOT restored by snapshots (barrier generation) */
+typedef struct {
+    int32_t world, rank;
+    uint64_t arena[8];
+    uint64_t signal[8];
+} rrl_peers_t;
+int rrl_peer_barrier(const rrl_peers_t* peers, int64_t* epoch, int64_t* counters, void* stream);
+/* the same barrier, also exchanging the Q_risk gate counts (experiment.py:407-410 must open on every rank in the same
+ * step): counters[RRL_C_EXT_VIOLS] = sum over the other ranks of (RRL_C_NUM_VIOLS + RRL_C_OFFLINE_VIOLS).
+ * Uses int64 slots at signal words [272, 272 + 2*world). */
+int rrl_peer_sync_gate_counts(const rrl_peers_t* peers, int64_t* epoch, int64_t* counters, void* stream);
+int rrl_sac_apply_p2p(const rrl_agent_config_t* cfg, float* arena, int64_t* counters, const rrl_peers_t* peers, void* stream);
+int rrl_qrisk_apply_p2p(const rrl_agent_config_t* cfg, float* arena, int64_t* counters, const rrl_peers_t* peers, void* stream);
+int rrl_recovery_apply_p2p(const rrl_agent_config_t* cfg, float* arena, int64_t* counters, const rrl_peers_t* peers, void* stream);
 
 /* Twin forward used by QRiskWrapper.get_value / __call__ and the critic (qrisk.py:184-196,
  * 303-307; model.py:65-76,188-199): q1,q2 fp32 [n]; s,a fp32 [n][2]. */

@@ -707,6 +707,9 @@ struct AdamArgs {
     // bookkeeping by the last CTA: counters[bump[i]] += 1 (i < n_bump)
     int bump[3];
     int n_bump;
+    // multi-GPU peer mode: the gradient is the sum over the ranks' arenas (peer-mapped), in rank order
+    const float* peer[8];
+    int n_peer;
 };
 __global__ void __launch_bounds__(kThreads) adam_kernel(const __grid_constant__ AdamArgs A) {
     if (A.counters[A.rows_counter] <= 0) return;
@@ -726,7 +729,14 @@ __global__ void __launch_bounds__(kThreads) adam_kernel(const __grid_constant__ 
         const int64_t o = A.off + i;
         float p = A.arena[o];
         if (A.lr64 > 0.0) {
-            const float g = A.arena[A.grad_off + o] * A.grad_scale;
+            float g;
+            if (A.n_peer > 0) {
+                g = 0.f;
+                for (int r = 0; r < A.n_peer; ++r) g += __ldcv(A.peer[r] + A.grad_off + o);   // NVLink peer loads, fixed order
+                g *= A.grad_scale;
+            } else {
+                g = A.arena[A.grad_off + o] * A.grad_scale;
+            }
             float m = A.arena[A.m_off + o], v = A.arena[A.v_off + o];
             m = m + (g - m) * (1.0f - A.b1);               // exp_avg.lerp_(grad, 1 - beta1)
             v = v * A.b2 + (1.0f - A.b2) * g * g;           // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
@@ -811,6 +821,56 @@ __global__ void init_scalars_kernel(float* scal, float alpha, double nu, double 
     sd[RRL_D_LOG_LAMBDA] = log(lambda);
     sd[RRL_D_LAMBDA] = lambda;
     sd[RRL_D_NU_LEARNED] = nu;
+}
+
+// (9c) cross-GPU barrier over peer-mapped signal pads (one thread per peer): publish this rank's generation into
+//      every peer's pad (release, system scope), then wait until every peer's generation has arrived in ours.
+constexpr int kPadBase = 256;
+struct PeerBarrierArgs {
+    uint32_t* signal[8];
+    int world, rank;
+    int64_t* epoch;
+    int64_t* counters;
+    int exchange;   // also exchange the Q_risk gate counts: EXT_VIOLS = sum over the OTHER ranks of (num_viols + offline_viols)
+};
+__global__ void peer_barrier_kernel(const PeerBarrierArgs A) {
+    __shared__ unsigned s_epoch;
+    if (threadIdx.x == 0) {
+        s_epoch = (unsigned)(++(*A.epoch));
+        __threadfence_system();          // this rank's gradient writes (earlier kernels of the stream) before the flag
+    }
+    __syncthreads();
+    const unsigned epoch = s_epoch;
+    const int r = threadIdx.x;
+    long long theirs = 0;
+    if (r < A.world) {
+        uint32_t* dst = A.signal[r] + kPadBase + A.rank;
+        if (A.exchange) {   // value first, then the flag (release): slot [rank] of every peer's pad
+            const long long mine = A.counters[RRL_C_NUM_VIOLS] + A.counters[RRL_C_OFFLINE_VIOLS];
+            long long* vdst = reinterpret_cast<long long*>(A.signal[r] + kPadBase + 16) + A.rank;
+            asm volatile("st.relaxed.sys.global.s64 [%0], %1;" ::"l"(vdst), "l"(mine) : "memory");
+        }
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(dst), "r"(epoch) : "memory");
+        const uint32_t* src = A.signal[A.rank] + kPadBase + r;
+        const bool lost = A.counters[RRL_C_ERROR] == 2;   // a peer was lost earlier: do not stall every later step as well
+        unsigned v;
+        unsigned long long t0, t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        do {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(src) : "memory");
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        } while (!lost && (int)(v - epoch) < 0 && t1 - t0 < 10000000000ull);   // give up after 10 s instead of hanging the GPU
+        if ((int)(v - epoch) < 0) A.counters[RRL_C_ERROR] = 2;
+        if (A.exchange && r != A.rank) {
+            const long long* vsrc = reinterpret_cast<const long long*>(A.signal[A.rank] + kPadBase + 16) + r;
+            asm volatile("ld.relaxed.sys.global.s64 %0, [%1];" : "=l"(theirs) : "l"(vsrc) : "memory");
+        }
+    }
+    if (A.exchange) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) theirs += __shfl_xor_sync(0xffffffffu, theirs, o);
+        if (threadIdx.x == 0) A.counters[RRL_C_EXT_VIOLS] = theirs;
+    }
 }
 
 // (10) soft_update (utils.py:46-49): target = target*(1-tau) + source*tau over a whole net (+ image refresh)
@@ -913,9 +973,13 @@ int imgs_of_net(const Layout& L, int net, ImgRef* out) {
 // (lr64 = 0), only the soft update of polyak_src into polyak_dst and the bookkeeping.
 int launch_adam(const rrl_agent_config_t* cfg, const Layout& L, float* arena, int64_t* counters, int net_a, int net_b,
                 int t_counter, int rows_counter, cudaStream_t st, int polyak_dst = -1, int polyak_src = -1, float tau = 0.f,
-                int upd_counter = -1, const int* bump = nullptr, int n_bump = 0) {
+                int upd_counter = -1, const int* bump = nullptr, int n_bump = 0, const rrl_peers_t* peers = nullptr) {
     AdamArgs A;
     memset(&A, 0, sizeof(A));
+    if (peers) {
+        A.n_peer = peers->world;
+        for (int r = 0; r < peers->world && r < 8; ++r) A.peer[r] = reinterpret_cast<const float*>(peers->arena[r]);
+    }
     A.arena = arena;
     const int first = net_a >= 0 ? net_a : polyak_src;
     A.off = L.net_off[first];
@@ -1328,7 +1392,16 @@ extern "C" int rrl_sac_backward(const rrl_agent_config_t* cfg, float* arena, con
     return 0;
 }
 
+static int sac_apply_impl(const rrl_agent_config_t* cfg, float* arena, int64_t* counters, const rrl_peers_t* peers, void* stream);
 extern "C" int rrl_sac_apply(const rrl_agent_config_t* cfg, float* arena, int64_t* counters, void* stream) {
+    return sac_apply_impl(cfg, arena, counters, nullptr, stream);
+}
+extern "C" int rrl_sac_apply_p2p(const rrl_agent_config_t* cfg, float* arena, int64_t* counters, const rrl_peers_t* peers,
+                                 void* stream) {
+    RRL_CHECK_ARG(peers && peers->world >= 1 && peers->world <= 8, "bad peers");
+    return sac_apply_impl(cfg, arena, counters, peers, stream);
+}
+static int sac_apply_impl(const rrl_agent_config_t* cfg, float* arena, int64_t* counters, const rrl_peers_t* peers, void* stream) {
     CHECK_CFG(cfg);
     RRL_CHECK_ARG(arena && counters, "null argument");
     const Layout L = make_layout(cfg);
@@ -1338,7 +1411,7 @@ extern "C" int rrl_sac_apply(const rrl_agent_config_t* cfg, float* arena, int64_
     // step bookkeeping -- one launch
     const int bump[3] = {RRL_C_ADAM_T0 + 0, RRL_C_ADAM_T0 + 1, RRL_C_SAC_UPDATES};
     int rc = launch_adam(cfg, L, arena, counters, RRL_NET_CRITIC, RRL_NET_POLICY, RRL_C_ADAM_T0 + 0, RRL_C_SAC_ROWS, st,
-                         RRL_NET_CRITIC_TARGET, RRL_NET_CRITIC, cfg->tau, RRL_C_SAC_UPDATES, bump, 3);
+                         RRL_NET_CRITIC_TARGET, RRL_NET_CRITIC, cfg->tau, RRL_C_SAC_UPDATES, bump, 3, peers);
     if (rc) return rc;
     if (cfg->algo_flags & (RRL_ALGO_AUTO_ALPHA | RRL_ALGO_UPDATE_NU | RRL_ALGO_RCPO)) {  // sac.py:241-271
         ScalarAdamArgs A;
@@ -1434,7 +1507,16 @@ extern "C" int rrl_qrisk_backward(const rrl_agent_config_t* cfg, float* arena, c
     return 0;
 }
 
+static int qrisk_apply_impl(const rrl_agent_config_t* cfg, float* arena, int64_t* counters, const rrl_peers_t* peers, void* stream);
 extern "C" int rrl_qrisk_apply(const rrl_agent_config_t* cfg, float* arena, int64_t* counters, void* stream) {
+    return qrisk_apply_impl(cfg, arena, counters, nullptr, stream);
+}
+extern "C" int rrl_qrisk_apply_p2p(const rrl_agent_config_t* cfg, float* arena, int64_t* counters, const rrl_peers_t* peers,
+                                   void* stream) {
+    RRL_CHECK_ARG(peers && peers->world >= 1 && peers->world <= 8, "bad peers");
+    return qrisk_apply_impl(cfg, arena, counters, peers, stream);
+}
+static int qrisk_apply_impl(const rrl_agent_config_t* cfg, float* arena, int64_t* counters, const rrl_peers_t* peers, void* stream) {
     CHECK_CFG(cfg);
     RRL_CHECK_ARG(arena && counters, "null argument");
     const Layout L = make_layout(cfg);
@@ -1443,7 +1525,7 @@ extern "C" int rrl_qrisk_apply(const rrl_agent_config_t* cfg, float* arena, int6
     // (qrisk.py:160-162: it reads the post-step critic, which the recovery-policy update in between does not touch)
     const int bump[1] = {RRL_C_ADAM_T0 + 2};
     return launch_adam(cfg, L, arena, counters, RRL_NET_QRISK, -1, RRL_C_ADAM_T0 + 2, RRL_C_QRISK_ROWS, st,
-                       RRL_NET_QRISK_TARGET, RRL_NET_QRISK, cfg->tau_safe, RRL_C_QRISK_UPDATES, bump, 1);
+                       RRL_NET_QRISK_TARGET, RRL_NET_QRISK, cfg->tau_safe, RRL_C_QRISK_UPDATES, bump, 1, peers);
 }
 
 // recovery policy on the POST-step safety critic (qrisk.py:150-158), then Polyak (qrisk.py:160-163)
@@ -1551,7 +1633,16 @@ extern "C" int rrl_recovery_backward(const rrl_agent_config_t* cfg, float* arena
     return 0;
 }
 
+static int recovery_apply_impl(const rrl_agent_config_t* cfg, float* arena, int64_t* counters, const rrl_peers_t* peers, void* stream);
 extern "C" int rrl_recovery_apply(const rrl_agent_config_t* cfg, float* arena, int64_t* counters, void* stream) {
+    return recovery_apply_impl(cfg, arena, counters, nullptr, stream);
+}
+extern "C" int rrl_recovery_apply_p2p(const rrl_agent_config_t* cfg, float* arena, int64_t* counters, const rrl_peers_t* peers,
+                                      void* stream) {
+    RRL_CHECK_ARG(peers && peers->world >= 1 && peers->world <= 8, "bad peers");
+    return recovery_apply_impl(cfg, arena, counters, peers, stream);
+}
+static int recovery_apply_impl(const rrl_agent_config_t* cfg, float* arena, int64_t* counters, const rrl_peers_t* peers, void* stream) {
     CHECK_CFG(cfg);
     RRL_CHECK_ARG(arena && counters, "null argument");
     const Layout L = make_layout(cfg);
@@ -1560,9 +1651,28 @@ extern "C" int rrl_recovery_apply(const rrl_agent_config_t* cfg, float* arena, i
     if (cfg->mf_recovery) {
         const int bump[2] = {RRL_C_ADAM_T0 + 3, RRL_C_QRISK_UPDATES};
         return launch_adam(cfg, L, arena, counters, RRL_NET_RECOVERY, -1, RRL_C_ADAM_T0 + 3, RRL_C_QRISK_ROWS, st, -1, -1,
-                           0.f, -1, bump, 2);
+                           0.f, -1, bump, 2, peers);
     }
     bump_kernel<<<1, 32, 0, st>>>(counters, RRL_C_QRISK_ROWS, -1, -1, RRL_C_QRISK_UPDATES);
+    RRL_CHECK_LAUNCH();
+    return 0;
+}
+
+static int peer_barrier_impl(const rrl_peers_t* peers, int64_t* epoch, int64_t* counters, int exchange, void* stream);
+extern "C" int rrl_peer_barrier(const rrl_peers_t* peers, int64_t* epoch, int64_t* counters, void* stream) {
+    return peer_barrier_impl(peers, epoch, counters, 0, stream);
+}
+extern "C" int rrl_peer_sync_gate_counts(const rrl_peers_t* peers, int64_t* epoch, int64_t* counters, void* stream) {
+    return peer_barrier_impl(peers, epoch, counters, 1, stream);
+}
+static int peer_barrier_impl(const rrl_peers_t* peers, int64_t* epoch, int64_t* counters, int exchange, void* stream) {
+    RRL_CHECK_ARG(peers && epoch && counters && peers->world >= 1 && peers->world <= 8 && peers->rank >= 0 &&
+                      peers->rank < peers->world, "bad argument");
+    PeerBarrierArgs A;
+    memset(&A, 0, sizeof(A));
+    for (int r = 0; r < peers->world; ++r) A.signal[r] = reinterpret_cast<uint32_t*>(peers->signal[r]);
+    A.world = peers->world; A.rank = peers->rank; A.epoch = epoch; A.counters = counters; A.exchange = exchange;
+    peer_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(A);
     RRL_CHECK_LAUNCH();
     return 0;
 }

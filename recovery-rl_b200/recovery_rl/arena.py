@@ -14,7 +14,7 @@ NETS = native.NET_NAMES
 
 
 class AgentArena(object):
-    def __init__(self, device, max_batch=256, **cfg_kwargs):
+    def __init__(self, device, max_batch=256, allocator=None, **cfg_kwargs):
         native.require_cuda()
         self.device = torch.device(device)
         max_batch = (int(max_batch) + 31) // 32 * 32
@@ -23,7 +23,10 @@ class AgentArena(object):
         n = native.agent_arena_floats(self.cfg)
         if n <= 0:
             raise native.RRLError("bad agent config: %s" % native.lib().rrl_last_error().decode())
-        self.arena = torch.zeros(n, dtype=torch.float32, device=self.device)
+        # allocator(n) -> zeroed float32 device tensor; the sharded engine passes a symmetric-memory allocator so that
+        # peers can read the gradient block over NVLink (dist_utils.PeerArena)
+        self.arena = torch.zeros(n, dtype=torch.float32, device=self.device) if allocator is None else allocator(n)
+        assert self.arena.dtype == torch.float32 and self.arena.numel() >= n and self.arena.is_contiguous()
         self.counters = torch.zeros(native.NUM_COUNTERS, dtype=torch.int64, device=self.device)
         self._views = {}
         self.grad_off, self.grad_count = native.agent_grad_range(self.cfg, -1)

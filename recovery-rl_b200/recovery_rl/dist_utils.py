@@ -44,6 +44,36 @@ def sync_gate_counts(counters, group=None):
     return int(0)
 
 
+class PeerArena(object):
+    """Symmetric-memory plumbing for the peer-summed optimizer step (include/rrl.h, rrl_peers_t).  torch's symmetric
+    memory does the allocation and the handle exchange; the data path (barrier flags, gradient loads) is ours.
+    Usage: pa = PeerArena(device, rank, world, group); arena = pa.allocate(n) [collective]; pa.peers -> native.Peers."""
+    PAD_BASE = 256          # uint32 words; the first KB of the signal pad is left to torch's own primitives
+
+    def __init__(self, device, rank, world, group=None):
+        self.device, self.rank, self.world, self.group = torch.device(device), int(rank), int(world), group
+        self.peers = None
+        self.handle = None
+
+    def allocate(self, n_floats):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        group = self.group if self.group is not None else dist.group.WORLD
+        t = symm.empty(int(n_floats), dtype=torch.float32, device=self.device)
+        self.handle = symm.rendezvous(t, group)
+        t.zero_()
+        pad = self.handle.get_signal_pad(self.rank, dtype=torch.int32)
+        pad[self.PAD_BASE:self.PAD_BASE + 64].zero_()
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=group)
+        h = self.handle
+        self.peers = native.make_peers(self.rank, list(h.buffer_ptrs), list(h.signal_pad_ptrs))
+        assert int(h.buffer_ptrs[self.rank]) == t.data_ptr()
+        self.epoch = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self.tensor = t
+        return t
+
+
 def shard(n_total, rank, world):
     """[lo, hi) of the env copies rank owns when a global env count is split (remainder to the first ranks)."""
     base, rem = divmod(int(n_total), int(world))

@@ -32,7 +32,7 @@ class VecEngine(object):
                  device="cuda:0", rank=0, world_size=1, process_group=None, host_inputs=False, log_outputs=False,
                  use_tensor_cores=0, maze_substeps=500, dgd=False, update_nu=False, rcpo=False, auto_alpha=False,
                  nu=0.01, lambda_rcpo=0.01, disable_action_relabeling=False, mb_recovery=False, mpc_popsize=None,
-                 mpc_num_elites=None):
+                 mpc_num_elites=None, peer_grads=False):
         native.require_cuda()
         self.device = torch.device(device)
         torch.cuda.set_device(self.device)
@@ -57,7 +57,13 @@ class VecEngine(object):
         self.host_inputs = bool(host_inputs)
         self.log_outputs = bool(log_outputs) or self.host_inputs
         sc = ACTION_SCALE[env_name]
-        self.agent = AgentArena(self.device, max_batch=self.B, gamma=gamma, alpha=alpha, tau=tau, lr=lr,
+        # peer_grads: the arena lives in symmetric memory and the optimizer-step kernel sums the ranks' gradient blocks
+        # itself over NVLink (one flag barrier per optimizer step) instead of an NCCL all-reduce
+        self.peer_arena = None
+        if peer_grads and self.world > 1:
+            self.peer_arena = dist_utils.PeerArena(self.device, self.rank, self.world, process_group)
+        self.peer_error = None
+        self.agent = AgentArena(self.device, max_batch=self.B, allocator=self._peer_alloc if self.peer_arena else None, gamma=gamma, alpha=alpha, tau=tau, lr=lr,
                                 gamma_safe=gamma_safe, tau_safe=tau_safe, eps_safe=eps_safe,
                                 target_update_interval=target_update_interval, mf_recovery=mf_recovery,
                                 action_scale=(sc, sc), grad_scale=1.0 / self.world,
@@ -83,7 +89,9 @@ class VecEngine(object):
         self.task_ring = torch.zeros(self.task_cap, 8, device=dev)
         self.cons_ring = torch.zeros(self.cons_cap, 8, device=dev)
         self.cons_flags = torch.zeros(self.cons_cap, dtype=torch.uint8, device=dev)
-        self.n_chunks = (self.cons_cap + FLAG_CHUNK - 1) // FLAG_CHUNK
+        # flag chunks of the stratified sampler: at most 8192 per ring (replay.cu), 512-byte granularity
+        self.flag_chunk = FLAG_CHUNK * max(1, -(-self.cons_cap // (8192 * FLAG_CHUNK)))
+        self.n_chunks = (self.cons_cap + self.flag_chunk - 1) // self.flag_chunk
         self.chunk_counts = torch.zeros(2, self.n_chunks, dtype=torch.int32, device=dev)
         # ONE CPython-compatible MT19937 stream shared by both buffers (replay_memory.py:16,41); every rank
         # gets its own stream (seed + rank) so that shards draw different batches
@@ -91,7 +99,7 @@ class VecEngine(object):
         self.losses = torch.zeros(16, device=dev)
         self.sac_sample_cfg = native.sample_config(self.task_cap, self.B, False, None, gate_mode=1)
         self.qr_sample_cfg = native.sample_config(self.cons_cap, self.B, True, self.pos_fraction, gate_mode=2,
-                                                  chunk=FLAG_CHUNK, gate_pos_fraction=self.gate_pos_fraction)
+                                                  chunk=self.flag_chunk, gate_pos_fraction=self.gate_pos_fraction)
         # per-step outputs (logging schema of experiment.py:421 / run_stats.pkl), only when asked for
         if self.log_outputs:
             self.out_next = torch.zeros(2, n, dtype=torch.float64, device=dev)
@@ -217,19 +225,43 @@ class VecEngine(object):
     def _all_reduce(self, net_names):
         if self.world == 1:
             return
+        if self.peer_arena is not None:      # every rank's gradients are complete -> apply kernels read them in place
+            native.peer_barrier(self.peer_arena.peers, self.peer_arena.epoch, self.counters)
+            return
         if self._grad_views is None:
             self._grad_views = dist_utils.grad_ranges(self.cfg)
         dist_utils.all_reduce_grads(self.arena, self._grad_views, net_names, self.pg)
 
+    def _peer_alloc(self, n):
+        """symmetric allocation, agreed on by all ranks: if it fails anywhere every rank keeps the NCCL path."""
+        import torch.distributed as dist
+        t = None
+        try:
+            t = self.peer_arena.allocate(n)
+        except Exception as ex:            # no symmetric memory on this system / driver
+            self.peer_error = repr(ex)
+        ok = torch.tensor([0 if t is None else 1], dtype=torch.int32, device=self.device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.pg)
+        if int(ok.item()) == 0:
+            self.peer_arena = None
+            return torch.zeros(n, dtype=torch.float32, device=self.device)
+        return t
+
+    @property
+    def _peers(self):
+        return self.peer_arena.peers if self.peer_arena is not None else None
+
     def _sync_gate_counts(self):
-        if self.world > 1:
+        if self.peer_arena is not None:
+            native.peer_sync_gate_counts(self.peer_arena.peers, self.peer_arena.epoch, self.counters)
+        elif self.world > 1:
             dist_utils.sync_gate_counts(self.counters, self.pg)
 
     def _qr_sample(self, sample_cfg=None):
         sc = sample_cfg or self.qr_sample_cfg
         k = 0
         if sc.pos_fraction >= 0:
-            native.replay_flag_count(self.cons_flags, self.cons_cap, FLAG_CHUNK, self.chunk_counts); k += 1
+            native.replay_flag_count(self.cons_flags, self.cons_cap, self.flag_chunk, self.chunk_counts); k += 1
         a = self.agent
         native.replay_sample(sc, self.cons_ring, self.mt_state, self.counters, native.C_QRISK_ROWS, a.scratch("qr_s"),
                              a.scratch("qr_a"), a.scratch("qr_c"), a.scratch("qr_s2"), a.scratch("qr_m"),
@@ -240,11 +272,12 @@ class VecEngine(object):
         cfg, ar, cn = self.cfg, self.arena, self.counters
         native.qrisk_backward(cfg, ar, cn, self.losses[8:], self._in("qr_eps_next"), seed=self.seed, stream_id=self.rank)
         self._all_reduce(["qrisk"])
-        native.qrisk_apply(cfg, ar, cn)
+        native.qrisk_apply(cfg, ar, cn, peers=self._peers)
         native.recovery_backward(cfg, ar, cn, self.losses[8:], self._in("qr_eps_rec"), seed=self.seed, stream_id=self.rank)
         self._all_reduce(["recovery"])
-        native.recovery_apply(cfg, ar, cn)
-        return 5 + 1 + (8 if self.mf_recovery else 0) + 1     # kernels launched (gpu_launches bookkeeping)
+        native.recovery_apply(cfg, ar, cn, peers=self._peers)
+        nb = 1 if self.peer_arena is not None else 0           # peer barrier kernels
+        return 5 + 1 + (8 if self.mf_recovery else 0) + 1 + 2 * nb     # kernels launched (gpu_launches bookkeeping)
 
     def qrisk_update(self, sample_cfg=None):
         return self._qr_sample(sample_cfg) + self._qr_compute()
@@ -265,8 +298,8 @@ class VecEngine(object):
             f32, f64 = self.agent.scalars()
             dist_utils.all_reduce_sum(f32[native.S_G_LOG_ALPHA:native.S_G_LOG_ALPHA + 1], self.pg)
             dist_utils.all_reduce_sum(f64[native.D_G_LOG_NU:native.D_G_LOG_LAMBDA + 1], self.pg)
-        native.sac_apply(cfg, ar, cn)
-        return 8 + 1 + (1 if self.scalar_algos else 0)
+        native.sac_apply(cfg, ar, cn, peers=self._peers)
+        return 8 + 1 + (1 if self.scalar_algos else 0) + (1 if self.peer_arena is not None else 0)
 
     def sac_update(self):
         return self._sac_sample() + self._sac_compute()
@@ -275,7 +308,7 @@ class VecEngine(object):
         """experiment.py:289-296: critic_safe_pretraining_steps x QRiskWrapper.update_parameters with
         batch_size = min(batch_size, len(constraint_demo_data)); no gate."""
         b = self.B if n_demos is None else min(self.B, int(n_demos))
-        sc = native.sample_config(self.cons_cap, b, True, self.pos_fraction, gate_mode=0, chunk=FLAG_CHUNK)
+        sc = native.sample_config(self.cons_cap, b, True, self.pos_fraction, gate_mode=0, chunk=self.flag_chunk)
         for _ in range(int(steps)):
             self.qrisk_update(sc)
 
@@ -289,6 +322,7 @@ class VecEngine(object):
             # on a side stream, forked after the SAC sample (stream order of the ONE shared generator) and joined
             # before the Q_risk kernels.  Captured as a fork/join in the CUDA graph.
             self._sync_gate_counts()
+            k += 1 if self.peer_arena is not None else 0
             self._ev_fork.record(main)
             self._side.wait_event(self._ev_fork)
             with torch.cuda.stream(self._side):

@@ -281,9 +281,37 @@ qrisk_backward = _upd(None, "rrl_qrisk_backward")
 recovery_backward = _upd(None, "rrl_recovery_backward")
 
 
+class Peers(C.Structure):
+    """rrl_peers_t: the ranks' arenas and signal pads as mapped in this process (symmetric memory)."""
+    _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("arena", C.c_uint64 * 8), ("signal", C.c_uint64 * 8)]
+
+
+def make_peers(rank, arena_ptrs, signal_ptrs):
+    if not (1 <= len(arena_ptrs) <= 8 and len(arena_ptrs) == len(signal_ptrs)):
+        raise RRLError("peer mode supports 1..8 ranks of one node")
+    P = Peers()
+    P.world, P.rank = len(arena_ptrs), int(rank)
+    for r, (a, s) in enumerate(zip(arena_ptrs, signal_ptrs)):
+        P.arena[r], P.signal[r] = int(a), int(s)
+    return P
+
+
+def peer_barrier(peers, epoch, counters, stream=None):
+    _check(lib().rrl_peer_barrier(C.byref(peers), p(epoch, "i64"), p(counters, "i64"), _stream(stream)), "rrl_peer_barrier")
+
+
+def peer_sync_gate_counts(peers, epoch, counters, stream=None):
+    _check(lib().rrl_peer_sync_gate_counts(C.byref(peers), p(epoch, "i64"), p(counters, "i64"), _stream(stream)),
+           "rrl_peer_sync_gate_counts")
+
+
 def _apply(name):
-    def call(cfg, arena, counters, stream=None):
-        _check(getattr(lib(), name)(C.byref(cfg), p(arena, "f32"), p(counters, "i64"), _stream(stream)), name)
+    def call(cfg, arena, counters, stream=None, peers=None):
+        if peers is None:
+            _check(getattr(lib(), name)(C.byref(cfg), p(arena, "f32"), p(counters, "i64"), _stream(stream)), name)
+        else:
+            _check(getattr(lib(), name + "_p2p")(C.byref(cfg), p(arena, "f32"), p(counters, "i64"), C.byref(peers),
+                                                 _stream(stream)), name + "_p2p")
     return call
 
 

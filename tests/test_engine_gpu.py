@@ -73,3 +73,20 @@ def test_graph_replay_equals_eager(native, cuda):
     c = a.read_counters()
     assert c["sac_updates"] == 5 and c["qrisk_updates"] == 5 + 5 and c["error"] == 0
     assert c["total_numsteps"] == 6 * 2048
+
+
+@pytest.mark.gpu
+def test_peer_grads_match_nccl():
+    """world 2: the optimizer-step kernel that sums the ranks' gradient blocks over NVLink peer memory leaves exactly the
+    parameters the NCCL all-reduce path leaves (tests/p2p_check.py).  Needs two GPUs."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    here = os.path.dirname(os.path.abspath(__file__))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29731", os.path.join(here, "p2p_check.py")],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "P2P_OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
