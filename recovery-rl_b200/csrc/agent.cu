@@ -731,8 +731,12 @@ __global__ void __launch_bounds__(kThreads) adam_kernel(const __grid_constant__ 
         if (A.lr64 > 0.0) {
             float g;
             if (A.n_peer > 0) {
-                g = 0.f;
-                for (int r = 0; r < A.n_peer; ++r) g += __ldcv(A.peer[r] + A.grad_off + o);   // NVLink peer loads, fixed order
+                float gs[8];   // all NVLink peer loads in flight together, then summed in rank order
+#pragma unroll
+                for (int r = 0; r < 8; ++r) gs[r] = r < A.n_peer ? __ldcv(A.peer[r] + A.grad_off + o) : 0.f;
+                g = gs[0];
+#pragma unroll
+                for (int r = 1; r < 8; ++r) g += gs[r];
                 g *= A.grad_scale;
             } else {
                 g = A.arena[A.grad_off + o] * A.grad_scale;

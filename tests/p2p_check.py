@@ -45,7 +45,8 @@ def main():
         b, cb, graphed = run(True, rank, world, dev, tc, 6)
         assert graphed, "peer-mode step was not captured into a graph"
         assert ca["sac_updates"] == cb["sac_updates"] > 0 and ca["qrisk_updates"] == cb["qrisk_updates"] > 0, (ca, cb)
-        same = torch.equal(a, b)
+        # world 2: a two-term sum is order-independent -> bit-equal; more ranks: NCCL's reduction order is its own
+        same = torch.equal(a, b) if world == 2 else torch.allclose(a, b, rtol=1e-3, atol=1e-4)
         other = [torch.empty_like(b) for _ in range(world)]
         dist.all_gather(other, b)
         across = all(torch.equal(o, b) for o in other)
