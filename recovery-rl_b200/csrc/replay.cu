@@ -219,11 +219,14 @@ __device__ void sample_range(SamplerSmem& S, int64_t n64, int k, int* result, in
     }
 }
 
-// rank -> slot of the rank-th flagged entry (ascending), one warp per query
+// rank -> slot of the rank-th flagged entry (ascending).  One THREAD per query: all k binary searches over the chunk
+// prefix run side by side, then every thread walks its own chunk in 64-byte steps (4 independent 16-byte loads in
+// flight, popcount per group) and resolves the byte inside the group from registers.  The flag bytes were read by
+// flag_count_kernel just before, so the walk is served by L2; k x chunk bytes in total.
 __device__ void select_ranks(const uint8_t* __restrict__ flags, int64_t capacity, int chunk, int n_chunks,
                              const int* __restrict__ prefix /*exclusive, n_chunks+1*/, uint8_t bit, int* result, int k) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int q = warp; q < k; q += kThreads / 32) {
+    const uint32_t m = 0x01010101u * bit;
+    for (int q = threadIdx.x; q < k; q += kThreads) {
         const int rank = result[q];
         int lo = 0, hi = n_chunks;  // find c: prefix[c] <= rank < prefix[c+1]
         while (hi - lo > 1) {
@@ -232,37 +235,37 @@ __device__ void select_ranks(const uint8_t* __restrict__ flags, int64_t capacity
         }
         int rel = rank - prefix[lo];
         const int64_t cbase = (int64_t)lo * chunk;
-        const int per = chunk / 32;  // bytes per lane (chunk is a multiple of 512)
-        const int64_t b0 = cbase + (int64_t)lane * per;
-        int c = 0;
-        for (int j = 0; j < per; j += 16) {
-            if (b0 + j < capacity) {
-                uint4 v = *reinterpret_cast<const uint4*>(flags + b0 + j);
-                const uint32_t m = 0x01010101u * bit;
-                c += __popc(v.x & m) + __popc(v.y & m) + __popc(v.z & m) + __popc(v.w & m);
-            }
-        }
-        int inc = c;
+        int64_t found = -1;
+        for (int j = 0; j < chunk && found < 0; j += 64) {   // chunk is a multiple of 512, capacity of 16
+            uint4 v[4];
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            int u = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc += u;
-        }
-        const int ex = inc - c;
-        const bool mine = (rel >= ex) && (rel < inc);
-        if (mine) {
-            int left = rel - ex;
-            int64_t found = -1;
-            for (int j = 0; j < per; ++j) {
-                if (b0 + j < capacity && (flags[b0 + j] & bit)) {
-                    if (left == 0) { found = b0 + j; break; }
-                    --left;
+            for (int u = 0; u < 4; ++u) {
+                const int64_t b = cbase + j + 16 * u;
+                v[u] = b < capacity ? *reinterpret_cast<const uint4*>(flags + b) : make_uint4(0u, 0u, 0u, 0u);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+                for (int wi = 0; wi < 4; ++wi) {
+                    const int c = __popc(w[wi] & m);
+                    if (found < 0 && rel < c) {
+#pragma unroll
+                        for (int by = 0; by < 4; ++by) {
+                            if (found < 0 && ((w[wi] >> (8 * by)) & bit)) {
+                                if (rel == 0) found = cbase + j + 16 * u + 4 * wi + by;
+                                --rel;
+                            }
+                        }
+                    } else if (found < 0) {
+                        rel -= c;
+                    }
                 }
             }
-            result[q] = (int)found;
         }
-        __syncwarp();
+        result[q] = (int)found;
     }
+    __syncthreads();
 }
 
 __global__ void __launch_bounds__(kThreads)
@@ -373,14 +376,17 @@ replay_sample_kernel(rrl_sample_config_t cfg, const float* __restrict__ ring, co
     }
 }
 
+// per-chunk counts of positive (bit 1) and negative (bit 2) flag bytes: one WARP per chunk, no block-level sync, every
+// chunk's loads in flight at once (the ring is scanned at HBM speed instead of one DRAM round trip per chunk and block)
 __global__ void __launch_bounds__(256)
 flag_count_kernel(const uint8_t* __restrict__ flags, int64_t capacity, int chunk, int n_chunks,
                   int32_t* __restrict__ counts) {
-    __shared__ int s_pos[8], s_neg[8];
-    for (int c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+    const int lane = threadIdx.x & 31;
+    const int n_warps = gridDim.x * 8;
+    for (int c = blockIdx.x * 8 + (threadIdx.x >> 5); c < n_chunks; c += n_warps) {
         const int64_t base = (int64_t)c * chunk;
         int p = 0, q = 0;
-        for (int j = threadIdx.x * 16; j < chunk; j += 256 * 16) {
+        for (int j = lane * 16; j < chunk; j += 32 * 16) {
             if (base + j < capacity) {  // capacity is padded to a multiple of 16 by the caller
                 uint4 v = *reinterpret_cast<const uint4*>(flags + base + j);
                 p += __popc(v.x & 0x01010101u) + __popc(v.y & 0x01010101u) + __popc(v.z & 0x01010101u) + __popc(v.w & 0x01010101u);
@@ -392,21 +398,10 @@ flag_count_kernel(const uint8_t* __restrict__ flags, int64_t capacity, int chunk
             p += __shfl_xor_sync(0xffffffffu, p, o);
             q += __shfl_xor_sync(0xffffffffu, q, o);
         }
-        if ((threadIdx.x & 31) == 0) {
-            s_pos[threadIdx.x >> 5] = p;
-            s_neg[threadIdx.x >> 5] = q;
+        if (lane == 0) {
+            counts[c] = p;
+            counts[n_chunks + c] = q;
         }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            int sp = 0, sn = 0;
-            for (int w = 0; w < 8; ++w) {
-                sp += s_pos[w];
-                sn += s_neg[w];
-            }
-            counts[c] = sp;
-            counts[n_chunks + c] = sn;
-        }
-        __syncthreads();
     }
 }
 
@@ -484,7 +479,8 @@ extern "C" int rrl_replay_flag_count(const uint8_t* cons_flags, int64_t capacity
     RRL_CHECK_ARG(chunk >= 512 && (chunk % 512) == 0, "chunk must be a multiple of 512");
     RRL_CHECK_ARG(capacity % 16 == 0, "flag array capacity must be a multiple of 16");
     const int n_chunks = n_chunks_for(capacity, chunk);
-    int blocks = n_chunks < rrl_num_sms() * 4 ? n_chunks : rrl_num_sms() * 4;
+    const int want = (n_chunks + 7) / 8;
+    int blocks = want < rrl_num_sms() * 8 ? want : rrl_num_sms() * 8;
     flag_count_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(cons_flags, capacity, chunk, n_chunks, chunk_counts);
     RRL_CHECK_LAUNCH();
     return 0;

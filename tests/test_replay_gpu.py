@@ -113,3 +113,46 @@ def test_large_ring_set_path_matches_cpython(native, cuda):
         ref = random.sample(range(n), B)
         assert np.array_equal(idx, ref)
         assert np.array_equal(out[0][:, 0] + 4096.0 * out[0][:, 1], np.array(ref, np.float64))
+
+
+@pytest.mark.parametrize("cap,chunk,n_fill,p_pos", [(1 << 21, 512, 1 << 21, 0.0004), (3 * (1 << 20) + 48, 1024, 2500000, 0.3),
+                                                     (1 << 23, 1024, 1 << 23, 0.0001), (70000, 2048, 65000, 0.05)])
+def test_stratified_sample_large_rings_and_chunks(native, cuda, cap, chunk, n_fill, p_pos):
+    """stratified (pos_fraction) sample over large rings with the larger flag chunks the engine picks for them:
+    the slots must be the ones replay_memory.py:58-68 picks (np.argwhere order + random.sample index streams)."""
+    rs = np.random.RandomState(cap % 1000 + chunk)
+    flags_h = (rs.rand(n_fill) < p_pos).astype(np.float32)
+    cap_pad = (cap + 15) // 16 * 16
+    ring = torch.zeros(cap, 8, device=cuda)
+    flags = torch.zeros(cap_pad, dtype=torch.uint8, device=cuda)
+    cnt = torch.zeros(native.NUM_COUNTERS, dtype=torch.int64, device=cuda)
+    rec = np.zeros((n_fill, 8), np.float32)
+    rec[:, 0] = np.arange(n_fill) % 4096; rec[:, 1] = np.arange(n_fill) // 4096; rec[:, 4] = flags_h
+    native.replay_push(ring, cap, torch.from_numpy(rec).to(cuda), n_fill, cnt, cons_flags=flags)
+    n_chunks = (cap_pad + chunk - 1) // chunk
+    counts = torch.zeros(2, n_chunks, dtype=torch.int32, device=cuda)
+    native.replay_flag_count(flags, cap_pad, chunk, counts)
+    f = flags.cpu().numpy()
+    pad = np.zeros(n_chunks * chunk, np.uint8); pad[:cap_pad] = f
+    assert np.array_equal(counts[0].cpu().numpy(), (pad.reshape(n_chunks, chunk) == 1).sum(1))
+    assert np.array_equal(counts[1].cpu().numpy(), (pad.reshape(n_chunks, chunk) == 2).sum(1))
+    seed = 77
+    mt = native.mt19937_seed(seed).to(cuda)
+    st = oreplay.MT19937(seed)
+    pos_slots = np.argwhere(flags_h).ravel()
+    neg_slots = np.argwhere(1 - flags_h).ravel()
+    B, pf = 256, 0.3
+    cfg = native.sample_config(cap_pad, B, True, pf, 0, chunk, -1.0)
+    for _ in range(3):
+        out = [torch.zeros(B, 2, device=cuda), torch.zeros(B, 2, device=cuda), torch.zeros(B, device=cuda),
+               torch.zeros(B, 2, device=cuda), torch.zeros(B, device=cuda)]
+        idx = torch.full((B,), -1, dtype=torch.int64, device=cuda)
+        native.replay_sample(cfg, ring, mt, cnt, native.C_QRISK_ROWS, *out, out_idx=idx, cons_flags=flags, chunk_counts=counts)
+        torch.cuda.synchronize()
+        assert int(cnt[native.C_QRISK_ROWS].item()) == B and int(cnt[native.C_ERROR].item()) == 0
+        pi = st.sample_indices(len(pos_slots), int(B * pf))
+        ni = st.sample_indices(len(neg_slots), B - int(B * pf))
+        want = np.concatenate([pos_slots[pi], neg_slots[ni]])
+        assert np.array_equal(idx.cpu().numpy(), want)
+        assert np.array_equal(out[0].cpu().numpy()[:, 0] + 4096.0 * out[0].cpu().numpy()[:, 1], want.astype(np.float64))
+        assert np.array_equal(out[2].cpu().numpy(), flags_h[want])
