@@ -1,23 +1,30 @@
-"""config/utils.py of the reference (:6-27): swish and the truncated-normal affine init of the ensemble.
-The init draws come from scipy's truncnorm on the numpy GLOBAL RNG, as in the reference (so `np.random.seed`
-pins them, experiment.py:91)."""
-import numpy as np
+"""Helpers of the PETS ensemble definition (the names the reference's config/utils.py:6-27 exports: `swish`,
+`truncated_normal`, `get_affine_params`).
+
+The initial weights are the reference's: scipy truncnorm draws on the numpy GLOBAL generator, clipped at two standard
+deviations, with std 1 / (2 sqrt(fan_in)); `np.random.seed` in experiment.py:91 therefore pins them.  Biases start at
+zero.  Shapes are [ensemble, fan_in, fan_out] and [ensemble, 1, fan_out] (batched `bmm` layout of config/maze.py:71-96).
+"""
+import math
+
 import torch
-from torch import nn as nn
-from scipy.stats import truncnorm
+from scipy import stats
+
+_CLIP = 2.0   # truncation of the normal, in standard deviations
 
 
 def swish(x):
-    return x * torch.sigmoid(x)
+    """x * sigmoid(x) (config/utils.py:6-7); the device kernels use the same expression (csrc/mpc.cu)."""
+    return torch.sigmoid(x) * x
 
 
 def truncated_normal(size, std):
-    val = truncnorm.rvs(-2, 2, size=size) * std
-    return torch.tensor(val, dtype=torch.float32)
+    draws = stats.truncnorm.rvs(-_CLIP, _CLIP, size=size)
+    return torch.as_tensor(draws * std).to(torch.float32)
 
 
 def get_affine_params(ensemble_size, in_features, out_features):
-    w = truncated_normal(size=(ensemble_size, in_features, out_features), std=1.0 / (2.0 * np.sqrt(in_features)))
-    w = nn.Parameter(w)
-    b = nn.Parameter(torch.zeros(ensemble_size, 1, out_features, dtype=torch.float32))
-    return w, b
+    std = 1.0 / (2.0 * math.sqrt(in_features))
+    weight = torch.nn.Parameter(truncated_normal((ensemble_size, in_features, out_features), std))
+    bias = torch.nn.Parameter(torch.zeros((ensemble_size, 1, out_features), dtype=torch.float32))
+    return weight, bias

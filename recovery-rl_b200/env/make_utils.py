@@ -1,27 +1,27 @@
-"""env id <-> class maps (reference env/make_utils.py:1-31), without the gym registry."""
-ENV_ID = {
-    'navigation1': 'Navigation-v0',
-    'navigation2': 'Navigation-v1',
-    'maze': 'Maze-v0',
-}
+"""Environment factory of the drop-in surface: `register_env(name)` / `make_env(name)` as called by
+experiment.py:157-158 (reference env/make_utils.py:1-31 does this through the gym registry; here a plain table maps
+the three point envs of the hot path to their host-side classes, which step through librrl.so)."""
+import importlib
 
-ENV_CLASS = {
-    'navigation1': 'Navigation1',
-    'navigation2': 'Navigation2',
-    'maze': 'MazeNavigation',
+# env-name flag -> (gym id the reference registers, module under env/, class)
+_TABLE = {
+    'navigation1': ('Navigation-v0', 'env.navigation1', 'Navigation1'),
+    'navigation2': ('Navigation-v1', 'env.navigation2', 'Navigation2'),
+    'maze': ('Maze-v0', 'env.maze', 'MazeNavigation'),
 }
-
-_REGISTRY = {}
+ENV_ID = {name: row[0] for name, row in _TABLE.items()}
+ENV_CLASS = {name: row[2] for name, row in _TABLE.items()}
+_constructors = {}
 
 
 def register_env(env_name):
-    assert env_name in ENV_ID, "unknown environment"
-    import importlib
-    module = importlib.import_module("env." + env_name)
-    _REGISTRY[ENV_ID[env_name]] = getattr(module, ENV_CLASS[env_name])
+    if env_name not in _TABLE:
+        raise AssertionError("unknown environment %r (have: %s)" % (env_name, ", ".join(sorted(_TABLE))))
+    _, module, cls = _TABLE[env_name]
+    _constructors[env_name] = getattr(importlib.import_module(module), cls)
+    return _constructors[env_name]
 
 
 def make_env(env_name):
-    if ENV_ID[env_name] not in _REGISTRY:
-        register_env(env_name)
-    return _REGISTRY[ENV_ID[env_name]]()
+    ctor = _constructors.get(env_name) or register_env(env_name)
+    return ctor()
