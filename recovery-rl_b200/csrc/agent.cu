@@ -863,7 +863,7 @@ __global__ void peer_barrier_kernel(const PeerBarrierArgs A) {
         do {
             asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(src) : "memory");
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-        } while (!lost && (int)(v - epoch) < 0 && t1 - t0 < 10000000000ull);   // give up after 10 s instead of hanging the GPU
+        } while (!lost && (int)(v - epoch) < 0 && t1 - t0 < 60000000000ull);   // give up after 60 s instead of hanging the GPU
         if ((int)(v - epoch) < 0) A.counters[RRL_C_ERROR] = 2;
         if (A.exchange && r != A.rank) {
             const long long* vsrc = reinterpret_cast<const long long*>(A.signal[A.rank] + kPadBase + 16) + r;

@@ -10,8 +10,9 @@ One `step()` is what recovery_rl/experiment.py:396-452 does for one env step, fo
 Everything lives in HBM; every call below only ENQUEUES kernels of librrl.so on the current stream, all
 data-dependent control flow (gates, effective batch rows, ring positions) is read from the device counter
 block, so the whole step is captured once into a CUDA graph and replayed.  With world_size > 1 each rank
-owns N/world env copies and its own replay shards; gradients are summed with one NCCL all-reduce per
-optimizer step over the flat gradient block (1/world applied inside Adam).
+owns N/world env copies and its own replay shards; gradients are summed inside the optimizer-step kernel over
+NVLink peer memory (peer_grads: symmetric arena + flag barrier) or, as a fallback, with one NCCL all-reduce per
+optimizer step over the flat gradient block (1/world applied inside Adam either way).
 """
 import numpy as np
 import torch
@@ -308,6 +309,10 @@ class VecEngine(object):
         """experiment.py:289-296: critic_safe_pretraining_steps x QRiskWrapper.update_parameters with
         batch_size = min(batch_size, len(constraint_demo_data)); no gate."""
         b = self.B if n_demos is None else min(self.B, int(n_demos))
+        if self.peer_arena is not None:      # ranks reach the first flag barrier together (host-side skew stays out of it)
+            import torch.distributed as dist
+            torch.cuda.synchronize(self.device)
+            dist.barrier(group=self.pg)
         sc = native.sample_config(self.cons_cap, b, True, self.pos_fraction, gate_mode=0, chunk=self.flag_chunk)
         for _ in range(int(steps)):
             self.qrisk_update(sc)
