@@ -339,12 +339,13 @@ def golden_agent(tag, env_name, scale, argv, B, n_updates=3, seed=11, dump_init=
 # ---------------------------------------------------------------------------------------
 # F. N = 1 whole-trajectory trace through Experiment (experiment.py:356-491)
 # ---------------------------------------------------------------------------------------
-def golden_trajectory():
+def golden_trajectory(env_name="navigation1", seed=7, gamma_safe="0.8", eps_safe="0.3", n_eps=12,
+                      fname="traj_nav1_seed7.npz"):
     harness.setup()
     import recovery_rl.replay_memory as rm
-    argv = ["--env-name", "navigation1", "--use_recovery", "--MF_recovery", "--gamma_safe", "0.8",
-            "--eps_safe", "0.3", "--num_eps", "12", "--num_unsafe_transitions", "2000",
-            "--critic_safe_pretraining_steps", "30", "--seed", "7", "--batch_size", "16",
+    argv = ["--env-name", env_name, "--use_recovery", "--MF_recovery", "--gamma_safe", gamma_safe,
+            "--eps_safe", eps_safe, "--num_eps", str(n_eps), "--num_unsafe_transitions", "2000",
+            "--critic_safe_pretraining_steps", "30", "--seed", str(seed), "--batch_size", "16",
             "--logdir", "/tmp/rrl_golden_runs"]
     idx_log = []
     orig_sample = random.sample
@@ -384,7 +385,7 @@ def golden_trajectory():
         n_pre_idx = len(idx_log)
         infos = []
         ep_len = []
-        for ep in range(1, 13):
+        for ep in range(1, n_eps + 1):
             info = exp.get_train_rollout(ep)
             infos += info
             ep_len.append(len(info))
@@ -421,7 +422,7 @@ def golden_trajectory():
            "weights_sha256": np.array(sha.hexdigest())}
     _dump_agent(exp.agent, "final_", out, STRIDE)
     out["stride"] = np.int64(STRIDE)
-    _save("traj_nav1_seed7.npz", **out)
+    _save(fname, **out)
 
 
 # ---------------------------------------------------------------------------------------
@@ -568,6 +569,7 @@ def main():
                  ["--use_recovery", "--MF_recovery", "--gamma_safe", "0.5", "--eps_safe", "0.15",
                   "--pos_fraction", "0.3"], 64, dump_init=False)
     golden_trajectory()
+    golden_trajectory("navigation2", 3, "0.65", "0.2", 8, "traj_nav2_seed3.npz")   # scripts/navigation2.sh:7 settings
     golden_algos()
 
 

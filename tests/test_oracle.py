@@ -116,18 +116,21 @@ def test_maze_scalar_matches_vectorised():
         assert np.array_equal(o[0], ns[i]) and o[1] == r[i] and o[2] == d[i] and o[3] == c[i] and o[4] == su[i]
 
 
-def test_oracle_loop_reproduces_reference_trajectory(golden_dir):
-    """oracle/loop.py fed the recorded noise == the reference's Experiment (12 episodes, seed 7): flags, episode
+@pytest.mark.parametrize("fname,env_name,seed,gamma_safe,eps_safe", [
+    ("traj_nav1_seed7.npz", "navigation1", 7, 0.8, 0.3), ("traj_nav2_seed3.npz", "navigation2", 3, 0.65, 0.2)])
+def test_oracle_loop_reproduces_reference_trajectory(golden_dir, fname, env_name, seed, gamma_safe, eps_safe):
+    """oracle/loop.py fed the recorded noise == the reference's Experiment (12 episodes seed 7 on Navigation1, 8 episodes
+    seed 3 on Navigation2 with the scripts/navigation2.sh:7 settings): flags, episode
     boundaries, replay indices and counters bit-exact; states / actions / final weights to fp32 round-off.
     (On the CPU that recorded the golden the whole trajectory is bit-identical; another CPU takes another MKL
     sgemm code path and the fp32 actions move by 1 ulp, so the float fields carry an absolute 1e-5.)"""
     from oracle.loop import OracleExperiment, NoiseSource
-    z = np.load(os.path.join(golden_dir, "traj_nav1_seed7.npz"))
+    z = np.load(os.path.join(golden_dir, fname))
     sizes = z["eps_sizes"]
     offs = np.concatenate([[0], np.cumsum(sizes)])
     eps = [z["eps"][offs[i]:offs[i + 1]] for i in range(len(sizes))]
-    noise = NoiseSource(7, eps=eps, env_noise=list(z["env_noise"]), rand_actions=list(z["rand_actions"]))
-    exp = OracleExperiment("navigation1", seed=7, batch_size=16, gamma_safe=0.8, eps_safe=0.3, noise=noise)
+    noise = NoiseSource(seed, eps=eps, env_noise=list(z["env_noise"]), rand_actions=list(z["rand_actions"]))
+    exp = OracleExperiment(env_name, seed=seed, batch_size=16, gamma_safe=gamma_safe, eps_safe=eps_safe, noise=noise)
     tr = [(z["offline_state"][i], z["offline_action"][i], z["offline_constraint"][i], z["offline_next_state"][i],
            z["offline_mask"][i]) for i in range(len(z["offline_state"]))]
     exp.pretrain(tr, 30, num_unsafe_transitions=2000)
