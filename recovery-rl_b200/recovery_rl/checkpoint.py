@@ -13,7 +13,6 @@ A checkpoint is one torch.save'd dict:
 """
 import collections
 
-import numpy as np
 import torch
 
 from . import native

@@ -4,9 +4,6 @@ Same class and `obtain_solution(init_mean, init_var)` contract as the reference,
 (sample -> cost -> elites -> smoothing) runs on the device for a batch of env copies at once: candidates are
 drawn, rolled through the ensemble, ranked and reduced by the kernels of csrc/mpc.cu.  `cost_function` is therefore
 not a numpy callback but the planner context (recovery_rl.MPC.MPC) that owns the device buffers."""
-import numpy as np
-import torch
-
 from . import native
 
 

@@ -6,7 +6,6 @@ import argparse
 import os
 import sys
 
-import numpy as np
 import torch
 import torch.distributed as dist
 

@@ -4,8 +4,6 @@ from the shared torch seed and distinct per-rank sampler streams."""
 import os
 import sys
 
-import numpy as np
-import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
