@@ -41,7 +41,6 @@ def sync_gate_counts(counters, group=None):
     total = local.clone()
     dist.all_reduce(total, op=dist.ReduceOp.SUM, group=group)
     counters[native.C_EXT_VIOLS:native.C_EXT_VIOLS + 1] = total - local
-    return int(0)
 
 
 class PeerArena(object):
