@@ -74,3 +74,25 @@ def test_no_cpu_fallback(native):
     cpu = torch.zeros(8)
     with pytest.raises(native.RRLError):
         native.p(cpu, "f32")
+
+
+def test_peer_table_packing_and_argument_checks(native):
+    """rrl_peers_t (the peer-memory gradient sum of the sharded run): packing of the host-side table and the argument
+    validation of the entry points, which happens before anything is launched (no GPU needed)."""
+    P = native.make_peers(1, [0x1000, 0x2000, 0x3000], [0x10, 0x20, 0x30])
+    assert (P.world, P.rank) == (3, 1)
+    assert list(P.arena)[:4] == [0x1000, 0x2000, 0x3000, 0] and list(P.signal)[:4] == [0x10, 0x20, 0x30, 0]
+    assert ctypes.sizeof(P) == 8 + 8 * 8 + 8 * 8                     # int32 world, rank; uint64 arena[8], signal[8]
+    with pytest.raises(native.RRLError):
+        native.make_peers(0, list(range(9)), list(range(9)))           # one node: at most 8 ranks
+    with pytest.raises(native.RRLError):
+        native.make_peers(0, [1, 2], [1])
+    lib = native.lib()
+    assert lib.rrl_peer_barrier(None, None, None, None) < 0
+    assert b"bad argument" in lib.rrl_last_error()
+    bad = native.make_peers(0, [0x1000], [0x10])
+    bad.rank = 5                                                        # rank outside [0, world)
+    one = (ctypes.c_int64 * 1)()
+    assert lib.rrl_peer_barrier(ctypes.byref(bad), one, one, None) < 0
+    cfg = native.agent_config(max_batch=256)
+    assert lib.rrl_sac_apply_p2p(ctypes.byref(cfg), None, None, None, None) < 0
