@@ -164,8 +164,9 @@ def run_reference(args, rank, world):
     exp = OracleExperiment(args.env_name, seed=args.seed, batch_size=args.batch, gamma_safe=0.5, eps_safe=0.15,
                            pos_fraction=0.3 if args.env_name == "maze" else -1.0)
     np.random.seed(args.seed)
-    tr = oenvs.maze_offline_data(2000, np.random.RandomState(args.seed)) if args.env_name == "maze" else \
-        oenvs.nav_offline_data(oenvs.KIND_BY_NAME[args.env_name], 2000)
+    n_demo = min(2000, args.demos)
+    tr = oenvs.maze_offline_data(n_demo, np.random.RandomState(args.seed)) if args.env_name == "maze" else \
+        oenvs.nav_offline_data(oenvs.KIND_BY_NAME[args.env_name], n_demo)
     exp.pretrain(tr, 10)
     while len(exp.memory) <= args.batch + 1:
         exp.step()

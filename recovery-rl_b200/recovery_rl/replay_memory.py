@@ -73,16 +73,22 @@ class ReplayMemory(object):
                          torch.zeros(batch_size, device=d), torch.zeros(batch_size, dtype=torch.int64, device=d))
         return self._out
 
+    def _flag_chunk(self):
+        """flag-chunk size of the stratified sampler: 512 B, grown in 512-B steps so that a ring never needs more than
+        the 8,192 chunks replay.cu handles (--replay_size above 4M transitions)."""
+        return FLAG_CHUNK * max(1, -(-self.cap_pad // (8192 * FLAG_CHUNK)))
+
     def _sample_device(self, batch_size, outs, pos_fraction=None, rows_counter=native.C_SAC_ROWS, idx=None):
         cfg = native.sample_config(self.cap_pad if (self.is_constraint and pos_fraction is not None) else self.capacity,
-                                   int(batch_size), self.is_constraint, pos_fraction, gate_mode=0, chunk=FLAG_CHUNK)
+                                   int(batch_size), self.is_constraint, pos_fraction, gate_mode=0, chunk=self._flag_chunk())
         chunk_counts = None
         if self.is_constraint and pos_fraction is not None:
-            n_chunks = (self.cap_pad + FLAG_CHUNK - 1) // FLAG_CHUNK
+            chunk = self._flag_chunk()
+            n_chunks = (self.cap_pad + chunk - 1) // chunk
             if getattr(self, "_chunk_counts", None) is None:
                 self._chunk_counts = torch.zeros(2, n_chunks, dtype=torch.int32, device=self.device)
             chunk_counts = self._chunk_counts
-            native.replay_flag_count(self.flags, self.cap_pad, FLAG_CHUNK, chunk_counts)
+            native.replay_flag_count(self.flags, self.cap_pad, chunk, chunk_counts)
         native.replay_sample(cfg, self.ring, _shared["mt"], self.counters, rows_counter, outs[0], outs[1], outs[2],
                              outs[3], outs[4], out_idx=idx, cons_flags=self.flags, chunk_counts=chunk_counts)
 
