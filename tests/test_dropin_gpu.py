@@ -73,13 +73,14 @@ def test_replay_memory_api_matches_cpython(native, cuda):
         mem.sample(301)
 
 
-def test_experiment_reproduces_reference_run(native, cuda, golden_dir, tmp_path):
+@pytest.mark.parametrize("fname,n_eps", [("traj_nav1_seed7.npz", 12), ("traj_nav2_seed3.npz", 8)])
+def test_experiment_reproduces_reference_run(native, cuda, golden_dir, tmp_path, fname, n_eps):
     """scripts/navigation1.sh-style command through the drop-in Experiment with LIVE RNGs (numpy, torch, Box,
     CPython-compatible sampler) == the reference's own run at seed 7: same episode lengths, constraint and
     recovery flags; states to fp32 round-off of the recovery actions."""
     import arg_utils
     from recovery_rl.experiment import Experiment
-    z = np.load(os.path.join(golden_dir, "traj_nav1_seed7.npz"))
+    z = np.load(os.path.join(golden_dir, fname))
     argv = [str(x) for x in z["argv"]]
     argv[argv.index("--logdir") + 1] = str(tmp_path)
     args = arg_utils.get_args(argv + ["--tensor_cores", "0"])
@@ -90,7 +91,7 @@ def test_experiment_reproduces_reference_run(native, cuda, golden_dir, tmp_path)
     assert np.array_equal(np.array([t[3] for t in off]), z["offline_next_state"])
     exp.pretrain_critic_recovery()
     infos, ep_len = [], []
-    for ep in range(1, 13):
+    for ep in range(1, n_eps + 1):
         info = exp.get_train_rollout(ep)
         infos += info
         ep_len.append(len(info))
