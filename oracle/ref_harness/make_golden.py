@@ -340,10 +340,10 @@ def golden_agent(tag, env_name, scale, argv, B, n_updates=3, seed=11, dump_init=
 # F. N = 1 whole-trajectory trace through Experiment (experiment.py:356-491)
 # ---------------------------------------------------------------------------------------
 def golden_trajectory(env_name="navigation1", seed=7, gamma_safe="0.8", eps_safe="0.3", n_eps=12,
-                      fname="traj_nav1_seed7.npz"):
+                      fname="traj_nav1_seed7.npz", algo=("--use_recovery", "--MF_recovery")):
     harness.setup()
     import recovery_rl.replay_memory as rm
-    argv = ["--env-name", env_name, "--use_recovery", "--MF_recovery", "--gamma_safe", gamma_safe,
+    argv = ["--env-name", env_name] + list(algo) + ["--gamma_safe", gamma_safe,
             "--eps_safe", eps_safe, "--num_eps", str(n_eps), "--num_unsafe_transitions", "2000",
             "--critic_safe_pretraining_steps", "30", "--seed", str(seed), "--batch_size", "16",
             "--logdir", "/tmp/rrl_golden_runs"]
@@ -380,7 +380,9 @@ def golden_trajectory(env_name="navigation1", seed=7, gamma_safe="0.8", eps_safe
         exp.env.action_space.sample = rec_as
         del harness.eps_log[:]
         np.random.randn = rec_randn
-        exp.pretrain_critic_recovery()
+        cfg = exp.exp_cfg
+        if cfg.use_recovery or cfg.DGD_constraints or cfg.RCPO:     # experiment.py:357-361
+            exp.pretrain_critic_recovery()
         n_pre_eps = len(harness.eps_log)
         n_pre_idx = len(idx_log)
         infos = []
@@ -570,6 +572,8 @@ def main():
                   "--pos_fraction", "0.3"], 64, dump_init=False)
     golden_trajectory()
     golden_trajectory("navigation2", 3, "0.65", "0.2", 8, "traj_nav2_seed3.npz")   # scripts/navigation2.sh:7 settings
+    golden_trajectory("navigation1", 2, "0.8", "0.3", 6, "traj_nav1_unconstrained.npz", algo=())   # navigation1.sh:21
+    golden_trajectory("navigation1", 6, "0.8", "0.3", 6, "traj_nav1_rp.npz", algo=("--constraint_reward_penalty", "1000"))
     golden_algos()
 
 

@@ -116,11 +116,14 @@ def test_maze_scalar_matches_vectorised():
         assert np.array_equal(o[0], ns[i]) and o[1] == r[i] and o[2] == d[i] and o[3] == c[i] and o[4] == su[i]
 
 
-@pytest.mark.parametrize("fname,env_name,seed,gamma_safe,eps_safe", [
-    ("traj_nav1_seed7.npz", "navigation1", 7, 0.8, 0.3), ("traj_nav2_seed3.npz", "navigation2", 3, 0.65, 0.2)])
-def test_oracle_loop_reproduces_reference_trajectory(golden_dir, fname, env_name, seed, gamma_safe, eps_safe):
+@pytest.mark.parametrize("fname,env_name,seed,gamma_safe,eps_safe,algo", [
+    ("traj_nav1_seed7.npz", "navigation1", 7, 0.8, 0.3, {}), ("traj_nav2_seed3.npz", "navigation2", 3, 0.65, 0.2, {}),
+    ("traj_nav1_unconstrained.npz", "navigation1", 2, 0.8, 0.3, dict(use_recovery=False)),
+    ("traj_nav1_rp.npz", "navigation1", 6, 0.8, 0.3, dict(use_recovery=False, constraint_reward_penalty=1000.0))])
+def test_oracle_loop_reproduces_reference_trajectory(golden_dir, fname, env_name, seed, gamma_safe, eps_safe, algo):
     """oracle/loop.py fed the recorded noise == the reference's Experiment (12 episodes seed 7 on Navigation1, 8 episodes
-    seed 3 on Navigation2 with the scripts/navigation2.sh:7 settings): flags, episode
+    seed 3 on Navigation2 with the scripts/navigation2.sh:7 settings, and the unconstrained / reward-penalty lines of
+    scripts/navigation1.sh:21,42 for 6 episodes): flags, episode
     boundaries, replay indices and counters bit-exact; states / actions / final weights to fp32 round-off.
     (On the CPU that recorded the golden the whole trajectory is bit-identical; another CPU takes another MKL
     sgemm code path and the fp32 actions move by 1 ulp, so the float fields carry an absolute 1e-5.)"""
@@ -130,10 +133,11 @@ def test_oracle_loop_reproduces_reference_trajectory(golden_dir, fname, env_name
     offs = np.concatenate([[0], np.cumsum(sizes)])
     eps = [z["eps"][offs[i]:offs[i + 1]] for i in range(len(sizes))]
     noise = NoiseSource(seed, eps=eps, env_noise=list(z["env_noise"]), rand_actions=list(z["rand_actions"]))
-    exp = OracleExperiment(env_name, seed=seed, batch_size=16, gamma_safe=gamma_safe, eps_safe=eps_safe, noise=noise)
+    exp = OracleExperiment(env_name, seed=seed, batch_size=16, gamma_safe=gamma_safe, eps_safe=eps_safe, noise=noise, **algo)
     tr = [(z["offline_state"][i], z["offline_action"][i], z["offline_constraint"][i], z["offline_next_state"][i],
            z["offline_mask"][i]) for i in range(len(z["offline_state"]))]
-    exp.pretrain(tr, 30, num_unsafe_transitions=2000)
+    if algo.get("use_recovery", True):            # experiment.py:357-361: only the constrained algorithms pre-train
+        exp.pretrain(tr, 30, num_unsafe_transitions=2000)
     assert len(exp.idx_log) == int(z["n_pre_idx"])
     infos = []
     for _ in range(int(z["ep_len"].sum())):
