@@ -278,8 +278,9 @@ class Agent(object):
         return qf1_loss.item(), qf2_loss.item(), policy_loss.item(), alpha_loss, alpha_log
 
     # ---- sac.py:139-161: SQRL action filter ------------------------------------------------------
-    def select_action_sqrl(self, state, eps, eps_safe=None, safe_samples=100):
-        """eps: [safe_samples, 2].  The Categorical draw comes from the torch global generator, as in the reference."""
+    def select_action_sqrl(self, state, eps, eps_safe=None, safe_samples=100, categorical=None):
+        """eps: [safe_samples, 2].  The Categorical draw comes from the torch global generator, as in the reference,
+        unless `categorical(probs) -> index` is given (replay of a recorded run)."""
         eps_safe = self.eps_safe if eps_safe is None else eps_safe
         with torch.no_grad():
             sb = torch.as_tensor(np.asarray(state), dtype=torch.float32).unsqueeze(0).repeat(safe_samples, 1)
@@ -291,7 +292,8 @@ class Agent(object):
                 return pi[torch.argmin(qmax)].numpy()
             # NB sac.py:157-159 indexes `pi` with the index INTO THE FILTERED SET (not thresh_idxs[sampled_idx]):
             # reproduced as written
-            return pi[torch.distributions.Categorical(probs).sample()].numpy()
+            j = torch.distributions.Categorical(probs).sample() if categorical is None else int(categorical(probs))
+            return pi[j].numpy()
 
     # ---- qrisk.py:86-182 ---------------------------------------------------------------------------
     def qrisk_update(self, batch, eps_next, eps_rec):

@@ -27,11 +27,18 @@ class NoiseSource(object):
     reference's call order (torch for agent eps, numpy for env noise and resets, a Box RandomState for
     random start actions)."""
 
-    def __init__(self, seed, eps=None, env_noise=None, rand_actions=None):
+    def __init__(self, seed, eps=None, env_noise=None, rand_actions=None, categorical=None):
+        self.cat = None if categorical is None else list(categorical)
         self.eps = None if eps is None else list(eps)
         self.env_noise = None if env_noise is None else list(env_noise)
         self.rand_actions = None if rand_actions is None else list(rand_actions)
         self.box_rng = np.random.RandomState(seed)
+
+    def categorical(self, probs):
+        """the SQRL action filter's Categorical draw (sac.py:156-158): recorded index, else the live torch generator"""
+        if self.cat is not None:
+            return int(self.cat.pop(0))
+        return int(torch.distributions.Categorical(probs).sample())
 
     def agent_eps(self, rows):
         if self.eps is not None:
@@ -57,7 +64,9 @@ class NoiseSource(object):
 class OracleExperiment(object):
     def __init__(self, env_name, seed=0, batch_size=256, replay_size=1000000, gamma=0.99, alpha=0.2, tau=0.005, lr=3e-4,
                  gamma_safe=0.5, tau_safe=0.0002, eps_safe=0.1, use_recovery=True, mf_recovery=True, pos_fraction=-1.0,
-                 constraint_reward_penalty=0.0, start_steps=100, noise=None):
+                 constraint_reward_penalty=0.0, start_steps=100, noise=None, dgd=False, update_nu=False, rcpo=False,
+                 nu=0.01, nu_schedule=False, nu_start=1e3, nu_end=0.0, num_eps=1000000, lambda_rcpo=0.01,
+                 constraint_sampling=False):
         self.env_name = env_name
         self.kind = envs.KIND_BY_NAME[env_name]
         self.B = batch_size
@@ -72,7 +81,17 @@ class OracleExperiment(object):
         sc = ACTION_SCALE[env_name]
         self.scale = sc
         self.agent = Agent(action_scale=(sc, sc), gamma=gamma, alpha=alpha, tau=tau, gamma_safe=gamma_safe,
-                           tau_safe=tau_safe, eps_safe=eps_safe, lr=lr, mf_recovery=mf_recovery)
+                           tau_safe=tau_safe, eps_safe=eps_safe, lr=lr, mf_recovery=mf_recovery, dgd=dgd,
+                           update_nu=update_nu, rcpo=rcpo, nu=nu, lambda_rcpo=lambda_rcpo)
+        # the safety critic is trained for Recovery RL and for the LR / RSPO / SQRL / RCPO comparisons (experiment.py:357-361,443)
+        self.uses_qrisk = bool(use_recovery or dgd or rcpo)
+        # experiment.py:80-87 + utils.py:62-64: the multiplier handed to every SAC update
+        if nu_schedule:
+            self.nu_fn = lambda t: nu_start + t / num_eps * (nu_end - nu_start) if t < num_eps else nu_end
+        else:
+            self.nu_fn = lambda t: nu
+        self.i_episode = 1
+        self.constraint_sampling = bool(constraint_sampling)      # SQRL action filter (sac.py:139-161)
         stream = SharedStream()
         self.memory = ReplayMemory(replay_size, seed, stream)
         self.recovery_memory = ConstraintReplayMemory(replay_size, seed, stream)
@@ -135,6 +154,9 @@ class OracleExperiment(object):
     def _get_action(self):
         if self.start_steps > self.total_numsteps:
             action = self.noise.random_action(self.scale)
+        elif self.constraint_sampling:
+            e = self.noise.agent_eps(100)
+            action = self.agent.select_action_sqrl(np.asarray(self.state, np.float32), e, categorical=self.noise.categorical)
         else:
             e = self.noise.agent_eps(1)
             action = self.agent.act(self.state[None], e, np.zeros((1, 2), np.float32), use_recovery=False)[0][0]
@@ -161,8 +183,8 @@ class OracleExperiment(object):
             batch = self.memory.gather(idx)
             e_next = self.noise.agent_eps(len(idx))
             e_cur = self.noise.agent_eps(len(idx))
-            self.last_losses = self.agent.sac_update(batch, e_next, e_cur, self.updates)
-            if self.use_recovery and len(self.recovery_memory) > self.B and \
+            self.last_losses = self.agent.sac_update(batch, e_next, e_cur, self.updates, nu=self.nu_fn(self.i_episode))
+            if len(self.recovery_memory) > self.B and \
                     (self.num_viols + self.num_constraint_violations) / self.B > self.gate_pos_fraction:
                 self._qrisk_update(self.B)
             self.updates += 1
@@ -180,7 +202,7 @@ class OracleExperiment(object):
         horizon = envs.MAZE_HORIZON if self.kind == envs.MAZE else envs.NAV_HORIZON
         done = done or self.ep_steps == horizon
         self.memory.push(state, action, reward, next_state, mask)
-        if self.use_recovery:
+        if self.uses_qrisk:
             self.recovery_memory.push(state, real_action, float(constraint), next_state, mask)
         self.state = next_state
         if done:
@@ -192,6 +214,7 @@ class OracleExperiment(object):
                     self.viol_and_no_recovery += 1
             self.num_successes += int(success)
             self.state = None
+            self.i_episode += 1
         info["episode_end"] = bool(done)
         return info
 

@@ -340,7 +340,7 @@ def golden_agent(tag, env_name, scale, argv, B, n_updates=3, seed=11, dump_init=
 # F. N = 1 whole-trajectory trace through Experiment (experiment.py:356-491)
 # ---------------------------------------------------------------------------------------
 def golden_trajectory(env_name="navigation1", seed=7, gamma_safe="0.8", eps_safe="0.3", n_eps=12,
-                      fname="traj_nav1_seed7.npz", algo=("--use_recovery", "--MF_recovery")):
+                      fname="traj_nav1_seed7.npz", algo=("--use_recovery", "--MF_recovery"), stride=None):
     harness.setup()
     import recovery_rl.replay_memory as rm
     argv = ["--env-name", env_name] + list(algo) + ["--gamma_safe", gamma_safe,
@@ -364,6 +364,15 @@ def golden_trajectory(env_name="navigation1", seed=7, gamma_safe="0.8", eps_safe
         env_noise.append(np.array(x, np.float64).ravel().copy())
         return x
 
+    cat_log = []
+    orig_cat = torch.distributions.Categorical.sample
+
+    def rec_cat(self, *a, **k):
+        j = orig_cat(self, *a, **k)
+        cat_log.append(int(j))
+        return j
+
+    torch.distributions.Categorical.sample = rec_cat
     so = sys.stdout
     sys.stdout = open(os.devnull, "w")
     try:
@@ -395,6 +404,7 @@ def golden_trajectory(env_name="navigation1", seed=7, gamma_safe="0.8", eps_safe
         sys.stdout = so
         np.random.randn = orig_randn
         rm.random.sample = orig_sample
+        torch.distributions.Categorical.sample = orig_cat
     sha = hashlib.sha256()
     for mod in (exp.agent.critic, exp.agent.policy, exp.agent.safety_critic.safety_critic,
                 exp.agent.safety_critic.policy):
@@ -421,9 +431,11 @@ def golden_trajectory(env_name="navigation1", seed=7, gamma_safe="0.8", eps_safe
            "offline_mask": np.array([float(t[4]) for t in offline]),
            "num_viols": np.int64(exp.num_viols), "num_successes": np.int64(exp.num_successes),
            "total_numsteps": np.int64(exp.total_numsteps), "updates": np.int64(exp.updates),
+           "cat_idx": np.array(cat_log, np.int64),     # SQRL: every Categorical draw of the action filter, in order
            "weights_sha256": np.array(sha.hexdigest())}
-    _dump_agent(exp.agent, "final_", out, STRIDE)
-    out["stride"] = np.int64(STRIDE)
+    stride = STRIDE if stride is None else stride
+    _dump_agent(exp.agent, "final_", out, stride)
+    out["stride"] = np.int64(stride)
     _save(fname, **out)
 
 
@@ -574,6 +586,16 @@ def main():
     golden_trajectory("navigation2", 3, "0.65", "0.2", 8, "traj_nav2_seed3.npz")   # scripts/navigation2.sh:7 settings
     golden_trajectory("navigation1", 2, "0.8", "0.3", 6, "traj_nav1_unconstrained.npz", algo=())   # navigation1.sh:21
     golden_trajectory("navigation1", 6, "0.8", "0.3", 6, "traj_nav1_rp.npz", algo=("--constraint_reward_penalty", "1000"))
+    # comparison algorithms of scripts/navigation1.sh (LR :28, RSPO :35, RCPO :56), 6 episodes each
+    golden_trajectory("navigation1", 3, "0.8", "0.3", 6, "traj_nav1_lr.npz", stride=29,
+                      algo=("--DGD_constraints", "--nu", "5000", "--update_nu"))
+    golden_trajectory("navigation1", 4, "0.8", "0.3", 6, "traj_nav1_rspo.npz", stride=29,
+                      algo=("--DGD_constraints", "--nu_schedule", "--nu_start", "10000"))
+    golden_trajectory("navigation1", 7, "0.8", "0.3", 6, "traj_nav1_rcpo.npz", stride=29, algo=("--RCPO", "--lambda", "1000"))
+    # SQRL :49, with eps_safe 0.45 / start_steps 20 so that both branches of the action filter occur (6 Categorical draws,
+    # 29 argmin fall-backs)
+    golden_trajectory("navigation1", 5, "0.8", "0.45", 6, "traj_nav1_sqrl.npz", stride=29,
+                      algo=("--DGD_constraints", "--use_constraint_sampling", "--nu", "5000", "--update_nu", "--start_steps", "20"))
     golden_algos()
 
 

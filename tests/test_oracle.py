@@ -119,7 +119,15 @@ def test_maze_scalar_matches_vectorised():
 @pytest.mark.parametrize("fname,env_name,seed,gamma_safe,eps_safe,algo", [
     ("traj_nav1_seed7.npz", "navigation1", 7, 0.8, 0.3, {}), ("traj_nav2_seed3.npz", "navigation2", 3, 0.65, 0.2, {}),
     ("traj_nav1_unconstrained.npz", "navigation1", 2, 0.8, 0.3, dict(use_recovery=False)),
-    ("traj_nav1_rp.npz", "navigation1", 6, 0.8, 0.3, dict(use_recovery=False, constraint_reward_penalty=1000.0))])
+    ("traj_nav1_rp.npz", "navigation1", 6, 0.8, 0.3, dict(use_recovery=False, constraint_reward_penalty=1000.0)),
+    ("traj_nav1_lr.npz", "navigation1", 3, 0.8, 0.3, dict(use_recovery=False, mf_recovery=False, dgd=True, update_nu=True,
+                                                        nu=5000.0)),
+    ("traj_nav1_rspo.npz", "navigation1", 4, 0.8, 0.3, dict(use_recovery=False, mf_recovery=False, dgd=True, nu_schedule=True,
+                                                          nu_start=10000.0, nu_end=0.0, num_eps=6)),
+    ("traj_nav1_rcpo.npz", "navigation1", 7, 0.8, 0.3, dict(use_recovery=False, mf_recovery=False, rcpo=True,
+                                                          lambda_rcpo=1000.0)),
+    ("traj_nav1_sqrl.npz", "navigation1", 5, 0.8, 0.45, dict(use_recovery=False, mf_recovery=False, dgd=True, update_nu=True,
+                                                           nu=5000.0, constraint_sampling=True, start_steps=20))])
 def test_oracle_loop_reproduces_reference_trajectory(golden_dir, fname, env_name, seed, gamma_safe, eps_safe, algo):
     """oracle/loop.py fed the recorded noise == the reference's Experiment (12 episodes seed 7 on Navigation1, 8 episodes
     seed 3 on Navigation2 with the scripts/navigation2.sh:7 settings, and the unconstrained / reward-penalty lines of
@@ -132,11 +140,12 @@ def test_oracle_loop_reproduces_reference_trajectory(golden_dir, fname, env_name
     sizes = z["eps_sizes"]
     offs = np.concatenate([[0], np.cumsum(sizes)])
     eps = [z["eps"][offs[i]:offs[i + 1]] for i in range(len(sizes))]
-    noise = NoiseSource(seed, eps=eps, env_noise=list(z["env_noise"]), rand_actions=list(z["rand_actions"]))
+    noise = NoiseSource(seed, eps=eps, env_noise=list(z["env_noise"]), rand_actions=list(z["rand_actions"]),
+                        categorical=list(z["cat_idx"]) if "cat_idx" in z.files else None)
     exp = OracleExperiment(env_name, seed=seed, batch_size=16, gamma_safe=gamma_safe, eps_safe=eps_safe, noise=noise, **algo)
     tr = [(z["offline_state"][i], z["offline_action"][i], z["offline_constraint"][i], z["offline_next_state"][i],
            z["offline_mask"][i]) for i in range(len(z["offline_state"]))]
-    if algo.get("use_recovery", True):            # experiment.py:357-361: only the constrained algorithms pre-train
+    if exp.uses_qrisk:                             # experiment.py:357-361: only the constrained algorithms pre-train
         exp.pretrain(tr, 30, num_unsafe_transitions=2000)
     assert len(exp.idx_log) == int(z["n_pre_idx"])
     infos = []
@@ -154,6 +163,8 @@ def test_oracle_loop_reproduces_reference_trajectory(golden_dir, fname, env_name
     assert exp.total_numsteps == int(z["total_numsteps"]) and exp.updates == int(z["updates"])
     stride = int(z["stride"])
     for net in ("critic", "critic_target", "policy", "qrisk", "qrisk_target", "recovery"):
+        if "final_%s_0" % net not in z.files:       # no recovery policy without --MF_recovery (qrisk.py:56-75)
+            continue
         for i, p in enumerate(exp.agent.params(net)):
             assert np.allclose(p.ravel()[::stride], z["final_%s_%d" % (net, i)], rtol=0, atol=1e-5)
 
