@@ -74,3 +74,52 @@ def test_no_cpu_fallback(native):
     cpu = torch.zeros(8)
     with pytest.raises(native.RRLError):
         native.p(cpu, "f32")
+
+
+def test_peer_table_packing_and_argument_checks(native):
+    """rrl_peers_t (the peer-memory gradient sum of the sharded run): packing of the host-side table and the argument
+    validation of the entry points, which happens before anything is launched (no GPU needed)."""
+    P = native.make_peers(1, [0x1000, 0x2000, 0x3000], [0x10, 0x20, 0x30])
+    assert (P.world, P.rank) == (3, 1)
+    assert list(P.arena)[:4] == [0x1000, 0x2000, 0x3000, 0] and list(P.signal)[:4] == [0x10, 0x20, 0x30, 0]
+    assert ctypes.sizeof(P) == 8 + 8 * 8 + 8 * 8                     # int32 world, rank; uint64 arena[8], signal[8]
+    with pytest.raises(native.RRLError):
+        native.make_peers(0, list(range(9)), list(range(9)))           # one node: at most 8 ranks
+    with pytest.raises(native.RRLError):
+        native.make_peers(0, [1, 2], [1])
+    lib = native.lib()
+    assert lib.rrl_peer_barrier(None, None, None, None) < 0
+    assert b"bad argument" in lib.rrl_last_error()
+    bad = native.make_peers(0, [0x1000], [0x10])
+    bad.rank = 5                                                        # rank outside [0, world)
+    one = (ctypes.c_int64 * 1)()
+    assert lib.rrl_peer_barrier(ctypes.byref(bad), one, one, None) < 0
+    cfg = native.agent_config(max_batch=256)
+    assert lib.rrl_sac_apply_p2p(ctypes.byref(cfg), None, None, None, None) < 0
+
+
+def test_entry_points_reject_bad_arguments_before_launching(native):
+    """error behaviour of the boundary: every call returns a negative code and leaves a message in rrl_last_error()
+    instead of launching on bad input (checked here without a device)."""
+    C = ctypes
+    lib = native.lib()
+    cfg = native.agent_config(max_batch=256)
+    cases = [
+        ("rrl_sac_apply", (None, None, None, None), b"null"),
+        ("rrl_qrisk_apply", (C.byref(cfg), None, None, None), b"null"),
+        ("rrl_recovery_apply", (C.byref(cfg), None, None, None), b"null"),
+        ("rrl_agent_refresh", (None, None, None), b"null"),
+        ("rrl_hard_update", (C.byref(cfg), None, C.c_int(9), C.c_int(9), None), b"null"),
+        ("rrl_replay_flag_count", (None, C.c_int64(0), C.c_int32(512), None, None), b"null"),
+        ("rrl_dyn_train_sync", (None, None, None), b"null"),
+        ("rrl_mt19937_seed_host", (None, C.c_int(0), None), b"bad key"),
+        ("rrl_counters_advance", (None, C.c_int64(1), C.c_int64(1), C.c_int64(1), C.c_int(1), C.c_int(1), None), b"null"),
+    ]
+    for name, args, text in cases:
+        assert getattr(lib, name)(*args) < 0, name
+        assert text in lib.rrl_last_error(), (name, lib.rrl_last_error())
+    bad = native.agent_config(max_batch=256)
+    bad.max_batch = 7
+    lib.rrl_agent_arena_floats.restype = C.c_int64
+    assert lib.rrl_agent_arena_floats(C.byref(bad)) < 0 and b"max_batch" in lib.rrl_last_error()
+    assert lib.rrl_agent_num_tensors(C.c_int(99)) < 0
