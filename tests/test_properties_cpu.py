@@ -9,7 +9,7 @@ from hypothesis import given, settings, strategies as st
 from oracle import envs as oenvs
 from oracle import replay as oreplay
 
-FAST = settings(max_examples=60, deadline=None)
+FAST = settings(max_examples=60, deadline=None, derandomize=True, database=None)
 
 
 def _setsize(k):
