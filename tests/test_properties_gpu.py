@@ -12,7 +12,7 @@ from test_env_gpu import _step
 from test_properties_cpu import _setsize
 
 pytestmark = pytest.mark.gpu
-GPU = settings(max_examples=25, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+GPU = settings(max_examples=25, deadline=None, derandomize=True, database=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
 
 
 def _device_sample(native, dev, seed, n, k):
