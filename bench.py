@@ -57,6 +57,7 @@ def parse():
     ap.add_argument("--tc", type=int, default=int(os.environ.get("RRL_TENSOR_CORES", "1")))
     ap.add_argument("--peer-grads", type=int, default=int(os.environ.get("RRL_PEER_GRADS", "1")),
                     help="N>1: sum the ranks' gradients inside the optimizer-step kernel over NVLink peer memory (0: NCCL)")
+    ap.add_argument("--e2e-pipeline", type=int, default=1, help="e2e leg through submit/collect (0: serial step_host)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-steps", type=int, default=400)
     return ap.parse_args()
@@ -331,11 +332,29 @@ def run_ours(args, rank, world, local_rank):
         eh.capture()
         for i in range(W):
             eh.step_host(pool[i % 4])
+        base_ticket = 0
+        if args.e2e_pipeline:
+            eh.enable_pipeline()
+            for i in range(4):                      # warm the two slots
+                tk = eh.submit(pool[i % 4])
+                if i >= 1:
+                    eh.collect(tk - 1)
+            eh.collect(3)
+            base_ticket = 4
         barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        for i in range(K):
-            eh.step_host(pool[i % 4])
+        if args.e2e_pipeline:
+            # every step still uploads its own inputs and downloads its own results inside the timed region; the
+            # copies run on their own streams next to the neighbouring steps' compute (results arrive one step later)
+            for i in range(K):
+                tk = eh.submit(pool[i % 4])
+                if i >= 1:
+                    eh.collect(tk - 1)
+            eh.collect(K - 1 + base_ticket)
+        else:
+            for i in range(K):
+                eh.step_host(pool[i % 4])
         torch.cuda.synchronize()
         t1 = time.perf_counter()
         e2e_s = torch.tensor([t1 - t0], dtype=torch.float64, device=dev)
@@ -344,8 +363,11 @@ def run_ours(args, rank, world, local_rank):
         e2e = {"value": world * args.envs * K / float(e2e_s.item()), "unit": UNIT,
                "h2d_bytes_per_step": eh.h2d_bytes_per_step(), "d2h_bytes_per_step": eh.d2h_bytes_per_step(),
                "ms_per_step": 1e3 * float(e2e_s.item()) / K,
-               "api": "VecEngine.step_host: pinned H2D of the step's random draws, graph replay, D2H of per-env "
-                      "next_state/reward/flags/action + losses + counters, host sync every step"}
+               "api": ("VecEngine.submit/collect: pinned H2D of the step's random draws and D2H of per-env next_state/reward/"
+                       "flags/action + losses + counters on copy streams, two staging slots, results collected one step "
+                       "later (host sync every step)") if args.e2e_pipeline else
+                      ("VecEngine.step_host: pinned H2D of the step's random draws, graph replay, D2H of per-env "
+                       "next_state/reward/flags/action + losses + counters, host sync every step")}
         assert eh.read_counters()["error"] == 0
         del eh
     except Exception as ex:  # report, never fake

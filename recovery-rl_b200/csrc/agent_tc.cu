@@ -126,12 +126,15 @@ __device__ __forceinline__ float4 epilogue_quarter(TcSmem& S, int pass, int n_ou
     const float4* w1v = reinterpret_cast<const float4*>(S.sm.w3[pass][1]);
     const float4* w2v = reinterpret_cast<const float4*>(S.sm.w3[pass][2]);
     const float4* w3v = reinterpret_cast<const float4*>(S.sm.w3[pass][3]);
-#pragma unroll 1
+    // both 32-column loads of the quarter in flight before the wait
+    float v64[64];
+    tmem_ld32(taddr + q * 64, v64);
+    tmem_ld32(taddr + q * 64 + 32, v64 + 32);
+    tmem_ld_wait();
+#pragma unroll
     for (int cc = 0; cc < 2; ++cc) {
-        float v[32];
+        const float* v = v64 + cc * 32;
         const int col0 = q * 64 + cc * 32;
-        tmem_ld32(taddr + col0, v);
-        tmem_ld_wait();
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
             const int i4 = (col0 >> 2) + j4;
@@ -156,7 +159,7 @@ __device__ __forceinline__ float4 epilogue_quarter(TcSmem& S, int pass, int n_ou
     return make_float4(out[0], out[1], out[2], out[3]);
 }
 
-__global__ void __launch_bounds__(kTcThreads, 1) act_tc_kernel(const __grid_constant__ TcActArgs T) {
+__global__ void __maxnreg__(112) act_tc_kernel(const __grid_constant__ TcActArgs T) {
     // declared aligned and used WITHOUT pointer arithmetic: rounding the address up through uintptr_t makes the
     // compiler lose the shared address space and emit generic LD / ST (long-scoreboard) instead of LDS / STS
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -264,7 +267,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) act_tc_kernel(const __grid_cons
                 const int pb = n_epi & 1;
                 ++n_epi;
                 S.part[pb][q][r] = mine;
-                asm volatile("bar.sync 1, %0;" ::"n"(kProd) : "memory");
+                // only the four warps of this TMEM lane quadrant exchange (rows r of quadrant warp & 3)
+                asm volatile("bar.sync %0, 128;" ::"r"(1 + (warp & 3)) : "memory");
                 const float4 p0 = S.part[pb][0][r], p1 = S.part[pb][1][r], p2 = S.part[pb][2][r], p3 = S.part[pb][3][r];
                 raw[0] = ((p0.x + p1.x) + (p2.x + p3.x)) + S.sm.b3[pass][0];
                 raw[1] = ((p0.y + p1.y) + (p2.y + p3.y)) + S.sm.b3[pass][1];

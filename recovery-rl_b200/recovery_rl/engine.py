@@ -422,6 +422,80 @@ class VecEngine(object):
         torch.cuda.current_stream().synchronize()
         return o
 
+    # ---- pipelined host-buffer steps: copies of step k overlap the compute of its neighbours -----------------
+    def _host_outputs(self):
+        return dict(losses=self.losses, counters=self.counters, next_state=self.out_next, reward=self.out_reward,
+                    done=self.out_done, constraint=self.out_cons, success=self.out_succ, recovery=self.recovery,
+                    action=self.action_real)
+
+    def enable_pipeline(self):
+        """Two-slot staging on both sides of the step so that the H2D copy of step k+1 and the D2H copy of step k-1 run
+        on their own streams (copy engines) while step k computes.  submit(inputs) -> ticket; collect(ticket) -> the
+        pinned outputs of that step.  A ticket must be collected before the second-next submit (slot reuse)."""
+        assert self.host_inputs
+        dev = self.device
+        self._pl_keys = list(self.in_host)
+        self._pl_in_dst = [self.in_dev[k] for k in self._pl_keys]
+        self._pl_in = [[torch.empty_like(t) for t in self._pl_in_dst] for _ in range(2)]
+        self._pl_in_host = [[torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in self._pl_in_dst] for _ in range(2)]
+        outs = self._host_outputs()
+        self._pl_out_keys = list(outs)
+        self._pl_out_src = [outs[k] for k in self._pl_out_keys]
+        self._pl_out = [[torch.empty_like(t) for t in self._pl_out_src] for _ in range(2)]
+        self._pl_out_host = [{k: torch.empty(t.shape, dtype=t.dtype).pin_memory()
+                              for k, t in zip(self._pl_out_keys, self._pl_out_src)} for _ in range(2)]
+        self._s_h2d = torch.cuda.Stream(device=dev)
+        self._s_d2h = torch.cuda.Stream(device=dev)
+        mk = lambda: [torch.cuda.Event(), torch.cuda.Event()]
+        self._ev_in_ready, self._ev_in_free, self._ev_out_ready, self._ev_out_done = mk(), mk(), mk(), mk()
+        self._pl_k = 0
+
+    def submit(self, inputs):
+        k = self._pl_k
+        b = k & 1
+        main = torch.cuda.current_stream()
+        srcs = []
+        for i, key in enumerate(self._pl_keys):
+            x = inputs[key]
+            d = self._pl_in[b][i]
+            if torch.is_tensor(x) and x.is_pinned() and x.shape == d.shape and x.dtype == d.dtype:
+                srcs.append(x)                               # caller's own pinned buffer: no staging copy
+            else:
+                if k >= 2:
+                    self._ev_in_ready[b].synchronize()       # the H2D that last read this host slot has finished
+                h = self._pl_in_host[b][i]
+                h.copy_(torch.as_tensor(x).reshape(h.shape))
+                srcs.append(h)
+        with torch.cuda.stream(self._s_h2d):
+            if k >= 2:
+                self._s_h2d.wait_event(self._ev_in_free[b])  # step k-2 has consumed this device slot
+            for src, d in zip(srcs, self._pl_in[b]):
+                d.copy_(src, non_blocking=True)
+            self._ev_in_ready[b].record(self._s_h2d)
+        main.wait_event(self._ev_in_ready[b])
+        torch._foreach_copy_(self._pl_in_dst, self._pl_in[b])
+        self._ev_in_free[b].record(main)
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._enqueue_step()
+        if k >= 2:
+            main.wait_event(self._ev_out_done[b])            # step k-2's D2H has drained this device slot
+        torch._foreach_copy_(self._pl_out[b], self._pl_out_src)
+        self._ev_out_ready[b].record(main)
+        with torch.cuda.stream(self._s_d2h):
+            self._s_d2h.wait_event(self._ev_out_ready[b])
+            for key, d in zip(self._pl_out_keys, self._pl_out[b]):
+                self._pl_out_host[b][key].copy_(d, non_blocking=True)
+            self._ev_out_done[b].record(self._s_d2h)
+        self._pl_k = k + 1
+        return k
+
+    def collect(self, ticket):
+        assert self._pl_k - 2 <= ticket < self._pl_k, "ticket already overwritten or not submitted"
+        self._ev_out_done[ticket & 1].synchronize()
+        return self._pl_out_host[ticket & 1]
+
     # ---- state snapshots (capture warm-up, tests) -----------------------------------------------------
     def snapshot(self):
         """everything one vector step mutates, incl. the ring slots its pushes will overwrite (they hold live

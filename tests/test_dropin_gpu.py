@@ -73,13 +73,14 @@ def test_replay_memory_api_matches_cpython(native, cuda):
         mem.sample(301)
 
 
-def test_experiment_reproduces_reference_run(native, cuda, golden_dir, tmp_path):
+@pytest.mark.parametrize("fname,n_eps", [("traj_nav1_seed7.npz", 12), ("traj_nav2_seed3.npz", 8)])
+def test_experiment_reproduces_reference_run(native, cuda, golden_dir, tmp_path, fname, n_eps):
     """scripts/navigation1.sh-style command through the drop-in Experiment with LIVE RNGs (numpy, torch, Box,
     CPython-compatible sampler) == the reference's own run at seed 7: same episode lengths, constraint and
     recovery flags; states to fp32 round-off of the recovery actions."""
     import arg_utils
     from recovery_rl.experiment import Experiment
-    z = np.load(os.path.join(golden_dir, "traj_nav1_seed7.npz"))
+    z = np.load(os.path.join(golden_dir, fname))
     argv = [str(x) for x in z["argv"]]
     argv[argv.index("--logdir") + 1] = str(tmp_path)
     args = arg_utils.get_args(argv + ["--tensor_cores", "0"])
@@ -90,7 +91,7 @@ def test_experiment_reproduces_reference_run(native, cuda, golden_dir, tmp_path)
     assert np.array_equal(np.array([t[3] for t in off]), z["offline_next_state"])
     exp.pretrain_critic_recovery()
     infos, ep_len = [], []
-    for ep in range(1, 13):
+    for ep in range(1, n_eps + 1):
         info = exp.get_train_rollout(ep)
         infos += info
         ep_len.append(len(info))
@@ -177,3 +178,30 @@ def test_vectorised_comparison_algorithms_run(native, cuda, tmp_path, algo):
     uses_qrisk = algo in ("LR", "RSPO", "RCPO")
     assert (stats[-1]["qrisk_updates"] > 20) == uses_qrisk
     assert torch.isfinite(exp.engine.arena[:exp.engine.agent.grad_off]).all()
+
+
+@pytest.mark.parametrize("tag", ["unconstrained", "lr", "rspo", "sqrl", "rp", "rcpo"])
+def test_experiment_reproduces_reference_comparison_runs(native, cuda, golden_dir, tmp_path, tag):
+    """the comparison-algorithm lines of scripts/navigation1.sh through the drop-in Experiment with LIVE RNGs == the
+    reference's own (shortened) runs recorded by oracle/ref_harness/make_golden_runs.py."""
+    import arg_utils
+    from recovery_rl.experiment import Experiment
+    z = np.load(os.path.join(golden_dir, "runs_nav1.npz"))
+    P = tag + "_"
+    argv = [str(x) for x in z[P + "argv"]]
+    argv[argv.index("--logdir") + 1] = str(tmp_path)
+    args = arg_utils.get_args(argv + ["--tensor_cores", "0"])
+    exp = Experiment(args)
+    if not args.disable_offline_updates and (args.use_recovery or args.DGD_constraints or args.RCPO):
+        exp.pretrain_critic_recovery()
+    infos, ep_len = [], []
+    for ep in range(1, len(z[P + "ep_len"]) + 1):
+        info = exp.get_train_rollout(ep)
+        infos += info
+        ep_len.append(len(info))
+    assert ep_len == list(z[P + "ep_len"])
+    assert np.array_equal(np.array([int(i["constraint"]) for i in infos]), z[P + "constraint"])
+    assert np.allclose(np.array([i["state"] for i in infos]), z[P + "state"], rtol=0, atol=1e-4)
+    assert np.allclose(np.array([i["action"] for i in infos]), z[P + "action"], rtol=0, atol=1e-4)
+    assert exp.num_viols == int(z[P + "num_viols"]) and exp.total_numsteps == int(z[P + "total_numsteps"])
+    assert exp.updates == int(z[P + "updates"])

@@ -90,3 +90,45 @@ def test_peer_grads_match_nccl():
                           "--master-addr", "127.0.0.1", "--master-port", "29731", os.path.join(here, "p2p_check.py")],
                          capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "P2P_OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
+
+
+@pytest.mark.gpu
+def test_pipelined_host_steps_match_serial():
+    """submit/collect (copies on their own streams, two staging slots) returns exactly what step_host returns for the
+    same inputs, step by step."""
+    import numpy as np
+    import torch
+    from recovery_rl.engine import VecEngine
+    n, B = 1024, 64
+    engines = []
+    for _ in range(2):
+        torch.manual_seed(9)
+        e = VecEngine("navigation1", n, batch_size=B, replay_size=8192, safe_replay_size=8192, gamma_safe=0.8, eps_safe=0.3,
+                      seed=9, host_inputs=True, start_steps=0)
+        e.init_agent()
+        e.reset(torch.zeros(2, n, dtype=torch.float64, device=e.device))
+        engines.append(e)
+    rs = np.random.RandomState(4)
+
+    def draw():
+        return dict(reset_draws=rs.randn(2, n), env_noise=rs.randn(2, n), eps_task=rs.randn(n, 2).astype(np.float32),
+                    eps_rec=rs.randn(n, 2).astype(np.float32), rand_u=rs.rand(n, 2).astype(np.float32),
+                    sac_eps_next=rs.randn(B, 2).astype(np.float32), sac_eps_cur=rs.randn(B, 2).astype(np.float32),
+                    qr_eps_next=rs.randn(B, 2).astype(np.float32), qr_eps_rec=rs.randn(B, 2).astype(np.float32))
+    inputs = [draw() for _ in range(7)]
+    a, b = engines
+    for e in engines:
+        e.step_host(inputs[0])
+        e.capture()
+    want = [{k: v.clone() for k, v in a.step_host(x).items()} for x in inputs[1:]]
+    b.enable_pipeline()
+    got = []
+    for i, x in enumerate(inputs[1:]):
+        t = b.submit(x)
+        if i >= 1:
+            got.append({k: v.clone() for k, v in b.collect(t - 1).items()})
+    got.append({k: v.clone() for k, v in b.collect(len(inputs) - 2).items()})
+    assert len(got) == len(want)
+    for i, (g, w) in enumerate(zip(got, want)):
+        for k in w:
+            assert torch.equal(g[k], w[k]), (i, k)
