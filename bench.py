@@ -1,16 +1,24 @@
 #!/usr/bin/env python
 """bench.py -- env-steps/sec of the Recovery RL hot path (rollout + SAC update + Q_risk/recovery update per
-vector step) on Maze, N parallel env copies per GPU, one process per GPU.
+vector step), N parallel env copies per GPU, one process per GPU.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config C2|C3|C4|C5]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 One "step" = one vector step of the workload named in config.workload: for each of the N env copies one
-composite action (policy -> Q_risk threshold -> recovery policy), one env step (500 physics substeps), two
-replay pushes; plus one SAC update and one Q_risk + recovery-policy update on batches of 256 sampled with
-the CPython-compatible sampler.  `value` is timed with inputs resident in HBM (Philox noise generated on
-device, whole step replayed as one CUDA graph); `e2e` goes through the host-buffer face (per-step random
-draws uploaded from pinned host memory, per-env results + losses + counters downloaded).
+composite action (policy -> Q_risk threshold -> recovery policy), one env step, two replay pushes; plus one SAC
+update and one Q_risk + recovery-policy update on sampled batches (CPython-compatible sampler).  `value` is timed
+with inputs resident in HBM (Philox noise generated on device, whole step replayed as one CUDA graph); `e2e` goes
+through the host-buffer face (per-step random draws uploaded from pinned host memory, per-env results + losses +
+counters downloaded).  Default workload = BASELINE config C4 (Maze, 65,536 env copies per GPU, batch 256).
+`--config C2|C3|C5` run the other BASELINE configs (Navigation1 4,096 x 256; Navigation2 8,192 x 1,024; Maze
+model-based recovery 2,048 envs x 1,000 CEM particles) through the same code.
+
+N > 1 adds, in the same JSON line: `strong` (the north-star form of C4: 65,536 env copies SHARDED over the N
+GPUs, with the 1-GPU time measured on rank 0 in the same run), `replicas_identical` (bitwise checksum of the
+six networks + Adam moments of every rank after the timed region) and `peer_equals_nccl` (the peer-memory
+gradient sum against the NCCL all-reduce path over 8 steps from the same start).
+
 `--impl reference` times the CPU restatement of the reference loop (oracle/loop.py; the reference itself is
 Python + MuJoCo and cannot travel to the GPU box) on the box's host cores, N = 1 env as the reference runs.
 """
@@ -31,11 +39,24 @@ for _p in (ROOT, PKG):
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
-METRIC = "env-steps/sec (rollout+SAC+Q_risk update) on Maze"
 UNIT = "env-steps/s"
+ENV_TITLE = {"maze": "Maze", "navigation1": "Navigation1", "navigation2": "Navigation2"}
 # algorithmic work per unit (DESIGN.md "Measurement")
 ACT_FLOP_PER_ENV = 134144 + 267264          # policy + twin Q_risk forward; + 133,120 where recovery triggers
 ENV_BYTES_PER_STEP = 120                    # state/action/ep_steps read, state/flags write, two 32 B pushes + flag
+# safety-critic hyper-parameters of the shipped scripts (scripts/{navigation1,navigation2,maze}.sh)
+HYPER = {"navigation1": dict(gamma_safe=0.8, eps_safe=0.3, pos_fraction=-1.0),
+         "navigation2": dict(gamma_safe=0.65, eps_safe=0.2, pos_fraction=-1.0),
+         "maze": dict(gamma_safe=0.5, eps_safe=0.15, pos_fraction=0.3)}
+CONFIGS = {"C2": dict(env_name="navigation1", envs=4096, batch=256),
+           "C3": dict(env_name="navigation2", envs=8192, batch=1024),
+           "C4": dict(env_name="maze", envs=65536, batch=256),
+           "C5": dict(env_name="maze", envs=2048, batch=256, mb=1)}
+STRONG_ENVS_TOTAL = 65536                   # BASELINE.json configs[3]: 65,536 env copies sharded over the GPUs
+
+
+def metric_name(env_name):
+    return "env-steps/sec (rollout+SAC+Q_risk update) on %s" % ENV_TITLE.get(env_name, env_name)
 
 
 def parse():
@@ -44,9 +65,12 @@ def parse():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--envs", type=int, default=65536, help="env copies PER GPU")
-    ap.add_argument("--batch", type=int, default=256)
-    ap.add_argument("--env-name", default="maze")
+    ap.add_argument("--config", default=None, choices=sorted(CONFIGS), help="a BASELINE.json config (default C4)")
+    ap.add_argument("--envs", type=int, default=None, help="env copies PER GPU (default: the config's)")
+    ap.add_argument("--batch", type=int, default=None)
+    ap.add_argument("--env-name", default=None)
+    ap.add_argument("--mb", type=int, default=None, help="model-based recovery (PETS/CEM planner) instead of the MF recovery policy")
+    ap.add_argument("--popsize", type=int, default=50, help="--mb: CEM candidates per env (x 20 particles)")
     ap.add_argument("--pretrain", type=int, default=1000, help="Q_risk pre-training updates (untimed)")
     ap.add_argument("--demos", type=int, default=10000)
     ap.add_argument("--replay", type=int, default=1 << 23,
@@ -59,26 +83,74 @@ def parse():
                     help="N>1: sum the ranks' gradients inside the optimizer-step kernel over NVLink peer memory (0: NCCL)")
     ap.add_argument("--e2e-pipeline", type=int, default=1, help="e2e leg through submit/collect (0: serial step_host)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-steps", type=int, default=400)
-    return ap.parse_args()
+    ap.add_argument("--no-checks", action="store_true", help="N>1: skip the strong-scaling / replica / peer==NCCL blocks")
+    ap.add_argument("--cpu-steps", type=int, default=300)
+    args = ap.parse_args()
+    base = dict(CONFIGS[args.config or "C4"])
+    for k in ("env_name", "envs", "batch", "mb"):
+        if getattr(args, k) is None:
+            setattr(args, k, base.get(k, 0))
+    args.config = args.config or ("C4" if (args.env_name, args.envs, args.batch, args.mb) == ("maze", 65536, 256, 0) else "custom")
+    return args
 
 
 # ----------------------------------------------------------------------------------------------------
 class ClockSampler(object):
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    """SM clock / throttle reasons sampled DURING the timed region (B200_PROFILING.md): NVML polled from a thread
+    every ~2 ms (a 20-step timed region is only ~10 ms long); nvidia-smi -lms as the fallback."""
+    REASONS = (("hw_slowdown", "nvmlClocksEventReasonHwSlowdown"), ("hw_thermal_slowdown", "nvmlClocksEventReasonHwThermalSlowdown"),
+               ("sw_thermal_slowdown", "nvmlClocksEventReasonSwThermalSlowdown"), ("sw_power_cap", "nvmlClocksEventReasonSwPowerCap"))
 
     def __init__(self, index):
         self.index = index
-        self.lines = []
-        self.proc = None
+        self.sm, self.reasons, self.lines = [], set(), []
+        self.mx = None
+        self.proc = self.thread = self.h = self.nv = None
+        self.stop_flag = False
+        self.how = None
+
+    def _nvml_handle(self):
+        import pynvml as nv
+        nv.nvmlInit()
+        try:
+            uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+            h = nv.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+        except Exception:
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.index]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else self.index
+            h = nv.nvmlDeviceGetHandleByIndex(idx)
+        self.mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+        return nv, h
+
+    def _poll(self):
+        nv, h = self.nv, self.h
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+                for name, const in self.REASONS:
+                    if r & getattr(nv, const):
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def start(self):
+        try:
+            self.nv, self.h = self._nvml_handle()
+            self.how = "nvml, 2 ms poll"
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nv = None
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
         try:
+            self.how = "nvidia-smi -lms 10"
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "10"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
         except Exception:
@@ -89,9 +161,14 @@ class ClockSampler(object):
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.nv is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=1.0)
+            return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.mx,
+                    "reasons": sorted(self.reasons), "samples": len(self.sm), "how": self.how}
         if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
+        time.sleep(0.05)
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
         for ln in self.lines:
@@ -106,7 +183,7 @@ class ClockSampler(object):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "how": self.how}
 
 
 def load_peaks():
@@ -120,7 +197,8 @@ def load_peaks():
 
 
 def load_traffic():
-    """dram bytes per launch of the dominant kernel from the committed ncu --set full capture, if any."""
+    """dram bytes per launch of the dominant kernels from the committed `ncu --set full` captures (profiles/): ncu
+    cannot run inside a timed bench, so this is the one roofline field that is NOT measured live."""
     try:
         with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
             return json.load(f)
@@ -129,14 +207,12 @@ def load_traffic():
 
 
 # ----------------------------------------------------------------------------------------------------
-def cpu_reference_run(args, steps, pretrain=10, demos=2000, threads=None):
-    """the CPU restatement of the reference loop (N = 1 env) on the host cores: env-steps/s after warm-up."""
+def _oracle_experiment(args, demos, pretrain):
     from oracle import envs as oenvs
     from oracle.loop import OracleExperiment
-    cores = threads or os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    exp = OracleExperiment(args.env_name, seed=args.seed, batch_size=args.batch, gamma_safe=0.5, eps_safe=0.15,
-                           pos_fraction=0.3 if args.env_name == "maze" else -1.0)
+    h = HYPER[args.env_name]
+    exp = OracleExperiment(args.env_name, seed=args.seed, batch_size=args.batch, gamma_safe=h["gamma_safe"],
+                           eps_safe=h["eps_safe"], pos_fraction=h["pos_fraction"])
     np.random.seed(args.seed)
     if args.env_name == "maze":
         tr = oenvs.maze_offline_data(demos, np.random.RandomState(args.seed))
@@ -147,41 +223,59 @@ def cpu_reference_run(args, steps, pretrain=10, demos=2000, threads=None):
         exp.step()
     for _ in range(5):
         exp.step()
-    dt = exp.run_steps(steps)
-    return steps / dt, cores, dt
+    return exp
+
+
+def thread_candidates():
+    n = os.cpu_count() or 1
+    return sorted(set(t for t in (1, 4, 8, n) if t <= n))
+
+
+def cpu_reference_sweep(args, steps):
+    """the CPU restatement of the reference loop (N = 1 env) on the host cores, at 1 / 4 / 8 / all torch threads:
+    (best env-steps/s, its thread count, {threads: env-steps/s}, seconds spent).  256-wide MLPs on batch 256 do not
+    scale past a few threads, so "all threads" alone would handicap the baseline."""
+    exp = _oracle_experiment(args, 2000, 10)
+    cand = thread_candidates()
+    per = max(20, steps // len(cand))
+    by, spent = {}, 0.0
+    for t in cand:
+        torch.set_num_threads(t)
+        exp.run_steps(5)
+        dt = exp.run_steps(per)
+        by[t] = per / dt
+        spent += dt
+    best = max(by, key=by.get)
+    return by[best], best, by, per, spent
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    t_all = []
     K = max(1, args.steps)
     per_step = max(20, min(args.cpu_steps, 4000 // max(1, K + args.warmup)))
-    cores = os.cpu_count() or 1
-    from oracle import envs as oenvs
-    from oracle.loop import OracleExperiment
+    exp = _oracle_experiment(args, min(2000, args.demos), 10)
+    # thread count: the best of 1 / 4 / 8 / all on a short probe (stated in the line)
+    probe = {}
+    for t in thread_candidates():
+        torch.set_num_threads(t)
+        exp.run_steps(3)
+        probe[t] = 15 / exp.run_steps(15)
+    cores = max(probe, key=probe.get)
     torch.set_num_threads(cores)
-    exp = OracleExperiment(args.env_name, seed=args.seed, batch_size=args.batch, gamma_safe=0.5, eps_safe=0.15,
-                           pos_fraction=0.3 if args.env_name == "maze" else -1.0)
-    np.random.seed(args.seed)
-    n_demo = min(2000, args.demos)
-    tr = oenvs.maze_offline_data(n_demo, np.random.RandomState(args.seed)) if args.env_name == "maze" else \
-        oenvs.nav_offline_data(oenvs.KIND_BY_NAME[args.env_name], n_demo)
-    exp.pretrain(tr, 10)
-    while len(exp.memory) <= args.batch + 1:
-        exp.step()
     for _ in range(args.warmup):
         exp.run_steps(per_step)
-    for _ in range(K):
-        t_all.append(exp.run_steps(per_step))
+    t_all = [exp.run_steps(per_step) for _ in range(K)]
     total = sum(t_all)
     value = K * per_step / total
-    sample = "%d env-steps per bench step, N=1 env, update every step, %d torch threads" % (per_step, cores)
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": K,
+    sample = "%d env-steps per bench step, N=1 env, update every step, %d torch threads (best of %s on a 15-step probe)" % (
+        per_step, cores, {k: round(v, 1) for k, v in probe.items()})
+    line = {"impl": "reference", "metric": metric_name(args.env_name), "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": K,
             "warmup": args.warmup, "ms_per_step": 1e3 * total / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "%s Recovery RL MF, CPU restatement of the reference loop (oracle/loop.py), N=1 env, batch %d"
-                                   % (args.env_name, args.batch), "env_steps_per_bench_step": per_step},
+                                   % (args.env_name, args.batch), "env_steps_per_bench_step": per_step,
+                       "host_cores": os.cpu_count(), "torch_threads": cores},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -189,15 +283,18 @@ def run_reference(args, rank, world):
 
 
 # ----------------------------------------------------------------------------------------------------
-def build_engine(args, rank, world, pg, host_inputs, dev):
+def build_engine(args, rank, world, pg, host_inputs, dev, envs=None, peer_grads=None):
     from recovery_rl.engine import VecEngine
     torch.manual_seed(args.seed)                  # identical xavier init on every rank
     maze = args.env_name == "maze"
     cap = int(getattr(args, "replay", 1000000))
-    eng = VecEngine(args.env_name, args.envs, batch_size=args.batch, replay_size=cap, safe_replay_size=cap, gamma_safe=0.5 if maze else 0.8,
-                    eps_safe=0.15 if maze else 0.3, pos_fraction=0.3 if maze else -1.0, seed=args.seed, device=dev,
+    h = HYPER[args.env_name]
+    mb = bool(getattr(args, "mb", 0))
+    peer = bool(args.peer_grads if peer_grads is None else peer_grads)
+    eng = VecEngine(args.env_name, int(envs or args.envs), batch_size=args.batch, replay_size=cap, safe_replay_size=cap,
+                    gamma_safe=h["gamma_safe"], eps_safe=h["eps_safe"], pos_fraction=h["pos_fraction"], seed=args.seed, device=dev,
                     rank=rank, world_size=world, process_group=pg, host_inputs=host_inputs, use_tensor_cores=args.tc,
-                    peer_grads=bool(args.peer_grads))
+                    peer_grads=peer, mf_recovery=not mb, mb_recovery=mb, mpc_popsize=getattr(args, "popsize", 50) if mb else None)
     eng.init_agent()
     rng = np.random.RandomState(args.seed + 1000 * rank)
     if maze:
@@ -209,6 +306,8 @@ def build_engine(args, rank, world, pg, host_inputs, dev):
         demos = importlib.import_module("env." + args.env_name).get_offline_data(min(args.demos, 4000))
     eng.push_offline(demos)
     eng.pretrain_qrisk(args.pretrain, n_demos=len(demos))
+    if mb:
+        eng.train_mb(demos[:4000], epochs=5)      # experiment.py:298-305 (ensemble fit on the demos, untimed)
     eng.reset()
     return eng
 
@@ -217,11 +316,11 @@ def grad_mode(eng, world):
     if world == 1:
         return "none (1 GPU)"
     if eng.peer_arena is not None:
-        return "peer-memory sum inside the optimizer-step kernel (NVLink loads, 1 flag barrier per optimizer step)"
-    return "nccl, flat grad block, 3 per step" + (" (peer mode unavailable: %s)" % eng.peer_error if eng.peer_error else "")
+        return "peer-memory sum inside the optimizer-step kernel (NVLink loads, flag barriers)"
+    return "nccl, flat grad block" + (" (peer mode unavailable: %s)" % eng.peer_error if eng.peer_error else "")
 
 
-def timed_steps(eng, K, flush, world, barrier):
+def timed_steps(eng, K, flush, barrier):
     """K graph replays, each bracketed by CUDA events on the launching stream; L2 flushed between steps."""
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     barrier()
@@ -248,6 +347,112 @@ def time_kernel(fn, K, flush):
     return float(np.mean([a.elapsed_time(b) for a, b in ev]))
 
 
+def ready_engine(args, rank, world, pg, dev, W, envs=None, peer_grads=None):
+    """engine with the task ring past the batch size on every rank, step captured as a CUDA graph, W warm-up replays."""
+    eng = build_engine(args, rank, world, pg, False, dev, envs=envs, peer_grads=peer_grads)
+    for _ in range(3):
+        eng.step()
+    torch.cuda.synchronize()
+    eng.capture()
+    for _ in range(W):
+        eng.replay()
+    torch.cuda.synchronize()
+    return eng
+
+
+def max_over_ranks(x, dev, world):
+    t = torch.tensor([x], dtype=torch.float64, device=dev)
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def state_checksum(eng):
+    """two 64-bit checksums over the BITS of the six networks (+ images) and the Adam moments of this rank."""
+    a = eng.agent
+    m_off, cnt = native_scratch(a, "adam_m")
+    v_off, _ = native_scratch(a, "adam_v")
+    parts = [eng.arena[:a.grad_off], eng.arena[m_off:m_off + cnt], eng.arena[v_off:v_off + cnt]]
+    out = []
+    for p in parts:
+        bits = p.contiguous().view(torch.int32).to(torch.int64)
+        w = (torch.arange(bits.numel(), device=bits.device, dtype=torch.int64) % 65521) + 1
+        out += [bits.sum(), (bits * w).sum()]
+    return torch.stack(out)
+
+
+def native_scratch(agent, name):
+    from recovery_rl import native
+    return native.agent_scratch_info(agent.cfg, name)
+
+
+def multi_gpu_checks(args, rank, world, pg, dev, eng, K, W, flush, barrier):
+    """N > 1: replica identity, the peer-memory sum against NCCL, and C4 as BASELINE states it (65,536 envs sharded)."""
+    import torch.distributed as dist
+    out = {}
+    # (1) every rank holds bit-identical networks + Adam state after the timed region
+    cs = state_checksum(eng)
+    allcs = [torch.empty_like(cs) for _ in range(world)]
+    dist.all_gather(allcs, cs)
+    out["replicas_identical"] = bool(all(torch.equal(c, allcs[0]) for c in allcs))
+    # (2) peer-memory gradient sum vs NCCL all-reduce: 8 steps from the same start (seeded build), small shard
+    try:
+        res = []
+        for peer in (1, 0):
+            small = argparse.Namespace(**vars(args))
+            small.envs, small.replay, small.pretrain, small.demos = 4096, 1 << 18, 50, 4000
+            e = build_engine(small, rank, world, pg, False, dev, peer_grads=peer)
+            active = e.peer_arena is not None
+            for _ in range(8):
+                e.step()
+            torch.cuda.synchronize()
+            assert e.read_counters()["error"] == 0
+            res.append((e.arena[:e.agent.grad_off].clone(), active, e.read_counters()))
+            del e
+        (pa, p_active, pc), (na, _, nc) = res
+        diff = float((pa - na).abs().max().item())
+        scale = float(na.abs().max().item())
+        info = {"peer_path_active": bool(p_active), "steps": 8, "envs_per_gpu": 4096, "bit_equal": bool(torch.equal(pa, na)),
+                "max_abs_diff": diff, "max_abs_param": scale, "updates": [pc["sac_updates"], pc["qrisk_updates"]],
+                "same_counters": pc["sac_updates"] == nc["sac_updates"] and pc["num_viols"] == nc["num_viols"],
+                "note": "peer path sums in rank order; NCCL's reduction order is its own: bit-equal is guaranteed at 2 ranks only"}
+        flag = torch.tensor([1 if (info["bit_equal"] or diff <= 1e-5 * max(scale, 1.0)) else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        info["equal_within_1e-5_all_ranks"] = bool(flag.item())
+        out["peer_equals_nccl"] = info
+    except Exception as ex:
+        out["peer_equals_nccl"] = {"error": repr(ex)}
+    # (3) strong scaling: 65,536 env copies in total, sharded; the 1-GPU time of the same total measured on rank 0
+    try:
+        per = STRONG_ENVS_TOTAL // world
+        es = ready_engine(args, rank, world, pg, dev, W, envs=per)
+        t = timed_steps(es, K, flush, barrier)
+        ms = max_over_ranks(sum(t), dev, world) / K
+        assert es.read_counters()["error"] == 0
+        es.graph = None
+        del es
+        n1_ms = None
+        if rank == 0:             # the other ranks wait at the barrier below; their GPUs idle
+            e1 = ready_engine(args, 0, 1, None, dev, W, envs=STRONG_ENVS_TOTAL)
+            t1 = timed_steps(e1, K, flush, lambda: None)
+            n1_ms = sum(t1) / K
+            e1.graph = None
+            del e1
+        barrier()
+        strong = {"envs_total": STRONG_ENVS_TOTAL, "envs_per_gpu": per, "ms_per_step": ms,
+                  "value": STRONG_ENVS_TOTAL / (ms * 1e-3), "unit": UNIT}
+        if n1_ms is not None:
+            strong["n1_ms_per_step"] = n1_ms
+            strong["n1_value"] = STRONG_ENVS_TOTAL / (n1_ms * 1e-3)
+            strong["speedup_vs_n1"] = n1_ms / ms
+            strong["efficiency_vs_n1"] = n1_ms / ms / world
+        out["strong"] = strong
+    except Exception as ex:
+        out["strong"] = {"error": repr(ex)}
+    return out
+
+
 def run_ours(args, rank, world, local_rank):
     import torch.distributed as dist
     from recovery_rl import native
@@ -264,24 +469,14 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
 
     K, W = args.steps, max(3, args.warmup)
-    eng = build_engine(args, rank, world, pg, False, dev)
-    for _ in range(3):
-        eng.step()                                 # task ring > batch on every rank before capture
-    torch.cuda.synchronize()
-    eng.capture()
+    eng = ready_engine(args, rank, world, pg, dev, W)
     flush = torch.zeros(64 * 1024 * 1024, device=dev)          # 256 MiB
-    for _ in range(W):
-        eng.replay()
-    torch.cuda.synchronize()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    times = timed_steps(eng, K, flush, world, barrier)
+    times = timed_steps(eng, K, flush, barrier)
     clocks = sampler.stop() if rank == 0 else None
-    total_ms = torch.tensor([sum(times)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
-    total_ms = float(total_ms.item())
+    total_ms = max_over_ranks(sum(times), dev, world)
     c = eng.read_counters()
     assert c["error"] == 0, "device-side error %r" % (c,)
     value = world * args.envs * K / (total_ms * 1e-3)
@@ -299,17 +494,41 @@ def run_ours(args, rank, world, local_rank):
                                                  cons_ring=eng.cons_ring, cons_flags=eng.cons_flags,
                                                  cons_capacity=eng.cons_cap), 20, flush)
     eng.restore(snap)
+    # the update chain (sample + SAC + Q_risk + recovery updates), eager launches on the stream, same L2-flushed timing
+    snap = eng.snapshot()
+
+    def updates_only():
+        eng._sac_sample()
+        if eng.online_qrisk:
+            eng._qr_sample()
+        eng._sac_compute()
+        if eng.online_qrisk:
+            eng._qr_compute()
+    upd_ms = None
+    if world == 1:
+        upd_ms = time_kernel(updates_only, 20, flush)
+    eng.restore(snap)
     act_tf = ACT_FLOP_PER_ENV * args.envs / (act_ms * 1e-3) / 1e12
     env_gbs = ENV_BYTES_PER_STEP * args.envs / (env_ms * 1e-3) / 1e9
+    step_ms = total_ms / K
     roofline = {"kernel": "act_kernel" if not args.tc else "act_tc_kernel", "bound": "tensor", "achieved": act_tf,
                 "peak": peaks["tf_burst"], "unit": "TFLOP/s", "frac": act_tf / peaks["tf_burst"],
-                "traffic": traffic.get("act_kernel_dram_bytes_per_launch"), "ms_per_launch": act_ms,
-                "share_of_step": act_ms / (total_ms / K), "peak_source": peaks["src"] + ", bf16 dense burst",
+                "traffic": traffic.get("act_kernel_dram_bytes_per_launch"),
+                "traffic_source": traffic.get("source", "profiles/roofline_traffic.json (ncu --set full capture; not measured in this run)"),
+                "ms_per_launch": act_ms,
+                "share_of_step": act_ms / step_ms, "peak_source": peaks["src"] + ", bf16 dense burst",
                 "algorithmic_flop_per_launch": ACT_FLOP_PER_ENV * args.envs}
     roofline_env = {"kernel": "env_step_kernel", "bound": "hbm", "achieved": env_gbs, "peak": peaks["hbm"], "unit": "GB/s",
                     "frac": env_gbs / peaks["hbm"], "traffic": traffic.get("env_step_kernel_dram_bytes_per_launch"),
-                    "ms_per_launch": env_ms, "share_of_step": env_ms / (total_ms / K),
-                    "note": "maze: 500 dependent fp64 substeps per env -> latency-bound, not bandwidth-bound (DESIGN.md)"}
+                    "ms_per_launch": env_ms, "share_of_step": env_ms / step_ms,
+                    "note": ("maze: 500 dependent fp64 substeps per env -> fp64-pipe / latency bound, not bandwidth-bound (DESIGN.md)"
+                             if args.env_name == "maze" else "navigation: one fp64 step per env; 120 B/env-step algorithmic")}
+    breakdown = {"step_ms": step_ms, "act_ms": act_ms, "env_ms": env_ms, "updates_eager_ms": upd_ms,
+                 "note": "kernels timed alone, L2 flushed before each; the update chain as eager launches (the step replays them in a graph)"}
+
+    multi = {}
+    if world > 1 and not args.no_checks:
+        multi = multi_gpu_checks(args, rank, world, pg, dev, eng, K, W, flush, barrier)
 
     # ---- end to end through the host-buffer face (pinned H2D of the step's random draws, D2H of results) ----
     del flush
@@ -357,34 +576,37 @@ def run_ours(args, rank, world, local_rank):
                 eh.step_host(pool[i % 4])
         torch.cuda.synchronize()
         t1 = time.perf_counter()
-        e2e_s = torch.tensor([t1 - t0], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * args.envs * K / float(e2e_s.item()), "unit": UNIT,
+        e2e_s = max_over_ranks(t1 - t0, dev, world)
+        e2e = {"value": world * args.envs * K / e2e_s, "unit": UNIT,
                "h2d_bytes_per_step": eh.h2d_bytes_per_step(), "d2h_bytes_per_step": eh.d2h_bytes_per_step(),
-               "ms_per_step": 1e3 * float(e2e_s.item()) / K,
+               "ms_per_step": 1e3 * e2e_s / K,
                "api": ("VecEngine.submit/collect: pinned H2D of the step's random draws and D2H of per-env next_state/reward/"
                        "flags/action + losses + counters on copy streams, two staging slots, results collected one step "
                        "later (host sync every step)") if args.e2e_pipeline else
                       ("VecEngine.step_host: pinned H2D of the step's random draws, graph replay, D2H of per-env "
                        "next_state/reward/flags/action + losses + counters, host sync every step")}
         assert eh.read_counters()["error"] == 0
+        eh.graph = None
         del eh
     except Exception as ex:  # report, never fake
         e2e = {"value": None, "unit": UNIT, "error": repr(ex)}
 
     cpu_baseline = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, cores, dt = cpu_reference_run(args, args.cpu_steps)
-        cpu_baseline = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                        "sample": "%d env-steps of the CPU restatement of the reference loop (oracle/loop.py), N=1 env, "
-                                  "SAC+Q_risk update every step, batch %d, %.1f s" % (args.cpu_steps, args.batch, dt)}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and not args.mb:
+        v, cores, by, per, dt = cpu_reference_sweep(args, args.cpu_steps)
+        cpu_baseline = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "host_cores": os.cpu_count(),
+                        "by_threads": {str(k): x for k, x in by.items()},
+                        "sample": "%d env-steps per thread setting of the CPU restatement of the reference loop (oracle/loop.py), "
+                                  "N=1 env, SAC+Q_risk update every step, batch %d, %.1f s in all; value = the best setting"
+                                  % (per, args.batch, dt)}
     if rank == 0:
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-                "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        recov = "model-based recovery (PETS/CEM, %d particles per env)" % (args.popsize * 20) if args.mb else "MF recovery"
+        line = {"metric": metric_name(args.env_name), "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32 (agent) / f64 (env)", "data": "synthetic",
-                "config": {"workload": "%s Recovery RL MF (SAC + Q_risk + MF recovery), %d env copies per GPU, batch %d, "
-                                       "one SAC + one Q_risk/recovery update per vector step" % (args.env_name, args.envs, args.batch),
+                "config": {"workload": "%s Recovery RL (SAC + Q_risk + %s), %d env copies per GPU, batch %d, "
+                                       "one SAC + one Q_risk/recovery update per vector step" % (args.env_name, recov, args.envs, args.batch),
+                           "baseline_config": args.config,
                            "envs_per_gpu": args.envs, "envs_total": world * args.envs, "batch": args.batch,
                            "replay_capacity": eng.task_cap, "pretrain_updates": args.pretrain,
                            "l2": "flushed between timed steps (256 MiB write, outside the per-step event pairs)",
@@ -392,10 +614,11 @@ def run_ours(args, rank, world, local_rank):
                            "rng": "Philox4x32-10 on device (value); host draws uploaded (e2e)",
                            "cuda_graph": eng.graph is not None, "tensor_cores": bool(args.tc),
                            "grad_allreduce": grad_mode(eng, world)},
-                "roofline": roofline, "roofline_env": roofline_env, "cpu_baseline": cpu_baseline, "e2e": e2e,
+                "roofline": roofline, "roofline_env": roofline_env, "breakdown": breakdown, "cpu_baseline": cpu_baseline, "e2e": e2e,
                 "gpu_launches": eng.launches_per_step * K, "launches_per_step": eng.launches_per_step, "clocks": clocks,
                 "counters": {k: c[k] for k in ("total_numsteps", "episodes", "num_viols", "num_successes", "sac_updates",
                                                "qrisk_updates")}}
+        line.update(multi)
         print(json.dumps(line))
         sys.stdout.flush()
     if world > 1:

@@ -296,6 +296,8 @@ int rrl_policy_sample(const rrl_agent_config_t* cfg, const float* arena, int net
 
 /* utils.soft_update / hard_update (utils.py:46-54) on whole nets. */
 int rrl_hard_update(const rrl_agent_config_t* cfg, float* arena, int dst_net, int src_net, void* stream);
+/* recovery_rl/utils.py:46-49 soft_update(target, source, tau): target = target*(1-tau) + source*tau (+ operand images). */
+int rrl_soft_update(const rrl_agent_config_t* cfg, float* arena, int dst_net, int src_net, float tau, void* stream);
 
 /* ------------------------------------------------------------------ model-based recovery (PETS / CEM) ---- */
 /* BASELINE config 5.  The planner of recovery_rl/MPC.py:322-467 + recovery_rl/optimizers.py:73-124 over the

@@ -1153,6 +1153,19 @@ extern "C" int rrl_hard_update(const rrl_agent_config_t* cfg, float* arena, int 
     return launch_polyak(L, arena, nullptr, dst_net, src_net, 1.0f, -1, -1, 1, (cudaStream_t)stream);
 }
 
+// utils.py:46-49 as a stand-alone call (the update kernels fuse it into their optimizer step; this is the reference's
+// `soft_update(target, source, tau)` helper for callers that use it directly)
+extern "C" int rrl_soft_update(const rrl_agent_config_t* cfg, float* arena, int dst_net, int src_net, float tau, void* stream) {
+    CHECK_CFG(cfg);
+    RRL_CHECK_ARG(arena, "null arena");
+    RRL_CHECK_ARG((dst_net == RRL_NET_CRITIC_TARGET && src_net == RRL_NET_CRITIC) ||
+                      (dst_net == RRL_NET_QRISK_TARGET && src_net == RRL_NET_QRISK),
+                  "soft_update: dst must be the target of src");
+    RRL_CHECK_ARG(tau >= 0.f && tau <= 1.f, "soft_update: tau must be in [0, 1]");
+    const Layout L = make_layout(cfg);
+    return launch_polyak(L, arena, nullptr, dst_net, src_net, tau, -1, -1, 1, (cudaStream_t)stream);
+}
+
 extern "C" int rrl_agent_act(const rrl_agent_config_t* cfg, float* arena, int64_t n, const double* state,
                              const float* eps_task, const float* eps_rec, const float* rand_u, int use_recovery,
                              int eval, int64_t start_steps, uint64_t seed, int32_t stream_id, const int64_t* counters,

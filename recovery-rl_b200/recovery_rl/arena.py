@@ -124,6 +124,9 @@ class AgentArena(object):
     def hard_update(self, dst, src):
         native.hard_update(self.cfg, self.arena, NETS.index(dst), NETS.index(src))
 
+    def soft_update(self, dst, src, tau):
+        native.soft_update(self.cfg, self.arena, NETS.index(dst), NETS.index(src), tau)
+
     # ---- batches (tests / N = 1 drop-in path; the vector engine samples on the device) ------------
     def set_batch(self, which, s, a, r, s2, m):
         """which: 'sac' | 'qr'.  Copies a host batch into the update scratch and sets the row counter."""

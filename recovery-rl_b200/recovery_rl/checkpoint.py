@@ -10,6 +10,8 @@ A checkpoint is one torch.save'd dict:
   counters  the int64 device counter block (step / episode / violation counts, ring positions, Adam steps)
   engine    (VecEngine only) env state, both replay rings (valid prefix) + flags, the CPython-compatible sampler
             state -- Philox draws are keyed by the vector-step counter, so a resumed run continues bit-identically.
+            Sharded runs (world > 1) write ONE FILE PER RANK (`shard_path`): env copies, replay shards and the sampler
+            stream (seeded seed + rank) are per-rank state; loading a shard written by another rank / world raises.
 """
 import collections
 
@@ -85,6 +87,19 @@ def load_agent_state(arena, state, load_counters=True):
     arena.refresh()                                   # k-major / fp16 operand images of the loaded weights
 
 
+def shard_path(path, rank, world):
+    """file of rank `rank` of a `world`-rank run: the path itself for one GPU, else <path>.rank<r>of<w>."""
+    return path if int(world) <= 1 else "%s.rank%dof%d" % (path, int(rank), int(world))
+
+
+def check_shard(e, rank, world):
+    """the engine dict `e` of a checkpoint must have been written by this rank of an equally sized run."""
+    r, w = int(e.get("rank", 0)), int(e.get("world", 1))
+    if (r, w) != (int(rank), int(world)):
+        raise ValueError("checkpoint shard was written by rank %d of %d, this process is rank %d of %d "
+                         "(env copies, replay shards and the sampler stream are per-rank state)" % (r, w, rank, world))
+
+
 def engine_state(eng):
     """recovery_rl.engine.VecEngine -> checkpoint dict."""
     st = agent_state(eng.agent)
@@ -92,6 +107,7 @@ def engine_state(eng):
     tl, cl = int(c[native.C_TASK_LEN]), int(c[native.C_CONS_LEN])
     st["engine"] = {
         "env_name": eng.env_name, "num_envs": eng.n, "task_cap": eng.task_cap, "cons_cap": eng.cons_cap,
+        "rank": int(eng.rank), "world": int(eng.world),
         "state": eng.state.cpu().clone(), "ep_steps": eng.ep_steps.cpu().clone(), "ep_return": eng.ep_return.cpu().clone(),
         "task_ring": eng.task_ring[:tl].cpu().clone(), "cons_ring": eng.cons_ring[:cl].cpu().clone(),
         "cons_flags": eng.cons_flags[:cl].cpu().clone(), "mt_state": eng.mt_state.cpu().clone(),
@@ -107,6 +123,7 @@ def load_engine_state(eng, state):
             or int(e["cons_cap"]) != eng.cons_cap:
         raise ValueError("checkpoint is for %s x %d envs (rings %d / %d)" % (e["env_name"], e["num_envs"], e["task_cap"],
                                                                            e["cons_cap"]))
+    check_shard(e, eng.rank, eng.world)
     load_agent_state(eng.agent, state, load_counters=True)
     dev = eng.device
     eng.state.copy_(e["state"].to(dev)); eng.ep_steps.copy_(e["ep_steps"].to(dev)); eng.ep_return.copy_(e["ep_return"].to(dev))
@@ -124,6 +141,7 @@ def save(path, obj):
     from .arena import AgentArena
     if hasattr(obj, "task_ring"):
         st = engine_state(obj)
+        path = shard_path(path, obj.rank, obj.world)
     else:
         st = agent_state(obj if isinstance(obj, AgentArena) else obj.arena)
     torch.save(st, path)
@@ -132,6 +150,8 @@ def save(path, obj):
 
 def load(path, obj):
     from .arena import AgentArena
+    if hasattr(obj, "task_ring"):
+        path = shard_path(path, obj.rank, obj.world)
     st = torch.load(path, map_location="cpu", weights_only=False)
     if hasattr(obj, "task_ring"):
         load_engine_state(obj, st)

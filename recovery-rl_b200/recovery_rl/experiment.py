@@ -32,10 +32,13 @@ def torchify(x):
 class Experiment:
     def __init__(self, exp_cfg):
         self.exp_cfg = exp_cfg
+        # one process per GPU: ranks > 0 log into their own directory (same naming, "_rank<r>" appended) so that ranks
+        # started in the same second never write the same args.pkl / run_stats.pkl
+        rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+        suffix = self.exp_cfg.logdir_suffix + ("_rank%d" % rank if world > 1 and rank > 0 else "")
         self.logdir = os.path.join(
             self.exp_cfg.logdir, '{}_SAC_{}_{}_{}'.format(datetime.datetime.now().strftime("%Y-%m-%d_%H-%M-%S"),
-                                                          self.exp_cfg.env_name, self.exp_cfg.policy,
-                                                          self.exp_cfg.logdir_suffix))
+                                                          self.exp_cfg.env_name, self.exp_cfg.policy, suffix))
         if not os.path.exists(self.logdir):
             os.makedirs(self.logdir)
         print("LOGDIR: ", self.logdir)
@@ -341,6 +344,12 @@ class Experiment:
         if getattr(c, "resume", ""):
             eng.load(c.resume)             # env state, replay, sampler and counters continue where the checkpoint stopped
         eng.capture()
+        ck_dir = self.logdir
+        if eng.world > 1:                  # all shards of a checkpoint live next to each other, in rank 0's logdir
+            import torch.distributed as dist
+            box = [self.logdir]
+            dist.broadcast_object_list(box, src=0, group=eng.pg)
+            ck_dir = box[0]
         k = min(max(int(getattr(c, "log_envs", 1)), 0), eng.n)
         train_rollouts, open_eps, vec_stats = [], [[] for _ in range(k)], []
         step = 0
@@ -367,7 +376,9 @@ class Experiment:
             if step % report_every == 0:
                 cn = eng.read_counters()
                 if cn["error"]:
-                    raise RuntimeError("device-side sampler error %d (sample larger than population)" % cn["error"])
+                    raise RuntimeError("device-side error %d: %s" % (cn["error"], {
+                        1: "sampler: sample larger than population (too few positives / negatives for one stratified batch)",
+                        2: "a peer GPU did not reach the gradient barrier within 60 s (peer lost or stalled)"}.get(cn["error"], "unknown")))
                 self.total_numsteps = cn["total_numsteps"]
                 self.num_viols, self.num_successes = cn["num_viols"], cn["num_successes"]
                 self.viol_and_recovery, self.viol_and_no_recovery = cn["viol_and_recovery"], cn["viol_and_no_recovery"]
@@ -385,8 +396,9 @@ class Experiment:
                     with open(osp.join(self.logdir, "run_stats.pkl"), "wb") as f:
                         pickle.dump(data, f)
                 ck = int(getattr(c, "checkpoint_every", 0))
-                if ck and (step // report_every) % ck == 0 and eng.rank == 0:
-                    eng.save(osp.join(self.logdir, "checkpoint.pt"))
+                if ck and (step // report_every) % ck == 0:
+                    # every rank writes its own shard (checkpoint.pt.rank<r>of<w>) into rank 0's naming scheme
+                    eng.save(osp.join(ck_dir, "checkpoint.pt"))
                 if cn["total_numsteps"] * eng.world > c.num_steps or cn["episodes"] * eng.world > c.num_eps:
                     break
         return vec_stats

@@ -336,6 +336,11 @@ def hard_update(cfg, arena, dst_net, src_net, stream=None):
            "rrl_hard_update")
 
 
+def soft_update(cfg, arena, dst_net, src_net, tau, stream=None):
+    _check(lib().rrl_soft_update(C.byref(cfg), p(arena, "f32"), int(dst_net), int(src_net), C.c_float(float(tau)),
+                                 _stream(stream)), "rrl_soft_update")
+
+
 # ------------------------------------------------------------------------------------------------
 # model-based recovery (PETS / CEM planner, csrc/mpc.cu)
 # ------------------------------------------------------------------------------------------------

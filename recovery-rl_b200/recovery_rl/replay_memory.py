@@ -97,18 +97,28 @@ class ReplayMemory(object):
             raise ValueError("Sample larger than population or is negative")
         o = self._outputs(batch_size)
         self._sample_device(batch_size, o, pos_fraction, idx=o[5])
-        if int(self.counters[native.C_ERROR].item()):
-            raise ValueError("Sample larger than population or is negative")
+        self._raise_on_sampler_error()
         self.last_idx = o[5][:batch_size].cpu().numpy()
         return tuple(x[:batch_size].cpu().numpy() for x in o[:5])
 
     def sample_into(self, arena, which, batch_size, pos_fraction=None):
         """device-to-device: the batch lands in the agent's update scratch, the row count in its counters."""
         names = {"sac": ("sac_s", "sac_a", "sac_r", "sac_s2", "sac_m"), "qr": ("qr_s", "qr_a", "qr_c", "qr_s2", "qr_m")}[which]
+        if batch_size > self._len:                           # random.sample raises (replay_memory.py:28,57-66)
+            raise ValueError("Sample larger than population or is negative")
         outs = [arena.scratch(n) for n in names]
         rc = native.C_SAC_ROWS if which == "sac" else native.C_QRISK_ROWS
         self._sample_device(batch_size, outs, pos_fraction, rows_counter=rc)
+        if self.is_constraint and pos_fraction is not None:
+            # too few positives / negatives for the stratified draw: the kernel flags it (rows = 0 would silently skip
+            # the update); the reference's random.sample raises here
+            self._raise_on_sampler_error()
         arena.counters[rc:rc + 1].copy_(self.counters[rc:rc + 1])
+
+    def _raise_on_sampler_error(self):
+        if int(self.counters[native.C_ERROR].item()):
+            self.counters[native.C_ERROR] = 0                # sticky on the device; the exception carries it from here
+            raise ValueError("Sample larger than population or is negative")
 
     def __len__(self):
         return self._len

@@ -32,6 +32,9 @@ class NetHandle(object):
     def hard_update_from(self, source):
         self.arena.hard_update(self.name, source.name)
 
+    def soft_update_from(self, source, tau):
+        self.arena.soft_update(self.name, source.name, tau)
+
 
 class SAC(object):
     def __init__(self, observation_space, action_space, args, logdir, im_shape=None, tmp_env=None):

@@ -84,3 +84,18 @@ def test_grad_block_is_contiguous_and_ordered():
     assert pos == off + cnt == off + 404008
     sizes = {k: v[1] for k, v in r.items()}
     assert sizes == {"critic": 134664, "policy": 67592, "qrisk": 134672, "recovery": 67080}
+
+
+def test_checkpoint_shards_are_per_rank():
+    """sharded runs write one checkpoint file per rank and refuse a shard written by another rank / world size
+    (env copies, replay shards and the seed+rank sampler stream are per-rank state)."""
+    import pytest
+    from recovery_rl import checkpoint
+    assert checkpoint.shard_path("/x/checkpoint.pt", 0, 1) == "/x/checkpoint.pt"
+    assert checkpoint.shard_path("/x/checkpoint.pt", 3, 8) == "/x/checkpoint.pt.rank3of8"
+    assert len({checkpoint.shard_path("c.pt", r, 4) for r in range(4)}) == 4
+    checkpoint.check_shard({"rank": 1, "world": 2}, 1, 2)
+    checkpoint.check_shard({}, 0, 1)                       # files written before shards existed: one GPU
+    for e, r, w in (({"rank": 0, "world": 2}, 1, 2), ({"rank": 0, "world": 1}, 0, 2), ({}, 1, 2)):
+        with pytest.raises(ValueError):
+            checkpoint.check_shard(e, r, w)
