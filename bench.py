@@ -78,7 +78,8 @@ def parse():
                          "turn that over in 15 vector steps, and once the agent has become safe the constraint ring holds "
                          "fewer violations than one stratified batch needs (random.sample would raise).")
     ap.add_argument("--seed", type=int, default=1)
-    ap.add_argument("--tc", type=int, default=int(os.environ.get("RRL_TENSOR_CORES", "1")))
+    ap.add_argument("--tc", type=int, default=int(os.environ.get("RRL_TENSOR_CORES", "2")),
+                    help="0: fp32 SIMT kernels, 1: tcgen05 kernels, 2: tcgen05 + update stages fused into the producing kernels")
     ap.add_argument("--peer-grads", type=int, default=int(os.environ.get("RRL_PEER_GRADS", "1")),
                     help="N>1: sum the ranks' gradients inside the optimizer-step kernel over NVLink peer memory (0: NCCL)")
     ap.add_argument("--e2e-pipeline", type=int, default=1, help="e2e leg through submit/collect (0: serial step_host)")

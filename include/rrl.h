@@ -61,6 +61,7 @@ enum {
     RRL_C_ADAM_T_NU      = 24, /*   log_nu (sac.py:259-261),                                                */
     RRL_C_ADAM_T_LAMBDA  = 25, /*   log_lambda_RCPO (sac.py:268-270)                                        */
     RRL_C_TICKET         = 26, /* scratch: CTA arrival ticket of the fused optimizer-step kernel (always 0 between launches) */
+    RRL_C_TICKET2        = 27, /* scratch: CTA arrival ticket of the update kernels whose last CTA runs the loss / sample-backward stage */
     RRL_NUM_COUNTERS     = 32
 };
 
@@ -164,7 +165,9 @@ typedef struct {
     int32_t target_update_interval;        /* arg_utils.py:39-43                            */
     int32_t mf_recovery;                   /* qrisk.py:150                                  */
     float grad_scale;                      /* 1/world_size applied inside Adam              */
-    int32_t use_tensor_cores;              /* act kernel: 0 = fp32 FFMA, 1 = tcgen05 fp16 hi/lo split (3 MMAs) */
+    int32_t use_tensor_cores;              /* 0 = fp32 FFMA kernels, 1 = tcgen05 fp16 hi/lo split (3 MMAs) for the acting kernel and the update
+                                              GEMMs, 2 = 1 + the per-row update stages (losses, sample backward) fused into the
+                                              producing kernels as last-CTA tails */
     /* comparison-algorithm branches of SAC.update_parameters (sac.py:52-72, 95-101, 116-117) */
     int32_t algo_flags;                    /* RRL_ALGO_* bits                               */
     float target_entropy;                  /* -dim(A) (sac.py:97-98)                         */

@@ -335,7 +335,10 @@ __global__ void __launch_bounds__(kThreads) gemm_stream_kernel(const __grid_cons
     }
 }
 
-// (3) layer-1 backward: gW1, gb1 (first H/32 blocks of x) and d(action input) (remaining blocks of x)
+// (3) layer-1 backward: gW1, gb1 (first H/32 blocks of x) and d(action input) (remaining blocks of x).
+//     Every warp keeps kL1Unroll independent row loads in flight (the batch is L2-resident: the kernel is a latency
+//     chain, not a bandwidth problem).  Optional tail (update_tails.cuh): the policy-sample backward that consumes the
+//     d(action) rows of all passes, run by the last CTA.
 struct L1BwdPass {
     const float *dh1, *xs, *xa, *W1;
     int n_in;
@@ -345,328 +348,120 @@ struct L1BwdPass {
 struct L1BwdArgs {
     L1BwdPass p[6];
     const int64_t* rows_ptr;
+    TailArgs tail;
 };
 
 constexpr int kL1ColBlocks = H / 32;  // blockIdx.x <  kL1ColBlocks : weight grads of 32 hidden units
 constexpr int kL1RowBlocks = 8;       // blockIdx.x >= kL1ColBlocks : d(action) for a slice of the rows
+constexpr int kL1Unroll = 8;
 
 __global__ void __launch_bounds__(kThreads) layer1_backward_kernel(const __grid_constant__ L1BwdArgs A) {
     const int64_t rows = *A.rows_ptr;
-    if (rows <= 0) return;
     const L1BwdPass& P = A.p[blockIdx.y];
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    if (blockIdx.x < kL1ColBlocks) {
-        if (!P.gW1) return;
-        __shared__ float red[5][8][32];
-        const int j = blockIdx.x * 32 + lane;
-        float g[4] = {0.f, 0.f, 0.f, 0.f}, gb = 0.f;
-        for (int64_t r = warp; r < rows; r += 8) {
-            const float d = P.dh1[r * H + j];
-            const float2 s = reinterpret_cast<const float2*>(P.xs)[r];
-            g[0] = fmaf(d, s.x, g[0]);
-            g[1] = fmaf(d, s.y, g[1]);
-            if (P.n_in == 4) {
-                const float2 a = reinterpret_cast<const float2*>(P.xa)[r];
-                g[2] = fmaf(d, a.x, g[2]);
-                g[3] = fmaf(d, a.y, g[3]);
+    __shared__ float red[5][8][32];
+    if (rows > 0 && blockIdx.x < kL1ColBlocks) {
+        if (P.gW1) {   // uniform per block
+            const int j = blockIdx.x * 32 + lane;
+            const bool four = P.n_in == 4;
+            float g[4] = {0.f, 0.f, 0.f, 0.f}, gb = 0.f;
+            for (int64_t r0 = warp; r0 < rows; r0 += 8 * kL1Unroll) {
+                float d[kL1Unroll];
+                float2 sv[kL1Unroll], av[kL1Unroll];
+#pragma unroll
+                for (int u = 0; u < kL1Unroll; ++u) {
+                    const int64_t r = r0 + 8 * u;
+                    const bool ok = r < rows;
+                    d[u] = ok ? __ldcg(P.dh1 + r * H + j) : 0.f;
+                    sv[u] = ok ? reinterpret_cast<const float2*>(P.xs)[r] : make_float2(0.f, 0.f);
+                    av[u] = (ok && four) ? reinterpret_cast<const float2*>(P.xa)[r] : make_float2(0.f, 0.f);
+                }
+#pragma unroll
+                for (int u = 0; u < kL1Unroll; ++u) {
+                    g[0] = fmaf(d[u], sv[u].x, g[0]);
+                    g[1] = fmaf(d[u], sv[u].y, g[1]);
+                    g[2] = fmaf(d[u], av[u].x, g[2]);
+                    g[3] = fmaf(d[u], av[u].y, g[3]);
+                    gb += d[u];
+                }
             }
-            gb += d;
-        }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) red[i][warp][lane] = g[i];
-        red[4][warp][lane] = gb;
-        __syncthreads();
-        if (warp == 0) {
-            float sum[5];
+            for (int i = 0; i < 4; ++i) red[i][warp][lane] = g[i];
+            red[4][warp][lane] = gb;
+            __syncthreads();
+            if (warp == 0) {
+                float sum[5];
 #pragma unroll
-            for (int q = 0; q < 5; ++q) {
-                float v = 0.f;
+                for (int q = 0; q < 5; ++q) {
+                    float v = 0.f;
 #pragma unroll
-                for (int y = 0; y < 8; ++y) v += red[q][y][lane];
-                sum[q] = v;
+                    for (int y = 0; y < 8; ++y) v += red[q][y][lane];
+                    sum[q] = v;
+                }
+                for (int i = 0; i < P.n_in; ++i) P.gW1[j * P.n_in + i] = sum[i];
+                P.gb1[j] = sum[4];
             }
-            for (int i = 0; i < P.n_in; ++i) P.gW1[j * P.n_in + i] = sum[i];
-            P.gb1[j] = sum[4];
         }
-    } else {
-        if (!P.dxa) return;
+    } else if (rows > 0 && P.dxa) {
         float w2[8], w3[8];
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
             w2[q] = P.W1[(lane + 32 * q) * 4 + 2];
             w3[q] = P.W1[(lane + 32 * q) * 4 + 3];
         }
-        for (int64_t r = (int64_t)(blockIdx.x - kL1ColBlocks) * 8 + warp; r < rows; r += 8 * kL1RowBlocks) {
-            float a0 = 0.f, a1 = 0.f;
+        constexpr int RU = 4;   // rows in flight per warp (8 coalesced 128-byte loads each)
+        for (int64_t r0 = (int64_t)(blockIdx.x - kL1ColBlocks) * 8 + warp; r0 < rows; r0 += 8 * kL1RowBlocks * RU) {
+            float d[RU][8];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const float d = P.dh1[r * H + lane + 32 * q];
-                a0 = fmaf(d, w2[q], a0);
-                a1 = fmaf(d, w3[q], a1);
+            for (int u = 0; u < RU; ++u) {
+                const int64_t r = r0 + (int64_t)u * 8 * kL1RowBlocks;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) d[u][q] = r < rows ? __ldcg(P.dh1 + r * H + lane + 32 * q) : 0.f;
             }
 #pragma unroll
-            for (int s = 16; s > 0; s >>= 1) {
-                a0 += __shfl_xor_sync(0xffffffffu, a0, s);
-                a1 += __shfl_xor_sync(0xffffffffu, a1, s);
+            for (int u = 0; u < RU; ++u) {
+                const int64_t r = r0 + (int64_t)u * 8 * kL1RowBlocks;
+                float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    a0 = fmaf(d[u][q], w2[q], a0);
+                    a1 = fmaf(d[u][q], w3[q], a1);
+                }
+#pragma unroll
+                for (int s = 16; s > 0; s >>= 1) {
+                    a0 += __shfl_xor_sync(0xffffffffu, a0, s);
+                    a1 += __shfl_xor_sync(0xffffffffu, a1, s);
+                }
+                if (lane == 0 && r < rows) reinterpret_cast<float2*>(P.dxa)[r] = make_float2(a0, a1);
             }
-            if (lane == 0) reinterpret_cast<float2*>(P.dxa)[r] = make_float2(a0, a1);
         }
     }
+    run_tail(A.tail);
 }
 
-// deterministic block sum of one float per thread (256 threads); result valid on thread 0
-__device__ float block_sum(float v, float* red /*[8]*/) {
-#pragma unroll
-    for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
-    __syncthreads();
-    float r = 0.f;
-    if (threadIdx.x == 0)
-        for (int w = 0; w < 8; ++w) r += red[w];
-    return r;
-}
-
-// (4) SAC losses (sac.py:192-231): TD target, critic MSE, policy loss, and the output gradients; plus the
-//     comparison branches: RCPO target penalty (:202-205), DGD policy penalty (:224-228) and the gradients of the
-//     three scalar multipliers log_alpha (:241-243), log_nu (:257-258), log_lambda (:266-267)
-struct SacLossArgs {
-    const float *r, *m, *next_logp, *qt1, *qt2, *qf1, *qf2, *logp, *qp1, *qp2;
-    const float *sq1, *sq2;  // Q_risk(s, pi)  (DGD / update_nu) or NULL
-    const float *qs1, *qs2;  // Q_risk(s, a)   (RCPO) or NULL
-    float *target, *dqf1, *dqf2, *dqp1, *dqp2, *minq, *dsq1, *dsq2, *losses;
-    float* scal;             // scalar block (RRL_S_* / RRL_D_*)
-    float gamma, eps_safe, target_entropy;
-    int flags;
-    const int64_t* rows_ptr;
-};
-__device__ double block_sum_d(double v, double* red /*[8]*/) {
-#pragma unroll
-    for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
-    __syncthreads();
-    double r = 0.0;
-    if (threadIdx.x == 0)
-        for (int w = 0; w < 8; ++w) r += red[w];
-    return r;
-}
+// (4)-(8) the per-row stages as kernels of their own (SIMT path and the unfused tcgen05 path; the fused path runs the
+//     same bodies as tails of the producing kernels, update_tails.cuh)
 __global__ void __launch_bounds__(kThreads) sac_loss_kernel(const __grid_constant__ SacLossArgs A) {
-    const int64_t rows = *A.rows_ptr;
-    if (rows <= 0) return;
-    __shared__ float red[8];
-    __shared__ double redd[8];
-    const float inv = 1.0f / (float)rows;
-    const float alpha = A.scal[RRL_S_ALPHA];
-    const float nu = A.scal[RRL_S_NU_ARG];
-    double* sd = reinterpret_cast<double*>(A.scal + RRL_S_F64_BASE);
-    const float lambda = (float)sd[RRL_D_LAMBDA];  // 0-dim float64 tensor times a float32 tensor: computed in float32
-    const bool dgd = (A.flags & RRL_ALGO_DGD) != 0, rcpo = (A.flags & RRL_ALGO_RCPO) != 0;
-    float l1 = 0.f, l2 = 0.f, lp = 0.f, la = 0.f;
-    double gnu = 0.0, glam = 0.0;
-    for (int64_t i = threadIdx.x; i < rows; i += kThreads) {
-        const float minq_next = fminf(A.qt1[i], A.qt2[i]) - alpha * A.next_logp[i];
-        float y = A.r[i] + A.m[i] * A.gamma * minq_next;
-        if (rcpo) {
-            const float qsafe = fmaxf(A.qs1[i], A.qs2[i]);
-            y -= lambda * qsafe;
-            glam += (double)(A.eps_safe - qsafe);
-        }
-        A.target[i] = y;
-        const float e1 = A.qf1[i] - y, e2 = A.qf2[i] - y;
-        l1 = fmaf(e1, e1, l1);
-        l2 = fmaf(e2, e2, l2);
-        A.dqf1[i] = 2.0f * e1 * inv;
-        A.dqf2[i] = 2.0f * e2 * inv;
-        const float p1 = A.qp1[i], p2 = A.qp2[i];
-        const float mq = fminf(p1, p2);
-        A.minq[i] = mq;
-        const float lg = A.logp[i];
-        float row = alpha * lg;
-        if (A.sq1) {
-            const float s1 = A.sq1[i], s2 = A.sq2[i];
-            const float ms = fmaxf(s1, s2);
-            gnu += (double)(A.eps_safe - ms);
-            if (dgd) {
-                row += nu * (ms - A.eps_safe);
-                // d(nu*max)/d(raw): torch.max routes to the larger input (ties split evenly), through the sigmoid
-                const float g1 = s1 > s2 ? nu * inv : (s1 == s2 ? 0.5f * nu * inv : 0.f);
-                const float g2 = s2 > s1 ? nu * inv : (s1 == s2 ? 0.5f * nu * inv : 0.f);
-                A.dsq1[i] = g1 * s1 * (1.0f - s1);
-                A.dsq2[i] = g2 * s2 * (1.0f - s2);
-            }
-        }
-        lp += row - mq;
-        la += lg + A.target_entropy;
-        // d(-min)/dq: torch.min(a, b) routes the gradient to the smaller input (ties split evenly)
-        A.dqp1[i] = p1 < p2 ? -inv : (p1 == p2 ? -0.5f * inv : 0.f);
-        A.dqp2[i] = p2 < p1 ? -inv : (p1 == p2 ? -0.5f * inv : 0.f);
-    }
-    const float s1 = block_sum(l1, red);
-    const float s2 = block_sum(l2, red);
-    const float s3 = block_sum(lp, red);
-    const float s4 = block_sum(la, red);
-    const double d1 = block_sum_d(gnu, redd);
-    const double d2 = block_sum_d(glam, redd);
-    if (threadIdx.x == 0) {
-        A.losses[0] = s1 * inv;
-        A.losses[1] = s2 * inv;
-        A.losses[2] = s3 * inv;
-        A.losses[4] = alpha;
-        float alpha_loss = 0.f;
-        if (A.flags & RRL_ALGO_AUTO_ALPHA) {  // alpha_loss = -(log_alpha * (log_pi + target_entropy)).mean()
-            const float mean_t = s4 * inv;
-            alpha_loss = -(A.scal[RRL_S_LOG_ALPHA] * mean_t);
-            A.scal[RRL_S_G_LOG_ALPHA] = -mean_t;
-        }
-        A.losses[3] = alpha_loss;
-        A.scal[RRL_S_ALPHA_LOSS] = alpha_loss;
-        if (A.flags & RRL_ALGO_UPDATE_NU) sd[RRL_D_G_LOG_NU] = d1 / (double)rows;
-        if (rcpo) sd[RRL_D_G_LOG_LAMBDA] = d2 / (double)rows;
-    }
+    __shared__ float red[32];
+    __shared__ double redd[32];
+    sac_loss_body(A, red, redd);
 }
-
-// (5) GaussianPolicy.sample backward: d raw(mean, log_std) from dL/da (through the critic) and alpha*logp
-struct GaussBwdArgs {
-    const float *raw, *eps, *dxa1, *dxa2, *dxa3, *dxa4;  // dxa3/4: through Q_risk(s, pi) (DGD) or NULL
-    float* draw;
-    const float* scal;
-    ActionSpace sp;
-    const int64_t* rows_ptr;
-};
 __global__ void __launch_bounds__(kThreads) gauss_backward_kernel(const __grid_constant__ GaussBwdArgs A) {
     const int64_t rows = *A.rows_ptr;
     const int64_t i = blockIdx.x * (int64_t)kThreads + threadIdx.x;
-    if (i >= rows) return;
-    const float inv = 1.0f / (float)rows;
-    const float4 rv = reinterpret_cast<const float4*>(A.raw)[i];
-    const float raw[4] = {rv.x, rv.y, rv.z, rv.w};
-    const float2 e = reinterpret_cast<const float2*>(A.eps)[i];
-    const float2 d1 = reinterpret_cast<const float2*>(A.dxa1)[i], d2 = reinterpret_cast<const float2*>(A.dxa2)[i];
-    float da[2] = {d1.x + d2.x, d1.y + d2.y};
-    if (A.dxa3) {
-        const float2 d3 = reinterpret_cast<const float2*>(A.dxa3)[i], d4 = reinterpret_cast<const float2*>(A.dxa4)[i];
-        da[0] += d3.x + d4.x;
-        da[1] += d3.y + d4.y;
-    }
-    const float alpha = A.scal[RRL_S_ALPHA];
-    const float ev[2] = {e.x, e.y};
-    float out[4];
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-        const float lsr = raw[2 + k];
-        const float ls = fminf(fmaxf(lsr, LOG_SIG_MIN), LOG_SIG_MAX);
-        const float sd = expf(ls);
-        const float x = fmaf(sd, ev[k], raw[k]);
-        const float y = tanhf(x);
-        const float om = 1.0f - y * y;
-        const float den = A.sp.scale[k] * om + 1e-6f;
-        // dL/dy = dL/da * scale + (alpha/B) * d(-log(scale*(1-y^2)+1e-6))/dy
-        const float dy = da[k] * A.sp.scale[k] + alpha * inv * (2.0f * A.sp.scale[k] * y) / den;
-        const float dx = dy * om;
-        out[k] = dx;                                               // d mean
-        const float dls = dx * sd * ev[k] - alpha * inv;           // through x and through -log(std)
-        out[2 + k] = (lsr >= LOG_SIG_MIN && lsr <= LOG_SIG_MAX) ? dls : 0.f;  // clamp backward
-    }
-    reinterpret_cast<float4*>(A.draw)[i] = make_float4(out[0], out[1], out[2], out[3]);
+    if (i < rows) gauss_backward_row(A, i, rows);
 }
-
-// (6) Q_risk losses (qrisk.py:118-148): target = c + m*gamma_safe*max(q1', q2'); MSE through the sigmoid
-struct QrLossArgs {
-    const float *c, *m, *qt1, *qt2, *q1, *q2;
-    float *target, *dq1, *dq2, *losses;
-    float gamma_safe;
-    const int64_t* rows_ptr;
-};
 __global__ void __launch_bounds__(kThreads) qrisk_loss_kernel(const __grid_constant__ QrLossArgs A) {
-    const int64_t rows = *A.rows_ptr;
-    if (rows <= 0) return;
-    __shared__ float red[8];
-    const float inv = 1.0f / (float)rows;
-    float l1 = 0.f, l2 = 0.f;
-    for (int64_t i = threadIdx.x; i < rows; i += kThreads) {
-        const float y = A.c[i] + A.m[i] * A.gamma_safe * fmaxf(A.qt1[i], A.qt2[i]);
-        A.target[i] = y;
-        const float q1 = A.q1[i], q2 = A.q2[i];
-        const float e1 = q1 - y, e2 = q2 - y;
-        l1 = fmaf(e1, e1, l1);
-        l2 = fmaf(e2, e2, l2);
-        A.dq1[i] = 2.0f * e1 * inv * q1 * (1.0f - q1);  // d/d(raw) through sigmoid
-        A.dq2[i] = 2.0f * e2 * inv * q2 * (1.0f - q2);
-    }
-    const float s1 = block_sum(l1, red);
-    const float s2 = block_sum(l2, red);
-    if (threadIdx.x == 0) {
-        A.losses[0] = s1 * inv;
-        A.losses[1] = s2 * inv;
-    }
+    __shared__ float red[32];
+    qrisk_loss_body(A, red);
 }
-
-// (7) recovery-policy loss (qrisk.py:150-155): mean max(Q1, Q2)(s, pi_rec(s))
-struct RecLossArgs {
-    const float *q1, *q2;
-    float *dq1, *dq2, *losses;
-    const int64_t* rows_ptr;
-};
 __global__ void __launch_bounds__(kThreads) recovery_loss_kernel(const __grid_constant__ RecLossArgs A) {
-    const int64_t rows = *A.rows_ptr;
-    if (rows <= 0) return;
-    __shared__ float red[8];
-    const float inv = 1.0f / (float)rows;
-    float l = 0.f;
-    for (int64_t i = threadIdx.x; i < rows; i += kThreads) {
-        const float q1 = A.q1[i], q2 = A.q2[i];
-        l += fmaxf(q1, q2);
-        const float g1 = q1 > q2 ? inv : (q1 == q2 ? 0.5f * inv : 0.f);
-        const float g2 = q2 > q1 ? inv : (q1 == q2 ? 0.5f * inv : 0.f);
-        A.dq1[i] = g1 * q1 * (1.0f - q1);
-        A.dq2[i] = g2 * q2 * (1.0f - q2);
-    }
-    const float s = block_sum(l, red);
-    if (threadIdx.x == 0) A.losses[2] = s * inv;
+    __shared__ float red[32];
+    recovery_loss_body(A, red);
 }
-
-// (8) StochasticPolicy.sample backward (single CTA): d raw mean, d log_std
-struct StochBwdArgs {
-    const float *raw, *eps, *dxa1, *dxa2, *dxa3, *dxa4, *log_std;  // dxa3/4 optional; g_log_std NULL: Deterministic policy
-    float *draw, *g_log_std;
-    ActionSpace sp;
-    const int64_t* rows_ptr;
-};
 __global__ void __launch_bounds__(kThreads) stoch_backward_kernel(const __grid_constant__ StochBwdArgs A) {
-    const int64_t rows = *A.rows_ptr;
-    if (rows <= 0) return;
-    __shared__ float red[8];
-    float gl[2] = {0.f, 0.f};
-    float sd[2], pass[2];
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-        const float ls = A.log_std[k];
-        sd[k] = expf(fmaxf(ls, MIN_LOG_STD));
-        pass[k] = ls >= MIN_LOG_STD ? 1.f : 0.f;
-    }
-    for (int64_t i = threadIdx.x; i < rows; i += kThreads) {
-        const float4 rv = reinterpret_cast<const float4*>(A.raw)[i];
-        const float2 e = reinterpret_cast<const float2*>(A.eps)[i];
-        const float2 d1 = reinterpret_cast<const float2*>(A.dxa1)[i], d2 = reinterpret_cast<const float2*>(A.dxa2)[i];
-        float da0 = d1.x + d2.x, da1 = d1.y + d2.y;
-        if (A.dxa3) {
-            const float2 d3 = reinterpret_cast<const float2*>(A.dxa3)[i], d4 = reinterpret_cast<const float2*>(A.dxa4)[i];
-            da0 += d3.x + d4.x;
-            da1 += d3.y + d4.y;
-        }
-        const float t0 = tanhf(rv.x), t1 = tanhf(rv.y);
-        reinterpret_cast<float4*>(A.draw)[i] =
-            make_float4(da0 * A.sp.scale[0] * (1.0f - t0 * t0), da1 * A.sp.scale[1] * (1.0f - t1 * t1), 0.f, 0.f);
-        gl[0] = fmaf(da0 * sd[0], e.x, gl[0]);
-        gl[1] = fmaf(da1 * sd[1], e.y, gl[1]);
-    }
-    const float s0 = block_sum(gl[0], red);
-    const float s1 = block_sum(gl[1], red);
-    if (threadIdx.x == 0 && A.g_log_std) {
-        A.g_log_std[0] = s0 * pass[0];
-        A.g_log_std[1] = s1 * pass[1];
-    }
+    __shared__ float red[32];
+    stoch_backward_body(A, red);
 }
 
 // (9) optimizer step, fused: Adam (torch.optim.Adam defaults: sac.py:84,114; qrisk.py:58,75) over a flat range,
@@ -1264,6 +1059,7 @@ extern "C" int rrl_sac_backward(const rrl_agent_config_t* cfg, float* arena, con
     const bool dgd = (flags & RRL_ALGO_DGD) != 0;
     const bool sq_pi = dgd || (flags & RRL_ALGO_UPDATE_NU);  // sac.py:221-222 is dead code otherwise
     RRL_CHECK_ARG(!det || (eps_next && eps_cur), "the Deterministic policy needs its noise as an input");
+    const bool fuse = cfg->use_tensor_cores >= 2;   // per-row stages run as tails of the producing kernels
     int pol_head = HEAD_GAUSS;
     const HeadW pw = task_policy_w(L, arena, cfg, &pol_head);
     const HeadG pg = head_g(L, arena, RRL_NET_POLICY, 0);
@@ -1304,21 +1100,21 @@ extern "C" int rrl_sac_backward(const rrl_agent_config_t* cfg, float* arena, con
             A.p[n++] = q_pass(L, arena, RRL_NET_QRISK, 1, s, a, -1, RA(RA_QS2));
         }
         A.n_pass = n;
+        SacLossArgs& T = A.tail.sac;   // TD target + losses + output gradients: tail of this launch (fused) or its own launch
+        T.r = r; T.m = m; T.next_logp = RA(RA_NEXT_LOGP); T.qt1 = RA(RA_QT1); T.qt2 = RA(RA_QT2);
+        T.qf1 = RA(RA_QF1); T.qf2 = RA(RA_QF2); T.logp = RA(RA_LOGP); T.qp1 = RA(RA_QP1); T.qp2 = RA(RA_QP2);
+        if (sq_pi) { T.sq1 = RA(RA_SQ1); T.sq2 = RA(RA_SQ2); T.dsq1 = RA(RA_DSQ1); T.dsq2 = RA(RA_DSQ2); }
+        if (rcpo) { T.qs1 = RA(RA_QS1); T.qs2 = RA(RA_QS2); }
+        T.target = RA(RA_TARGET); T.dqf1 = RA(RA_DQF1); T.dqf2 = RA(RA_DQF2); T.dqp1 = RA(RA_DQP1); T.dqp2 = RA(RA_DQP2);
+        T.minq = RA(RA_MINQ); T.losses = losses; T.scal = scal; T.gamma = cfg->gamma; T.eps_safe = cfg->eps_safe;
+        T.target_entropy = cfg->target_entropy; T.flags = flags; T.rows_ptr = rows_ptr;
+        if (fuse) { A.tail.kind = TAIL_SAC_LOSS; A.tail.ticket = counters + RRL_C_TICKET2; }
         int rc = launch_forward<32>(A, R, st);
         if (rc) return rc;
-    }
-    {
-        SacLossArgs A;
-        memset(&A, 0, sizeof(A));
-        A.r = r; A.m = m; A.next_logp = RA(RA_NEXT_LOGP); A.qt1 = RA(RA_QT1); A.qt2 = RA(RA_QT2);
-        A.qf1 = RA(RA_QF1); A.qf2 = RA(RA_QF2); A.logp = RA(RA_LOGP); A.qp1 = RA(RA_QP1); A.qp2 = RA(RA_QP2);
-        if (sq_pi) { A.sq1 = RA(RA_SQ1); A.sq2 = RA(RA_SQ2); A.dsq1 = RA(RA_DSQ1); A.dsq2 = RA(RA_DSQ2); }
-        if (rcpo) { A.qs1 = RA(RA_QS1); A.qs2 = RA(RA_QS2); }
-        A.target = RA(RA_TARGET); A.dqf1 = RA(RA_DQF1); A.dqf2 = RA(RA_DQF2); A.dqp1 = RA(RA_DQP1); A.dqp2 = RA(RA_DQP2);
-        A.minq = RA(RA_MINQ); A.losses = losses; A.scal = scal; A.gamma = cfg->gamma; A.eps_safe = cfg->eps_safe;
-        A.target_entropy = cfg->target_entropy; A.flags = flags; A.rows_ptr = rows_ptr;
-        sac_loss_kernel<<<1, kThreads, 0, st>>>(A);
-        RRL_CHECK_LAUNCH();
+        if (!fuse) {
+            sac_loss_kernel<<<1, kThreads, 0, st>>>(T);
+            RRL_CHECK_LAUNCH();
+        }
     }
     const HeadW c1 = head_w(L, arena, RRL_NET_CRITIC, 0), c2 = head_w(L, arena, RRL_NET_CRITIC, 1);
     const HeadG g1 = head_g(L, arena, RRL_NET_CRITIC, 0), g2 = head_g(L, arena, RRL_NET_CRITIC, 1);
@@ -1361,25 +1157,28 @@ extern "C" int rrl_sac_backward(const rrl_agent_config_t* cfg, float* arena, con
             if (q < 2) { p.gW1 = g.W1; p.gb1 = g.b1; }
             else p.dxa = dxa[q];
         }
+        // policy-sample backward (needs d(action) of every pass): tail of this launch (fused) or its own launch
+        if (!det) {
+            GaussBwdArgs& T = A.tail.gauss;
+            T.raw = R4(R4_RAW_POL); T.eps = R2(R2_EPS_CUR); T.dxa1 = R2(R2_DPI); T.dxa2 = R2(R2_DPI_B);
+            if (dgd) { T.dxa3 = R2(R2_DPI_S1); T.dxa4 = R2(R2_DPI_S2); }
+            T.draw = R4(R4_DRAW_POL); T.scal = scal; T.sp = sp; T.rows_ptr = rows_ptr;
+            if (fuse) A.tail.kind = TAIL_GAUSS_BWD;
+        } else {  // DeterministicPolicy: a = tanh(raw)*scale + bias + noise
+            StochBwdArgs& T = A.tail.stoch;
+            T.raw = R4(R4_RAW_POL); T.eps = R2(R2_EPS_CUR); T.dxa1 = R2(R2_DPI); T.dxa2 = R2(R2_DPI_B);
+            if (dgd) { T.dxa3 = R2(R2_DPI_S1); T.dxa4 = R2(R2_DPI_S2); }
+            T.log_std = pw.log_std; T.draw = R4(R4_DRAW_POL); T.g_log_std = nullptr; T.sp = sp; T.rows_ptr = rows_ptr;
+            if (fuse) A.tail.kind = TAIL_STOCH_BWD;
+        }
+        A.tail.ticket = counters + RRL_C_TICKET2;
         layer1_backward_kernel<<<dim3(kL1ColBlocks + kL1RowBlocks, nq), kThreads, 0, st>>>(A);
         RRL_CHECK_LAUNCH();
-    }
-    if (!det) {
-        GaussBwdArgs A;
-        memset(&A, 0, sizeof(A));
-        A.raw = R4(R4_RAW_POL); A.eps = R2(R2_EPS_CUR); A.dxa1 = R2(R2_DPI); A.dxa2 = R2(R2_DPI_B);
-        if (dgd) { A.dxa3 = R2(R2_DPI_S1); A.dxa4 = R2(R2_DPI_S2); }
-        A.draw = R4(R4_DRAW_POL); A.scal = scal; A.sp = sp; A.rows_ptr = rows_ptr;
-        gauss_backward_kernel<<<(unsigned)((R + kThreads - 1) / kThreads), kThreads, 0, st>>>(A);
-        RRL_CHECK_LAUNCH();
-    } else {  // DeterministicPolicy: a = tanh(raw)*scale + bias + noise
-        StochBwdArgs A;
-        memset(&A, 0, sizeof(A));
-        A.raw = R4(R4_RAW_POL); A.eps = R2(R2_EPS_CUR); A.dxa1 = R2(R2_DPI); A.dxa2 = R2(R2_DPI_B);
-        if (dgd) { A.dxa3 = R2(R2_DPI_S1); A.dxa4 = R2(R2_DPI_S2); }
-        A.log_std = pw.log_std; A.draw = R4(R4_DRAW_POL); A.g_log_std = nullptr; A.sp = sp; A.rows_ptr = rows_ptr;
-        stoch_backward_kernel<<<1, kThreads, 0, st>>>(A);
-        RRL_CHECK_LAUNCH();
+        if (!fuse) {
+            if (!det) gauss_backward_kernel<<<(unsigned)((R + kThreads - 1) / kThreads), kThreads, 0, st>>>(A.tail.gauss);
+            else stoch_backward_kernel<<<1, kThreads, 0, st>>>(A.tail.stoch);
+            RRL_CHECK_LAUNCH();
+        }
     }
     {  // policy: head backward + dh1 + gW2 / gW3 / gb3 / gb2
         GemmArgs G;
@@ -1457,6 +1256,7 @@ extern "C" int rrl_qrisk_backward(const rrl_agent_config_t* cfg, float* arena, c
     auto R2 = [&](int id) { return arena + L.rows2_f[id]; };
     if (!losses) losses = arena + L.losses + 8;
     const ActionSpace sp = action_space(cfg);
+    const bool fuse = cfg->use_tensor_cores >= 2;
     {  // a' ~ TASK policy(s')  (qrisk.py:118-120; policy = agent.policy, experiment.py:413)
         FwdArgs A;
         memset(&A, 0, sizeof(A));
@@ -1478,16 +1278,17 @@ extern "C" int rrl_qrisk_backward(const rrl_agent_config_t* cfg, float* arena, c
         A.p[1] = q_pass(L, arena, RRL_NET_QRISK_TARGET, 1, s2, R2(R2_QR_NEXT_A), -1, RA(RA_QR_QT2));
         A.p[2] = q_pass(L, arena, RRL_NET_QRISK, 0, s, a, 0, RA(RA_QR_Q1));
         A.p[3] = q_pass(L, arena, RRL_NET_QRISK, 1, s, a, 1, RA(RA_QR_Q2));
+        QrLossArgs& T = A.tail.qr;
+        T.c = c; T.m = m; T.qt1 = RA(RA_QR_QT1); T.qt2 = RA(RA_QR_QT2); T.q1 = RA(RA_QR_Q1); T.q2 = RA(RA_QR_Q2);
+        T.target = RA(RA_QR_TARGET); T.dq1 = RA(RA_QR_DQ1); T.dq2 = RA(RA_QR_DQ2); T.losses = losses;
+        T.gamma_safe = cfg->gamma_safe; T.rows_ptr = rows_ptr;
+        if (fuse) { A.tail.kind = TAIL_QR_LOSS; A.tail.ticket = counters + RRL_C_TICKET2; }
         int rc = launch_forward<32>(A, R, st);
         if (rc) return rc;
-    }
-    {
-        QrLossArgs A;
-        A.c = c; A.m = m; A.qt1 = RA(RA_QR_QT1); A.qt2 = RA(RA_QR_QT2); A.q1 = RA(RA_QR_Q1); A.q2 = RA(RA_QR_Q2);
-        A.target = RA(RA_QR_TARGET); A.dq1 = RA(RA_QR_DQ1); A.dq2 = RA(RA_QR_DQ2); A.losses = losses;
-        A.gamma_safe = cfg->gamma_safe; A.rows_ptr = rows_ptr;
-        qrisk_loss_kernel<<<1, kThreads, 0, st>>>(A);
-        RRL_CHECK_LAUNCH();
+        if (!fuse) {
+            qrisk_loss_kernel<<<1, kThreads, 0, st>>>(T);
+            RRL_CHECK_LAUNCH();
+        }
     }
     const HeadW c1 = head_w(L, arena, RRL_NET_QRISK, 0), c2 = head_w(L, arena, RRL_NET_QRISK, 1);
     const HeadG g1 = head_g(L, arena, RRL_NET_QRISK, 0), g2 = head_g(L, arena, RRL_NET_QRISK, 1);
@@ -1560,6 +1361,7 @@ extern "C" int rrl_recovery_backward(const rrl_agent_config_t* cfg, float* arena
     auto R4 = [&](int id) { return arena + L.rows4_f[id]; };
     if (!losses) losses = arena + L.losses + 8;
     const ActionSpace sp = action_space(cfg);
+    const bool fuse = cfg->use_tensor_cores >= 2;
     if (!cfg->mf_recovery) return 0;
     {
         FwdArgs A;
@@ -1580,17 +1382,20 @@ extern "C" int rrl_recovery_backward(const rrl_agent_config_t* cfg, float* arena
         A.n_pass = 2; A.rows_ptr = rows_ptr; A.sp = sp; A.use_tc = cfg->use_tensor_cores;
         A.p[0] = q_pass(L, arena, RRL_NET_QRISK, 0, s, R2(R2_REC_PI), 2, RA(RA_REC_Q1));
         A.p[1] = q_pass(L, arena, RRL_NET_QRISK, 1, s, R2(R2_REC_PI), 3, RA(RA_REC_Q2));
+        RecLossArgs& T = A.tail.rec;
+        T.q1 = RA(RA_REC_Q1); T.q2 = RA(RA_REC_Q2); T.dq1 = RA(RA_REC_DQ1); T.dq2 = RA(RA_REC_DQ2); T.losses = losses;
+        T.rows_ptr = rows_ptr;
+        if (fuse) { A.tail.kind = TAIL_REC_LOSS; A.tail.ticket = counters + RRL_C_TICKET2; }
         int rc = launch_forward<32>(A, R, st);
         if (rc) return rc;
-    }
-    {
-        RecLossArgs A;
-        A.q1 = RA(RA_REC_Q1); A.q2 = RA(RA_REC_Q2); A.dq1 = RA(RA_REC_DQ1); A.dq2 = RA(RA_REC_DQ2); A.losses = losses;
-        A.rows_ptr = rows_ptr;
-        recovery_loss_kernel<<<1, kThreads, 0, st>>>(A);
-        RRL_CHECK_LAUNCH();
+        if (!fuse) {
+            recovery_loss_kernel<<<1, kThreads, 0, st>>>(T);
+            RRL_CHECK_LAUNCH();
+        }
     }
     const HeadW c1 = head_w(L, arena, RRL_NET_QRISK, 0), c2 = head_w(L, arena, RRL_NET_QRISK, 1);
+    const HeadW pw = head_w(L, arena, RRL_NET_RECOVERY, 0);
+    const HeadG pg = head_g(L, arena, RRL_NET_RECOVERY, 0);
     {  // back through the (post-step) safety critic into the action: head backward + dh1
         GemmArgs G;
         memset(&G, 0, sizeof(G));
@@ -1612,17 +1417,17 @@ extern "C" int rrl_recovery_backward(const rrl_agent_config_t* cfg, float* arena
             p.dh1 = arena + L.dh1[2 + q]; p.xs = s; p.xa = R2(R2_REC_PI); p.W1 = (q ? c2 : c1).W1; p.n_in = 4;
             p.dxa = q ? R2(R2_DPI) : R2(R2_REC_DPI);
         }
+        StochBwdArgs& T = A.tail.stoch;   // StochasticPolicy.sample backward: tail of this launch (fused) or its own launch
+        T.raw = R4(R4_RAW_REC); T.eps = R2(R2_REC_EPS); T.dxa1 = R2(R2_REC_DPI); T.dxa2 = R2(R2_DPI);
+        T.log_std = pw.log_std; T.draw = R4(R4_DRAW_REC); T.g_log_std = pg.log_std; T.sp = sp; T.rows_ptr = rows_ptr;
+        A.tail.ticket = counters + RRL_C_TICKET2;
+        if (fuse) A.tail.kind = TAIL_STOCH_BWD;
         layer1_backward_kernel<<<dim3(kL1ColBlocks + kL1RowBlocks, 2), kThreads, 0, st>>>(A);
         RRL_CHECK_LAUNCH();
-    }
-    const HeadW pw = head_w(L, arena, RRL_NET_RECOVERY, 0);
-    const HeadG pg = head_g(L, arena, RRL_NET_RECOVERY, 0);
-    {
-        StochBwdArgs A;
-        A.raw = R4(R4_RAW_REC); A.eps = R2(R2_REC_EPS); A.dxa1 = R2(R2_REC_DPI); A.dxa2 = R2(R2_DPI);
-        A.log_std = pw.log_std; A.draw = R4(R4_DRAW_REC); A.g_log_std = pg.log_std; A.sp = sp; A.rows_ptr = rows_ptr;
-        stoch_backward_kernel<<<1, kThreads, 0, st>>>(A);
-        RRL_CHECK_LAUNCH();
+        if (!fuse) {
+            stoch_backward_kernel<<<1, kThreads, 0, st>>>(T);
+            RRL_CHECK_LAUNCH();
+        }
     }
     {  // recovery policy: head backward + dh1 + gW2 / gW3 / gb3 / gb2
         GemmArgs G;

@@ -2,23 +2,15 @@
 // weight views into the arena, the head post-processing of the four network families, acting arguments.
 #pragma once
 #include "agent_layout.cuh"
+#include "update_tails.cuh"
 #include <cuda_fp16.h>
 
 namespace rrl {
 
 enum Head { HEAD_Q = 0, HEAD_QRISK = 1, HEAD_GAUSS = 2, HEAD_STOCH = 3, HEAD_DET = 4 };
 
-#define LOG_SIG_MAX 2.0f
-#define LOG_SIG_MIN (-20.0f)
-#define MIN_LOG_STD (-13.815510557964274f) /* np.log(1e-6), model.py:499 */
-#define HALF_LOG_2PI 0.9189385332046727f   /* math.log(math.sqrt(2*math.pi)) */
 
 static __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
-
-
-struct ActionSpace {
-    float scale[2], bias[2];
-};
 
 // ---------------------------------------------------------------------------------------------
 // weights of one single-head MLP (pointers into the arena)
@@ -171,6 +163,7 @@ struct FwdArgs {
     const int64_t* counters;
     int step_counter;  // which counter supplies the Philox step
     int use_tc;        // run the 256x256 contraction on tcgen05 (agent_tc.cu) instead of the fp32 SIMT tile
+    TailArgs tail;     // stage run by the last CTA of the launch (update_tails.cuh); kind 0: none
 };
 
 // head-specific tail of one row: raw[0..3] = W3 h2 + b3 -> Q value / sigmoid / sampled action + log-prob

@@ -28,11 +28,22 @@ using namespace rrl::tc;
 namespace {
 
 #ifdef RRL_TC_TIMING
-__device__ unsigned long long g_tc_time[64][8];
+// profiling build (-DRRL_TC_TIMING): per-launch, per-CTA stage time stamps of the update kernels (globaltimer, ns)
+//   g_tc_log[launch % 256][cta % 16][0..7]: 0 start, 1 setup done, 2 producers done, 3 accumulator ready, 4 epilogue
+//   done, 5 TMEM released, 6 tail done;  g_tc_kind[launch % 256]: 1 fwd, 2 bwd (+ grid dims)
+__device__ unsigned long long g_tc_log[256][16][8];
+__device__ unsigned int g_tc_launch;
+__device__ int g_tc_kind[256][4];
 __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
-#define TSTAMP(i) do { if ((threadIdx.x & 127) == 0 && threadIdx.x < 512) g_tc_time[(blockIdx.y * 4 + blockIdx.x) & 63][i] = gtime(); } while (0)
+#define TSTAMP(i) do { if (threadIdx.x == 0) g_tc_log[*(volatile unsigned int*)&g_tc_launch & 255][(blockIdx.y * gridDim.x + blockIdx.x) & 15][i] = gtime(); } while (0)
+#define TLAUNCH_END(kind) do { __syncthreads(); if (threadIdx.x == 0) { const unsigned l = *(volatile unsigned int*)&g_tc_launch & 255; \
+        if (blockIdx.x == 0 && blockIdx.y == 0) { g_tc_kind[l][0] = kind; g_tc_kind[l][1] = gridDim.x; g_tc_kind[l][2] = gridDim.y; } \
+        __threadfence(); const unsigned done = atomicAdd(&g_tc_done, 1u); \
+        if (done == gridDim.x * gridDim.y - 1) { g_tc_done = 0; __threadfence(); atomicAdd(&g_tc_launch, 1u); } } } while (0)
+__device__ unsigned int g_tc_done;
 #else
 #define TSTAMP(i)
+#define TLAUNCH_END(kind)
 #endif
 
 enum { PASS_POL = 0, PASS_REC = 1, PASS_QR1 = 2, PASS_QR2 = 3 };
@@ -126,15 +137,12 @@ __device__ __forceinline__ float4 epilogue_quarter(TcSmem& S, int pass, int n_ou
     const float4* w1v = reinterpret_cast<const float4*>(S.sm.w3[pass][1]);
     const float4* w2v = reinterpret_cast<const float4*>(S.sm.w3[pass][2]);
     const float4* w3v = reinterpret_cast<const float4*>(S.sm.w3[pass][3]);
-    // both 32-column loads of the quarter in flight before the wait
-    float v64[64];
-    tmem_ld32(taddr + q * 64, v64);
-    tmem_ld32(taddr + q * 64 + 32, v64 + 32);
-    tmem_ld_wait();
-#pragma unroll
+#pragma unroll 1
     for (int cc = 0; cc < 2; ++cc) {
-        const float* v = v64 + cc * 32;
+        float v[32];
         const int col0 = q * 64 + cc * 32;
+        tmem_ld32(taddr + col0, v);
+        tmem_ld_wait();
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
             const int i4 = (col0 >> 2) + j4;
@@ -159,7 +167,7 @@ __device__ __forceinline__ float4 epilogue_quarter(TcSmem& S, int pass, int n_ou
     return make_float4(out[0], out[1], out[2], out[3]);
 }
 
-__global__ void __maxnreg__(112) act_tc_kernel(const __grid_constant__ TcActArgs T) {
+__global__ void __launch_bounds__(kTcThreads, 1) act_tc_kernel(const __grid_constant__ TcActArgs T) {
     // declared aligned and used WITHOUT pointer arithmetic: rounding the address up through uintptr_t makes the
     // compiler lose the shared address space and emit generic LD / ST (long-scoreboard) instead of LDS / STS
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -417,7 +425,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
     FwdTcSmem& S = *reinterpret_cast<FwdTcSmem*>(smem_raw);
     const int64_t rows = A.rows_ptr ? *A.rows_ptr : A.rows_const;
     const int64_t row0 = (int64_t)blockIdx.x * TM;
-    if (row0 >= rows) return;                       // uniform: before any barrier / TMEM allocation
+    TSTAMP(0);
+    if (row0 >= rows) {                             // uniform: before any barrier / TMEM allocation
+        run_tail(A.tail);
+        TLAUNCH_END(1);
+        return;
+    }
     const FwdPass& P = A.p[blockIdx.y];
     const HeadW& w = P.w;
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
@@ -462,6 +475,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = S.tmem_base;
+    TSTAMP(1);
 
     if (warp < kProd / 32) {
         const int q = warp >> 2, r = (warp & 3) * 32 + lane;
@@ -511,7 +525,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
             mbar_arrive_warp(smem_u32(&S.full[stage]));
         }
         // ---- epilogue: columns [64 q, 64 q + 64) of this row ----
+        TSTAMP(2);
         mbar_wait(smem_u32(&S.acc_full), 0);
+        TSTAMP(3);
         tc_fence_after();
         float out[4] = {0.f, 0.f, 0.f, 0.f};
         const int n_out = w.na + w.nb;
@@ -599,6 +615,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
     __syncthreads();
     if (warp == kProd / 32) tmem_dealloc(tmem_base, 256);
     TSTAMP(5);
+    run_tail(A.tail);
+    TSTAMP(6);
+    TLAUNCH_END(1);
 }
 
 
@@ -941,6 +960,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const __grid_cons
     __syncthreads();
     if (warp == kProd / 32) tmem_dealloc(tmem_base, 256);
     TSTAMP(5);
+    TLAUNCH_END(2);
 }
 
 }  // namespace
@@ -963,8 +983,14 @@ int fwd_tc_launch(const FwdArgs& A, int64_t max_rows, cudaStream_t st) {
 }
 
 #ifdef RRL_TC_TIMING
-extern "C" int rrl_debug_tc_times(unsigned long long* out) {
-    return (int)cudaMemcpyFromSymbol(out, g_tc_time, sizeof(unsigned long long) * 64 * 8);
+// out_log: 256*16*8 uint64, out_kind: 256*4 int32, returns the number of launches logged so far (negative: CUDA error)
+extern "C" int rrl_debug_tc_times(unsigned long long* out_log, int* out_kind) {
+    unsigned int n = 0;
+    if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+    if (cudaMemcpyFromSymbol(out_log, g_tc_log, sizeof(unsigned long long) * 256 * 16 * 8) != cudaSuccess) return -1;
+    if (cudaMemcpyFromSymbol(out_kind, g_tc_kind, sizeof(int) * 256 * 4) != cudaSuccess) return -1;
+    if (cudaMemcpyFromSymbol(&n, g_tc_launch, sizeof(n)) != cudaSuccess) return -1;
+    return (int)n;
 }
 #endif
 int bwd_tc_launch(const GemmArgs& G, int64_t max_rows, cudaStream_t st) {

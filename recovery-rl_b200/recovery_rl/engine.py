@@ -56,6 +56,7 @@ class VecEngine(object):
         self.start_steps = int(start_steps)
         self.relabel = not disable_action_relabeling            # experiment.py:438-441
         self.host_inputs = bool(host_inputs)
+        self.fused = int(use_tensor_cores) >= 2                 # use_tensor_cores 2: tcgen05 + fused update stages
         self.log_outputs = bool(log_outputs) or self.host_inputs
         sc = ACTION_SCALE[env_name]
         # peer_grads: the arena lives in symmetric memory and the optimizer-step kernel sums the ranks' gradient blocks
@@ -278,7 +279,8 @@ class VecEngine(object):
         self._all_reduce(["recovery"])
         native.recovery_apply(cfg, ar, cn, peers=self._peers)
         nb = 1 if self.peer_arena is not None else 0           # peer barrier kernels
-        return 5 + 1 + (8 if self.mf_recovery else 0) + 1 + 2 * nb     # kernels launched (gpu_launches bookkeeping)
+        f = 1 if self.fused else 0                             # loss / sample-backward stages run as kernel tails
+        return (5 - f) + 1 + ((8 - 2 * f) if self.mf_recovery else 0) + 1 + 2 * nb     # kernels launched (gpu_launches bookkeeping)
 
     def qrisk_update(self, sample_cfg=None):
         return self._qr_sample(sample_cfg) + self._qr_compute()
@@ -300,7 +302,7 @@ class VecEngine(object):
             dist_utils.all_reduce_sum(f32[native.S_G_LOG_ALPHA:native.S_G_LOG_ALPHA + 1], self.pg)
             dist_utils.all_reduce_sum(f64[native.D_G_LOG_NU:native.D_G_LOG_LAMBDA + 1], self.pg)
         native.sac_apply(cfg, ar, cn, peers=self._peers)
-        return 8 + 1 + (1 if self.scalar_algos else 0) + (1 if self.peer_arena is not None else 0)
+        return (6 if self.fused else 8) + 1 + (1 if self.scalar_algos else 0) + (1 if self.peer_arena is not None else 0)
 
     def sac_update(self):
         return self._sac_sample() + self._sac_compute()

@@ -67,11 +67,12 @@ def _dev(x, dev):
     return torch.as_tensor(np.ascontiguousarray(x), dtype=torch.float32).to(dev)
 
 
-@pytest.mark.parametrize("tc_updates", [0, 1])
+@pytest.mark.parametrize("tc_updates", [0, 1, 2])
 @pytest.mark.parametrize("tag", ["nav1_b256", "maze_b64"])
 def test_updates_and_acting_vs_reference(native, cuda, golden_dir, tag, tc_updates):
     """tc_updates = 1: the forward passes of the updates run their 256x256 contractions on tcgen05 (fp16 hi/lo
-    split, fwd_tc_kernel) and must meet the same 1e-4 bar as the fp32 SIMT tiles."""
+    split, fwd_tc_kernel) and must meet the same 1e-4 bar as the fp32 SIMT tiles; tc_updates = 2: additionally the
+    loss / sample-backward stages run as last-CTA tails of the producing kernels (the path bench.py times)."""
     z = np.load(os.path.join(golden_dir, "agent_%s.npz" % tag))
     B = int(z["B"])
     stride = int(z["stride"])

@@ -14,7 +14,7 @@ from test_oracle import ALGO_TAGS, algo_oracle_agent, algo_noise
 pytestmark = pytest.mark.gpu
 
 
-def _arena(native, dev, z, tag, B):
+def _arena(native, dev, z, tag, B, tc=1):
     from recovery_rl.arena import AgentArena
     P = tag + "_"
     f = z[P + "flags"]
@@ -24,7 +24,7 @@ def _arena(native, dev, z, tag, B):
                       eps_safe=float(z[P + "eps_safe"]), lr=float(z[P + "lr"]), action_scale=(sc, sc),
                       mf_recovery=bool(int(z[P + "mf_recovery"])), dgd=bool(f[0]), update_nu=bool(f[1]), rcpo=bool(f[2]),
                       auto_alpha=bool(f[3]), deterministic=bool(f[4]), nu=float(z[P + "nu"]),
-                      lambda_rcpo=float(z[P + "lambda_RCPO"]), use_tensor_cores=1)   # update forwards on tcgen05
+                      lambda_rcpo=float(z[P + "lambda_RCPO"]), use_tensor_cores=tc)   # update GEMMs on tcgen05 (2: + fused stages)
 
 
 def _pad_det(mods):
@@ -90,14 +90,15 @@ def _noise_dev(e, B, dev):
     return _dev(e, dev)
 
 
+@pytest.mark.parametrize("tc", [1, 2])
 @pytest.mark.parametrize("tag", ALGO_TAGS)
-def test_comparison_branches_vs_reference(native, cuda, golden_dir, tag):
+def test_comparison_branches_vs_reference(native, cuda, golden_dir, tag, tc):
     z = np.load(os.path.join(golden_dir, "agent_algos_b64.npz"))
     B = int(z["B"])
     P = tag + "_"
     stride = int(z["stride"])
     ora = algo_oracle_agent(z, tag)
-    ar = _arena(native, cuda, z, tag, B)
+    ar = _arena(native, cuda, z, tag, B, tc)
     losses = torch.zeros(16, device=cuda)
     det = ora.deterministic
     sc = float(z[P + "scale"])

@@ -33,7 +33,7 @@ BASELINE_CASES = {
 }
 
 
-@pytest.mark.parametrize("tensor_cores", [0, 1])
+@pytest.mark.parametrize("tensor_cores", [0, 1, 2])
 @pytest.mark.parametrize("case", sorted(BASELINE_CASES))
 def test_baseline_configs_match_oracle(native, cuda, case, tensor_cores):
     kw = dict(steps=3, seed=11, verbose=False, tensor_cores=tensor_cores)
