@@ -568,6 +568,192 @@ __global__ void __launch_bounds__(kThreads) adam_kernel(const __grid_constant__ 
     }
 }
 
+// (9') the same optimizer step with COALESCED operand-image refresh (tcgen05 path).  adam_kernel above scatters three
+//      image elements per parameter (4-byte stores 1 KB apart for the transposed fp32 image, 2-byte stores for the fp16
+//      hi/lo images): ~1.5 M sector writes per SAC step.  Here a CTA owns a 32x32 tile of a hidden matrix: float4 loads
+//      of p / g / m / v (peer gradients included), Adam + soft target update in registers, the tile (and the target's
+//      tile) transposed through shared memory, then every image is written in 16-byte pieces, contiguous per warp:
+//          fp32 W2^T image      thread (k, 4 consecutive n)                      128-byte runs
+//          tcgen05 image of W2  thread (n, 8 consecutive k) -> hi + lo uint4     512-byte runs
+//          ... and of W2^T      thread (k, 8 consecutive n) -> hi + lo uint4     512-byte runs
+//      The remaining tensors (W1, biases, heads: a few thousand floats per net) go through flat CTAs.  Same arithmetic
+//      per element as adam_kernel (bit-identical parameters).
+struct AdamW2 {
+    ImgRef src;      // the stepped hidden matrix and its three images
+    ImgRef tgt;      // its target-net counterpart (valid if has_tgt)
+    int has_tgt;
+};
+struct AdamTileArgs {
+    float* arena;
+    int64_t grad_off, m_off, v_off;
+    float b1, b2, eps, grad_scale;
+    double lr64;
+    int64_t* counters;
+    int t_counter, rows_counter;
+    AdamW2 w2[4];
+    int n_w2;
+    int64_t seg_off[24], seg_cnt[24];   // the other tensors of the stepped nets
+    int n_seg, n_flat;                  // flat CTAs
+    int64_t tgt_src_off, tgt_off, tgt_count;
+    float tau;
+    int upd_counter, interval;
+    int bump[3];
+    int n_bump;
+    const float* peer[8];
+    int n_peer;
+};
+__device__ __forceinline__ void adam_elem(float& p, float g, float& m, float& v, float b1, float b2, float eps, float step_size,
+                                          float bc2s) {
+    m = m + (g - m) * (1.0f - b1);               // exp_avg.lerp_(grad, 1 - beta1)
+    v = v * b2 + (1.0f - b2) * g * g;             // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+    const float denom = sqrtf(v) / bc2s + eps;
+    p = p - step_size * (m / denom);
+}
+__device__ __forceinline__ void half_split8(const float* w, uint4* hi, uint4* lo) {   // tc_image_store's split, 8 at once
+    __align__(16) __half h[8], l[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const float sv = fmaxf(fminf(w[e] * kTcScaleB, 60000.0f), -60000.0f);
+        h[e] = __float2half_rn(sv);
+        l[e] = __float2half_rn(sv - __half2float(h[e]));
+    }
+    *hi = *reinterpret_cast<const uint4*>(h);
+    *lo = *reinterpret_cast<const uint4*>(l);
+}
+// the three images of one 32x32 tile (rows n0.., columns k0..) held in shared memory as tile[n][k]
+__device__ __forceinline__ void write_tile_images(float* arena, const ImgRef& R, const float (*tile)[33], int n0, int k0) {
+    const int t = threadIdx.x;
+    {   // fp32 W2^T image: [k][n]
+        const int kk = t >> 3, nq = t & 7;
+        const float4 v = make_float4(tile[nq * 4 + 0][kk], tile[nq * 4 + 1][kk], tile[nq * 4 + 2][kk], tile[nq * 4 + 3][kk]);
+        *reinterpret_cast<float4*>(arena + R.img + (int64_t)(k0 + kk) * H + n0 + nq * 4) = v;
+    }
+    constexpr size_t kLo = (size_t)4 * 32 * 64;   // halves between the hi and the lo image of one 32-wide k chunk
+    if (t < 128) {   // tcgen05 image of W2: element (n, k)
+        const int nl = t & 31, kg = t >> 5;
+        float w[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) w[e] = tile[nl][kg * 8 + e];
+        uint4 hi, lo;
+        half_split8(w, &hi, &lo);
+        const int n = n0 + nl, c = k0 >> 5;
+        __half* img = reinterpret_cast<__half*>(arena + R.tc);
+        const size_t base = ((((size_t)c * 2) * 4 + kg) * 32 + (n >> 3)) * 64 + (n & 7) * 8;
+        *reinterpret_cast<uint4*>(img + base) = hi;
+        *reinterpret_cast<uint4*>(img + base + kLo) = lo;
+    } else {         // tcgen05 image of W2^T: element (n' = k, k' = n)
+        const int kl = (t - 128) & 31, ng = (t - 128) >> 5;
+        float w[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) w[e] = tile[ng * 8 + e][kl];
+        uint4 hi, lo;
+        half_split8(w, &hi, &lo);
+        const int k = k0 + kl, c = n0 >> 5;
+        __half* img = reinterpret_cast<__half*>(arena + R.tcT);
+        const size_t base = ((((size_t)c * 2) * 4 + ng) * 32 + (k >> 3)) * 64 + (k & 7) * 8;
+        *reinterpret_cast<uint4*>(img + base) = hi;
+        *reinterpret_cast<uint4*>(img + base + kLo) = lo;
+    }
+}
+__global__ void __launch_bounds__(kThreads) adam_tile_kernel(const __grid_constant__ AdamTileArgs A) {
+    if (A.counters[A.rows_counter] <= 0) return;
+    __shared__ float s_bc[2];
+    __shared__ int s_polyak;
+    __shared__ float tile[32][33], ttile[32][33];
+    const int t = threadIdx.x;
+    if (t == 0) {  // bias corrections and step size in double (python floats in torch), once per block
+        const double tstep = (double)(A.counters[A.t_counter] + 1);
+        s_bc[0] = (float)(A.lr64 / (1.0 - pow((double)A.b1, tstep)));
+        s_bc[1] = (float)sqrt(1.0 - pow((double)A.b2, tstep));
+        s_polyak = A.tgt_count > 0 && (A.interval <= 1 || (A.counters[A.upd_counter] % A.interval) == 0);
+    }
+    __syncthreads();
+    const float step_size = s_bc[0], bc2s = s_bc[1];
+    const bool polyak = s_polyak != 0;
+    const float omt = (float)(1.0 - (double)A.tau);
+    const int n_tile_ctas = A.n_w2 * 64;
+    if ((int)blockIdx.x < n_tile_ctas) {
+        const AdamW2& W = A.w2[blockIdx.x >> 6];
+        const int tl = blockIdx.x & 63, n0 = (tl >> 3) * 32, k0 = (tl & 7) * 32;
+        const int rn = t >> 3, kq = t & 7;
+        const int64_t o = W.src.off + (int64_t)(n0 + rn) * H + k0 + kq * 4;
+        float4 p4 = *reinterpret_cast<const float4*>(A.arena + o);
+        float4 g4;
+        if (A.n_peer > 0) {
+            float4 gs[8];   // all NVLink peer loads in flight together, then summed in rank order
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+                gs[r] = r < A.n_peer ? __ldcv(reinterpret_cast<const float4*>(A.peer[r] + A.grad_off + o)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            g4 = gs[0];
+#pragma unroll
+            for (int r = 1; r < 8; ++r) { g4.x += gs[r].x; g4.y += gs[r].y; g4.z += gs[r].z; g4.w += gs[r].w; }
+        } else {
+            g4 = *reinterpret_cast<const float4*>(A.arena + A.grad_off + o);
+        }
+        float4 m4 = *reinterpret_cast<const float4*>(A.arena + A.m_off + o);
+        float4 v4 = *reinterpret_cast<const float4*>(A.arena + A.v_off + o);
+        float4 tp4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        const bool do_tgt = polyak && W.has_tgt;
+        const int64_t to = W.tgt.off + (int64_t)(n0 + rn) * H + k0 + kq * 4;
+        if (do_tgt) tp4 = *reinterpret_cast<const float4*>(A.arena + to);
+        adam_elem(p4.x, g4.x * A.grad_scale, m4.x, v4.x, A.b1, A.b2, A.eps, step_size, bc2s);
+        adam_elem(p4.y, g4.y * A.grad_scale, m4.y, v4.y, A.b1, A.b2, A.eps, step_size, bc2s);
+        adam_elem(p4.z, g4.z * A.grad_scale, m4.z, v4.z, A.b1, A.b2, A.eps, step_size, bc2s);
+        adam_elem(p4.w, g4.w * A.grad_scale, m4.w, v4.w, A.b1, A.b2, A.eps, step_size, bc2s);
+        *reinterpret_cast<float4*>(A.arena + o) = p4;
+        *reinterpret_cast<float4*>(A.arena + A.m_off + o) = m4;
+        *reinterpret_cast<float4*>(A.arena + A.v_off + o) = v4;
+        tile[rn][kq * 4 + 0] = p4.x; tile[rn][kq * 4 + 1] = p4.y; tile[rn][kq * 4 + 2] = p4.z; tile[rn][kq * 4 + 3] = p4.w;
+        if (do_tgt) {
+            tp4.x = tp4.x * omt + p4.x * A.tau; tp4.y = tp4.y * omt + p4.y * A.tau;
+            tp4.z = tp4.z * omt + p4.z * A.tau; tp4.w = tp4.w * omt + p4.w * A.tau;
+            *reinterpret_cast<float4*>(A.arena + to) = tp4;
+            ttile[rn][kq * 4 + 0] = tp4.x; ttile[rn][kq * 4 + 1] = tp4.y; ttile[rn][kq * 4 + 2] = tp4.z; ttile[rn][kq * 4 + 3] = tp4.w;
+        }
+        __syncthreads();
+        write_tile_images(A.arena, W.src, tile, n0, k0);
+        if (do_tgt) write_tile_images(A.arena, W.tgt, ttile, n0, k0);
+    } else {
+        const int fb = blockIdx.x - n_tile_ctas;
+        for (int sg = 0; sg < A.n_seg; ++sg) {
+            for (int64_t i = (int64_t)fb * kThreads + t; i < A.seg_cnt[sg]; i += (int64_t)A.n_flat * kThreads) {
+                const int64_t o = A.seg_off[sg] + i;
+                float p = A.arena[o];
+                float g;
+                if (A.n_peer > 0) {
+                    float gs[8];
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) gs[r] = r < A.n_peer ? __ldcv(A.peer[r] + A.grad_off + o) : 0.f;
+                    g = gs[0];
+#pragma unroll
+                    for (int r = 1; r < 8; ++r) g += gs[r];
+                } else {
+                    g = A.arena[A.grad_off + o];
+                }
+                float m = A.arena[A.m_off + o], v = A.arena[A.v_off + o];
+                adam_elem(p, g * A.grad_scale, m, v, A.b1, A.b2, A.eps, step_size, bc2s);
+                A.arena[A.m_off + o] = m;
+                A.arena[A.v_off + o] = v;
+                A.arena[o] = p;
+                if (polyak) {
+                    const int64_t d0 = o - A.tgt_src_off;
+                    if (d0 >= 0 && d0 < A.tgt_count) A.arena[A.tgt_off + d0] = A.arena[A.tgt_off + d0] * omt + p * A.tau;
+                }
+            }
+        }
+    }
+    // every CTA has read the counters above; the last one to arrive bumps them
+    __syncthreads();
+    if (t == 0 && A.n_bump > 0) {
+        __threadfence();
+        const unsigned long long ticket = atomicAdd(reinterpret_cast<unsigned long long*>(A.counters + RRL_C_TICKET), 1ull);
+        if (ticket == (unsigned long long)gridDim.x - 1) {
+            A.counters[RRL_C_TICKET] = 0;
+            for (int i = 0; i < A.n_bump; ++i) A.counters[A.bump[i]] += 1;
+        }
+    }
+}
+
 // (9b) Adam on the scalar multipliers (sac.py:241-271): log_alpha is a float32 tensor with lr; log_nu and
 //      log_lambda_RCPO are float64 tensors (np.log of a python float) with lr 0.1*lr.  One thread.
 struct ScalarAdamArgs {
@@ -768,11 +954,17 @@ int imgs_of_net(const Layout& L, int net, ImgRef* out) {
     return heads;
 }
 
+int launch_adam_tiled(const rrl_agent_config_t* cfg, const Layout& L, float* arena, int64_t* counters, int net_a, int net_b,
+                      int t_counter, int rows_counter, cudaStream_t st, int polyak_dst, int polyak_src, float tau,
+                      int upd_counter, const int* bump, int n_bump, const rrl_peers_t* peers);
 // nets a (and b, contiguous after a in storage order) share one launch.  net_a < 0 with polyak_src >= 0: no Adam
 // (lr64 = 0), only the soft update of polyak_src into polyak_dst and the bookkeeping.
 int launch_adam(const rrl_agent_config_t* cfg, const Layout& L, float* arena, int64_t* counters, int net_a, int net_b,
                 int t_counter, int rows_counter, cudaStream_t st, int polyak_dst = -1, int polyak_src = -1, float tau = 0.f,
                 int upd_counter = -1, const int* bump = nullptr, int n_bump = 0, const rrl_peers_t* peers = nullptr) {
+    if (cfg->use_tensor_cores && net_a >= 0)   // tcgen05 path: coalesced image refresh (bit-identical parameters)
+        return launch_adam_tiled(cfg, L, arena, counters, net_a, net_b, t_counter >= 0 ? t_counter : RRL_C_ADAM_T0, rows_counter, st,
+                                 polyak_dst, polyak_src, tau, upd_counter, bump, n_bump, peers);
     AdamArgs A;
     memset(&A, 0, sizeof(A));
     if (peers) {
@@ -806,6 +998,58 @@ int launch_adam(const rrl_agent_config_t* cfg, const Layout& L, float* arena, in
     RRL_CHECK_LAUNCH();
     return 0;
 }
+// the tiled variant (adam_tile_kernel): same arguments; nets a (and b) are stepped, polyak_src -> polyak_dst soft-updated
+int launch_adam_tiled(const rrl_agent_config_t* cfg, const Layout& L, float* arena, int64_t* counters, int net_a, int net_b,
+                      int t_counter, int rows_counter, cudaStream_t st, int polyak_dst, int polyak_src, float tau,
+                      int upd_counter, const int* bump, int n_bump, const rrl_peers_t* peers) {
+    AdamTileArgs A;
+    memset(&A, 0, sizeof(A));
+    if (peers) {
+        A.n_peer = peers->world;
+        for (int r = 0; r < peers->world && r < 8; ++r) A.peer[r] = reinterpret_cast<const float*>(peers->arena[r]);
+    }
+    A.arena = arena;
+    A.grad_off = L.grad_off; A.m_off = L.m_off; A.v_off = L.v_off;
+    A.b1 = cfg->beta1; A.b2 = cfg->beta2; A.eps = cfg->adam_eps; A.grad_scale = cfg->grad_scale;
+    A.lr64 = cfg->lr64 > 0.0 ? cfg->lr64 : (double)cfg->lr;
+    A.counters = counters;
+    A.t_counter = t_counter; A.rows_counter = rows_counter;
+    const int nets[2] = {net_a, net_b};
+    for (int ni = 0; ni < 2; ++ni) {
+        const int net = nets[ni];
+        if (net < 0) continue;
+        ImgRef src[2], tgt[2];
+        const int heads = imgs_of_net(L, net, src);
+        const bool has_tgt = polyak_dst >= 0 && polyak_src == net;
+        if (has_tgt) imgs_of_net(L, polyak_dst, tgt);
+        for (int h = 0; h < heads; ++h) {
+            AdamW2& W = A.w2[A.n_w2++];
+            W.src = src[h];
+            W.has_tgt = has_tgt ? 1 : 0;
+            if (has_tgt) W.tgt = tgt[h];
+        }
+        for (int t = 0; t < L.n_tensors[net]; ++t) {
+            bool is_w2 = false;
+            for (int h = 0; h < heads; ++h) is_w2 = is_w2 || (t == w2_tensor(net, h));
+            if (is_w2) continue;
+            const TDesc d = L.t_desc[net][t];
+            if (A.n_seg >= 24) { rrl_set_error("launch_adam_tiled: too many tensors"); return -2; }
+            A.seg_off[A.n_seg] = L.t_off[net][t];
+            A.seg_cnt[A.n_seg] = (int64_t)d.rows * (d.cols ? d.cols : 1);
+            ++A.n_seg;
+        }
+    }
+    if (polyak_dst >= 0) {
+        A.tgt_src_off = L.net_off[polyak_src]; A.tgt_off = L.net_off[polyak_dst]; A.tgt_count = L.net_size[polyak_dst];
+        A.tau = tau; A.upd_counter = upd_counter; A.interval = cfg->target_update_interval;
+    }
+    for (int i = 0; i < n_bump && i < 3; ++i) A.bump[i] = bump[i];
+    A.n_bump = n_bump < 3 ? n_bump : 3;
+    A.n_flat = 4;
+    adam_tile_kernel<<<A.n_w2 * 64 + A.n_flat, kThreads, 0, st>>>(A);
+    RRL_CHECK_LAUNCH();
+    return 0;
+}
 int launch_polyak(const Layout& L, float* arena, const int64_t* counters, int dst, int src, float tau, int rows_counter,
                   int upd_counter, int interval, cudaStream_t st) {
     PolyakArgs A;
@@ -831,14 +1075,24 @@ int launch_gemm(GemmArgs& G, int n_pass, int mt, int64_t max_rows, int use_tc, c
     return 0;
 }
 
-FwdPass q_pass(const Layout& L, float* arena, int net, int head, const float* xs, const float* xa, int slot, float* out_q) {
+inline uint32_t* slot_bits(const Layout& L, float* arena, int slot) { return reinterpret_cast<uint32_t*>(arena + L.dh2t[slot]); }
+
+// layer 1 of the pass + its inputs + the sign bits of h2 (tcgen05 backward: h1 / relu' are recomputed, never loaded)
+inline void bwd_inputs(GemmPass& p, const HeadW& w, const float* xs, const float* xa, const Layout& L, float* arena, int slot) {
+    p.W1 = w.W1; p.b1 = w.b1; p.n_in = w.n_in; p.xs = xs; p.xa = xa; p.h2bits = slot_bits(L, arena, slot);
+}
+
+// slot >= 0: activations are kept for the backward pass; weight_pass: the backward also has a WEIGHT pass for it
+FwdPass q_pass(const Layout& L, float* arena, int net, int head, const float* xs, const float* xa, int slot, float* out_q,
+               bool weight_pass = false) {
     FwdPass p;
     memset(&p, 0, sizeof(p));
     p.w = head_w(L, arena, net, head);
     p.tc_img = tc_img_of(L, arena, net, head);
     p.head = (net == RRL_NET_QRISK || net == RRL_NET_QRISK_TARGET) ? HEAD_QRISK : HEAD_Q;
     p.xs = xs; p.xa = xa;
-    if (slot >= 0) { p.h1 = arena + L.h1[slot]; p.h2 = arena + L.h2[slot]; }
+    if (slot >= 0) { p.h1 = arena + L.h1[slot]; p.h2 = arena + L.h2[slot]; p.h2bits = slot_bits(L, arena, slot); }
+    p.keep_h2 = weight_pass ? 1 : 0;
     p.out_q = out_q;
     return p;
 }
@@ -1074,7 +1328,7 @@ extern "C" int rrl_sac_backward(const rrl_agent_config_t* cfg, float* arena, con
         p0.draw_id = RRL_DRAW_SAC_NEXT; p0.out_a = R2(R2_NEXT_A); p0.out_logp = RA(RA_NEXT_LOGP);
         FwdPass& p1 = A.p[1];
         p1.w = pw; p1.head = pol_head; p1.xs = s; p1.eps = eps_cur; p1.draw_id = RRL_DRAW_SAC_CUR; p1.tc_img = p0.tc_img;
-        p1.h1 = arena + L.h1[4]; p1.h2 = arena + L.h2[4];
+        p1.h1 = arena + L.h1[4]; p1.h2 = arena + L.h2[4]; p1.h2bits = slot_bits(L, arena, 4); p1.keep_h2 = 1;
         p1.out_a = R2(R2_PI); p1.out_logp = RA(RA_LOGP); p1.out_raw = R4(R4_RAW_POL); p1.out_eps = R2(R2_EPS_CUR);
         int rc = launch_forward<32>(A, R, st);
         if (rc) return rc;
@@ -1087,8 +1341,8 @@ extern "C" int rrl_sac_backward(const rrl_agent_config_t* cfg, float* arena, con
         int n = 0;
         A.p[n++] = q_pass(L, arena, RRL_NET_CRITIC_TARGET, 0, s2, R2(R2_NEXT_A), -1, RA(RA_QT1));
         A.p[n++] = q_pass(L, arena, RRL_NET_CRITIC_TARGET, 1, s2, R2(R2_NEXT_A), -1, RA(RA_QT2));
-        A.p[n++] = q_pass(L, arena, RRL_NET_CRITIC, 0, s, a, 0, RA(RA_QF1));
-        A.p[n++] = q_pass(L, arena, RRL_NET_CRITIC, 1, s, a, 1, RA(RA_QF2));
+        A.p[n++] = q_pass(L, arena, RRL_NET_CRITIC, 0, s, a, 0, RA(RA_QF1), true);
+        A.p[n++] = q_pass(L, arena, RRL_NET_CRITIC, 1, s, a, 1, RA(RA_QF2), true);
         A.p[n++] = q_pass(L, arena, RRL_NET_CRITIC, 0, s, R2(R2_PI), 2, RA(RA_QP1));
         A.p[n++] = q_pass(L, arena, RRL_NET_CRITIC, 1, s, R2(R2_PI), 3, RA(RA_QP2));
         if (sq_pi) {
@@ -1132,6 +1386,7 @@ extern "C" int rrl_sac_backward(const rrl_agent_config_t* cfg, float* arena, con
             const HeadW& w = q < 4 ? ((q & 1) ? c2 : c1) : ((q & 1) ? k2 : k1);
             p.dout = dout[q]; p.stride = 1; p.n_out = 1; p.na = 1; p.W3a = w.W3a; p.h2 = arena + L.h2[slot[q]];
             p.B = w.W2; p.tc_imgT = w.tc_imgT; p.k_is_rows = 0; p.mask = arena + L.h1[slot[q]]; p.C = arena + L.dh1[slot[q]];
+            bwd_inputs(p, w, s, q < 2 ? a : R2(R2_PI), L, arena, slot[q]);
         }
         for (int q = 0; q < 2; ++q) {
             GemmPass& p = G.p[n++];
@@ -1140,6 +1395,7 @@ extern "C" int rrl_sac_backward(const rrl_agent_config_t* cfg, float* arena, con
             p.dout = dout[q]; p.stride = 1; p.n_out = 1; p.na = 1; p.W3a = w.W3a; p.h2 = arena + L.h2[q];
             p.B = arena + L.h1[q]; p.k_is_rows = 1; p.C = g.W2;
             p.gW3a = g.W3a; p.gb3a = g.b3a; p.gb2 = g.b2;
+            bwd_inputs(p, w, s, a, L, arena, q);
         }
         const int mt = (int)((R > H ? R : H) / 32);
         { int rc = launch_gemm(G, n, mt, R, cfg->use_tensor_cores, st); if (rc) return rc; }
@@ -1188,6 +1444,7 @@ extern "C" int rrl_sac_backward(const rrl_agent_config_t* cfg, float* arena, con
             GemmPass& p = G.p[q];
             p.dout = R4(R4_DRAW_POL); p.stride = 4; p.n_out = det ? 2 : 4; p.na = 2; p.W3a = pw.W3a; p.W3b = pw.W3b;
             p.h2 = arena + L.h2[4];
+            bwd_inputs(p, pw, s, nullptr, L, arena, 4);
         }
         G.p[0].B = pw.W2; G.p[0].tc_imgT = pw.tc_imgT; G.p[0].mask = arena + L.h1[4]; G.p[0].C = arena + L.dh1[4];
         G.p[1].B = arena + L.h1[4]; G.p[1].k_is_rows = 1; G.p[1].C = pg.W2;
@@ -1276,8 +1533,8 @@ extern "C" int rrl_qrisk_backward(const rrl_agent_config_t* cfg, float* arena, c
         A.n_pass = 4; A.rows_ptr = rows_ptr; A.sp = sp; A.use_tc = cfg->use_tensor_cores;
         A.p[0] = q_pass(L, arena, RRL_NET_QRISK_TARGET, 0, s2, R2(R2_QR_NEXT_A), -1, RA(RA_QR_QT1));
         A.p[1] = q_pass(L, arena, RRL_NET_QRISK_TARGET, 1, s2, R2(R2_QR_NEXT_A), -1, RA(RA_QR_QT2));
-        A.p[2] = q_pass(L, arena, RRL_NET_QRISK, 0, s, a, 0, RA(RA_QR_Q1));
-        A.p[3] = q_pass(L, arena, RRL_NET_QRISK, 1, s, a, 1, RA(RA_QR_Q2));
+        A.p[2] = q_pass(L, arena, RRL_NET_QRISK, 0, s, a, 0, RA(RA_QR_Q1), true);
+        A.p[3] = q_pass(L, arena, RRL_NET_QRISK, 1, s, a, 1, RA(RA_QR_Q2), true);
         QrLossArgs& T = A.tail.qr;
         T.c = c; T.m = m; T.qt1 = RA(RA_QR_QT1); T.qt2 = RA(RA_QR_QT2); T.q1 = RA(RA_QR_Q1); T.q2 = RA(RA_QR_Q2);
         T.target = RA(RA_QR_TARGET); T.dq1 = RA(RA_QR_DQ1); T.dq2 = RA(RA_QR_DQ2); T.losses = losses;
@@ -1302,6 +1559,7 @@ extern "C" int rrl_qrisk_backward(const rrl_agent_config_t* cfg, float* arena, c
             GemmPass& p = G.p[q];
             p.dout = q ? RA(RA_QR_DQ2) : RA(RA_QR_DQ1); p.stride = 1; p.n_out = 1; p.na = 1; p.W3a = w.W3a;
             p.h2 = arena + L.h2[q]; p.B = w.W2; p.tc_imgT = w.tc_imgT; p.mask = arena + L.h1[q]; p.C = arena + L.dh1[q];
+            bwd_inputs(p, w, s, a, L, arena, q);
             GemmPass& ww = G.p[2 + q];
             ww = p;
             ww.B = arena + L.h1[q]; ww.k_is_rows = 1; ww.mask = nullptr; ww.C = g.W2;
@@ -1371,7 +1629,8 @@ extern "C" int rrl_recovery_backward(const rrl_agent_config_t* cfg, float* arena
         FwdPass& p0 = A.p[0];
         p0.w = head_w(L, arena, RRL_NET_RECOVERY, 0); p0.head = HEAD_STOCH; p0.xs = s; p0.eps = eps_rec;
         p0.tc_img = tc_img_of(L, arena, RRL_NET_RECOVERY, 0);
-        p0.draw_id = RRL_DRAW_QR_REC; p0.h1 = arena + L.h1[4]; p0.h2 = arena + L.h2[4];
+        p0.draw_id = RRL_DRAW_QR_REC; p0.h1 = arena + L.h1[4]; p0.h2 = arena + L.h2[4]; p0.h2bits = slot_bits(L, arena, 4);
+        p0.keep_h2 = 1;
         p0.out_a = R2(R2_REC_PI); p0.out_logp = RA(RA_REC_LOGP); p0.out_raw = R4(R4_RAW_REC); p0.out_eps = R2(R2_REC_EPS);
         int rc = launch_forward<32>(A, R, st);
         if (rc) return rc;
@@ -1405,6 +1664,7 @@ extern "C" int rrl_recovery_backward(const rrl_agent_config_t* cfg, float* arena
             p.dout = q ? RA(RA_REC_DQ2) : RA(RA_REC_DQ1); p.stride = 1; p.n_out = 1; p.na = 1; p.W3a = (q ? c2 : c1).W3a;
             p.h2 = arena + L.h2[2 + q]; p.B = (q ? c2 : c1).W2; p.tc_imgT = (q ? c2 : c1).tc_imgT;
             p.mask = arena + L.h1[2 + q]; p.C = arena + L.dh1[2 + q];
+            bwd_inputs(p, q ? c2 : c1, s, R2(R2_REC_PI), L, arena, 2 + q);
         }
         { int rc = launch_gemm(G, 2, (int)(R / 32), R, cfg->use_tensor_cores, st); if (rc) return rc; }
     }
@@ -1436,6 +1696,7 @@ extern "C" int rrl_recovery_backward(const rrl_agent_config_t* cfg, float* arena
         for (int q = 0; q < 2; ++q) {
             GemmPass& p = G.p[q];
             p.dout = R4(R4_DRAW_REC); p.stride = 4; p.n_out = 2; p.na = 2; p.W3a = pw.W3a; p.h2 = arena + L.h2[4];
+            bwd_inputs(p, pw, s, nullptr, L, arena, 4);
         }
         G.p[0].B = pw.W2; G.p[0].tc_imgT = pw.tc_imgT; G.p[0].mask = arena + L.h1[4]; G.p[0].C = arena + L.dh1[4];
         G.p[1].B = arena + L.h1[4]; G.p[1].k_is_rows = 1; G.p[1].C = pg.W2;

@@ -146,7 +146,10 @@ struct FwdPass {
     int head;
     const float* xs;  // [rows][2]
     const float* xa;  // [rows][2] (n_in == 4)
-    float *h1, *h2;
+    float *h1, *h2;    // activations kept for the backward pass (SIMT path: both; tcgen05 path: h2 only where a WEIGHT pass
+                       // needs its values -- h1 is recomputed from the inputs, relu'(h2) comes from h2bits)
+    uint32_t* h2bits;  // tcgen05 path: sign bits of h2, [rows][H / 32] words (bit j of word w: h2[row][32 w + j] > 0)
+    int keep_h2;       // tcgen05 path: the backward has a WEIGHT pass for this forward pass (h2 values needed, not only signs)
     const float* eps;  // [rows][2] or NULL (Philox)
     uint32_t draw_id;
     float *out_q, *out_a, *out_logp, *out_mean, *out_raw, *out_eps;
@@ -251,10 +254,15 @@ struct GemmPass {
     const float *W3a, *W3b, *h2;
     const float* B;     // SIMT: W2 [H][H] (DATA) or h1 [rows][H] (WEIGHT)
     int k_is_rows;      // K = rows (WEIGHT) else K = H (DATA)
-    const float* mask;  // DATA: h1
+    const float* mask;  // DATA: h1 (SIMT path)
     float* C;
     float *gW3a, *gW3b, *gb3a, *gb3b, *gb2;  // WEIGHT only
     const __half* tc_imgT;  // DATA on tcgen05: fp16 hi/lo image of W2^T
+    // tcgen05 path: layer 1 of the pass and its inputs (h1 and relu'(h1) are recomputed, never loaded) and the sign bits
+    // of h2 written by the forward kernel (relu'(h2) of the DATA producers)
+    const float *W1, *b1, *xs, *xa;
+    int n_in;
+    const uint32_t* h2bits;
 };
 struct GemmArgs {
     GemmPass p[8];

@@ -494,10 +494,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
         const bool four = w.n_in == 4;
         for (int c = 0; c < NCHUNK; ++c) {
             const int stage = c % NSTAGE;
-            mbar_wait(smem_u32(&S.empty[stage]), ((c / NSTAGE) & 1) ^ 1);
             unsigned char* a_hi = S.stage[stage];
             unsigned char* a_lo = a_hi + A_IMG;
-            float hv[8], hs[8];
+            float hs[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
                 const int k = c * KCH + q * 8 + e;
@@ -508,19 +507,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
                     h = fmaf(wv.z, x2, h);
                     h = fmaf(wv.w, x3, h);
                 }
-                h = fmaxf(h, 0.f);
-                hv[e] = h * (1.0f / SA);      // exact: SA is a power of two
-                hs[e] = fminf(h, 60000.0f);
+                hs[e] = fminf(fmaxf(h, 0.f), 60000.0f);    // h1 * SA; the backward kernels recompute it (never stored)
             }
             uint4 hi, lo;
             split8(hs, &hi, &lo);
+            mbar_wait(smem_u32(&S.empty[stage]), ((c / NSTAGE) & 1) ^ 1);   // after the arithmetic: the wait overlaps it
             *reinterpret_cast<uint4*>(a_hi + q * LBO_A + r * 16) = hi;
             *reinterpret_cast<uint4*>(a_lo + q * LBO_A + r * 16) = lo;
-            if (P.h1 && live) {
-                float4* dst = reinterpret_cast<float4*>(P.h1 + row * H + c * KCH + q * 8);
-                dst[0] = make_float4(hv[0], hv[1], hv[2], hv[3]);
-                dst[1] = make_float4(hv[4], hv[5], hv[6], hv[7]);
-            }
             fence_proxy_async();
             mbar_arrive_warp(smem_u32(&S.full[stage]));
         }
@@ -557,7 +550,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
                     }
                 }
             }
-            if (P.h2)
+            if (P.h2bits && live) {   // relu'(h2) for the backward DATA producers: one word per 32 columns
+                uint32_t mb = 0u;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) mb |= v[j] > 0.f ? (1u << j) : 0u;
+                P.h2bits[row * (H / 32) + q * 2 + cc] = mb;
+            }
+            if (P.h2 && P.keep_h2)
                 warp_block_rows(scratch, v, lane, [&](int rl, int c4, float4 hv) {
                     if (wrow0 + rl < rows) *reinterpret_cast<float4*>(P.h2 + (wrow0 + rl) * H + col0 + 4 * c4) = hv;
                 });
@@ -630,6 +629,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
 constexpr int kDoutRows = 1024;
 struct BwdTcSmem {
     unsigned char stage[NSTAGE][STAGE_BYTES];
+    float W1[H][4];                 // layer 1 of the pass, pre-multiplied by SA like the forward kernel (h1 is recomputed)
+    float b1[H];
+    float4 xin[kDoutRows];          // the pass's inputs (s, a): rows of this tile (DATA) / of the whole batch (WEIGHT)
     float w3[4][H];
     float red[kProd][6];            // WEIGHT: per-thread partial sums (gb2, gW3[0..3])
     float4 douts[kDoutRows];        // WEIGHT: dout of the whole batch (rows <= kDoutRows), zero-padded to 4 outputs
@@ -663,10 +665,38 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const __grid_cons
     const int n_chunks = weight ? (int)((rows + KCH - 1) / KCH) : NCHUNK;
 
     // ---- setup ----
-    for (int k = t; k < H; k += kTcThreads)
+    const bool four = P.n_in == 4;
+    for (int k = t; k < H; k += kTcThreads) {
 #pragma unroll
         for (int o = 0; o < 4; ++o)
             S.w3[o][k] = o < P.na ? P.W3a[o * H + k] : (o < P.n_out ? P.W3b[(o - P.na) * H + k] : 0.f);
+        float4 w1 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (four) {
+            w1 = *reinterpret_cast<const float4*>(P.W1 + k * 4);
+        } else {
+            const float2 v = *reinterpret_cast<const float2*>(P.W1 + k * 2);
+            w1.x = v.x; w1.y = v.y;
+        }
+        w1.x *= SA; w1.y *= SA; w1.z *= SA; w1.w *= SA;       // exact (power of two): same values as fwd_tc_kernel
+        *reinterpret_cast<float4*>(S.W1[k]) = w1;
+        S.b1[k] = P.b1[k] * SA;
+    }
+    {   // inputs of the rows this CTA touches: its 128-row tile (DATA) or the whole batch (WEIGHT, if it fits)
+        const int64_t xbase = weight ? 0 : (int64_t)tile * TM;
+        const int nx = weight ? (rows <= kDoutRows ? (int)rows : 0) : TM;
+        for (int i = t; i < nx; i += kTcThreads) {
+            float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (xbase + i < rows) {
+                const float2 sv = reinterpret_cast<const float2*>(P.xs)[xbase + i];
+                x.x = sv.x; x.y = sv.y;
+                if (four) {
+                    const float2 av = reinterpret_cast<const float2*>(P.xa)[xbase + i];
+                    x.z = av.x; x.w = av.y;
+                }
+            }
+            S.xin[i] = x;
+        }
+    }
     if (t == 0) {
         for (int s = 0; s < NSTAGE; ++s) {
             mbar_init(smem_u32(&S.full[s]), weight ? kProdWarps : kProdWarps + 1);
@@ -734,26 +764,27 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const __grid_cons
                         bound = fmaf(fabsf(d[o]), S.wmax[o], bound);
                     }
             const float sc = pow2_scale(bound);
-            float4 hn0 = make_float4(0.f, 0.f, 0.f, 0.f), hn1 = hn0;
-            if (live) {
-                hn0 = *reinterpret_cast<const float4*>(P.h2 + row * H + q * 8);
-                hn1 = *reinterpret_cast<const float4*>(P.h2 + row * H + q * 8 + 4);
+            // relu'(h2) of the row: 256 sign bits written by the forward kernel (no activation loads in this loop)
+            uint32_t hb[NCHUNK];
+            {
+                uint4 b0 = make_uint4(0u, 0u, 0u, 0u), b1v = b0;
+                if (live) {
+                    b0 = *reinterpret_cast<const uint4*>(P.h2bits + row * (H / 32));
+                    b1v = *reinterpret_cast<const uint4*>(P.h2bits + row * (H / 32) + 4);
+                }
+                hb[0] = b0.x; hb[1] = b0.y; hb[2] = b0.z; hb[3] = b0.w; hb[4] = b1v.x; hb[5] = b1v.y; hb[6] = b1v.z; hb[7] = b1v.w;
             }
+#pragma unroll
             for (int c = 0; c < NCHUNK; ++c) {
                 const int stage = c % NSTAGE;
                 const int k0 = c * KCH + q * 8;
-                const float4 h0 = hn0, h1v = hn1;
-                if (live && c + 1 < NCHUNK) {          // next chunk's h2 in flight while this one is converted
-                    hn0 = *reinterpret_cast<const float4*>(P.h2 + row * H + k0 + KCH);
-                    hn1 = *reinterpret_cast<const float4*>(P.h2 + row * H + k0 + KCH + 4);
-                }
-                const float hv[8] = {h0.x, h0.y, h0.z, h0.w, h1v.x, h1v.y, h1v.z, h1v.w};
+                const uint32_t bits = hb[c] >> (q * 8);
                 float gv[8];
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
                     float v = d[0] * S.w3[0][k0 + e];
                     v = fmaf(d[1], S.w3[1][k0 + e], v); v = fmaf(d[2], S.w3[2][k0 + e], v); v = fmaf(d[3], S.w3[3][k0 + e], v);
-                    gv[e] = hv[e] > 0.f ? v * sc : 0.f;
+                    gv[e] = ((bits >> e) & 1u) ? v * sc : 0.f;
                 }
                 uint4 hi, lo;
                 split8(gv, &hi, &lo);
@@ -782,10 +813,22 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const __grid_cons
                 warp_block_rows(scratch, v, lane, [&](int rl, int c4, float4 g) {
                     const int64_t rr = wrow0 + rl;
                     if (rr < rows) {
-                        const float4 mk = *reinterpret_cast<const float4*>(P.mask + rr * H + col0 + 4 * c4);
-                        g.x = mk.x > 0.f ? g.x : 0.f; g.y = mk.y > 0.f ? g.y : 0.f;
-                        g.z = mk.z > 0.f ? g.z : 0.f; g.w = mk.w > 0.f ? g.w : 0.f;
-                        *reinterpret_cast<float4*>(P.C + rr * H + col0 + 4 * c4) = g;
+                        // relu'(h1): the sign of layer 1 recomputed from the row's inputs (same FMA chain as the forward)
+                        const float4 x = S.xin[(warp & 3) * 32 + rl];
+                        float gg[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int k = col0 + 4 * c4 + i;
+                            const float4 wv = *reinterpret_cast<const float4*>(S.W1[k]);
+                            float h = fmaf(wv.x, x.x, S.b1[k]);
+                            h = fmaf(wv.y, x.y, h);
+                            if (four) {
+                                h = fmaf(wv.z, x.z, h);
+                                h = fmaf(wv.w, x.w, h);
+                            }
+                            gg[i] = h > 0.f ? gg[i] : 0.f;
+                        }
+                        *reinterpret_cast<float4*>(P.C + rr * H + col0 + 4 * c4) = make_float4(gg[0], gg[1], gg[2], gg[3]);
                     }
                 });
             }
@@ -804,25 +847,59 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const __grid_cons
             float gb2 = 0.f, gw[4] = {0.f, 0.f, 0.f, 0.f};
             const int nB0 = t & (H - 1), kcB0 = t >> 8;                 // B role, item 0: (n, kc)
             const int nB1 = (t + kProd) & (H - 1), kcB1 = (t + kProd) >> 8;
-            float h2n[8], h1n[2][8];                                     // prefetched operands of the NEXT chunk
+            // B operand = h1^T (scaled by SA): recomputed from the rows' inputs with the forward kernel's FMA chain -- no
+            // activation loads; the rows' (s, a) sit in shared memory (or, for batches beyond kDoutRows, in L1 / L2)
+            const bool x_smem = rows <= kDoutRows;
+            const float4 w1B0 = *reinterpret_cast<const float4*>(S.W1[nB0]), w1B1 = *reinterpret_cast<const float4*>(S.W1[nB1]);
+            const float b1B0 = S.b1[nB0], b1B1 = S.b1[nB1];
+            auto row_x = [&](int64_t rb) -> float4 {
+                if (x_smem) return S.xin[rb];
+                float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+                const float2 sv = reinterpret_cast<const float2*>(P.xs)[rb];
+                x.x = sv.x; x.y = sv.y;
+                if (four) {
+                    const float2 av2 = reinterpret_cast<const float2*>(P.xa)[rb];
+                    x.z = av2.x; x.w = av2.y;
+                }
+                return x;
+            };
+            auto h1_scaled = [&](const float4& wv, float bb, const float4& x) -> float {
+                float h = fmaf(wv.x, x.x, bb);
+                h = fmaf(wv.y, x.y, h);
+                if (four) {
+                    h = fmaf(wv.z, x.z, h);
+                    h = fmaf(wv.w, x.w, h);
+                }
+                return fminf(fmaxf(h, 0.f), 60000.0f);
+            };
+            float h2n[8];                                                // prefetched h2 column values of the NEXT chunk
             auto prefetch = [&](int c) {
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
                     const int64_t ra = (int64_t)c * KCH + kc * 8 + e;
                     h2n[e] = ra < rows ? P.h2[ra * H + mcol] : 0.f;
-                    const int64_t rb0 = (int64_t)c * KCH + kcB0 * 8 + e, rb1 = (int64_t)c * KCH + kcB1 * 8 + e;
-                    h1n[0][e] = rb0 < rows ? P.B[rb0 * H + nB0] : 0.f;
-                    h1n[1][e] = rb1 < rows ? P.B[rb1 * H + nB1] : 0.f;
                 }
             };
             prefetch(0);
             for (int c = 0; c < n_chunks; ++c) {
                 const int stage = c % NSTAGE;
                 const int64_t r0 = (int64_t)c * KCH + kc * 8;
-                float h2c[8], h1c[2][8];
+                float h2c[8];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) { h2c[e] = h2n[e]; h1c[0][e] = h1n[0][e]; h1c[1][e] = h1n[1][e]; }
+                for (int e = 0; e < 8; ++e) h2c[e] = h2n[e];
                 if (c + 1 < n_chunks) prefetch(c + 1);                   // in flight while this chunk is converted
+                uint4 ahi, alo, bhi[2], blo[2];
+                {
+                    float bv0[8], bv1[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const int64_t rb0 = (int64_t)c * KCH + kcB0 * 8 + e, rb1 = (int64_t)c * KCH + kcB1 * 8 + e;
+                        bv0[e] = rb0 < rows ? h1_scaled(w1B0, b1B0, row_x(rb0)) : 0.f;
+                        bv1[e] = rb1 < rows ? h1_scaled(w1B1, b1B1, row_x(rb1)) : 0.f;
+                    }
+                    split8(bv0, &bhi[0], &blo[0]);
+                    split8(bv1, &bhi[1], &blo[1]);
+                }
                 float av[8];
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
@@ -848,15 +925,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const __grid_cons
                     }
                     av[e] = v;
                 }
-                uint4 ahi, alo, bhi[2], blo[2];
                 split8(av, &ahi, &alo);
-#pragma unroll
-                for (int u = 0; u < 2; ++u) {
-                    float bv[8];
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) bv[e] = fminf(h1c[u][e] * SA, 60000.0f);
-                    split8(bv, &bhi[u], &blo[u]);
-                }
                 mbar_wait(smem_u32(&S.empty[stage]), ((c / NSTAGE) & 1) ^ 1);
                 unsigned char* a_hi = S.stage[stage];
                 unsigned char* b_hi = a_hi + 2 * A_IMG;

@@ -64,10 +64,9 @@ __device__ __forceinline__ bool maze_touch(const EnvParams& P, double x, double 
 // Speculative chunks: v starts at 0 and v <- c_a*v + fb keeps the sign of fb, so every coordinate moves
 // MONOTONICALLY during one env step (rounding is monotone).  The positions tested inside a chunk of MAZE_CHUNK
 // substeps therefore lie in the box spanned by the chunk's first and last position.  A chunk is integrated
-// test-free; only if that box comes within R + 2e-6 of a solid (maze_may_touch) the lane rewinds and replays the
-// chunk with the exact per-substep test.  A lane replays the chunk in which it touches (plus, rarely, chunks
-// spent within 2e-6 of a solid without touching), so all 32 envs of a warp run the same 500-substep schedule
-// instead of serialising divergent test paths.
+// test-free; only if that box comes within R + 2e-6 of a solid (maze_may_touch) the lane runs the exact per-substep
+// test on the chunk's stored pre-integration positions (plus, rarely, chunks spent within 2e-6 of a solid without
+// touching), so all 32 envs of a warp run the same 500-substep schedule instead of serialising divergent test paths.
 constexpr int MAZE_CHUNK = 10;
 // Conservative pre-test in fp32 (FMA/ALU pipes, the fp64 pipe is the busy one): can ANY point of the box
 // [xl,xh]x[yl,yh] touch a solid?  Planes: threshold + 1e-6.  Walls: the distance from the box to the rectangle
@@ -103,35 +102,41 @@ __device__ __forceinline__ void maze_substeps_warp(const EnvParams& P, bool idle
     const int nsub = P.cfg.maze_substeps;
     double vx = 0.0, vy = 0.0;
     bool frozen = idle;  // idle lanes (beyond n) and lanes in contact do not move
-    for (int k = 0; k < nsub; k += MAZE_CHUNK) {
-        const int c = min(MAZE_CHUNK, nsub - k);
-        const double sx = x, sy = y, svx = vx, svy = vy;
-        bool may = false;
-        if (!frozen) {
-            if (c == MAZE_CHUNK) {
+    int k = 0;
+    // full chunks: integrate test-free and KEEP the MAZE_CHUNK pre-integration positions (registers: the loop is fully
+    // unrolled, every position is a distinct value anyway).  A lane whose chunk box can touch a solid runs the exact
+    // fp64 test on the stored positions -- independent tests, no re-integration, no dependent chain -- and freezes at the
+    // first one that touches.  Frozen lanes compute along (their results are discarded by selects, not by branches).
+    for (; k + MAZE_CHUNK <= nsub; k += MAZE_CHUNK) {
+        double px[MAZE_CHUNK], py[MAZE_CHUNK];
+        double nx = x, ny = y;
 #pragma unroll
-                for (int j = 0; j < MAZE_CHUNK; ++j) maze_integrate(P, fbx, fby, x, y, vx, vy);
-            } else {
-                for (int j = 0; j < c; ++j) maze_integrate(P, fbx, fby, x, y, vx, vy);
-            }
-            const float fx0 = (float)sx, fx1 = (float)x, fy0 = (float)sy, fy1 = (float)y;
-            may = maze_may_touch(P, fminf(fx0, fx1), fmaxf(fx0, fx1), fminf(fy0, fy1), fmaxf(fy0, fy1));
+        for (int j = 0; j < MAZE_CHUNK; ++j) {
+            px[j] = nx; py[j] = ny;
+            maze_integrate(P, fbx, fby, nx, ny, vx, vy);
         }
+        const float fx0 = (float)x, fx1 = (float)nx, fy0 = (float)y, fy1 = (float)ny;
+        const bool may = !frozen && maze_may_touch(P, fminf(fx0, fx1), fmaxf(fx0, fx1), fminf(fy0, fy1), fmaxf(fy0, fy1));
+        bool hit = false;
         if (__any_sync(0xffffffffu, may)) {
-            if (may) {  // rewind, replay the chunk with the exact test before every substep
-                x = sx; y = sy; vx = svx; vy = svy;
-                for (int j = 0; j < c; ++j) {
-                    if (maze_touch(P, x, y)) {
-                        frozen = true;
-                        contact = true;
-                        break;
-                    }
-                    maze_integrate(P, fbx, fby, x, y, vx, vy);
-                }
+            if (may) {
+                double hx = 0.0, hy = 0.0;
+#pragma unroll
+                for (int j = MAZE_CHUNK - 1; j >= 0; --j)   // descending: the LOWEST touching substep wins
+                    if (maze_touch(P, px[j], py[j])) { hit = true; hx = px[j]; hy = py[j]; }
+                if (hit) { nx = hx; ny = hy; }
             }
-            if (__all_sync(0xffffffffu, frozen)) break;
         }
+        if (!frozen) { x = nx; y = ny; }
+        if (hit) { frozen = true; contact = true; }
+        if (__all_sync(0xffffffffu, frozen)) return;
     }
+    // remainder (substep counts that are not a multiple of the chunk: tests only): exact test before every substep
+    if (!frozen)
+        for (; k < nsub; ++k) {
+            if (maze_touch(P, x, y)) { contact = true; break; }
+            maze_integrate(P, fbx, fby, x, y, vx, vy);
+        }
 }
 
 __device__ __forceinline__ void reset_state(const EnvParams& P, int64_t i, const double* draws, int64_t n,
