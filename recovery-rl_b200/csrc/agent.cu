@@ -593,7 +593,8 @@ struct AdamTileArgs {
     AdamW2 w2[4];
     int n_w2;
     int64_t seg_off[24], seg_cnt[24];   // the other tensors of the stepped nets
-    int n_seg, n_flat;                  // flat CTAs
+    int n_seg, n_flat;                  // flat CTAs: one per 256 elements of a segment (a segment is a latency chain)
+    unsigned char flat_seg[64], flat_blk[64];
     int64_t tgt_src_off, tgt_off, tgt_count;
     float tau;
     int upd_counter, interval;
@@ -715,31 +716,31 @@ __global__ void __launch_bounds__(kThreads) adam_tile_kernel(const __grid_consta
         if (do_tgt) write_tile_images(A.arena, W.tgt, ttile, n0, k0);
     } else {
         const int fb = blockIdx.x - n_tile_ctas;
-        for (int sg = 0; sg < A.n_seg; ++sg) {
-            for (int64_t i = (int64_t)fb * kThreads + t; i < A.seg_cnt[sg]; i += (int64_t)A.n_flat * kThreads) {
-                const int64_t o = A.seg_off[sg] + i;
-                float p = A.arena[o];
-                float g;
-                if (A.n_peer > 0) {
-                    float gs[8];
+        const int sg = A.flat_seg[fb];
+        const int64_t i = (int64_t)A.flat_blk[fb] * kThreads + t;
+        if (i < A.seg_cnt[sg]) {
+            const int64_t o = A.seg_off[sg] + i;
+            float p = A.arena[o];
+            float g;
+            if (A.n_peer > 0) {
+                float gs[8];
 #pragma unroll
-                    for (int r = 0; r < 8; ++r) gs[r] = r < A.n_peer ? __ldcv(A.peer[r] + A.grad_off + o) : 0.f;
-                    g = gs[0];
+                for (int r = 0; r < 8; ++r) gs[r] = r < A.n_peer ? __ldcv(A.peer[r] + A.grad_off + o) : 0.f;
+                g = gs[0];
 #pragma unroll
-                    for (int r = 1; r < 8; ++r) g += gs[r];
-                } else {
-                    g = A.arena[A.grad_off + o];
-                }
-                float m = A.arena[A.m_off + o], v = A.arena[A.v_off + o];
-                adam_elem(p, g * A.grad_scale, m, v, A.b1, A.b2, A.eps, step_size, bc2s);
-                A.arena[A.m_off + o] = m;
-                A.arena[A.v_off + o] = v;
-                A.arena[o] = p;
-                if (polyak) {
-                    const int64_t d0 = o - A.tgt_src_off;
-                    if (d0 >= 0 && d0 < A.tgt_count) A.arena[A.tgt_off + d0] = A.arena[A.tgt_off + d0] * omt + p * A.tau;
-                }
+                for (int r = 1; r < 8; ++r) g += gs[r];
+            } else {
+                g = A.arena[A.grad_off + o];
             }
+            float m = A.arena[A.m_off + o], v = A.arena[A.v_off + o];
+            const int64_t d0 = o - A.tgt_src_off;
+            const bool tg = polyak && d0 >= 0 && d0 < A.tgt_count;
+            const float tp = tg ? A.arena[A.tgt_off + d0] : 0.f;
+            adam_elem(p, g * A.grad_scale, m, v, A.b1, A.b2, A.eps, step_size, bc2s);
+            A.arena[A.m_off + o] = m;
+            A.arena[A.v_off + o] = v;
+            A.arena[o] = p;
+            if (tg) A.arena[A.tgt_off + d0] = tp * omt + p * A.tau;
         }
     }
     // every CTA has read the counters above; the last one to arrive bumps them
@@ -1045,7 +1046,13 @@ int launch_adam_tiled(const rrl_agent_config_t* cfg, const Layout& L, float* are
     }
     for (int i = 0; i < n_bump && i < 3; ++i) A.bump[i] = bump[i];
     A.n_bump = n_bump < 3 ? n_bump : 3;
-    A.n_flat = 4;
+    for (int sg = 0; sg < A.n_seg; ++sg)
+        for (int64_t b = 0; b * kThreads < A.seg_cnt[sg]; ++b) {
+            if (A.n_flat >= 64) { rrl_set_error("launch_adam_tiled: too many flat blocks"); return -2; }
+            A.flat_seg[A.n_flat] = (unsigned char)sg;
+            A.flat_blk[A.n_flat] = (unsigned char)b;
+            ++A.n_flat;
+        }
     adam_tile_kernel<<<A.n_w2 * 64 + A.n_flat, kThreads, 0, st>>>(A);
     RRL_CHECK_LAUNCH();
     return 0;
@@ -1080,6 +1087,13 @@ inline uint32_t* slot_bits(const Layout& L, float* arena, int slot) { return rei
 // layer 1 of the pass + its inputs + the sign bits of h2 (tcgen05 backward: h1 / relu' are recomputed, never loaded)
 inline void bwd_inputs(GemmPass& p, const HeadW& w, const float* xs, const float* xa, const Layout& L, float* arena, int slot) {
     p.W1 = w.W1; p.b1 = w.b1; p.n_in = w.n_in; p.xs = xs; p.xa = xa; p.h2bits = slot_bits(L, arena, slot);
+}
+// fused layer-1 backward of a DATA pass (tcgen05 path, use_tensor_cores 2): weight gradients (gW1, gb1) or d(action) (dxa);
+// dh1 is then not stored.  The slot's dh2 region holds the cross-tile ticket (word 0) and the per-tile partial sums.
+inline void fuse_l1(GemmPass& p, float* gW1, float* gb1, float* dxa, const Layout& L, float* arena, int slot) {
+    p.gW1 = gW1; p.gb1 = gb1; p.dxa = dxa; p.C = nullptr;
+    p.l1ticket = reinterpret_cast<int*>(arena + L.dh2[slot]);
+    p.l1part = arena + L.dh2[slot] + 64;
 }
 
 // slot >= 0: activations are kept for the backward pass; weight_pass: the backward also has a WEIGHT pass for it
@@ -1397,10 +1411,8 @@ extern "C" int rrl_sac_backward(const rrl_agent_config_t* cfg, float* arena, con
             p.gW3a = g.W3a; p.gb3a = g.b3a; p.gb2 = g.b2;
             bwd_inputs(p, w, s, a, L, arena, q);
         }
-        const int mt = (int)((R > H ? R : H) / 32);
-        { int rc = launch_gemm(G, n, mt, R, cfg->use_tensor_cores, st); if (rc) return rc; }
-    }
-    {  // layer-1 backward: weight grads for (s, a); d/d(pi) for (s, pi)
+        // layer-1 backward: weight grads for (s, a); d/d(pi) for (s, pi) -- then the policy-sample backward (needs d(action)
+        // of every pass).  Fused (use_tensor_cores 2): epilogue + tail of the GEMM launch; else launches of their own.
         L1BwdArgs A;
         memset(&A, 0, sizeof(A));
         A.rows_ptr = rows_ptr;
@@ -1412,27 +1424,32 @@ extern "C" int rrl_sac_backward(const rrl_agent_config_t* cfg, float* arena, con
             p.dh1 = arena + L.dh1[slot[q]]; p.xs = s; p.xa = q < 2 ? a : R2(R2_PI); p.W1 = w.W1; p.n_in = 4;
             if (q < 2) { p.gW1 = g.W1; p.gb1 = g.b1; }
             else p.dxa = dxa[q];
+            if (fuse) fuse_l1(G.p[q], p.gW1, p.gb1, p.dxa, L, arena, slot[q]);
         }
-        // policy-sample backward (needs d(action) of every pass): tail of this launch (fused) or its own launch
+        TailArgs T;
+        memset(&T, 0, sizeof(T));
+        T.ticket = counters + RRL_C_TICKET2;
         if (!det) {
-            GaussBwdArgs& T = A.tail.gauss;
-            T.raw = R4(R4_RAW_POL); T.eps = R2(R2_EPS_CUR); T.dxa1 = R2(R2_DPI); T.dxa2 = R2(R2_DPI_B);
-            if (dgd) { T.dxa3 = R2(R2_DPI_S1); T.dxa4 = R2(R2_DPI_S2); }
-            T.draw = R4(R4_DRAW_POL); T.scal = scal; T.sp = sp; T.rows_ptr = rows_ptr;
-            if (fuse) A.tail.kind = TAIL_GAUSS_BWD;
+            GaussBwdArgs& B = T.gauss;
+            B.raw = R4(R4_RAW_POL); B.eps = R2(R2_EPS_CUR); B.dxa1 = R2(R2_DPI); B.dxa2 = R2(R2_DPI_B);
+            if (dgd) { B.dxa3 = R2(R2_DPI_S1); B.dxa4 = R2(R2_DPI_S2); }
+            B.draw = R4(R4_DRAW_POL); B.scal = scal; B.sp = sp; B.rows_ptr = rows_ptr;
+            T.kind = TAIL_GAUSS_BWD;
         } else {  // DeterministicPolicy: a = tanh(raw)*scale + bias + noise
-            StochBwdArgs& T = A.tail.stoch;
-            T.raw = R4(R4_RAW_POL); T.eps = R2(R2_EPS_CUR); T.dxa1 = R2(R2_DPI); T.dxa2 = R2(R2_DPI_B);
-            if (dgd) { T.dxa3 = R2(R2_DPI_S1); T.dxa4 = R2(R2_DPI_S2); }
-            T.log_std = pw.log_std; T.draw = R4(R4_DRAW_POL); T.g_log_std = nullptr; T.sp = sp; T.rows_ptr = rows_ptr;
-            if (fuse) A.tail.kind = TAIL_STOCH_BWD;
+            StochBwdArgs& B = T.stoch;
+            B.raw = R4(R4_RAW_POL); B.eps = R2(R2_EPS_CUR); B.dxa1 = R2(R2_DPI); B.dxa2 = R2(R2_DPI_B);
+            if (dgd) { B.dxa3 = R2(R2_DPI_S1); B.dxa4 = R2(R2_DPI_S2); }
+            B.log_std = pw.log_std; B.draw = R4(R4_DRAW_POL); B.g_log_std = nullptr; B.sp = sp; B.rows_ptr = rows_ptr;
+            T.kind = TAIL_STOCH_BWD;
         }
-        A.tail.ticket = counters + RRL_C_TICKET2;
-        layer1_backward_kernel<<<dim3(kL1ColBlocks + kL1RowBlocks, nq), kThreads, 0, st>>>(A);
-        RRL_CHECK_LAUNCH();
+        if (fuse) G.tail = T;
+        const int mt = (int)((R > H ? R : H) / 32);
+        { int rc = launch_gemm(G, n, mt, R, cfg->use_tensor_cores, st); if (rc) return rc; }
         if (!fuse) {
-            if (!det) gauss_backward_kernel<<<(unsigned)((R + kThreads - 1) / kThreads), kThreads, 0, st>>>(A.tail.gauss);
-            else stoch_backward_kernel<<<1, kThreads, 0, st>>>(A.tail.stoch);
+            layer1_backward_kernel<<<dim3(kL1ColBlocks + kL1RowBlocks, nq), kThreads, 0, st>>>(A);
+            RRL_CHECK_LAUNCH();
+            if (!det) gauss_backward_kernel<<<(unsigned)((R + kThreads - 1) / kThreads), kThreads, 0, st>>>(T.gauss);
+            else stoch_backward_kernel<<<1, kThreads, 0, st>>>(T.stoch);
             RRL_CHECK_LAUNCH();
         }
     }
@@ -1450,10 +1467,11 @@ extern "C" int rrl_sac_backward(const rrl_agent_config_t* cfg, float* arena, con
         G.p[1].B = arena + L.h1[4]; G.p[1].k_is_rows = 1; G.p[1].C = pg.W2;
         G.p[1].gW3a = pg.W3a; G.p[1].gb3a = pg.b3a; G.p[1].gb2 = pg.b2;
         if (!det) { G.p[1].gW3b = pg.W3b; G.p[1].gb3b = pg.b3b; }
+        if (fuse) fuse_l1(G.p[0], pg.W1, pg.b1, nullptr, L, arena, 4);
         const int mt = (int)((R > H ? R : H) / 32);
         { int rc = launch_gemm(G, 2, mt, R, cfg->use_tensor_cores, st); if (rc) return rc; }
     }
-    {
+    if (!fuse) {
         L1BwdArgs A;
         memset(&A, 0, sizeof(A));
         A.rows_ptr = rows_ptr;
@@ -1564,11 +1582,12 @@ extern "C" int rrl_qrisk_backward(const rrl_agent_config_t* cfg, float* arena, c
             ww = p;
             ww.B = arena + L.h1[q]; ww.k_is_rows = 1; ww.mask = nullptr; ww.C = g.W2;
             ww.gW3a = g.W3a; ww.gb3a = g.b3a; ww.gb2 = g.b2;
+            if (fuse) fuse_l1(p, g.W1, g.b1, nullptr, L, arena, q);
         }
         const int mt = (int)((R > H ? R : H) / 32);
         { int rc = launch_gemm(G, 4, mt, R, cfg->use_tensor_cores, st); if (rc) return rc; }
     }
-    {
+    if (!fuse) {
         L1BwdArgs A;
         memset(&A, 0, sizeof(A));
         A.rows_ptr = rows_ptr;
@@ -1655,41 +1674,42 @@ extern "C" int rrl_recovery_backward(const rrl_agent_config_t* cfg, float* arena
     const HeadW c1 = head_w(L, arena, RRL_NET_QRISK, 0), c2 = head_w(L, arena, RRL_NET_QRISK, 1);
     const HeadW pw = head_w(L, arena, RRL_NET_RECOVERY, 0);
     const HeadG pg = head_g(L, arena, RRL_NET_RECOVERY, 0);
-    {  // back through the (post-step) safety critic into the action: head backward + dh1
+    {  // back through the (post-step) safety critic into the action: head backward + dh1, layer-1 backward (d(action)) and
+       // the StochasticPolicy.sample backward -- fused into the GEMM launch (use_tensor_cores 2) or launches of their own
         GemmArgs G;
         memset(&G, 0, sizeof(G));
         G.rows_ptr = rows_ptr;
+        L1BwdArgs A;
+        memset(&A, 0, sizeof(A));
+        A.rows_ptr = rows_ptr;
         for (int q = 0; q < 2; ++q) {
             GemmPass& p = G.p[q];
             p.dout = q ? RA(RA_REC_DQ2) : RA(RA_REC_DQ1); p.stride = 1; p.n_out = 1; p.na = 1; p.W3a = (q ? c2 : c1).W3a;
             p.h2 = arena + L.h2[2 + q]; p.B = (q ? c2 : c1).W2; p.tc_imgT = (q ? c2 : c1).tc_imgT;
             p.mask = arena + L.h1[2 + q]; p.C = arena + L.dh1[2 + q];
             bwd_inputs(p, q ? c2 : c1, s, R2(R2_REC_PI), L, arena, 2 + q);
+            L1BwdPass& l = A.p[q];
+            l.dh1 = arena + L.dh1[2 + q]; l.xs = s; l.xa = R2(R2_REC_PI); l.W1 = (q ? c2 : c1).W1; l.n_in = 4;
+            l.dxa = q ? R2(R2_DPI) : R2(R2_REC_DPI);
+            if (fuse) fuse_l1(p, nullptr, nullptr, l.dxa, L, arena, 2 + q);
         }
+        TailArgs T;
+        memset(&T, 0, sizeof(T));
+        T.ticket = counters + RRL_C_TICKET2;
+        T.kind = TAIL_STOCH_BWD;
+        StochBwdArgs& B = T.stoch;
+        B.raw = R4(R4_RAW_REC); B.eps = R2(R2_REC_EPS); B.dxa1 = R2(R2_REC_DPI); B.dxa2 = R2(R2_DPI);
+        B.log_std = pw.log_std; B.draw = R4(R4_DRAW_REC); B.g_log_std = pg.log_std; B.sp = sp; B.rows_ptr = rows_ptr;
+        if (fuse) G.tail = T;
         { int rc = launch_gemm(G, 2, (int)(R / 32), R, cfg->use_tensor_cores, st); if (rc) return rc; }
-    }
-    {
-        L1BwdArgs A;
-        memset(&A, 0, sizeof(A));
-        A.rows_ptr = rows_ptr;
-        for (int q = 0; q < 2; ++q) {
-            L1BwdPass& p = A.p[q];
-            p.dh1 = arena + L.dh1[2 + q]; p.xs = s; p.xa = R2(R2_REC_PI); p.W1 = (q ? c2 : c1).W1; p.n_in = 4;
-            p.dxa = q ? R2(R2_DPI) : R2(R2_REC_DPI);
-        }
-        StochBwdArgs& T = A.tail.stoch;   // StochasticPolicy.sample backward: tail of this launch (fused) or its own launch
-        T.raw = R4(R4_RAW_REC); T.eps = R2(R2_REC_EPS); T.dxa1 = R2(R2_REC_DPI); T.dxa2 = R2(R2_DPI);
-        T.log_std = pw.log_std; T.draw = R4(R4_DRAW_REC); T.g_log_std = pg.log_std; T.sp = sp; T.rows_ptr = rows_ptr;
-        A.tail.ticket = counters + RRL_C_TICKET2;
-        if (fuse) A.tail.kind = TAIL_STOCH_BWD;
-        layer1_backward_kernel<<<dim3(kL1ColBlocks + kL1RowBlocks, 2), kThreads, 0, st>>>(A);
-        RRL_CHECK_LAUNCH();
         if (!fuse) {
-            stoch_backward_kernel<<<1, kThreads, 0, st>>>(T);
+            layer1_backward_kernel<<<dim3(kL1ColBlocks + kL1RowBlocks, 2), kThreads, 0, st>>>(A);
+            RRL_CHECK_LAUNCH();
+            stoch_backward_kernel<<<1, kThreads, 0, st>>>(B);
             RRL_CHECK_LAUNCH();
         }
     }
-    {  // recovery policy: head backward + dh1 + gW2 / gW3 / gb3 / gb2
+    {  // recovery policy: head backward + dh1 + gW2 / gW3 / gb3 / gb2 (+ layer-1 weight gradients when fused)
         GemmArgs G;
         memset(&G, 0, sizeof(G));
         G.rows_ptr = rows_ptr;
@@ -1701,10 +1721,11 @@ extern "C" int rrl_recovery_backward(const rrl_agent_config_t* cfg, float* arena
         G.p[0].B = pw.W2; G.p[0].tc_imgT = pw.tc_imgT; G.p[0].mask = arena + L.h1[4]; G.p[0].C = arena + L.dh1[4];
         G.p[1].B = arena + L.h1[4]; G.p[1].k_is_rows = 1; G.p[1].C = pg.W2;
         G.p[1].gW3a = pg.W3a; G.p[1].gb3a = pg.b3a; G.p[1].gb2 = pg.b2;
+        if (fuse) fuse_l1(G.p[0], pg.W1, pg.b1, nullptr, L, arena, 4);
         const int mt = (int)((R > H ? R : H) / 32);
         { int rc = launch_gemm(G, 2, mt, R, cfg->use_tensor_cores, st); if (rc) return rc; }
     }
-    {
+    if (!fuse) {
         L1BwdArgs A;
         memset(&A, 0, sizeof(A));
         A.rows_ptr = rows_ptr;

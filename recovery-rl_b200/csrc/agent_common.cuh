@@ -263,12 +263,18 @@ struct GemmPass {
     const float *W1, *b1, *xs, *xa;
     int n_in;
     const uint32_t* h2bits;
+    // tcgen05 path, fused layer-1 backward (DATA passes; C may then be NULL: dh1 is consumed in the epilogue, never stored):
+    //   gW1 / gb1 (weight gradients of layer 1; column sums over the rows, reduced across the row tiles through l1part by
+    //   the last tile to arrive at l1ticket) or dxa ([rows][2], gradient w.r.t. the action inputs); never both
+    float *gW1, *gb1, *dxa, *l1part;
+    int* l1ticket;
 };
 struct GemmArgs {
     GemmPass p[8];
     const int64_t* rows_ptr;
     int n_pass;
     int use_tc;
+    TailArgs tail;      // stage run by the last CTA of the launch (update_tails.cuh); kind 0: none
 };
 int bwd_tc_launch(const GemmArgs& G, int64_t max_rows, cudaStream_t st);
 

@@ -551,9 +551,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
                 }
             }
             if (P.h2bits && live) {   // relu'(h2) for the backward DATA producers: one word per 32 columns
-                uint32_t mb = 0u;
+                uint32_t mb = 0u;   // v >= +0 after the ReLU: non-zero bit pattern <=> h2 > 0
 #pragma unroll
-                for (int j = 0; j < 32; ++j) mb |= v[j] > 0.f ? (1u << j) : 0u;
+                for (int j = 31; j >= 0; --j) mb = (mb << 1) + min(__float_as_uint(v[j]), 1u);
                 P.h2bits[row * (H / 32) + q * 2 + cc] = mb;
             }
             if (P.h2 && P.keep_h2)
@@ -632,6 +632,8 @@ struct BwdTcSmem {
     float W1[H][4];                 // layer 1 of the pass, pre-multiplied by SA like the forward kernel (h1 is recomputed)
     float b1[H];
     float4 xin[kDoutRows];          // the pass's inputs (s, a): rows of this tile (DATA) / of the whole batch (WEIGHT)
+    float W1z[H], W1w[H];           // DATA: the action columns of W1 (* SA), component-major (conflict-free epilogue reads)
+    uint32_t h1b[TM][H / 32];       // DATA: sign bits of the tile's h1 (relu' mask of the epilogue), computed by the producers
     float w3[4][H];
     float red[kProd][6];            // WEIGHT: per-thread partial sums (gb2, gW3[0..3])
     float4 douts[kDoutRows];        // WEIGHT: dout of the whole batch (rows <= kDoutRows), zero-padded to 4 outputs
@@ -656,11 +658,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const __grid_cons
     TSTAMP(0);
     BwdTcSmem& S = *reinterpret_cast<BwdTcSmem*>(smem_raw);
     const int64_t rows = *G.rows_ptr;
-    if (rows <= 0) return;
     const GemmPass& P = G.p[blockIdx.y];
     const bool weight = P.k_is_rows != 0;
     const int tile = blockIdx.x;
-    if (weight ? (tile >= H / TM) : ((int64_t)tile * TM >= rows)) return;   // uniform exit
+    if (rows <= 0 || (weight ? (tile >= H / TM) : ((int64_t)tile * TM >= rows))) {   // uniform exit
+        run_tail(G.tail);
+        return;
+    }
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
     const int n_chunks = weight ? (int)((rows + KCH - 1) / KCH) : NCHUNK;
 
@@ -679,6 +683,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const __grid_cons
         }
         w1.x *= SA; w1.y *= SA; w1.z *= SA; w1.w *= SA;       // exact (power of two): same values as fwd_tc_kernel
         *reinterpret_cast<float4*>(S.W1[k]) = w1;
+        S.W1z[k] = w1.z; S.W1w[k] = w1.w;
         S.b1[k] = P.b1[k] * SA;
     }
     {   // inputs of the rows this CTA touches: its 128-row tile (DATA) or the whole batch (WEIGHT, if it fits)
@@ -795,12 +800,43 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const __grid_cons
                 fence_proxy_async();
                 mbar_arrive_warp(smem_u32(&S.full[stage]));
             }
+            {   // relu'(h1) of the tile while the MMAs drain: the sign of layer 1 recomputed from the row's inputs with the
+                // forward kernel's FMA chain; thread (r, q) covers columns [64 q, 64 q + 64) of its row
+                const float4 x = S.xin[r];
+#pragma unroll
+                for (int wd = 0; wd < 2; ++wd) {
+                    uint32_t mb = 0u;
+#pragma unroll 8
+                    for (int j = 31; j >= 0; --j) {
+                        const int k = q * 64 + wd * 32 + j;
+                        const float4 wv = *reinterpret_cast<const float4*>(S.W1[k]);
+                        float h = fmaf(wv.x, x.x, S.b1[k]);
+                        h = fmaf(wv.y, x.y, h);
+                        if (four) {
+                            h = fmaf(wv.z, x.z, h);
+                            h = fmaf(wv.w, x.w, h);
+                        }
+                        mb = (mb << 1) + (h > 0.f ? 1u : 0u);
+                    }
+                    S.h1b[r][q * 2 + wd] = mb;
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(kProd) : "memory");
+            }
             TSTAMP(2);
             mbar_wait(smem_u32(&S.acc_full), 0);
             TSTAMP(3);
             tc_fence_after();
             const float inv = 1.0f / (sc * SB);
             float* scratch = reinterpret_cast<float*>(S.stage) + warp * kXposeFloats;   // stages are free after acc_full
+            // fused layer-1 backward (layer1_backward_kernel's arithmetic on the tile, dh1 never leaves the SM):
+            //   colpart [4 row quadrants][H][5]  per-quadrant column sums  sum_r dh1[r][k] * {x0, x1, x2, x3, 1}
+            //   dxapart [4 column quarters][TM]  per-quarter row sums      sum_k dh1[r][k] * W1[k][2 | 3]
+            float* colpart = reinterpret_cast<float*>(S.stage) + kProdWarps * kXposeFloats;
+            float2* dxapart = reinterpret_cast<float2*>(colpart + 4 * H * 5);
+            const bool want_gw = P.gW1 != nullptr, want_dxa = P.dxa != nullptr;
+            float acc[20];   // want_dxa: [i][2] over the thread's 8 rows; want_gw: [column j][5], restarted per 32-column block
+#pragma unroll
+            for (int u = 0; u < 20; ++u) acc[u] = 0.f;
             const int64_t wrow0 = (int64_t)tile * TM + (warp & 3) * 32;
 #pragma unroll 1
             for (int cc = 0; cc < 2; ++cc) {
@@ -810,29 +846,104 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const __grid_cons
                 tmem_ld_wait();
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] *= inv;      // this row's scale
-                warp_block_rows(scratch, v, lane, [&](int rl, int c4, float4 g) {
+                warp_block_rows_i(scratch, v, lane, [&](int i, int rl, int c4, float4 g) {
                     const int64_t rr = wrow0 + rl;
-                    if (rr < rows) {
-                        // relu'(h1): the sign of layer 1 recomputed from the row's inputs (same FMA chain as the forward)
-                        const float4 x = S.xin[(warp & 3) * 32 + rl];
-                        float gg[4] = {g.x, g.y, g.z, g.w};
+                    const bool ok = rr < rows;
+                    const int lr = (warp & 3) * 32 + rl;
+                    const uint32_t hbits = ok ? (S.h1b[lr][col0 >> 5] >> (4 * c4)) : 0u;   // relu'(h1) of the 4 columns
+                    const float4 x = S.xin[lr];
+                    float gg[4] = {g.x, g.y, g.z, g.w};
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const int k = col0 + 4 * c4 + i;
-                            const float4 wv = *reinterpret_cast<const float4*>(S.W1[k]);
-                            float h = fmaf(wv.x, x.x, S.b1[k]);
-                            h = fmaf(wv.y, x.y, h);
-                            if (four) {
-                                h = fmaf(wv.z, x.z, h);
-                                h = fmaf(wv.w, x.w, h);
-                            }
-                            gg[i] = h > 0.f ? gg[i] : 0.f;
+                    for (int j = 0; j < 4; ++j) {
+                        const int k = col0 + 4 * c4 + j;
+                        gg[j] = ((hbits >> j) & 1u) ? gg[j] : 0.f;
+                        if (want_dxa) {   // W1 is staged pre-multiplied by SA: undone once per row below
+                            acc[2 * i] = fmaf(gg[j], S.W1z[k], acc[2 * i]);
+                            acc[2 * i + 1] = fmaf(gg[j], S.W1w[k], acc[2 * i + 1]);
                         }
-                        *reinterpret_cast<float4*>(P.C + rr * H + col0 + 4 * c4) = make_float4(gg[0], gg[1], gg[2], gg[3]);
+                        if (want_gw) {
+                            acc[5 * j + 0] = fmaf(gg[j], x.x, acc[5 * j + 0]);
+                            acc[5 * j + 1] = fmaf(gg[j], x.y, acc[5 * j + 1]);
+                            acc[5 * j + 2] = fmaf(gg[j], x.z, acc[5 * j + 2]);
+                            acc[5 * j + 3] = fmaf(gg[j], x.w, acc[5 * j + 3]);
+                            acc[5 * j + 4] += gg[j];
+                        }
                     }
+                    if (P.C && ok) *reinterpret_cast<float4*>(P.C + rr * H + col0 + 4 * c4) = make_float4(gg[0], gg[1], gg[2], gg[3]);
                 });
+                if (want_gw) {   // the four row groups of the warp (lane >> 3), then one writer per column
+#pragma unroll
+                    for (int u = 0; u < 20; ++u) {
+                        float a = acc[u];
+                        a += __shfl_xor_sync(0xffffffffu, a, 8);
+                        a += __shfl_xor_sync(0xffffffffu, a, 16);
+                        if (lane < 8) colpart[((warp & 3) * H + col0 + 4 * lane + u / 5) * 5 + u % 5] = a;
+                        acc[u] = 0.f;
+                    }
+                }
+            }
+            if (want_dxa) {      // the eight column groups of the warp (lane & 7), then one writer per row
+#pragma unroll
+                for (int u = 0; u < 16; ++u) {
+                    float a = acc[u];
+                    a += __shfl_xor_sync(0xffffffffu, a, 1);
+                    a += __shfl_xor_sync(0xffffffffu, a, 2);
+                    a += __shfl_xor_sync(0xffffffffu, a, 4);
+                    acc[u] = a;
+                }
+                if ((lane & 7) == 0) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) dxapart[q * TM + (warp & 3) * 32 + i * 4 + (lane >> 3)] = make_float2(acc[2 * i], acc[2 * i + 1]);
+                }
             }
             tc_fence_before();
+            if (want_gw || want_dxa) {
+                asm volatile("bar.sync 1, %0;" ::"n"(kProd) : "memory");
+                if (want_dxa && t < TM) {
+                    const int64_t rr = (int64_t)tile * TM + t;
+                    const float2 p0 = dxapart[t], p1 = dxapart[TM + t], p2 = dxapart[2 * TM + t], p3 = dxapart[3 * TM + t];
+                    if (rr < rows)
+                        reinterpret_cast<float2*>(P.dxa)[rr] = make_float2(((p0.x + p1.x) + (p2.x + p3.x)) * (1.0f / SA),
+                                                                           ((p0.y + p1.y) + (p2.y + p3.y)) * (1.0f / SA));
+                }
+                if (want_gw) {
+                    const int n_tiles = (int)((rows + TM - 1) / TM);
+                    float s5[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+                    if (t < H) {
+#pragma unroll
+                        for (int u = 0; u < 5; ++u)
+                            s5[u] = (colpart[(0 * H + t) * 5 + u] + colpart[(1 * H + t) * 5 + u]) +
+                                    (colpart[(2 * H + t) * 5 + u] + colpart[(3 * H + t) * 5 + u]);
+                    }
+                    bool writer = n_tiles == 1;
+                    if (n_tiles > 1) {   // partial sums of this tile -> global; the last tile to arrive adds them up in tile order
+                        if (t < H) {
+#pragma unroll
+                            for (int u = 0; u < 5; ++u) P.l1part[((size_t)tile * H + t) * 5 + u] = s5[u];
+                        }
+                        __threadfence();
+                        asm volatile("bar.sync 1, %0;" ::"n"(kProd) : "memory");
+                        if (t == 0) {
+                            const int arrived = atomicAdd(P.l1ticket, 1);
+                            S.red4[0][0] = (arrived == n_tiles - 1) ? 1.f : 0.f;
+                            if (arrived == n_tiles - 1) { *reinterpret_cast<volatile int*>(P.l1ticket) = 0; __threadfence(); }
+                        }
+                        asm volatile("bar.sync 1, %0;" ::"n"(kProd) : "memory");
+                        writer = S.red4[0][0] != 0.f;
+                        if (writer && t < H) {
+#pragma unroll
+                            for (int u = 0; u < 5; ++u) s5[u] = 0.f;
+                            for (int tl = 0; tl < n_tiles; ++tl)
+#pragma unroll
+                                for (int u = 0; u < 5; ++u) s5[u] += __ldcg(P.l1part + ((size_t)tl * H + t) * 5 + u);
+                        }
+                    }
+                    if (writer && t < H) {
+                        for (int u = 0; u < P.n_in; ++u) P.gW1[t * P.n_in + u] = s5[u];
+                        P.gb1[t] = s5[4];
+                    }
+                }
+            }
         } else {
             // ================= WEIGHT: thread (m, kc) stages A, threads (n, kc) x2 stage B =================
             const int m = t & (TM - 1), kc = t >> 7;             // A role: out unit m0 + m, core column kc (8 rows)
@@ -1029,6 +1140,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const __grid_cons
     __syncthreads();
     if (warp == kProd / 32) tmem_dealloc(tmem_base, 256);
     TSTAMP(5);
+    run_tail(G.tail);
     TLAUNCH_END(2);
 }
 

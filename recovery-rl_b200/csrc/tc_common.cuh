@@ -145,5 +145,20 @@ __device__ __forceinline__ void warp_block_rows(float* scratch, const float (&v)
     __syncwarp();
 }
 
+// the same, also handing the callback its compile-time step i (rows i * 4 + (lane >> 3)): f(i, row_in_block, c4, value)
+template <typename F>
+__device__ __forceinline__ void warp_block_rows_i(float* scratch, const float (&v)[32], int lane, F&& f) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<float4*>(scratch + lane * 36 + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int rl = i * 4 + (lane >> 3), c4 = lane & 7;
+        f(i, rl, c4, *reinterpret_cast<const float4*>(scratch + rl * 36 + 4 * c4));
+    }
+    __syncwarp();
+}
+
 }  // namespace tc
 }  // namespace rrl

@@ -279,8 +279,10 @@ class VecEngine(object):
         self._all_reduce(["recovery"])
         native.recovery_apply(cfg, ar, cn, peers=self._peers)
         nb = 1 if self.peer_arena is not None else 0           # peer barrier kernels
-        f = 1 if self.fused else 0                             # loss / sample-backward stages run as kernel tails
-        return (5 - f) + 1 + ((8 - 2 * f) if self.mf_recovery else 0) + 1 + 2 * nb     # kernels launched (gpu_launches bookkeeping)
+        # kernels launched (gpu_launches bookkeeping).  fused: the loss / sample-backward stages run as kernel tails and the
+        # layer-1 backward in the epilogue of the backward GEMM -> fwd, fwd, bwd [, bwd] per update
+        qr, rec = (3, 4) if self.fused else (5, 8)
+        return qr + 1 + (rec if self.mf_recovery else 0) + 1 + 2 * nb
 
     def qrisk_update(self, sample_cfg=None):
         return self._qr_sample(sample_cfg) + self._qr_compute()
@@ -302,7 +304,7 @@ class VecEngine(object):
             dist_utils.all_reduce_sum(f32[native.S_G_LOG_ALPHA:native.S_G_LOG_ALPHA + 1], self.pg)
             dist_utils.all_reduce_sum(f64[native.D_G_LOG_NU:native.D_G_LOG_LAMBDA + 1], self.pg)
         native.sac_apply(cfg, ar, cn, peers=self._peers)
-        return (6 if self.fused else 8) + 1 + (1 if self.scalar_algos else 0) + (1 if self.peer_arena is not None else 0)
+        return (4 if self.fused else 8) + 1 + (1 if self.scalar_algos else 0) + (1 if self.peer_arena is not None else 0)
 
     def sac_update(self):
         return self._sac_sample() + self._sac_compute()

@@ -129,6 +129,13 @@ def test_pipelined_host_steps_match_serial():
             got.append({k: v.clone() for k, v in b.collect(t - 1).items()})
     got.append({k: v.clone() for k, v in b.collect(len(inputs) - 2).items()})
     assert len(got) == len(want)
+    from recovery_rl import native
     for i, (g, w) in enumerate(zip(got, want)):
         for k in w:
-            assert torch.equal(g[k], w[k]), (i, k)
+            a, b = g[k].clone(), w[k].clone()
+            if k == "counters":          # the return sum is an fp64 atomicAdd over the env copies: order-dependent last bits
+                ra, rb = a[native.C_RETURN_SUM_BITS:native.C_RETURN_SUM_BITS + 1].view(torch.float64), \
+                    b[native.C_RETURN_SUM_BITS:native.C_RETURN_SUM_BITS + 1].view(torch.float64)
+                assert abs(float(ra) - float(rb)) <= 1e-9 * (1 + abs(float(rb))), (i, float(ra), float(rb))
+                a[native.C_RETURN_SUM_BITS] = b[native.C_RETURN_SUM_BITS] = 0
+            assert torch.equal(a, b), (i, k)
