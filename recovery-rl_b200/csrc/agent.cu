@@ -1083,10 +1083,12 @@ int launch_gemm(GemmArgs& G, int n_pass, int mt, int64_t max_rows, int use_tc, c
 }
 
 inline uint32_t* slot_bits(const Layout& L, float* arena, int slot) { return reinterpret_cast<uint32_t*>(arena + L.dh2t[slot]); }
+inline uint32_t* slot_bits1(const Layout& L, float* arena, int slot) { return slot_bits(L, arena, slot) + L.R * (H / 32); }
 
 // layer 1 of the pass + its inputs + the sign bits of h2 (tcgen05 backward: h1 / relu' are recomputed, never loaded)
 inline void bwd_inputs(GemmPass& p, const HeadW& w, const float* xs, const float* xa, const Layout& L, float* arena, int slot) {
     p.W1 = w.W1; p.b1 = w.b1; p.n_in = w.n_in; p.xs = xs; p.xa = xa; p.h2bits = slot_bits(L, arena, slot);
+    p.h1bits = slot_bits1(L, arena, slot);
 }
 // fused layer-1 backward of a DATA pass (tcgen05 path, use_tensor_cores 2): weight gradients (gW1, gb1) or d(action) (dxa);
 // dh1 is then not stored.  The slot's dh2 region holds the cross-tile ticket (word 0) and the per-tile partial sums.
@@ -1105,7 +1107,9 @@ FwdPass q_pass(const Layout& L, float* arena, int net, int head, const float* xs
     p.tc_img = tc_img_of(L, arena, net, head);
     p.head = (net == RRL_NET_QRISK || net == RRL_NET_QRISK_TARGET) ? HEAD_QRISK : HEAD_Q;
     p.xs = xs; p.xa = xa;
-    if (slot >= 0) { p.h1 = arena + L.h1[slot]; p.h2 = arena + L.h2[slot]; p.h2bits = slot_bits(L, arena, slot); }
+    if (slot >= 0) {
+        p.h1 = arena + L.h1[slot]; p.h2 = arena + L.h2[slot]; p.h2bits = slot_bits(L, arena, slot); p.h1bits = slot_bits1(L, arena, slot);
+    }
     p.keep_h2 = weight_pass ? 1 : 0;
     p.out_q = out_q;
     return p;
@@ -1342,7 +1346,8 @@ extern "C" int rrl_sac_backward(const rrl_agent_config_t* cfg, float* arena, con
         p0.draw_id = RRL_DRAW_SAC_NEXT; p0.out_a = R2(R2_NEXT_A); p0.out_logp = RA(RA_NEXT_LOGP);
         FwdPass& p1 = A.p[1];
         p1.w = pw; p1.head = pol_head; p1.xs = s; p1.eps = eps_cur; p1.draw_id = RRL_DRAW_SAC_CUR; p1.tc_img = p0.tc_img;
-        p1.h1 = arena + L.h1[4]; p1.h2 = arena + L.h2[4]; p1.h2bits = slot_bits(L, arena, 4); p1.keep_h2 = 1;
+        p1.h1 = arena + L.h1[4]; p1.h2 = arena + L.h2[4]; p1.h2bits = slot_bits(L, arena, 4); p1.h1bits = slot_bits1(L, arena, 4);
+        p1.keep_h2 = 1;
         p1.out_a = R2(R2_PI); p1.out_logp = RA(RA_LOGP); p1.out_raw = R4(R4_RAW_POL); p1.out_eps = R2(R2_EPS_CUR);
         int rc = launch_forward<32>(A, R, st);
         if (rc) return rc;
@@ -1649,7 +1654,7 @@ extern "C" int rrl_recovery_backward(const rrl_agent_config_t* cfg, float* arena
         p0.w = head_w(L, arena, RRL_NET_RECOVERY, 0); p0.head = HEAD_STOCH; p0.xs = s; p0.eps = eps_rec;
         p0.tc_img = tc_img_of(L, arena, RRL_NET_RECOVERY, 0);
         p0.draw_id = RRL_DRAW_QR_REC; p0.h1 = arena + L.h1[4]; p0.h2 = arena + L.h2[4]; p0.h2bits = slot_bits(L, arena, 4);
-        p0.keep_h2 = 1;
+        p0.h1bits = slot_bits1(L, arena, 4); p0.keep_h2 = 1;
         p0.out_a = R2(R2_REC_PI); p0.out_logp = RA(RA_REC_LOGP); p0.out_raw = R4(R4_RAW_REC); p0.out_eps = R2(R2_REC_EPS);
         int rc = launch_forward<32>(A, R, st);
         if (rc) return rc;

@@ -149,6 +149,8 @@ struct FwdPass {
     float *h1, *h2;    // activations kept for the backward pass (SIMT path: both; tcgen05 path: h2 only where a WEIGHT pass
                        // needs its values -- h1 is recomputed from the inputs, relu'(h2) comes from h2bits)
     uint32_t* h2bits;  // tcgen05 path: sign bits of h2, [rows][H / 32] words (bit j of word w: h2[row][32 w + j] > 0)
+    uint32_t* h1bits;  // tcgen05 path: sign bits of h1, [rows][32] BYTES: byte (k / 8 % 4) * 8 + k / 32, bit k % 8 (the
+                       // order the forward producers hold them in: thread (row, quarter) owns 8 contiguous bytes)
     int keep_h2;       // tcgen05 path: the backward has a WEIGHT pass for this forward pass (h2 values needed, not only signs)
     const float* eps;  // [rows][2] or NULL (Philox)
     uint32_t draw_id;
@@ -263,6 +265,7 @@ struct GemmPass {
     const float *W1, *b1, *xs, *xa;
     int n_in;
     const uint32_t* h2bits;
+    const uint32_t* h1bits;   // relu'(h1) of the DATA epilogue (layout: FwdPass::h1bits)
     // tcgen05 path, fused layer-1 backward (DATA passes; C may then be NULL: dh1 is consumed in the epilogue, never stored):
     //   gW1 / gb1 (weight gradients of layer 1; column sums over the rows, reduced across the row tiles through l1part by
     //   the last tile to arrive at l1ticket) or dxa ([rows][2], gradient w.r.t. the action inputs); never both

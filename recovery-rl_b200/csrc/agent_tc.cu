@@ -492,6 +492,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
             }
         }
         const bool four = w.n_in == 4;
+        // h1 image of this warp's 32-row chunk (tc_common.cuh): [row chunk][hi | lo][n-group][row] x 16 B.  Written for every
+        // row of the tile (rows beyond the batch meet a zero A operand in the WEIGHT pass)
+        uint4* h1img = (P.keep_h2 && P.h1) ? reinterpret_cast<uint4*>(P.h1) + (size_t)(row0 / 32 + (warp & 3)) * (2 * 32 * 32) : nullptr;
+        unsigned long long h1bytes = 0ull;   // byte c: relu'(h1) of this thread's 8 hidden units of k-chunk c
         for (int c = 0; c < NCHUNK; ++c) {
             const int stage = c % NSTAGE;
             unsigned char* a_hi = S.stage[stage];
@@ -507,16 +511,28 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
                     h = fmaf(wv.z, x2, h);
                     h = fmaf(wv.w, x3, h);
                 }
-                hs[e] = fminf(fmaxf(h, 0.f), 60000.0f);    // h1 * SA; the backward kernels recompute it (never stored)
+                hs[e] = fminf(fmaxf(h, 0.f), 60000.0f);    // h1 * SA (fp32 h1 itself is never stored)
+            }
+            if (P.h1bits) {
+                uint32_t by = 0u;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) by |= hs[e] > 0.f ? (1u << e) : 0u;
+                h1bytes |= (unsigned long long)by << (8 * c);
             }
             uint4 hi, lo;
             split8(hs, &hi, &lo);
+            if (h1img) {   // the same 16-byte pieces, row-major, for the WEIGHT pass of the backward (512 B contiguous per warp)
+                const size_t u = (size_t)(c * 4 + q) * 32 + lane;
+                h1img[u] = hi;
+                h1img[u + 32 * 32] = lo;
+            }
             mbar_wait(smem_u32(&S.empty[stage]), ((c / NSTAGE) & 1) ^ 1);   // after the arithmetic: the wait overlaps it
             *reinterpret_cast<uint4*>(a_hi + q * LBO_A + r * 16) = hi;
             *reinterpret_cast<uint4*>(a_lo + q * LBO_A + r * 16) = lo;
             fence_proxy_async();
             mbar_arrive_warp(smem_u32(&S.full[stage]));
         }
+        if (P.h1bits && live) reinterpret_cast<unsigned long long*>(P.h1bits)[row * 4 + q] = h1bytes;
         // ---- epilogue: columns [64 q, 64 q + 64) of this row ----
         TSTAMP(2);
         mbar_wait(smem_u32(&S.acc_full), 0);
@@ -631,9 +647,9 @@ struct BwdTcSmem {
     unsigned char stage[NSTAGE][STAGE_BYTES];
     float W1[H][4];                 // layer 1 of the pass, pre-multiplied by SA like the forward kernel (h1 is recomputed)
     float b1[H];
-    float4 xin[kDoutRows];          // the pass's inputs (s, a): rows of this tile (DATA) / of the whole batch (WEIGHT)
+    float4 xin[TM];                 // DATA: the inputs (s, a) of the tile's rows
     float W1z[H], W1w[H];           // DATA: the action columns of W1 (* SA), component-major (conflict-free epilogue reads)
-    uint32_t h1b[TM][H / 32];       // DATA: sign bits of the tile's h1 (relu' mask of the epilogue), computed by the producers
+    uint32_t h1b[TM][H / 32];       // DATA: sign bits of the tile's h1 (relu' mask of the epilogue; FwdPass::h1bits layout)
     float w3[4][H];
     float red[kProd][6];            // WEIGHT: per-thread partial sums (gb2, gW3[0..3])
     float4 douts[kDoutRows];        // WEIGHT: dout of the whole batch (rows <= kDoutRows), zero-padded to 4 outputs
@@ -674,6 +690,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const __grid_cons
 #pragma unroll
         for (int o = 0; o < 4; ++o)
             S.w3[o][k] = o < P.na ? P.W3a[o * H + k] : (o < P.n_out ? P.W3b[(o - P.na) * H + k] : 0.f);
+        if (weight) continue;                                  // layer 1 is only recomputed by the DATA tiles
         float4 w1 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (four) {
             w1 = *reinterpret_cast<const float4*>(P.W1 + k * 4);
@@ -686,9 +703,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const __grid_cons
         S.W1z[k] = w1.z; S.W1w[k] = w1.w;
         S.b1[k] = P.b1[k] * SA;
     }
-    {   // inputs of the rows this CTA touches: its 128-row tile (DATA) or the whole batch (WEIGHT, if it fits)
-        const int64_t xbase = weight ? 0 : (int64_t)tile * TM;
-        const int nx = weight ? (rows <= kDoutRows ? (int)rows : 0) : TM;
+    if (!weight) {   // inputs (s, a) of the 128 rows of this DATA tile
+        const int64_t xbase = (int64_t)tile * TM;
+        const int nx = TM;
         for (int i = t; i < nx; i += kTcThreads) {
             float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
             if (xbase + i < rows) {
@@ -701,10 +718,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const __grid_cons
             }
             S.xin[i] = x;
         }
+        for (int i = t; i < TM * (H / 32); i += kTcThreads)
+            (&S.h1b[0][0])[i] = (xbase + i / (H / 32) < rows) ? P.h1bits[xbase * (H / 32) + i] : 0u;
     }
     if (t == 0) {
         for (int s = 0; s < NSTAGE; ++s) {
-            mbar_init(smem_u32(&S.full[s]), weight ? kProdWarps : kProdWarps + 1);
+            mbar_init(smem_u32(&S.full[s]), kProdWarps + 1);   // producer warps + the loader's expect_tx arrival
             mbar_init(smem_u32(&S.empty[s]), 1);
         }
         mbar_init(smem_u32(&S.acc_full), 1);
@@ -770,20 +789,25 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const __grid_cons
                     }
             const float sc = pow2_scale(bound);
             // relu'(h2) of the row: 256 sign bits written by the forward kernel (no activation loads in this loop)
-            uint32_t hb[NCHUNK];
+            unsigned long long hbytes;   // byte c = the sign bits of this thread's 8 columns of k-chunk c
             {
                 uint4 b0 = make_uint4(0u, 0u, 0u, 0u), b1v = b0;
                 if (live) {
                     b0 = *reinterpret_cast<const uint4*>(P.h2bits + row * (H / 32));
                     b1v = *reinterpret_cast<const uint4*>(P.h2bits + row * (H / 32) + 4);
                 }
-                hb[0] = b0.x; hb[1] = b0.y; hb[2] = b0.z; hb[3] = b0.w; hb[4] = b1v.x; hb[5] = b1v.y; hb[6] = b1v.z; hb[7] = b1v.w;
+                const int sh = q * 8;
+                const uint32_t lo4 = ((b0.x >> sh) & 0xffu) | (((b0.y >> sh) & 0xffu) << 8) | (((b0.z >> sh) & 0xffu) << 16) |
+                                     (((b0.w >> sh) & 0xffu) << 24);
+                const uint32_t hi4 = ((b1v.x >> sh) & 0xffu) | (((b1v.y >> sh) & 0xffu) << 8) | (((b1v.z >> sh) & 0xffu) << 16) |
+                                     (((b1v.w >> sh) & 0xffu) << 24);
+                hbytes = ((unsigned long long)hi4 << 32) | lo4;
             }
-#pragma unroll
+#pragma unroll 1
             for (int c = 0; c < NCHUNK; ++c) {
                 const int stage = c % NSTAGE;
                 const int k0 = c * KCH + q * 8;
-                const uint32_t bits = hb[c] >> (q * 8);
+                const uint32_t bits = (uint32_t)(hbytes >> (8 * c));
                 float gv[8];
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
@@ -799,28 +823,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const __grid_cons
                 *reinterpret_cast<uint4*>(a_hi + A_IMG + q * LBO_A + r * 16) = lo;
                 fence_proxy_async();
                 mbar_arrive_warp(smem_u32(&S.full[stage]));
-            }
-            {   // relu'(h1) of the tile while the MMAs drain: the sign of layer 1 recomputed from the row's inputs with the
-                // forward kernel's FMA chain; thread (r, q) covers columns [64 q, 64 q + 64) of its row
-                const float4 x = S.xin[r];
-#pragma unroll
-                for (int wd = 0; wd < 2; ++wd) {
-                    uint32_t mb = 0u;
-#pragma unroll 8
-                    for (int j = 31; j >= 0; --j) {
-                        const int k = q * 64 + wd * 32 + j;
-                        const float4 wv = *reinterpret_cast<const float4*>(S.W1[k]);
-                        float h = fmaf(wv.x, x.x, S.b1[k]);
-                        h = fmaf(wv.y, x.y, h);
-                        if (four) {
-                            h = fmaf(wv.z, x.z, h);
-                            h = fmaf(wv.w, x.w, h);
-                        }
-                        mb = (mb << 1) + (h > 0.f ? 1u : 0u);
-                    }
-                    S.h1b[r][q * 2 + wd] = mb;
-                }
-                asm volatile("bar.sync 1, %0;" ::"n"(kProd) : "memory");
             }
             TSTAMP(2);
             mbar_wait(smem_u32(&S.acc_full), 0);
@@ -850,7 +852,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const __grid_cons
                     const int64_t rr = wrow0 + rl;
                     const bool ok = rr < rows;
                     const int lr = (warp & 3) * 32 + rl;
-                    const uint32_t hbits = ok ? (S.h1b[lr][col0 >> 5] >> (4 * c4)) : 0u;   // relu'(h1) of the 4 columns
+                    // relu'(h1) of the 4 columns: byte (k / 8 % 4) * 8 + k / 32 of the row, bits k % 8 .. + 3
+                    const uint32_t hbits = ok ? (uint32_t)(reinterpret_cast<const unsigned char*>(S.h1b[lr])[(c4 >> 1) * 8 + (col0 >> 5)] >> ((c4 & 1) * 4)) : 0u;
                     const float4 x = S.xin[lr];
                     float gg[4] = {g.x, g.y, g.z, g.w};
 #pragma unroll
@@ -945,7 +948,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const __grid_cons
                 }
             }
         } else {
-            // ================= WEIGHT: thread (m, kc) stages A, threads (n, kc) x2 stage B =================
+            // ================= WEIGHT: thread (m, kc) stages A; B arrives by bulk copy =================
             const int m = t & (TM - 1), kc = t >> 7;             // A role: out unit m0 + m, core column kc (8 rows)
             const int mcol = tile * TM + m;
             float bound = 0.f;
@@ -956,33 +959,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const __grid_cons
 #pragma unroll
             for (int o = 0; o < 4; ++o) w3m[o] = S.w3[o][mcol];
             float gb2 = 0.f, gw[4] = {0.f, 0.f, 0.f, 0.f};
-            const int nB0 = t & (H - 1), kcB0 = t >> 8;                 // B role, item 0: (n, kc)
-            const int nB1 = (t + kProd) & (H - 1), kcB1 = (t + kProd) >> 8;
-            // B operand = h1^T (scaled by SA): recomputed from the rows' inputs with the forward kernel's FMA chain -- no
-            // activation loads; the rows' (s, a) sit in shared memory (or, for batches beyond kDoutRows, in L1 / L2)
-            const bool x_smem = rows <= kDoutRows;
-            const float4 w1B0 = *reinterpret_cast<const float4*>(S.W1[nB0]), w1B1 = *reinterpret_cast<const float4*>(S.W1[nB1]);
-            const float b1B0 = S.b1[nB0], b1B1 = S.b1[nB1];
-            auto row_x = [&](int64_t rb) -> float4 {
-                if (x_smem) return S.xin[rb];
-                float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-                const float2 sv = reinterpret_cast<const float2*>(P.xs)[rb];
-                x.x = sv.x; x.y = sv.y;
-                if (four) {
-                    const float2 av2 = reinterpret_cast<const float2*>(P.xa)[rb];
-                    x.z = av2.x; x.w = av2.y;
-                }
-                return x;
-            };
-            auto h1_scaled = [&](const float4& wv, float bb, const float4& x) -> float {
-                float h = fmaf(wv.x, x.x, bb);
-                h = fmaf(wv.y, x.y, h);
-                if (four) {
-                    h = fmaf(wv.z, x.z, h);
-                    h = fmaf(wv.w, x.w, h);
-                }
-                return fminf(fmaxf(h, 0.f), 60000.0f);
-            };
+            // B operand = h1 (scaled by SA): the fp16 hi / lo image the forward kernel wrote, row-major == MN-major for this
+            // contraction (K = batch rows): the loader thread bulk-copies one 32-row chunk per stage, no transpose, no
+            // producer work
             float h2n[8];                                                // prefetched h2 column values of the NEXT chunk
             auto prefetch = [&](int c) {
 #pragma unroll
@@ -999,18 +978,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const __grid_cons
 #pragma unroll
                 for (int e = 0; e < 8; ++e) h2c[e] = h2n[e];
                 if (c + 1 < n_chunks) prefetch(c + 1);                   // in flight while this chunk is converted
-                uint4 ahi, alo, bhi[2], blo[2];
-                {
-                    float bv0[8], bv1[8];
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        const int64_t rb0 = (int64_t)c * KCH + kcB0 * 8 + e, rb1 = (int64_t)c * KCH + kcB1 * 8 + e;
-                        bv0[e] = rb0 < rows ? h1_scaled(w1B0, b1B0, row_x(rb0)) : 0.f;
-                        bv1[e] = rb1 < rows ? h1_scaled(w1B1, b1B1, row_x(rb1)) : 0.f;
-                    }
-                    split8(bv0, &bhi[0], &blo[0]);
-                    split8(bv1, &bhi[1], &blo[1]);
-                }
+                uint4 ahi, alo;
                 float av[8];
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
@@ -1039,13 +1007,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const __grid_cons
                 split8(av, &ahi, &alo);
                 mbar_wait(smem_u32(&S.empty[stage]), ((c / NSTAGE) & 1) ^ 1);
                 unsigned char* a_hi = S.stage[stage];
-                unsigned char* b_hi = a_hi + 2 * A_IMG;
                 *reinterpret_cast<uint4*>(a_hi + kc * LBO_A + m * 16) = ahi;
                 *reinterpret_cast<uint4*>(a_hi + A_IMG + kc * LBO_A + m * 16) = alo;
-                *reinterpret_cast<uint4*>(b_hi + kcB0 * LBO_B + nB0 * 16) = bhi[0];
-                *reinterpret_cast<uint4*>(b_hi + B_IMG + kcB0 * LBO_B + nB0 * 16) = blo[0];
-                *reinterpret_cast<uint4*>(b_hi + kcB1 * LBO_B + nB1 * 16) = bhi[1];
-                *reinterpret_cast<uint4*>(b_hi + B_IMG + kcB1 * LBO_B + nB1 * 16) = blo[1];
                 fence_proxy_async();
                 mbar_arrive_warp(smem_u32(&S.full[stage]));
             }
@@ -1101,6 +1064,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const __grid_cons
         }
     } else if (warp == kProd / 32) {
         if (lane == 0) {
+            // DATA: B = W2^T image, K-major.  WEIGHT: B = h1 image, MN-major (16 k-rows = two 128-byte k-groups per MMA)
+            const uint32_t lbo_b = weight ? LBO_BMN : LBO_B, sbo_b = weight ? SBO_BMN : SBO, kstep_b = weight ? 2 * LBO_BMN : 2 * LBO_B;
+            const uint32_t idesc = weight ? IDESC_BMN : IDESC;
             for (int c = 0; c < n_chunks; ++c) {
                 const int stage = c % NSTAGE;
                 mbar_wait(smem_u32(&S.full[stage]), (c / NSTAGE) & 1);
@@ -1111,20 +1077,21 @@ __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const __grid_cons
                 for (int j = 0; j < KCH / 16; ++j) {
                     const uint64_t dah = make_desc(a_hi + j * 2 * LBO_A, LBO_A, SBO);
                     const uint64_t dal = make_desc(a_lo + j * 2 * LBO_A, LBO_A, SBO);
-                    const uint64_t dbh = make_desc(b_hi + j * 2 * LBO_B, LBO_B, SBO);
-                    const uint64_t dbl = make_desc(b_lo + j * 2 * LBO_B, LBO_B, SBO);
-                    umma_f16(tmem_base, dah, dbh, (c | j) ? 1u : 0u);
-                    umma_f16(tmem_base, dah, dbl, 1u);
-                    umma_f16(tmem_base, dal, dbh, 1u);
+                    const uint64_t dbh = make_desc(b_hi + j * kstep_b, lbo_b, sbo_b);
+                    const uint64_t dbl = make_desc(b_lo + j * kstep_b, lbo_b, sbo_b);
+                    umma_f16_idesc(tmem_base, dah, dbh, (c | j) ? 1u : 0u, idesc);
+                    umma_f16_idesc(tmem_base, dah, dbl, 1u, idesc);
+                    umma_f16_idesc(tmem_base, dal, dbh, 1u, idesc);
                 }
                 umma_commit(smem_u32(&S.empty[stage]));
             }
             umma_commit(smem_u32(&S.acc_full));
         }
-    } else if (!weight) {
+    } else {
         if (lane == 0) {
-            const unsigned char* img = reinterpret_cast<const unsigned char*>(P.tc_imgT);
-            for (int c = 0; c < NCHUNK; ++c) {
+            // DATA: the W2^T image, chunk c of 8.  WEIGHT: the h1 image, row chunk c (32 KB: hi then lo, the stage's B layout)
+            const unsigned char* img = reinterpret_cast<const unsigned char*>(weight ? static_cast<const void*>(P.B) : static_cast<const void*>(P.tc_imgT));
+            for (int c = 0; c < n_chunks; ++c) {
                 const int stage = c % NSTAGE;
                 mbar_wait(smem_u32(&S.empty[stage]), ((c / NSTAGE) & 1) ^ 1);
                 const uint32_t bar = smem_u32(&S.full[stage]);

@@ -26,6 +26,13 @@ constexpr uint32_t LBO_A = 16 * 128, LBO_B = 32 * 128, SBO = 128;
 // instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (bits 4-5 = 1), a/b format F16 (0),
 // K-major A and B, N >> 3 at bit 17, M >> 4 at bit 24
 constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(H >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+// the same with operand B MN-major (b_major, bit 16): B[n][k] stored with n contiguous -- the WEIGHT pass of the backward
+// (K = batch rows) reads the row-major h1 image the forward kernel wrote, without a transpose.  Canonical MN-major layout,
+// no swizzle (cute::UMMA make_umma_desc<Major::MN>, INTERLEAVE): 16-byte units of 8 consecutive n; consecutive k 16 B
+// apart inside a group of 8 k; LBO = byte stride between k-groups, SBO = byte stride between n-groups.
+constexpr uint32_t IDESC_BMN = IDESC | (1u << 16);
+// h1 image (global == shared layout of one 32-row k-chunk): [hi | lo][n-group g = n / 8 (32)][row in chunk (32)] x 16 B
+constexpr uint32_t LBO_BMN = 8 * 16, SBO_BMN = 32 * 16;
 
 
 // ---- PTX wrappers -----------------------------------------------------------------------------------
@@ -75,13 +82,16 @@ __device__ __forceinline__ void tmem_relinquish() { asm volatile("tcgen05.relinq
 __device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
 }
-__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+__device__ __forceinline__ void umma_f16_idesc(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t accumulate, uint32_t idesc) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-        "l"(adesc), "l"(bdesc), "r"(IDESC), "r"(accumulate)
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+    umma_f16_idesc(d_tmem, adesc, bdesc, accumulate, IDESC);
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");

@@ -283,6 +283,19 @@ struct TailArgs {
 
 // Called by ALL threads of EVERY CTA of the grid after the CTA's last global store (also by CTAs that have nothing to
 // do).  The last CTA to arrive runs the stage; the ticket is left at 0 for the next launch.
+// NOT inlined: the stage bodies are large and a kernel calls this from its early-exit path as well as from its end; one
+// out-of-line copy keeps the kernels' instruction footprint (the tensor-core kernels run three warp roles through
+// different code at once) within the instruction cache.
+static __device__ __noinline__ void run_tail_stage(const TailArgs& T, float* red, double* redd) {
+    switch (T.kind) {
+        case TAIL_SAC_LOSS: sac_loss_body(T.sac, red, redd); break;
+        case TAIL_QR_LOSS: qrisk_loss_body(T.qr, red); break;
+        case TAIL_REC_LOSS: recovery_loss_body(T.rec, red); break;
+        case TAIL_GAUSS_BWD: gauss_backward_body(T.gauss); break;
+        case TAIL_STOCH_BWD: stoch_backward_body(T.stoch, red); break;
+        default: break;
+    }
+}
 __device__ __forceinline__ void run_tail(const TailArgs& T) {
     if (T.kind == TAIL_NONE) return;
     __shared__ int s_tail_last;
@@ -301,14 +314,7 @@ __device__ __forceinline__ void run_tail(const TailArgs& T) {
     }
     __syncthreads();
     if (!s_tail_last) return;
-    switch (T.kind) {
-        case TAIL_SAC_LOSS: sac_loss_body(T.sac, s_tail_red, s_tail_redd); break;
-        case TAIL_QR_LOSS: qrisk_loss_body(T.qr, s_tail_red); break;
-        case TAIL_REC_LOSS: recovery_loss_body(T.rec, s_tail_red); break;
-        case TAIL_GAUSS_BWD: gauss_backward_body(T.gauss); break;
-        case TAIL_STOCH_BWD: stoch_backward_body(T.stoch, s_tail_red); break;
-        default: break;
-    }
+    run_tail_stage(T, s_tail_red, s_tail_redd);
 }
 
 }  // namespace rrl

@@ -500,6 +500,54 @@ class VecEngine(object):
         self._ev_out_done[ticket & 1].synchronize()
         return self._pl_out_host[ticket & 1]
 
+    # ---- evaluation rollouts (experiment.py:372-374, 493-538) ---------------------------------------------
+    def eval_rollout(self, n_eval=1):
+        """get_test_rollout for `n_eval` fresh env copies at once: the task policy acts in eval mode (its mean action,
+        sac.py:166-167), the Q_risk threshold and the recovery policy are the training ones (experiment.py:546-577 with
+        train=False), nothing is pushed to the replay rings, no update runs and none of the training state (env copies,
+        counters, sampler, Philox step) is touched: the rollout has its own env state and its own counter block.
+        Returns a list of episodes, each a list of per-step info dicts (the reference's test_stats schema)."""
+        k = int(n_eval)
+        dev = self.device
+        ev = getattr(self, "_eval", None)
+        if ev is None or ev["k"] != k:
+            ev = dict(k=k, state=torch.zeros(2, k, dtype=torch.float64, device=dev), ep_steps=torch.zeros(k, dtype=torch.int32, device=dev),
+                      ep_return=torch.zeros(k, dtype=torch.float64, device=dev), a_task=torch.zeros(k, 2, device=dev),
+                      a_real=torch.zeros(k, 2, device=dev), rec=torch.zeros(k, dtype=torch.uint8, device=dev),
+                      q=torch.zeros(k, device=dev), counters=torch.zeros(native.NUM_COUNTERS, dtype=torch.int64, device=dev),
+                      nxt=torch.zeros(2, k, dtype=torch.float64, device=dev), rew=torch.zeros(k, dtype=torch.float64, device=dev),
+                      done=torch.zeros(k, dtype=torch.uint8, device=dev), cons=torch.zeros(k, dtype=torch.uint8, device=dev),
+                      succ=torch.zeros(k, dtype=torch.uint8, device=dev), calls=0,
+                      cfg=native.env_config(self.kind, k, horizon=HORIZON[self.env_name], reward_penalty=0.0,
+                                            seed=self.seed + 7919, stream_id=self.rank,
+                                            maze_substeps=self.env_cfg.maze_substeps))
+            self._eval = ev
+        ev["counters"].zero_()
+        ev["counters"][native.C_VEC_STEP] = 1000003 * ev["calls"]      # fresh Philox draws for every evaluation
+        ev["calls"] += 1
+        native.env_reset(ev["cfg"], ev["state"], ev["ep_steps"], ev["ep_return"], ev["counters"])
+        episodes = [[] for _ in range(k)]
+        alive = np.ones(k, bool)
+        for _ in range(HORIZON[self.env_name] + 1):
+            prev = ev["state"].t().cpu().numpy().copy()
+            native.agent_act(self.cfg, self.arena, k, ev["state"], ev["counters"], ev["a_task"], ev["a_real"], ev["rec"], ev["q"],
+                             use_recovery=self.use_recovery and self.mpc is None, eval=True, start_steps=0,
+                             seed=self.seed + 7919, stream_id=self.rank)
+            native.env_step(ev["cfg"], ev["a_task"], ev["a_real"], ev["state"], ev["ep_steps"], ev["ep_return"], ev["counters"],
+                            recovery=ev["rec"], out_next_state=ev["nxt"], out_reward=ev["rew"], out_done=ev["done"],
+                            out_constraint=ev["cons"], out_success=ev["succ"])
+            native.counters_advance(ev["counters"], k, 1, 1, False, False)
+            ns, rw = ev["nxt"].t().cpu().numpy(), ev["rew"].cpu().numpy()
+            dn, cs, su = ev["done"].cpu().numpy(), ev["cons"].cpu().numpy(), ev["succ"].cpu().numpy()
+            ac, rc = ev["a_real"].cpu().numpy(), ev["rec"].cpu().numpy()
+            for i in np.flatnonzero(alive):
+                episodes[i].append({"constraint": int(cs[i]), "reward": float(rw[i]), "state": prev[i], "next_state": ns[i].copy(),
+                                    "action": ac[i].copy(), "success": bool(su[i]), "recovery": bool(rc[i])})
+            alive &= ~dn.astype(bool)
+            if not alive.any():
+                break
+        return episodes
+
     # ---- state snapshots (capture warm-up, tests) -----------------------------------------------------
     def snapshot(self):
         """everything one vector step mutates, incl. the ring slots its pushes will overwrite (they hold live

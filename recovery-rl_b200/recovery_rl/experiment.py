@@ -351,7 +351,11 @@ class Experiment:
             dist.broadcast_object_list(box, src=0, group=eng.pg)
             ck_dir = box[0]
         k = min(max(int(getattr(c, "log_envs", 1)), 0), eng.n)
-        train_rollouts, open_eps, vec_stats = [], [[] for _ in range(k)], []
+        train_rollouts, open_eps, vec_stats, test_rollouts = [], [[] for _ in range(k)], [], []
+        # experiment.py:372-374: one test rollout after every 10th training episode -- here after every 10 episodes PER ENV
+        # COPY (10 * N * world finished episodes), max(1, log_envs) eval copies at once, rank 0 only (replicas are identical)
+        eval_every = 10 * eng.n * eng.world
+        next_eval = eval_every
         step = 0
         while True:
             if k:
@@ -392,7 +396,10 @@ class Experiment:
                     if eng.rank == 0:
                         print("Vector step: {}, total numsteps: {}, episodes: {}, violations: {}, successes: {}".format(
                             step, cn["total_numsteps"], cn["episodes"], cn["num_viols"], cn["num_successes"]))
-                    data = {"test_stats": [], "train_stats": train_rollouts, "vec_stats": vec_stats}
+                    if c.eval and eng.rank == 0 and cn["episodes"] * eng.world >= next_eval:
+                        test_rollouts.extend(eng.eval_rollout(max(1, k)))          # experiment.py:493-538
+                        next_eval += eval_every * max(1, (cn["episodes"] * eng.world - next_eval) // eval_every + 1)
+                    data = {"test_stats": test_rollouts, "train_stats": train_rollouts, "vec_stats": vec_stats}
                     with open(osp.join(self.logdir, "run_stats.pkl"), "wb") as f:
                         pickle.dump(data, f)
                 ck = int(getattr(c, "checkpoint_every", 0))

@@ -139,3 +139,52 @@ def test_pipelined_host_steps_match_serial():
                 assert abs(float(ra) - float(rb)) <= 1e-9 * (1 + abs(float(rb))), (i, float(ra), float(rb))
                 a[native.C_RETURN_SUM_BITS] = b[native.C_RETURN_SUM_BITS] = 0
             assert torch.equal(a, b), (i, k)
+
+
+@pytest.mark.gpu
+def test_eval_rollout_is_side_effect_free_and_uses_the_mean_action():
+    """VecEngine.eval_rollout (experiment.py:493-538): eval-mode task action = the policy's mean action, same Q_risk
+    threshold; episodes chain and end at done / the horizon; the training state is untouched."""
+    import numpy as np
+    import torch
+    from oracle import envs as oenvs
+    from oracle.agent import Agent
+    from recovery_rl import native
+    from recovery_rl.engine import VecEngine
+    torch.manual_seed(3)
+    np.random.seed(3)
+    ora = Agent(action_scale=(np.float32(1.0),) * 2, gamma_safe=0.8, eps_safe=0.3)
+    eng = VecEngine("navigation1", 256, batch_size=64, replay_size=8192, safe_replay_size=8192, gamma_safe=0.8, eps_safe=0.3,
+                    seed=3, start_steps=0, use_tensor_cores=2)
+    eng.init_agent(ora.nets())
+    eng.push_offline(oenvs.nav_offline_data(oenvs.KIND_BY_NAME["navigation1"], 400))
+    eng.pretrain_qrisk(3, n_demos=400)
+    eng.reset()
+    for _ in range(3):
+        eng.step()
+    torch.cuda.synchronize()
+    P = {net: eng.agent.params(net) for net in native.NET_NAMES}
+    ora.load(lambda net, i: P[net][i])
+    before = dict(arena=eng.arena.clone(), counters=eng.counters.clone(), state=eng.state.clone(), mt=eng.mt_state.clone(),
+                  ep_steps=eng.ep_steps.clone())
+    eps = eng.eval_rollout(16)
+    torch.cuda.synchronize()
+    assert torch.equal(eng.arena, before["arena"]) and torch.equal(eng.counters, before["counters"])
+    assert torch.equal(eng.state, before["state"]) and torch.equal(eng.mt_state, before["mt"])
+    assert torch.equal(eng.ep_steps, before["ep_steps"])
+    assert len(eps) == 16
+    s0 = np.array([e[0]["state"] for e in eps])
+    a_task, a_real, rec, qv = ora.act(s0, np.zeros((16, 2), np.float32), np.zeros((16, 2), np.float32), eps_safe=0.3)
+    got_rec = np.array([e[0]["recovery"] for e in eps])
+    sure = np.abs(qv - 0.3) > 1e-4
+    assert np.array_equal(got_rec[sure], rec[sure])
+    plain = sure & ~rec                                  # no recovery: executed action == the policy's mean action
+    got_a = np.array([e[0]["action"] for e in eps])
+    assert np.allclose(got_a[plain], a_task[plain], rtol=1e-4, atol=1e-5)
+    for e in eps:
+        assert 1 <= len(e) <= 100
+        for a, b in zip(e, e[1:]):
+            assert np.array_equal(a["next_state"], b["state"])          # the episode chains (no reset inside it)
+        assert all(k in e[0] for k in ("constraint", "reward", "state", "next_state", "action", "success", "recovery"))
+    eps2 = eng.eval_rollout(16)
+    assert len(eps2) == 16 and not np.array_equal(np.array([e[0]["state"] for e in eps2]), s0)    # fresh reset draws
