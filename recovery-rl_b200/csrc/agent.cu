@@ -442,7 +442,7 @@ __global__ void __launch_bounds__(kThreads) layer1_backward_kernel(const __grid_
 // (4)-(8) the per-row stages as kernels of their own (SIMT path and the unfused tcgen05 path; the fused path runs the
 //     same bodies as tails of the producing kernels, update_tails.cuh)
 __global__ void __launch_bounds__(kThreads) sac_loss_kernel(const __grid_constant__ SacLossArgs A) {
-    __shared__ float red[32];
+    __shared__ float red[4 * 32];
     __shared__ double redd[32];
     sac_loss_body(A, red, redd);
 }
@@ -452,7 +452,7 @@ __global__ void __launch_bounds__(kThreads) gauss_backward_kernel(const __grid_c
     if (i < rows) gauss_backward_row(A, i, rows);
 }
 __global__ void __launch_bounds__(kThreads) qrisk_loss_kernel(const __grid_constant__ QrLossArgs A) {
-    __shared__ float red[32];
+    __shared__ float red[4 * 32];
     qrisk_loss_body(A, red);
 }
 __global__ void __launch_bounds__(kThreads) recovery_loss_kernel(const __grid_constant__ RecLossArgs A) {

@@ -39,6 +39,28 @@ __device__ __forceinline__ T block_sum_any(T v, T* red /*[32]*/) {
     return r;
 }
 
+// four sums at once (one shuffle tree, one shared-memory exchange): valid on thread 0.  red: [4][32]
+__device__ __forceinline__ void block_sum4(float (&v)[4], float* red) {
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], s);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) red[i * 32 + (threadIdx.x >> 5)] = v[i];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float r = 0.f;
+            for (int w = 0; w < nw; ++w) r += red[i * 32 + w];
+            v[i] = r;
+        }
+    }
+}
+
 // ---- SAC losses (sac.py:192-231): TD target, critic MSE, policy loss, and the output gradients; plus the comparison
 //      branches: RCPO target penalty (:202-205), DGD policy penalty (:224-228) and the gradients of the three scalar
 //      multipliers log_alpha (:241-243), log_nu (:257-258), log_lambda (:266-267)
@@ -101,10 +123,9 @@ __device__ __forceinline__ void sac_loss_body(const SacLossArgs& A, float* red, 
         A.dqp1[i] = p1 < p2 ? -inv : (p1 == p2 ? -0.5f * inv : 0.f);
         A.dqp2[i] = p2 < p1 ? -inv : (p1 == p2 ? -0.5f * inv : 0.f);
     }
-    const float s1 = block_sum_any(l1, red);
-    const float s2 = block_sum_any(l2, red);
-    const float s3 = block_sum_any(lp, red);
-    const float s4 = block_sum_any(la, red);
+    float s4v[4] = {l1, l2, lp, la};
+    block_sum4(s4v, red);
+    const float s1 = s4v[0], s2 = s4v[1], s3 = s4v[2], s4 = s4v[3];
     const bool need_d = (A.flags & (RRL_ALGO_UPDATE_NU | RRL_ALGO_RCPO)) != 0;   // uniform
     const double d1 = need_d ? block_sum_any(gnu, redd) : 0.0;
     const double d2 = need_d ? block_sum_any(glam, redd) : 0.0;
@@ -148,11 +169,11 @@ __device__ __forceinline__ void qrisk_loss_body(const QrLossArgs& A, float* red)
         A.dq1[i] = 2.0f * e1 * inv * q1 * (1.0f - q1);  // d/d(raw) through sigmoid
         A.dq2[i] = 2.0f * e2 * inv * q2 * (1.0f - q2);
     }
-    const float s1 = block_sum_any(l1, red);
-    const float s2 = block_sum_any(l2, red);
+    float s4v[4] = {l1, l2, 0.f, 0.f};
+    block_sum4(s4v, red);
     if (threadIdx.x == 0) {
-        A.losses[0] = s1 * inv;
-        A.losses[1] = s2 * inv;
+        A.losses[0] = s4v[0] * inv;
+        A.losses[1] = s4v[1] * inv;
     }
 }
 
@@ -299,7 +320,7 @@ static __device__ __noinline__ void run_tail_stage(const TailArgs& T, float* red
 __device__ __forceinline__ void run_tail(const TailArgs& T) {
     if (T.kind == TAIL_NONE) return;
     __shared__ int s_tail_last;
-    __shared__ float s_tail_red[32];
+    __shared__ float s_tail_red[4 * 32];
     __shared__ double s_tail_redd[32];
     __syncthreads();                       // every thread's stores precede thread 0's fence + ticket
     if (threadIdx.x == 0) {
