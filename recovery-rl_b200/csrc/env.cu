@@ -97,39 +97,82 @@ __device__ __forceinline__ void maze_integrate(const EnvParams& P, double fbx, d
     x = __dadd_rn(x, __dmul_rn(P.h, vx));
     y = __dadd_rn(y, __dmul_rn(P.h, vy));
 }
+// branch-free form of maze_may_touch (same margins): straight-line fp32 code the scheduler can interleave with the fp64
+// dependency chains of the next chunk's integration
+__device__ __forceinline__ bool maze_may_touch_bf(const EnvParams& P, float xl, float xh, float yl, float yh) {
+    const bool planes = (xl <= P.f_plane_lo) | (xh >= P.f_plane_hi) | (yl <= P.f_plane_lo) | (yh >= P.f_plane_hi);
+    const float dx1 = fmaxf(fmaxf(P.f_wx0[0] - xh, xl - P.f_wx1[0]), 0.f);  // walls 1A / 1B share their x range
+    const float dx2 = fmaxf(fmaxf(P.f_wx0[2] - xh, xl - P.f_wx1[2]), 0.f);  // walls 2A / 2B
+    const float d0 = fmaxf(fmaxf(P.f_wy0[0] - yh, yl - P.f_wy1[0]), 0.f);
+    const float d1 = fmaxf(fmaxf(P.f_wy0[1] - yh, yl - P.f_wy1[1]), 0.f);
+    const float d2 = fmaxf(fmaxf(P.f_wy0[2] - yh, yl - P.f_wy1[2]), 0.f);
+    const float d3 = fmaxf(fmaxf(P.f_wy0[3] - yh, yl - P.f_wy1[3]), 0.f);
+    const float x1 = dx1 * dx1, x2 = dx2 * dx2;
+    const bool walls = (fmaf(d0, d0, x1) < P.f_rm2) | (fmaf(d1, d1, x1) < P.f_rm2) | (fmaf(d2, d2, x2) < P.f_rm2) |
+                       (fmaf(d3, d3, x2) < P.f_rm2);
+    return planes | walls;
+}
 __device__ __forceinline__ void maze_substeps_warp(const EnvParams& P, bool idle, double fbx, double fby, double& x,
                                                    double& y, bool& contact) {
     const int nsub = P.cfg.maze_substeps;
     double vx = 0.0, vy = 0.0;
     bool frozen = idle;  // idle lanes (beyond n) and lanes in contact do not move
     int k = 0;
-    // full chunks: integrate test-free and KEEP the MAZE_CHUNK pre-integration positions (registers: the loop is fully
-    // unrolled, every position is a distinct value anyway).  A lane whose chunk box can touch a solid runs the exact
-    // fp64 test on the stored positions -- independent tests, no re-integration, no dependent chain -- and freezes at the
-    // first one that touches.  Frozen lanes compute along (their results are discarded by selects, not by branches).
-    for (; k + MAZE_CHUNK <= nsub; k += MAZE_CHUNK) {
-        double px[MAZE_CHUNK], py[MAZE_CHUNK];
-        double nx = x, ny = y;
-#pragma unroll
-        for (int j = 0; j < MAZE_CHUNK; ++j) {
-            px[j] = nx; py[j] = ny;
-            maze_integrate(P, fbx, fby, nx, ny, vx, vy);
-        }
-        const float fx0 = (float)x, fx1 = (float)nx, fy0 = (float)y, fy1 = (float)ny;
-        const bool may = !frozen && maze_may_touch(P, fminf(fx0, fx1), fmaxf(fx0, fx1), fminf(fy0, fy1), fmaxf(fy0, fy1));
+    // Full chunks, software-pipelined by one chunk: chunk c is integrated test-free and its MAZE_CHUNK pre-integration
+    // positions are KEPT (registers: the loop is fully unrolled); the conservative fp32 box test of chunk c runs inside the
+    // straight-line code that integrates chunk c + 1 (independent instruction streams: the fp64 pipe and the fp32 / ALU pipes
+    // overlap).  A lane whose box can touch a solid runs the exact fp64 test on the stored positions of chunk c -- independent
+    // tests, no re-integration -- and freezes at the first one that touches; its speculative chunk c + 1 is then dropped.
+    // Frozen lanes compute along (their results are discarded by selects, not by branches).
+    double ax[MAZE_CHUNK], ay[MAZE_CHUNK], bx[MAZE_CHUNK], by[MAZE_CHUNK];   // ping-pong: positions of two consecutive chunks
+    float fx0 = 0.f, fx1 = 0.f, fy0 = 0.f, fy1 = 0.f;                          // box of the chunk whose test is pending
+    bool pending = false;
+    // exact tests of the pending chunk (positions qx / qy); true if the lane touched in it
+    auto resolve = [&](bool may, const double (&qx)[MAZE_CHUNK], const double (&qy)[MAZE_CHUNK]) -> bool {
         bool hit = false;
         if (__any_sync(0xffffffffu, may)) {
             if (may) {
                 double hx = 0.0, hy = 0.0;
 #pragma unroll
                 for (int j = MAZE_CHUNK - 1; j >= 0; --j)   // descending: the LOWEST touching substep wins
-                    if (maze_touch(P, px[j], py[j])) { hit = true; hx = px[j]; hy = py[j]; }
-                if (hit) { nx = hx; ny = hy; }
+                    if (maze_touch(P, qx[j], qy[j])) { hit = true; hx = qx[j]; hy = qy[j]; }
+                if (hit) { x = hx; y = hy; }
             }
         }
-        if (!frozen) { x = nx; y = ny; }
+        return hit;
+    };
+    // one chunk: integrate into (cx, cy) while the pending chunk (qx, qy) is tested; returns true when every lane is frozen
+    auto chunk = [&](double (&cx)[MAZE_CHUNK], double (&cy)[MAZE_CHUNK], const double (&qx)[MAZE_CHUNK],
+                     const double (&qy)[MAZE_CHUNK]) -> bool {
+        double nx = x, ny = y, nvx = vx, nvy = vy;
+#pragma unroll
+        for (int j = 0; j < MAZE_CHUNK; ++j) {
+            cx[j] = nx; cy[j] = ny;
+            maze_integrate(P, fbx, fby, nx, ny, nvx, nvy);
+        }
+        // test of the previous chunk (same basic block as the integration above)
+        const bool may = pending & !frozen & maze_may_touch_bf(P, fminf(fx0, fx1), fmaxf(fx0, fx1), fminf(fy0, fy1), fmaxf(fy0, fy1));
+        if (resolve(may, qx, qy)) { frozen = true; contact = true; }
+        fx0 = (float)x; fy0 = (float)y;            // box of THIS chunk: from its start ...
+        if (!frozen) { x = nx; y = ny; vx = nvx; vy = nvy; }
+        fx1 = (float)nx; fy1 = (float)ny;          // ... to its end (unused once frozen)
+        pending = true;
+        return __all_sync(0xffffffffu, frozen);
+    };
+    bool last_in_a = false;
+    for (; k + 2 * MAZE_CHUNK <= nsub; k += 2 * MAZE_CHUNK) {
+        if (chunk(ax, ay, bx, by)) return;
+        if (chunk(bx, by, ax, ay)) return;
+    }
+    if (k + MAZE_CHUNK <= nsub) {
+        if (chunk(ax, ay, bx, by)) return;
+        k += MAZE_CHUNK;
+        last_in_a = true;
+    }
+    if (pending) {   // the last full chunk
+        const bool may = !frozen & maze_may_touch_bf(P, fminf(fx0, fx1), fmaxf(fx0, fx1), fminf(fy0, fy1), fmaxf(fy0, fy1));
+        const bool hit = last_in_a ? resolve(may, ax, ay) : resolve(may, bx, by);
         if (hit) { frozen = true; contact = true; }
-        if (__all_sync(0xffffffffu, frozen)) return;
     }
     // remainder (substep counts that are not a multiple of the chunk: tests only): exact test before every substep
     if (!frozen)
