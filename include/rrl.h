@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define RRL_VERSION 3
+#define RRL_VERSION 4
 
 const char* rrl_last_error(void);
 int rrl_version(void);
@@ -62,6 +62,8 @@ enum {
     RRL_C_ADAM_T_LAMBDA  = 25, /*   log_lambda_RCPO (sac.py:268-270)                                        */
     RRL_C_TICKET         = 26, /* scratch: CTA arrival ticket of the fused optimizer-step kernel (always 0 between launches) */
     RRL_C_TICKET2        = 27, /* scratch: CTA arrival ticket of the update kernels whose last CTA runs the loss / sample-backward stage */
+    RRL_C_GATE_SATISFIED = 28, /* multi-GPU: the violation count of the Q_risk online gate (experiment.py:410) has passed its threshold on
+                                  every rank (monotone: counts only grow) -> rrl_peer_sync_gate_counts stops exchanging */
     RRL_NUM_COUNTERS     = 32
 };
 
@@ -278,12 +280,20 @@ typedef struct {
     int32_t world, rank;
     uint64_t arena[8];
     uint64_t signal[8];
+    uint64_t epoch;      /* device pointer to the int64 barrier generation counter of this rank, or 0.  Non-zero: the
+                            rrl_*_apply_p2p kernels (tcgen05 path) run the flag barrier THEMSELVES before they load the peers'
+                            gradients -- CTA 0 publishes this rank's generation, every CTA waits on the local pad -- and the
+                            caller launches no rrl_peer_barrier in front of them */
 } rrl_peers_t;
 int rrl_peer_barrier(const rrl_peers_t* peers, int64_t* epoch, int64_t* counters, void* stream);
 /* the same barrier, also exchanging the Q_risk gate counts (experiment.py:407-410 must open on every rank in the same
  * step): counters[RRL_C_EXT_VIOLS] = sum over the other ranks of (RRL_C_NUM_VIOLS + RRL_C_OFFLINE_VIOLS).
- * Uses int64 slots at signal words [272, 272 + 2*world). */
-int rrl_peer_sync_gate_counts(const rrl_peers_t* peers, int64_t* epoch, int64_t* counters, void* stream);
+ * Uses int64 slots at signal words [272, 272 + 2*world).  gate_batch / gate_pos_fraction: the gate's own threshold
+ * (total / batch > pos_fraction, experiment.py:410); once it is passed -- on every rank in the same step, and for good, the
+ * counts only grow -- RRL_C_GATE_SATISFIED is set and later calls return without touching the other GPUs (gate_batch 0:
+ * exchange forever). */
+int rrl_peer_sync_gate_counts(const rrl_peers_t* peers, int64_t* epoch, int64_t* counters, int32_t gate_batch,
+                              double gate_pos_fraction, void* stream);
 int rrl_sac_apply_p2p(const rrl_agent_config_t* cfg, float* arena, int64_t* counters, const rrl_peers_t* peers, void* stream);
 int rrl_qrisk_apply_p2p(const rrl_agent_config_t* cfg, float* arena, int64_t* counters, const rrl_peers_t* peers, void* stream);
 int rrl_recovery_apply_p2p(const rrl_agent_config_t* cfg, float* arena, int64_t* counters, const rrl_peers_t* peers, void* stream);

@@ -568,6 +568,7 @@ __global__ void __launch_bounds__(kThreads) adam_kernel(const __grid_constant__ 
     }
 }
 
+constexpr int kPadBase = 256;   // first signal-pad word used by our barriers (the first KB is left to torch's own primitives)
 // (9') the same optimizer step with COALESCED operand-image refresh (tcgen05 path).  adam_kernel above scatters three
 //      image elements per parameter (4-byte stores 1 KB apart for the transposed fp32 image, 2-byte stores for the fp16
 //      hi/lo images): ~1.5 M sector writes per SAC step.  Here a CTA owns a 32x32 tile of a hidden matrix: float4 loads
@@ -602,6 +603,10 @@ struct AdamTileArgs {
     int n_bump;
     const float* peer[8];
     int n_peer;
+    // fused cross-GPU flag barrier (rrl_peers_t::epoch != 0): signal pads of all ranks, this rank, the generation counter
+    uint32_t* signal[8];
+    int rank;
+    int64_t* epoch;
 };
 __device__ __forceinline__ void adam_elem(float& p, float g, float& m, float& v, float b1, float b2, float eps, float step_size,
                                           float bc2s) {
@@ -672,6 +677,30 @@ __global__ void __launch_bounds__(kThreads) adam_tile_kernel(const __grid_consta
     const float step_size = s_bc[0], bc2s = s_bc[1];
     const bool polyak = s_polyak != 0;
     const float omt = (float)(1.0 - (double)A.tau);
+    if (A.epoch) {
+        // Cross-GPU barrier inside the optimizer step: this rank's gradients were completed by the previous kernels of the
+        // stream, so CTA 0 publishes generation g = *epoch + 1 into every peer's pad (release, system scope); EVERY CTA then
+        // waits until all peers' generation g has arrived in the local pad before it loads their gradients.  The last CTA
+        // stores g (below).  A CTA waits only on OTHER ranks' CTA 0, never on a CTA of its own grid.
+        const unsigned g = (unsigned)(*reinterpret_cast<volatile int64_t*>(A.epoch) + 1);
+        if (blockIdx.x == 0 && t < A.n_peer) {
+            __threadfence_system();
+            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(A.signal[t] + kPadBase + A.rank), "r"(g) : "memory");
+        }
+        if (t < A.n_peer) {
+            const uint32_t* src = A.signal[A.rank] + kPadBase + t;
+            const bool lost = A.counters[RRL_C_ERROR] == 2;   // a peer was lost earlier: do not stall every later step as well
+            unsigned v;
+            unsigned long long t0, t1;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+            do {
+                asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(src) : "memory");
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            } while (!lost && (int)(v - g) < 0 && t1 - t0 < 60000000000ull);   // give up after 60 s instead of hanging the GPU
+            if ((int)(v - g) < 0) A.counters[RRL_C_ERROR] = 2;
+        }
+        __syncthreads();
+    }
     const int n_tile_ctas = A.n_w2 * 64;
     if ((int)blockIdx.x < n_tile_ctas) {
         const AdamW2& W = A.w2[blockIdx.x >> 6];
@@ -751,6 +780,7 @@ __global__ void __launch_bounds__(kThreads) adam_tile_kernel(const __grid_consta
         if (ticket == (unsigned long long)gridDim.x - 1) {
             A.counters[RRL_C_TICKET] = 0;
             for (int i = 0; i < A.n_bump; ++i) A.counters[A.bump[i]] += 1;
+            if (A.epoch) *A.epoch += 1;       // every CTA has read the old generation (its ticket came after its wait)
         }
     }
 }
@@ -811,15 +841,19 @@ __global__ void init_scalars_kernel(float* scal, float alpha, double nu, double 
 
 // (9c) cross-GPU barrier over peer-mapped signal pads (one thread per peer): publish this rank's generation into
 //      every peer's pad (release, system scope), then wait until every peer's generation has arrived in ours.
-constexpr int kPadBase = 256;
 struct PeerBarrierArgs {
     uint32_t* signal[8];
     int world, rank;
     int64_t* epoch;
     int64_t* counters;
     int exchange;   // also exchange the Q_risk gate counts: EXT_VIOLS = sum over the OTHER ranks of (num_viols + offline_viols)
+    int gate_batch;             // batch size and pos_fraction of the online gate (experiment.py:410); 0: never stop exchanging
+    double gate_pos_fraction;
 };
 __global__ void peer_barrier_kernel(const PeerBarrierArgs A) {
+    // gate exchange: once the violation count has passed the gate's threshold on every rank (the same total everywhere, so
+    // the same step everywhere) it stays passed -- counts only grow -- and the exchange has nothing left to decide
+    if (A.exchange && A.counters[RRL_C_GATE_SATISFIED]) return;
     __shared__ unsigned s_epoch;
     if (threadIdx.x == 0) {
         s_epoch = (unsigned)(++(*A.epoch));
@@ -855,7 +889,12 @@ __global__ void peer_barrier_kernel(const PeerBarrierArgs A) {
     if (A.exchange) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) theirs += __shfl_xor_sync(0xffffffffu, theirs, o);
-        if (threadIdx.x == 0) A.counters[RRL_C_EXT_VIOLS] = theirs;
+        if (threadIdx.x == 0) {
+            A.counters[RRL_C_EXT_VIOLS] = theirs;
+            const long long total = theirs + A.counters[RRL_C_NUM_VIOLS] + A.counters[RRL_C_OFFLINE_VIOLS];
+            if (A.gate_batch > 0 && (double)total / (double)A.gate_batch > A.gate_pos_fraction && A.counters[RRL_C_ERROR] == 0)
+                A.counters[RRL_C_GATE_SATISFIED] = 1;
+        }
     }
 }
 
@@ -1007,7 +1046,12 @@ int launch_adam_tiled(const rrl_agent_config_t* cfg, const Layout& L, float* are
     memset(&A, 0, sizeof(A));
     if (peers) {
         A.n_peer = peers->world;
-        for (int r = 0; r < peers->world && r < 8; ++r) A.peer[r] = reinterpret_cast<const float*>(peers->arena[r]);
+        for (int r = 0; r < peers->world && r < 8; ++r) {
+            A.peer[r] = reinterpret_cast<const float*>(peers->arena[r]);
+            A.signal[r] = reinterpret_cast<uint32_t*>(peers->signal[r]);
+        }
+        A.rank = peers->rank;
+        A.epoch = reinterpret_cast<int64_t*>(peers->epoch);
     }
     A.arena = arena;
     A.grad_off = L.grad_off; A.m_off = L.m_off; A.v_off = L.v_off;
@@ -1767,20 +1811,24 @@ static int recovery_apply_impl(const rrl_agent_config_t* cfg, float* arena, int6
     return 0;
 }
 
-static int peer_barrier_impl(const rrl_peers_t* peers, int64_t* epoch, int64_t* counters, int exchange, void* stream);
+static int peer_barrier_impl(const rrl_peers_t* peers, int64_t* epoch, int64_t* counters, int exchange, int gate_batch,
+                             double gate_pos_fraction, void* stream);
 extern "C" int rrl_peer_barrier(const rrl_peers_t* peers, int64_t* epoch, int64_t* counters, void* stream) {
-    return peer_barrier_impl(peers, epoch, counters, 0, stream);
+    return peer_barrier_impl(peers, epoch, counters, 0, 0, 0.0, stream);
 }
-extern "C" int rrl_peer_sync_gate_counts(const rrl_peers_t* peers, int64_t* epoch, int64_t* counters, void* stream) {
-    return peer_barrier_impl(peers, epoch, counters, 1, stream);
+extern "C" int rrl_peer_sync_gate_counts(const rrl_peers_t* peers, int64_t* epoch, int64_t* counters, int32_t gate_batch,
+                                         double gate_pos_fraction, void* stream) {
+    return peer_barrier_impl(peers, epoch, counters, 1, gate_batch, gate_pos_fraction, stream);
 }
-static int peer_barrier_impl(const rrl_peers_t* peers, int64_t* epoch, int64_t* counters, int exchange, void* stream) {
+static int peer_barrier_impl(const rrl_peers_t* peers, int64_t* epoch, int64_t* counters, int exchange, int gate_batch,
+                             double gate_pos_fraction, void* stream) {
     RRL_CHECK_ARG(peers && epoch && counters && peers->world >= 1 && peers->world <= 8 && peers->rank >= 0 &&
                       peers->rank < peers->world, "bad argument");
     PeerBarrierArgs A;
     memset(&A, 0, sizeof(A));
     for (int r = 0; r < peers->world; ++r) A.signal[r] = reinterpret_cast<uint32_t*>(peers->signal[r]);
     A.world = peers->world; A.rank = peers->rank; A.epoch = epoch; A.counters = counters; A.exchange = exchange;
+    A.gate_batch = gate_batch; A.gate_pos_fraction = gate_pos_fraction;
     peer_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(A);
     RRL_CHECK_LAUNCH();
     return 0;

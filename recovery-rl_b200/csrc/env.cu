@@ -64,9 +64,10 @@ __device__ __forceinline__ bool maze_touch(const EnvParams& P, double x, double 
 // Speculative chunks: v starts at 0 and v <- c_a*v + fb keeps the sign of fb, so every coordinate moves
 // MONOTONICALLY during one env step (rounding is monotone).  The positions tested inside a chunk of MAZE_CHUNK
 // substeps therefore lie in the box spanned by the chunk's first and last position.  A chunk is integrated
-// test-free; only if that box comes within R + 2e-6 of a solid (maze_may_touch) the lane runs the exact per-substep
-// test on the chunk's stored pre-integration positions (plus, rarely, chunks spent within 2e-6 of a solid without
-// touching), so all 32 envs of a warp run the same 500-substep schedule instead of serialising divergent test paths.
+// test-free; only if that box comes within R + 2e-6 of a solid (maze_may_touch) the lane rewinds and replays the
+// chunk with the exact per-substep test.  A lane replays the chunk in which it touches (plus, rarely, chunks
+// spent within 2e-6 of a solid without touching), so all 32 envs of a warp run the same 500-substep schedule
+// instead of serialising divergent test paths.
 constexpr int MAZE_CHUNK = 10;
 // Conservative pre-test in fp32 (FMA/ALU pipes, the fp64 pipe is the busy one): can ANY point of the box
 // [xl,xh]x[yl,yh] touch a solid?  Planes: threshold + 1e-6.  Walls: the distance from the box to the rectangle
@@ -97,89 +98,40 @@ __device__ __forceinline__ void maze_integrate(const EnvParams& P, double fbx, d
     x = __dadd_rn(x, __dmul_rn(P.h, vx));
     y = __dadd_rn(y, __dmul_rn(P.h, vy));
 }
-// branch-free form of maze_may_touch (same margins): straight-line fp32 code the scheduler can interleave with the fp64
-// dependency chains of the next chunk's integration
-__device__ __forceinline__ bool maze_may_touch_bf(const EnvParams& P, float xl, float xh, float yl, float yh) {
-    const bool planes = (xl <= P.f_plane_lo) | (xh >= P.f_plane_hi) | (yl <= P.f_plane_lo) | (yh >= P.f_plane_hi);
-    const float dx1 = fmaxf(fmaxf(P.f_wx0[0] - xh, xl - P.f_wx1[0]), 0.f);  // walls 1A / 1B share their x range
-    const float dx2 = fmaxf(fmaxf(P.f_wx0[2] - xh, xl - P.f_wx1[2]), 0.f);  // walls 2A / 2B
-    const float d0 = fmaxf(fmaxf(P.f_wy0[0] - yh, yl - P.f_wy1[0]), 0.f);
-    const float d1 = fmaxf(fmaxf(P.f_wy0[1] - yh, yl - P.f_wy1[1]), 0.f);
-    const float d2 = fmaxf(fmaxf(P.f_wy0[2] - yh, yl - P.f_wy1[2]), 0.f);
-    const float d3 = fmaxf(fmaxf(P.f_wy0[3] - yh, yl - P.f_wy1[3]), 0.f);
-    const float x1 = dx1 * dx1, x2 = dx2 * dx2;
-    const bool walls = (fmaf(d0, d0, x1) < P.f_rm2) | (fmaf(d1, d1, x1) < P.f_rm2) | (fmaf(d2, d2, x2) < P.f_rm2) |
-                       (fmaf(d3, d3, x2) < P.f_rm2);
-    return planes | walls;
-}
 __device__ __forceinline__ void maze_substeps_warp(const EnvParams& P, bool idle, double fbx, double fby, double& x,
                                                    double& y, bool& contact) {
     const int nsub = P.cfg.maze_substeps;
     double vx = 0.0, vy = 0.0;
     bool frozen = idle;  // idle lanes (beyond n) and lanes in contact do not move
-    int k = 0;
-    // Full chunks, software-pipelined by one chunk: chunk c is integrated test-free and its MAZE_CHUNK pre-integration
-    // positions are KEPT (registers: the loop is fully unrolled); the conservative fp32 box test of chunk c runs inside the
-    // straight-line code that integrates chunk c + 1 (independent instruction streams: the fp64 pipe and the fp32 / ALU pipes
-    // overlap).  A lane whose box can touch a solid runs the exact fp64 test on the stored positions of chunk c -- independent
-    // tests, no re-integration -- and freezes at the first one that touches; its speculative chunk c + 1 is then dropped.
-    // Frozen lanes compute along (their results are discarded by selects, not by branches).
-    double ax[MAZE_CHUNK], ay[MAZE_CHUNK], bx[MAZE_CHUNK], by[MAZE_CHUNK];   // ping-pong: positions of two consecutive chunks
-    float fx0 = 0.f, fx1 = 0.f, fy0 = 0.f, fy1 = 0.f;                          // box of the chunk whose test is pending
-    bool pending = false;
-    // exact tests of the pending chunk (positions qx / qy); true if the lane touched in it
-    auto resolve = [&](bool may, const double (&qx)[MAZE_CHUNK], const double (&qy)[MAZE_CHUNK]) -> bool {
-        bool hit = false;
-        if (__any_sync(0xffffffffu, may)) {
-            if (may) {
-                double hx = 0.0, hy = 0.0;
+    for (int k = 0; k < nsub; k += MAZE_CHUNK) {
+        const int c = min(MAZE_CHUNK, nsub - k);
+        const double sx = x, sy = y, svx = vx, svy = vy;
+        bool may = false;
+        if (!frozen) {
+            if (c == MAZE_CHUNK) {
 #pragma unroll
-                for (int j = MAZE_CHUNK - 1; j >= 0; --j)   // descending: the LOWEST touching substep wins
-                    if (maze_touch(P, qx[j], qy[j])) { hit = true; hx = qx[j]; hy = qy[j]; }
-                if (hit) { x = hx; y = hy; }
+                for (int j = 0; j < MAZE_CHUNK; ++j) maze_integrate(P, fbx, fby, x, y, vx, vy);
+            } else {
+                for (int j = 0; j < c; ++j) maze_integrate(P, fbx, fby, x, y, vx, vy);
             }
+            const float fx0 = (float)sx, fx1 = (float)x, fy0 = (float)sy, fy1 = (float)y;
+            may = maze_may_touch(P, fminf(fx0, fx1), fmaxf(fx0, fx1), fminf(fy0, fy1), fmaxf(fy0, fy1));
         }
-        return hit;
-    };
-    // one chunk: integrate into (cx, cy) while the pending chunk (qx, qy) is tested; returns true when every lane is frozen
-    auto chunk = [&](double (&cx)[MAZE_CHUNK], double (&cy)[MAZE_CHUNK], const double (&qx)[MAZE_CHUNK],
-                     const double (&qy)[MAZE_CHUNK]) -> bool {
-        double nx = x, ny = y, nvx = vx, nvy = vy;
-#pragma unroll
-        for (int j = 0; j < MAZE_CHUNK; ++j) {
-            cx[j] = nx; cy[j] = ny;
-            maze_integrate(P, fbx, fby, nx, ny, nvx, nvy);
+        if (__any_sync(0xffffffffu, may)) {
+            if (may) {  // rewind, replay the chunk with the exact test before every substep
+                x = sx; y = sy; vx = svx; vy = svy;
+                for (int j = 0; j < c; ++j) {
+                    if (maze_touch(P, x, y)) {
+                        frozen = true;
+                        contact = true;
+                        break;
+                    }
+                    maze_integrate(P, fbx, fby, x, y, vx, vy);
+                }
+            }
+            if (__all_sync(0xffffffffu, frozen)) break;
         }
-        // test of the previous chunk (same basic block as the integration above)
-        const bool may = pending & !frozen & maze_may_touch_bf(P, fminf(fx0, fx1), fmaxf(fx0, fx1), fminf(fy0, fy1), fmaxf(fy0, fy1));
-        if (resolve(may, qx, qy)) { frozen = true; contact = true; }
-        fx0 = (float)x; fy0 = (float)y;            // box of THIS chunk: from its start ...
-        if (!frozen) { x = nx; y = ny; vx = nvx; vy = nvy; }
-        fx1 = (float)nx; fy1 = (float)ny;          // ... to its end (unused once frozen)
-        pending = true;
-        return __all_sync(0xffffffffu, frozen);
-    };
-    bool last_in_a = false;
-    for (; k + 2 * MAZE_CHUNK <= nsub; k += 2 * MAZE_CHUNK) {
-        if (chunk(ax, ay, bx, by)) return;
-        if (chunk(bx, by, ax, ay)) return;
     }
-    if (k + MAZE_CHUNK <= nsub) {
-        if (chunk(ax, ay, bx, by)) return;
-        k += MAZE_CHUNK;
-        last_in_a = true;
-    }
-    if (pending) {   // the last full chunk
-        const bool may = !frozen & maze_may_touch_bf(P, fminf(fx0, fx1), fmaxf(fx0, fx1), fminf(fy0, fy1), fmaxf(fy0, fy1));
-        const bool hit = last_in_a ? resolve(may, ax, ay) : resolve(may, bx, by);
-        if (hit) { frozen = true; contact = true; }
-    }
-    // remainder (substep counts that are not a multiple of the chunk: tests only): exact test before every substep
-    if (!frozen)
-        for (; k < nsub; ++k) {
-            if (maze_touch(P, x, y)) { contact = true; break; }
-            maze_integrate(P, fbx, fby, x, y, vx, vy);
-        }
 }
 
 __device__ __forceinline__ void reset_state(const EnvParams& P, int64_t i, const double* draws, int64_t n,

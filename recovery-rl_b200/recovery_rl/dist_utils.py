@@ -66,9 +66,13 @@ class PeerArena(object):
         torch.cuda.synchronize(self.device)
         dist.barrier(group=group)
         h = self.handle
-        self.peers = native.make_peers(self.rank, list(h.buffer_ptrs), list(h.signal_pad_ptrs))
-        assert int(h.buffer_ptrs[self.rank]) == t.data_ptr()
         self.epoch = torch.zeros(1, dtype=torch.int64, device=self.device)
+        # `peers`: barriers are separate launches (rrl_peer_barrier);  `peers_fused`: the optimizer-step kernel runs the
+        # barrier itself (rrl_peers_t::epoch) -- same pads, same generation counter
+        self.peers = native.make_peers(self.rank, list(h.buffer_ptrs), list(h.signal_pad_ptrs))
+        self.peers_fused = native.make_peers(self.rank, list(h.buffer_ptrs), list(h.signal_pad_ptrs),
+                                             epoch_ptr=self.epoch.data_ptr())
+        assert int(h.buffer_ptrs[self.rank]) == t.data_ptr()
         self.tensor = t
         return t
 

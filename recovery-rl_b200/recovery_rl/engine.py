@@ -228,7 +228,8 @@ class VecEngine(object):
         if self.world == 1:
             return
         if self.peer_arena is not None:      # every rank's gradients are complete -> apply kernels read them in place
-            native.peer_barrier(self.peer_arena.peers, self.peer_arena.epoch, self.counters)
+            if not self.fused_barrier:       # (fused: the optimizer-step kernel runs the flag barrier itself)
+                native.peer_barrier(self.peer_arena.peers, self.peer_arena.epoch, self.counters)
             return
         if self._grad_views is None:
             self._grad_views = dist_utils.grad_ranges(self.cfg)
@@ -251,11 +252,19 @@ class VecEngine(object):
 
     @property
     def _peers(self):
-        return self.peer_arena.peers if self.peer_arena is not None else None
+        if self.peer_arena is None:
+            return None
+        return self.peer_arena.peers_fused if self.fused_barrier else self.peer_arena.peers
+
+    @property
+    def fused_barrier(self):
+        """peer mode on the tcgen05 path: the tiled optimizer-step kernel publishes / waits for the gradient flags itself"""
+        return self.peer_arena is not None and int(self.cfg.use_tensor_cores) >= 1
 
     def _sync_gate_counts(self):
         if self.peer_arena is not None:
-            native.peer_sync_gate_counts(self.peer_arena.peers, self.peer_arena.epoch, self.counters)
+            native.peer_sync_gate_counts(self.peer_arena.peers, self.peer_arena.epoch, self.counters, gate_batch=self.B,
+                                         gate_pos_fraction=self.gate_pos_fraction)
         elif self.world > 1:
             dist_utils.sync_gate_counts(self.counters, self.pg)
 
@@ -278,7 +287,7 @@ class VecEngine(object):
         native.recovery_backward(cfg, ar, cn, self.losses[8:], self._in("qr_eps_rec"), seed=self.seed, stream_id=self.rank)
         self._all_reduce(["recovery"])
         native.recovery_apply(cfg, ar, cn, peers=self._peers)
-        nb = 1 if self.peer_arena is not None else 0           # peer barrier kernels
+        nb = 1 if (self.peer_arena is not None and not self.fused_barrier) else 0           # peer barrier kernels
         # kernels launched (gpu_launches bookkeeping).  fused: the loss / sample-backward stages run as kernel tails and the
         # layer-1 backward in the epilogue of the backward GEMM -> fwd, fwd, bwd [, bwd] per update
         qr, rec = (3, 4) if self.fused else (5, 8)
@@ -304,7 +313,8 @@ class VecEngine(object):
             dist_utils.all_reduce_sum(f32[native.S_G_LOG_ALPHA:native.S_G_LOG_ALPHA + 1], self.pg)
             dist_utils.all_reduce_sum(f64[native.D_G_LOG_NU:native.D_G_LOG_LAMBDA + 1], self.pg)
         native.sac_apply(cfg, ar, cn, peers=self._peers)
-        return (4 if self.fused else 8) + 1 + (1 if self.scalar_algos else 0) + (1 if self.peer_arena is not None else 0)
+        return (4 if self.fused else 8) + 1 + (1 if self.scalar_algos else 0) + \
+            (1 if (self.peer_arena is not None and not self.fused_barrier) else 0)
 
     def sac_update(self):
         return self._sac_sample() + self._sac_compute()
@@ -341,6 +351,13 @@ class VecEngine(object):
         if self.online_qrisk:
             main.wait_event(self._ev_join)
             k += self._qr_compute()                                                # experiment.py:407-415
+        elif self.peer_arena is not None:
+            # ONE optimizer step per vector step (plain SAC / reward penalty / --disable_online_updates): nothing else keeps
+            # a fast rank from rewriting its gradient block (next step's backward) while a slow rank still sums it, so the
+            # step ends with a barrier of its own.  (With the Q_risk and recovery steps in between, a block is rewritten
+            # only after two later barriers.)
+            native.peer_barrier(self.peer_arena.peers, self.peer_arena.epoch, self.counters)
+            k += 1
         # (the fp16 hi/lo tcgen05 operand images are refreshed by the optimizer-step kernels themselves)
         native.agent_act(self.cfg, self.arena, self.n, self.state, self.counters, self.action_task, self.action_real,
                          self.recovery, self.qrisk, self._in("eps_task"), self._in("eps_rec"), self._in("rand_u"),

@@ -283,14 +283,17 @@ recovery_backward = _upd(None, "rrl_recovery_backward")
 
 class Peers(C.Structure):
     """rrl_peers_t: the ranks' arenas and signal pads as mapped in this process (symmetric memory)."""
-    _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("arena", C.c_uint64 * 8), ("signal", C.c_uint64 * 8)]
+    _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("arena", C.c_uint64 * 8), ("signal", C.c_uint64 * 8),
+                ("epoch", C.c_uint64)]
 
 
-def make_peers(rank, arena_ptrs, signal_ptrs):
+def make_peers(rank, arena_ptrs, signal_ptrs, epoch_ptr=0):
+    """epoch_ptr != 0: the optimizer-step kernels run the flag barrier themselves (rrl.h, rrl_peers_t::epoch)."""
     if not (1 <= len(arena_ptrs) <= 8 and len(arena_ptrs) == len(signal_ptrs)):
         raise RRLError("peer mode supports 1..8 ranks of one node")
     P = Peers()
     P.world, P.rank = len(arena_ptrs), int(rank)
+    P.epoch = int(epoch_ptr)
     for r, (a, s) in enumerate(zip(arena_ptrs, signal_ptrs)):
         P.arena[r], P.signal[r] = int(a), int(s)
     return P
@@ -300,8 +303,9 @@ def peer_barrier(peers, epoch, counters, stream=None):
     _check(lib().rrl_peer_barrier(C.byref(peers), p(epoch, "i64"), p(counters, "i64"), _stream(stream)), "rrl_peer_barrier")
 
 
-def peer_sync_gate_counts(peers, epoch, counters, stream=None):
-    _check(lib().rrl_peer_sync_gate_counts(C.byref(peers), p(epoch, "i64"), p(counters, "i64"), _stream(stream)),
+def peer_sync_gate_counts(peers, epoch, counters, gate_batch=0, gate_pos_fraction=0.0, stream=None):
+    _check(lib().rrl_peer_sync_gate_counts(C.byref(peers), p(epoch, "i64"), p(counters, "i64"), C.c_int32(int(gate_batch)),
+                                           C.c_double(float(gate_pos_fraction)), _stream(stream)),
            "rrl_peer_sync_gate_counts")
 
 
