@@ -61,6 +61,7 @@ struct TcSmem {
     unsigned char stage[NSTAGE][STAGE_BYTES];
     TcSmall sm;
     float4 part[2][4][TM];   // per-row partial head sums of the 4 column quarters (double-buffered)
+    float2 act[TM];          // the tile's task actions: epilogue role (lane = row) -> producer role (two other rows)
     unsigned long long full[NSTAGE], empty[NSTAGE], acc_full[2], acc_empty[2];
     uint32_t tmem_base;
 };
@@ -108,25 +109,27 @@ __device__ __forceinline__ const HeadW& pass_head(const ActArgs& a, int p) {
     return p == PASS_POL ? a.pol : (p == PASS_REC ? a.rec : (p == PASS_QR1 ? a.qr1 : a.qr2));
 }
 
-// producer: layer 1 of `pass`, row r, the 8 hidden units of core column q of k-chunk c -> stage (fp16 hi/lo,
-// canonical layout).  W1/b1 are staged pre-multiplied by SA (a power of two: exact).
-// layer 1 of `pass`, one row, the 8 hidden units of core column q of k-chunk c, as fp16 hi/lo (registers)
-__device__ __forceinline__ void layer1_chunk(const TcSmem& S, int pass, int c, int q, float x0, float x1, float x2, float x3,
-                                             bool four, uint4* hi, uint4* lo) {
-    float hv[8];
+// producer: layer 1 of `pass`, the 8 hidden units of core column q of k-chunk c for TWO rows, as fp16 hi/lo pieces of the
+// canonical A layout (registers).  W1 / b1 are staged pre-multiplied by SA (a power of two: exact) and read once for both rows.
+__device__ __forceinline__ void layer1_chunk2(const TcSmem& S, int pass, int c, int q, const float (&xa)[4], const float (&xb)[4],
+                                              bool four, uint4* hia, uint4* loa, uint4* hib, uint4* lob) {
+    float ha[8], hb[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
         const int k = c * KCH + q * 8 + e;
         const float4 wv = *reinterpret_cast<const float4*>(S.sm.W1[pass][k]);
-        float h = fmaf(wv.x, x0, S.sm.b1[pass][k]);
-        h = fmaf(wv.y, x1, h);
+        const float b = S.sm.b1[pass][k];
+        float u = fmaf(wv.x, xa[0], b), v = fmaf(wv.x, xb[0], b);
+        u = fmaf(wv.y, xa[1], u); v = fmaf(wv.y, xb[1], v);
         if (four) {
-            h = fmaf(wv.z, x2, h);
-            h = fmaf(wv.w, x3, h);
+            u = fmaf(wv.z, xa[2], u); v = fmaf(wv.z, xb[2], v);
+            u = fmaf(wv.w, xa[3], u); v = fmaf(wv.w, xb[3], v);
         }
-        hv[e] = fminf(fmaxf(h, 0.f), 60000.0f);
+        ha[e] = fminf(fmaxf(u, 0.f), 60000.0f);
+        hb[e] = fminf(fmaxf(v, 0.f), 60000.0f);
     }
-    split8(hv, hi, lo);
+    split8(ha, hia, loa);
+    split8(hb, hib, lob);
 }
 
 // epilogue: columns [64 q, 64 q + 64) of this thread's row of accumulator `d` -> partial head sums
@@ -209,7 +212,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) act_tc_kernel(const __grid_cons
     if (t < 2 && n_pass > 1) S.sm.log_std[t] = A.rec.log_std[t];
     if (t == 0) {
         for (int s = 0; s < NSTAGE; ++s) {
-            mbar_init(smem_u32(&S.full[s]), kProdWarps + 1);  // one arrival per producer warp + the loader's expect_tx arrival
+            mbar_init(smem_u32(&S.full[s]), kProdWarps / 2 + 1);  // the 8 producer warps of the chunk's group + the loader's expect_tx
             mbar_init(smem_u32(&S.empty[s]), 1);      // tcgen05.commit
         }
         for (int d = 0; d < 2; ++d) {
@@ -231,38 +234,47 @@ __global__ void __launch_bounds__(kTcThreads, 1) act_tc_kernel(const __grid_cons
     const bool random_phase = A.counters && !A.eval && (A.start_steps > A.counters[RRL_C_TOTAL_NUMSTEPS]);
 
     if (warp < kProd / 32) {
-        // ========== producer + epilogue: 4 threads (q = 0..3) per row r; TMEM lane quadrant = warp % 4 ==========
-        uint32_t it = 0;            // running (pass, chunk) index: stage = it % NSTAGE
+        // ========== producer + epilogue ==========
+        // epilogue role: 4 threads (q = 0..3) per row r; TMEM lane quadrant = warp % 4
+        // producer role: the two warp groups (warps 0-7 / 8-15) take alternate k-chunks; a thread stages core column pq of TWO
+        //                rows (pa, pa + 64) per chunk, so every W1 / b1 element it reads from shared memory serves two rows
+        uint32_t it = 0;            // running (pass, chunk) index of the tile loop: stage = it % NSTAGE
         uint32_t acc_use[2] = {0, 0};
         uint32_t n_epi = 0;         // epilogues done (selects the partial-sum buffer)
         const int q = warp >> 2, r = (warp & 3) * 32 + lane;
+        const int grp = warp >> 3, pq = (t & 255) >> 6, pa = t & 63, pb2 = pa + 64;
         const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const int64_t row = tile * TM + r;
             const bool live = row < A.n;
-            float sx = 0.f, sy = 0.f;
-            if (live) {  // torch.FloatTensor(state): fp64 -> fp32 (sac.py:137)
-                sx = (float)A.state[row];
-                sy = (float)A.state[A.n + row];
+            float xa[4] = {0.f, 0.f, 0.f, 0.f}, xb[4] = {0.f, 0.f, 0.f, 0.f};   // (s, a) of the producer role's two rows
+            {   // torch.FloatTensor(state): fp64 -> fp32 (sac.py:137)
+                const int64_t ra = tile * TM + pa, rb = tile * TM + pb2;
+                if (ra < A.n) { xa[0] = (float)A.state[ra]; xa[1] = (float)A.state[A.n + ra]; }
+                if (rb < A.n) { xb[0] = (float)A.state[rb]; xb[1] = (float)A.state[A.n + rb]; }
             }
             float at[2] = {0.f, 0.f}, ar[2] = {0.f, 0.f}, arec[2] = {0.f, 0.f};
             float q1 = 0.f, qmax = 0.f;
             bool rec = false;
-            auto produce_pass = [&](int pass, float x2, float x3) {
+            auto produce_pass = [&](int pass) {
                 const bool four = pass >= PASS_QR1;
-                // software pipeline: chunk c + 1 is computed between the stores of chunk c and their proxy fence
-                uint4 hi, lo;
-                layer1_chunk(S, pass, 0, q, sx, sy, x2, x3, four, &hi, &lo);
-                for (int c = 0; c < NCHUNK; ++c, ++it) {
-                    const int stage = it % NSTAGE;
-                    mbar_wait(smem_u32(&S.empty[stage]), ((it / NSTAGE) & 1) ^ 1);
+                // software pipeline: the group's next chunk is computed between the stores of a chunk and their proxy fence
+                uint4 hia, loa, hib, lob;
+                layer1_chunk2(S, pass, grp, pq, xa, xb, four, &hia, &loa, &hib, &lob);
+                for (int c = grp; c < NCHUNK; c += 2) {
+                    const uint32_t ic = it + c;
+                    const int stage = ic % NSTAGE;
+                    mbar_wait(smem_u32(&S.empty[stage]), ((ic / NSTAGE) & 1) ^ 1);
                     unsigned char* a_hi = S.stage[stage];
-                    *reinterpret_cast<uint4*>(a_hi + q * LBO_A + r * 16) = hi;
-                    *reinterpret_cast<uint4*>(a_hi + A_IMG + q * LBO_A + r * 16) = lo;
-                    if (c + 1 < NCHUNK) layer1_chunk(S, pass, c + 1, q, sx, sy, x2, x3, four, &hi, &lo);
+                    *reinterpret_cast<uint4*>(a_hi + pq * LBO_A + pa * 16) = hia;
+                    *reinterpret_cast<uint4*>(a_hi + A_IMG + pq * LBO_A + pa * 16) = loa;
+                    *reinterpret_cast<uint4*>(a_hi + pq * LBO_A + pb2 * 16) = hib;
+                    *reinterpret_cast<uint4*>(a_hi + A_IMG + pq * LBO_A + pb2 * 16) = lob;
+                    if (c + 2 < NCHUNK) layer1_chunk2(S, pass, c + 2, pq, xa, xb, four, &hia, &loa, &hib, &lob);
                     fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
                     mbar_arrive_warp(smem_u32(&S.full[stage]));
                 }
+                it += NCHUNK;
             };
             auto epilogue_pass = [&](int pass, int d, int n_out, float raw[4]) {
                 mbar_wait(smem_u32(&S.acc_full[d]), acc_use[d] & 1);
@@ -284,8 +296,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) act_tc_kernel(const __grid_cons
                 raw[3] = ((p0.w + p1.w) + (p2.w + p3.w)) + S.sm.b3[pass][3];
             };
             float raw[4];
-            produce_pass(PASS_POL, 0.f, 0.f);
-            if (n_pass > 1) produce_pass(PASS_REC, 0.f, 0.f);
+            produce_pass(PASS_POL);
+            if (n_pass > 1) produce_pass(PASS_REC);
             // ---- policy head (model.py:325-338) ----
             epilogue_pass(PASS_POL, 0, 4, raw);
             if (!random_phase) {
@@ -314,7 +326,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) act_tc_kernel(const __grid_cons
             }
             ar[0] = at[0]; ar[1] = at[1];
             if (n_pass > 1) {
-                produce_pass(PASS_QR1, at[0], at[1]);
+                // hand the task actions from the epilogue role (this thread's row r) to the producer role (rows pa, pa + 64).
+                // Reuse is safe: a thread reaches the next tile's exchange only after the MMAs of this tile's Q_risk passes,
+                // i.e. after every producer has read its two actions.
+                if (q == 0) S.act[r] = make_float2(at[0], at[1]);
+                asm volatile("bar.sync 5, %0;" ::"n"(kProd) : "memory");
+                {
+                    const float2 aa = S.act[pa], ab = S.act[pb2];
+                    xa[2] = aa.x; xa[3] = aa.y; xb[2] = ab.x; xb[3] = ab.y;
+                }
+                produce_pass(PASS_QR1);
                 // ---- recovery policy head (model.py:512-525) ----
                 epilogue_pass(PASS_REC, 1, 2, raw);
                 {
@@ -327,7 +348,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) act_tc_kernel(const __grid_cons
                     }
                     stoch_sample(raw, S.sm.log_std, e, A.sp, arec, mean_a, &lp);
                 }
-                produce_pass(PASS_QR2, at[0], at[1]);
+                produce_pass(PASS_QR2);
                 epilogue_pass(PASS_QR1, 0, 1, raw);
                 q1 = sigmoidf_(raw[0]);
                 epilogue_pass(PASS_QR2, 1, 1, raw);
