@@ -226,6 +226,15 @@ int rrl_agent_refresh(const rrl_agent_config_t* cfg, float* arena, void* stream)
  * recovery policy); call after an optimizer step when cfg->use_tensor_cores is set. */
 int rrl_agent_tc_refresh(const rrl_agent_config_t* cfg, float* arena, void* stream);
 
+/* Stages of the composite action, for callers that overlap acting with the updates (rrl_agent_act_stage): each stage only
+ * needs the networks named, so it can be enqueued right after THEIR optimizer step, next to the remaining updates.
+ * All three in one call == rrl_agent_act. */
+enum {
+    RRL_ACT_STAGE_POLICY = 1,    /* task policy (sac.py:133-168) or the start-phase random action -> action_task            */
+    RRL_ACT_STAGE_QRISK = 2,     /* Q_risk(s, action_task) (qrisk.py:184-196), threshold (experiment.py:555) -> qrisk_out, recovery */
+    RRL_ACT_STAGE_RECOVERY = 4,  /* recovery policy (qrisk.py:198-213), select -> action_real                                */
+    RRL_ACT_STAGE_ALL = 7
+};
 /* Composite action selection for N envs (experiment.py:546-577; sac.py:133-168;
  * qrisk.py:184-213; model.py:317-338, 512-525):
  *   a_task = tanh(mu + sigma*eps_task)*scale + bias   (or mean action when eval != 0;
@@ -238,6 +247,13 @@ int rrl_agent_act(const rrl_agent_config_t* cfg, float* arena, int64_t n, const 
                   int use_recovery, int eval, int64_t start_steps, uint64_t seed, int32_t stream_id,
                   const int64_t* counters, float* action_task, float* action_real,
                   uint8_t* recovery, float* qrisk_out, void* stream);
+/* The same, restricted to `stages` (RRL_ACT_STAGE_* bits; tcgen05 path only unless stages == RRL_ACT_STAGE_ALL) on at most
+ * `max_ctas` SMs (0: all): later stages read action_task / recovery written by the earlier ones. */
+int rrl_agent_act_stage(const rrl_agent_config_t* cfg, float* arena, int64_t n, const double* state,
+                  const float* eps_task, const float* eps_rec, const float* rand_u,
+                  int use_recovery, int eval, int64_t start_steps, uint64_t seed, int32_t stream_id,
+                  const int64_t* counters, float* action_task, float* action_real,
+                  uint8_t* recovery, float* qrisk_out, int stages, int max_ctas, void* stream);
 
 /* SAC.update_parameters (sac.py:170-277, ordering "Variant B" of SURVEY.md §8c) split so that
  * the host can all-reduce the gradient block between the two halves:

@@ -1282,6 +1282,15 @@ extern "C" int rrl_agent_act(const rrl_agent_config_t* cfg, float* arena, int64_
                              int eval, int64_t start_steps, uint64_t seed, int32_t stream_id, const int64_t* counters,
                              float* action_task, float* action_real, uint8_t* recovery, float* qrisk_out,
                              void* stream) {
+    return rrl_agent_act_stage(cfg, arena, n, state, eps_task, eps_rec, rand_u, use_recovery, eval, start_steps, seed, stream_id,
+                               counters, action_task, action_real, recovery, qrisk_out, RRL_ACT_STAGE_ALL, 0, stream);
+}
+
+extern "C" int rrl_agent_act_stage(const rrl_agent_config_t* cfg, float* arena, int64_t n, const double* state,
+                                   const float* eps_task, const float* eps_rec, const float* rand_u, int use_recovery,
+                                   int eval, int64_t start_steps, uint64_t seed, int32_t stream_id, const int64_t* counters,
+                                   float* action_task, float* action_real, uint8_t* recovery, float* qrisk_out, int stages,
+                                   int max_ctas, void* stream) {
     CHECK_CFG(cfg);
     RRL_CHECK_ARG(arena && state && action_task && action_real, "null argument");
     RRL_CHECK_ARG(n > 0, "n must be positive");
@@ -1299,7 +1308,8 @@ extern "C" int rrl_agent_act(const rrl_agent_config_t* cfg, float* arena, int64_
     A.eps_safe = cfg->eps_safe;
     A.sp = action_space(cfg);
     A.action_task = action_task; A.action_real = action_real; A.qrisk_out = qrisk_out; A.recovery = recovery;
-    if (cfg->use_tensor_cores) return act_tc_launch(A, arena, L, (cudaStream_t)stream);
+    if (cfg->use_tensor_cores) return act_tc_launch(A, arena, L, stages, max_ctas, (cudaStream_t)stream);
+    RRL_CHECK_ARG(stages == RRL_ACT_STAGE_ALL, "staged acting runs on the tcgen05 path only (use_tensor_cores >= 1)");
     static bool configured = false;
     const size_t smem = sizeof(FwdSmem<64>);
     if (!configured) {

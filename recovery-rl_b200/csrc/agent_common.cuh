@@ -234,7 +234,7 @@ int mpc_rollout_tc_launch(const MpcTcArgs& T, cudaStream_t st);
 int dyn_tc_images_launch(float* dyn_image, cudaStream_t st);
 
 // agent_tc.cu
-int act_tc_launch(const ActArgs& A, const float* arena, const Layout& L, cudaStream_t st);
+int act_tc_launch(const ActArgs& A, const float* arena, const Layout& L, int stages, int max_ctas, cudaStream_t st);
 int tc_images_launch(float* arena, const Layout& L, cudaStream_t st);
 int fwd_tc_launch(const FwdArgs& A, int64_t max_rows, cudaStream_t st);
 inline const __half* tc_img_of(const Layout& L, const float* arena, int net, int head) {

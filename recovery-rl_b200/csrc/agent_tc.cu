@@ -99,10 +99,16 @@ __global__ void __launch_bounds__(256) tc_images_kernel(const __grid_constant__ 
 }
 
 // ---- the acting kernel -----------------------------------------------------------------------------
+// Stages of the composite action (experiment.py:546-577).  All three in one launch reproduce the fused kernel; the vector
+// engine launches them separately so that each runs as soon as ITS networks have been stepped, next to the remaining updates
+// (task policy after the SAC step, Q_risk after the safety-critic step, recovery policy + select after the recovery step):
+//   ACT_STAGE_POLICY    task action (policy pass, or the uniform random action of the start phase)  -> action_task
+//   ACT_STAGE_QRISK     Q_risk(s, action_task) twin pass -> qrisk_out, recovery flag          (reads action_task)
+//   ACT_STAGE_RECOVERY  recovery policy pass, select  -> action_real          (reads action_task, recovery flag)
 struct TcActArgs {
     ActArgs a;
     const __half* img[4];  // by pass: POL, REC, QR1, QR2
-    int n_pass;            // 1 (no recovery) or 4
+    int stages;            // RRL_ACT_STAGE_* bits
 };
 
 __device__ __forceinline__ const HeadW& pass_head(const ActArgs& a, int p) {
@@ -177,11 +183,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) act_tc_kernel(const __grid_cons
     TcSmem& S = *reinterpret_cast<TcSmem*>(smem_raw);
     const ActArgs& A = T.a;
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
-    const int n_pass = T.n_pass;
     const int64_t n_tiles = (A.n + TM - 1) / TM;
+    // passes of this launch, in issue order (POL, REC, QR1, QR2); accumulator of a pass = its position & 1
+    const bool sP = (T.stages & RRL_ACT_STAGE_POLICY) != 0;
+    const bool sR = A.use_recovery && (T.stages & RRL_ACT_STAGE_RECOVERY) != 0;
+    const bool sQ = A.use_recovery && (T.stages & RRL_ACT_STAGE_QRISK) != 0;
+    int plist[4], n_pass = 0;
+    if (sP) plist[n_pass++] = PASS_POL;
+    if (sR) plist[n_pass++] = PASS_REC;
+    if (sQ) { plist[n_pass++] = PASS_QR1; plist[n_pass++] = PASS_QR2; }
+    const int dP = 0, dR = sP ? 1 : 0, dQ1 = ((sP ? 1 : 0) + (sR ? 1 : 0)) & 1, dQ2 = dQ1 ^ 1;
 
     // ---- one-time setup: small tensors, barriers, TMEM ----
-    for (int p = 0; p < n_pass; ++p) {
+    for (int pi = 0; pi < n_pass; ++pi) {
+        const int p = plist[pi];
         const HeadW& w = pass_head(A, p);
         for (int k = t; k < H; k += kTcThreads) {
             float4 w1 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -209,7 +224,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) act_tc_kernel(const __grid_cons
             S.sm.b3[p][t] = v;
         }
     }
-    if (t < 2 && n_pass > 1) S.sm.log_std[t] = A.rec.log_std[t];
+    if (t < 2 && sR) S.sm.log_std[t] = A.rec.log_std[t];
     if (t == 0) {
         for (int s = 0; s < NSTAGE; ++s) {
             mbar_init(smem_u32(&S.full[s]), kProdWarps / 2 + 1);  // the 8 producer warps of the chunk's group + the loader's expect_tx
@@ -296,71 +311,87 @@ __global__ void __launch_bounds__(kTcThreads, 1) act_tc_kernel(const __grid_cons
                 raw[3] = ((p0.w + p1.w) + (p2.w + p3.w)) + S.sm.b3[pass][3];
             };
             float raw[4];
-            produce_pass(PASS_POL);
-            if (n_pass > 1) produce_pass(PASS_REC);
-            // ---- policy head (model.py:325-338) ----
-            epilogue_pass(PASS_POL, 0, 4, raw);
-            if (!random_phase) {
-                float e[2], mean_a[2], lp;
-                if (A.eps_task) {
-                    const float2 ev = live ? reinterpret_cast<const float2*>(A.eps_task)[row] : make_float2(0.f, 0.f);
-                    e[0] = ev.x; e[1] = ev.y;
-                } else {
-                    philox_eps(A.seed, A.stream_id, (uint64_t)row, vstep, RRL_DRAW_ACT_TASK, e);
-                }
-                gauss_sample(raw, e, A.sp, at, &lp, mean_a);
-                if (A.eval) { at[0] = mean_a[0]; at[1] = mean_a[1]; }
-            } else {  // env.action_space.sample() (experiment.py:559-560)
-                float u[2] = {0.f, 0.f};
-                if (A.rand_u) {
-                    if (live) {
-                        const float2 uv = reinterpret_cast<const float2*>(A.rand_u)[row];
-                        u[0] = uv.x; u[1] = uv.y;
-                    }
-                } else {
-                    const Philox4 p = rrl_philox(A.seed, A.stream_id, (uint64_t)row, vstep, RRL_DRAW_ACT_RAND);
-                    u[0] = rrl_u24(p.x); u[1] = rrl_u24(p.y);
-                }
-                at[0] = fmaf(2.0f * u[0] - 1.0f, A.sp.scale[0], A.sp.bias[0]);
-                at[1] = fmaf(2.0f * u[1] - 1.0f, A.sp.scale[1], A.sp.bias[1]);
-            }
-            ar[0] = at[0]; ar[1] = at[1];
-            if (n_pass > 1) {
-                // hand the task actions from the epilogue role (this thread's row r) to the producer role (rows pa, pa + 64).
-                // Reuse is safe: a thread reaches the next tile's exchange only after the MMAs of this tile's Q_risk passes,
-                // i.e. after every producer has read its two actions.
-                if (q == 0) S.act[r] = make_float2(at[0], at[1]);
-                asm volatile("bar.sync 5, %0;" ::"n"(kProd) : "memory");
-                {
-                    const float2 aa = S.act[pa], ab = S.act[pb2];
-                    xa[2] = aa.x; xa[3] = aa.y; xb[2] = ab.x; xb[3] = ab.y;
-                }
-                produce_pass(PASS_QR1);
-                // ---- recovery policy head (model.py:512-525) ----
-                epilogue_pass(PASS_REC, 1, 2, raw);
-                {
+            if (sP) produce_pass(PASS_POL);
+            if (sR) produce_pass(PASS_REC);
+            if (sP) {
+                // ---- policy head (model.py:325-338) ----
+                epilogue_pass(PASS_POL, dP, 4, raw);
+                if (!random_phase) {
                     float e[2], mean_a[2], lp;
-                    if (A.eps_rec) {
-                        const float2 ev = live ? reinterpret_cast<const float2*>(A.eps_rec)[row] : make_float2(0.f, 0.f);
+                    if (A.eps_task) {
+                        const float2 ev = live ? reinterpret_cast<const float2*>(A.eps_task)[row] : make_float2(0.f, 0.f);
                         e[0] = ev.x; e[1] = ev.y;
                     } else {
-                        philox_eps(A.seed, A.stream_id, (uint64_t)row, vstep, RRL_DRAW_ACT_REC, e);
+                        philox_eps(A.seed, A.stream_id, (uint64_t)row, vstep, RRL_DRAW_ACT_TASK, e);
                     }
-                    stoch_sample(raw, S.sm.log_std, e, A.sp, arec, mean_a, &lp);
+                    gauss_sample(raw, e, A.sp, at, &lp, mean_a);
+                    if (A.eval) { at[0] = mean_a[0]; at[1] = mean_a[1]; }
+                } else {  // env.action_space.sample() (experiment.py:559-560)
+                    float u[2] = {0.f, 0.f};
+                    if (A.rand_u) {
+                        if (live) {
+                            const float2 uv = reinterpret_cast<const float2*>(A.rand_u)[row];
+                            u[0] = uv.x; u[1] = uv.y;
+                        }
+                    } else {
+                        const Philox4 p = rrl_philox(A.seed, A.stream_id, (uint64_t)row, vstep, RRL_DRAW_ACT_RAND);
+                        u[0] = rrl_u24(p.x); u[1] = rrl_u24(p.y);
+                    }
+                    at[0] = fmaf(2.0f * u[0] - 1.0f, A.sp.scale[0], A.sp.bias[0]);
+                    at[1] = fmaf(2.0f * u[1] - 1.0f, A.sp.scale[1], A.sp.bias[1]);
                 }
+            } else if (live) {   // a later stage: the task action of an earlier launch
+                const float2 av = reinterpret_cast<const float2*>(A.action_task)[row];
+                at[0] = av.x; at[1] = av.y;
+            }
+            ar[0] = at[0]; ar[1] = at[1];
+            if (sQ) {
+                if (sP) {
+                    // hand the task actions from the epilogue role (this thread's row r) to the producer role (rows pa, pa + 64).
+                    // Reuse is safe: a thread reaches the next tile's exchange only after the MMAs of this tile's Q_risk passes,
+                    // i.e. after every producer has read its two actions.
+                    if (q == 0) S.act[r] = make_float2(at[0], at[1]);
+                    asm volatile("bar.sync 5, %0;" ::"n"(kProd) : "memory");
+                    const float2 aa = S.act[pa], ab = S.act[pb2];
+                    xa[2] = aa.x; xa[3] = aa.y; xb[2] = ab.x; xb[3] = ab.y;
+                } else {
+                    const int64_t ra = tile * TM + pa, rb = tile * TM + pb2;
+                    if (ra < A.n) { const float2 aa = reinterpret_cast<const float2*>(A.action_task)[ra]; xa[2] = aa.x; xa[3] = aa.y; }
+                    if (rb < A.n) { const float2 ab = reinterpret_cast<const float2*>(A.action_task)[rb]; xb[2] = ab.x; xb[3] = ab.y; }
+                }
+                produce_pass(PASS_QR1);
+            }
+            if (sR) {
+                // ---- recovery policy head (model.py:512-525) ----
+                epilogue_pass(PASS_REC, dR, 2, raw);
+                float e[2], mean_a[2], lp;
+                if (A.eps_rec) {
+                    const float2 ev = live ? reinterpret_cast<const float2*>(A.eps_rec)[row] : make_float2(0.f, 0.f);
+                    e[0] = ev.x; e[1] = ev.y;
+                } else {
+                    philox_eps(A.seed, A.stream_id, (uint64_t)row, vstep, RRL_DRAW_ACT_REC, e);
+                }
+                stoch_sample(raw, S.sm.log_std, e, A.sp, arec, mean_a, &lp);
+            }
+            if (sQ) {
                 produce_pass(PASS_QR2);
-                epilogue_pass(PASS_QR1, 0, 1, raw);
+                epilogue_pass(PASS_QR1, dQ1, 1, raw);
                 q1 = sigmoidf_(raw[0]);
-                epilogue_pass(PASS_QR2, 1, 1, raw);
+                epilogue_pass(PASS_QR2, dQ2, 1, raw);
                 qmax = fmaxf(q1, sigmoidf_(raw[0]));   // qrisk.py:196
                 rec = qmax > A.eps_safe;               // experiment.py:555
-                if (rec) { ar[0] = arec[0]; ar[1] = arec[1]; }
+            } else if (sR && live) {
+                rec = A.recovery[row] != 0;            // decided by the Q_risk stage of an earlier launch
             }
+            if (rec) { ar[0] = arec[0]; ar[1] = arec[1]; }
             if (live && q == 0) {
-                reinterpret_cast<float2*>(A.action_task)[row] = make_float2(at[0], at[1]);
-                reinterpret_cast<float2*>(A.action_real)[row] = make_float2(ar[0], ar[1]);
-                if (A.recovery) A.recovery[row] = rec ? 1 : 0;
-                if (A.qrisk_out) A.qrisk_out[row] = qmax;
+                if (sP) reinterpret_cast<float2*>(A.action_task)[row] = make_float2(at[0], at[1]);
+                if (sQ) {
+                    if (A.recovery) A.recovery[row] = rec ? 1 : 0;
+                    if (A.qrisk_out) A.qrisk_out[row] = qmax;
+                }
+                // the executed action: decided once the recovery stage has run (or at once without a recovery policy)
+                if (sR || !A.use_recovery) reinterpret_cast<float2*>(A.action_real)[row] = make_float2(ar[0], ar[1]);
             }
         }
     } else if (warp == kProd / 32) {
@@ -369,8 +400,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) act_tc_kernel(const __grid_cons
             uint32_t it = 0;
             uint32_t acc_use[2] = {0, 0};
             for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                for (int p = 0; p < n_pass; ++p) {
-                    const int d = p & 1;  // POL -> 0, REC -> 1, QR1 -> 0, QR2 -> 1
+                for (int pi = 0; pi < n_pass; ++pi) {
+                    const int d = pi & 1;  // all stages: POL -> 0, REC -> 1, QR1 -> 0, QR2 -> 1
                     mbar_wait(smem_u32(&S.acc_empty[d]), (acc_use[d] & 1) ^ 1);
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + d * H;
@@ -402,8 +433,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) act_tc_kernel(const __grid_cons
         if (lane == 0) {
             uint32_t it = 0;
             for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                for (int p = 0; p < n_pass; ++p) {
-                    const unsigned char* img = reinterpret_cast<const unsigned char*>(T.img[p]);
+                for (int pi = 0; pi < n_pass; ++pi) {
+                    const unsigned char* img = reinterpret_cast<const unsigned char*>(T.img[plist[pi]]);
                     for (int c = 0; c < NCHUNK; ++c, ++it) {
                         const int stage = it % NSTAGE;
                         mbar_wait(smem_u32(&S.empty[stage]), ((it / NSTAGE) & 1) ^ 1);
@@ -1200,14 +1231,18 @@ int tc_images_launch(float* arena, const Layout& L, cudaStream_t st) {
     return 0;
 }
 
-int act_tc_launch(const ActArgs& A, const float* arena, const Layout& L, cudaStream_t st) {
+int act_tc_launch(const ActArgs& A, const float* arena, const Layout& L, int stages, int max_ctas, cudaStream_t st) {
     TcActArgs T;
     T.a = A;
     T.img[PASS_POL] = tc_img_of(L, arena, RRL_NET_POLICY, 0);   // pass order: POL, REC, QR1, QR2
     T.img[PASS_REC] = tc_img_of(L, arena, RRL_NET_RECOVERY, 0);
     T.img[PASS_QR1] = tc_img_of(L, arena, RRL_NET_QRISK, 0);
     T.img[PASS_QR2] = tc_img_of(L, arena, RRL_NET_QRISK, 1);
-    T.n_pass = A.use_recovery ? 4 : 1;
+    T.stages = stages;
+    if ((stages & ~RRL_ACT_STAGE_ALL) || !(stages & RRL_ACT_STAGE_ALL)) { rrl_set_error("act_tc_launch: bad stage mask %d", stages); return -2; }
+    if (!A.use_recovery && !(stages & RRL_ACT_STAGE_POLICY)) return 0;   // nothing to do: no Q_risk / recovery stages without a recovery policy
+    if ((stages & (RRL_ACT_STAGE_QRISK | RRL_ACT_STAGE_RECOVERY)) != (RRL_ACT_STAGE_QRISK | RRL_ACT_STAGE_RECOVERY) && A.use_recovery &&
+        !A.recovery) { rrl_set_error("act_tc_launch: staged acting needs the recovery flag array"); return -2; }
     static bool configured = false;
     const size_t smem = sizeof(TcSmem) + 128;
     if (!configured) {
@@ -1215,7 +1250,8 @@ int act_tc_launch(const ActArgs& A, const float* arena, const Layout& L, cudaStr
         configured = true;
     }
     const int64_t tiles = (A.n + TM - 1) / TM;
-    const int64_t sms = rrl_num_sms();
+    int64_t sms = rrl_num_sms();
+    if (max_ctas > 0 && max_ctas < sms) sms = max_ctas;
     const int grid = (int)(tiles < sms ? tiles : sms);
     act_tc_kernel<<<grid, kTcThreads, smem, st>>>(T);
     RRL_CHECK_LAUNCH();

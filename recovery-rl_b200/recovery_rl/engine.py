@@ -56,6 +56,7 @@ class VecEngine(object):
         self.start_steps = int(start_steps)
         self.relabel = not disable_action_relabeling            # experiment.py:438-441
         self.host_inputs = bool(host_inputs)
+        self.act_staging = True                                 # set False to act with the single fused launch
         self.fused = int(use_tensor_cores) >= 2                 # use_tensor_cores 2: tcgen05 + fused update stages
         self.log_outputs = bool(log_outputs) or self.host_inputs
         sc = ACTION_SCALE[env_name]
@@ -156,6 +157,10 @@ class VecEngine(object):
         self._side = torch.cuda.Stream(device=dev)
         self._ev_fork = torch.cuda.Event()
         self._ev_join = torch.cuda.Event()
+        self._side2 = torch.cuda.Stream(device=dev)           # staged acting (policy / Q_risk stages next to the updates)
+        self._ev_act = torch.cuda.Event()
+        self._ev_stage = [torch.cuda.Event(), torch.cuda.Event()]
+        self.stage_ctas = 128                                 # SMs a side-stream acting stage may occupy (148 - the updates' 16 + slack)
         self.launches_per_step = 0
         self._grad_views = None
 
@@ -257,6 +262,13 @@ class VecEngine(object):
         return self.peer_arena.peers_fused if self.fused_barrier else self.peer_arena.peers
 
     @property
+    def staged_act(self):
+        """acting split into stages that overlap the updates (see _enqueue_step): tcgen05 path, model-free recovery, online
+        safety-critic updates (every stage then follows an optimizer step of its own)"""
+        return (int(self.cfg.use_tensor_cores) >= 1 and self.use_recovery and self.mf_recovery and self.online_qrisk
+                and self.mpc is None and self.act_staging)
+
+    @property
     def fused_barrier(self):
         """peer mode on the tcgen05 path: the tiled optimizer-step kernel publishes / waits for the gradient flags itself"""
         return self.peer_arena is not None and int(self.cfg.use_tensor_cores) >= 1
@@ -279,11 +291,15 @@ class VecEngine(object):
                              cons_flags=self.cons_flags, chunk_counts=self.chunk_counts)
         return k + 1
 
-    def _qr_compute(self):
+    def _qr_compute(self, between=None):
+        """safety-critic step, then (MF recovery) the recovery-policy step on the post-step critic.  `between`: called
+        after the safety-critic optimizer step has been enqueued (staged acting forks its Q_risk stage there)."""
         cfg, ar, cn = self.cfg, self.arena, self.counters
         native.qrisk_backward(cfg, ar, cn, self.losses[8:], self._in("qr_eps_next"), seed=self.seed, stream_id=self.rank)
         self._all_reduce(["qrisk"])
         native.qrisk_apply(cfg, ar, cn, peers=self._peers)
+        if between is not None:
+            between()
         native.recovery_backward(cfg, ar, cn, self.losses[8:], self._in("qr_eps_rec"), seed=self.seed, stream_id=self.rank)
         self._all_reduce(["recovery"])
         native.recovery_apply(cfg, ar, cn, peers=self._peers)
@@ -348,21 +364,43 @@ class VecEngine(object):
                 k += self._qr_sample()
                 self._ev_join.record(self._side)
         k += self._sac_compute()                                                   # experiment.py:397-406
+        # Staged acting (tcgen05 path, MF recovery, online safety-critic updates): each stage of the composite action only
+        # needs SOME of the networks, so it is enqueued on a second side stream as soon as those have been stepped and runs
+        # on a bounded number of SMs NEXT TO the remaining (latency-bound, <= 16-CTA) update kernels:
+        #   task policy  after the SAC step        (while the safety critic is updated)
+        #   Q_risk       after the safety-critic step (while the recovery policy is updated)
+        #   recovery policy + select after the recovery step, on the main stream
+        # Same kernels, same arithmetic, same results as the fused launch; only the schedule differs.
+        staged = self.staged_act
+
+        def act_stage(stages, max_ctas=0):
+            native.agent_act(self.cfg, self.arena, self.n, self.state, self.counters, self.action_task, self.action_real,
+                             self.recovery, self.qrisk, self._in("eps_task"), self._in("eps_rec"), self._in("rand_u"),
+                             use_recovery=self.use_recovery, start_steps=self.start_steps, seed=self.seed,
+                             stream_id=self.rank, stages=stages, max_ctas=max_ctas)                  # experiment.py:419
+
+        def fork_stage(stages, slot):
+            ev = self._ev_stage[slot]
+            ev.record(main)
+            self._side2.wait_event(ev)
+            with torch.cuda.stream(self._side2):
+                act_stage(stages, self.stage_ctas)
+                self._ev_act.record(self._side2)
+
+        if staged:
+            fork_stage(native.ACT_STAGE_POLICY, 0)
+            k += 1
         if self.online_qrisk:
             main.wait_event(self._ev_join)
-            k += self._qr_compute()                                                # experiment.py:407-415
-        elif self.peer_arena is not None:
-            # ONE optimizer step per vector step (plain SAC / reward penalty / --disable_online_updates): nothing else keeps
-            # a fast rank from rewriting its gradient block (next step's backward) while a slow rank still sums it, so the
-            # step ends with a barrier of its own.  (With the Q_risk and recovery steps in between, a block is rewritten
-            # only after two later barriers.)
-            native.peer_barrier(self.peer_arena.peers, self.peer_arena.epoch, self.counters)
-            k += 1
+            k += self._qr_compute(between=(lambda: fork_stage(native.ACT_STAGE_QRISK, 1)) if staged else None)   # experiment.py:407-415
+            if staged:
+                k += 1
         # (the fp16 hi/lo tcgen05 operand images are refreshed by the optimizer-step kernels themselves)
-        native.agent_act(self.cfg, self.arena, self.n, self.state, self.counters, self.action_task, self.action_real,
-                         self.recovery, self.qrisk, self._in("eps_task"), self._in("eps_rec"), self._in("rand_u"),
-                         use_recovery=self.use_recovery, start_steps=self.start_steps, seed=self.seed,
-                         stream_id=self.rank)                                      # experiment.py:419
+        if staged:
+            main.wait_event(self._ev_act)                                          # the Q_risk stage (after the policy stage)
+            act_stage(native.ACT_STAGE_RECOVERY)
+        else:
+            act_stage(native.ACT_STAGE_ALL)
         a64 = None
         if self.mpc is not None:                                                   # experiment.py:568-573
             plan = self.mpc.plan(mask=self.recovery)

@@ -255,14 +255,18 @@ def agent_tc_refresh(cfg, arena, stream=None):
     _check(lib().rrl_agent_tc_refresh(C.byref(cfg), p(arena, "f32"), _stream(stream)), "rrl_agent_tc_refresh")
 
 
+ACT_STAGE_POLICY, ACT_STAGE_QRISK, ACT_STAGE_RECOVERY, ACT_STAGE_ALL = 1, 2, 4, 7
+
+
 def agent_act(cfg, arena, n, state, counters, action_task, action_real, recovery=None, qrisk_out=None,
               eps_task=None, eps_rec=None, rand_u=None, use_recovery=True, eval=False, start_steps=0, seed=0,
-              stream_id=0, stream=None):
-    _check(lib().rrl_agent_act(C.byref(cfg), p(arena, "f32"), C.c_int64(n), p(state, "f64"), p(eps_task, "f32"),
-                               p(eps_rec, "f32"), p(rand_u, "f32"), int(use_recovery), int(eval),
-                               C.c_int64(start_steps), C.c_uint64(seed & 0xFFFFFFFFFFFFFFFF), C.c_int32(stream_id),
-                               p(counters, "i64"), p(action_task, "f32"), p(action_real, "f32"), p(recovery, "u8"),
-                               p(qrisk_out, "f32"), _stream(stream)), "rrl_agent_act")
+              stream_id=0, stream=None, stages=ACT_STAGE_ALL, max_ctas=0):
+    """stages: ACT_STAGE_* bits (all: the fused composite action); max_ctas: SMs the launch may occupy (0: all)."""
+    _check(lib().rrl_agent_act_stage(C.byref(cfg), p(arena, "f32"), C.c_int64(n), p(state, "f64"), p(eps_task, "f32"),
+                                     p(eps_rec, "f32"), p(rand_u, "f32"), int(use_recovery), int(eval),
+                                     C.c_int64(start_steps), C.c_uint64(seed & 0xFFFFFFFFFFFFFFFF), C.c_int32(stream_id),
+                                     p(counters, "i64"), p(action_task, "f32"), p(action_real, "f32"), p(recovery, "u8"),
+                                     p(qrisk_out, "f32"), int(stages), int(max_ctas), _stream(stream)), "rrl_agent_act_stage")
 
 
 def _upd(fn, name):

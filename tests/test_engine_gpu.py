@@ -189,3 +189,45 @@ def test_eval_rollout_is_side_effect_free_and_uses_the_mean_action():
         assert all(k in e[0] for k in ("constraint", "reward", "state", "next_state", "action", "success", "recovery"))
     eps2 = eng.eval_rollout(16)
     assert len(eps2) == 16 and not np.array_equal(np.array([e[0]["state"] for e in eps2]), s0)    # fresh reset draws
+
+
+@pytest.mark.gpu
+def test_staged_acting_equals_fused_launch():
+    """the three acting stages enqueued next to the updates (policy after the SAC step, Q_risk after the safety-critic step,
+    recovery + select after the recovery step) leave exactly the state the single fused acting launch leaves."""
+    import numpy as np
+    import torch
+    from recovery_rl import native
+    from recovery_rl.engine import VecEngine
+    from env.maze import get_offline_data
+
+    def make(staging):
+        torch.manual_seed(1)
+        e = VecEngine("maze", 4096, batch_size=64, replay_size=32768, safe_replay_size=32768, gamma_safe=0.5, eps_safe=0.15,
+                      pos_fraction=0.3, seed=9, start_steps=4096 * 2, use_tensor_cores=2)      # two steps of the random phase
+        e.act_staging = staging
+        e.init_agent()
+        e.push_offline(get_offline_data(2000, rng=np.random.RandomState(4)))
+        e.pretrain_qrisk(5)
+        e.reset()
+        return e
+
+    a, b = make(False), make(True)
+    assert b.staged_act and not a.staged_act
+    for _ in range(3):
+        a.step(); b.step()
+    b.capture()
+    a.capture()
+    for _ in range(4):
+        a.replay(); b.replay()
+    torch.cuda.synchronize()
+    for name in ("action_task", "action_real", "recovery", "qrisk", "state", "ep_steps", "mt_state"):
+        assert torch.equal(getattr(a, name), getattr(b, name)), name
+    ca, cb = a.counters.clone(), b.counters.clone()
+    ca[native.C_RETURN_SUM_BITS] = cb[native.C_RETURN_SUM_BITS] = 0      # fp64 atomicAdd: order-dependent bits
+    assert torch.equal(ca, cb)
+    g = a.agent.grad_off
+    assert torch.equal(a.arena[:g].view(torch.int32), b.arena[:g].view(torch.int32))     # all six networks, bit-exact
+    c = b.read_counters()
+    assert c["error"] == 0 and c["sac_updates"] >= 6 and c["qrisk_updates"] >= 6 + 5
+    assert int(b.recovery.sum()) > 0                                      # the recovery branch was exercised
