@@ -247,7 +247,7 @@ int rrl_agent_act(const rrl_agent_config_t* cfg, float* arena, int64_t n, const 
                   int use_recovery, int eval, int64_t start_steps, uint64_t seed, int32_t stream_id,
                   const int64_t* counters, float* action_task, float* action_real,
                   uint8_t* recovery, float* qrisk_out, void* stream);
-/* The same, restricted to `stages` (RRL_ACT_STAGE_* bits; tcgen05 path only unless stages == RRL_ACT_STAGE_ALL) on at most
+/* The same, restricted to `stages` (ONE RRL_ACT_STAGE_* or RRL_ACT_STAGE_ALL; single stages on the tcgen05 path only) on at most
  * `max_ctas` SMs (0: all): later stages read action_task / recovery written by the earlier ones. */
 int rrl_agent_act_stage(const rrl_agent_config_t* cfg, float* arena, int64_t n, const double* state,
                   const float* eps_task, const float* eps_rec, const float* rand_u,

@@ -192,7 +192,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) act_tc_kernel(const __grid_cons
     if (sP) plist[n_pass++] = PASS_POL;
     if (sR) plist[n_pass++] = PASS_REC;
     if (sQ) { plist[n_pass++] = PASS_QR1; plist[n_pass++] = PASS_QR2; }
-    const int dP = 0, dR = sP ? 1 : 0, dQ1 = ((sP ? 1 : 0) + (sR ? 1 : 0)) & 1, dQ2 = dQ1 ^ 1;
 
     // ---- one-time setup: small tensors, barriers, TMEM ----
     for (int pi = 0; pi < n_pass; ++pi) {
@@ -253,45 +252,77 @@ __global__ void __launch_bounds__(kTcThreads, 1) act_tc_kernel(const __grid_cons
         // epilogue role: 4 threads (q = 0..3) per row r; TMEM lane quadrant = warp % 4
         // producer role: the two warp groups (warps 0-7 / 8-15) take alternate k-chunks; a thread stages core column pq of TWO
         //                rows (pa, pa + 64) per chunk, so every W1 / b1 element it reads from shared memory serves two rows
-        uint32_t it = 0;            // running (pass, chunk) index of the tile loop: stage = it % NSTAGE
+        // Schedule: the CTA's work is a flat list of items k = (tile, pass) in issue order; item k accumulates in TMEM buffer
+        // k & 1.  A thread runs  epilogue(k - 2); produce(k)  for k = 0, 1, ...: the epilogue of an item lags its production by
+        // two items, across tile boundaries as well, so the tensor pipe always has the next item's operands staged while the
+        // SIMT warps drain an accumulator (the MMAs of item k wait for buffer k & 1, released by epilogue(k - 2) just before).
+        // Within a tile this is the order POL, REC | epi POL | QR1 | epi REC | QR2 | epi QR1 | next POL | epi QR2 | ...
         uint32_t acc_use[2] = {0, 0};
         uint32_t n_epi = 0;         // epilogues done (selects the partial-sum buffer)
         const int q = warp >> 2, r = (warp & 3) * 32 + lane;
         const int grp = warp >> 3, pq = (t & 255) >> 6, pa = t & 63, pb2 = pa + 64;
         const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            const int64_t row = tile * TM + r;
-            const bool live = row < A.n;
-            float xa[4] = {0.f, 0.f, 0.f, 0.f}, xb[4] = {0.f, 0.f, 0.f, 0.f};   // (s, a) of the producer role's two rows
-            {   // torch.FloatTensor(state): fp64 -> fp32 (sac.py:137)
-                const int64_t ra = tile * TM + pa, rb = tile * TM + pb2;
+        const int64_t my_tiles = (int64_t)blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+        const int64_t n_items = my_tiles * n_pass;
+        float xa[4] = {0.f, 0.f, 0.f, 0.f}, xb[4] = {0.f, 0.f, 0.f, 0.f};   // producer role: (s, a) of its two rows, current tile
+        // epilogue role: state of the tile whose accumulators are being drained
+        float at[2] = {0.f, 0.f}, arec[2] = {0.f, 0.f};
+        float q1 = 0.f, qmax = 0.f;
+
+        auto produce_item = [&](int64_t k) {
+            const int pos = (int)(k % n_pass);
+            const int64_t tile = blockIdx.x + (k / n_pass) * gridDim.x;
+            const int pass = plist[pos];
+            const int64_t ra = tile * TM + pa, rb = tile * TM + pb2;
+            if (pos == 0) {   // torch.FloatTensor(state): fp64 -> fp32 (sac.py:137)
+                xa[0] = xa[1] = xb[0] = xb[1] = 0.f;
                 if (ra < A.n) { xa[0] = (float)A.state[ra]; xa[1] = (float)A.state[A.n + ra]; }
                 if (rb < A.n) { xb[0] = (float)A.state[rb]; xb[1] = (float)A.state[A.n + rb]; }
             }
-            float at[2] = {0.f, 0.f}, ar[2] = {0.f, 0.f}, arec[2] = {0.f, 0.f};
-            float q1 = 0.f, qmax = 0.f;
-            bool rec = false;
-            auto produce_pass = [&](int pass) {
-                const bool four = pass >= PASS_QR1;
-                // software pipeline: the group's next chunk is computed between the stores of a chunk and their proxy fence
-                uint4 hia, loa, hib, lob;
-                layer1_chunk2(S, pass, grp, pq, xa, xb, four, &hia, &loa, &hib, &lob);
-                for (int c = grp; c < NCHUNK; c += 2) {
-                    const uint32_t ic = it + c;
-                    const int stage = ic % NSTAGE;
-                    mbar_wait(smem_u32(&S.empty[stage]), ((ic / NSTAGE) & 1) ^ 1);
-                    unsigned char* a_hi = S.stage[stage];
-                    *reinterpret_cast<uint4*>(a_hi + pq * LBO_A + pa * 16) = hia;
-                    *reinterpret_cast<uint4*>(a_hi + A_IMG + pq * LBO_A + pa * 16) = loa;
-                    *reinterpret_cast<uint4*>(a_hi + pq * LBO_A + pb2 * 16) = hib;
-                    *reinterpret_cast<uint4*>(a_hi + A_IMG + pq * LBO_A + pb2 * 16) = lob;
-                    if (c + 2 < NCHUNK) layer1_chunk2(S, pass, c + 2, pq, xa, xb, four, &hia, &loa, &hib, &lob);
-                    fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
-                    mbar_arrive_warp(smem_u32(&S.full[stage]));
+            if (pass == PASS_QR1) {   // the task actions of the tile
+                xa[2] = xa[3] = xb[2] = xb[3] = 0.f;
+                if (sP) {
+                    // from the epilogue role (lane = row), which wrote them at the end of this tile's policy epilogue (two items
+                    // ago).  S.act is rewritten by the NEXT tile's policy epilogue, which needs that tile's policy MMAs, i.e.
+                    // every producer past this point.
+                    asm volatile("bar.sync 5, %0;" ::"n"(kProd) : "memory");
+                    const float2 aa = S.act[pa], ab = S.act[pb2];
+                    xa[2] = aa.x; xa[3] = aa.y; xb[2] = ab.x; xb[3] = ab.y;
+                } else {              // a later stage: from the policy stage's launch
+                    if (ra < A.n) { const float2 aa = reinterpret_cast<const float2*>(A.action_task)[ra]; xa[2] = aa.x; xa[3] = aa.y; }
+                    if (rb < A.n) { const float2 ab = reinterpret_cast<const float2*>(A.action_task)[rb]; xb[2] = ab.x; xb[3] = ab.y; }
                 }
-                it += NCHUNK;
-            };
-            auto epilogue_pass = [&](int pass, int d, int n_out, float raw[4]) {
+            }
+            const bool four = pass >= PASS_QR1;
+            const uint32_t it = (uint32_t)k * NCHUNK;    // running chunk index: stage = (it + c) % NSTAGE
+            // software pipeline: the group's next chunk is computed between the stores of a chunk and their proxy fence
+            uint4 hia, loa, hib, lob;
+            layer1_chunk2(S, pass, grp, pq, xa, xb, four, &hia, &loa, &hib, &lob);
+            for (int c = grp; c < NCHUNK; c += 2) {
+                const uint32_t ic = it + c;
+                const int stage = ic % NSTAGE;
+                mbar_wait(smem_u32(&S.empty[stage]), ((ic / NSTAGE) & 1) ^ 1);
+                unsigned char* a_hi = S.stage[stage];
+                *reinterpret_cast<uint4*>(a_hi + pq * LBO_A + pa * 16) = hia;
+                *reinterpret_cast<uint4*>(a_hi + A_IMG + pq * LBO_A + pa * 16) = loa;
+                *reinterpret_cast<uint4*>(a_hi + pq * LBO_A + pb2 * 16) = hib;
+                *reinterpret_cast<uint4*>(a_hi + A_IMG + pq * LBO_A + pb2 * 16) = lob;
+                if (c + 2 < NCHUNK) layer1_chunk2(S, pass, c + 2, pq, xa, xb, four, &hia, &loa, &hib, &lob);
+                fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+                mbar_arrive_warp(smem_u32(&S.full[stage]));
+            }
+        };
+
+        auto epilogue_item = [&](int64_t k) {
+            const int pos = (int)(k % n_pass);
+            const int64_t tile = blockIdx.x + (k / n_pass) * gridDim.x;
+            const int pass = plist[pos];
+            const int d = (int)(k & 1);
+            const int64_t row = tile * TM + r;
+            const bool live = row < A.n;
+            const int n_out = pass == PASS_POL ? 4 : (pass == PASS_REC ? 2 : 1);
+            float raw[4];
+            {
                 mbar_wait(smem_u32(&S.acc_full[d]), acc_use[d] & 1);
                 tc_fence_after();
                 const float4 mine = epilogue_quarter(S, pass, n_out, lane_addr + d * H, q);
@@ -309,13 +340,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) act_tc_kernel(const __grid_cons
                 raw[1] = ((p0.y + p1.y) + (p2.y + p3.y)) + S.sm.b3[pass][1];
                 raw[2] = ((p0.z + p1.z) + (p2.z + p3.z)) + S.sm.b3[pass][2];
                 raw[3] = ((p0.w + p1.w) + (p2.w + p3.w)) + S.sm.b3[pass][3];
-            };
-            float raw[4];
-            if (sP) produce_pass(PASS_POL);
-            if (sR) produce_pass(PASS_REC);
-            if (sP) {
+            }
+            if (pos == 0 && !sP) {   // a later stage: the task action of an earlier launch
+                at[0] = at[1] = 0.f;
+                if (live) {
+                    const float2 av = reinterpret_cast<const float2*>(A.action_task)[row];
+                    at[0] = av.x; at[1] = av.y;
+                }
+            }
+            if (pass == PASS_POL) {
                 // ---- policy head (model.py:325-338) ----
-                epilogue_pass(PASS_POL, dP, 4, raw);
                 if (!random_phase) {
                     float e[2], mean_a[2], lp;
                     if (A.eps_task) {
@@ -340,30 +374,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) act_tc_kernel(const __grid_cons
                     at[0] = fmaf(2.0f * u[0] - 1.0f, A.sp.scale[0], A.sp.bias[0]);
                     at[1] = fmaf(2.0f * u[1] - 1.0f, A.sp.scale[1], A.sp.bias[1]);
                 }
-            } else if (live) {   // a later stage: the task action of an earlier launch
-                const float2 av = reinterpret_cast<const float2*>(A.action_task)[row];
-                at[0] = av.x; at[1] = av.y;
-            }
-            ar[0] = at[0]; ar[1] = at[1];
-            if (sQ) {
-                if (sP) {
-                    // hand the task actions from the epilogue role (this thread's row r) to the producer role (rows pa, pa + 64).
-                    // Reuse is safe: a thread reaches the next tile's exchange only after the MMAs of this tile's Q_risk passes,
-                    // i.e. after every producer has read its two actions.
-                    if (q == 0) S.act[r] = make_float2(at[0], at[1]);
-                    asm volatile("bar.sync 5, %0;" ::"n"(kProd) : "memory");
-                    const float2 aa = S.act[pa], ab = S.act[pb2];
-                    xa[2] = aa.x; xa[3] = aa.y; xb[2] = ab.x; xb[3] = ab.y;
-                } else {
-                    const int64_t ra = tile * TM + pa, rb = tile * TM + pb2;
-                    if (ra < A.n) { const float2 aa = reinterpret_cast<const float2*>(A.action_task)[ra]; xa[2] = aa.x; xa[3] = aa.y; }
-                    if (rb < A.n) { const float2 ab = reinterpret_cast<const float2*>(A.action_task)[rb]; xb[2] = ab.x; xb[3] = ab.y; }
-                }
-                produce_pass(PASS_QR1);
-            }
-            if (sR) {
+                if (sQ && q == 0) S.act[r] = make_float2(at[0], at[1]);   // -> the producer role (produce_item, PASS_QR1)
+                if (live && q == 0) reinterpret_cast<float2*>(A.action_task)[row] = make_float2(at[0], at[1]);
+            } else if (pass == PASS_REC) {
                 // ---- recovery policy head (model.py:512-525) ----
-                epilogue_pass(PASS_REC, dR, 2, raw);
                 float e[2], mean_a[2], lp;
                 if (A.eps_rec) {
                     const float2 ev = live ? reinterpret_cast<const float2*>(A.eps_rec)[row] : make_float2(0.f, 0.f);
@@ -372,36 +386,38 @@ __global__ void __launch_bounds__(kTcThreads, 1) act_tc_kernel(const __grid_cons
                     philox_eps(A.seed, A.stream_id, (uint64_t)row, vstep, RRL_DRAW_ACT_REC, e);
                 }
                 stoch_sample(raw, S.sm.log_std, e, A.sp, arec, mean_a, &lp);
-            }
-            if (sQ) {
-                produce_pass(PASS_QR2);
-                epilogue_pass(PASS_QR1, dQ1, 1, raw);
+            } else if (pass == PASS_QR1) {
                 q1 = sigmoidf_(raw[0]);
-                epilogue_pass(PASS_QR2, dQ2, 1, raw);
+            } else {
                 qmax = fmaxf(q1, sigmoidf_(raw[0]));   // qrisk.py:196
-                rec = qmax > A.eps_safe;               // experiment.py:555
-            } else if (sR && live) {
-                rec = A.recovery[row] != 0;            // decided by the Q_risk stage of an earlier launch
             }
-            if (rec) { ar[0] = arec[0]; ar[1] = arec[1]; }
-            if (live && q == 0) {
-                if (sP) reinterpret_cast<float2*>(A.action_task)[row] = make_float2(at[0], at[1]);
+            if (pos == n_pass - 1 && live && q == 0) {   // last pass of the tile: decide and write
+                bool rec = false;
                 if (sQ) {
+                    rec = qmax > A.eps_safe;               // experiment.py:555
                     if (A.recovery) A.recovery[row] = rec ? 1 : 0;
                     if (A.qrisk_out) A.qrisk_out[row] = qmax;
+                } else if (sR) {
+                    rec = A.recovery[row] != 0;            // decided by the Q_risk stage of an earlier launch
                 }
                 // the executed action: decided once the recovery stage has run (or at once without a recovery policy)
-                if (sR || !A.use_recovery) reinterpret_cast<float2*>(A.action_real)[row] = make_float2(ar[0], ar[1]);
+                if (sR || !A.use_recovery)
+                    reinterpret_cast<float2*>(A.action_real)[row] = rec ? make_float2(arec[0], arec[1]) : make_float2(at[0], at[1]);
             }
+        };
+
+        for (int64_t k = 0; k < n_items + 2; ++k) {
+            if (k >= 2) epilogue_item(k - 2);
+            if (k < n_items) produce_item(k);
         }
     } else if (warp == kProd / 32) {
         // ================= MMA issuer (one thread) =================
         if (lane == 0) {
-            uint32_t it = 0;
+            uint32_t it = 0, item = 0;
             uint32_t acc_use[2] = {0, 0};
             for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                for (int pi = 0; pi < n_pass; ++pi) {
-                    const int d = pi & 1;  // all stages: POL -> 0, REC -> 1, QR1 -> 0, QR2 -> 1
+                for (int pi = 0; pi < n_pass; ++pi, ++item) {
+                    const int d = item & 1;  // accumulator = item parity (four passes per tile: POL -> 0, REC -> 1, QR1 -> 0, QR2 -> 1)
                     mbar_wait(smem_u32(&S.acc_empty[d]), (acc_use[d] & 1) ^ 1);
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + d * H;
@@ -1239,7 +1255,12 @@ int act_tc_launch(const ActArgs& A, const float* arena, const Layout& L, int sta
     T.img[PASS_QR1] = tc_img_of(L, arena, RRL_NET_QRISK, 0);
     T.img[PASS_QR2] = tc_img_of(L, arena, RRL_NET_QRISK, 1);
     T.stages = stages;
-    if ((stages & ~RRL_ACT_STAGE_ALL) || !(stages & RRL_ACT_STAGE_ALL)) { rrl_set_error("act_tc_launch: bad stage mask %d", stages); return -2; }
+    // one stage, or all of them: the kernel's schedule (epilogue two items behind production) relies on the recovery pass
+    // sitting between the policy pass and the Q_risk passes that consume its action
+    if (stages != RRL_ACT_STAGE_POLICY && stages != RRL_ACT_STAGE_QRISK && stages != RRL_ACT_STAGE_RECOVERY && stages != RRL_ACT_STAGE_ALL) {
+        rrl_set_error("act_tc_launch: stages must be one RRL_ACT_STAGE_* or RRL_ACT_STAGE_ALL (got %d)", stages);
+        return -2;
+    }
     if (!A.use_recovery && !(stages & RRL_ACT_STAGE_POLICY)) return 0;   // nothing to do: no Q_risk / recovery stages without a recovery policy
     if ((stages & (RRL_ACT_STAGE_QRISK | RRL_ACT_STAGE_RECOVERY)) != (RRL_ACT_STAGE_QRISK | RRL_ACT_STAGE_RECOVERY) && A.use_recovery &&
         !A.recovery) { rrl_set_error("act_tc_launch: staged acting needs the recovery flag array"); return -2; }
