@@ -47,6 +47,7 @@ __device__ unsigned int g_tc_done;
 #endif
 
 enum { PASS_POL = 0, PASS_REC = 1, PASS_QR1 = 2, PASS_QR2 = 3 };
+constexpr int kActProdWarps = 8, kActEpiWarps = 8;   // acting kernel: warps 0-7 stage operands, warps 8-15 drain accumulators
 
 struct TcSmall {
     float W1[4][H][4];
@@ -60,7 +61,7 @@ struct TcSmall {
 struct TcSmem {
     unsigned char stage[NSTAGE][STAGE_BYTES];
     TcSmall sm;
-    float4 part[2][4][TM];   // per-row partial head sums of the 4 column quarters (double-buffered)
+    float4 part[2][2][TM];   // per-row partial head sums of the 2 column halves (double-buffered)
     float2 act[TM];          // the tile's task actions: epilogue role (lane = row) -> producer role (two other rows)
     unsigned long long full[NSTAGE], empty[NSTAGE], acc_full[2], acc_empty[2];
     uint32_t tmem_base;
@@ -138,8 +139,10 @@ __device__ __forceinline__ void layer1_chunk2(const TcSmem& S, int pass, int c, 
     split8(hb, hib, lob);
 }
 
-// epilogue: columns [64 q, 64 q + 64) of this thread's row of accumulator `d` -> partial head sums
-__device__ __forceinline__ float4 epilogue_quarter(TcSmem& S, int pass, int n_out, uint32_t taddr, int q) {
+// epilogue: N_BLK 32-column blocks starting at column col_begin of this thread's row of an accumulator -> partial head sums
+// (bias + ReLU of layer 2, dot products with the N_OUT head rows)
+template <int N_OUT, int N_BLK>
+__device__ __forceinline__ float4 epilogue_cols(TcSmem& S, int pass, uint32_t taddr, int col_begin) {
     float out[4] = {0.f, 0.f, 0.f, 0.f};
     const float4* b2v = reinterpret_cast<const float4*>(S.sm.b2[pass]);
     const float4* w0v = reinterpret_cast<const float4*>(S.sm.w3[pass][0]);
@@ -147,9 +150,9 @@ __device__ __forceinline__ float4 epilogue_quarter(TcSmem& S, int pass, int n_ou
     const float4* w2v = reinterpret_cast<const float4*>(S.sm.w3[pass][2]);
     const float4* w3v = reinterpret_cast<const float4*>(S.sm.w3[pass][3]);
 #pragma unroll 1
-    for (int cc = 0; cc < 2; ++cc) {
+    for (int cc = 0; cc < N_BLK; ++cc) {
         float v[32];
-        const int col0 = q * 64 + cc * 32;
+        const int col0 = col_begin + cc * 32;
         tmem_ld32(taddr + col0, v);
         tmem_ld_wait();
 #pragma unroll
@@ -162,11 +165,11 @@ __device__ __forceinline__ float4 epilogue_quarter(TcSmem& S, int pass, int n_ou
             const float h3 = fmaxf(fmaf(v[4 * j4 + 3], INV_SCALE, b.w), 0.f);
             const float4 wa = w0v[i4];
             out[0] = fmaf(h3, wa.w, fmaf(h2, wa.z, fmaf(h1, wa.y, fmaf(h0, wa.x, out[0]))));
-            if (n_out > 1) {
+            if (N_OUT > 1) {
                 const float4 wb = w1v[i4];
                 out[1] = fmaf(h3, wb.w, fmaf(h2, wb.z, fmaf(h1, wb.y, fmaf(h0, wb.x, out[1]))));
             }
-            if (n_out > 2) {
+            if (N_OUT > 2) {
                 const float4 wc = w2v[i4], wd = w3v[i4];
                 out[2] = fmaf(h3, wc.w, fmaf(h2, wc.z, fmaf(h1, wc.y, fmaf(h0, wc.x, out[2]))));
                 out[3] = fmaf(h3, wd.w, fmaf(h2, wd.z, fmaf(h1, wd.y, fmaf(h0, wd.x, out[3]))));
@@ -226,12 +229,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) act_tc_kernel(const __grid_cons
     if (t < 2 && sR) S.sm.log_std[t] = A.rec.log_std[t];
     if (t == 0) {
         for (int s = 0; s < NSTAGE; ++s) {
-            mbar_init(smem_u32(&S.full[s]), kProdWarps / 2 + 1);  // the 8 producer warps of the chunk's group + the loader's expect_tx
+            mbar_init(smem_u32(&S.full[s]), kActProdWarps + 1);   // the producer warps + the loader's expect_tx arrival
             mbar_init(smem_u32(&S.empty[s]), 1);      // tcgen05.commit
         }
         for (int d = 0; d < 2; ++d) {
             mbar_init(smem_u32(&S.acc_full[d]), 1);   // tcgen05.commit
-            mbar_init(smem_u32(&S.acc_empty[d]), kProdWarps); // one arrival per epilogue warp
+            mbar_init(smem_u32(&S.acc_empty[d]), kActEpiWarps);   // one arrival per epilogue warp
         }
         fence_barrier_init();
     }
@@ -248,167 +251,168 @@ __global__ void __launch_bounds__(kTcThreads, 1) act_tc_kernel(const __grid_cons
     const bool random_phase = A.counters && !A.eval && (A.start_steps > A.counters[RRL_C_TOTAL_NUMSTEPS]);
 
     if (warp < kProd / 32) {
-        // ========== producer + epilogue ==========
-        // epilogue role: 4 threads (q = 0..3) per row r; TMEM lane quadrant = warp % 4
-        // producer role: the two warp groups (warps 0-7 / 8-15) take alternate k-chunks; a thread stages core column pq of TWO
-        //                rows (pa, pa + 64) per chunk, so every W1 / b1 element it reads from shared memory serves two rows
-        // Schedule: the CTA's work is a flat list of items k = (tile, pass) in issue order; item k accumulates in TMEM buffer
-        // k & 1.  A thread runs  epilogue(k - 2); produce(k)  for k = 0, 1, ...: the epilogue of an item lags its production by
-        // two items, across tile boundaries as well, so the tensor pipe always has the next item's operands staged while the
-        // SIMT warps drain an accumulator (the MMAs of item k wait for buffer k & 1, released by epilogue(k - 2) just before).
-        // Within a tile this is the order POL, REC | epi POL | QR1 | epi REC | QR2 | epi QR1 | next POL | epi QR2 | ...
-        uint32_t acc_use[2] = {0, 0};
-        uint32_t n_epi = 0;         // epilogues done (selects the partial-sum buffer)
-        const int q = warp >> 2, r = (warp & 3) * 32 + lane;
-        const int grp = warp >> 3, pq = (t & 255) >> 6, pa = t & 63, pb2 = pa + 64;
-        const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+        // ========== producer warps (0-7) and epilogue warps (8-15) ==========
+        // The CTA's work is a flat list of items k = (tile, pass) in issue order; item k accumulates in TMEM buffer k & 1.
+        //   producer warps: a thread stages core column pq of TWO rows (pa, pa + 64) of every k-chunk (W1 / b1 are read from
+        //                   shared memory once for both rows); they never touch TMEM and run ahead of the MMAs by the depth of
+        //                   the operand ring, across passes and tiles
+        //   epilogue warps: two per TMEM lane quadrant (lane = row r), each draining one 128-column half of the accumulator:
+        //                   bias + ReLU + head dot products, the halves exchanged through shared memory, then the head maths
+        // The only hand-off from the epilogue to the producer role is the tile's task action (the Q_risk passes' input), through
+        // S.act and named barrier 5 (all 512 threads): the epilogue warps arrive after the policy head of tile t, the producers
+        // before staging its first Q_risk chunk.
         const int64_t my_tiles = (int64_t)blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
         const int64_t n_items = my_tiles * n_pass;
-        float xa[4] = {0.f, 0.f, 0.f, 0.f}, xb[4] = {0.f, 0.f, 0.f, 0.f};   // producer role: (s, a) of its two rows, current tile
-        // epilogue role: state of the tile whose accumulators are being drained
-        float at[2] = {0.f, 0.f}, arec[2] = {0.f, 0.f};
-        float q1 = 0.f, qmax = 0.f;
-
-        auto produce_item = [&](int64_t k) {
-            const int pos = (int)(k % n_pass);
-            const int64_t tile = blockIdx.x + (k / n_pass) * gridDim.x;
-            const int pass = plist[pos];
-            const int64_t ra = tile * TM + pa, rb = tile * TM + pb2;
-            if (pos == 0) {   // torch.FloatTensor(state): fp64 -> fp32 (sac.py:137)
-                xa[0] = xa[1] = xb[0] = xb[1] = 0.f;
-                if (ra < A.n) { xa[0] = (float)A.state[ra]; xa[1] = (float)A.state[A.n + ra]; }
-                if (rb < A.n) { xb[0] = (float)A.state[rb]; xb[1] = (float)A.state[A.n + rb]; }
-            }
-            if (pass == PASS_QR1) {   // the task actions of the tile
-                xa[2] = xa[3] = xb[2] = xb[3] = 0.f;
-                if (sP) {
-                    // from the epilogue role (lane = row), which wrote them at the end of this tile's policy epilogue (two items
-                    // ago).  S.act is rewritten by the NEXT tile's policy epilogue, which needs that tile's policy MMAs, i.e.
-                    // every producer past this point.
-                    asm volatile("bar.sync 5, %0;" ::"n"(kProd) : "memory");
-                    const float2 aa = S.act[pa], ab = S.act[pb2];
-                    xa[2] = aa.x; xa[3] = aa.y; xb[2] = ab.x; xb[3] = ab.y;
-                } else {              // a later stage: from the policy stage's launch
-                    if (ra < A.n) { const float2 aa = reinterpret_cast<const float2*>(A.action_task)[ra]; xa[2] = aa.x; xa[3] = aa.y; }
-                    if (rb < A.n) { const float2 ab = reinterpret_cast<const float2*>(A.action_task)[rb]; xb[2] = ab.x; xb[3] = ab.y; }
+        if (warp < kActProdWarps) {
+            const int pq = t >> 6, pa = t & 63, pb2 = pa + 64;
+            float xa[4] = {0.f, 0.f, 0.f, 0.f}, xb[4] = {0.f, 0.f, 0.f, 0.f};   // (s, a) of the thread's two rows, current tile
+            for (int64_t k = 0; k < n_items; ++k) {
+                const int pos = (int)(k % n_pass);
+                const int64_t tile = blockIdx.x + (k / n_pass) * gridDim.x;
+                const int pass = plist[pos];
+                const int64_t ra = tile * TM + pa, rb = tile * TM + pb2;
+                if (pos == 0) {   // torch.FloatTensor(state): fp64 -> fp32 (sac.py:137)
+                    xa[0] = xa[1] = xb[0] = xb[1] = 0.f;
+                    if (ra < A.n) { xa[0] = (float)A.state[ra]; xa[1] = (float)A.state[A.n + ra]; }
+                    if (rb < A.n) { xb[0] = (float)A.state[rb]; xb[1] = (float)A.state[A.n + rb]; }
+                }
+                if (pass == PASS_QR1) {   // the task actions of the tile
+                    xa[2] = xa[3] = xb[2] = xb[3] = 0.f;
+                    if (sP) {
+                        asm volatile("bar.sync 5, %0;" ::"n"(kProd) : "memory");     // written by the epilogue warps (policy head)
+                        const float2 aa = S.act[pa], ab = S.act[pb2];
+                        xa[2] = aa.x; xa[3] = aa.y; xb[2] = ab.x; xb[3] = ab.y;
+                    } else {              // a later stage: from the policy stage's launch
+                        if (ra < A.n) { const float2 aa = reinterpret_cast<const float2*>(A.action_task)[ra]; xa[2] = aa.x; xa[3] = aa.y; }
+                        if (rb < A.n) { const float2 ab = reinterpret_cast<const float2*>(A.action_task)[rb]; xb[2] = ab.x; xb[3] = ab.y; }
+                    }
+                }
+                const bool four = pass >= PASS_QR1;
+                const uint32_t it = (uint32_t)k * NCHUNK;    // running chunk index: stage = (it + c) % NSTAGE
+                // software pipeline: the next chunk is computed between the stores of a chunk and their proxy fence
+                uint4 hia, loa, hib, lob;
+                layer1_chunk2(S, pass, 0, pq, xa, xb, four, &hia, &loa, &hib, &lob);
+                for (int c = 0; c < NCHUNK; ++c) {
+                    const uint32_t ic = it + c;
+                    const int stage = ic % NSTAGE;
+                    mbar_wait(smem_u32(&S.empty[stage]), ((ic / NSTAGE) & 1) ^ 1);
+                    unsigned char* a_hi = S.stage[stage];
+                    *reinterpret_cast<uint4*>(a_hi + pq * LBO_A + pa * 16) = hia;
+                    *reinterpret_cast<uint4*>(a_hi + A_IMG + pq * LBO_A + pa * 16) = loa;
+                    *reinterpret_cast<uint4*>(a_hi + pq * LBO_A + pb2 * 16) = hib;
+                    *reinterpret_cast<uint4*>(a_hi + A_IMG + pq * LBO_A + pb2 * 16) = lob;
+                    if (c + 1 < NCHUNK) layer1_chunk2(S, pass, c + 1, pq, xa, xb, four, &hia, &loa, &hib, &lob);
+                    fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+                    mbar_arrive_warp(smem_u32(&S.full[stage]));
                 }
             }
-            const bool four = pass >= PASS_QR1;
-            const uint32_t it = (uint32_t)k * NCHUNK;    // running chunk index: stage = (it + c) % NSTAGE
-            // software pipeline: the group's next chunk is computed between the stores of a chunk and their proxy fence
-            uint4 hia, loa, hib, lob;
-            layer1_chunk2(S, pass, grp, pq, xa, xb, four, &hia, &loa, &hib, &lob);
-            for (int c = grp; c < NCHUNK; c += 2) {
-                const uint32_t ic = it + c;
-                const int stage = ic % NSTAGE;
-                mbar_wait(smem_u32(&S.empty[stage]), ((ic / NSTAGE) & 1) ^ 1);
-                unsigned char* a_hi = S.stage[stage];
-                *reinterpret_cast<uint4*>(a_hi + pq * LBO_A + pa * 16) = hia;
-                *reinterpret_cast<uint4*>(a_hi + A_IMG + pq * LBO_A + pa * 16) = loa;
-                *reinterpret_cast<uint4*>(a_hi + pq * LBO_A + pb2 * 16) = hib;
-                *reinterpret_cast<uint4*>(a_hi + A_IMG + pq * LBO_A + pb2 * 16) = lob;
-                if (c + 2 < NCHUNK) layer1_chunk2(S, pass, c + 2, pq, xa, xb, four, &hia, &loa, &hib, &lob);
-                fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
-                mbar_arrive_warp(smem_u32(&S.full[stage]));
-            }
-        };
-
-        auto epilogue_item = [&](int64_t k) {
-            const int pos = (int)(k % n_pass);
-            const int64_t tile = blockIdx.x + (k / n_pass) * gridDim.x;
-            const int pass = plist[pos];
-            const int d = (int)(k & 1);
-            const int64_t row = tile * TM + r;
-            const bool live = row < A.n;
-            const int n_out = pass == PASS_POL ? 4 : (pass == PASS_REC ? 2 : 1);
-            float raw[4];
-            {
-                mbar_wait(smem_u32(&S.acc_full[d]), acc_use[d] & 1);
-                tc_fence_after();
-                const float4 mine = epilogue_quarter(S, pass, n_out, lane_addr + d * H, q);
-                tc_fence_before();
-                mbar_arrive_warp(smem_u32(&S.acc_empty[d]));
-                ++acc_use[d];
-                // exchange the four column quarters of the row; every thread of the row then holds the full sums
-                const int pb = n_epi & 1;
-                ++n_epi;
-                S.part[pb][q][r] = mine;
-                // only the four warps of this TMEM lane quadrant exchange (rows r of quadrant warp & 3)
-                asm volatile("bar.sync %0, 128;" ::"r"(1 + (warp & 3)) : "memory");
-                const float4 p0 = S.part[pb][0][r], p1 = S.part[pb][1][r], p2 = S.part[pb][2][r], p3 = S.part[pb][3][r];
-                raw[0] = ((p0.x + p1.x) + (p2.x + p3.x)) + S.sm.b3[pass][0];
-                raw[1] = ((p0.y + p1.y) + (p2.y + p3.y)) + S.sm.b3[pass][1];
-                raw[2] = ((p0.z + p1.z) + (p2.z + p3.z)) + S.sm.b3[pass][2];
-                raw[3] = ((p0.w + p1.w) + (p2.w + p3.w)) + S.sm.b3[pass][3];
-            }
-            if (pos == 0 && !sP) {   // a later stage: the task action of an earlier launch
-                at[0] = at[1] = 0.f;
-                if (live) {
-                    const float2 av = reinterpret_cast<const float2*>(A.action_task)[row];
-                    at[0] = av.x; at[1] = av.y;
+        } else {
+            const int ew = warp - kActProdWarps;                 // 0..7
+            const int hq = ew >> 2, r = (ew & 3) * 32 + lane;    // column half, row (TMEM lane quadrant = warp % 4 = ew % 4)
+            const uint32_t lane_addr = tmem_base + ((uint32_t)((ew & 3) * 32) << 16);
+            uint32_t acc_use[2] = {0, 0};
+            uint32_t n_epi = 0;         // epilogues done (selects the partial-sum buffer)
+            float at[2] = {0.f, 0.f}, arec[2] = {0.f, 0.f};      // state of the tile whose accumulators are being drained
+            float q1 = 0.f, qmax = 0.f;
+            for (int64_t k = 0; k < n_items; ++k) {
+                const int pos = (int)(k % n_pass);
+                const int64_t tile = blockIdx.x + (k / n_pass) * gridDim.x;
+                const int pass = plist[pos];
+                const int d = (int)(k & 1);
+                const int64_t row = tile * TM + r;
+                const bool live = row < A.n;
+                float raw[4];
+                {
+                    mbar_wait(smem_u32(&S.acc_full[d]), acc_use[d] & 1);
+                    tc_fence_after();
+                    const uint32_t taddr = lane_addr + d * H;
+                    float4 mine;
+                    if (pass == PASS_POL) mine = epilogue_cols<4, 4>(S, PASS_POL, taddr, hq * 128);
+                    else if (pass == PASS_REC) mine = epilogue_cols<2, 4>(S, PASS_REC, taddr, hq * 128);
+                    else mine = epilogue_cols<1, 4>(S, pass, taddr, hq * 128);
+                    tc_fence_before();
+                    mbar_arrive_warp(smem_u32(&S.acc_empty[d]));
+                    ++acc_use[d];
+                    // exchange the two column halves of the row; both threads of the row then hold the full sums
+                    const int pb = n_epi & 1;
+                    ++n_epi;
+                    S.part[pb][hq][r] = mine;
+                    // only the two warps of this TMEM lane quadrant exchange (rows r of quadrant ew & 3)
+                    asm volatile("bar.sync %0, 64;" ::"r"(1 + (ew & 3)) : "memory");
+                    const float4 p0 = S.part[pb][0][r], p1 = S.part[pb][1][r];
+                    raw[0] = (p0.x + p1.x) + S.sm.b3[pass][0];
+                    raw[1] = (p0.y + p1.y) + S.sm.b3[pass][1];
+                    raw[2] = (p0.z + p1.z) + S.sm.b3[pass][2];
+                    raw[3] = (p0.w + p1.w) + S.sm.b3[pass][3];
                 }
-            }
-            if (pass == PASS_POL) {
-                // ---- policy head (model.py:325-338) ----
-                if (!random_phase) {
+                if (pos == 0 && !sP) {   // a later stage: the task action of an earlier launch
+                    at[0] = at[1] = 0.f;
+                    if (live) {
+                        const float2 av = reinterpret_cast<const float2*>(A.action_task)[row];
+                        at[0] = av.x; at[1] = av.y;
+                    }
+                }
+                if (pass == PASS_POL) {
+                    // ---- policy head (model.py:325-338) ----
+                    if (!random_phase) {
+                        float e[2], mean_a[2], lp;
+                        if (A.eps_task) {
+                            const float2 ev = live ? reinterpret_cast<const float2*>(A.eps_task)[row] : make_float2(0.f, 0.f);
+                            e[0] = ev.x; e[1] = ev.y;
+                        } else {
+                            philox_eps(A.seed, A.stream_id, (uint64_t)row, vstep, RRL_DRAW_ACT_TASK, e);
+                        }
+                        gauss_sample(raw, e, A.sp, at, &lp, mean_a);
+                        if (A.eval) { at[0] = mean_a[0]; at[1] = mean_a[1]; }
+                    } else {  // env.action_space.sample() (experiment.py:559-560)
+                        float u[2] = {0.f, 0.f};
+                        if (A.rand_u) {
+                            if (live) {
+                                const float2 uv = reinterpret_cast<const float2*>(A.rand_u)[row];
+                                u[0] = uv.x; u[1] = uv.y;
+                            }
+                        } else {
+                            const Philox4 p = rrl_philox(A.seed, A.stream_id, (uint64_t)row, vstep, RRL_DRAW_ACT_RAND);
+                            u[0] = rrl_u24(p.x); u[1] = rrl_u24(p.y);
+                        }
+                        at[0] = fmaf(2.0f * u[0] - 1.0f, A.sp.scale[0], A.sp.bias[0]);
+                        at[1] = fmaf(2.0f * u[1] - 1.0f, A.sp.scale[1], A.sp.bias[1]);
+                    }
+                    if (live && hq == 0) reinterpret_cast<float2*>(A.action_task)[row] = make_float2(at[0], at[1]);
+                    if (sQ) {   // -> the producer warps (first Q_risk chunk of this tile).  S.act is rewritten by the NEXT tile's
+                                // policy head, which needs that tile's policy MMAs, i.e. the producers past their read of this one
+                        if (hq == 0) S.act[r] = make_float2(at[0], at[1]);
+                        asm volatile("bar.sync 5, %0;" ::"n"(kProd) : "memory");
+                    }
+                } else if (pass == PASS_REC) {
+                    // ---- recovery policy head (model.py:512-525) ----
                     float e[2], mean_a[2], lp;
-                    if (A.eps_task) {
-                        const float2 ev = live ? reinterpret_cast<const float2*>(A.eps_task)[row] : make_float2(0.f, 0.f);
+                    if (A.eps_rec) {
+                        const float2 ev = live ? reinterpret_cast<const float2*>(A.eps_rec)[row] : make_float2(0.f, 0.f);
                         e[0] = ev.x; e[1] = ev.y;
                     } else {
-                        philox_eps(A.seed, A.stream_id, (uint64_t)row, vstep, RRL_DRAW_ACT_TASK, e);
+                        philox_eps(A.seed, A.stream_id, (uint64_t)row, vstep, RRL_DRAW_ACT_REC, e);
                     }
-                    gauss_sample(raw, e, A.sp, at, &lp, mean_a);
-                    if (A.eval) { at[0] = mean_a[0]; at[1] = mean_a[1]; }
-                } else {  // env.action_space.sample() (experiment.py:559-560)
-                    float u[2] = {0.f, 0.f};
-                    if (A.rand_u) {
-                        if (live) {
-                            const float2 uv = reinterpret_cast<const float2*>(A.rand_u)[row];
-                            u[0] = uv.x; u[1] = uv.y;
-                        }
-                    } else {
-                        const Philox4 p = rrl_philox(A.seed, A.stream_id, (uint64_t)row, vstep, RRL_DRAW_ACT_RAND);
-                        u[0] = rrl_u24(p.x); u[1] = rrl_u24(p.y);
-                    }
-                    at[0] = fmaf(2.0f * u[0] - 1.0f, A.sp.scale[0], A.sp.bias[0]);
-                    at[1] = fmaf(2.0f * u[1] - 1.0f, A.sp.scale[1], A.sp.bias[1]);
-                }
-                if (sQ && q == 0) S.act[r] = make_float2(at[0], at[1]);   // -> the producer role (produce_item, PASS_QR1)
-                if (live && q == 0) reinterpret_cast<float2*>(A.action_task)[row] = make_float2(at[0], at[1]);
-            } else if (pass == PASS_REC) {
-                // ---- recovery policy head (model.py:512-525) ----
-                float e[2], mean_a[2], lp;
-                if (A.eps_rec) {
-                    const float2 ev = live ? reinterpret_cast<const float2*>(A.eps_rec)[row] : make_float2(0.f, 0.f);
-                    e[0] = ev.x; e[1] = ev.y;
+                    stoch_sample(raw, S.sm.log_std, e, A.sp, arec, mean_a, &lp);
+                } else if (pass == PASS_QR1) {
+                    q1 = sigmoidf_(raw[0]);
                 } else {
-                    philox_eps(A.seed, A.stream_id, (uint64_t)row, vstep, RRL_DRAW_ACT_REC, e);
+                    qmax = fmaxf(q1, sigmoidf_(raw[0]));   // qrisk.py:196
                 }
-                stoch_sample(raw, S.sm.log_std, e, A.sp, arec, mean_a, &lp);
-            } else if (pass == PASS_QR1) {
-                q1 = sigmoidf_(raw[0]);
-            } else {
-                qmax = fmaxf(q1, sigmoidf_(raw[0]));   // qrisk.py:196
-            }
-            if (pos == n_pass - 1 && live && q == 0) {   // last pass of the tile: decide and write
-                bool rec = false;
-                if (sQ) {
-                    rec = qmax > A.eps_safe;               // experiment.py:555
-                    if (A.recovery) A.recovery[row] = rec ? 1 : 0;
-                    if (A.qrisk_out) A.qrisk_out[row] = qmax;
-                } else if (sR) {
-                    rec = A.recovery[row] != 0;            // decided by the Q_risk stage of an earlier launch
+                if (pos == n_pass - 1 && live && hq == 0) {   // last pass of the tile: decide and write
+                    bool rec = false;
+                    if (sQ) {
+                        rec = qmax > A.eps_safe;               // experiment.py:555
+                        if (A.recovery) A.recovery[row] = rec ? 1 : 0;
+                        if (A.qrisk_out) A.qrisk_out[row] = qmax;
+                    } else if (sR) {
+                        rec = A.recovery[row] != 0;            // decided by the Q_risk stage of an earlier launch
+                    }
+                    // the executed action: decided once the recovery stage has run (or at once without a recovery policy)
+                    if (sR || !A.use_recovery)
+                        reinterpret_cast<float2*>(A.action_real)[row] = rec ? make_float2(arec[0], arec[1]) : make_float2(at[0], at[1]);
                 }
-                // the executed action: decided once the recovery stage has run (or at once without a recovery policy)
-                if (sR || !A.use_recovery)
-                    reinterpret_cast<float2*>(A.action_real)[row] = rec ? make_float2(arec[0], arec[1]) : make_float2(at[0], at[1]);
             }
-        };
-
-        for (int64_t k = 0; k < n_items + 2; ++k) {
-            if (k >= 2) epilogue_item(k - 2);
-            if (k < n_items) produce_item(k);
         }
     } else if (warp == kProd / 32) {
         // ================= MMA issuer (one thread) =================
