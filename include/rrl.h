@@ -282,6 +282,13 @@ int rrl_recovery_backward(const rrl_agent_config_t* cfg, float* arena, const flo
                           uint64_t seed, int32_t stream_id, int64_t* counters, float* losses,
                           void* stream);
 int rrl_recovery_apply(const rrl_agent_config_t* cfg, float* arena, int64_t* counters, void* stream);
+/* rrl_recovery_backward in two calls, for callers that overlap: the recovery policy's own forward pass (qrisk.py:150-151
+ * `self.policy.sample(state_batch)`) needs only the sampled batch and the recovery policy, so it can be enqueued on another
+ * stream next to the SAC / safety-critic updates; rrl_recovery_backward_rest is everything that needs the POST-step safety
+ * critic (qrisk.py:152-158).  rrl_recovery_forward + rrl_recovery_backward_rest == rrl_recovery_backward. */
+int rrl_recovery_forward(const rrl_agent_config_t* cfg, float* arena, const float* eps_rec, uint64_t seed, int32_t stream_id,
+                         int64_t* counters, void* stream);
+int rrl_recovery_backward_rest(const rrl_agent_config_t* cfg, float* arena, int64_t* counters, float* losses, void* stream);
 
 /* ---- multi-GPU: gradient sum fused into the optimizer step over NVLink peer memory --------------------------------
  * With the agent arena of every rank allocated in symmetric (peer-mapped) memory, the NCCL all-reduce between

@@ -1683,8 +1683,10 @@ static int qrisk_apply_impl(const rrl_agent_config_t* cfg, float* arena, int64_t
 }
 
 // recovery policy on the POST-step safety critic (qrisk.py:150-158), then Polyak (qrisk.py:160-163)
-extern "C" int rrl_recovery_backward(const rrl_agent_config_t* cfg, float* arena, const float* eps_rec, uint64_t seed,
-                                     int32_t stream_id, int64_t* counters, float* losses, void* stream) {
+// do_forward: the recovery policy's own forward pass (needs only the sampled batch and the recovery policy: the vector
+// engine enqueues it next to the SAC update);  do_rest: everything that needs the POST-step safety critic
+static int recovery_backward_impl(const rrl_agent_config_t* cfg, float* arena, const float* eps_rec, uint64_t seed,
+                                  int32_t stream_id, int64_t* counters, float* losses, void* stream, bool do_forward, bool do_rest) {
     CHECK_CFG(cfg);
     RRL_CHECK_ARG(arena && counters, "null argument");
     const Layout L = make_layout(cfg);
@@ -1699,7 +1701,7 @@ extern "C" int rrl_recovery_backward(const rrl_agent_config_t* cfg, float* arena
     const ActionSpace sp = action_space(cfg);
     const bool fuse = cfg->use_tensor_cores >= 2;
     if (!cfg->mf_recovery) return 0;
-    {
+    if (do_forward) {
         FwdArgs A;
         memset(&A, 0, sizeof(A));
         A.n_pass = 1; A.rows_ptr = rows_ptr; A.sp = sp; A.use_tc = cfg->use_tensor_cores; A.seed = seed; A.stream_id = (uint32_t)stream_id;
@@ -1707,12 +1709,13 @@ extern "C" int rrl_recovery_backward(const rrl_agent_config_t* cfg, float* arena
         FwdPass& p0 = A.p[0];
         p0.w = head_w(L, arena, RRL_NET_RECOVERY, 0); p0.head = HEAD_STOCH; p0.xs = s; p0.eps = eps_rec;
         p0.tc_img = tc_img_of(L, arena, RRL_NET_RECOVERY, 0);
-        p0.draw_id = RRL_DRAW_QR_REC; p0.h1 = arena + L.h1[4]; p0.h2 = arena + L.h2[4]; p0.h2bits = slot_bits(L, arena, 4);
-        p0.h1bits = slot_bits1(L, arena, 4); p0.keep_h2 = 1;
+        p0.draw_id = RRL_DRAW_QR_REC; p0.h1 = arena + L.h1[kRecSlot]; p0.h2 = arena + L.h2[kRecSlot];
+        p0.h2bits = slot_bits(L, arena, kRecSlot); p0.h1bits = slot_bits1(L, arena, kRecSlot); p0.keep_h2 = 1;
         p0.out_a = R2(R2_REC_PI); p0.out_logp = RA(RA_REC_LOGP); p0.out_raw = R4(R4_RAW_REC); p0.out_eps = R2(R2_REC_EPS);
         int rc = launch_forward<32>(A, R, st);
         if (rc) return rc;
     }
+    if (!do_rest) return 0;
     {
         FwdArgs A;
         memset(&A, 0, sizeof(A));
@@ -1774,13 +1777,13 @@ extern "C" int rrl_recovery_backward(const rrl_agent_config_t* cfg, float* arena
         G.rows_ptr = rows_ptr;
         for (int q = 0; q < 2; ++q) {
             GemmPass& p = G.p[q];
-            p.dout = R4(R4_DRAW_REC); p.stride = 4; p.n_out = 2; p.na = 2; p.W3a = pw.W3a; p.h2 = arena + L.h2[4];
-            bwd_inputs(p, pw, s, nullptr, L, arena, 4);
+            p.dout = R4(R4_DRAW_REC); p.stride = 4; p.n_out = 2; p.na = 2; p.W3a = pw.W3a; p.h2 = arena + L.h2[kRecSlot];
+            bwd_inputs(p, pw, s, nullptr, L, arena, kRecSlot);
         }
-        G.p[0].B = pw.W2; G.p[0].tc_imgT = pw.tc_imgT; G.p[0].mask = arena + L.h1[4]; G.p[0].C = arena + L.dh1[4];
-        G.p[1].B = arena + L.h1[4]; G.p[1].k_is_rows = 1; G.p[1].C = pg.W2;
+        G.p[0].B = pw.W2; G.p[0].tc_imgT = pw.tc_imgT; G.p[0].mask = arena + L.h1[kRecSlot]; G.p[0].C = arena + L.dh1[kRecSlot];
+        G.p[1].B = arena + L.h1[kRecSlot]; G.p[1].k_is_rows = 1; G.p[1].C = pg.W2;
         G.p[1].gW3a = pg.W3a; G.p[1].gb3a = pg.b3a; G.p[1].gb2 = pg.b2;
-        if (fuse) fuse_l1(G.p[0], pg.W1, pg.b1, nullptr, L, arena, 4);
+        if (fuse) fuse_l1(G.p[0], pg.W1, pg.b1, nullptr, L, arena, kRecSlot);
         const int mt = (int)((R > H ? R : H) / 32);
         { int rc = launch_gemm(G, 2, mt, R, cfg->use_tensor_cores, st); if (rc) return rc; }
     }
@@ -1789,11 +1792,22 @@ extern "C" int rrl_recovery_backward(const rrl_agent_config_t* cfg, float* arena
         memset(&A, 0, sizeof(A));
         A.rows_ptr = rows_ptr;
         L1BwdPass& p = A.p[0];
-        p.dh1 = arena + L.dh1[4]; p.xs = s; p.W1 = pw.W1; p.n_in = 2; p.gW1 = pg.W1; p.gb1 = pg.b1;
+        p.dh1 = arena + L.dh1[kRecSlot]; p.xs = s; p.W1 = pw.W1; p.n_in = 2; p.gW1 = pg.W1; p.gb1 = pg.b1;
         layer1_backward_kernel<<<dim3(kL1ColBlocks, 1), kThreads, 0, st>>>(A);
         RRL_CHECK_LAUNCH();
     }
     return 0;
+}
+extern "C" int rrl_recovery_backward(const rrl_agent_config_t* cfg, float* arena, const float* eps_rec, uint64_t seed,
+                                     int32_t stream_id, int64_t* counters, float* losses, void* stream) {
+    return recovery_backward_impl(cfg, arena, eps_rec, seed, stream_id, counters, losses, stream, true, true);
+}
+extern "C" int rrl_recovery_forward(const rrl_agent_config_t* cfg, float* arena, const float* eps_rec, uint64_t seed,
+                                    int32_t stream_id, int64_t* counters, void* stream) {
+    return recovery_backward_impl(cfg, arena, eps_rec, seed, stream_id, counters, nullptr, stream, true, false);
+}
+extern "C" int rrl_recovery_backward_rest(const rrl_agent_config_t* cfg, float* arena, int64_t* counters, float* losses, void* stream) {
+    return recovery_backward_impl(cfg, arena, nullptr, 0, 0, counters, losses, stream, false, true);
 }
 
 static int recovery_apply_impl(const rrl_agent_config_t* cfg, float* arena, int64_t* counters, const rrl_peers_t* peers, void* stream);

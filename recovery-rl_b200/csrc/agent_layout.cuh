@@ -19,7 +19,9 @@ constexpr int H = 256;  // hidden width (arg_utils.py:89-92); all kernels are sp
 constexpr int kMaxTensors = 14;
 constexpr int kNumImages = 10;
 constexpr int kTcHeads = kNumImages;  // one fp16 hi/lo tcgen05 operand image per 256x256 hidden matrix (index = image_index)
-constexpr int kPassSlots = 7;  // activation slots shared by the SAC and Q_risk updates (5, 6: Q_risk(s, pi) of the DGD branch)
+constexpr int kPassSlots = 8;  // activation slots shared by the SAC and Q_risk updates (5, 6: Q_risk(s, pi) of the DGD branch;
+                               // 7: the recovery policy, whose forward pass may run next to the SAC update)
+constexpr int kRecSlot = 7;
 
 struct TDesc {
     int rows, cols;  // cols == 0: 1-D tensor of `rows` elements

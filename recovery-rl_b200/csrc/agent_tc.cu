@@ -266,15 +266,25 @@ __global__ void __launch_bounds__(kTcThreads, 1) act_tc_kernel(const __grid_cons
         if (warp < kActProdWarps) {
             const int pq = t >> 6, pa = t & 63, pb2 = pa + 64;
             float xa[4] = {0.f, 0.f, 0.f, 0.f}, xb[4] = {0.f, 0.f, 0.f, 0.f};   // (s, a) of the thread's two rows, current tile
+            // the states of a tile are fetched one tile ahead (fp64 loads from HBM / L2: ~1 us if waited for at the tile's start)
+            double nsa0 = 0.0, nsa1 = 0.0, nsb0 = 0.0, nsb1 = 0.0;
+            auto fetch_state = [&](int64_t tile) {
+                const int64_t ra = tile * TM + pa, rb = tile * TM + pb2;
+                nsa0 = nsa1 = nsb0 = nsb1 = 0.0;
+                if (tile < n_tiles) {
+                    if (ra < A.n) { nsa0 = A.state[ra]; nsa1 = A.state[A.n + ra]; }
+                    if (rb < A.n) { nsb0 = A.state[rb]; nsb1 = A.state[A.n + rb]; }
+                }
+            };
+            fetch_state(blockIdx.x);
             for (int64_t k = 0; k < n_items; ++k) {
                 const int pos = (int)(k % n_pass);
                 const int64_t tile = blockIdx.x + (k / n_pass) * gridDim.x;
                 const int pass = plist[pos];
                 const int64_t ra = tile * TM + pa, rb = tile * TM + pb2;
                 if (pos == 0) {   // torch.FloatTensor(state): fp64 -> fp32 (sac.py:137)
-                    xa[0] = xa[1] = xb[0] = xb[1] = 0.f;
-                    if (ra < A.n) { xa[0] = (float)A.state[ra]; xa[1] = (float)A.state[A.n + ra]; }
-                    if (rb < A.n) { xb[0] = (float)A.state[rb]; xb[1] = (float)A.state[A.n + rb]; }
+                    xa[0] = (float)nsa0; xa[1] = (float)nsa1; xb[0] = (float)nsb0; xb[1] = (float)nsb1;
+                    fetch_state(tile + gridDim.x);
                 }
                 if (pass == PASS_QR1) {   // the task actions of the tile
                     xa[2] = xa[3] = xb[2] = xb[3] = 0.f;

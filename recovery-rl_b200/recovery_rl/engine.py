@@ -269,6 +269,11 @@ class VecEngine(object):
                 and self.mpc is None and self.act_staging)
 
     @property
+    def early_rec_forward(self):
+        """the recovery policy's forward pass of the recovery update runs on the sampling side stream (tcgen05 path)"""
+        return int(self.cfg.use_tensor_cores) >= 1 and self.mf_recovery and self.online_qrisk and self.act_staging
+
+    @property
     def fused_barrier(self):
         """peer mode on the tcgen05 path: the tiled optimizer-step kernel publishes / waits for the gradient flags itself"""
         return self.peer_arena is not None and int(self.cfg.use_tensor_cores) >= 1
@@ -291,16 +296,20 @@ class VecEngine(object):
                              cons_flags=self.cons_flags, chunk_counts=self.chunk_counts)
         return k + 1
 
-    def _qr_compute(self, between=None):
+    def _qr_compute(self, between=None, rec_forward_done=False):
         """safety-critic step, then (MF recovery) the recovery-policy step on the post-step critic.  `between`: called
-        after the safety-critic optimizer step has been enqueued (staged acting forks its Q_risk stage there)."""
+        after the safety-critic optimizer step has been enqueued (staged acting forks its Q_risk stage there).
+        rec_forward_done: the recovery policy's forward pass was already enqueued (side stream, next to the SAC update)."""
         cfg, ar, cn = self.cfg, self.arena, self.counters
         native.qrisk_backward(cfg, ar, cn, self.losses[8:], self._in("qr_eps_next"), seed=self.seed, stream_id=self.rank)
         self._all_reduce(["qrisk"])
         native.qrisk_apply(cfg, ar, cn, peers=self._peers)
         if between is not None:
             between()
-        native.recovery_backward(cfg, ar, cn, self.losses[8:], self._in("qr_eps_rec"), seed=self.seed, stream_id=self.rank)
+        if rec_forward_done:
+            native.recovery_backward_rest(cfg, ar, cn, self.losses[8:])
+        else:
+            native.recovery_backward(cfg, ar, cn, self.losses[8:], self._in("qr_eps_rec"), seed=self.seed, stream_id=self.rank)
         self._all_reduce(["recovery"])
         native.recovery_apply(cfg, ar, cn, peers=self._peers)
         nb = 1 if (self.peer_arena is not None and not self.fused_barrier) else 0           # peer barrier kernels
@@ -362,6 +371,10 @@ class VecEngine(object):
             self._side.wait_event(self._ev_fork)
             with torch.cuda.stream(self._side):
                 k += self._qr_sample()
+                if self.early_rec_forward:
+                    # the recovery policy's forward pass on the Q_risk batch needs neither the SAC nor the safety-critic step
+                    native.recovery_forward(self.cfg, self.arena, self.counters, self._in("qr_eps_rec"), seed=self.seed,
+                                            stream_id=self.rank)
                 self._ev_join.record(self._side)
         k += self._sac_compute()                                                   # experiment.py:397-406
         # Staged acting (tcgen05 path, MF recovery, online safety-critic updates): each stage of the composite action only
@@ -392,7 +405,8 @@ class VecEngine(object):
             k += 1
         if self.online_qrisk:
             main.wait_event(self._ev_join)
-            k += self._qr_compute(between=(lambda: fork_stage(native.ACT_STAGE_QRISK, 1)) if staged else None)   # experiment.py:407-415
+            k += self._qr_compute(between=(lambda: fork_stage(native.ACT_STAGE_QRISK, 1)) if staged else None,
+                                  rec_forward_done=self.early_rec_forward)   # experiment.py:407-415
             if staged:
                 k += 1
         # (the fp16 hi/lo tcgen05 operand images are refreshed by the optimizer-step kernels themselves)

@@ -285,6 +285,17 @@ qrisk_backward = _upd(None, "rrl_qrisk_backward")
 recovery_backward = _upd(None, "rrl_recovery_backward")
 
 
+def recovery_forward(cfg, arena, counters, eps_rec=None, seed=0, stream_id=0, stream=None):
+    """the recovery policy's own forward pass of rrl_recovery_backward (may run next to the other updates)"""
+    _check(lib().rrl_recovery_forward(C.byref(cfg), p(arena, "f32"), p(eps_rec, "f32"), C.c_uint64(seed & 0xFFFFFFFFFFFFFFFF),
+                                      C.c_int32(stream_id), p(counters, "i64"), _stream(stream)), "rrl_recovery_forward")
+
+
+def recovery_backward_rest(cfg, arena, counters, losses, stream=None):
+    _check(lib().rrl_recovery_backward_rest(C.byref(cfg), p(arena, "f32"), p(counters, "i64"), p(losses, "f32"), _stream(stream)),
+           "rrl_recovery_backward_rest")
+
+
 class Peers(C.Structure):
     """rrl_peers_t: the ranks' arenas and signal pads as mapped in this process (symmetric memory)."""
     _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("arena", C.c_uint64 * 8), ("signal", C.c_uint64 * 8),
