@@ -539,14 +539,17 @@ def run_ours(args, rank, world, local_rank):
         pool = []
         rs = np.random.RandomState(args.seed + 77 + rank)
         n, B = args.envs, args.batch
-        for _ in range(4):
+        for _ in range(4):      # four pre-drawn input sets, each ONE pinned flat buffer (VecEngine.new_host_inputs)
             d = dict(reset_draws=rs.rand(2, n), eps_task=rs.randn(n, 2).astype(np.float32),
                      eps_rec=rs.randn(n, 2).astype(np.float32), rand_u=rs.rand(n, 2).astype(np.float32),
                      sac_eps_next=rs.randn(B, 2).astype(np.float32), sac_eps_cur=rs.randn(B, 2).astype(np.float32),
                      qr_eps_next=rs.randn(B, 2).astype(np.float32), qr_eps_rec=rs.randn(B, 2).astype(np.float32))
             if args.env_name != "maze":
                 d["env_noise"] = rs.randn(2, n)
-            pool.append({k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in d.items()})
+            hs = eh.new_host_inputs()
+            for k, v in d.items():
+                hs[k].copy_(torch.from_numpy(np.ascontiguousarray(v)))
+            pool.append(hs)
         for i in range(3):
             eh.step_host(pool[i % 4])
         eh.capture()
@@ -581,9 +584,9 @@ def run_ours(args, rank, world, local_rank):
         e2e = {"value": world * args.envs * K / e2e_s, "unit": UNIT,
                "h2d_bytes_per_step": eh.h2d_bytes_per_step(), "d2h_bytes_per_step": eh.d2h_bytes_per_step(),
                "ms_per_step": 1e3 * e2e_s / K,
-               "api": ("VecEngine.submit/collect: pinned H2D of the step's random draws and D2H of per-env next_state/reward/"
-                       "flags/action + losses + counters on copy streams, two staging slots, results collected one step "
-                       "later (host sync every step)") if args.e2e_pipeline else
+               "api": ("VecEngine.submit/collect: pinned H2D of the step's random draws (one flat buffer) and D2H of per-env "
+                       "next_state/reward/flags/action (one flat buffer) + losses + counters on copy streams, two staging "
+                       "slots, results collected one step later (host sync every step)") if args.e2e_pipeline else
                       ("VecEngine.step_host: pinned H2D of the step's random draws, graph replay, D2H of per-env "
                        "next_state/reward/flags/action + losses + counters, host sync every step")}
         assert eh.read_counters()["error"] == 0

@@ -25,6 +25,36 @@ ACTION_SCALE = {"navigation1": 1.0, "navigation2": 1.0, "maze": float(np.float32
 FLAG_CHUNK = 512
 
 
+def _carve(specs, device=None, pinned=False):
+    """specs: [(name, shape, dtype)] -> (flat uint8 buffer, {name: typed view}); every view starts on a 256-byte boundary.
+    One flat buffer = ONE copy per direction for the whole set (the host face moves ~10 arrays per step)."""
+    offs, total = [], 0
+    for _, shape, dtype in specs:
+        nbytes = int(np.prod(shape)) * torch.empty((), dtype=dtype).element_size()
+        offs.append((total, nbytes))
+        total += (nbytes + 255) // 256 * 256
+    flat = torch.zeros(total, dtype=torch.uint8).pin_memory() if pinned else torch.zeros(total, dtype=torch.uint8, device=device)
+    views = {name: flat[o:o + nb].view(dtype).view(*shape) for (name, shape, dtype), (o, nb) in zip(specs, offs)}
+    return flat, views
+
+
+class HostInputs(object):
+    """One step's random draws in ONE pinned host buffer laid out like the engine's device staging (VecEngine.new_host_inputs):
+    fill the typed views in `.views` in place; submit() / step_host() then upload the whole set with a single copy."""
+
+    def __init__(self, specs):
+        self.flat, self.views = _carve(specs, pinned=True)
+
+    def __getitem__(self, k):
+        return self.views[k]
+
+    def __contains__(self, k):
+        return k in self.views
+
+    def keys(self):
+        return self.views.keys()
+
+
 class VecEngine(object):
     def __init__(self, env_name, num_envs, batch_size=256, replay_size=1000000, safe_replay_size=1000000,
                  gamma=0.99, alpha=0.2, tau=0.005, lr=3e-4, gamma_safe=0.5, tau_safe=0.0002, eps_safe=0.1,
@@ -86,9 +116,15 @@ class VecEngine(object):
         self.ep_steps = torch.zeros(n, dtype=torch.int32, device=dev)
         self.ep_return = torch.zeros(n, dtype=torch.float64, device=dev)
         self.action_task = torch.zeros(n, 2, device=dev)
-        self.action_real = torch.zeros(n, 2, device=dev)
-        self.recovery = torch.zeros(n, dtype=torch.uint8, device=dev)
         self.qrisk = torch.zeros(n, device=dev)
+        # what the host face downloads every step lives in ONE flat device buffer (one D2H copy): per-env next_state / reward /
+        # flags / executed action
+        self._out_specs = [("next_state", (2, n), torch.float64), ("reward", (n,), torch.float64), ("done", (n,), torch.uint8),
+                           ("constraint", (n,), torch.uint8), ("success", (n,), torch.uint8), ("recovery", (n,), torch.uint8),
+                           ("action", (n, 2), torch.float32)]
+        self._out_flat, ov = _carve(self._out_specs, device=dev)
+        self.action_real = ov["action"]
+        self.recovery = ov["recovery"]
         self.task_ring = torch.zeros(self.task_cap, 8, device=dev)
         self.cons_ring = torch.zeros(self.cons_cap, 8, device=dev)
         self.cons_flags = torch.zeros(self.cons_cap, dtype=torch.uint8, device=dev)
@@ -105,31 +141,26 @@ class VecEngine(object):
                                                   chunk=self.flag_chunk, gate_pos_fraction=self.gate_pos_fraction)
         # per-step outputs (logging schema of experiment.py:421 / run_stats.pkl), only when asked for
         if self.log_outputs:
-            self.out_next = torch.zeros(2, n, dtype=torch.float64, device=dev)
-            self.out_reward = torch.zeros(n, dtype=torch.float64, device=dev)
-            self.out_done = torch.zeros(n, dtype=torch.uint8, device=dev)
-            self.out_cons = torch.zeros(n, dtype=torch.uint8, device=dev)
-            self.out_succ = torch.zeros(n, dtype=torch.uint8, device=dev)
+            self.out_next, self.out_reward, self.out_done = ov["next_state"], ov["reward"], ov["done"]
+            self.out_cons, self.out_succ = ov["constraint"], ov["success"]
         else:
             self.out_next = self.out_reward = self.out_done = self.out_cons = self.out_succ = None
         # host-supplied randomness (parity / end-to-end mode): device staging + pinned host buffers
         if self.host_inputs:
             B = self.B
-            self.in_dev = dict(
-                reset_draws=torch.zeros(2, n, dtype=torch.float64, device=dev),
-                env_noise=torch.zeros(2, n, dtype=torch.float64, device=dev) if self.kind != native.ENV_MAZE else None,
-                eps_task=torch.zeros(n, 2, device=dev), eps_rec=torch.zeros(n, 2, device=dev),
-                rand_u=torch.zeros(n, 2, device=dev),
-                sac_eps_next=torch.zeros(B, 2, device=dev), sac_eps_cur=torch.zeros(B, 2, device=dev),
-                qr_eps_next=torch.zeros(B, 2, device=dev), qr_eps_rec=torch.zeros(B, 2, device=dev))
-            self.in_host = {k: torch.zeros(v.shape, dtype=v.dtype).pin_memory() for k, v in self.in_dev.items()
-                            if v is not None}
-            self.out_host = dict(
-                losses=torch.zeros(16).pin_memory(), counters=torch.zeros(native.NUM_COUNTERS, dtype=torch.int64).pin_memory(),
-                next_state=torch.zeros(2, n, dtype=torch.float64).pin_memory(), reward=torch.zeros(n, dtype=torch.float64).pin_memory(),
-                done=torch.zeros(n, dtype=torch.uint8).pin_memory(), constraint=torch.zeros(n, dtype=torch.uint8).pin_memory(),
-                success=torch.zeros(n, dtype=torch.uint8).pin_memory(), recovery=torch.zeros(n, dtype=torch.uint8).pin_memory(),
-                action=torch.zeros(n, 2).pin_memory())
+            self._in_specs = [("reset_draws", (2, n), torch.float64)] + \
+                ([("env_noise", (2, n), torch.float64)] if self.kind != native.ENV_MAZE else []) + \
+                [("eps_task", (n, 2), torch.float32), ("eps_rec", (n, 2), torch.float32), ("rand_u", (n, 2), torch.float32),
+                 ("sac_eps_next", (B, 2), torch.float32), ("sac_eps_cur", (B, 2), torch.float32),
+                 ("qr_eps_next", (B, 2), torch.float32), ("qr_eps_rec", (B, 2), torch.float32)]
+            self._in_flat, self.in_dev = _carve(self._in_specs, device=dev)         # the step's kernels read these views
+            if self.kind == native.ENV_MAZE:
+                self.in_dev["env_noise"] = None
+            self._in_host_set = HostInputs(self._in_specs)
+            self.in_host = self._in_host_set.views
+            self._out_host_flat, oh = _carve(self._out_specs, pinned=True)
+            self.out_host = dict(losses=torch.zeros(16).pin_memory(),
+                                 counters=torch.zeros(native.NUM_COUNTERS, dtype=torch.int64).pin_memory(), **oh)
         else:
             self.in_dev = {}
         # model-based recovery (BASELINE config 5): the PETS / CEM planner proposes the recovery action for every env
@@ -469,54 +500,55 @@ class VecEngine(object):
         """inputs: dict of host arrays for this step's random draws (see self.in_host).  Uploads them from
         pinned memory, runs the step, downloads losses / counters / per-env outputs into pinned buffers."""
         assert self.host_inputs
-        for k, h in self.in_host.items():
-            src = h
-            if inputs is not None and k in inputs:
-                x = inputs[k]
-                if torch.is_tensor(x) and x.is_pinned() and x.shape == h.shape and x.dtype == h.dtype:
-                    src = x                                   # caller's own pinned buffer: no staging copy
-                else:
-                    h.copy_(torch.as_tensor(x).reshape(h.shape))
-            self.in_dev[k].copy_(src, non_blocking=True)
+        src = self._stage_host(inputs, self._in_host_set)
+        self._in_flat.copy_(src.flat, non_blocking=True)                 # ONE H2D copy for all of the step's inputs
         if self.graph is not None:
             self.graph.replay()
         else:
             self._enqueue_step()
         o = self.out_host
+        self._out_host_flat.copy_(self._out_flat, non_blocking=True)     # ONE D2H copy for the per-env results
         o["losses"].copy_(self.losses, non_blocking=True)
         o["counters"].copy_(self.counters, non_blocking=True)
-        o["next_state"].copy_(self.out_next, non_blocking=True)
-        o["reward"].copy_(self.out_reward, non_blocking=True)
-        o["done"].copy_(self.out_done, non_blocking=True)
-        o["constraint"].copy_(self.out_cons, non_blocking=True)
-        o["success"].copy_(self.out_succ, non_blocking=True)
-        o["recovery"].copy_(self.recovery, non_blocking=True)
-        o["action"].copy_(self.action_real, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return o
 
-    # ---- pipelined host-buffer steps: copies of step k overlap the compute of its neighbours -----------------
-    def _host_outputs(self):
-        return dict(losses=self.losses, counters=self.counters, next_state=self.out_next, reward=self.out_reward,
-                    done=self.out_done, constraint=self.out_cons, success=self.out_succ, recovery=self.recovery,
-                    action=self.action_real)
+    def new_host_inputs(self):
+        """a pinned, flat input set for this engine (HostInputs): fill `.views[name]` in place, hand it to step_host / submit."""
+        assert self.host_inputs
+        return HostInputs(self._in_specs)
 
+    def _stage_host(self, inputs, slot):
+        """inputs -> a HostInputs set ready for one flat upload: a HostInputs of this engine is used as is (zero-copy);
+        a dict of arrays / tensors is packed into the pinned set `slot` (missing keys keep the slot's previous contents)."""
+        if isinstance(inputs, HostInputs):
+            assert inputs.flat.numel() == slot.flat.numel(), "HostInputs of another engine"
+            return inputs
+        if inputs is not None:
+            for k, h in slot.views.items():
+                if k in inputs:
+                    x = inputs[k]
+                    h.copy_(x if torch.is_tensor(x) else torch.as_tensor(x).reshape(h.shape))
+        return slot
+
+    # ---- pipelined host-buffer steps: copies of step k overlap the compute of its neighbours -----------------
     def enable_pipeline(self):
         """Two-slot staging on both sides of the step so that the H2D copy of step k+1 and the D2H copy of step k-1 run
         on their own streams (copy engines) while step k computes.  submit(inputs) -> ticket; collect(ticket) -> the
-        pinned outputs of that step.  A ticket must be collected before the second-next submit (slot reuse)."""
+        pinned outputs of that step.  A ticket must be collected before the second-next submit (slot reuse).  Every set is
+        ONE flat buffer: per step one H2D + one D2D on the way in, one D2D + one D2H (+ losses, counters) on the way out."""
         assert self.host_inputs
         dev = self.device
-        self._pl_keys = list(self.in_host)
-        self._pl_in_dst = [self.in_dev[k] for k in self._pl_keys]
-        self._pl_in = [[torch.empty_like(t) for t in self._pl_in_dst] for _ in range(2)]
-        self._pl_in_host = [[torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in self._pl_in_dst] for _ in range(2)]
-        outs = self._host_outputs()
-        self._pl_out_keys = list(outs)
-        self._pl_out_src = [outs[k] for k in self._pl_out_keys]
-        self._pl_out = [[torch.empty_like(t) for t in self._pl_out_src] for _ in range(2)]
-        self._pl_out_host = [{k: torch.empty(t.shape, dtype=t.dtype).pin_memory()
-                              for k, t in zip(self._pl_out_keys, self._pl_out_src)} for _ in range(2)]
+        self._pl_in_dev = [torch.empty_like(self._in_flat) for _ in range(2)]
+        self._pl_in_host = [HostInputs(self._in_specs) for _ in range(2)]
+        self._pl_out_dev = [torch.empty_like(self._out_flat) for _ in range(2)]
+        self._pl_small_dev = [(torch.empty_like(self.losses), torch.empty_like(self.counters)) for _ in range(2)]
+        self._pl_out_host = []
+        for _ in range(2):
+            flat, views = _carve(self._out_specs, pinned=True)
+            views = dict(views, losses=torch.zeros(16).pin_memory(),
+                         counters=torch.zeros(native.NUM_COUNTERS, dtype=torch.int64).pin_memory())
+            self._pl_out_host.append((flat, views))
         self._s_h2d = torch.cuda.Stream(device=dev)
         self._s_d2h = torch.cuda.Stream(device=dev)
         mk = lambda: [torch.cuda.Event(), torch.cuda.Event()]
@@ -527,26 +559,16 @@ class VecEngine(object):
         k = self._pl_k
         b = k & 1
         main = torch.cuda.current_stream()
-        srcs = []
-        for i, key in enumerate(self._pl_keys):
-            x = inputs[key]
-            d = self._pl_in[b][i]
-            if torch.is_tensor(x) and x.is_pinned() and x.shape == d.shape and x.dtype == d.dtype:
-                srcs.append(x)                               # caller's own pinned buffer: no staging copy
-            else:
-                if k >= 2:
-                    self._ev_in_ready[b].synchronize()       # the H2D that last read this host slot has finished
-                h = self._pl_in_host[b][i]
-                h.copy_(torch.as_tensor(x).reshape(h.shape))
-                srcs.append(h)
+        if not isinstance(inputs, HostInputs) and k >= 2:
+            self._ev_in_ready[b].synchronize()               # the H2D that last read this pinned slot has finished
+        src = self._stage_host(inputs, self._pl_in_host[b])
         with torch.cuda.stream(self._s_h2d):
             if k >= 2:
                 self._s_h2d.wait_event(self._ev_in_free[b])  # step k-2 has consumed this device slot
-            for src, d in zip(srcs, self._pl_in[b]):
-                d.copy_(src, non_blocking=True)
+            self._pl_in_dev[b].copy_(src.flat, non_blocking=True)
             self._ev_in_ready[b].record(self._s_h2d)
         main.wait_event(self._ev_in_ready[b])
-        torch._foreach_copy_(self._pl_in_dst, self._pl_in[b])
+        self._in_flat.copy_(self._pl_in_dev[b], non_blocking=True)
         self._ev_in_free[b].record(main)
         if self.graph is not None:
             self.graph.replay()
@@ -554,12 +576,16 @@ class VecEngine(object):
             self._enqueue_step()
         if k >= 2:
             main.wait_event(self._ev_out_done[b])            # step k-2's D2H has drained this device slot
-        torch._foreach_copy_(self._pl_out[b], self._pl_out_src)
+        self._pl_out_dev[b].copy_(self._out_flat, non_blocking=True)
+        self._pl_small_dev[b][0].copy_(self.losses, non_blocking=True)
+        self._pl_small_dev[b][1].copy_(self.counters, non_blocking=True)
         self._ev_out_ready[b].record(main)
         with torch.cuda.stream(self._s_d2h):
             self._s_d2h.wait_event(self._ev_out_ready[b])
-            for key, d in zip(self._pl_out_keys, self._pl_out[b]):
-                self._pl_out_host[b][key].copy_(d, non_blocking=True)
+            flat, views = self._pl_out_host[b]
+            flat.copy_(self._pl_out_dev[b], non_blocking=True)
+            views["losses"].copy_(self._pl_small_dev[b][0], non_blocking=True)
+            views["counters"].copy_(self._pl_small_dev[b][1], non_blocking=True)
             self._ev_out_done[b].record(self._s_d2h)
         self._pl_k = k + 1
         return k
@@ -567,7 +593,7 @@ class VecEngine(object):
     def collect(self, ticket):
         assert self._pl_k - 2 <= ticket < self._pl_k, "ticket already overwritten or not submitted"
         self._ev_out_done[ticket & 1].synchronize()
-        return self._pl_out_host[ticket & 1]
+        return self._pl_out_host[ticket & 1][1]
 
     # ---- evaluation rollouts (experiment.py:372-374, 493-538) ---------------------------------------------
     def eval_rollout(self, n_eval=1):
