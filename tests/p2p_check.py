@@ -34,6 +34,45 @@ def run(peer, rank, world, dev, tc, steps):
     return params, cn, eng.graph is not None
 
 
+def resume_check(rank, world, dev):
+    """sharded checkpoint: every rank writes / reads its own shard (checkpoint.pt.rank<r>of<w>); a resumed run continues
+    bit-identically on every rank, and a shard of another rank is refused."""
+    import tempfile
+    import bench
+    from recovery_rl import checkpoint
+    args = argparse.Namespace(env_name="navigation1", envs=1024, batch=64, seed=7, tc=2, demos=1000, pretrain=10, peer_grads=1,
+                              replay=1 << 16)
+    box = [tempfile.mkdtemp(prefix="rrl_ck_") if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    path = os.path.join(box[0], "checkpoint.pt")
+    a = bench.build_engine(args, rank, world, dist.group.WORLD, False, dev)
+    for _ in range(4):
+        a.step()
+    torch.cuda.synchronize()
+    saved = a.save(path)
+    assert saved == checkpoint.shard_path(path, rank, world) and os.path.exists(saved), saved
+    for _ in range(3):
+        a.step()
+    torch.cuda.synchronize()
+    b = bench.build_engine(args, rank, world, dist.group.WORLD, False, dev)
+    b.load(path)
+    for _ in range(3):
+        b.step()
+    torch.cuda.synchronize()
+    g = a.agent.grad_off
+    same = torch.equal(a.arena[:g].view(torch.int32), b.arena[:g].view(torch.int32)) and torch.equal(a.state, b.state) and \
+        torch.equal(a.mt_state, b.mt_state) and a.read_counters()["total_numsteps"] == b.read_counters()["total_numsteps"]
+    refused = False
+    try:
+        st = torch.load(checkpoint.shard_path(path, (rank + 1) % world, world), map_location="cpu", weights_only=False)
+        checkpoint.load_engine_state(b, st)
+    except ValueError:
+        refused = True
+    if rank == 0:
+        print("sharded resume bit-identical: %s  foreign shard refused: %s" % (same, refused), flush=True)
+    assert same and refused
+
+
 def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     dev = torch.device("cuda", int(os.environ["LOCAL_RANK"]))
@@ -53,6 +92,7 @@ def main():
             print("tc=%d nccl==peer: %s  ranks identical: %s  sac_updates=%d qrisk_updates=%d max|diff|=%.3e" % (
                 tc, same, across, cb["sac_updates"], cb["qrisk_updates"], float((a - b).abs().max())), flush=True)
         assert same and across
+    resume_check(rank, world, dev)
     dist.barrier()
     if rank == 0:
         print("P2P_OK", flush=True)

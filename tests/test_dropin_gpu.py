@@ -243,3 +243,25 @@ def test_experiment_reproduces_reference_comparison_runs(native, cuda, golden_di
         assert ep_len == list(z[P + "ep_len"])
         assert exp.num_viols == int(z[P + "num_viols"]) and exp.total_numsteps == int(z[P + "total_numsteps"])
         assert exp.updates == int(z[P + "updates"])
+
+
+def test_utils_soft_and_hard_update_delegates(native, cuda):
+    """recovery_rl.utils.soft_update / hard_update with the reference's signature (utils.py:46-54) on the device nets."""
+    from recovery_rl import utils
+    from recovery_rl.arena import AgentArena
+    from recovery_rl.model import build_reference_modules
+    from recovery_rl.sac import NetHandle
+    torch.manual_seed(0)
+    ar = AgentArena(cuda, max_batch=64)
+    ar.load_modules(build_reference_modules())
+    src, tgt = NetHandle(ar, "critic"), NetHandle(ar, "critic_target")
+    utils.hard_update(tgt, src)
+    for p, q in zip(src.parameters(), tgt.parameters()):
+        assert torch.equal(p, q)
+    for p in src.parameters():
+        p.add_(0.25)
+    before = [q.clone() for q in tgt.parameters()]
+    utils.soft_update(tgt, src, 0.1)
+    torch.cuda.synchronize()
+    for p, q0, q in zip(src.parameters(), before, tgt.parameters()):
+        assert torch.allclose(q, q0 * (1.0 - 0.1) + p * 0.1, rtol=0, atol=1e-7)
