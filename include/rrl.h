@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define RRL_VERSION 4
+#define RRL_VERSION 5
 
 const char* rrl_last_error(void);
 int rrl_version(void);
@@ -255,6 +255,37 @@ int rrl_agent_act_stage(const rrl_agent_config_t* cfg, float* arena, int64_t n, 
                   const int64_t* counters, float* action_task, float* action_real,
                   uint8_t* recovery, float* qrisk_out, int stages, int max_ctas, void* stream);
 
+/* ---- comparison branches of the acting path, vectorised over env copies (csrc/select.cu) ----
+ * Every env copy evaluates `samples` candidate actions through the batched forward passes above; `workspace` holds the
+ * candidates of one chunk of env copies (rrl_select_workspace_floats(chunk_envs, samples) floats; a workspace smaller than
+ * n env copies makes the call loop over chunks, the draws do not depend on the chunking). */
+int64_t rrl_select_workspace_floats(int64_t chunk_envs, int32_t samples);
+/* SAC.select_action with --use_constraint_sampling (SQRL, sac.py:139-161): per env copy
+ *   pi_j, log_pi_j = GaussianPolicy.sample(state), j < samples (100 in the reference);  q_j = max(Q1,Q2)_risk(state, pi_j)
+ *   F = {j : q_j <= eps_safe};  F empty: a = pi[argmin q];  else r ~ Categorical(exp(log_pi_F)) and a = pi[r] -- r is the index
+ *   INTO F used on the unfiltered list, as sac.py:157-159 is written.
+ * The Categorical draw is an inverse-CDF draw over F in sample order with one uniform per env.  While total_numsteps <
+ * start_steps the action is U(low, high) as in rrl_agent_act (experiment.py:559-560).  Writes action_task = action_real = a,
+ * recovery = 0, qrisk_out = q of the chosen candidate.
+ * eps_cand fp32 [n][samples][2] N(0,1) or NULL (Philox); cat_u fp32 [n] U[0,1) or NULL; rand_u fp32 [n][2] or NULL. */
+int rrl_sqrl_select_action(const rrl_agent_config_t* cfg, float* arena, int64_t n, int32_t samples, const double* state,
+                           const float* eps_cand, const float* cat_u, const float* rand_u, int64_t start_steps,
+                           uint64_t seed, int32_t stream_id, const int64_t* counters, float* workspace,
+                           int64_t workspace_floats, float* action_task, float* action_real, uint8_t* recovery,
+                           float* qrisk_out, void* stream);
+/* QRiskWrapper.select_action with --Q_sampling_recovery (qrisk.py:214-225): for every env copy whose recovery flag is set
+ * (NULL: all), `samples` (1000 in the reference) uniform actions of the Box, a_real = the one with the smallest
+ * max(Q1,Q2)_risk.  cand_u fp32 [n][samples][2] U[0,1) or NULL (Philox). */
+int rrl_qsample_recovery_action(const rrl_agent_config_t* cfg, float* arena, int64_t n, int32_t samples,
+                                const double* state, const float* cand_u, const uint8_t* recovery, uint64_t seed,
+                                int32_t stream_id, const int64_t* counters, float* workspace, int64_t workspace_floats,
+                                float* action_real, void* stream);
+/* --add_both_transitions (experiment.py:446-448): after rrl_env_step + rrl_counters_advance, every env copy whose recovery
+ * policy acted pushes (state, real_action, reward, next_state, mask) into the task ring as well: the rows are appended in
+ * env order after the step's n rows and TASK_POS / TASK_LEN advance by their number.  Needs task_capacity >= 2 n. */
+int rrl_replay_push_both(float* task_ring, int64_t task_capacity, int64_t n, const uint8_t* recovery,
+                         const float* action_real, int64_t* counters, void* stream);
+
 /* SAC.update_parameters (sac.py:170-277, ordering "Variant B" of SURVEY.md §8c) split so that
  * the host can all-reduce the gradient block between the two halves:
  *   rrl_sac_backward : forward passes, losses, grads of critic and policy into the grad block
@@ -265,7 +296,7 @@ int rrl_agent_act_stage(const rrl_agent_config_t* cfg, float* arena, int64_t n, 
  * cfg->algo_flags selects the comparison branches: they read alpha / nu / lambda from the scalar block, add the
  * Q_risk(s,a) (RCPO) and Q_risk(s,pi) (DGD, update_nu) passes, and rrl_sac_apply also steps the scalar Adams.
  * With RRL_ALGO_DETERMINISTIC eps_next / eps_cur hold the (already scaled and clamped) noise vector of
- * DeterministicPolicy.sample repeated on every row, and must not be NULL. */
+ * DeterministicPolicy.sample repeated on every row; NULL draws ONE such vector per pass from Philox. */
 int rrl_sac_backward(const rrl_agent_config_t* cfg, float* arena, const float* eps_next,
                      const float* eps_cur, uint64_t seed, int32_t stream_id, int64_t* counters,
                      float* losses, void* stream);

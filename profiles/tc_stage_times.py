@@ -26,7 +26,7 @@ def build_timing_lib():
     out = os.path.join(out_dir, "librrl_timing.so")
     csrc = os.path.join(PKG, "csrc")
     srcs = [("api.cu", []), ("env.cu", ["-fmad=false"]), ("replay.cu", ["-fmad=false"]), ("agent.cu", []),
-            ("agent_tc.cu", ["-DRRL_TC_TIMING"]), ("mpc.cu", []), ("mpc_tc.cu", [])]
+            ("agent_tc.cu", ["-DRRL_TC_TIMING"]), ("select.cu", []), ("mpc.cu", []), ("mpc_tc.cu", [])]
     objs, procs = [], []
     for src, extra in srcs:
         obj = os.path.join(out_dir, src.replace(".cu", ".o"))

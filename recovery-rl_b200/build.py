@@ -23,6 +23,7 @@ SOURCES = [
     ("replay.cu", ["-fmad=false"]),
     ("agent.cu", []),
     ("agent_tc.cu", []),
+    ("select.cu", []),
     ("mpc.cu", []),
     ("mpc_tc.cu", []),
 ]

@@ -78,8 +78,14 @@ __global__ void __launch_bounds__(kThreads, 2) act_kernel(const __grid_constant_
                     e[0] = ev.x; e[1] = ev.y;
                 } else {
                     philox_eps(A.seed, A.stream_id, (uint64_t)row, vstep, RRL_DRAW_ACT_TASK, e);
+                    if (A.det) det_noise(e);
                 }
-                gauss_sample(raw, e, A.sp, at, &lp, mean_a);
+                if (A.det) {  // DeterministicPolicy.sample (model.py:475-481): every env copy is its own sample() call
+                    const float zero_ls[2] = {0.f, 0.f};
+                    stoch_sample(raw, zero_ls, e, A.sp, at, mean_a, &lp);
+                } else {
+                    gauss_sample(raw, e, A.sp, at, &lp, mean_a);
+                }
                 if (A.eval) { at[0] = mean_a[0]; at[1] = mean_a[1]; }  // sac.py:166-167
             }
         } else if (live) {  // env.action_space.sample(): U(low, high)  (experiment.py:559-560)
@@ -1306,6 +1312,7 @@ extern "C" int rrl_agent_act_stage(const rrl_agent_config_t* cfg, float* arena, 
     A.use_recovery = use_recovery; A.eval = eval; A.start_steps = start_steps;
     A.seed = seed; A.stream_id = (uint32_t)stream_id; A.counters = counters;
     A.eps_safe = cfg->eps_safe;
+    A.det = (cfg->algo_flags & RRL_ALGO_DETERMINISTIC) ? 1 : 0;
     A.sp = action_space(cfg);
     A.action_task = action_task; A.action_real = action_real; A.qrisk_out = qrisk_out; A.recovery = recovery;
     if (cfg->use_tensor_cores) return act_tc_launch(A, arena, L, stages, max_ctas, (cudaStream_t)stream);
@@ -1384,7 +1391,7 @@ extern "C" int rrl_sac_backward(const rrl_agent_config_t* cfg, float* arena, con
     const bool rcpo = (flags & RRL_ALGO_RCPO) != 0;
     const bool dgd = (flags & RRL_ALGO_DGD) != 0;
     const bool sq_pi = dgd || (flags & RRL_ALGO_UPDATE_NU);  // sac.py:221-222 is dead code otherwise
-    RRL_CHECK_ARG(!det || (eps_next && eps_cur), "the Deterministic policy needs its noise as an input");
+    // (Deterministic policy: eps_next / eps_cur are the caller's noise vectors; NULL draws them from Philox, index 0 for every row)
     const bool fuse = cfg->use_tensor_cores >= 2;   // per-row stages run as tails of the producing kernels
     int pol_head = HEAD_GAUSS;
     const HeadW pw = task_policy_w(L, arena, cfg, &pol_head);
@@ -1599,7 +1606,6 @@ extern "C" int rrl_qrisk_backward(const rrl_agent_config_t* cfg, float* arena, c
         FwdPass& p0 = A.p[0];
         p0.w = task_policy_w(L, arena, cfg, &p0.head); p0.xs = s2; p0.eps = eps_next;
         p0.tc_img = tc_img_of(L, arena, RRL_NET_POLICY, 0);
-        RRL_CHECK_ARG(p0.head != HEAD_DET || eps_next, "the Deterministic policy needs its noise as an input");
         p0.draw_id = RRL_DRAW_QR_NEXT; p0.out_a = R2(R2_QR_NEXT_A); p0.out_logp = RA(RA_QR_NEXT_LOGP);
         int rc = launch_forward<32>(A, R, st);
         if (rc) return rc;

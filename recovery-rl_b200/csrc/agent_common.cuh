@@ -117,6 +117,12 @@ static __device__ __forceinline__ void stoch_sample(const float raw[2], const fl
     *logp = lp;
 }
 
+// DeterministicPolicy.sample (model.py:478-479): noise ~ N(0, 0.1) clamped to +-0.25, from a standard normal draw
+static __device__ __forceinline__ void det_noise(float e[2]) {
+    e[0] = fminf(fmaxf(0.1f * e[0], -0.25f), 0.25f);
+    e[1] = fminf(fmaxf(0.1f * e[1], -0.25f), 0.25f);
+}
+
 static __device__ __forceinline__ void philox_eps(uint64_t seed, uint32_t stream_id, uint64_t row, uint64_t step, uint32_t draw,
                                            float e[2]) {
     const Philox4 p = rrl_philox(seed, stream_id, row, step, draw);
@@ -184,7 +190,9 @@ static __device__ __forceinline__ void forward_tail(const FwdPass& P, const FwdA
             const float2 ev = reinterpret_cast<const float2*>(P.eps)[row];
             e[0] = ev.x; e[1] = ev.y;
         } else {
-            philox_eps(A.seed, A.stream_id, (uint64_t)row, (uint64_t)A.counters[A.step_counter], P.draw_id, e);
+            // DeterministicPolicy: ONE noise vector per sample() call, broadcast over the batch (model.py:478-480)
+            philox_eps(A.seed, A.stream_id, P.head == HEAD_DET ? 0 : (uint64_t)row, (uint64_t)A.counters[A.step_counter], P.draw_id, e);
+            if (P.head == HEAD_DET) det_noise(e);
         }
         float a[2], mean_a[2], lp;
         if (P.head == HEAD_GAUSS) gauss_sample(raw, e, A.sp, a, &lp, mean_a);
@@ -203,6 +211,7 @@ struct ActArgs {
     const double* state;  // [2][n]
     const float *eps_task, *eps_rec, *rand_u;
     int use_recovery, eval;
+    int det;  // task policy = DeterministicPolicy (model.py:447-485): a = tanh(mean)*scale + bias + noise, eps_task = the noise
     int64_t start_steps;
     uint64_t seed;
     uint32_t stream_id;

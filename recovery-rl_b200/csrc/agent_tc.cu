@@ -371,8 +371,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) act_tc_kernel(const __grid_cons
                             e[0] = ev.x; e[1] = ev.y;
                         } else {
                             philox_eps(A.seed, A.stream_id, (uint64_t)row, vstep, RRL_DRAW_ACT_TASK, e);
+                            if (A.det) det_noise(e);
                         }
-                        gauss_sample(raw, e, A.sp, at, &lp, mean_a);
+                        if (A.det) {  // DeterministicPolicy.sample (model.py:475-481)
+                            const float zero_ls[2] = {0.f, 0.f};
+                            stoch_sample(raw, zero_ls, e, A.sp, at, mean_a, &lp);
+                        } else {
+                            gauss_sample(raw, e, A.sp, at, &lp, mean_a);
+                        }
                         if (A.eval) { at[0] = mean_a[0]; at[1] = mean_a[1]; }
                     } else {  // env.action_space.sample() (experiment.py:559-560)
                         float u[2] = {0.f, 0.f};

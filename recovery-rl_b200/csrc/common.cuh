@@ -66,7 +66,10 @@ enum {
     RRL_DRAW_QR_REC = 9,
     RRL_DRAW_INIT_RESET = 10,
     RRL_DRAW_MPC_EPS = 11,  // + 16 * CEM iteration
-    RRL_DRAW_MPC_Z = 12     // + 16 * CEM iteration
+    RRL_DRAW_MPC_Z = 12,    // + 16 * CEM iteration
+    RRL_DRAW_SQRL_EPS = 13, // SQRL action filter: the candidates' Gaussian noise (index = env * samples + j)
+    RRL_DRAW_SQRL_CAT = 14, // SQRL action filter: the Categorical draw (index = env)
+    RRL_DRAW_QSAMPLE = 15   // Q-sampling recovery: the uniform candidate actions (index = env * samples + j)
 };
 
 struct Philox4 {

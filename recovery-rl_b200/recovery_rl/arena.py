@@ -112,7 +112,10 @@ class AgentArena(object):
         def getter(net, i):
             if net not in modules:
                 return None
-            return list(modules[net].parameters())[i].detach().cpu().numpy()
+            ps = list(modules[net].parameters())
+            if i >= len(ps):             # DeterministicPolicy: no log_std head (the arena keeps the Gaussian layout, head unused)
+                return None
+            return ps[i].detach().cpu().numpy()
         self.load_params(getter)
 
     def params(self, net):

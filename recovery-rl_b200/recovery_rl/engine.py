@@ -63,7 +63,8 @@ class VecEngine(object):
                  device="cuda:0", rank=0, world_size=1, process_group=None, host_inputs=False, log_outputs=False,
                  use_tensor_cores=0, maze_substeps=500, dgd=False, update_nu=False, rcpo=False, auto_alpha=False,
                  nu=0.01, lambda_rcpo=0.01, disable_action_relabeling=False, mb_recovery=False, mpc_popsize=None,
-                 mpc_num_elites=None, peer_grads=False):
+                 mpc_num_elites=None, peer_grads=False, constraint_sampling=False, q_sampling_recovery=False,
+                 add_both_transitions=False, deterministic=False, safe_samples=100, q_samples=1000):
         native.require_cuda()
         self.device = torch.device(device)
         torch.cuda.set_device(self.device)
@@ -84,6 +85,18 @@ class VecEngine(object):
         self.gate_pos_fraction = float(pos_fraction)                          # experiment.py:410
         self.pos_fraction = pos_fraction if pos_fraction >= 0 else None        # qrisk.py:77
         self.start_steps = int(start_steps)
+        # comparison branches of the acting path (csrc/select.cu): SQRL's action filter (sac.py:139-161), Q-sampling recovery
+        # (qrisk.py:214-225), the second push of --add_both_transitions (experiment.py:446-448), --policy Deterministic
+        self.constraint_sampling = bool(constraint_sampling)
+        self.q_sampling = bool(q_sampling_recovery) and self.use_recovery and not self.mf_recovery
+        self.add_both = bool(add_both_transitions) and self.use_recovery
+        self.deterministic = bool(deterministic)
+        self.safe_samples, self.q_samples = int(safe_samples), int(q_samples)    # sac.py:140, qrisk.py:216 hard-code 100 / 1000
+        if self.constraint_sampling and (self.use_recovery or self.deterministic):
+            raise ValueError("the SQRL action filter (use_constraint_sampling) replaces the Gaussian task policy's own draw; the "
+                             "reference's scripts never combine it with use_recovery or --policy Deterministic")
+        if self.q_sampling and mb_recovery:
+            raise ValueError("Q_sampling_recovery and the model-based planner are alternatives (experiment.py:568-573)")
         self.relabel = not disable_action_relabeling            # experiment.py:438-441
         self.host_inputs = bool(host_inputs)
         self.act_staging = True                                 # set False to act with the single fused launch
@@ -101,7 +114,7 @@ class VecEngine(object):
                                 target_update_interval=target_update_interval, mf_recovery=mf_recovery,
                                 action_scale=(sc, sc), grad_scale=1.0 / self.world,
                                 use_tensor_cores=use_tensor_cores, dgd=dgd, update_nu=update_nu, rcpo=rcpo,
-                                auto_alpha=auto_alpha, nu=nu, lambda_rcpo=lambda_rcpo)
+                                auto_alpha=auto_alpha, nu=nu, lambda_rcpo=lambda_rcpo, deterministic=self.deterministic)
         self.cfg = self.agent.cfg
         self.arena = self.agent.arena
         self.counters = self.agent.counters
@@ -110,7 +123,7 @@ class VecEngine(object):
                                          maze_substeps=maze_substeps)
         dev = self.device
         n = self.n
-        self.task_cap = max(int(replay_size), n)
+        self.task_cap = max(int(replay_size), 2 * n if self.add_both else n)
         self.cons_cap = (max(int(safe_replay_size), n) + 15) // 16 * 16
         self.state = torch.zeros(2, n, dtype=torch.float64, device=dev)
         self.ep_steps = torch.zeros(n, dtype=torch.int32, device=dev)
@@ -152,7 +165,10 @@ class VecEngine(object):
                 ([("env_noise", (2, n), torch.float64)] if self.kind != native.ENV_MAZE else []) + \
                 [("eps_task", (n, 2), torch.float32), ("eps_rec", (n, 2), torch.float32), ("rand_u", (n, 2), torch.float32),
                  ("sac_eps_next", (B, 2), torch.float32), ("sac_eps_cur", (B, 2), torch.float32),
-                 ("qr_eps_next", (B, 2), torch.float32), ("qr_eps_rec", (B, 2), torch.float32)]
+                 ("qr_eps_next", (B, 2), torch.float32), ("qr_eps_rec", (B, 2), torch.float32)] + \
+                ([("sqrl_eps", (n, self.safe_samples, 2), torch.float32), ("sqrl_u", (n,), torch.float32)]
+                 if self.constraint_sampling else []) + \
+                ([("qs_u", (n, self.q_samples, 2), torch.float32)] if self.q_sampling else [])
             self._in_flat, self.in_dev = _carve(self._in_specs, device=dev)         # the step's kernels read these views
             if self.kind == native.ENV_MAZE:
                 self.in_dev["env_noise"] = None
@@ -184,6 +200,13 @@ class VecEngine(object):
             self.mpc.state = self.state                      # the planner reads the env state in place
             self.mpc.counters = self.counters                # Philox step counter
             self.action64 = torch.zeros(n, 2, dtype=torch.float64, device=dev)
+        self._sel_ws = None
+        if self.constraint_sampling or self.q_sampling:
+            # candidate workspace: at most ~8M candidate rows (288 MB) at a time, larger env counts loop over chunks
+            k_s = self.safe_samples if self.constraint_sampling else self.q_samples
+            chunk = min(n, max(1, (1 << 23) // k_s))
+            self._sel_ws = torch.empty(native.select_workspace_floats(chunk, k_s), device=dev)
+            self._sel_chunks = -(-n // chunk)
         self.graph = None
         self._side = torch.cuda.Stream(device=dev)
         self._ev_fork = torch.cuda.Event()
@@ -211,7 +234,7 @@ class VecEngine(object):
         if modules is None:
             from .model import build_reference_modules
             sc = ACTION_SCALE[self.env_name]
-            modules = build_reference_modules(hidden=256, action_scale=(sc, sc))
+            modules = build_reference_modules(hidden=256, action_scale=(sc, sc), deterministic=self.deterministic)
         self.agent.load_modules(modules)
 
     def train_mb(self, transitions=None, n_recent=50000, epochs=None):
@@ -297,7 +320,7 @@ class VecEngine(object):
         """acting split into stages that overlap the updates (see _enqueue_step): tcgen05 path, model-free recovery, online
         safety-critic updates (every stage then follows an optimizer step of its own)"""
         return (int(self.cfg.use_tensor_cores) >= 1 and self.use_recovery and self.mf_recovery and self.online_qrisk
-                and self.mpc is None and self.act_staging)
+                and self.mpc is None and self.act_staging and not self.constraint_sampling)
 
     @property
     def early_rec_forward(self):
@@ -444,8 +467,19 @@ class VecEngine(object):
         if staged:
             main.wait_event(self._ev_act)                                          # the Q_risk stage (after the policy stage)
             act_stage(native.ACT_STAGE_RECOVERY)
+        elif self.constraint_sampling:                                             # sac.py:139-161 (SQRL)
+            native.sqrl_select_action(self.cfg, self.arena, self.n, self.safe_samples, self.state, self.counters, self._sel_ws,
+                                      self.action_task, self.action_real, self.recovery, self.qrisk,
+                                      eps_cand=self._in("sqrl_eps"), cat_u=self._in("sqrl_u"), rand_u=self._in("rand_u"),
+                                      start_steps=self.start_steps, seed=self.seed, stream_id=self.rank)
+            k += 4 * self._sel_chunks - 1
         else:
             act_stage(native.ACT_STAGE_ALL)
+        if self.q_sampling:                                                        # qrisk.py:214-225
+            native.qsample_recovery_action(self.cfg, self.arena, self.n, self.q_samples, self.state, self.counters, self._sel_ws,
+                                           self.action_real, recovery=self.recovery, cand_u=self._in("qs_u"), seed=self.seed,
+                                           stream_id=self.rank)
+            k += 3 * self._sel_chunks
         a64 = None
         if self.mpc is not None:                                                   # experiment.py:568-573
             plan = self.mpc.plan(mask=self.recovery)
@@ -464,6 +498,9 @@ class VecEngine(object):
                         out_reward=self.out_reward, out_done=self.out_done, out_constraint=self.out_cons,
                         out_success=self.out_succ, action_f64=a64)                 # experiment.py:420-461
         native.counters_advance(self.counters, self.n, self.task_cap, self.cons_cap, True, self.uses_qrisk)
+        if self.add_both:                                                          # experiment.py:446-448
+            native.replay_push_both(self.task_ring, self.task_cap, self.n, self.recovery, self.action_real, self.counters)
+            k += 1
         self.launches_per_step = k + 3
         return self.launches_per_step
 
@@ -625,9 +662,17 @@ class VecEngine(object):
         alive = np.ones(k, bool)
         for _ in range(HORIZON[self.env_name] + 1):
             prev = ev["state"].t().cpu().numpy().copy()
-            native.agent_act(self.cfg, self.arena, k, ev["state"], ev["counters"], ev["a_task"], ev["a_real"], ev["rec"], ev["q"],
-                             use_recovery=self.use_recovery and self.mpc is None, eval=True, start_steps=0,
-                             seed=self.seed + 7919, stream_id=self.rank)
+            if self.constraint_sampling:       # sac.py:139-161 ignores `eval`: the filter samples in test rollouts too
+                native.sqrl_select_action(self.cfg, self.arena, k, self.safe_samples, ev["state"], ev["counters"], self._sel_ws,
+                                          ev["a_task"], ev["a_real"], ev["rec"], ev["q"], start_steps=0, seed=self.seed + 7919,
+                                          stream_id=self.rank)
+            else:
+                native.agent_act(self.cfg, self.arena, k, ev["state"], ev["counters"], ev["a_task"], ev["a_real"], ev["rec"], ev["q"],
+                                 use_recovery=self.use_recovery and self.mpc is None, eval=True, start_steps=0,
+                                 seed=self.seed + 7919, stream_id=self.rank)
+            if self.q_sampling:
+                native.qsample_recovery_action(self.cfg, self.arena, k, self.q_samples, ev["state"], ev["counters"], self._sel_ws,
+                                               ev["a_real"], recovery=ev["rec"], seed=self.seed + 7919, stream_id=self.rank)
             native.env_step(ev["cfg"], ev["a_task"], ev["a_real"], ev["state"], ev["ep_steps"], ev["ep_return"], ev["counters"],
                             recovery=ev["rec"], out_next_state=ev["nxt"], out_reward=ev["rew"], out_done=ev["done"],
                             out_constraint=ev["cons"], out_success=ev["succ"])
@@ -649,7 +694,8 @@ class VecEngine(object):
         transitions once a ring has wrapped, e.g. after a resume)."""
         c = self.counters.cpu()
         ar = torch.arange(self.n, device=self.device)
-        t_idx = (int(c[native.C_TASK_POS]) + ar) % self.task_cap
+        ar_t = torch.arange(2 * self.n, device=self.device) if self.add_both else ar     # + the add_both_transitions rows
+        t_idx = (int(c[native.C_TASK_POS]) + ar_t) % self.task_cap
         c_idx = (int(c[native.C_CONS_POS]) + ar) % self.cons_cap
         return dict(arena=self.arena.clone(), counters=self.counters.clone(), state=self.state.clone(),
                     ep_steps=self.ep_steps.clone(), ep_return=self.ep_return.clone(), mt=self.mt_state.clone(),

@@ -117,12 +117,9 @@ class Experiment:
                 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
             pg = dist.group.WORLD
         dev = torch.device("cuda", torch.cuda.current_device())
-        if c.use_constraint_sampling or c.policy != "Gaussian" or (c.use_recovery and c.Q_sampling_recovery):
-            raise NotImplementedError("--use_constraint_sampling (SQRL), --policy Deterministic and --Q_sampling_recovery "
-                                      "run on the --num_envs 1 path only")
-        if c.add_both_transitions:
-            raise NotImplementedError("--add_both_transitions (a data-dependent number of pushes per step) runs on the "
-                                      "--num_envs 1 path only")
+        if c.use_constraint_sampling and (c.use_recovery or c.policy != "Gaussian"):
+            raise NotImplementedError("--use_constraint_sampling (SQRL) together with --use_recovery / --policy Deterministic runs "
+                                      "on the --num_envs 1 path only (no reference script combines them)")
         eng = VecEngine(c.env_name, self.num_envs, batch_size=c.batch_size, replay_size=c.replay_size,
                         safe_replay_size=c.safe_replay_size, gamma=c.gamma, alpha=c.alpha, tau=c.tau, lr=c.lr,
                         gamma_safe=c.gamma_safe, tau_safe=c.tau_safe, eps_safe=c.eps_safe,
@@ -135,7 +132,9 @@ class Experiment:
                         dgd=c.DGD_constraints, update_nu=c.update_nu, rcpo=c.RCPO,
                         auto_alpha=bool(c.automatic_entropy_tuning), nu=c.nu, lambda_rcpo=c.lambda_RCPO,
                         disable_action_relabeling=c.disable_action_relabeling, mb_recovery=self.mb_recovery,
-                        mpc_popsize=getattr(c, "mpc_popsize", None))
+                        mpc_popsize=getattr(c, "mpc_popsize", None), constraint_sampling=c.use_constraint_sampling,
+                        q_sampling_recovery=c.Q_sampling_recovery, add_both_transitions=c.add_both_transitions,
+                        deterministic=c.policy != "Gaussian")
         eng.init_agent()          # same torch seed on every rank -> identical replicas
         return eng
 

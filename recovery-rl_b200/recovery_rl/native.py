@@ -269,6 +269,38 @@ def agent_act(cfg, arena, n, state, counters, action_task, action_real, recovery
                                      p(qrisk_out, "f32"), int(stages), int(max_ctas), _stream(stream)), "rrl_agent_act_stage")
 
 
+def select_workspace_floats(chunk_envs, samples):
+    lib().rrl_select_workspace_floats.restype = C.c_int64
+    return int(lib().rrl_select_workspace_floats(C.c_int64(chunk_envs), C.c_int32(samples)))
+
+
+def sqrl_select_action(cfg, arena, n, samples, state, counters, workspace, action_task, action_real, recovery=None,
+                       qrisk_out=None, eps_cand=None, cat_u=None, rand_u=None, start_steps=0, seed=0, stream_id=0, stream=None):
+    """SAC.select_action with --use_constraint_sampling (sac.py:139-161) for n env copies (include/rrl.h)."""
+    _check(lib().rrl_sqrl_select_action(C.byref(cfg), p(arena, "f32"), C.c_int64(n), C.c_int32(samples), p(state, "f64"),
+                                        p(eps_cand, "f32"), p(cat_u, "f32"), p(rand_u, "f32"), C.c_int64(start_steps),
+                                        C.c_uint64(seed & 0xFFFFFFFFFFFFFFFF), C.c_int32(stream_id), p(counters, "i64"),
+                                        p(workspace, "f32"), C.c_int64(workspace.numel()), p(action_task, "f32"),
+                                        p(action_real, "f32"), p(recovery, "u8"), p(qrisk_out, "f32"), _stream(stream)),
+           "rrl_sqrl_select_action")
+
+
+def qsample_recovery_action(cfg, arena, n, samples, state, counters, workspace, action_real, recovery=None, cand_u=None,
+                            seed=0, stream_id=0, stream=None):
+    """QRiskWrapper.select_action with --Q_sampling_recovery (qrisk.py:214-225) for the env copies whose flag is set."""
+    _check(lib().rrl_qsample_recovery_action(C.byref(cfg), p(arena, "f32"), C.c_int64(n), C.c_int32(samples), p(state, "f64"),
+                                             p(cand_u, "f32"), p(recovery, "u8"), C.c_uint64(seed & 0xFFFFFFFFFFFFFFFF),
+                                             C.c_int32(stream_id), p(counters, "i64"), p(workspace, "f32"),
+                                             C.c_int64(workspace.numel()), p(action_real, "f32"), _stream(stream)),
+           "rrl_qsample_recovery_action")
+
+
+def replay_push_both(task_ring, task_capacity, n, recovery, action_real, counters, stream=None):
+    """--add_both_transitions (experiment.py:446-448), after env_step + counters_advance."""
+    _check(lib().rrl_replay_push_both(p(task_ring, "f32"), C.c_int64(task_capacity), C.c_int64(n), p(recovery, "u8"),
+                                      p(action_real, "f32"), p(counters, "i64"), _stream(stream)), "rrl_replay_push_both")
+
+
 def _upd(fn, name):
     def call(cfg, arena, counters, losses, eps_a=None, eps_b=None, seed=0, stream_id=0, stream=None):
         args = [C.byref(cfg), p(arena, "f32"), p(eps_a, "f32")]

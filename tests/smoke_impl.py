@@ -15,7 +15,7 @@ def _close(a, b, what, rtol=1e-4, atol=1e-5):
 
 
 def run(env_name="navigation1", n=512, B=64, steps=4, seed=3, verbose=True, gamma_safe=0.8, eps_safe=0.3, pos_fraction=-1.0,
-        replay=8192, demos_n=400, tensor_cores=0):
+        replay=8192, demos_n=400, tensor_cores=0, deterministic=False):
     from oracle import envs as oenvs
     from oracle.agent import Agent
     from recovery_rl import native
@@ -26,10 +26,10 @@ def run(env_name="navigation1", n=512, B=64, steps=4, seed=3, verbose=True, gamm
     sc = ACTION_SCALE[env_name]
     torch.manual_seed(seed)
     np.random.seed(seed)
-    ora = Agent(action_scale=(np.float32(sc),) * 2, gamma_safe=gamma_safe, eps_safe=eps_safe)
+    ora = Agent(action_scale=(np.float32(sc),) * 2, gamma_safe=gamma_safe, eps_safe=eps_safe, deterministic=deterministic)
     eng = VecEngine(env_name, n, batch_size=B, replay_size=max(replay, 2 * n), safe_replay_size=max(replay, 2 * n),
                     gamma_safe=gamma_safe, eps_safe=eps_safe, pos_fraction=pos_fraction, seed=seed, host_inputs=True,
-                    start_steps=0, use_tensor_cores=tensor_cores)
+                    start_steps=0, use_tensor_cores=tensor_cores, deterministic=deterministic)
     eng.init_agent(ora.nets())
     rs = np.random.RandomState(seed)
     if kind == oenvs.MAZE:
@@ -56,6 +56,13 @@ def run(env_name="navigation1", n=512, B=64, steps=4, seed=3, verbose=True, gamm
                    qr_eps_next=rs.randn(B, 2).astype(np.float32), qr_eps_rec=rs.randn(B, 2).astype(np.float32))
         if kind != oenvs.MAZE:
             inp["env_noise"] = rs.randn(n, 2).T
+        if deterministic:
+            # --policy Deterministic (model.py:475-481): the policy's draw is N(0, 0.1) clamped to +-0.25 -- one vector per
+            # sample() call, i.e. per env copy when acting and ONE for the whole batch inside an update
+            clamp = lambda z: np.clip(np.float32(0.1) * z, -0.25, 0.25).astype(np.float32)
+            inp["eps_task"] = clamp(inp["eps_task"])
+            for k in ("sac_eps_next", "sac_eps_cur", "qr_eps_next"):
+                inp[k] = np.repeat(clamp(inp[k][:1]), B, axis=0)
         before = eng.read_counters()
         out = eng.step_host(inp)
         cn = eng.read_counters()

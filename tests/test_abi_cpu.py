@@ -19,7 +19,7 @@ def test_every_declared_symbol_is_exported(native):
     lib = ctypes.CDLL(native.LIB_PATH)
     missing = [n for n in names if not hasattr(lib, n)]
     assert not missing, missing
-    assert native.version() == 4
+    assert native.version() == 5
 
 
 def test_arena_layout_matches_reference_parameter_shapes(native):

@@ -192,7 +192,7 @@ def test_script_algorithm_lines_run(native, cuda, tmp_path, algo, env_name):
         assert torch.isfinite(rp.dyn_image).all()
 
 
-@pytest.mark.parametrize("algo", ["LR", "RSPO", "RCPO", "RP", "unconstrained"])
+@pytest.mark.parametrize("algo", ["LR", "RSPO", "SQRL", "RCPO", "RP", "unconstrained"])
 def test_vectorised_comparison_algorithms_run(native, cuda, tmp_path, algo):
     import arg_utils
     from recovery_rl.experiment import Experiment
@@ -203,7 +203,7 @@ def test_vectorised_comparison_algorithms_run(native, cuda, tmp_path, algo):
     exp = Experiment(arg_utils.get_args(argv))
     stats = exp.run()
     assert stats[-1]["total_numsteps"] > 30000 and stats[-1]["error"] == 0 and stats[-1]["sac_updates"] > 20
-    uses_qrisk = algo in ("LR", "RSPO", "RCPO")
+    uses_qrisk = algo in ("LR", "RSPO", "SQRL", "RCPO")
     assert (stats[-1]["qrisk_updates"] > 20) == uses_qrisk
     assert torch.isfinite(exp.engine.arena[:exp.engine.agent.grad_off]).all()
 
