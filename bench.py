@@ -617,7 +617,9 @@ def run_ours(args, rank, world, local_rank):
                            "timing": "sum of per-step CUDA-event intervals on the launching stream, max over ranks",
                            "rng": "Philox4x32-10 on device (value); host draws uploaded (e2e)",
                            "cuda_graph": eng.graph is not None, "tensor_cores": bool(args.tc),
-                           "grad_allreduce": grad_mode(eng, world)},
+                           "grad_allreduce": grad_mode(eng, world),
+                           "programmatic_dependent_launch": __import__("recovery_rl.native", fromlist=["x"]).pdl_enabled(),
+                           "stage_ctas": eng.stage_ctas},
                 "roofline": roofline, "roofline_env": roofline_env, "breakdown": breakdown, "cpu_baseline": cpu_baseline, "e2e": e2e,
                 "gpu_launches": eng.launches_per_step * K, "launches_per_step": eng.launches_per_step, "clocks": clocks,
                 "counters": {k: c[k] for k in ("total_numsteps", "episodes", "num_viols", "num_successes", "sac_updates",

@@ -31,6 +31,13 @@ extern "C" {
 
 const char* rrl_last_error(void);
 int rrl_version(void);
+/* Programmatic dependent launch of the vector step's kernels (sampler, tcgen05 forward / backward, optimizer step, acting,
+ * env step): each is scheduled while its predecessor in the stream still runs and waits (griddepcontrol.wait, its first
+ * statement) for that kernel's completion, which hides the launch latency of the ~20 short dependent kernels of a step.
+ * OFF by default (measured slower on B200 inside the captured step: 0.366 vs 0.339 ms); RRL_PDL=1 in the environment or
+ * rrl_set_pdl(1) turns it on.  Returns the previous setting
+ * (enabled < 0: query only). */
+int rrl_set_pdl(int enabled);
 
 /* ------------------------------------------------------------------ environments ------- */
 enum { RRL_ENV_NAV1 = 0, RRL_ENV_NAV2 = 1, RRL_ENV_MAZE = 2 };

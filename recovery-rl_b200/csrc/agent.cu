@@ -668,6 +668,7 @@ __device__ __forceinline__ void write_tile_images(float* arena, const ImgRef& R,
     }
 }
 __global__ void __launch_bounds__(kThreads) adam_tile_kernel(const __grid_constant__ AdamTileArgs A) {
+    pdl_wait();   // programmatic dependent launch (common.cuh): before the first global read, on every path
     if (A.counters[A.rows_counter] <= 0) return;
     __shared__ float s_bc[2];
     __shared__ int s_polyak;
@@ -1103,8 +1104,7 @@ int launch_adam_tiled(const rrl_agent_config_t* cfg, const Layout& L, float* are
             A.flat_blk[A.n_flat] = (unsigned char)b;
             ++A.n_flat;
         }
-    adam_tile_kernel<<<A.n_w2 * 64 + A.n_flat, kThreads, 0, st>>>(A);
-    RRL_CHECK_LAUNCH();
+    RRL_CUDA(rrl_launch_pdl(adam_tile_kernel, dim3(A.n_w2 * 64 + A.n_flat), dim3(kThreads), 0, st, A));
     return 0;
 }
 int launch_polyak(const Layout& L, float* arena, const int64_t* counters, int dst, int src, float tau, int rows_counter,

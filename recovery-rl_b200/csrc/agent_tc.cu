@@ -185,6 +185,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) act_tc_kernel(const __grid_cons
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     TcSmem& S = *reinterpret_cast<TcSmem*>(smem_raw);
     const ActArgs& A = T.a;
+    pdl_wait();   // programmatic dependent launch (common.cuh)
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
     const int64_t n_tiles = (A.n + TM - 1) / TM;
     // passes of this launch, in issue order (POL, REC, QR1, QR2); accumulator of a pass = its position & 1
@@ -511,6 +512,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fwd_tc_kernel(const __grid_cons
     // compiler lose the shared address space and emit generic LD / ST (long-scoreboard) instead of LDS / STS
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     FwdTcSmem& S = *reinterpret_cast<FwdTcSmem*>(smem_raw);
+    pdl_wait();   // programmatic dependent launch (common.cuh): the previous kernel of the stream has completed past here
     const int64_t rows = A.rows_ptr ? *A.rows_ptr : A.rows_const;
     const int64_t row0 = (int64_t)blockIdx.x * TM;
     TSTAMP(0);
@@ -759,6 +761,7 @@ __device__ __forceinline__ float pow2_scale(float bound) {
 
 __global__ void __launch_bounds__(kTcThreads, 1) bwd_tc_kernel(const __grid_constant__ GemmArgs G) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];   // see act_tc_kernel: no pointer arithmetic on the base
+    pdl_wait();
     TSTAMP(0);
     BwdTcSmem& S = *reinterpret_cast<BwdTcSmem*>(smem_raw);
     const int64_t rows = *G.rows_ptr;
@@ -1213,8 +1216,7 @@ int fwd_tc_launch(const FwdArgs& A, int64_t max_rows, cudaStream_t st) {
     for (int i = 0; i < A.n_pass; ++i)
         if (!A.p[i].tc_img) { rrl_set_error("fwd_tc_launch: pass %d has no tcgen05 weight image", i); return -2; }
     dim3 grid((unsigned)((max_rows + TM - 1) / TM), (unsigned)A.n_pass);
-    fwd_tc_kernel<<<grid, kTcThreads, smem, st>>>(A);
-    RRL_CHECK_LAUNCH();
+    RRL_CUDA(rrl_launch_pdl(fwd_tc_kernel, grid, dim3(kTcThreads), smem, st, A));
     return 0;
 }
 
@@ -1240,8 +1242,7 @@ int bwd_tc_launch(const GemmArgs& G, int64_t max_rows, cudaStream_t st) {
         if (!G.p[i].k_is_rows && !G.p[i].tc_imgT) { rrl_set_error("bwd_tc_launch: pass %d has no W2^T image", i); return -2; }
     int64_t tiles = (max_rows + TM - 1) / TM;
     if (tiles < H / TM) tiles = H / TM;
-    bwd_tc_kernel<<<dim3((unsigned)tiles, (unsigned)G.n_pass), kTcThreads, smem, st>>>(G);
-    RRL_CHECK_LAUNCH();
+    RRL_CUDA(rrl_launch_pdl(bwd_tc_kernel, dim3((unsigned)tiles, (unsigned)G.n_pass), dim3(kTcThreads), smem, st, G));
     return 0;
 }
 
@@ -1294,8 +1295,7 @@ int act_tc_launch(const ActArgs& A, const float* arena, const Layout& L, int sta
     int64_t sms = rrl_num_sms();
     if (max_ctas > 0 && max_ctas < sms) sms = max_ctas;
     const int grid = (int)(tiles < sms ? tiles : sms);
-    act_tc_kernel<<<grid, kTcThreads, smem, st>>>(T);
-    RRL_CHECK_LAUNCH();
+    RRL_CUDA(rrl_launch_pdl(act_tc_kernel, dim3(grid), dim3(kTcThreads), smem, st, T));
     return 0;
 }
 

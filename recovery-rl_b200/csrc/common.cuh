@@ -39,6 +39,34 @@ void rrl_set_error(const char* fmt, ...);
         }                                                                               \
     } while (0)
 
+// ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch: the kernels of the vector step are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization, so that the NEXT kernel of the stream is scheduled (its CTAs resident,
+// parameters loaded) while the current one still runs; it blocks in pdl_wait() -- the first thing every such kernel does,
+// on every path, before it touches global memory -- until the previous kernel has completed and flushed.  A kernel releases
+// its successor right after its own wait, so at most one future kernel is resident at a time.  OFF by default: on B200 the
+// captured step got SLOWER with it (0.366 vs 0.339 ms, profiles/r2/pdl_ab.txt); RRL_PDL=1 in the environment (or
+// rrl_set_pdl(1)) turns it on.  Without the launch attribute the waits are no-ops and the kernels are stream-ordered.
+// ---------------------------------------------------------------------------------------------
+int rrl_pdl_enabled();
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+template <typename... KArgs, typename... Args>
+static inline cudaError_t rrl_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = rrl_pdl_enabled() ? 1 : 0;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
+
 static inline int rrl_num_sms() {
     static int sms = 0;
     if (!sms) {

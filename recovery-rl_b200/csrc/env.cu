@@ -191,6 +191,7 @@ env_step_kernel(EnvParams P, const float* __restrict__ a_task, const float* __re
                 int64_t* __restrict__ counters, double* __restrict__ o_next, double* __restrict__ o_reward,
                 uint8_t* __restrict__ o_done, uint8_t* __restrict__ o_cons, uint8_t* __restrict__ o_succ,
                 const double* __restrict__ a_f64) {
+    pdl_wait();   // programmatic dependent launch (common.cuh): the acting kernel has completed past here
     const int64_t n = P.cfg.n_envs;
     const int kind = P.cfg.kind;
     const uint64_t vstep = (uint64_t)counters[RRL_C_VEC_STEP];
@@ -325,6 +326,7 @@ env_step_kernel(EnvParams P, const float* __restrict__ a_task, const float* __re
 
 __global__ void counters_advance_kernel(int64_t* counters, int64_t n, int64_t task_cap, int64_t cons_cap,
                                         int push_task, int push_cons) {
+    pdl_wait();
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         counters[RRL_C_TOTAL_NUMSTEPS] += n;
         counters[RRL_C_VEC_STEP] += 1;
@@ -419,20 +421,19 @@ extern "C" int rrl_env_step(const rrl_env_config_t* cfg, const float* action_tas
     EnvParams P = make_params(cfg);
     // maze: 500 dependent substeps per env and divergent contact paths -> small CTAs balance the 148 SMs better
     const int threads = cfg->kind == RRL_ENV_MAZE ? 64 : 256;
-    env_step_kernel<<<grid_for(cfg->n_envs, threads), threads, 0, (cudaStream_t)stream>>>(
-        P, action_task, action_real, recovery, noise, reset_draws, state, ep_steps, ep_return, task_ring,
-        task_capacity > 0 ? task_capacity : 1, cons_ring, cons_flags, cons_capacity > 0 ? cons_capacity : 1, counters,
-        out_next_state, out_reward, out_done, out_constraint, out_success, action_real_f64);
-    RRL_CHECK_LAUNCH();
+    RRL_CUDA(rrl_launch_pdl(env_step_kernel, dim3(grid_for(cfg->n_envs, threads)), dim3(threads), 0, (cudaStream_t)stream,
+                            P, action_task, action_real, recovery, noise, reset_draws, state, ep_steps, ep_return, task_ring,
+                            task_capacity > 0 ? task_capacity : (int64_t)1, cons_ring, cons_flags,
+                            cons_capacity > 0 ? cons_capacity : (int64_t)1, counters, out_next_state, out_reward, out_done,
+                            out_constraint, out_success, action_real_f64));
     return 0;
 }
 
 extern "C" int rrl_counters_advance(int64_t* counters, int64_t n, int64_t task_capacity, int64_t cons_capacity,
                                     int push_task, int push_cons, void* stream) {
     RRL_CHECK_ARG(counters, "null counters");
-    counters_advance_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(counters, n, task_capacity > 0 ? task_capacity : 1,
-                                                               cons_capacity > 0 ? cons_capacity : 1, push_task,
-                                                               push_cons);
-    RRL_CHECK_LAUNCH();
+    RRL_CUDA(rrl_launch_pdl(counters_advance_kernel, dim3(1), dim3(32), 0, (cudaStream_t)stream, counters, n,
+                            task_capacity > 0 ? task_capacity : (int64_t)1, cons_capacity > 0 ? cons_capacity : (int64_t)1,
+                            push_task, push_cons));
     return 0;
 }

@@ -283,6 +283,7 @@ replay_sample_kernel(rrl_sample_config_t cfg, const float* __restrict__ ring, co
     const int t = threadIdx.x;
     const int B = cfg.batch_size;
     const bool strat = cfg.is_constraint && cfg.pos_fraction >= 0.0;
+    pdl_wait();   // programmatic dependent launch (common.cuh)
 
     // ---- gates and effective batch size (experiment.py:397,407-410; qrisk.py:100-104) ---------
     const int64_t len = counters[cfg.is_constraint ? RRL_C_CONS_LEN : RRL_C_TASK_LEN];
@@ -519,9 +520,8 @@ extern "C" int rrl_replay_sample(const rrl_sample_config_t* cfg, const float* ri
         RRL_CUDA(cudaFuncSetAttribute(replay_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    replay_sample_kernel<<<1, kThreads, smem, (cudaStream_t)stream>>>(*cfg, ring, cons_flags, chunk_counts, n_chunks,
-                                                                      mt_state, counters, rows_counter, out_idx, out_s,
-                                                                      out_a, out_r, out_s2, out_m, tab, log_t, work_ints);
-    RRL_CHECK_LAUNCH();
+    RRL_CUDA(rrl_launch_pdl(replay_sample_kernel, dim3(1), dim3(kThreads), smem, (cudaStream_t)stream, *cfg, ring, cons_flags,
+                            chunk_counts, n_chunks, mt_state, counters, rows_counter, out_idx, out_s, out_a, out_r, out_s2, out_m,
+                            tab, log_t, work_ints));
     return 0;
 }

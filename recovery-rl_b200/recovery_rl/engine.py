@@ -14,6 +14,8 @@ owns N/world env copies and its own replay shards; gradients are summed inside t
 NVLink peer memory (peer_grads: symmetric arena + flag barrier) or, as a fallback, with one NCCL all-reduce per
 optimizer step over the flat gradient block (1/world applied inside Adam either way).
 """
+import os
+
 import numpy as np
 import torch
 
@@ -214,7 +216,9 @@ class VecEngine(object):
         self._side2 = torch.cuda.Stream(device=dev)           # staged acting (policy / Q_risk stages next to the updates)
         self._ev_act = torch.cuda.Event()
         self._ev_stage = [torch.cuda.Event(), torch.cuda.Event()]
-        self.stage_ctas = 128                                 # SMs a side-stream acting stage may occupy (148 - the updates' 16 + slack)
+        # SMs a side-stream acting stage may occupy: 148 - the running update kernel's <= 16 CTAs (+ the next update kernel's,
+        # resident early under programmatic dependent launch)
+        self.stage_ctas = int(os.environ.get("RRL_STAGE_CTAS", "128"))
         self.launches_per_step = 0
         self._grad_views = None
 
@@ -514,17 +518,27 @@ class VecEngine(object):
         self._enqueue_step()
         torch.cuda.synchronize()
         self.restore(saved)
+        self.graph = self._try_capture()
+        if self.graph is None and native.set_pdl(False):
+            # programmatic dependent launches could not be captured on this driver: stream-ordered launches instead
+            self.pdl_disabled = self.capture_error
+            self.restore(saved)
+            self.graph = self._try_capture()
+            if self.graph is None:
+                native.set_pdl(True)
+        self.restore(saved)
+        return self.graph
+
+    def _try_capture(self):
         try:
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 self._enqueue_step()
-            self.graph = g
+            return g
         except Exception as ex:     # e.g. a collective that cannot be captured: keep the eager path
-            self.graph = None
             self.capture_error = repr(ex)
             torch.cuda.synchronize()
-        self.restore(saved)
-        return self.graph
+            return None
 
     def replay(self):
         if self.graph is None:

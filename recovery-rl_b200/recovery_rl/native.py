@@ -111,6 +111,15 @@ def version():
     return lib().rrl_version()
 
 
+def set_pdl(enabled):
+    """programmatic dependent launch of the step's kernels (include/rrl.h); returns the previous setting"""
+    return bool(lib().rrl_set_pdl(int(bool(enabled))))
+
+
+def pdl_enabled():
+    return bool(lib().rrl_set_pdl(-1))
+
+
 # ------------------------------------------------------------------------------------------------
 # environments
 # ------------------------------------------------------------------------------------------------
