@@ -1295,7 +1295,9 @@ int act_tc_launch(const ActArgs& A, const float* arena, const Layout& L, int sta
     int64_t sms = rrl_num_sms();
     if (max_ctas > 0 && max_ctas < sms) sms = max_ctas;
     const int grid = (int)(tiles < sms ? tiles : sms);
-    RRL_CUDA(rrl_launch_pdl(act_tc_kernel, dim3(grid), dim3(kTcThreads), smem, st, T));
+    // a bounded (side-stream) stage is NOT made resident early: its one-CTA-per-SM footprint, blocked in pdl_wait(), would keep
+    // the SMs from the update kernels it is meant to run next to
+    RRL_CUDA(rrl_launch_pdl_if(max_ctas <= 0, act_tc_kernel, dim3(grid), dim3(kTcThreads), smem, st, T));
     return 0;
 }
 

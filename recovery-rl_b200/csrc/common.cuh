@@ -55,15 +55,20 @@ __device__ __forceinline__ void pdl_wait() {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 template <typename... KArgs, typename... Args>
-static inline cudaError_t rrl_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+static inline cudaError_t rrl_launch_pdl_if(bool allow, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                           Args&&... args) {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = rrl_pdl_enabled() ? 1 : 0;
+    at[0].val.programmaticStreamSerializationAllowed = (allow && rrl_pdl_enabled()) ? 1 : 0;
     cfg.attrs = at; cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+template <typename... KArgs, typename... Args>
+static inline cudaError_t rrl_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    return rrl_launch_pdl_if(true, kernel, grid, block, smem, st, static_cast<Args&&>(args)...);
 }
 #endif
 
