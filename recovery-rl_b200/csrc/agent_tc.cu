@@ -20,6 +20,7 @@
 // TMEM accumulators (acc_full / acc_empty) so the epilogue of one network overlaps the MMAs of the next.
 // Pass order per tile: policy, recovery, Q_risk head 1, Q_risk head 2 (the two state-only networks first so
 // the tensor pipe has work while the policy epilogue produces the action the Q_risk passes need).
+#include <type_traits>
 #include "tc_common.cuh"
 
 using namespace rrl;
@@ -118,8 +119,9 @@ __device__ __forceinline__ const HeadW& pass_head(const ActArgs& a, int p) {
 
 // producer: layer 1 of `pass`, the 8 hidden units of core column q of k-chunk c for TWO rows, as fp16 hi/lo pieces of the
 // canonical A layout (registers).  W1 / b1 are staged pre-multiplied by SA (a power of two: exact) and read once for both rows.
+template <bool FOUR>
 __device__ __forceinline__ void layer1_chunk2(const TcSmem& S, int pass, int c, int q, const float (&xa)[4], const float (&xb)[4],
-                                              bool four, uint4* hia, uint4* loa, uint4* hib, uint4* lob) {
+                                              uint4* hia, uint4* loa, uint4* hib, uint4* lob) {
     float ha[8], hb[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
@@ -128,7 +130,7 @@ __device__ __forceinline__ void layer1_chunk2(const TcSmem& S, int pass, int c, 
         const float b = S.sm.b1[pass][k];
         float u = fmaf(wv.x, xa[0], b), v = fmaf(wv.x, xb[0], b);
         u = fmaf(wv.y, xa[1], u); v = fmaf(wv.y, xb[1], v);
-        if (four) {
+        if (FOUR) {   // compile-time: a predicated FFMA still takes its issue slot
             u = fmaf(wv.z, xa[2], u); v = fmaf(wv.z, xb[2], v);
             u = fmaf(wv.w, xa[3], u); v = fmaf(wv.w, xb[3], v);
         }
@@ -301,21 +303,26 @@ __global__ void __launch_bounds__(kTcThreads, 1) act_tc_kernel(const __grid_cons
                 const bool four = pass >= PASS_QR1;
                 const uint32_t it = (uint32_t)k * NCHUNK;    // running chunk index: stage = (it + c) % NSTAGE
                 // software pipeline: the next chunk is computed between the stores of a chunk and their proxy fence
-                uint4 hia, loa, hib, lob;
-                layer1_chunk2(S, pass, 0, pq, xa, xb, four, &hia, &loa, &hib, &lob);
-                for (int c = 0; c < NCHUNK; ++c) {
-                    const uint32_t ic = it + c;
-                    const int stage = ic % NSTAGE;
-                    mbar_wait(smem_u32(&S.empty[stage]), ((ic / NSTAGE) & 1) ^ 1);
-                    unsigned char* a_hi = S.stage[stage];
-                    *reinterpret_cast<uint4*>(a_hi + pq * LBO_A + pa * 16) = hia;
-                    *reinterpret_cast<uint4*>(a_hi + A_IMG + pq * LBO_A + pa * 16) = loa;
-                    *reinterpret_cast<uint4*>(a_hi + pq * LBO_A + pb2 * 16) = hib;
-                    *reinterpret_cast<uint4*>(a_hi + A_IMG + pq * LBO_A + pb2 * 16) = lob;
-                    if (c + 1 < NCHUNK) layer1_chunk2(S, pass, c + 1, pq, xa, xb, four, &hia, &loa, &hib, &lob);
-                    fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
-                    mbar_arrive_warp(smem_u32(&S.full[stage]));
-                }
+                auto produce = [&](auto four_c) {
+                    constexpr bool FOUR = decltype(four_c)::value;
+                    uint4 hia, loa, hib, lob;
+                    layer1_chunk2<FOUR>(S, pass, 0, pq, xa, xb, &hia, &loa, &hib, &lob);
+                    for (int c = 0; c < NCHUNK; ++c) {
+                        const uint32_t ic = it + c;
+                        const int stage = ic % NSTAGE;
+                        mbar_wait(smem_u32(&S.empty[stage]), ((ic / NSTAGE) & 1) ^ 1);
+                        unsigned char* a_hi = S.stage[stage];
+                        *reinterpret_cast<uint4*>(a_hi + pq * LBO_A + pa * 16) = hia;
+                        *reinterpret_cast<uint4*>(a_hi + A_IMG + pq * LBO_A + pa * 16) = loa;
+                        *reinterpret_cast<uint4*>(a_hi + pq * LBO_A + pb2 * 16) = hib;
+                        *reinterpret_cast<uint4*>(a_hi + A_IMG + pq * LBO_A + pb2 * 16) = lob;
+                        if (c + 1 < NCHUNK) layer1_chunk2<FOUR>(S, pass, c + 1, pq, xa, xb, &hia, &loa, &hib, &lob);
+                        fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+                        mbar_arrive_warp(smem_u32(&S.full[stage]));
+                    }
+                };
+                if (four) produce(std::true_type{});
+                else produce(std::false_type{});
             }
         } else {
             const int ew = warp - kActProdWarps;                 // 0..7
