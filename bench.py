@@ -475,9 +475,33 @@ def run_ours(args, rank, world, local_rank):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    bw0 = eng.counters[native.C_BARRIER_WAIT_NS:native.C_BARRIERS + 1].clone()
+    opt0 = int(eng.counters[native.C_OPT_STEP_NS])
+    if hasattr(native.lib(), "rrl_debug_opt_times"):
+        import ctypes as _ct
+        native.lib().rrl_debug_opt_times((_ct.c_uint64 * 4)())          # reset the diagnostic sums
     times = timed_steps(eng, K, flush, barrier)
     clocks = sampler.stop() if rank == 0 else None
     total_ms = max_over_ranks(sum(times), dev, world)
+    opt_step_us = (int(eng.counters[native.C_OPT_STEP_NS]) - opt0) * 1e-3 / K     # inside the optimizer-step kernels, per step
+    import ctypes
+    dbg4 = (ctypes.c_uint64 * 4)()
+    opt_dbg = None
+    if hasattr(native.lib(), "rrl_debug_opt_times") and native.lib().rrl_debug_opt_times(dbg4) == 0 and dbg4[3]:
+        opt_dbg = {"launches": int(dbg4[3]), "barrier_us_per_launch": dbg4[0] * 1e-3 / dbg4[3],
+                   "grad_loads_us_per_launch": dbg4[1] * 1e-3 / dbg4[3], "rest_us_per_launch": dbg4[2] * 1e-3 / dbg4[3]}
+    barrier_wait = None
+    if world > 1:
+        # how long each rank's optimizer-step kernels waited for the slowest peer's gradient flag inside the timed region
+        # (device-side globaltimer, include/rrl.h RRL_C_BARRIER_WAIT_NS): rank skew + signal latency, the rest of the
+        # multi-GPU overhead is the peer loads
+        bw = (eng.counters[native.C_BARRIER_WAIT_NS:native.C_BARRIERS + 1] - bw0).double()
+        allbw = [torch.empty_like(bw) for _ in range(world)]
+        dist.all_gather(allbw, bw)
+        per_rank = [float(b[0]) * 1e-3 / K for b in allbw]
+        barrier_wait = {"us_per_step_by_rank": [round(x, 2) for x in per_rank], "us_per_step_mean": sum(per_rank) / world,
+                        "barriers_per_step": float(allbw[0][1]) / K,
+                        "note": "time CTA 0 of the optimizer-step kernels spent waiting for the peers' gradient flags (device globaltimer)"}
     c = eng.read_counters()
     assert c["error"] == 0, "device-side error %r" % (c,)
     value = world * args.envs * K / (total_ms * 1e-3)
@@ -525,11 +549,14 @@ def run_ours(args, rank, world, local_rank):
                     "note": ("maze: 500 dependent fp64 substeps per env -> fp64-pipe / latency bound, not bandwidth-bound (DESIGN.md)"
                              if args.env_name == "maze" else "navigation: one fp64 step per env; 120 B/env-step algorithmic")}
     breakdown = {"step_ms": step_ms, "act_ms": act_ms, "env_ms": env_ms, "updates_eager_ms": upd_ms,
+                 "optimizer_step_kernels_us_per_step": opt_step_us, "optimizer_step_cta0": opt_dbg,
                  "note": "kernels timed alone, L2 flushed before each; the update chain as eager launches (the step replays them in a graph)"}
 
     multi = {}
     if world > 1 and not args.no_checks:
         multi = multi_gpu_checks(args, rank, world, pg, dev, eng, K, W, flush, barrier)
+    if barrier_wait is not None:
+        multi["barrier_wait"] = barrier_wait
 
     # ---- end to end through the host-buffer face (pinned H2D of the step's random draws, D2H of results) ----
     del flush

@@ -71,6 +71,10 @@ enum {
     RRL_C_TICKET2        = 27, /* scratch: CTA arrival ticket of the update kernels whose last CTA runs the loss / sample-backward stage */
     RRL_C_GATE_SATISFIED = 28, /* multi-GPU: the violation count of the Q_risk online gate (experiment.py:410) has passed its threshold on
                                   every rank (monotone: counts only grow) -> rrl_peer_sync_gate_counts stops exchanging */
+    RRL_C_BARRIER_WAIT_NS= 29, /* multi-GPU diagnostic: nanoseconds CTA 0 of the optimizer-step kernels has spent waiting for the slowest
+                                  peer's gradient flag (rank skew + signal latency), summed over barriers (fused-barrier path) */
+    RRL_C_BARRIERS       = 30, /*   ... and the number of such barriers                                                         */
+    RRL_C_OPT_STEP_NS    = 31, /* diagnostic: nanoseconds inside the tiled optimizer-step kernels (CTA 0 start -> last CTA end), summed */
     RRL_NUM_COUNTERS     = 32
 };
 

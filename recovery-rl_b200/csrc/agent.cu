@@ -667,13 +667,44 @@ __device__ __forceinline__ void write_tile_images(float* arena, const ImgRef& R,
         *reinterpret_cast<uint4*>(img + base + kLo) = lo;
     }
 }
+__device__ unsigned long long g_opt_t0;   // diagnostic (RRL_C_OPT_STEP_NS): start stamp of the running optimizer-step kernel
+// diagnostic: CTA 0's time line inside the optimizer-step kernels, summed over launches (ns): [0] start -> barrier done,
+// [1] -> gradients (own + peers') loaded, [2] -> CTA 0 done, [3] launches  (rrl_debug_opt_times)
+__device__ unsigned long long g_opt_dbg[4];
+__device__ __forceinline__ unsigned long long gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)::"memory");
+    return t;
+}
 __global__ void __launch_bounds__(kThreads) adam_tile_kernel(const __grid_constant__ AdamTileArgs A) {
     pdl_wait();   // programmatic dependent launch (common.cuh): before the first global read, on every path
     if (A.counters[A.rows_counter] <= 0) return;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        unsigned long long t0;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        g_opt_t0 = t0;
+    }
     __shared__ float s_bc[2];
     __shared__ int s_polyak;
     __shared__ float tile[32][33], ttile[32][33];
     const int t = threadIdx.x;
+    // tile CTAs: parameters and moments are loaded BEFORE the block waits for thread 0's double-precision bias corrections (two
+    // pow() calls, ~1.5 us) and for the peers' flags: independent of both
+    const int n_tile_ctas = A.n_w2 * 64;
+    const bool is_tile = (int)blockIdx.x < n_tile_ctas;
+    const AdamW2& W = A.w2[is_tile ? (blockIdx.x >> 6) : 0];
+    const int tl = blockIdx.x & 63, n0 = (tl >> 3) * 32, k0 = (tl & 7) * 32;
+    const int rn = t >> 3, kq = t & 7;
+    const int64_t o = W.src.off + (int64_t)(n0 + rn) * H + k0 + kq * 4;
+    const int64_t to = W.tgt.off + (int64_t)(n0 + rn) * H + k0 + kq * 4;
+    float4 p4 = make_float4(0.f, 0.f, 0.f, 0.f), m4 = p4, v4 = p4, tp4 = p4, g4 = p4;
+    if (is_tile) {
+        p4 = *reinterpret_cast<const float4*>(A.arena + o);
+        m4 = *reinterpret_cast<const float4*>(A.arena + A.m_off + o);
+        v4 = *reinterpret_cast<const float4*>(A.arena + A.v_off + o);
+        if (W.has_tgt && A.tgt_count > 0) tp4 = *reinterpret_cast<const float4*>(A.arena + to);
+        if (A.n_peer == 0) g4 = *reinterpret_cast<const float4*>(A.arena + A.grad_off + o);
+    }
     if (t == 0) {  // bias corrections and step size in double (python floats in torch), once per block
         const double tstep = (double)(A.counters[A.t_counter] + 1);
         s_bc[0] = (float)(A.lr64 / (1.0 - pow((double)A.b1, tstep)));
@@ -690,8 +721,13 @@ __global__ void __launch_bounds__(kThreads) adam_tile_kernel(const __grid_consta
         // waits until all peers' generation g has arrived in the local pad before it loads their gradients.  The last CTA
         // stores g (below).  A CTA waits only on OTHER ranks' CTA 0, never on a CTA of its own grid.
         const unsigned g = (unsigned)(*reinterpret_cast<volatile int64_t*>(A.epoch) + 1);
+        __shared__ unsigned long long s_wait;
+        if (t == 0) s_wait = 0ull;
+        __syncthreads();
         if (blockIdx.x == 0 && t < A.n_peer) {
-            __threadfence_system();
+            // the gradients were written by EARLIER kernels of the stream: the grid boundary orders them before this thread, and
+            // the release store is cumulative over that order -- no separate fence.sys (it cost 2 us per barrier: 0.3608 ->
+            // 0.3538 ms per step on 2 GPUs, profiles/r2/sync_modes.txt)
             asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(A.signal[t] + kPadBase + A.rank), "r"(g) : "memory");
         }
         if (t < A.n_peer) {
@@ -705,17 +741,18 @@ __global__ void __launch_bounds__(kThreads) adam_tile_kernel(const __grid_consta
                 asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
             } while (!lost && (int)(v - g) < 0 && t1 - t0 < 60000000000ull);   // give up after 60 s instead of hanging the GPU
             if ((int)(v - g) < 0) A.counters[RRL_C_ERROR] = 2;
+            if (blockIdx.x == 0) atomicMax(&s_wait, t1 - t0);
         }
         __syncthreads();
+        if (blockIdx.x == 0 && t == 0) {   // diagnostic: how long this rank waited for its slowest peer (skew + signal latency)
+            A.counters[RRL_C_BARRIER_WAIT_NS] += (int64_t)s_wait;
+            A.counters[RRL_C_BARRIERS] += 1;
+        }
     }
-    const int n_tile_ctas = A.n_w2 * 64;
-    if ((int)blockIdx.x < n_tile_ctas) {
-        const AdamW2& W = A.w2[blockIdx.x >> 6];
-        const int tl = blockIdx.x & 63, n0 = (tl >> 3) * 32, k0 = (tl & 7) * 32;
-        const int rn = t >> 3, kq = t & 7;
-        const int64_t o = W.src.off + (int64_t)(n0 + rn) * H + k0 + kq * 4;
-        float4 p4 = *reinterpret_cast<const float4*>(A.arena + o);
-        float4 g4;
+    const bool dbg = blockIdx.x == 0 && t == 0;
+    unsigned long long d1 = 0, d2 = 0;
+    if (dbg) d1 = gtime();
+    if (is_tile) {
         if (A.n_peer > 0) {
             float4 gs[8];   // all NVLink peer loads in flight together, then summed in rank order
 #pragma unroll
@@ -724,15 +761,9 @@ __global__ void __launch_bounds__(kThreads) adam_tile_kernel(const __grid_consta
             g4 = gs[0];
 #pragma unroll
             for (int r = 1; r < 8; ++r) { g4.x += gs[r].x; g4.y += gs[r].y; g4.z += gs[r].z; g4.w += gs[r].w; }
-        } else {
-            g4 = *reinterpret_cast<const float4*>(A.arena + A.grad_off + o);
         }
-        float4 m4 = *reinterpret_cast<const float4*>(A.arena + A.m_off + o);
-        float4 v4 = *reinterpret_cast<const float4*>(A.arena + A.v_off + o);
-        float4 tp4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (dbg) { d2 = gtime(); if (g4.x == 1.2345678e33f) d2 += 1; }   // (the compare pins the stamp behind the loads)
         const bool do_tgt = polyak && W.has_tgt;
-        const int64_t to = W.tgt.off + (int64_t)(n0 + rn) * H + k0 + kq * 4;
-        if (do_tgt) tp4 = *reinterpret_cast<const float4*>(A.arena + to);
         adam_elem(p4.x, g4.x * A.grad_scale, m4.x, v4.x, A.b1, A.b2, A.eps, step_size, bc2s);
         adam_elem(p4.y, g4.y * A.grad_scale, m4.y, v4.y, A.b1, A.b2, A.eps, step_size, bc2s);
         adam_elem(p4.z, g4.z * A.grad_scale, m4.z, v4.z, A.b1, A.b2, A.eps, step_size, bc2s);
@@ -781,6 +812,11 @@ __global__ void __launch_bounds__(kThreads) adam_tile_kernel(const __grid_consta
     }
     // every CTA has read the counters above; the last one to arrive bumps them
     __syncthreads();
+    if (dbg) {
+        const unsigned long long d3 = gtime();
+        const unsigned long long t0 = *reinterpret_cast<volatile unsigned long long*>(&g_opt_t0);
+        g_opt_dbg[0] += d1 - t0; g_opt_dbg[1] += d2 - d1; g_opt_dbg[2] += d3 - d2; g_opt_dbg[3] += 1;
+    }
     if (t == 0 && A.n_bump > 0) {
         __threadfence();
         const unsigned long long ticket = atomicAdd(reinterpret_cast<unsigned long long*>(A.counters + RRL_C_TICKET), 1ull);
@@ -788,6 +824,10 @@ __global__ void __launch_bounds__(kThreads) adam_tile_kernel(const __grid_consta
             A.counters[RRL_C_TICKET] = 0;
             for (int i = 0; i < A.n_bump; ++i) A.counters[A.bump[i]] += 1;
             if (A.epoch) *A.epoch += 1;       // every CTA has read the old generation (its ticket came after its wait)
+            unsigned long long t1;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            const unsigned long long t0 = *reinterpret_cast<volatile unsigned long long*>(&g_opt_t0);
+            if (t1 > t0) A.counters[RRL_C_OPT_STEP_NS] += (int64_t)(t1 - t0);
         }
     }
 }
@@ -863,8 +903,8 @@ __global__ void peer_barrier_kernel(const PeerBarrierArgs A) {
     if (A.exchange && A.counters[RRL_C_GATE_SATISFIED]) return;
     __shared__ unsigned s_epoch;
     if (threadIdx.x == 0) {
-        s_epoch = (unsigned)(++(*A.epoch));
-        __threadfence_system();          // this rank's gradient writes (earlier kernels of the stream) before the flag
+        s_epoch = (unsigned)(++(*A.epoch));   // (this rank's gradient writes come from earlier kernels of the stream: ordered
+                                              //  before the release stores below by the grid boundary, no separate fence.sys)
     }
     __syncthreads();
     const unsigned epoch = s_epoch;
@@ -1861,5 +1901,15 @@ static int peer_barrier_impl(const rrl_peers_t* peers, int64_t* epoch, int64_t* 
     A.gate_batch = gate_batch; A.gate_pos_fraction = gate_pos_fraction;
     peer_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(A);
     RRL_CHECK_LAUNCH();
+    return 0;
+}
+
+// diagnostic: CTA 0's time line inside the tiled optimizer-step kernels since the last call (ns, summed): out[0] start -> barrier
+// done, out[1] -> gradients loaded, out[2] -> CTA 0 done, out[3] launches.  Resets the sums.
+extern "C" int rrl_debug_opt_times(unsigned long long* out4) {
+    if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+    if (cudaMemcpyFromSymbol(out4, g_opt_dbg, sizeof(unsigned long long) * 4) != cudaSuccess) return -1;
+    unsigned long long z[4] = {0, 0, 0, 0};
+    if (cudaMemcpyToSymbol(g_opt_dbg, z, sizeof(z)) != cudaSuccess) return -1;
     return 0;
 }
