@@ -317,6 +317,8 @@ def grad_mode(eng, world):
     if world == 1:
         return "none (1 GPU)"
     if eng.peer_arena is not None:
+        if getattr(eng.peer_arena, "multicast", False) and eng.fused_barrier:
+            return "in-switch sum inside the optimizer-step kernel (multimem.ld_reduce on the symmetric arena, flag barriers)"
         return "peer-memory sum inside the optimizer-step kernel (NVLink loads, flag barriers)"
     return "nccl, flat grad block" + (" (peer mode unavailable: %s)" % eng.peer_error if eng.peer_error else "")
 

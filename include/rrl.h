@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define RRL_VERSION 5
+#define RRL_VERSION 6
 
 const char* rrl_last_error(void);
 int rrl_version(void);
@@ -349,6 +349,10 @@ typedef struct {
                             rrl_*_apply_p2p kernels (tcgen05 path) run the flag barrier THEMSELVES before they load the peers'
                             gradients -- CTA 0 publishes this rank's generation, every CTA waits on the local pad -- and the
                             caller launches no rrl_peer_barrier in front of them */
+    uint64_t mc_arena;   /* multicast (NVLS) address of the symmetric arena, or 0.  Non-zero: the optimizer-step kernels read the SUM of
+                            all ranks' gradients with multimem.ld_reduce (reduced inside the NVSwitch: 1 x instead of world x gradient
+                            bytes per rank) instead of loading every peer's block.  The summation order is the switch's, identical on
+                            every rank; like NCCL's it differs from the rank-order sum of the peer loads by rounding above 2 ranks */
 } rrl_peers_t;
 int rrl_peer_barrier(const rrl_peers_t* peers, int64_t* epoch, int64_t* counters, void* stream);
 /* the same barrier, also exchanging the Q_risk gate counts (experiment.py:407-410 must open on every rank in the same

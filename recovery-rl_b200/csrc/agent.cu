@@ -613,7 +613,19 @@ struct AdamTileArgs {
     uint32_t* signal[8];
     int rank;
     int64_t* epoch;
+    const float* mc;   // multicast (NVLS) address of the arena or NULL: gradient sum by multimem.ld_reduce instead of n_peer loads
 };
+__device__ __forceinline__ float4 multimem_sum4(const float* mc_addr) {
+    float4 v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(mc_addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ float multimem_sum1(const float* mc_addr) {
+    float v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.f32 %0, [%1];" : "=f"(v) : "l"(mc_addr) : "memory");
+    return v;
+}
 __device__ __forceinline__ void adam_elem(float& p, float g, float& m, float& v, float b1, float b2, float eps, float step_size,
                                           float bc2s) {
     m = m + (g - m) * (1.0f - b1);               // exp_avg.lerp_(grad, 1 - beta1)
@@ -753,7 +765,9 @@ __global__ void __launch_bounds__(kThreads) adam_tile_kernel(const __grid_consta
     unsigned long long d1 = 0, d2 = 0;
     if (dbg) d1 = gtime();
     if (is_tile) {
-        if (A.n_peer > 0) {
+        if (A.mc) {
+            g4 = multimem_sum4(A.mc + A.grad_off + o);   // reduced inside the NVSwitch
+        } else if (A.n_peer > 0) {
             float4 gs[8];   // all NVLink peer loads in flight together, then summed in rank order
 #pragma unroll
             for (int r = 0; r < 8; ++r)
@@ -789,7 +803,9 @@ __global__ void __launch_bounds__(kThreads) adam_tile_kernel(const __grid_consta
             const int64_t o = A.seg_off[sg] + i;
             float p = A.arena[o];
             float g;
-            if (A.n_peer > 0) {
+            if (A.mc) {
+                g = multimem_sum1(A.mc + A.grad_off + o);
+            } else if (A.n_peer > 0) {
                 float gs[8];
 #pragma unroll
                 for (int r = 0; r < 8; ++r) gs[r] = r < A.n_peer ? __ldcv(A.peer[r] + A.grad_off + o) : 0.f;
@@ -1099,6 +1115,7 @@ int launch_adam_tiled(const rrl_agent_config_t* cfg, const Layout& L, float* are
         }
         A.rank = peers->rank;
         A.epoch = reinterpret_cast<int64_t*>(peers->epoch);
+        A.mc = (peers->epoch && peers->mc_arena) ? reinterpret_cast<const float*>(peers->mc_arena) : nullptr;
     }
     A.arena = arena;
     A.grad_off = L.grad_off; A.m_off = L.m_off; A.v_off = L.v_off;

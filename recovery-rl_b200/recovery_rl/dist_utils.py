@@ -70,8 +70,20 @@ class PeerArena(object):
         # `peers`: barriers are separate launches (rrl_peer_barrier);  `peers_fused`: the optimizer-step kernel runs the
         # barrier itself (rrl_peers_t::epoch) -- same pads, same generation counter
         self.peers = native.make_peers(self.rank, list(h.buffer_ptrs), list(h.signal_pad_ptrs))
+        # multicast (NVLS) mapping of the arena, when the fabric has one: with RRL_MULTIMEM=1 the optimizer-step kernels read the
+        # gradient SUM with multimem.ld_reduce instead of world peer loads.  Off by default: measured no faster (2 GPUs 0.3570 vs
+        # 0.3555 ms, 4 GPUs 0.3787 vs 0.3782 ms per step, profiles/r2/sync_modes.txt) -- every requester's reduction still pulls
+        # every source GPU's block through that GPU's links -- and the peer loads keep the rank-order (reproducible) sum
+        import os
+        mc = 0
+        try:
+            if os.environ.get("RRL_MULTIMEM", "0") == "1":
+                mc = int(getattr(h, "multicast_ptr", 0) or 0)
+        except Exception:
+            mc = 0
+        self.multicast = mc != 0
         self.peers_fused = native.make_peers(self.rank, list(h.buffer_ptrs), list(h.signal_pad_ptrs),
-                                             epoch_ptr=self.epoch.data_ptr())
+                                             epoch_ptr=self.epoch.data_ptr(), mc_ptr=mc)
         assert int(h.buffer_ptrs[self.rank]) == t.data_ptr()
         self.tensor = t
         return t

@@ -341,16 +341,18 @@ def recovery_backward_rest(cfg, arena, counters, losses, stream=None):
 class Peers(C.Structure):
     """rrl_peers_t: the ranks' arenas and signal pads as mapped in this process (symmetric memory)."""
     _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("arena", C.c_uint64 * 8), ("signal", C.c_uint64 * 8),
-                ("epoch", C.c_uint64)]
+                ("epoch", C.c_uint64), ("mc_arena", C.c_uint64)]
 
 
-def make_peers(rank, arena_ptrs, signal_ptrs, epoch_ptr=0):
-    """epoch_ptr != 0: the optimizer-step kernels run the flag barrier themselves (rrl.h, rrl_peers_t::epoch)."""
+def make_peers(rank, arena_ptrs, signal_ptrs, epoch_ptr=0, mc_ptr=0):
+    """epoch_ptr != 0: the optimizer-step kernels run the flag barrier themselves (rrl.h, rrl_peers_t::epoch);
+    mc_ptr != 0: and read the gradient sum through the multicast mapping (multimem.ld_reduce, rrl_peers_t::mc_arena)."""
     if not (1 <= len(arena_ptrs) <= 8 and len(arena_ptrs) == len(signal_ptrs)):
         raise RRLError("peer mode supports 1..8 ranks of one node")
     P = Peers()
     P.world, P.rank = len(arena_ptrs), int(rank)
     P.epoch = int(epoch_ptr)
+    P.mc_arena = int(mc_ptr)
     for r, (a, s) in enumerate(zip(arena_ptrs, signal_ptrs)):
         P.arena[r], P.signal[r] = int(a), int(s)
     return P

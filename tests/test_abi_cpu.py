@@ -19,7 +19,7 @@ def test_every_declared_symbol_is_exported(native):
     lib = ctypes.CDLL(native.LIB_PATH)
     missing = [n for n in names if not hasattr(lib, n)]
     assert not missing, missing
-    assert native.version() == 5
+    assert native.version() == 6
 
 
 def test_arena_layout_matches_reference_parameter_shapes(native):
@@ -82,7 +82,7 @@ def test_peer_table_packing_and_argument_checks(native):
     P = native.make_peers(1, [0x1000, 0x2000, 0x3000], [0x10, 0x20, 0x30])
     assert (P.world, P.rank) == (3, 1)
     assert list(P.arena)[:4] == [0x1000, 0x2000, 0x3000, 0] and list(P.signal)[:4] == [0x10, 0x20, 0x30, 0]
-    assert ctypes.sizeof(P) == 8 + 8 * 8 + 8 * 8 + 8                 # int32 world, rank; uint64 arena[8], signal[8], epoch
+    assert ctypes.sizeof(P) == 8 + 8 * 8 + 8 * 8 + 8 + 8             # int32 world, rank; uint64 arena[8], signal[8], epoch, mc_arena
     assert native.make_peers(0, [1, 2], [3, 4], epoch_ptr=0x40).epoch == 0x40 and P.epoch == 0
     with pytest.raises(native.RRLError):
         native.make_peers(0, list(range(9)), list(range(9)))           # one node: at most 8 ranks
