@@ -1,0 +1,12 @@
+set -x
+O=gpurun_out/r2f3; mkdir -p $O
+python -m pytest tests -m gpu -q > $O/pytest_full.log 2>&1; echo "pytest rc=$?" >> $O/pytest_full.log; tail -4 $O/pytest_full.log
+python __graft_entry__.py --smoke > $O/smoke.log 2>&1; echo "smoke rc=$?"; tail -2 $O/smoke.log
+timeout 900 python bench.py > $O/bench_default.json 2> $O/bench_default.err; echo "bench rc=$?"
+timeout 600 python bench.py --impl reference --steps 5 --warmup 2 > $O/bench_reference.json 2> $O/bench_reference.err; echo "ref rc=$?"
+python - <<'PY'
+import json
+d=json.loads(open("gpurun_out/r2f3/bench_default.json").read().strip().splitlines()[-1])
+print("value %.1fM ms %.4f e2e %.1fM roofline %.4f cpu %s clocks %s launches %s" % (d["value"]/1e6, d["ms_per_step"], d["e2e"]["value"]/1e6, d["roofline"]["frac"], d["cpu_baseline"]["value"], d["clocks"], d["gpu_launches"]))
+r=json.loads(open("gpurun_out/r2f3/bench_reference.json").read().strip().splitlines()[-1]); print("reference", r["value"], r["cpu_baseline"])
+PY
