@@ -477,30 +477,25 @@ def run_ours(args, rank, world, local_rank):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    bw0 = eng.counters[native.C_BARRIER_WAIT_NS:native.C_BARRIERS + 1].clone()
-    opt0 = int(eng.counters[native.C_OPT_STEP_NS])
-    if hasattr(native.lib(), "rrl_debug_opt_times"):
-        import ctypes as _ct
-        native.lib().rrl_debug_opt_times((_ct.c_uint64 * 4)())          # reset the diagnostic sums
+    native.debug_opt_times()                    # reset the optimizer-step diagnostics (include/rrl.h, rrl_debug_opt_times)
     times = timed_steps(eng, K, flush, barrier)
     clocks = sampler.stop() if rank == 0 else None
     total_ms = max_over_ranks(sum(times), dev, world)
-    opt_step_us = (int(eng.counters[native.C_OPT_STEP_NS]) - opt0) * 1e-3 / K     # inside the optimizer-step kernels, per step
-    import ctypes
-    dbg4 = (ctypes.c_uint64 * 4)()
+    od = native.debug_opt_times()               # device globaltimer sums over the timed region (tcgen05 path; zeros otherwise)
+    opt_step_us = od["kernels_us"] / K          # inside the optimizer-step kernels, per step
     opt_dbg = None
-    if hasattr(native.lib(), "rrl_debug_opt_times") and native.lib().rrl_debug_opt_times(dbg4) == 0 and dbg4[3]:
-        opt_dbg = {"launches": int(dbg4[3]), "barrier_us_per_launch": dbg4[0] * 1e-3 / dbg4[3],
-                   "grad_loads_us_per_launch": dbg4[1] * 1e-3 / dbg4[3], "rest_us_per_launch": dbg4[2] * 1e-3 / dbg4[3]}
+    if od["launches"]:
+        n = od["launches"]
+        opt_dbg = {"launches": n, "barrier_us_per_launch": od["cta0_barrier_us"] / n,
+                   "grad_loads_us_per_launch": od["cta0_grad_loads_us"] / n, "rest_us_per_launch": od["cta0_rest_us"] / n}
     barrier_wait = None
     if world > 1:
-        # how long each rank's optimizer-step kernels waited for the slowest peer's gradient flag inside the timed region
-        # (device-side globaltimer, include/rrl.h RRL_C_BARRIER_WAIT_NS): rank skew + signal latency, the rest of the
-        # multi-GPU overhead is the peer loads
-        bw = (eng.counters[native.C_BARRIER_WAIT_NS:native.C_BARRIERS + 1] - bw0).double()
+        # how long each rank's optimizer-step kernels waited for the slowest peer's gradient flag inside the timed region: rank
+        # skew + signal latency; the rest of the multi-GPU overhead is the peer loads (optimizer_step_cta0)
+        bw = torch.tensor([od["flag_wait_us"], float(od["barriers"])], dtype=torch.float64, device=dev)
         allbw = [torch.empty_like(bw) for _ in range(world)]
         dist.all_gather(allbw, bw)
-        per_rank = [float(b[0]) * 1e-3 / K for b in allbw]
+        per_rank = [float(b[0]) / K for b in allbw]
         barrier_wait = {"us_per_step_by_rank": [round(x, 2) for x in per_rank], "us_per_step_mean": sum(per_rank) / world,
                         "barriers_per_step": float(allbw[0][1]) / K,
                         "note": "time CTA 0 of the optimizer-step kernels spent waiting for the peers' gradient flags (device globaltimer)"}

@@ -38,6 +38,13 @@ int rrl_version(void);
  * rrl_set_pdl(1) turns it on.  Returns the previous setting
  * (enabled < 0: query only). */
 int rrl_set_pdl(int enabled);
+/* Diagnostics of the tiled optimizer-step kernels (tcgen05 path) since the previous call, summed over launches, device
+ * globaltimer nanoseconds; kept OUTSIDE the counter block (which stays deterministic).  Synchronises the device, resets the sums.
+ *   out[0] CTA 0: kernel start -> bias corrections / cross-GPU barrier done   out[1] -> gradients (own + peers') loaded
+ *   out[2] -> CTA 0 done          out[3] launches
+ *   out[4] time CTA 0 waited for the slowest peer's gradient flag (fused barrier: rank skew + signal latency)   out[5] barriers
+ *   out[6] CTA 0 start -> last CTA end (the whole kernel)                     out[7] reserved */
+int rrl_debug_opt_times(unsigned long long* out8);
 
 /* ------------------------------------------------------------------ environments ------- */
 enum { RRL_ENV_NAV1 = 0, RRL_ENV_NAV2 = 1, RRL_ENV_MAZE = 2 };
@@ -71,10 +78,6 @@ enum {
     RRL_C_TICKET2        = 27, /* scratch: CTA arrival ticket of the update kernels whose last CTA runs the loss / sample-backward stage */
     RRL_C_GATE_SATISFIED = 28, /* multi-GPU: the violation count of the Q_risk online gate (experiment.py:410) has passed its threshold on
                                   every rank (monotone: counts only grow) -> rrl_peer_sync_gate_counts stops exchanging */
-    RRL_C_BARRIER_WAIT_NS= 29, /* multi-GPU diagnostic: nanoseconds CTA 0 of the optimizer-step kernels has spent waiting for the slowest
-                                  peer's gradient flag (rank skew + signal latency), summed over barriers (fused-barrier path) */
-    RRL_C_BARRIERS       = 30, /*   ... and the number of such barriers                                                         */
-    RRL_C_OPT_STEP_NS    = 31, /* diagnostic: nanoseconds inside the tiled optimizer-step kernels (CTA 0 start -> last CTA end), summed */
     RRL_NUM_COUNTERS     = 32
 };
 

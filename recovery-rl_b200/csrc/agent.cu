@@ -679,10 +679,11 @@ __device__ __forceinline__ void write_tile_images(float* arena, const ImgRef& R,
         *reinterpret_cast<uint4*>(img + base + kLo) = lo;
     }
 }
-__device__ unsigned long long g_opt_t0;   // diagnostic (RRL_C_OPT_STEP_NS): start stamp of the running optimizer-step kernel
-// diagnostic: CTA 0's time line inside the optimizer-step kernels, summed over launches (ns): [0] start -> barrier done,
-// [1] -> gradients (own + peers') loaded, [2] -> CTA 0 done, [3] launches  (rrl_debug_opt_times)
-__device__ unsigned long long g_opt_dbg[4];
+__device__ unsigned long long g_opt_t0;   // diagnostic: start stamp (CTA 0) of the running optimizer-step kernel
+// diagnostics of the optimizer-step kernels (rrl_debug_opt_times, include/rrl.h), summed over launches (ns): [0] CTA 0 start ->
+// barrier done, [1] -> gradients (own + peers') loaded, [2] -> CTA 0 done, [3] launches, [4] CTA 0's wait for the slowest peer's
+// flag, [5] barriers, [6] CTA 0 start -> last CTA end.  Deliberately NOT in the counter block: that one stays deterministic
+__device__ unsigned long long g_opt_dbg[8];
 __device__ __forceinline__ unsigned long long gtime() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)::"memory");
@@ -757,8 +758,8 @@ __global__ void __launch_bounds__(kThreads) adam_tile_kernel(const __grid_consta
         }
         __syncthreads();
         if (blockIdx.x == 0 && t == 0) {   // diagnostic: how long this rank waited for its slowest peer (skew + signal latency)
-            A.counters[RRL_C_BARRIER_WAIT_NS] += (int64_t)s_wait;
-            A.counters[RRL_C_BARRIERS] += 1;
+            g_opt_dbg[4] += s_wait;
+            g_opt_dbg[5] += 1;
         }
     }
     const bool dbg = blockIdx.x == 0 && t == 0;
@@ -843,7 +844,7 @@ __global__ void __launch_bounds__(kThreads) adam_tile_kernel(const __grid_consta
             unsigned long long t1;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
             const unsigned long long t0 = *reinterpret_cast<volatile unsigned long long*>(&g_opt_t0);
-            if (t1 > t0) A.counters[RRL_C_OPT_STEP_NS] += (int64_t)(t1 - t0);
+            if (t1 > t0) g_opt_dbg[6] += t1 - t0;
         }
     }
 }
@@ -1921,12 +1922,10 @@ static int peer_barrier_impl(const rrl_peers_t* peers, int64_t* epoch, int64_t* 
     return 0;
 }
 
-// diagnostic: CTA 0's time line inside the tiled optimizer-step kernels since the last call (ns, summed): out[0] start -> barrier
-// done, out[1] -> gradients loaded, out[2] -> CTA 0 done, out[3] launches.  Resets the sums.
-extern "C" int rrl_debug_opt_times(unsigned long long* out4) {
+extern "C" int rrl_debug_opt_times(unsigned long long* out8) {
     if (cudaDeviceSynchronize() != cudaSuccess) return -1;
-    if (cudaMemcpyFromSymbol(out4, g_opt_dbg, sizeof(unsigned long long) * 4) != cudaSuccess) return -1;
-    unsigned long long z[4] = {0, 0, 0, 0};
+    if (cudaMemcpyFromSymbol(out8, g_opt_dbg, sizeof(unsigned long long) * 8) != cudaSuccess) return -1;
+    unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (cudaMemcpyToSymbol(g_opt_dbg, z, sizeof(z)) != cudaSuccess) return -1;
     return 0;
 }

@@ -22,7 +22,6 @@ C_OFFLINE_VIOLS, C_VEC_STEP, C_SAC_UPDATES, C_QRISK_UPDATES = 6, 7, 8, 9
 C_TASK_POS, C_TASK_LEN, C_CONS_POS, C_CONS_LEN, C_SAC_ROWS, C_QRISK_ROWS, C_ADAM_T0 = 10, 11, 12, 13, 14, 15, 16
 C_EXT_VIOLS, C_RETURN_SUM_BITS, C_ERROR, NUM_COUNTERS = 20, 21, 22, 32
 C_ADAM_T_ALPHA, C_ADAM_T_NU, C_ADAM_T_LAMBDA = 23, 24, 25
-C_BARRIER_WAIT_NS, C_BARRIERS, C_OPT_STEP_NS = 29, 30, 31        # multi-GPU diagnostic (fused gradient barrier)
 # comparison-algorithm branches (rrl_agent_config_t.algo_flags) and the scalar block ("scalars" scratch region)
 ALGO_DGD, ALGO_UPDATE_NU, ALGO_RCPO, ALGO_AUTO_ALPHA, ALGO_DETERMINISTIC = 1, 2, 4, 8, 16
 S_ALPHA, S_NU_ARG, S_LOG_ALPHA, S_G_LOG_ALPHA, S_M_ALPHA, S_V_ALPHA, S_ALPHA_LOSS, S_F64_BASE = 0, 1, 2, 3, 4, 5, 6, 8
@@ -115,6 +114,14 @@ def version():
 def set_pdl(enabled):
     """programmatic dependent launch of the step's kernels (include/rrl.h); returns the previous setting"""
     return bool(lib().rrl_set_pdl(int(bool(enabled))))
+
+
+def debug_opt_times():
+    """diagnostics of the optimizer-step kernels since the previous call (include/rrl.h): dict of microseconds / counts"""
+    out = (C.c_uint64 * 8)()
+    _check(lib().rrl_debug_opt_times(out), "rrl_debug_opt_times")
+    return dict(cta0_barrier_us=out[0] * 1e-3, cta0_grad_loads_us=out[1] * 1e-3, cta0_rest_us=out[2] * 1e-3, launches=int(out[3]),
+                flag_wait_us=out[4] * 1e-3, barriers=int(out[5]), kernels_us=out[6] * 1e-3)
 
 
 def pdl_enabled():
