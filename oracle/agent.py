@@ -295,6 +295,17 @@ class Agent(object):
             j = torch.distributions.Categorical(probs).sample() if categorical is None else int(categorical(probs))
             return pi[j].numpy()
 
+    # ---- qrisk.py:214-225: Q-sampling recovery -----------------------------------------------------
+    def select_action_qsample(self, state, candidates):
+        """candidates: [samples, 2] float32 draws of `ac_space.sample()` (1000 in the reference, gym Box: uniform in
+        [low, high]); returns the one with the smallest max(Q1, Q2)_risk(state, .)  (qrisk.py:196, 222-224).
+        PINNED against tests/golden/qsample_nav1.npz (the reference's own QRiskWrapper.select_action)."""
+        cand = torch.as_tensor(np.asarray(candidates), dtype=torch.float32)
+        with torch.no_grad():
+            sb = torch.as_tensor(np.asarray(state), dtype=torch.float32).unsqueeze(0).repeat(len(cand), 1)
+            qmax = torch.max(*self.qrisk(sb, cand))
+            return cand[torch.argmin(qmax)].numpy()
+
     # ---- qrisk.py:86-182 ---------------------------------------------------------------------------
     def qrisk_update(self, batch, eps_next, eps_rec):
         s, a, c, s2, m = [torch.as_tensor(np.asarray(x), dtype=torch.float32) for x in batch]

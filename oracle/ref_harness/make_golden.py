@@ -571,6 +571,60 @@ def golden_algos(B=64, n_qr=12, n_updates=3, seed=23):
     _save("agent_algos_b%d.npz" % B, **out)
 
 
+# ---------------------------------------------------------------------------------------
+# F. Q-sampling recovery (reference recovery_rl/qrisk.py:214-225): 1000 uniform candidate actions from the action
+#    space, the one with the smallest max(Q1, Q2)_risk.  The networks are the xavier-initialised ones of
+#    agent_nav1_b256.npz (same seed, same construction order: checked through the init sha256), so only the
+#    candidates and the chosen actions are stored.
+# ---------------------------------------------------------------------------------------
+def golden_qsample(seed=11, n_states=8):
+    harness.setup()
+    from gym.spaces import Box
+    from recovery_rl.sac import SAC
+    args = harness.get_args(["--use_recovery", "--Q_sampling_recovery", "--gamma_safe", "0.8", "--eps_safe", "0.3",
+                             "--env-name", "navigation1", "--seed", str(seed), "--batch_size", "256"])
+    torch.manual_seed(seed)
+    np.random.seed(seed)
+    obs_space = Box(-np.ones(2) * float("inf"), np.ones(2) * float("inf"))
+    act_space = Box(-np.ones(2) * 1.0, np.ones(2) * 1.0)
+    agent = SAC(obs_space, act_space, args, "/tmp/none", tmp_env=_DummyEnv())
+    qr = agent.safety_critic
+    sha = hashlib.sha256()
+    for mod in (agent.critic, agent.policy, qr.safety_critic, qr.policy):
+        for p in mod.parameters():
+            sha.update(p.detach().numpy().tobytes())
+    ref = np.load(os.path.join(OUT, "agent_nav1_b256.npz"))
+    assert sha.hexdigest() == str(ref["init_sha256"]), "construction order changed: the stored init weights are not these"
+    rng = np.random.RandomState(4321)
+    st = np.stack([rng.uniform(-75, 10, n_states), rng.uniform(-9, 9, n_states)], 1)
+    qr.ac_space.seed(2026)
+    recorded = []
+    inner = qr.ac_space.sample
+
+    def recording_sample():
+        a = inner()
+        recorded.append(a.copy())
+        return a
+    qr.ac_space.sample = recording_sample
+    acts = np.zeros((n_states, 2), np.float32)
+    for i in range(n_states):
+        acts[i] = qr.select_action(st[i])
+    cands = np.asarray(recorded, np.float32).reshape(n_states, 1000, 2)
+    # the chosen action is one of the candidates; store its index and the margin to the runner-up for the tests' tie guard
+    with torch.no_grad():
+        idx = np.zeros(n_states, np.int64)
+        gap = np.zeros(n_states)
+        for i in range(n_states):
+            sb = torch.FloatTensor(st[i]).unsqueeze(0).repeat(1000, 1)
+            q = qr.get_value(sb, torch.FloatTensor(cands[i])).numpy().ravel()
+            idx[i] = int(np.argmin(q))
+            srt = np.sort(q)
+            gap[i] = srt[1] - srt[0]
+            assert np.array_equal(cands[i, idx[i]], acts[i])
+    _save("qsample_nav1.npz", seed=np.int64(seed), states=st, candidates=cands, actions=acts, index=idx, gap=gap,
+          init_sha256=np.array(sha.hexdigest()))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     harness.setup()
@@ -597,6 +651,7 @@ def main():
     golden_trajectory("navigation1", 5, "0.8", "0.45", 6, "traj_nav1_sqrl.npz", stride=29,
                       algo=("--DGD_constraints", "--use_constraint_sampling", "--nu", "5000", "--update_nu", "--start_steps", "20"))
     golden_algos()
+    golden_qsample()
 
 
 if __name__ == "__main__":

@@ -309,3 +309,22 @@ def test_oracle_mpc_matches_reference(golden_dir, tag):
         assert np.allclose(a, z[P + "act_actions"][i], rtol=1e-5, atol=1e-7)
         assert np.allclose(m.prev_sol, z[P + "act_prev_sol"][i], rtol=1e-5, atol=1e-7)
     assert np.allclose(np.array(m.iter_costs), z[P + "act_iter_costs"], rtol=1e-5, atol=1e-6)
+
+
+def test_oracle_q_sampling_recovery_matches_reference(golden_dir):
+    """qrisk.py:214-225 through the reference's own QRiskWrapper.select_action (oracle/ref_harness/make_golden.py,
+    golden_qsample): of the recorded 1000 uniform candidates, the restatement picks the same one for every state."""
+    import torch
+    from oracle.agent import Agent
+    z = np.load(os.path.join(golden_dir, "qsample_nav1.npz"))
+    init = np.load(os.path.join(golden_dir, "agent_nav1_b256.npz"))
+    assert str(z["init_sha256"]) == str(init["init_sha256"])            # the networks are that file's xavier init
+    torch.manual_seed(int(z["seed"]))
+    np.random.seed(int(z["seed"]))
+    ora = Agent(action_scale=(np.float32(1.0),) * 2, gamma_safe=0.8, eps_safe=0.3)
+    for i, p in enumerate(ora.params("qrisk")):
+        assert np.array_equal(p, init["init_qrisk_%d" % i]), i           # same construction order, same draws
+    for i in range(len(z["states"])):
+        a = ora.select_action_qsample(z["states"][i], z["candidates"][i])
+        assert np.array_equal(a, z["actions"][i]), i
+        assert np.array_equal(z["candidates"][i, int(z["index"][i])], z["actions"][i])

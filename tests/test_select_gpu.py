@@ -247,3 +247,58 @@ def test_philox_mode_runs_the_comparison_branches_in_a_graph(native, cuda):
     c = q.read_counters()
     assert c["error"] == 0 and c["task_len"] >= 6 * 1024 and torch.isfinite(q.action_real).all()
     assert (q.action_real.abs() <= 0.1 + 1e-6).all()
+
+
+def test_q_sampling_recovery_vs_reference_golden(native, cuda, golden_dir):
+    """tests/golden/qsample_nav1.npz holds the candidates the REFERENCE's QRiskWrapper.select_action drew (qrisk.py:214-225, gym
+    Box shim of the harness) and the actions it returned: the drop-in QRiskWrapper (N = 1 path) fed the same candidates returns
+    the same actions, and so does the vector kernel for 8 env copies at once."""
+    import argparse
+    from env.spaces import Box
+    from oracle.agent import Agent
+    from recovery_rl.sac import SAC
+    z = np.load(os.path.join(golden_dir, "qsample_nav1.npz"))
+    torch.manual_seed(int(z["seed"]))
+    np.random.seed(int(z["seed"]))
+    ora = Agent(action_scale=(np.float32(1.0),) * 2, gamma_safe=0.8, eps_safe=0.3)       # the golden's xavier init (test_oracle.py)
+    args = argparse.Namespace(gamma=0.99, tau=0.005, alpha=0.2, env_name="navigation1", policy="Gaussian", target_update_interval=1,
+                              automatic_entropy_tuning=False, gamma_safe=0.8, eps_safe=0.3, nu=0.01, batch_size=64,
+                              lr=3e-4, tau_safe=0.0002, MF_recovery=False, Q_sampling_recovery=True, hidden_size=256,
+                              DGD_constraints=False, update_nu=False, RCPO=False, use_constraint_sampling=False,
+                              lambda_RCPO=0.01, pos_fraction=-1, cnn=False, vismpc_recovery=False)
+    one = np.float32(1.0)
+    agent = SAC(Box(-np.ones(2) * np.inf, np.ones(2) * np.inf), Box(-np.ones(2) * one, np.ones(2) * one), args, "/tmp/none")
+    agent.arena.load_modules(ora.nets())
+    qr = agent.safety_critic
+    n = len(z["states"])
+    sure = z["gap"] > 1e-5                       # runner-up further away than the fp32 ordering noise of two implementations
+
+    class Replayed(object):
+        def __init__(self, cands):
+            self.c = list(cands)
+
+        def sample(self):
+            return self.c.pop(0)
+    # (a) the drop-in QRiskWrapper
+    for i in range(n):
+        qr.ac_space = Replayed(z["candidates"][i])
+        a = qr.select_action(z["states"][i])
+        if sure[i]:
+            assert np.array_equal(a, z["actions"][i]), i
+    # (b) the vector kernel: every env copy flagged, candidates handed over as the uniforms they were drawn from
+    ar = agent.arena
+    dev = ar.arena.device
+    state = torch.from_numpy(np.ascontiguousarray(z["states"].T)).to(dev)
+    cand_u = torch.from_numpy(((z["candidates"].astype(np.float64) + 1.0) * 0.5).astype(np.float32)).to(dev).contiguous()
+    a_real = torch.zeros(n, 2, device=dev)
+    flags = torch.ones(n, dtype=torch.uint8, device=dev)
+    ws = torch.empty(native.select_workspace_floats(3, 1000), device=dev)      # 3 env copies per chunk: 3 chunks
+    native.qsample_recovery_action(ar.cfg, ar.arena, n, 1000, state, ar.counters, ws, a_real, recovery=flags, cand_u=cand_u)
+    got = a_real.cpu().numpy()
+    assert sure.sum() >= 6
+    assert np.allclose(got[sure], z["actions"][sure], rtol=0, atol=2e-7), np.abs(got - z["actions"]).max(1)
+    flags[1::2] = 0                              # unflagged env copies keep their action
+    a_real.fill_(7.0)
+    native.qsample_recovery_action(ar.cfg, ar.arena, n, 1000, state, ar.counters, ws, a_real, recovery=flags, cand_u=cand_u)
+    got = a_real.cpu().numpy()
+    assert (got[1::2] == 7.0).all() and np.allclose(got[0::2][sure[0::2]], z["actions"][0::2][sure[0::2]], rtol=0, atol=2e-7)
