@@ -9,9 +9,10 @@
  *   - every function returns 0 on success, <0 on error; rrl_last_error() gives the message
  *     (thread-local).  Launch-only: functions ENQUEUE work on `stream` (a cudaStream_t passed
  *     as void*) and never synchronise, so every call is CUDA-graph capturable, except the
- *     explicitly named *_host helpers which touch host memory.
+ *     explicitly named *_host helpers which touch host memory and the rrl_debug_* diagnostics (they synchronise the device).
  *   - all arrays are caller-owned DEVICE pointers (e.g. torch tensors' data_ptr()); nothing
- *     is allocated here.  No global state; the device is whatever is current (cudaSetDevice).
+ *     is allocated here.  No global state besides the launch-mode switch (rrl_set_pdl) and the diagnostic sums of
+ *     rrl_debug_opt_times; the device is whatever is current (cudaSetDevice).
  *   - layouts: env state fp64 SoA [2][n] (plane 0 = x, plane 1 = y); actions fp32 [n][2];
  *     replay = ring of 32-byte records {s.x,s.y,a.x,a.y,r,s2.x,s2.y,mask} fp32 (one DRAM
  *     sector per transition) + one flag byte per slot for the constraint buffer.
