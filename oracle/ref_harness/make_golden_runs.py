@@ -24,6 +24,12 @@ RUNS = {   # tag -> (seed, the algorithm flags of the script line)
     "rp": (6, ["--constraint_reward_penalty", "1000"]),
     "rcpo": (7, ["--gamma_safe", "0.8", "--eps_safe", "0.3", "--RCPO", "--lambda", "1000"]),
 }
+# recovery branches that no script line uses (experiment.py:446-448, qrisk.py:214-225) -> tests/golden/runs_nav1_extra.npz;
+# eps_safe low enough that the barely trained safety critic triggers recoveries within 6 episodes
+EXTRA_RUNS = {
+    "addboth": (8, ["--use_recovery", "--MF_recovery", "--gamma_safe", "0.8", "--eps_safe", "0.05", "--add_both_transitions"]),
+    "qsample": (9, ["--use_recovery", "--Q_sampling_recovery", "--gamma_safe", "0.8", "--eps_safe", "0.05"]),
+}
 STRIDE = 37
 
 
@@ -51,7 +57,8 @@ def one_run(tag, seed, flags):
            P + "constraint": np.array([int(i["constraint"]) for i in infos], np.uint8),
            P + "recovery": np.array([bool(i.get("recovery", False)) for i in infos], np.uint8),
            P + "num_viols": np.int64(exp.num_viols), P + "num_successes": np.int64(exp.num_successes),
-           P + "total_numsteps": np.int64(exp.total_numsteps), P + "updates": np.int64(exp.updates)}
+           P + "total_numsteps": np.int64(exp.total_numsteps), P + "updates": np.int64(exp.updates),
+           P + "memory_len": np.int64(len(exp.memory)), P + "recovery_memory_len": np.int64(len(exp.recovery_memory))}
     nets = {"critic": exp.agent.critic, "policy": exp.agent.policy, "qrisk": exp.agent.safety_critic.safety_critic}
     for name, mod in nets.items():
         for k, p in enumerate(mod.parameters()):
@@ -65,6 +72,16 @@ def one_run(tag, seed, flags):
     return out
 
 
+def main_extra():
+    out = {"stride": np.int64(STRIDE), "tags": np.array(sorted(EXTRA_RUNS))}
+    for tag in sorted(EXTRA_RUNS):
+        seed, flags = EXTRA_RUNS[tag]
+        out.update(one_run(tag, seed, flags))
+    path = os.path.join(ROOT, "tests", "golden", "runs_nav1_extra.npz")
+    np.savez_compressed(path, **out)
+    print("wrote %s (%.1f KB)" % (path, os.path.getsize(path) / 1024.0))
+
+
 def main():
     out = {"stride": np.int64(STRIDE), "tags": np.array(sorted(RUNS))}
     for tag in sorted(RUNS):
@@ -76,4 +93,8 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if "--extra" in sys.argv:
+        main_extra()           # leaves runs_nav1.npz untouched
+    else:
+        main()
+        main_extra()

@@ -208,13 +208,15 @@ def test_vectorised_comparison_algorithms_run(native, cuda, tmp_path, algo):
     assert torch.isfinite(exp.engine.arena[:exp.engine.agent.grad_off]).all()
 
 
-@pytest.mark.parametrize("tag", ["unconstrained", "lr", "rspo", "sqrl", "rp", "rcpo"])
+@pytest.mark.parametrize("tag", ["unconstrained", "lr", "rspo", "sqrl", "rp", "rcpo", "addboth", "qsample"])
 def test_experiment_reproduces_reference_comparison_runs(native, cuda, golden_dir, tmp_path, tag):
     """the comparison-algorithm lines of scripts/navigation1.sh through the drop-in Experiment with LIVE RNGs == the
-    reference's own (shortened) runs recorded by oracle/ref_harness/make_golden_runs.py."""
+    reference's own (shortened) runs recorded by oracle/ref_harness/make_golden_runs.py; `addboth` / `qsample`: the two
+    recovery branches no script line uses (--add_both_transitions, experiment.py:446-448; --Q_sampling_recovery,
+    qrisk.py:214-225), recorded the same way into runs_nav1_extra.npz."""
     import arg_utils
     from recovery_rl.experiment import Experiment
-    z = np.load(os.path.join(golden_dir, "runs_nav1.npz"))
+    z = np.load(os.path.join(golden_dir, "runs_nav1_extra.npz" if tag in ("addboth", "qsample") else "runs_nav1.npz"))
     P = tag + "_"
     argv = [str(x) for x in z[P + "argv"]]
     argv[argv.index("--logdir") + 1] = str(tmp_path)
@@ -238,11 +240,19 @@ def test_experiment_reproduces_reference_comparison_runs(native, cuda, golden_di
         (np.abs(ac[:n] - z[P + "action"][:n]).max(1) > 1e-4)
     first = int(np.flatnonzero(bad)[0]) if bad.any() else n
     print("%s: within 1e-4 of the reference run for %d of %d steps" % (tag, first, len(z[P + "constraint"])))
-    assert first >= min(MIN_FREE_RUNNING_PREFIX, len(z[P + "constraint"])), (tag, first)
+    # Q-sampling picks the arg-min of 1,000 candidates every step: two candidates closer than the fp32 ordering noise of the two
+    # implementations (the golden of tests/test_select_gpu.py has gaps down to 3e-6) may swap and end the common prefix early
+    need = 5 if tag == "qsample" else min(MIN_FREE_RUNNING_PREFIX, len(z[P + "constraint"]))
+    assert first >= need, (tag, first)
     if first == len(z[P + "constraint"]) == len(con):
         assert ep_len == list(z[P + "ep_len"])
         assert exp.num_viols == int(z[P + "num_viols"]) and exp.total_numsteps == int(z[P + "total_numsteps"])
         assert exp.updates == int(z[P + "updates"])
+        if P + "memory_len" in z.files:       # add_both_transitions: two task-buffer pushes per recovery step
+            assert len(exp.memory) == int(z[P + "memory_len"]) and len(exp.recovery_memory) == int(z[P + "recovery_memory_len"])
+        if tag in ("addboth", "qsample"):
+            rec = np.array([bool(i.get("recovery", False)) for i in infos])
+            assert np.array_equal(rec, z[P + "recovery"].astype(bool)) and rec.any()
 
 
 def test_utils_soft_and_hard_update_delegates(native, cuda):
