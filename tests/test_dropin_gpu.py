@@ -192,18 +192,26 @@ def test_script_algorithm_lines_run(native, cuda, tmp_path, algo, env_name):
         assert torch.isfinite(rp.dyn_image).all()
 
 
-@pytest.mark.parametrize("algo", ["LR", "RSPO", "SQRL", "RCPO", "RP", "unconstrained"])
+# flags no script line uses, through the vector engine as well (device RNG + CUDA graph)
+EXTRA_LINES = {
+    "DET": ["--policy", "Deterministic", "--use_recovery", "--MF_recovery"],
+    "QSAMPLE": ["--use_recovery", "--Q_sampling_recovery"],
+    "ADDBOTH": ["--use_recovery", "--MF_recovery", "--add_both_transitions"],
+}
+
+
+@pytest.mark.parametrize("algo", ["LR", "RSPO", "SQRL", "RCPO", "RP", "unconstrained", "DET", "QSAMPLE", "ADDBOTH"])
 def test_vectorised_comparison_algorithms_run(native, cuda, tmp_path, algo):
     import arg_utils
     from recovery_rl.experiment import Experiment
-    argv = ["--env-name", "navigation1", "--gamma_safe", "0.8", "--eps_safe", "0.3"] + SCRIPT_LINES[algo] + \
+    argv = ["--env-name", "navigation1", "--gamma_safe", "0.8", "--eps_safe", "0.3"] + dict(SCRIPT_LINES, **EXTRA_LINES)[algo] + \
         ["--num_unsafe_transitions", "2000", "--critic_safe_pretraining_steps", "20", "--batch_size", "64",
          "--num_envs", "512", "--num_steps", "30000", "--seed", "3", "--logdir", str(tmp_path), "--replay_size", "60000",
          "--safe_replay_size", "60000"]
     exp = Experiment(arg_utils.get_args(argv))
     stats = exp.run()
     assert stats[-1]["total_numsteps"] > 30000 and stats[-1]["error"] == 0 and stats[-1]["sac_updates"] > 20
-    uses_qrisk = algo in ("LR", "RSPO", "SQRL", "RCPO")
+    uses_qrisk = algo in ("LR", "RSPO", "SQRL", "RCPO", "DET", "QSAMPLE", "ADDBOTH")
     assert (stats[-1]["qrisk_updates"] > 20) == uses_qrisk
     assert torch.isfinite(exp.engine.arena[:exp.engine.agent.grad_off]).all()
 
