@@ -124,3 +124,29 @@ def test_entry_points_reject_bad_arguments_before_launching(native):
     lib.rrl_agent_arena_floats.restype = C.c_int64
     assert lib.rrl_agent_arena_floats(C.byref(bad)) < 0 and b"max_batch" in lib.rrl_last_error()
     assert lib.rrl_agent_num_tensors(C.c_int(99)) < 0
+
+
+def test_header_is_plain_c_and_links_against_the_library(native, tmp_path):
+    """include/rrl.h compiles as C99 (no C++ or torch types in the boundary) and a C program that takes the address of every
+    declared entry point links against librrl.so."""
+    import re
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = os.path.join(root, "include", "rrl.h")
+    text = open(hdr).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    names = sorted(set(re.findall(r"\b(rrl_[a-z0-9_]+)\s*\(", text)))
+    assert len(names) > 40
+    src = tmp_path / "link_all.c"
+    src.write_text('#include "rrl.h"\n#include <stdio.h>\nint main(void) {\n    const void* f[] = {%s};\n'
+                   '    printf("%%d %%d\\n", (int)(sizeof(f) / sizeof(f[0])), rrl_version());\n    return 0;\n}\n'
+                   % ", ".join("(const void*)%s" % n for n in names))
+    lib_dir = os.path.join(root, "recovery-rl_b200")
+    exe = tmp_path / "link_all"
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic-errors", "-Wno-pedantic", "-I", os.path.join(root, "include"),
+                           str(src), "-o", str(exe), "-L", lib_dir, "-l:librrl.so", "-Wl,-rpath," + lib_dir])
+    out = subprocess.check_output([str(exe)], text=True).split()
+    assert int(out[0]) == len(names) and int(out[1]) == native.version()
