@@ -2,7 +2,7 @@
 
 Restates recovery_rl/experiment.py:261-296 (Q_risk pre-training on the constraint demos), :379-461
 (get_train_rollout: update gates, composite action, env step, reward penalty, mask-before-horizon,
-relabelled pushes, episode statistics) and :546-577 (get_action) on top of oracle/{agent,replay,envs}.py.
+relabelled pushes incl. the second push of --add_both_transitions, episode statistics) and :546-577 (get_action) on top of oracle/{agent,replay,envs}.py.
 It is the `cpu_baseline` / `--impl reference` arm of bench.py ("port": the reference itself is Python and
 cannot travel to the GPU box) and the checker for the whole-trajectory parity test.
 
@@ -66,7 +66,7 @@ class OracleExperiment(object):
                  gamma_safe=0.5, tau_safe=0.0002, eps_safe=0.1, use_recovery=True, mf_recovery=True, pos_fraction=-1.0,
                  constraint_reward_penalty=0.0, start_steps=100, noise=None, dgd=False, update_nu=False, rcpo=False,
                  nu=0.01, nu_schedule=False, nu_start=1e3, nu_end=0.0, num_eps=1000000, lambda_rcpo=0.01,
-                 constraint_sampling=False):
+                 constraint_sampling=False, add_both_transitions=False, q_sampling_recovery=False, q_samples=1000):
         self.env_name = env_name
         self.kind = envs.KIND_BY_NAME[env_name]
         self.B = batch_size
@@ -92,6 +92,9 @@ class OracleExperiment(object):
             self.nu_fn = lambda t: nu
         self.i_episode = 1
         self.constraint_sampling = bool(constraint_sampling)      # SQRL action filter (sac.py:139-161)
+        self.add_both = bool(add_both_transitions)                # experiment.py:446-448
+        self.q_sampling = bool(q_sampling_recovery) and not mf_recovery      # qrisk.py:207-225: MF_recovery is tested first
+        self.q_samples = int(q_samples)                           # qrisk.py:216, 220 hard-code 1000
         stream = SharedStream()
         self.memory = ReplayMemory(replay_size, seed, stream)
         self.recovery_memory = ConstraintReplayMemory(replay_size, seed, stream)
@@ -167,6 +170,10 @@ class OracleExperiment(object):
             at = torch.as_tensor(np.asarray(action)[None], dtype=torch.float32)
             q1, q2 = self.agent.qrisk(st, at)
             risky = bool(torch.max(q1, q2) > self.eps_safe)
+            if risky and self.q_sampling:
+                # qrisk.py:214-225: 1000 x ac_space.sample() (the env's own action space: the stream of the random start actions)
+                cands = np.array([self.noise.random_action(self.scale) for _ in range(self.q_samples)], np.float32)
+                return action, self.agent.select_action_qsample(np.asarray(self.state, np.float32), cands), True
             if risky:
                 e = self.noise.agent_eps(1)
                 real, _, _ = self.agent.recovery.sample(st, torch.as_tensor(e, dtype=torch.float32))
@@ -204,6 +211,8 @@ class OracleExperiment(object):
         self.memory.push(state, action, reward, next_state, mask)
         if self.uses_qrisk:
             self.recovery_memory.push(state, real_action, float(constraint), next_state, mask)
+            if recovery_used and self.add_both:                   # experiment.py:446-448
+                self.memory.push(state, real_action, reward, next_state, mask)
         self.state = next_state
         if done:
             if constraint:

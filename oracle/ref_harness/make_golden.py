@@ -625,6 +625,16 @@ def golden_qsample(seed=11, n_states=8):
           init_sha256=np.array(sha.hexdigest()))
 
 
+def golden_extra_trajectories():
+    # the two recovery branches no script line uses, with eps_safe low enough that the barely trained safety critic
+    # triggers recoveries in every episode: --add_both_transitions (experiment.py:446-448) and --Q_sampling_recovery
+    # (qrisk.py:214-225; the 1000 candidates per recovery step are part of `rand_actions`, the env's action-space stream)
+    golden_trajectory("navigation1", 8, "0.8", "0.05", 6, "traj_nav1_addboth.npz", stride=29,
+                      algo=("--use_recovery", "--MF_recovery", "--add_both_transitions"))
+    golden_trajectory("navigation1", 9, "0.8", "0.05", 6, "traj_nav1_qsample.npz", stride=29,
+                      algo=("--use_recovery", "--Q_sampling_recovery"))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     harness.setup()
@@ -652,6 +662,7 @@ def main():
                       algo=("--DGD_constraints", "--use_constraint_sampling", "--nu", "5000", "--update_nu", "--start_steps", "20"))
     golden_algos()
     golden_qsample()
+    golden_extra_trajectories()
 
 
 if __name__ == "__main__":

@@ -127,7 +127,11 @@ def test_maze_scalar_matches_vectorised():
     ("traj_nav1_rcpo.npz", "navigation1", 7, 0.8, 0.3, dict(use_recovery=False, mf_recovery=False, rcpo=True,
                                                           lambda_rcpo=1000.0)),
     ("traj_nav1_sqrl.npz", "navigation1", 5, 0.8, 0.45, dict(use_recovery=False, mf_recovery=False, dgd=True, update_nu=True,
-                                                           nu=5000.0, constraint_sampling=True, start_steps=20))])
+                                                           nu=5000.0, constraint_sampling=True, start_steps=20)),
+    # the two recovery branches no script line uses: --add_both_transitions (experiment.py:446-448), --Q_sampling_recovery
+    # (qrisk.py:214-225; its 1000 candidates per recovery step come out of the recorded action-space stream)
+    ("traj_nav1_addboth.npz", "navigation1", 8, 0.8, 0.05, dict(add_both_transitions=True)),
+    ("traj_nav1_qsample.npz", "navigation1", 9, 0.8, 0.05, dict(mf_recovery=False, q_sampling_recovery=True))])
 def test_oracle_loop_reproduces_reference_trajectory(golden_dir, fname, env_name, seed, gamma_safe, eps_safe, algo):
     """oracle/loop.py fed the recorded noise == the reference's Experiment (12 episodes seed 7 on Navigation1, 8 episodes
     seed 3 on Navigation2 with the scripts/navigation2.sh:7 settings, and the unconstrained / reward-penalty lines of
@@ -161,6 +165,10 @@ def test_oracle_loop_reproduces_reference_trajectory(golden_dir, fname, env_name
     assert np.array_equal(np.concatenate(exp.idx_log), z["idx"])
     assert exp.num_viols == int(z["num_viols"]) and exp.num_successes == int(z["num_successes"])
     assert exp.total_numsteps == int(z["total_numsteps"]) and exp.updates == int(z["updates"])
+    if algo.get("add_both_transitions"):
+        assert len(exp.memory) == exp.total_numsteps + int(z["recovery"].sum())     # one more task-buffer row per recovery step
+    if algo.get("q_sampling_recovery"):
+        assert not noise.rand_actions and int(z["recovery"].sum()) > 0              # every recorded candidate was consumed
     stride = int(z["stride"])
     for net in ("critic", "critic_target", "policy", "qrisk", "qrisk_target", "recovery"):
         if "final_%s_0" % net not in z.files:       # no recovery policy without --MF_recovery (qrisk.py:56-75)
