@@ -47,6 +47,16 @@ class NoiseSource(object):
             return e
         return torch.randn(rows, 2).numpy()
 
+    def det_noise(self):
+        """DeterministicPolicy.sample's draw (model.py:478-479): ONE N(0, 0.1) vector per call, clamped to +-0.25.  Recorded
+        draws are the raw vectors (the reference clamps out of place), live ones come from the torch global generator."""
+        if self.eps is not None:
+            e = np.asarray(self.eps.pop(0), np.float32).reshape(-1)
+            assert e.shape == (2,), e.shape
+            return np.clip(e, np.float32(-0.25), np.float32(0.25))
+        from .agent import deterministic_noise
+        return deterministic_noise().numpy()
+
     def randn2(self):
         if self.env_noise is not None:
             return self.env_noise.pop(0)
@@ -66,7 +76,8 @@ class OracleExperiment(object):
                  gamma_safe=0.5, tau_safe=0.0002, eps_safe=0.1, use_recovery=True, mf_recovery=True, pos_fraction=-1.0,
                  constraint_reward_penalty=0.0, start_steps=100, noise=None, dgd=False, update_nu=False, rcpo=False,
                  nu=0.01, nu_schedule=False, nu_start=1e3, nu_end=0.0, num_eps=1000000, lambda_rcpo=0.01,
-                 constraint_sampling=False, add_both_transitions=False, q_sampling_recovery=False, q_samples=1000):
+                 constraint_sampling=False, add_both_transitions=False, q_sampling_recovery=False, q_samples=1000,
+                 deterministic=False):
         self.env_name = env_name
         self.kind = envs.KIND_BY_NAME[env_name]
         self.B = batch_size
@@ -82,7 +93,7 @@ class OracleExperiment(object):
         self.scale = sc
         self.agent = Agent(action_scale=(sc, sc), gamma=gamma, alpha=alpha, tau=tau, gamma_safe=gamma_safe,
                            tau_safe=tau_safe, eps_safe=eps_safe, lr=lr, mf_recovery=mf_recovery, dgd=dgd,
-                           update_nu=update_nu, rcpo=rcpo, nu=nu, lambda_rcpo=lambda_rcpo)
+                           update_nu=update_nu, rcpo=rcpo, nu=nu, lambda_rcpo=lambda_rcpo, deterministic=deterministic)
         # the safety critic is trained for Recovery RL and for the LR / RSPO / SQRL / RCPO comparisons (experiment.py:357-361,443)
         self.uses_qrisk = bool(use_recovery or dgd or rcpo)
         # experiment.py:80-87 + utils.py:62-64: the multiplier handed to every SAC update
@@ -129,7 +140,7 @@ class OracleExperiment(object):
         idx = mem.sample_slots(batch_size, self.pos_fraction)
         self.idx_log.append(idx)
         batch = mem.gather(idx)
-        e_next = self.noise.agent_eps(batch_size)
+        e_next = self.noise.det_noise() if self.agent.deterministic else self.noise.agent_eps(batch_size)
         e_rec = self.noise.agent_eps(batch_size) if self.agent.mf_recovery else None
         return self.agent.qrisk_update(batch, e_next, e_rec)
 
@@ -161,7 +172,7 @@ class OracleExperiment(object):
             e = self.noise.agent_eps(100)
             action = self.agent.select_action_sqrl(np.asarray(self.state, np.float32), e, categorical=self.noise.categorical)
         else:
-            e = self.noise.agent_eps(1)
+            e = self.noise.det_noise()[None] if self.agent.deterministic else self.noise.agent_eps(1)
             action = self.agent.act(self.state[None], e, np.zeros((1, 2), np.float32), use_recovery=False)[0][0]
         if not self.use_recovery:
             return action, np.copy(action), False
@@ -188,8 +199,11 @@ class OracleExperiment(object):
             idx = self.memory.sample_slots(min(self.B, len(self.memory)))
             self.idx_log.append(idx)
             batch = self.memory.gather(idx)
-            e_next = self.noise.agent_eps(len(idx))
-            e_cur = self.noise.agent_eps(len(idx))
+            if self.agent.deterministic:                     # --policy Deterministic: one noise vector per sample() call
+                e_next, e_cur = self.noise.det_noise(), self.noise.det_noise()
+            else:
+                e_next = self.noise.agent_eps(len(idx))
+                e_cur = self.noise.agent_eps(len(idx))
             self.last_losses = self.agent.sac_update(batch, e_next, e_cur, self.updates, nu=self.nu_fn(self.i_episode))
             if len(self.recovery_memory) > self.B and \
                     (self.num_viols + self.num_constraint_violations) / self.B > self.gate_pos_fraction:

@@ -388,6 +388,17 @@ def golden_trajectory(env_name="navigation1", seed=7, gamma_safe="0.8", eps_safe
 
         exp.env.action_space.sample = rec_as
         del harness.eps_log[:]
+        if "Deterministic" in algo:
+            # DeterministicPolicy.sample draws with self.noise.normal_ (model.py:478), not through Normal.rsample: record
+            # the raw vector it leaves in self.noise after every call, in call order with the other draws
+            pol = exp.agent.policy
+            orig_ps = pol.sample
+
+            def rec_ps(state):
+                res = orig_ps(state)
+                harness.eps_log.append(pol.noise.detach().cpu().numpy().reshape(1, 2).copy())
+                return res
+            pol.sample = rec_ps
         np.random.randn = rec_randn
         cfg = exp.exp_cfg
         if cfg.use_recovery or cfg.DGD_constraints or cfg.RCPO:     # experiment.py:357-361
@@ -633,6 +644,10 @@ def golden_extra_trajectories():
                       algo=("--use_recovery", "--MF_recovery", "--add_both_transitions"))
     golden_trajectory("navigation1", 9, "0.8", "0.05", 6, "traj_nav1_qsample.npz", stride=29,
                       algo=("--use_recovery", "--Q_sampling_recovery"))
+    # --policy Deterministic (model.py:447-485; alpha = 0, sac.py:115-117) under Recovery RL MF, start_steps 20 so that the
+    # policy itself acts for most of the run
+    golden_trajectory("navigation1", 10, "0.8", "0.3", 6, "traj_nav1_det.npz", stride=29,
+                      algo=("--policy", "Deterministic", "--use_recovery", "--MF_recovery", "--start_steps", "20"))
 
 
 def main():

@@ -131,7 +131,9 @@ def test_maze_scalar_matches_vectorised():
     # the two recovery branches no script line uses: --add_both_transitions (experiment.py:446-448), --Q_sampling_recovery
     # (qrisk.py:214-225; its 1000 candidates per recovery step come out of the recorded action-space stream)
     ("traj_nav1_addboth.npz", "navigation1", 8, 0.8, 0.05, dict(add_both_transitions=True)),
-    ("traj_nav1_qsample.npz", "navigation1", 9, 0.8, 0.05, dict(mf_recovery=False, q_sampling_recovery=True))])
+    ("traj_nav1_qsample.npz", "navigation1", 9, 0.8, 0.05, dict(mf_recovery=False, q_sampling_recovery=True)),
+    # --policy Deterministic (model.py:447-485, alpha = 0): its self.noise.normal_ draws are recorded raw, in call order
+    ("traj_nav1_det.npz", "navigation1", 10, 0.8, 0.3, dict(deterministic=True, start_steps=20))])
 def test_oracle_loop_reproduces_reference_trajectory(golden_dir, fname, env_name, seed, gamma_safe, eps_safe, algo):
     """oracle/loop.py fed the recorded noise == the reference's Experiment (12 episodes seed 7 on Navigation1, 8 episodes
     seed 3 on Navigation2 with the scripts/navigation2.sh:7 settings, and the unconstrained / reward-penalty lines of
