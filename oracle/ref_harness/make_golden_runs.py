@@ -29,6 +29,8 @@ RUNS = {   # tag -> (seed, the algorithm flags of the script line)
 EXTRA_RUNS = {
     "addboth": (8, ["--use_recovery", "--MF_recovery", "--gamma_safe", "0.8", "--eps_safe", "0.05", "--add_both_transitions"]),
     "qsample": (9, ["--use_recovery", "--Q_sampling_recovery", "--gamma_safe", "0.8", "--eps_safe", "0.05"]),
+    "det": (10, ["--policy", "Deterministic", "--use_recovery", "--MF_recovery", "--gamma_safe", "0.8", "--eps_safe", "0.3",
+                 "--start_steps", "20"]),
 }
 STRIDE = 37
 

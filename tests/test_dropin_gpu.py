@@ -216,15 +216,15 @@ def test_vectorised_comparison_algorithms_run(native, cuda, tmp_path, algo):
     assert torch.isfinite(exp.engine.arena[:exp.engine.agent.grad_off]).all()
 
 
-@pytest.mark.parametrize("tag", ["unconstrained", "lr", "rspo", "sqrl", "rp", "rcpo", "addboth", "qsample"])
+@pytest.mark.parametrize("tag", ["unconstrained", "lr", "rspo", "sqrl", "rp", "rcpo", "addboth", "qsample", "det"])
 def test_experiment_reproduces_reference_comparison_runs(native, cuda, golden_dir, tmp_path, tag):
     """the comparison-algorithm lines of scripts/navigation1.sh through the drop-in Experiment with LIVE RNGs == the
-    reference's own (shortened) runs recorded by oracle/ref_harness/make_golden_runs.py; `addboth` / `qsample`: the two
-    recovery branches no script line uses (--add_both_transitions, experiment.py:446-448; --Q_sampling_recovery,
-    qrisk.py:214-225), recorded the same way into runs_nav1_extra.npz."""
+    reference's own (shortened) runs recorded by oracle/ref_harness/make_golden_runs.py; `addboth` / `qsample` / `det`: the
+    branches no script line uses (--add_both_transitions, experiment.py:446-448; --Q_sampling_recovery, qrisk.py:214-225;
+    --policy Deterministic, model.py:447-485), recorded the same way into runs_nav1_extra.npz."""
     import arg_utils
     from recovery_rl.experiment import Experiment
-    z = np.load(os.path.join(golden_dir, "runs_nav1_extra.npz" if tag in ("addboth", "qsample") else "runs_nav1.npz"))
+    z = np.load(os.path.join(golden_dir, "runs_nav1_extra.npz" if tag in ("addboth", "qsample", "det") else "runs_nav1.npz"))
     P = tag + "_"
     argv = [str(x) for x in z[P + "argv"]]
     argv[argv.index("--logdir") + 1] = str(tmp_path)
